@@ -1,0 +1,274 @@
+"""`DeterministicVI` surface of the reference, backed by the CUDA library.
+
+Mirrors, for the hot path only:
+  src/DeterministicVI.jl:39-105           generic_init_source, catalog_init_source, init_sources
+  src/deterministic_vi/elbo_args.jl:165-211   ElboArgs
+  src/SensitiveFloats.jl:23-47            SensitiveFloat (result container)
+  src/deterministic_vi/elbo_objective.jl:400-492  elbo_likelihood / elbo
+`elbo_likelihood(ea, vp)` has the reference's meaning and error behaviour (raises on a
+non-finite result like assert_all_finite, elbo_args.jl:145); the arithmetic runs in
+libceleste_cuda.so on the current CUDA device.  `DeviceField` is the batched entry the
+reference lacks (many (ElboArgs, vp) per launch; SURVEY.md 8b "Threading").
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import weakref
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from .flatten import FlatImages, FlatPatches, csr_tasks, out_sizes
+from .model import (CatalogEntry, Image, ImagePatch, NUM_PARAMS, ids)
+
+VariationalParams = List[np.ndarray]   # Vector{Vector{Float64}}: one 44-vector per source
+
+
+# ------------------------------------------------------------------ DeterministicVI.jl
+def generic_init_source(init_pos) -> np.ndarray:
+    """DeterministicVI.jl:39-53."""
+    ret = np.empty(NUM_PARAMS)
+    ret[ids.is_star] = 0.5
+    ret[ids.pos] = init_pos
+    ret[ids.flux_loc] = math.log(2.0)
+    ret[ids.flux_scale] = 1e-3
+    ret[ids.gal_frac_dev] = 0.5
+    ret[ids.gal_axis_ratio] = 0.5
+    ret[ids.gal_angle] = 0.0
+    ret[ids.gal_radius_px] = 1.0
+    ret[ids.k] = 1.0 / ids.k.shape[0]
+    ret[ids.color_mean] = 0.0
+    ret[ids.color_var] = 1e-2
+    return ret
+
+
+def catalog_init_source(ce: CatalogEntry, max_gal_radius_px=float("inf")) -> np.ndarray:
+    """DeterministicVI.jl:59-91."""
+    ret = generic_init_source(ce.pos)
+    ret[ids.is_star[0]] = 0.8 if ce.is_star else 0.2
+    ret[ids.is_star[1]] = 0.2 if ce.is_star else 0.8
+    ret[ids.flux_loc[0]] = math.log(max(0.1, ce.star_fluxes[2]))
+    ret[ids.flux_loc[1]] = math.log(max(0.1, ce.gal_fluxes[2]))
+
+    def get_color(c_var, c_mean):
+        if c_var > 0 and c_mean > 0:
+            return min(max(math.log(c_var / c_mean), -9.0), 9.0)
+        if c_var > 0 and c_mean <= 0:
+            return 3.0
+        if c_var <= 0 and c_mean > 0:
+            return -3.0
+        return 0.0
+
+    def get_colors(raw):
+        return [get_color(raw[c + 1], raw[c]) for c in range(4)]
+
+    ret[ids.color_mean[:, 0]] = get_colors(ce.star_fluxes)
+    ret[ids.color_mean[:, 1]] = get_colors(ce.gal_fluxes)
+    ret[ids.gal_frac_dev] = min(max(ce.gal_frac_dev, 0.015), 0.985)
+    ret[ids.gal_axis_ratio] = 0.8 if ce.is_star else min(max(ce.gal_axis_ratio, 0.015), 0.985)
+    ret[ids.gal_angle] = ce.gal_angle
+    ret[ids.gal_radius_px] = 0.2 if ce.is_star else min(max_gal_radius_px, max(ce.gal_radius_px, 0.2))
+    return ret
+
+
+def init_sources(target_sources: Sequence[int], catalog: Sequence[CatalogEntry]) -> VariationalParams:
+    """DeterministicVI.jl:94-103 (target_sources 0-based here)."""
+    ret = [catalog_init_source(ce) for ce in catalog]
+    for s in target_sources:
+        ret[s][:] = generic_init_source(catalog[s].pos)
+    return ret
+
+
+# ------------------------------------------------------------------ SensitiveFloats.jl
+class SensitiveFloat:
+    """SensitiveFloats.jl:23-47: value, d (local_P x local_S), h ((P S) x (P S), p fastest)."""
+
+    def __init__(self, local_P: int, local_S: int, has_gradient=True, has_hessian=True):
+        assert has_gradient or not has_hessian
+        self.local_P, self.local_S = local_P, local_S
+        self.has_gradient, self.has_hessian = has_gradient, has_hessian
+        self.v = 0.0
+        self.d = np.zeros((local_P * has_gradient, local_S * has_gradient), order="F")
+        hd = local_P * local_S * has_hessian
+        self.h = np.zeros((hd, hd), order="F")
+
+    @property
+    def mode(self) -> int:
+        return _lib.MODE_HESS if self.has_hessian else (_lib.MODE_GRAD if self.has_gradient else _lib.MODE_VALUE)
+
+
+class ElboIntermediateVariables:
+    """elbo_args.jl:29-113: only the parts a caller observes -- the result `elbo` (whose
+    has_gradient/has_hessian flags select the mode, elbo_objective.jl:69,95) and the two
+    pixel-visit counters (elbo_args.jl:62-63).  The scratch itself lives on the device."""
+
+    def __init__(self, num_active_sources: int, calculate_gradient=True, calculate_hessian=True):
+        self.elbo = SensitiveFloat(NUM_PARAMS, num_active_sources, calculate_gradient,
+                                   calculate_gradient and calculate_hessian)
+        self.active_pixel_counter = 0
+        self.inactive_pixel_counter = 0
+
+
+# ------------------------------------------------------------------ device-resident box
+class DeviceField:
+    """Images + patch matrix of one inference box, resident in HBM (celeste_field)."""
+
+    def __init__(self, images: Sequence[Image], patches: np.ndarray, device: int = -1):
+        lib = _lib.load()
+        ndev = C.c_int(0)
+        _lib.check(lib.celeste_init(device, C.byref(ndev)))
+        self.images = list(images)
+        self.patches = patches
+        self._flat_images = FlatImages(self.images)
+        self._handle = C.c_void_p()
+        _lib.check(lib.celeste_field_create(C.byref(self._handle), self._flat_images.N, self._flat_images.arr))
+        self._finalizer = weakref.finalize(self, lib.celeste_field_destroy, self._handle)
+        self._row = {}
+        self.set_patches(patches)
+
+    def set_patches(self, patches: np.ndarray):
+        lib = _lib.load()
+        fp = FlatPatches(patches)
+        _lib.check(lib.celeste_patches_set(self._handle, fp.S_tot, fp.N, fp.arr))
+        self.patches = patches
+        self._row = {id(patches[s, 0]): s for s in range(patches.shape[0])} if patches.shape[1] else {}
+
+    def row_of(self, patch: ImagePatch) -> Optional[int]:
+        return self._row.get(id(patch))
+
+    def elbo_batch(self, tasks, mode: int = _lib.MODE_HESS, check_finite: bool = True):
+        """tasks: list of (rows_1based, active_local_1based, vp 44 x S).  Returns dict of arrays."""
+        lib = _lib.load()
+        task_ptr, src, active_ptr, act, vp = csr_tasks(tasks)
+        n = len(tasks)
+        nd, nh = out_sizes(active_ptr)
+        v = np.zeros(n)
+        d = np.zeros(nd if mode >= 1 else 0)
+        h = np.zeros(nh if mode >= 2 else 0)
+        counters = np.zeros(2 * n, dtype=np.int64)
+        flags = np.zeros(n, dtype=np.int32)
+
+        def p(a):
+            return a.ctypes.data if a.size else None
+        st = lib.celeste_elbo_batch(self._handle, n, p(task_ptr), p(src), p(active_ptr), p(act), p(vp), mode,
+                                    p(v), p(d), p(h), p(counters), p(flags))
+        _lib.check(st, allow_nonfinite=not check_finite)
+        return {"v": v, "d": d, "h": h, "counters": counters.reshape(n, 2), "flags": flags,
+                "active_ptr": active_ptr}
+
+    def make_plan(self, tasks_rows, tasks_active):
+        return Plan(self, tasks_rows, tasks_active)
+
+
+class Plan:
+    """A registered task list (celeste_plan): evaluate it repeatedly with new vp."""
+
+    def __init__(self, field: DeviceField, tasks_rows, tasks_active):
+        lib = _lib.load()
+        self.field = field
+        dummy = [(r, a, np.zeros((44, len(r)))) for r, a in zip(tasks_rows, tasks_active)]
+        self.task_ptr, self.src, self.active_ptr, self.act, _ = csr_tasks(dummy)
+        self.n_tasks = len(dummy)
+        self.n_src = int(self.task_ptr[-1])
+        self.nd, self.nh = out_sizes(self.active_ptr)
+        self._handle = C.c_void_p()
+        _lib.check(lib.celeste_plan_create(field._handle, C.byref(self._handle), self.n_tasks,
+                                           self.task_ptr.ctypes.data, self.src.ctypes.data,
+                                           self.active_ptr.ctypes.data, self.act.ctypes.data))
+        self._finalizer = weakref.finalize(self, lib.celeste_plan_destroy, self._handle)
+
+    def launches(self, mode: int) -> int:
+        return int(_lib.load().celeste_plan_launches(self._handle, mode))
+
+    def run_host(self, vp_flat: np.ndarray, mode: int, out=None, check_finite=True):
+        lib = _lib.load()
+        n = self.n_tasks
+        if out is None:
+            out = {"v": np.zeros(n), "d": np.zeros(self.nd if mode >= 1 else 0),
+                   "h": np.zeros(self.nh if mode >= 2 else 0),
+                   "counters": np.zeros(2 * n, dtype=np.int64), "flags": np.zeros(n, dtype=np.int32)}
+
+        def p(a):
+            return a.ctypes.data if a.size else None
+        st = lib.celeste_elbo_plan_host(self._handle, p(vp_flat), mode, p(out["v"]), p(out["d"]), p(out["h"]),
+                                        p(out["counters"]), p(out["flags"]))
+        _lib.check(st, allow_nonfinite=not check_finite)
+        return out
+
+    def run_device(self, vp_dev_ptr: int, mode: int, v_ptr: int, d_ptr: int, h_ptr: int,
+                   counters_ptr: int, flags_ptr: int, stream: int = 0):
+        st = _lib.load().celeste_elbo_plan_device(self._handle, vp_dev_ptr, mode, v_ptr, d_ptr or None, h_ptr or None,
+                                                  counters_ptr, flags_ptr, stream or None)
+        _lib.check(st)
+
+
+# ------------------------------------------------------------------ elbo_args.jl:165-211
+class ElboArgs:
+    """elbo_args.jl:165-211.  `patches` is the S x N object matrix of ImagePatch;
+    `active_sources` are 1-based local indices exactly as in the reference."""
+
+    def __init__(self, images: Sequence[Image], patches: np.ndarray, active_sources: Sequence[int],
+                 psf_K: int = 2, include_kl: bool = True, field: Optional[DeviceField] = None):
+        self.S = patches.shape[0]
+        self.Sa = len(active_sources)
+        self.N = len(images)
+        assert patches.shape[1] == self.N
+        assert psf_K > 0
+        self.psf_K = psf_K
+        self.images = list(images)
+        self.patches = patches
+        self.active_sources = list(active_sources)
+        self.include_kl = include_kl
+        self._field = field
+        self._rows = None
+
+    def device_rows(self):
+        """(DeviceField, 1-based rows of ea.patches inside it); uploads on first use."""
+        if self._field is not None and self._rows is None:
+            rows = [self._field.row_of(self.patches[s, 0]) if self.N else None for s in range(self.S)]
+            if any(r is None for r in rows):
+                self._field = None
+            else:
+                self._rows = [r + 1 for r in rows]
+        if self._field is None:
+            self._field = DeviceField(self.images, self.patches)
+            self._rows = list(range(1, self.S + 1))
+        return self._field, self._rows
+
+
+def _vp_matrix(vp: VariationalParams) -> np.ndarray:
+    return np.stack([np.asarray(v, dtype=np.float64) for v in vp], axis=1)
+
+
+def elbo_likelihood(ea: ElboArgs, vp: VariationalParams,
+                    elbo_vars: Optional[ElboIntermediateVariables] = None) -> SensitiveFloat:
+    """elbo_objective.jl:400-474 on the GPU.  Returns elbo_vars.elbo filled in place."""
+    if elbo_vars is None:
+        elbo_vars = ElboIntermediateVariables(ea.Sa)
+    fieldobj, rows = ea.device_rows()
+    res = elbo_vars.elbo
+    out = fieldobj.elbo_batch([(rows, ea.active_sources, _vp_matrix(vp))], mode=res.mode)
+    res.v = float(out["v"][0])
+    if res.has_gradient:
+        res.d[:, :] = out["d"].reshape((NUM_PARAMS, ea.Sa), order="F")
+    if res.has_hessian:
+        res.h[:, :] = out["h"].reshape((NUM_PARAMS * ea.Sa, NUM_PARAMS * ea.Sa), order="F")
+    elbo_vars.active_pixel_counter += int(out["counters"][0, 0])
+    elbo_vars.inactive_pixel_counter += int(out["counters"][0, 1])
+    return res
+
+
+def elbo(ea: ElboArgs, vp: VariationalParams,
+         elbo_vars: Optional[ElboIntermediateVariables] = None) -> SensitiveFloat:
+    """elbo_objective.jl:482-492.  The KL term (elbo_kl.jl) is pixel-free host work that
+    stays with the caller; requesting it here is an error
+    rather than a silent omission."""
+    for vs in vp:
+        if not np.all(np.isfinite(vs)):
+            raise AssertionError("vp contains NaNs or Infs")     # elbo_objective.jl:487
+    if ea.include_kl:
+        raise NotImplementedError("include_kl=true: subtract_kl_all_sources! (elbo_kl.jl:214) stays on the "
+                                  "host side of the boundary; construct ElboArgs(..., include_kl=False)")
+    return elbo_likelihood(ea, vp, elbo_vars)

@@ -1,0 +1,225 @@
+/*
+ * celeste_cuda.h -- C ABI of the B200-native (sm_100a) ELBO hot path of Celeste.jl.
+ *
+ * Drop-in boundary: this library replaces exactly one
+ * reference method,
+ *
+ *   DeterministicVI.elbo_likelihood(ea::ElboArgs, vp::VariationalParams{Float64},
+ *                                   elbo_vars, bvn_bundle)
+ *       src/deterministic_vi/elbo_objective.jl:400-474
+ *
+ * (and its direct callee tree: load_source_brightnesses source_brightness.jl:213,
+ * load_bvn_mixtures! fsm_util.jl:111, add_pixel_term! elbo_objective.jl:330,
+ * star_light_density! fsm_util.jl:225, populate_gal_fsm! fsm_util.jl:194,
+ * calculate_G_s! elbo_objective.jl:17, add_elbo_log_term! elbo_objective.jl:274,
+ * and the SensitiveFloats algebra SensitiveFloats.jl:83-250).
+ *
+ * Conventions (they mirror the reference's own FFI, src/SEP.jl:39-46,137-150):
+ *   - every entry point returns an int status, 0 == CELESTE_OK; a message for a
+ *     status is obtained with celeste_get_errmsg (cf. sep_get_errmsg);
+ *   - opaque handles are created/destroyed by the library; every data buffer is
+ *     caller-owned and only has to stay alive for the duration of the call;
+ *   - all matrices are column-major (Julia layout), "h fastest";
+ *   - integer indices that name sources are 1-based, exactly the values the
+ *     Julia side holds (ea.active_sources, rows of ea.patches);
+ *   - no exception / longjmp ever crosses this boundary;
+ *   - the library never silently falls back to a CPU path: without a usable
+ *     CUDA device every compute entry point returns CELESTE_ERR_NO_DEVICE.
+ *
+ * Only T == Float64 is redirected here; ForwardDiff.Dual calls stay in Julia
+ * (test/test_elbo.jl:232).
+ */
+#ifndef CELESTE_CUDA_H
+#define CELESTE_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- layout constants of the reference parameterisation ------------------ */
+/* length(CanonicalParams), src/model/param_set.jl:107 */
+#define CELESTE_NUM_PARAMS 44
+/* NUM_BANDS (u g r i z) */
+#define CELESTE_NUM_BANDS 5
+/* 1-based canonical ids, src/model/param_set.jl:88-100 */
+#define CELESTE_ID_POS 1           /* 1:2   */
+#define CELESTE_ID_GAL_FRAC_DEV 3
+#define CELESTE_ID_GAL_AXIS_RATIO 4
+#define CELESTE_ID_GAL_ANGLE 5
+#define CELESTE_ID_GAL_RADIUS_PX 6
+#define CELESTE_ID_FLUX_LOC 7      /* 7:8   (star, galaxy) */
+#define CELESTE_ID_FLUX_SCALE 9    /* 9:10  */
+#define CELESTE_ID_COLOR_MEAN 11   /* 11:18 (4 x 2 col-major) */
+#define CELESTE_ID_COLOR_VAR 19    /* 19:26 */
+#define CELESTE_ID_IS_STAR 27      /* 27:28 */
+#define CELESTE_ID_K 29            /* 29:44 (never receives likelihood derivatives) */
+
+/* ---- status codes --------------------------------------------------------- */
+#define CELESTE_OK 0
+#define CELESTE_ERR_NO_DEVICE 1     /* no CUDA device / driver; nothing was computed */
+#define CELESTE_ERR_BAD_ARG 2
+#define CELESTE_ERR_ALLOC 3
+#define CELESTE_ERR_CUDA 4          /* a CUDA runtime call failed; see errmsg detail */
+#define CELESTE_ERR_UNSUPPORTED 5   /* e.g. Sa > 1 in this build: caller keeps the Julia path */
+#define CELESTE_ERR_NONFINITE 6     /* assert_all_finite (elbo_args.jl:145) would have thrown */
+#define CELESTE_ERR_STATE 7
+
+/* evaluation mode == (elbo.has_gradient, elbo.has_hessian), elbo_objective.jl:69,95 */
+#define CELESTE_MODE_VALUE 0
+#define CELESTE_MODE_GRAD 1
+#define CELESTE_MODE_HESS 2
+
+/* per-task flag bits written to `flags` */
+#define CELESTE_FLAG_NONFINITE 1
+
+/*
+ * One Model.Image (src/model/image_model.jl:6-38), flattened.
+ * `sky` is the DENSE matrix img.sky[h, w] materialised by the host (for SDSS the
+ * Float32 bilinear rule of src/SDSSIO.jl:70-98 must be evaluated by the caller
+ * so that no Float32 rounding can differ).  `log_iota[h]` must be
+ * Float64(log(nelec_per_nmgy[h]::Float32)) -- the reference evaluates that log
+ * in Float32 (elbo_objective.jl:292); NULL lets the library do (double)logf().
+ */
+typedef struct celeste_image {
+    int32_t H, W;                  /* image_model.jl:7-8 */
+    int32_t band;                  /* img.b, 1..5 */
+    const float*  pixels;          /* H x W, electrons, NaN == masked */
+    const float*  sky;             /* H x W, nmgy */
+    const float*  nelec_per_nmgy;  /* H (varies by row) */
+    const double* log_iota;        /* H or NULL */
+} celeste_image;
+
+/*
+ * One Model.ImagePatch (src/model/imaged_sources.jl:60-71), flattened.
+ * psf      : K x 7 doubles per component k: alphaBar, xiBar[1:2], tauBar[1,1],
+ *            tauBar[2,1], tauBar[1,2], tauBar[2,2]   (psf_model.jl:17-29)
+ * itp_coefs: the prefiltered cubic B-spline coefficient array of patch.itp_psf
+ *            (Interpolations.jl `itp.coefs`, padded by one on each side:
+ *            (n1+2) x (n2+2), 53 x 53 for the 51 x 51 stamp), column-major.
+ *            Patches that share one array may pass the same pointer; the
+ *            library de-duplicates by (pointer, dims).
+ */
+typedef struct celeste_patch {
+    int64_t bitmap_offset[2];            /* imaged_sources.jl:69 (box corner - 1) */
+    int32_t H2, W2;                      /* size(active_pixel_bitmap) */
+    const uint8_t* active_pixel_bitmap;  /* H2 x W2, 0/1 */
+    double wcs_jacobian[4];              /* 2 x 2 col-major */
+    double world_center[2];
+    double pixel_center[2];
+    int32_t K;                           /* psf components (ea.psf_K) */
+    const double* psf;                   /* K x 7 */
+    const double* itp_coefs;
+    int32_t itp_dims[2];                 /* padded dims, e.g. {53, 53} */
+} celeste_patch;
+
+typedef struct celeste_field celeste_field;
+
+/* Like sep_get_errmsg (src/SEP.jl:41): short message for a status code. buf >= 61 bytes. */
+void celeste_get_errmsg(int status, char* buf);
+/* Longer, thread-local detail of the most recent failure on the calling thread. buf >= 512. */
+void celeste_get_errdetail(char* buf);
+
+/* Library/ABI version: major*10000 + minor*100 + patch. */
+int celeste_version(void);
+
+/*
+ * Select / probe the CUDA device this process evaluates on (one process per GPU:
+ * ParallelRun shards sources across processes).  device < 0 keeps the
+ * current device.  n_devices_out (may be NULL) receives cudaGetDeviceCount.
+ */
+int celeste_init(int device, int* n_devices_out);
+
+/*
+ * Upload the images of one inference box (ea.images, elbo_args.jl:178) once.
+ * Pixel planes stay resident in HBM until celeste_field_destroy.
+ */
+int celeste_field_create(celeste_field** out, int32_t N, const celeste_image* imgs);
+
+/*
+ * Upload the S_tot x N patch matrix (`patches` of ParallelRun._infer_box,
+ * ParallelRun.jl:610-637; column-major: patch of source s (1-based) in image n
+ * is p[(s-1) + (n-1)*S_tot]).  May be called again to replace the patch set.
+ */
+int celeste_patches_set(celeste_field* f, int32_t S_tot, int32_t N, const celeste_patch* p);
+
+/*
+ * Evaluate elbo_likelihood for a batch of independent (ElboArgs, vp) tasks.
+ *
+ * Task t (0-based) owns the local sources  source_ids[task_ptr[t] .. task_ptr[t+1])
+ * -- 1-based rows of the patch matrix, in the order of ea.patches' rows
+ * (ParallelRun.jl:242,485: target first, then its neighbours) -- and the
+ * variational parameters vp[44 * task_ptr[t] ...] (44 x S_t column-major, i.e.
+ * vp[s] of the reference concatenated; re-read on every call, never cached,
+ * SURVEY appendix B.10).  active_idx[active_ptr[t] .. active_ptr[t+1]) are
+ * ea.active_sources (1-based LOCAL indices, 1..S_t).
+ *
+ * Outputs (caller-allocated, host memory), with Sa_t = active_ptr[t+1]-active_ptr[t]
+ * and P = 44*Sa_t:
+ *   v[t]                               elbo.v[]
+ *   d[44*active_ptr[t] ...]            elbo.d, 44 x Sa_t col-major      (mode >= 1)
+ *   h[h_ptr(t) ...]                    elbo.h, P x P col-major, symmetric (mode == 2),
+ *                                      h_ptr(t) = sum_{u<t} (44*Sa_u)^2
+ *   counters[2*t + {0,1}]              active / inactive pixel-visit counters
+ *                                      (elbo_objective.jl:353-357)
+ *   flags[t]                           CELESTE_FLAG_* bits
+ * d / h may be NULL when the mode does not produce them.
+ *
+ * Returns CELESTE_ERR_NONFINITE if any task produced a non-finite value (all
+ * outputs are still written; inspect flags[]), CELESTE_ERR_UNSUPPORTED if a task
+ * has Sa_t != 1 (this build keeps those on the reference path).
+ */
+int celeste_elbo_batch(celeste_field* f, int32_t n_tasks,
+                       const int32_t* task_ptr, const int32_t* source_ids,
+                       const int32_t* active_ptr, const int32_t* active_idx,
+                       const double* vp, int32_t mode,
+                       double* v, double* d, double* h,
+                       int64_t* counters, int32_t* flags);
+
+/*
+ * Single-task, thread-safe convenience with the shape of the reference call
+ * (one ElboArgs): used by the elbo_likelihood method override.
+ */
+int celeste_elbo_single(celeste_field* f, int32_t S, const int32_t* source_ids,
+                        int32_t Sa, const int32_t* active_idx,
+                        const double* vp, int32_t mode,
+                        double* v, double* d, double* h,
+                        int64_t* counters, int32_t* flags);
+
+/*
+ * Device-resident variant: every pointer argument is a DEVICE pointer on the
+ * current device, work is enqueued on `cuda_stream` (a cudaStream_t, NULL == the
+ * legacy default stream) and the call returns without synchronising.  The task
+ * plan (task_ptr/source_ids/active_*) must have been registered with
+ * celeste_plan_create.  Used to time the kernels with inputs resident in HBM.
+ */
+typedef struct celeste_plan celeste_plan;
+int celeste_plan_create(celeste_field* f, celeste_plan** out, int32_t n_tasks,
+                        const int32_t* task_ptr, const int32_t* source_ids,
+                        const int32_t* active_ptr, const int32_t* active_idx);
+void celeste_plan_destroy(celeste_plan* p);
+/* number of kernel launches one celeste_elbo_plan_device call enqueues */
+int celeste_plan_launches(const celeste_plan* p, int32_t mode);
+int celeste_elbo_plan_device(celeste_plan* p, const double* vp_dev, int32_t mode,
+                             double* v_dev, double* d_dev, double* h_dev,
+                             int64_t* counters_dev, int32_t* flags_dev,
+                             void* cuda_stream);
+/* Same plan, HOST buffers, pinned staging + H2D/D2H inside the call (synchronous). */
+int celeste_elbo_plan_host(celeste_plan* p, const double* vp, int32_t mode,
+                           double* v, double* d, double* h,
+                           int64_t* counters, int32_t* flags);
+
+void celeste_field_destroy(celeste_field* f);
+
+/*
+ * Measured FP64 FMA peak of the current device (a register-resident DFMA chain,
+ * 2 flop per FMA), in TFLOP/s: the denominator of the roofline of this
+ * FP64-pipe-bound path.  Runs on `cuda_stream`, synchronises.
+ */
+int celeste_fp64_peak(double* tflops_out, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CELESTE_CUDA_H */
