@@ -1,0 +1,562 @@
+// celeste_abi.cu -- C ABI (include/celeste_cuda.h) over the sm_100a kernels.
+// Host-side plumbing only: handles, uploads, the task plan, kernel launches, status codes.
+// No CPU implementation of the path exists in this library: without a CUDA device every
+// compute entry point returns CELESTE_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <memory>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <new>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/celeste_cuda.h"
+#include "celeste_kernels.cuh"
+
+using namespace celeste;
+
+namespace {
+
+thread_local char g_detail[512] = "";
+
+void set_detail(const char* fmt, ...) __attribute__((format(printf, 1, 2)));
+void set_detail(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_detail, sizeof g_detail, fmt, ap);
+    va_end(ap);
+}
+
+#define CUDA_TRY(expr)                                                                             \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            set_detail("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));       \
+            return (_e == cudaErrorMemoryAllocation) ? CELESTE_ERR_ALLOC                           \
+                   : (_e == cudaErrorNoDevice || _e == cudaErrorInsufficientDriver ||              \
+                      _e == cudaErrorInitializationError)                                          \
+                       ? CELESTE_ERR_NO_DEVICE                                                     \
+                       : CELESTE_ERR_CUDA;                                                         \
+        }                                                                                          \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    cudaError_t alloc(size_t count) {
+        release();
+        n = count;
+        if (count == 0) return cudaSuccess;
+        return cudaMalloc((void**)&p, count * sizeof(T));
+    }
+    cudaError_t upload(const std::vector<T>& h) {
+        cudaError_t e = alloc(h.size());
+        if (e != cudaSuccess || h.empty()) return e;
+        return cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+    }
+    cudaError_t ensure(size_t count) { return count <= n ? cudaSuccess : alloc(count); }
+};
+
+// light_source_model.jl:45-72
+void galaxy_prototypes(double eta[NPROTO], double nu[NPROTO]) {
+    const double dev_amp[8] = {4.26347652e-2, 2.40127183e-1, 6.85907632e-1, 1.51937350,
+                               2.83627243,    4.46467501,    5.72440830,    5.60989349};
+    const double dev_var[8] = {2.23759216e-4, 1.00220099e-3, 4.18731126e-3, 1.69432589e-2,
+                               6.84850479e-2, 2.87207080e-1, 1.33320254,    8.40215071};
+    const double exp_amp[6] = {2.34853813e-3, 3.07995260e-2, 2.23364214e-1, 1.17949102, 4.33873750, 5.99820770};
+    const double exp_var[6] = {1.20078965e-3, 8.84526493e-3, 3.91463084e-2,
+                               1.39976817e-1, 4.60962500e-1, 1.50159566};
+    double sd = 0, se = 0;
+    for (double a : dev_amp) sd += a;
+    for (double a : exp_amp) se += a;
+    const double er0 = 1.078031, er1 = 0.928896;
+    for (int j = 0; j < 8; ++j) {
+        eta[j] = dev_amp[j] / sd;
+        nu[j] = dev_var[j] / (er0 * er0);
+    }
+    for (int j = 0; j < 6; ++j) {
+        eta[8 + j] = exp_amp[j] / se;
+        nu[8 + j] = exp_var[j] / (er1 * er1);
+    }
+}
+
+int upload_constants() {
+    double eta[NPROTO], nu[NPROTO];
+    galaxy_prototypes(eta, nu);
+    CUDA_TRY(cudaMemcpyToSymbol(c_proto_eta, eta, sizeof eta));
+    CUDA_TRY(cudaMemcpyToSymbol(c_proto_nu, nu, sizeof nu));
+    return CELESTE_OK;
+}
+
+template <int MODE>
+size_t pixel_smem_bytes() {
+    return ((size_t)NAcc<MODE>::value * PIX_THREADS + (size_t)MAX_COMPS * COMP_STRIDE) * sizeof(double);
+}
+
+int configure_kernels() {
+    CUDA_TRY(cudaFuncSetAttribute(pixel_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pixel_smem_bytes<0>()));
+    CUDA_TRY(cudaFuncSetAttribute(pixel_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pixel_smem_bytes<1>()));
+    CUDA_TRY(cudaFuncSetAttribute(pixel_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pixel_smem_bytes<2>()));
+    return CELESTE_OK;
+}
+
+int ensure_device_ready() {
+    int dev = -1;
+    CUDA_TRY(cudaGetDevice(&dev));
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    static std::map<int, int> ready;
+    auto it = ready.find(dev);
+    if (it != ready.end()) return it->second;
+    int st = upload_constants();
+    if (st == CELESTE_OK) st = configure_kernels();
+    ready[dev] = st;
+    return st;
+}
+
+}  // namespace
+
+struct celeste_field {
+    int device = 0;
+    int N = 0;
+    int S_tot = 0;
+    std::vector<ImageDev> h_images;
+    std::vector<DevBuf<float>> pixels, sky, iota;
+    std::vector<DevBuf<double>> pixconst;
+    DevBuf<ImageDev> d_images;
+    // patches
+    std::vector<PatchDev> h_patches;
+    DevBuf<PatchDev> d_patches;
+    DevBuf<uint8_t> bitmap_pool;
+    DevBuf<double> double_pool;   // psf records + spline coefficient arrays
+    unsigned long long patch_generation = 0;
+};
+
+struct celeste_plan {
+    celeste_field* field = nullptr;
+    unsigned long long patch_generation = 0;
+    int n_tasks = 0, n_slots = 0, N = 0;
+    int n_blocks = 0, chunk_pixels = 0;
+    std::vector<int> h_task_ptr;
+    DevBuf<int> task_ptr, src_row, act_slot, chunk_ptr;
+    DevBuf<int2> blockmap;
+    DevBuf<double> slotimg, slotbr, partials;
+    // staging for the host-buffer entry point
+    DevBuf<double> vp_dev, v_dev, d_dev, h_dev;
+    DevBuf<long long> counters_dev;
+    DevBuf<int> flags_dev;
+    cudaStream_t stream = nullptr;
+    ~celeste_plan() {
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+extern "C" {
+
+void celeste_get_errmsg(int status, char* buf) {
+    const char* m;
+    switch (status) {
+        case CELESTE_OK: m = "ok"; break;
+        case CELESTE_ERR_NO_DEVICE: m = "no usable CUDA device (no CPU fallback exists)"; break;
+        case CELESTE_ERR_BAD_ARG: m = "invalid argument"; break;
+        case CELESTE_ERR_ALLOC: m = "device memory allocation failed"; break;
+        case CELESTE_ERR_CUDA: m = "CUDA runtime error"; break;
+        case CELESTE_ERR_UNSUPPORTED: m = "unsupported configuration (keep the reference path)"; break;
+        case CELESTE_ERR_NONFINITE: m = "ELBO value/gradient/Hessian contains Inf/NaNs"; break;
+        case CELESTE_ERR_STATE: m = "handle in wrong state"; break;
+        default: m = "unknown status"; break;
+    }
+    std::snprintf(buf, 61, "%s", m);
+}
+
+void celeste_get_errdetail(char* buf) { std::snprintf(buf, 512, "%s", g_detail); }
+
+int celeste_version(void) { return 100; }
+
+int celeste_init(int device, int* n_devices_out) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (n_devices_out) *n_devices_out = (e == cudaSuccess) ? n : 0;
+    if (e != cudaSuccess || n == 0) {
+        set_detail("cudaGetDeviceCount: %s (n=%d)", cudaGetErrorString(e), n);
+        return CELESTE_ERR_NO_DEVICE;
+    }
+    if (device >= 0) {
+        if (device >= n) {
+            set_detail("device %d requested, %d present", device, n);
+            return CELESTE_ERR_BAD_ARG;
+        }
+        CUDA_TRY(cudaSetDevice(device));
+    }
+    return ensure_device_ready();
+}
+
+int celeste_field_create(celeste_field** out, int32_t N, const celeste_image* imgs) {
+    if (!out || N < 0 || (N > 0 && !imgs)) {
+        set_detail("field_create: bad arguments");
+        return CELESTE_ERR_BAD_ARG;
+    }
+    *out = nullptr;
+    int st = ensure_device_ready();
+    if (st != CELESTE_OK) return st;
+    celeste_field* f = new (std::nothrow) celeste_field;
+    if (!f) return CELESTE_ERR_ALLOC;
+    std::unique_ptr<celeste_field> guard(f);
+    CUDA_TRY(cudaGetDevice(&f->device));
+    f->N = N;
+    f->pixels.resize(N);
+    f->sky.resize(N);
+    f->iota.resize(N);
+    f->pixconst.resize(N);
+    f->h_images.resize(N);
+    for (int n = 0; n < N; ++n) {
+        const celeste_image& im = imgs[n];
+        if (im.H <= 0 || im.W <= 0 || im.band < 1 || im.band > CELESTE_NUM_BANDS || !im.pixels || !im.sky ||
+            !im.nelec_per_nmgy) {
+            set_detail("field_create: image %d malformed (H=%d W=%d band=%d)", n, im.H, im.W, im.band);
+            return CELESTE_ERR_BAD_ARG;
+        }
+        const size_t np = (size_t)im.H * im.W;
+        CUDA_TRY(f->pixels[n].alloc(np));
+        CUDA_TRY(f->sky[n].alloc(np));
+        CUDA_TRY(f->iota[n].alloc(im.H));
+        CUDA_TRY(f->pixconst[n].alloc(np));
+        CUDA_TRY(cudaMemcpy(f->pixels[n].p, im.pixels, np * sizeof(float), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(f->sky[n].p, im.sky, np * sizeof(float), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(f->iota[n].p, im.nelec_per_nmgy, im.H * sizeof(float), cudaMemcpyHostToDevice));
+        DevBuf<double> li;
+        if (im.log_iota) {
+            CUDA_TRY(li.alloc(im.H));
+            CUDA_TRY(cudaMemcpy(li.p, im.log_iota, im.H * sizeof(double), cudaMemcpyHostToDevice));
+        }
+        prep_image_kernel<<<1184, 256>>>(im.H, im.W, f->pixels[n].p, f->iota[n].p, li.p, f->pixconst[n].p);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaDeviceSynchronize());
+        ImageDev d;
+        d.H = im.H;
+        d.W = im.W;
+        d.band = im.band;
+        d.pixels = f->pixels[n].p;
+        d.sky = f->sky[n].p;
+        d.iota = f->iota[n].p;
+        d.pixconst = f->pixconst[n].p;
+        f->h_images[n] = d;
+    }
+    CUDA_TRY(f->d_images.upload(f->h_images));
+    *out = guard.release();
+    return CELESTE_OK;
+}
+
+int celeste_patches_set(celeste_field* f, int32_t S_tot, int32_t N, const celeste_patch* p) {
+    if (!f || S_tot < 0 || N != f->N || (S_tot > 0 && N > 0 && !p)) {
+        set_detail("patches_set: bad arguments (N=%d, field N=%d)", N, f ? f->N : -1);
+        return CELESTE_ERR_BAD_ARG;
+    }
+    CUDA_TRY(cudaSetDevice(f->device));
+    const size_t np = (size_t)S_tot * N;
+    // pool layout: bitmaps; doubles (psf records, de-duplicated spline coefficient arrays)
+    std::vector<uint8_t> hb;
+    std::vector<double> hd;
+    std::vector<size_t> bm_off(np), psf_off(np), coef_off(np);
+    std::map<std::pair<const double*, std::pair<int, int>>, size_t> coef_seen;
+    for (size_t i = 0; i < np; ++i) {
+        const celeste_patch& q = p[i];
+        if (q.H2 < 0 || q.W2 < 0 || q.K < 1 || q.K > MAX_K || !q.psf || !q.itp_coefs || q.itp_dims[0] < 4 ||
+            q.itp_dims[1] < 4 || ((size_t)q.H2 * q.W2 > 0 && !q.active_pixel_bitmap)) {
+            set_detail("patches_set: patch %zu malformed (H2=%d W2=%d K=%d, K must be 1..%d)", i, q.H2, q.W2, q.K, MAX_K);
+            return q.K > MAX_K ? CELESTE_ERR_UNSUPPORTED : CELESTE_ERR_BAD_ARG;
+        }
+        bm_off[i] = hb.size();
+        const size_t nb = (size_t)q.H2 * q.W2;
+        if (nb) hb.insert(hb.end(), q.active_pixel_bitmap, q.active_pixel_bitmap + nb);
+        psf_off[i] = hd.size();
+        hd.insert(hd.end(), q.psf, q.psf + 7 * (size_t)q.K);
+        auto key = std::make_pair(q.itp_coefs, std::make_pair((int)q.itp_dims[0], (int)q.itp_dims[1]));
+        auto it = coef_seen.find(key);
+        if (it == coef_seen.end()) {
+            coef_off[i] = hd.size();
+            hd.insert(hd.end(), q.itp_coefs, q.itp_coefs + (size_t)q.itp_dims[0] * q.itp_dims[1]);
+            coef_seen[key] = coef_off[i];
+        } else {
+            coef_off[i] = it->second;
+        }
+    }
+    if (hb.empty()) hb.push_back(0);
+    CUDA_TRY(f->bitmap_pool.upload(hb));
+    CUDA_TRY(f->double_pool.upload(hd));
+    f->h_patches.resize(np);
+    for (size_t i = 0; i < np; ++i) {
+        const celeste_patch& q = p[i];
+        PatchDev d;
+        d.off_h = (int)q.bitmap_offset[0];
+        d.off_w = (int)q.bitmap_offset[1];
+        d.H2 = q.H2;
+        d.W2 = q.W2;
+        d.bitmap = f->bitmap_pool.p + bm_off[i];
+        for (int k = 0; k < 4; ++k) d.J[k] = q.wcs_jacobian[k];
+        d.wc[0] = q.world_center[0];
+        d.wc[1] = q.world_center[1];
+        d.pc[0] = q.pixel_center[0];
+        d.pc[1] = q.pixel_center[1];
+        d.K = q.K;
+        d.psf = f->double_pool.p + psf_off[i];
+        d.coefs = f->double_pool.p + coef_off[i];
+        d.n1 = q.itp_dims[0];
+        d.n2 = q.itp_dims[1];
+        f->h_patches[i] = d;
+    }
+    CUDA_TRY(f->d_patches.upload(f->h_patches));
+    f->S_tot = S_tot;
+    f->patch_generation++;
+    return CELESTE_OK;
+}
+
+void celeste_field_destroy(celeste_field* f) { delete f; }
+
+int celeste_plan_create(celeste_field* f, celeste_plan** out, int32_t n_tasks, const int32_t* task_ptr,
+                        const int32_t* source_ids, const int32_t* active_ptr, const int32_t* active_idx) {
+    if (!f || !out || n_tasks < 0 || !task_ptr || !active_ptr || (n_tasks > 0 && (!source_ids || !active_idx))) {
+        set_detail("plan_create: bad arguments");
+        return CELESTE_ERR_BAD_ARG;
+    }
+    *out = nullptr;
+    CUDA_TRY(cudaSetDevice(f->device));
+    std::unique_ptr<celeste_plan> pl(new (std::nothrow) celeste_plan);
+    if (!pl) return CELESTE_ERR_ALLOC;
+    pl->field = f;
+    pl->patch_generation = f->patch_generation;
+    pl->n_tasks = n_tasks;
+    pl->N = f->N;
+    const int n_slots = task_ptr[n_tasks];
+    pl->n_slots = n_slots;
+    pl->h_task_ptr.assign(task_ptr, task_ptr + n_tasks + 1);
+    std::vector<int> src_row(n_slots), act_slot(n_tasks);
+    for (int t = 0; t < n_tasks; ++t) {
+        const int s0 = task_ptr[t], s1 = task_ptr[t + 1];
+        if (s0 < 0 || s1 < s0 || (t == 0 && s0 != 0)) {
+            set_detail("plan_create: task_ptr not a prefix array at task %d", t);
+            return CELESTE_ERR_BAD_ARG;
+        }
+        const int Sa = active_ptr[t + 1] - active_ptr[t];
+        if (Sa != 1) {
+            set_detail("plan_create: task %d has Sa=%d active sources; this build evaluates Sa == 1 "
+                       "(production, ParallelRun.jl:253,489) and leaves Sa > 1 on the reference path", t, Sa);
+            return CELESTE_ERR_UNSUPPORTED;
+        }
+        const int a = active_idx[active_ptr[t]];
+        if (a < 1 || a > s1 - s0) {
+            set_detail("plan_create: task %d active index %d outside 1..%d", t, a, s1 - s0);
+            return CELESTE_ERR_BAD_ARG;
+        }
+        act_slot[t] = s0 + a - 1;
+        for (int s = s0; s < s1; ++s) {
+            const int row = source_ids[s];
+            if (row < 1 || row > f->S_tot) {
+                set_detail("plan_create: task %d source id %d outside 1..%d", t, row, f->S_tot);
+                return CELESTE_ERR_BAD_ARG;
+            }
+            src_row[s] = row - 1;
+        }
+    }
+    // block map: one block per (task, image, chunk of the active patch's pixels)
+    const int chunk_pixels = 4 * PIX_THREADS;
+    pl->chunk_pixels = chunk_pixels;
+    std::vector<int> chunk_ptr((size_t)n_tasks * pl->N + 1, 0);
+    std::vector<int2> blockmap;
+    for (int t = 0; t < n_tasks; ++t)
+        for (int n = 0; n < pl->N; ++n) {
+            const PatchDev& pa = f->h_patches[(size_t)src_row[act_slot[t]] + (size_t)n * f->S_tot];
+            const long npix = (long)pa.H2 * pa.W2;
+            const int nchunk = (int)((npix + chunk_pixels - 1) / chunk_pixels);
+            const int tn = t * pl->N + n;
+            chunk_ptr[tn + 1] = chunk_ptr[tn] + nchunk;
+            for (int c = 0; c < nchunk; ++c) blockmap.push_back(make_int2(tn, c));
+        }
+    pl->n_blocks = (int)blockmap.size();
+    std::vector<int> tp(task_ptr, task_ptr + n_tasks + 1);
+    CUDA_TRY(pl->task_ptr.upload(tp));
+    CUDA_TRY(pl->src_row.upload(src_row));
+    CUDA_TRY(pl->act_slot.upload(act_slot));
+    CUDA_TRY(pl->chunk_ptr.upload(chunk_ptr));
+    CUDA_TRY(pl->blockmap.upload(blockmap));
+    CUDA_TRY(pl->slotimg.alloc((size_t)n_slots * pl->N * SLOTIMG_STRIDE));
+    CUDA_TRY(pl->slotbr.alloc((size_t)n_slots * SLOTBR_STRIDE));
+    CUDA_TRY(pl->partials.alloc((size_t)pl->n_blocks * NACC_MODE2));
+    *out = pl.release();
+    return CELESTE_OK;
+}
+
+void celeste_plan_destroy(celeste_plan* p) { delete p; }
+
+int celeste_plan_launches(const celeste_plan* p, int32_t mode) {
+    (void)mode;
+    if (!p || p->n_tasks == 0) return 0;
+    return p->n_blocks > 0 ? 3 : 2;   // setup, pixel, epilogue
+}
+
+}  // extern "C"
+
+static PlanDev plan_dev(const celeste_plan* p) {
+    PlanDev d;
+    d.n_tasks = p->n_tasks;
+    d.N = p->N;
+    d.S_tot = p->field->S_tot;
+    d.n_slots = p->n_slots;
+    d.task_ptr = p->task_ptr.p;
+    d.src_row = p->src_row.p;
+    d.act_slot = p->act_slot.p;
+    d.blockmap = p->blockmap.p;
+    d.chunk_ptr = p->chunk_ptr.p;
+    d.slotimg = p->slotimg.p;
+    d.slotbr = p->slotbr.p;
+    d.partials = p->partials.p;
+    return d;
+}
+
+template <int MODE>
+static int launch_mode(celeste_plan* p, const double* vp_dev, double* v, double* d, double* h, long long* counters,
+                       int* flags, cudaStream_t st) {
+    const PlanDev pd = plan_dev(p);
+    FieldDev fd;
+    fd.images = p->field->d_images.p;
+    fd.patches = p->field->d_patches.p;
+    const long total = (long)p->n_slots * p->N * MAX_COMPS;
+    const int sblocks = (int)std::min<long>((total + 255) / 256, 148L * 16);
+    setup_kernel<<<sblocks, 256, 0, st>>>(pd, fd, vp_dev);
+    if (p->n_blocks > 0)
+        pixel_kernel<MODE><<<p->n_blocks, PIX_THREADS, pixel_smem_bytes<MODE>(), st>>>(pd, fd, p->chunk_pixels);
+    epilogue_kernel<MODE><<<p->n_tasks, EPI_THREADS, 0, st>>>(pd, fd, vp_dev, v, d, h, counters, flags);
+    CUDA_TRY(cudaGetLastError());
+    return CELESTE_OK;
+}
+
+extern "C" {
+
+int celeste_elbo_plan_device(celeste_plan* p, const double* vp_dev, int32_t mode, double* v_dev, double* d_dev,
+                             double* h_dev, int64_t* counters_dev, int32_t* flags_dev, void* cuda_stream) {
+    if (!p || !vp_dev || !v_dev || !counters_dev || !flags_dev || mode < 0 || mode > 2 || (mode >= 1 && !d_dev) ||
+        (mode >= 2 && !h_dev)) {
+        set_detail("elbo_plan_device: bad arguments (mode=%d)", mode);
+        return CELESTE_ERR_BAD_ARG;
+    }
+    if (p->patch_generation != p->field->patch_generation) {
+        set_detail("plan is stale: celeste_patches_set was called after celeste_plan_create");
+        return CELESTE_ERR_STATE;
+    }
+    if (p->n_tasks == 0) return CELESTE_OK;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    long long* c = reinterpret_cast<long long*>(counters_dev);
+    switch (mode) {
+        case 0: return launch_mode<0>(p, vp_dev, v_dev, d_dev, h_dev, c, flags_dev, st);
+        case 1: return launch_mode<1>(p, vp_dev, v_dev, d_dev, h_dev, c, flags_dev, st);
+        default: return launch_mode<2>(p, vp_dev, v_dev, d_dev, h_dev, c, flags_dev, st);
+    }
+}
+
+int celeste_elbo_plan_host(celeste_plan* p, const double* vp, int32_t mode, double* v, double* d, double* h,
+                           int64_t* counters, int32_t* flags) {
+    if (!p || !vp || !v || mode < 0 || mode > 2 || (mode >= 1 && !d) || (mode >= 2 && !h)) {
+        set_detail("elbo_plan_host: bad arguments (mode=%d)", mode);
+        return CELESTE_ERR_BAD_ARG;
+    }
+    if (p->n_tasks == 0) return CELESTE_OK;
+    CUDA_TRY(cudaSetDevice(p->field->device));
+    if (!p->stream) CUDA_TRY(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    const size_t nt = p->n_tasks;
+    CUDA_TRY(p->vp_dev.ensure((size_t)p->n_slots * NPARAM));
+    CUDA_TRY(p->v_dev.ensure(nt));
+    CUDA_TRY(p->counters_dev.ensure(2 * nt));
+    CUDA_TRY(p->flags_dev.ensure(nt));
+    if (mode >= 1) CUDA_TRY(p->d_dev.ensure(nt * NPARAM));
+    if (mode >= 2) CUDA_TRY(p->h_dev.ensure(nt * NPARAM * NPARAM));
+    cudaStream_t st = p->stream;
+    CUDA_TRY(cudaMemcpyAsync(p->vp_dev.p, vp, (size_t)p->n_slots * NPARAM * sizeof(double), cudaMemcpyHostToDevice, st));
+    int rc = celeste_elbo_plan_device(p, p->vp_dev.p, mode, p->v_dev.p, p->d_dev.p, p->h_dev.p,
+                                      reinterpret_cast<int64_t*>(p->counters_dev.p), p->flags_dev.p, st);
+    if (rc != CELESTE_OK) return rc;
+    std::vector<int> hflags(nt);
+    CUDA_TRY(cudaMemcpyAsync(v, p->v_dev.p, nt * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (mode >= 1) CUDA_TRY(cudaMemcpyAsync(d, p->d_dev.p, nt * NPARAM * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (mode >= 2)
+        CUDA_TRY(cudaMemcpyAsync(h, p->h_dev.p, nt * NPARAM * NPARAM * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (counters)
+        CUDA_TRY(cudaMemcpyAsync(counters, p->counters_dev.p, 2 * nt * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(hflags.data(), p->flags_dev.p, nt * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    bool bad = false;
+    for (size_t t = 0; t < nt; ++t) {
+        if (flags) flags[t] = hflags[t];
+        if (hflags[t] & CELESTE_FLAG_NONFINITE) {
+            if (!bad) set_detail("task %zu: non-finite ELBO (assert_all_finite, elbo_args.jl:145)", t);
+            bad = true;
+        }
+    }
+    return bad ? CELESTE_ERR_NONFINITE : CELESTE_OK;
+}
+
+int celeste_elbo_batch(celeste_field* f, int32_t n_tasks, const int32_t* task_ptr, const int32_t* source_ids,
+                       const int32_t* active_ptr, const int32_t* active_idx, const double* vp, int32_t mode, double* v,
+                       double* d, double* h, int64_t* counters, int32_t* flags) {
+    if (n_tasks == 0) return CELESTE_OK;
+    celeste_plan* pl = nullptr;
+    int rc = celeste_plan_create(f, &pl, n_tasks, task_ptr, source_ids, active_ptr, active_idx);
+    if (rc != CELESTE_OK) return rc;
+    rc = celeste_elbo_plan_host(pl, vp, mode, v, d, h, counters, flags);
+    celeste_plan_destroy(pl);
+    return rc;
+}
+
+int celeste_elbo_single(celeste_field* f, int32_t S, const int32_t* source_ids, int32_t Sa, const int32_t* active_idx,
+                        const double* vp, int32_t mode, double* v, double* d, double* h, int64_t* counters,
+                        int32_t* flags) {
+    const int32_t task_ptr[2] = {0, S};
+    const int32_t active_ptr[2] = {0, Sa};
+    return celeste_elbo_batch(f, 1, task_ptr, source_ids, active_ptr, active_idx, vp, mode, v, d, h, counters, flags);
+}
+
+int celeste_fp64_peak(double* tflops_out, void* cuda_stream) {
+    if (!tflops_out) return CELESTE_ERR_BAD_ARG;
+    int st0 = ensure_device_ready();
+    if (st0 != CELESTE_OK) return st0;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    DevBuf<double> out;
+    CUDA_TRY(out.alloc(1));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    const int blocks = 148 * 8, threads = 256, iters = 4096;
+    dfma_peak_kernel<<<blocks, threads, 0, st>>>(out.p, 64, 1.0);   // warm-up
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CUDA_TRY(cudaEventRecord(e0, st));
+        dfma_peak_kernel<<<blocks, threads, 0, st>>>(out.p, iters, 1.0);
+        CUDA_TRY(cudaEventRecord(e1, st));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 64.0 * iters * (double)blocks * threads;
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    CUDA_TRY(cudaGetLastError());
+    *tflops_out = best;
+    return CELESTE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,468 @@
+// celeste_kernels.cuh -- sm_100a kernels of the ELBO hot path (see DESIGN.md "Kernels").
+//
+//   prep_image_kernel   once per image: pixconst = x log(iota) - lgamma(x + 1)   (elbo_objective.jl:292,391)
+//   setup_kernel        per evaluation: mixtures of every (task source, image)   (fsm_util.jl:111-169)
+//                       + per-source brightness moments                          (source_brightness.jl:27-202)
+//   pixel_kernel<MODE>  THE hot loop: one block per (task, image, pixel chunk)   (elbo_objective.jl:330-470)
+//   epilogue_kernel<MODE> per task: fixed-order reduction of the chunk partials, raw -> parameter
+//                       chain rule, 44 x 44 SensitiveFloat output                (SensitiveFloats.jl:23-47)
+//
+// FP64-pipe bound by design: the pixel kernel touches ~20 B of HBM per pixel-visit
+// and executes ~1.5k (grad) / ~4k (Hessian) FP64 instructions for it; everything a thread needs
+// per component comes from shared memory (active source) or L1-resident broadcasts (neighbours).
+#ifndef CELESTE_KERNELS_CUH
+#define CELESTE_KERNELS_CUH
+
+#ifndef CELESTE_HOST_EMULATION   // tests/host_emul compiles this file with a host emulation layer instead
+#include <cuda_runtime.h>
+#define CEL_DYNAMIC_SMEM(name) extern __shared__ double name[]
+#else
+#define CEL_DYNAMIC_SMEM(name) double* name = ::cuda_emul::dynamic_smem()
+#endif
+
+#include "elbo_math.cuh"
+
+namespace celeste {
+
+struct ImageDev {
+    int H, W, band;
+    const float* pixels;
+    const float* sky;
+    const float* iota;
+    const double* pixconst;   // x*log_iota[h] - lgamma(x+1)
+};
+
+struct PatchDev {
+    int off_h, off_w, H2, W2;   // bitmap_offset, size(active_pixel_bitmap)
+    const uint8_t* bitmap;
+    double J[4];                // wcs_jacobian, col-major
+    double wc[2], pc[2];
+    int K;
+    const double* psf;          // K x 7
+    const double* coefs;        // padded spline coefficients
+    int n1, n2;
+};
+
+// per (task source slot, image) scratch written by setup_kernel
+constexpr int SLOTIMG_STRIDE = MAX_COMPS * COMP_STRIDE + 2;   // comps + m_pos
+// per slot: El[2][5], Ell[2][5], a[2], theta
+constexpr int SLOTBR_STRIDE = 24;
+
+struct PlanDev {
+    int n_tasks, N, S_tot, n_slots;
+    const int* task_ptr;     // n_tasks + 1 (slot ranges)
+    const int* src_row;      // n_slots: 0-based patch row of each slot
+    const int* act_slot;     // n_tasks: slot of the (single) active source
+    const int2* blockmap;    // n_blocks: (task * N + n, chunk)
+    const int* chunk_ptr;    // n_tasks * N + 1: first block of (task, n)
+    double* slotimg;         // n_slots * N * SLOTIMG_STRIDE
+    double* slotbr;          // n_slots * SLOTBR_STRIDE
+    double* partials;        // n_blocks * NACC
+};
+
+struct FieldDev {
+    const ImageDev* images;
+    const PatchDev* patches;  // s + n * S_tot
+};
+
+__constant__ double c_proto_eta[NPROTO];
+__constant__ double c_proto_nu[NPROTO];
+
+struct LdGlobal {
+    __device__ __forceinline__ double operator()(const double* p) const { return __ldg(p); }
+};
+struct LdShared {
+    __device__ __forceinline__ double operator()(const double* p) const { return *p; }
+};
+
+// ------------------------------------------------------------------------------------------------
+__global__ void prep_image_kernel(int H, int W, const float* __restrict__ pixels, const float* __restrict__ iota,
+                                  const double* __restrict__ log_iota, double* __restrict__ pixconst) {
+    const size_t n = (size_t)H * W;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int h = (int)(i % H);
+        const double x = (double)pixels[i];
+        const double li = log_iota ? log_iota[h] : (double)logf(iota[h]);   // Float32 log, elbo_objective.jl:292
+        pixconst[i] = x * li - lgamma(x + 1.0);
+    }
+}
+
+// one thread per (slot, image, component)
+__global__ void setup_kernel(PlanDev plan, FieldDev field, const double* __restrict__ vp) {
+    const long total = (long)plan.n_slots * plan.N * MAX_COMPS;
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % MAX_COMPS);
+        const long sn = idx / MAX_COMPS;
+        const int n = (int)(sn % plan.N);
+        const int slot = (int)(sn / plan.N);
+        const double* vs = vp + (size_t)NPARAM * slot;
+        const PatchDev& p = field.patches[plan.src_row[slot] + (size_t)n * plan.S_tot];
+        double* rec = plan.slotimg + ((size_t)slot * plan.N + n) * SLOTIMG_STRIDE;
+        // linear_world_to_pix, wcs_utils.jl:14-18
+        const double d0 = vs[0] - p.wc[0], d1 = vs[1] - p.wc[1];
+        const double m1 = (p.J[0] * d0 + p.J[2] * d1) + p.pc[0];
+        const double m2 = (p.J[1] * d0 + p.J[3] * d1) + p.pc[1];
+        if (c < NPROTO * p.K) {
+            const int j = c / p.K, k = c % p.K;
+            make_component(p.psf + 7 * k, c_proto_eta[j], c_proto_nu[j], m1, m2, vs[3], vs[4], vs[5],
+                           rec + c * COMP_STRIDE);
+        }
+        if (c == 0) {
+            rec[MAX_COMPS * COMP_STRIDE + 0] = m1;
+            rec[MAX_COMPS * COMP_STRIDE + 1] = m2;
+            if (n == 0) {
+                double El[2][5], Ell[2][5];
+                brightness_values(vs, El, Ell);
+                double* br = plan.slotbr + (size_t)slot * SLOTBR_STRIDE;
+                for (int i = 0; i < 2; ++i)
+                    for (int b = 0; b < 5; ++b) {
+                        br[i * 5 + b] = El[i][b];
+                        br[10 + i * 5 + b] = Ell[i][b];
+                    }
+                br[20] = vs[26];
+                br[21] = vs[27];
+                br[22] = vs[2];
+                br[23] = 0.0;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+constexpr int PIX_THREADS = 128;
+constexpr int MAX_NB_LIST = 64;
+
+template <int MODE>
+__global__ void __launch_bounds__(PIX_THREADS) pixel_kernel(PlanDev plan, FieldDev field, int chunk_pixels) {
+    constexpr int NACC = NAcc<MODE>::value;
+    CEL_DYNAMIC_SMEM(smem);
+    double* acc = smem;                                    // NACC x PIX_THREADS
+    double* s_comps = acc + NACC * PIX_THREADS;           // MAX_COMPS * 6
+    __shared__ int s_nb[MAX_NB_LIST];
+    __shared__ int s_nb_count;
+    __shared__ int s_nb_overflow;
+
+    const int tid = threadIdx.x;
+    const int2 bm = plan.blockmap[blockIdx.x];
+    const int tn = bm.x, chunk = bm.y;
+    const int t = tn / plan.N, n = tn % plan.N;
+    const int slot0 = plan.task_ptr[t], slot1 = plan.task_ptr[t + 1];
+    const int aslot = plan.act_slot[t];
+    const ImageDev img = field.images[n];
+    const PatchDev pa = field.patches[plan.src_row[aslot] + (size_t)n * plan.S_tot];
+    const int npix = pa.H2 * pa.W2;
+    const int first = chunk * chunk_pixels;
+    const int last = min(first + chunk_pixels, npix);      // exclusive
+
+#pragma unroll
+    for (int a = 0; a < NACC; ++a) acc[a * PIX_THREADS + tid] = 0.0;
+    const double* arec = plan.slotimg + ((size_t)aslot * plan.N + n) * SLOTIMG_STRIDE;
+    for (int i = tid; i < NPROTO * pa.K * COMP_STRIDE; i += PIX_THREADS) s_comps[i] = arec[i];
+    if (tid == 0) {
+        s_nb_count = 0;
+        s_nb_overflow = 0;
+    }
+    __syncthreads();
+
+    // neighbours whose patch in this image can touch this chunk's pixels (ordered compaction by warp 0,
+    // so the summation order over neighbours -- hence the result -- is deterministic)
+    if (tid < 32 && last > first) {
+        const int w2_lo = first / pa.H2, w2_hi = (last - 1) / pa.H2;
+        int h2_lo = 0, h2_hi = pa.H2 - 1;
+        if (w2_lo == w2_hi) {
+            h2_lo = first % pa.H2;
+            h2_hi = (last - 1) % pa.H2;
+        }
+        const int bh_lo = pa.off_h + h2_lo + 1, bh_hi = pa.off_h + h2_hi + 1;   // 1-based image rows
+        const int bw_lo = pa.off_w + w2_lo + 1, bw_hi = pa.off_w + w2_hi + 1;
+        for (int base = slot0; base < slot1; base += 32) {
+            const int s = base + tid;
+            bool hit = false;
+            if (s < slot1 && s != aslot) {
+                const PatchDev& p = field.patches[plan.src_row[s] + (size_t)n * plan.S_tot];
+                // rows off_h+1 .. off_h+H2, columns off_w+1 .. off_w+W2-1 (strict `w2 < W2`, elbo_objective.jl:349)
+                hit = (p.off_h + 1 <= bh_hi) && (p.off_h + p.H2 >= bh_lo) && (p.off_w + 1 <= bw_hi) &&
+                      (p.off_w + p.W2 - 1 >= bw_lo);
+            }
+            const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+            const int pos = s_nb_count + __popc(ballot & ((1u << tid) - 1u));
+            if (hit) {
+                if (pos < MAX_NB_LIST)
+                    s_nb[pos] = s;
+                else
+                    s_nb_overflow = 1;
+            }
+            __syncwarp();
+            if (tid == 0) s_nb_count = min(s_nb_count + __popc(ballot), MAX_NB_LIST);
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+
+    const double* abr = plan.slotbr + (size_t)aslot * SLOTBR_STRIDE;
+    const int b = img.band - 1;
+    const double a1 = abr[20], a2 = abr[21], theta = abr[22];
+    const double cb[4] = {a1 * abr[b], a2 * abr[5 + b], a1 * abr[10 + b], a2 * abr[15 + b]};
+    const double am1 = arec[MAX_COMPS * COMP_STRIDE], am2 = arec[MAX_COMPS * COMP_STRIDE + 1];
+
+    // value-only contribution of neighbour slot s at image pixel (h, w) (elbo_objective.jl:342-372, inactive branch)
+    auto neighbour = [&](int s, int h, int w, double& Ebg, double& Vbg, double& cnt) {
+        const PatchDev& p = field.patches[plan.src_row[s] + (size_t)n * plan.S_tot];
+        const int h2 = h - p.off_h, w2 = w - p.off_w;
+        if (h2 < 1 || h2 > p.H2 || w2 < 1 || w2 >= p.W2) return;
+        if (!p.bitmap[(h2 - 1) + (size_t)(w2 - 1) * p.H2]) return;
+        cnt += 1.0;
+        const double* rec = plan.slotimg + ((size_t)s * plan.N + n) * SLOTIMG_STRIDE;
+        const double* br = plan.slotbr + (size_t)s * SLOTBR_STRIDE;
+        const double m1 = __ldg(rec + MAX_COMPS * COMP_STRIDE), m2 = __ldg(rec + MAX_COMPS * COMP_STRIDE + 1);
+        double f0, gd[2], hd[3];
+        star_eval<0>(LdGlobal(), p.coefs, p.n1, p.n2, (double)h - m1 + 26.0, (double)w - m2 + 26.0, f0, gd, hd);
+        const double f1 = gal_value(LdGlobal(), rec, p.K, __ldg(br + 22), (double)h, (double)w);
+        const double na1 = __ldg(br + 20), na2 = __ldg(br + 21);
+        const double Es = na1 * __ldg(br + b) * f0 + na2 * __ldg(br + 5 + b) * f1;
+        const double E2s = na1 * __ldg(br + 10 + b) * f0 * f0 + na2 * __ldg(br + 15 + b) * f1 * f1;
+        Ebg += Es;
+        Vbg += E2s - Es * Es;
+    };
+
+    for (int pix = first + tid; pix < last; pix += PIX_THREADS) {
+        const int h2 = pix % pa.H2, w2 = pix / pa.H2;        // 0-based local
+        if (!pa.bitmap[pix]) continue;                       // elbo_objective.jl:445
+        const int h = pa.off_h + h2 + 1, w = pa.off_w + w2 + 1;   // 1-based image coordinates
+        const size_t ipix = (size_t)(h - 1) + (size_t)(w - 1) * img.H;
+        const float xf = img.pixels[ipix];
+        if (isnan(xf)) continue;                             // :459
+        PixelConsts pc;
+        pc.x = (double)xf;
+        pc.iota = (double)img.iota[h - 1];
+        pc.pixconst = img.pixconst[ipix];
+        double Ebg = (double)img.sky[ipix];                  // :374
+        double Vbg = 0.0;
+        double cnt_inactive = 0.0;
+        const int nnb = s_nb_count;
+        for (int i = 0; i < nnb; ++i) neighbour(s_nb[i], h, w, Ebg, Vbg, cnt_inactive);
+        if (s_nb_overflow) {
+            // rare: more overlapping neighbours than the list holds; scan the remaining slots in order
+            const int last_listed = s_nb[MAX_NB_LIST - 1];
+            for (int s = last_listed + 1; s < slot1; ++s)
+                if (s != aslot) neighbour(s, h, w, Ebg, Vbg, cnt_inactive);
+        }
+        const bool covered = (w2 + 1) < pa.W2;               // strict last column, :349
+        double f0 = 0.0, g0[2] = {0.0, 0.0}, h0[3] = {0.0, 0.0, 0.0};
+        GalRaw gal;
+        gal.f = 0.0;
+        if (covered) {
+            star_eval<MODE>(LdGlobal(), pa.coefs, pa.n1, pa.n2, (double)h - am1 + 26.0, (double)w - am2 + 26.0, f0, g0,
+                            h0);
+            gal_eval<MODE>(LdShared(), s_comps, pa.K, c_proto_nu, theta, (double)h, (double)w, gal);
+            acc[ACC_CNT_ACTIVE * PIX_THREADS + tid] += 1.0;
+        }
+        acc[ACC_CNT_INACTIVE * PIX_THREADS + tid] += cnt_inactive;
+        pixel_accumulate<MODE>(acc + tid, PIX_THREADS, pc, Ebg, Vbg, covered, cb, f0, g0, h0, gal);
+    }
+    __syncthreads();
+
+    // fixed-order block reduction: warp w reduces accumulators a = w, w + 4, ...
+    const int warp = tid >> 5, lane = tid & 31;
+    double* out = plan.partials + (size_t)blockIdx.x * NACC;
+    for (int a = warp; a < NACC; a += PIX_THREADS / 32) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < PIX_THREADS / 32; ++k) s += acc[a * PIX_THREADS + lane + 32 * k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) out[a] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+constexpr int EPI_THREADS = 128;
+constexpr int NY = 10;   // intermediate variables: c (4) then y (6)
+
+template <int MODE>
+__global__ void __launch_bounds__(EPI_THREADS) epilogue_kernel(PlanDev plan, FieldDev field,
+                                                               const double* __restrict__ vp, double* __restrict__ out_v,
+                                                               double* __restrict__ out_d, double* __restrict__ out_h,
+                                                               long long* __restrict__ out_counters,
+                                                               int* __restrict__ out_flags) {
+    constexpr int NACC = NAcc<MODE>::value;
+    __shared__ double ysum[NACC_MODE2];
+    __shared__ double Jy[NY][NLIVE];
+    __shared__ double Hyy[NY][NY];
+    __shared__ double Wm[NY][NLIVE];
+    __shared__ double Hacc[NLIVE][NLIVE];
+    __shared__ double gacc[NLIVE];
+    __shared__ double s_val, s_cnt[2];
+    __shared__ double J0[3][3], T0[3][3][3];
+    __shared__ int s_bad;
+
+    const int tid = threadIdx.x;
+    const int t = blockIdx.x;
+    const int aslot = plan.act_slot[t];
+    const double* vs = vp + (size_t)NPARAM * aslot;
+    const double* br = plan.slotbr + (size_t)aslot * SLOTBR_STRIDE;
+
+    for (int i = tid; i < NLIVE * NLIVE; i += EPI_THREADS) (&Hacc[0][0])[i] = 0.0;
+    if (tid < NLIVE) gacc[tid] = 0.0;
+    if (tid == 0) {
+        s_val = 0.0;
+        s_cnt[0] = s_cnt[1] = 0.0;
+        s_bad = 0;
+        if (MODE >= 1) sigma_derivs(vs[3], vs[4], vs[5], J0, T0);
+    }
+    __syncthreads();
+
+    for (int n = 0; n < plan.N; ++n) {
+        const int tn = t * plan.N + n;
+        const int c0 = plan.chunk_ptr[tn], c1 = plan.chunk_ptr[tn + 1];
+        for (int a = tid; a < NACC; a += EPI_THREADS) {
+            double s = 0.0;
+            for (int c = c0; c < c1; ++c) s += plan.partials[(size_t)c * NACC + a];
+            ysum[a] = s;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            s_val += ysum[ACC_VAL];
+            s_cnt[0] += ysum[ACC_CNT_ACTIVE];
+            s_cnt[1] += ysum[ACC_CNT_INACTIVE];
+        }
+        if (MODE >= 1) {
+            const PatchDev& p = field.patches[plan.src_row[aslot] + (size_t)n * plan.S_tot];
+            const int b = field.images[n].band - 1;
+            for (int i = tid; i < NY * NLIVE; i += EPI_THREADS) (&Jy[0][0])[i] = 0.0;
+            __syncthreads();
+            if (tid == 0) {
+                // y rows 4..9: x1 x2 S11 S12 S22 theta  (dx_a/dpos_b = -J[a][b])
+                Jy[4][0] = -p.J[0];
+                Jy[4][1] = -p.J[2];
+                Jy[5][0] = -p.J[1];
+                Jy[5][1] = -p.J[3];
+                for (int k = 0; k < 3; ++k)
+                    for (int j = 0; j < 3; ++j) Jy[6 + k][3 + j] = J0[k][j];
+                Jy[9][2] = 1.0;
+                double ka[10], la[10];
+                band_coefs(b, ka, la);
+                for (int i = 0; i < 2; ++i) {
+                    const double ai = br[20 + i], El = br[i * 5 + b], Ell = br[10 + i * 5 + b];
+                    Jy[i][26 + i] = El;
+                    Jy[2 + i][26 + i] = Ell;
+                    for (int k = 0; k < 10; ++k) {
+                        Jy[i][bright_id(i, k)] = ai * El * ka[k];
+                        Jy[2 + i][bright_id(i, k)] = ai * Ell * la[k];
+                    }
+                }
+            }
+            if (MODE >= 2 && tid == 32) {
+                for (int c = 0; c < 4; ++c)
+                    for (int d = c; d < 4; ++d) Hyy[c][d] = Hyy[d][c] = ysum[ACC_CC + tri4(c, d)];
+                for (int c = 0; c < 4; ++c)
+                    for (int k = 0; k < 6; ++k) Hyy[c][4 + k] = Hyy[4 + k][c] = ysum[ACC_CR + c * 6 + k];
+                for (int k = 0; k < 6; ++k)
+                    for (int l = k; l < 6; ++l) Hyy[4 + k][4 + l] = Hyy[4 + l][4 + k] = ysum[ACC_HH + tri6(k, l)];
+            }
+            __syncthreads();
+            if (tid < NLIVE) {
+                double g = 0.0;
+                for (int c = 0; c < 4; ++c) g += Jy[c][tid] * ysum[ACC_C1 + c];
+                for (int k = 0; k < 6; ++k) g += Jy[4 + k][tid] * ysum[ACC_G + k];
+                gacc[tid] += g;
+            }
+            if (MODE >= 2) {
+                for (int i = tid; i < NY * NLIVE; i += EPI_THREADS) {
+                    const int r = i / NLIVE, q = i % NLIVE;
+                    double s = 0.0;
+                    for (int k = 0; k < NY; ++k) s += Hyy[r][k] * Jy[k][q];
+                    Wm[r][q] = s;
+                }
+                __syncthreads();
+                for (int i = tid; i < NLIVE * NLIVE; i += EPI_THREADS) {
+                    const int pp = i / NLIVE, q = i % NLIVE;
+                    double s = 0.0;
+                    for (int r = 0; r < NY; ++r) s += Jy[r][pp] * Wm[r][q];
+                    Hacc[pp][q] += s;
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    // curvature of Sigma(shape): sum_k dL/dS_k * T0[k]   (transform_bvn_derivs_hessian!:481-488)
+                    for (int j = 0; j < 3; ++j)
+                        for (int l = 0; l < 3; ++l) {
+                            double s = 0.0;
+                            for (int k = 0; k < 3; ++k) s += ysum[ACC_G + 2 + k] * T0[k][j][l];
+                            Hacc[3 + j][3 + l] += s;
+                        }
+                    // curvature of c(a, beta): E * kappa kappa' and the (a, beta) cross terms
+                    double ka[10], la[10];
+                    band_coefs(b, ka, la);
+                    for (int i = 0; i < 2; ++i) {
+                        const double ai = br[20 + i], El = br[i * 5 + b], Ell = br[10 + i * 5 + b];
+                        const double cA = ysum[ACC_C1 + i], cB = ysum[ACC_C1 + 2 + i];
+                        for (int k = 0; k < 10; ++k) {
+                            const int pk = bright_id(i, k);
+                            const double cross = cA * El * ka[k] + cB * Ell * la[k];
+                            Hacc[26 + i][pk] += cross;
+                            Hacc[pk][26 + i] += cross;
+                            for (int l = 0; l < 10; ++l)
+                                Hacc[pk][bright_id(i, l)] += ai * (cA * El * ka[k] * ka[l] + cB * Ell * la[k] * la[l]);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // outputs, SensitiveFloat layout (p fastest); rows/cols 29..44 (ids.k) stay zero
+    int bad = 0;
+    if (tid == 0) {
+        out_v[t] = s_val;
+        out_counters[2 * t] = (long long)(s_cnt[0] + 0.5);
+        out_counters[2 * t + 1] = (long long)(s_cnt[1] + 0.5);
+        bad |= !isfinite(s_val);
+    }
+    if (MODE >= 1) {
+        for (int i = tid; i < NPARAM; i += EPI_THREADS) {
+            const double g = i < NLIVE ? gacc[i] : 0.0;
+            out_d[(size_t)NPARAM * t + i] = g;
+            bad |= !isfinite(g);
+        }
+    }
+    if (MODE >= 2) {
+        double* H = out_h + (size_t)NPARAM * NPARAM * t;
+        for (int i = tid; i < NPARAM * NPARAM; i += EPI_THREADS) {
+            const int r = i % NPARAM, c = i / NPARAM;
+            double v = 0.0;
+            if (r < NLIVE && c < NLIVE) v = 0.5 * (Hacc[r][c] + Hacc[c][r]);   // exactly symmetric output
+            H[i] = v;
+            bad |= !isfinite(v);
+        }
+    }
+    if (bad) atomicOr(&s_bad, 1);
+    __syncthreads();
+    if (tid == 0) out_flags[t] = s_bad ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Register-resident DFMA chains: the measured FP64 peak that bounds pixel_kernel.
+__global__ void dfma_peak_kernel(double* out, int iters, double seed) {
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+           a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = fma(a0, m, c);
+            a1 = fma(a1, m, c);
+            a2 = fma(a2, m, c);
+            a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c);
+            a5 = fma(a5, m, c);
+            a6 = fma(a6, m, c);
+            a7 = fma(a7, m, c);
+        }
+    }
+    const double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 12345.678) out[0] = s;   // never true; keeps the chain alive
+}
+
+}  // namespace celeste
+#endif

@@ -1,0 +1,479 @@
+// elbo_math.cuh -- per-pixel arithmetic of the ELBO hot path, written B200-first.
+//
+// The reference evaluates, for every (pixel, source), 28 Gaussian components and pushes
+// each one through a dense chain rule into a 44 x 44 SensitiveFloat
+// (BivariateNormals.jl:208-571, fsm_util.jl:255-346, elbo_objective.jl:17-327,
+// SensitiveFloats.jl:99-250).  This file computes the same function, reorganised so the
+// per-pixel work is a short FP64 FMA stream with no memory traffic:
+//
+//  * all 14K components of a source share one shape Jacobian up to the scalar nuBar
+//    (GalaxySigmaDerivs returns j*nuBar, t*nuBar: BivariateNormals.jl:396) and one
+//    position Jacobian -J (transform_bvn_ux_derivs!:414), so derivatives are accumulated
+//    in the RAW coordinates y = (x1, x2, Sigma11, Sigma12, Sigma22, theta) with weights
+//    w, w*nuBar, w*nuBar^2 and transformed to (pos, gal_frac_dev, axis_ratio, angle,
+//    radius) ONCE per (source, image) in the epilogue -- not once per component;
+//  * the pixel term depends on the 28 live parameters only through the raw coordinates
+//    and four per-band scalars c = (a1 E_l1, a2 E_l2, a1 E_ll1, a2 E_ll2)
+//    (calculate_G_s!, elbo_objective.jl:62-66), so each thread accumulates the
+//    value / gradient / Hessian of the pixel term in (c, y) space: 1 + 10 + 55 numbers.
+//
+// Mathematically identical to the reference; differs by floating-point reassociation
+// only (parity tolerance 1e-8).
+//
+// Functions are __host__ __device__ so that tests/host_emul can compile this exact
+// arithmetic with g++ and compare it with the oracle on a machine without a GPU.  The
+// shipped library only ever calls them from kernels.
+#ifndef CELESTE_ELBO_MATH_CUH
+#define CELESTE_ELBO_MATH_CUH
+
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define CEL_HD __host__ __device__ __forceinline__
+#else
+#define CEL_HD inline
+#endif
+
+namespace celeste {
+
+constexpr int NPARAM = 44;     // length(CanonicalParams), param_set.jl:107
+constexpr int NLIVE = 28;      // canonical ids 1..28 receive likelihood derivatives (ids.k never does)
+constexpr int NPROTO = 14;     // 8 dev + 6 exp prototype components, light_source_model.jl:45-72
+constexpr int NPROTO_DEV = 8;
+constexpr int MAX_K = 4;       // PSF components supported per patch (reference default psf_K = 2)
+constexpr int COMP_STRIDE = 6; // doubles per component record
+constexpr int MAX_COMPS = NPROTO * MAX_K;
+
+// accumulator layout in (c, y) space.  y order: x1 x2 S11 S12 S22 theta; c order: A1 A2 B1 B2
+constexpr int ACC_VAL = 0, ACC_CNT_ACTIVE = 1, ACC_CNT_INACTIVE = 2;
+constexpr int ACC_G = 3;        // 6: dL/dy
+constexpr int ACC_C1 = 9;       // 4: dL/dc
+constexpr int ACC_HH = 13;      // 21: d2L/dy dy, packed upper triangle row-major (k<=l)
+constexpr int ACC_CC = 34;      // 10: d2L/dc dc, packed upper triangle
+constexpr int ACC_CR = 44;      // 24: d2L/dc dy, [c][k]
+constexpr int NACC_MODE0 = 3, NACC_MODE1 = 13, NACC_MODE2 = 68;
+template <int MODE> struct NAcc { static constexpr int value = MODE == 0 ? NACC_MODE0 : (MODE == 1 ? NACC_MODE1 : NACC_MODE2); };
+CEL_HD constexpr int tri6(int k, int l) { return k * 6 - (k * (k - 1)) / 2 + (l - k); }   // k <= l < 6
+CEL_HD constexpr int tri4(int k, int l) { return k * 4 - (k * (k - 1)) / 2 + (l - k); }   // k <= l < 4
+
+// ---------------------------------------------------------------------------------------------
+// Cubic B-spline (Interpolations.jl BSpline(Cubic(Line())), OnGrid; un-vendored dependency,
+// REQUIRE:21): weights at fractional offset f for taps i-1..i+2, with first/second derivatives.
+template <int MODE>
+CEL_HD void cubic_weights(double f, double* w, double* dw, double* ddw) {
+    const double o = 1.0 - f;
+    const double f2 = f * f, o2 = o * o;
+    w[0] = (1.0 / 6.0) * o2 * o;
+    w[1] = 2.0 / 3.0 - f2 + 0.5 * f2 * f;
+    w[2] = 2.0 / 3.0 - o2 + 0.5 * o2 * o;
+    w[3] = (1.0 / 6.0) * f2 * f;
+    if (MODE >= 1) {
+        dw[0] = -0.5 * o2;
+        dw[1] = f * (1.5 * f - 2.0);
+        dw[2] = o * (2.0 - 1.5 * o);
+        dw[3] = 0.5 * f2;
+    }
+    if (MODE >= 2) {
+        ddw[0] = o;
+        ddw[1] = 3.0 * f - 2.0;
+        ddw[2] = 3.0 * o - 2.0;
+        ddw[3] = f;
+    }
+}
+
+// Star density of fsm_util.jl:225-248 in RAW coordinates: value f0, gradient g0 (2) and
+// Hessian h0 (xx, xy, yy) with respect to the spline ARGUMENT (which moves by -J dpos, the
+// same Jacobian as the galaxy's x: the epilogue applies it).  coefs: padded (n1 x n2) col-major.
+template <int MODE, typename LD>
+CEL_HD void star_eval(LD ld, const double* coefs, int n1, int n2, double ax, double ay, double& f0, double* g0,
+                      double* h0) {
+    const int s1 = n1 - 2, s2 = n2 - 2;
+    int ix = (int)floor(ax);
+    ix = ix < 1 ? 1 : (ix > s1 - 1 ? s1 - 1 : ix);
+    int iy = (int)floor(ay);
+    iy = iy < 1 ? 1 : (iy > s2 - 1 ? s2 - 1 : iy);
+    double wx[4], dwx[4], ddwx[4], wy[4], dwy[4], ddwy[4];
+    cubic_weights<MODE>(ax - ix, wx, dwx, ddwx);
+    cubic_weights<MODE>(ay - iy, wy, dwy, ddwy);
+    double v = 0, gx = 0, gy = 0, hxx = 0, hxy = 0, hyy = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        const double* col = coefs + (size_t)(iy - 1 + b) * n1 + (ix - 1);
+        const double c0 = ld(col), c1 = ld(col + 1), c2 = ld(col + 2), c3 = ld(col + 3);
+        const double r = wx[0] * c0 + wx[1] * c1 + wx[2] * c2 + wx[3] * c3;
+        v += wy[b] * r;
+        if (MODE >= 1) {
+            const double rd = dwx[0] * c0 + dwx[1] * c1 + dwx[2] * c2 + dwx[3] * c3;
+            gx += wy[b] * rd;
+            gy += dwy[b] * r;
+            if (MODE >= 2) {
+                const double rdd = ddwx[0] * c0 + ddwx[1] * c1 + ddwx[2] * c2 + ddwx[3] * c3;
+                hxx += wy[b] * rdd;
+                hxy += dwy[b] * rd;
+                hyy += ddwy[b] * r;
+            }
+        }
+    }
+    // softpluslikeinv, fsm_util.jl:222
+    if (v < 0) {
+        const double e = 1e-3 * exp(v);
+        f0 = e;
+        if (MODE >= 1) {
+            g0[0] = e * gx;
+            g0[1] = e * gy;
+        }
+        if (MODE >= 2) {
+            h0[0] = e * (gx * gx + hxx);
+            h0[1] = e * (gx * gy + hxy);
+            h0[2] = e * (gy * gy + hyy);
+        }
+    } else {
+        f0 = 1e-3 * (v + 1.0);
+        if (MODE >= 1) {
+            g0[0] = 1e-3 * gx;
+            g0[1] = 1e-3 * gy;
+        }
+        if (MODE >= 2) {
+            h0[0] = 1e-3 * hxx;
+            h0[1] = 1e-3 * hxy;
+            h0[2] = 1e-3 * hyy;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Galaxy mixture (populate_gal_fsm! fsm_util.jl:194-219 + accum_galaxy_pos!:255-346) in raw
+// coordinates.  Component record: mu1 mu2 L11 L12 L22 z   (z excludes gal_frac_dev).
+//   r[6]   = d f1 / d(x1, x2, S11, S12, S22, theta)
+//   R[21]  = d2 f1 / dy dy packed upper triangle (theta-theta entry is identically 0)
+struct GalRaw {
+    double f;
+    double r[6];
+    double R[21];
+};
+
+template <int MODE, typename LD>
+CEL_HD void gal_eval(LD ld, const double* comps, int K, const double* nu /*14*/, double theta, double hx, double wy,
+                     GalRaw& o) {
+    double f = 0, ft = 0;
+    double ax1 = 0, ax2 = 0, tx1 = 0, tx2 = 0;           // sum w p, sum wd p
+    double u1 = 0, u2 = 0, u3 = 0;                       // sum w gS          (xx block: heat-equation identity)
+    double as1 = 0, as2 = 0, as3 = 0;                    // sum w nu gS
+    double ts1 = 0, ts2 = 0, ts3 = 0;                    // sum wd nu gS
+    double xs11 = 0, xs12 = 0, xs13 = 0, xs21 = 0, xs22 = 0, xs23 = 0;   // sum w nu (HxS + gx gS')
+    double ss11 = 0, ss12 = 0, ss13 = 0, ss22 = 0, ss23 = 0, ss33 = 0;   // sum w nu^2 (HSS + gS gS')
+    const int ncomp = NPROTO * K;
+    const int ndev = NPROTO_DEV * K;
+    for (int c = 0; c < ncomp; ++c) {
+        const double* cp = comps + c * COMP_STRIDE;
+        const double mu1 = ld(cp), mu2 = ld(cp + 1), l11 = ld(cp + 2), l12 = ld(cp + 3), l22 = ld(cp + 4),
+                     z = ld(cp + 5);
+        const bool dev = c < ndev;
+        const double thc = dev ? theta : 1.0 - theta;
+        const double d1 = hx - mu1, d2 = wy - mu2;
+        const double p1 = l11 * d1 + l12 * d2;
+        const double p2 = l12 * d1 + l22 * d2;
+        const double q = d1 * p1 + d2 * p2;
+        const double fp = z * exp(-0.5 * q);     // f_pre, BivariateNormals.jl:219
+        const double w = thc * fp;
+        f += w;
+        if (MODE >= 1) {
+            const double nuc = nu[c / K];
+            const double wd = dev ? fp : -fp;    // gal_frac_dev_dir * f_pre, fsm_util.jl:291
+            ft += wd;
+            ax1 += w * p1;
+            ax2 += w * p2;
+            const double a = p1 * p1, b = p1 * p2, cc = p2 * p2;
+            const double g1 = 0.5 * a - 0.5 * l11;   // bvn_sig_d, BivariateNormals.jl:267-272
+            const double g2 = b - l12;
+            const double g3 = 0.5 * cc - 0.5 * l22;
+            const double wn = w * nuc;
+            as1 += wn * g1;
+            as2 += wn * g2;
+            as3 += wn * g3;
+            if (MODE >= 2) {
+                const double wdn = wd * nuc;
+                tx1 += wd * p1;
+                tx2 += wd * p2;
+                ts1 += wdn * g1;
+                ts2 += wdn * g2;
+                ts3 += wdn * g3;
+                u1 += w * g1;
+                u2 += w * g2;
+                u3 += w * g3;
+                // bvn_xsig_h (BivariateNormals.jl:310-316) + g_x g_S', with g_x = -p
+                xs11 += wn * (p1 * (l11 - g1));
+                xs12 += wn * (p1 * (l12 - g2) + p2 * l11);
+                xs13 += wn * (p2 * l12 - p1 * g3);
+                xs21 += wn * (p1 * l12 - p2 * g1);
+                xs22 += wn * (p2 * (l12 - g2) + p1 * l22);
+                xs23 += wn * (p2 * (l22 - g3));
+                // bvn_sigsig_h (BivariateNormals.jl:293-306, dsiginv_dsig:168-183) + g_S g_S'
+                const double wnn = wn * nuc;
+                ss11 += wnn * (l11 * (0.5 * l11 - a) + g1 * g1);
+                ss12 += wnn * (l12 * (l11 - a) - b * l11 + g1 * g2);
+                ss13 += wnn * (l12 * (0.5 * l12 - b) + g1 * g3);
+                ss22 += wnn * (l22 * (l11 - a) + l12 * (l12 - 2.0 * b) - cc * l11 + g2 * g2);
+                ss23 += wnn * (l12 * (l22 - cc) - b * l22 + g2 * g3);
+                ss33 += wnn * (l22 * (0.5 * l22 - cc) + g3 * g3);
+            }
+        }
+    }
+    o.f = f;
+    if (MODE >= 1) {
+        o.r[0] = -ax1;
+        o.r[1] = -ax2;
+        o.r[2] = as1;
+        o.r[3] = as2;
+        o.r[4] = as3;
+        o.r[5] = ft;
+    }
+    if (MODE >= 2) {
+        double* R = o.R;
+        // H_xx + g_x g_x' = (p1^2 - L11, p1 p2 - L12, p2^2 - L22) = (2 g1, g2, 2 g3)
+        R[tri6(0, 0)] = 2.0 * u1;
+        R[tri6(0, 1)] = u2;
+        R[tri6(1, 1)] = 2.0 * u3;
+        R[tri6(0, 2)] = xs11;
+        R[tri6(0, 3)] = xs12;
+        R[tri6(0, 4)] = xs13;
+        R[tri6(1, 2)] = xs21;
+        R[tri6(1, 3)] = xs22;
+        R[tri6(1, 4)] = xs23;
+        R[tri6(0, 5)] = -tx1;
+        R[tri6(1, 5)] = -tx2;
+        R[tri6(2, 2)] = ss11;
+        R[tri6(2, 3)] = ss12;
+        R[tri6(2, 4)] = ss13;
+        R[tri6(3, 3)] = ss22;
+        R[tri6(3, 4)] = ss23;
+        R[tri6(4, 4)] = ss33;
+        R[tri6(2, 5)] = ts1;
+        R[tri6(3, 5)] = ts2;
+        R[tri6(4, 5)] = ts3;
+        R[tri6(5, 5)] = 0.0;
+    }
+}
+
+// value-only mixture for a neighbour (is_active_source == false, fsm_util.jl:265)
+template <typename LD>
+CEL_HD double gal_value(LD ld, const double* comps, int K, double theta, double hx, double wy) {
+    double fd = 0, fe = 0;
+    const int ncomp = NPROTO * K;
+    const int ndev = NPROTO_DEV * K;
+    for (int c = 0; c < ncomp; ++c) {
+        const double* cp = comps + c * COMP_STRIDE;
+        const double mu1 = ld(cp), mu2 = ld(cp + 1), l11 = ld(cp + 2), l12 = ld(cp + 3), l22 = ld(cp + 4),
+                     z = ld(cp + 5);
+        const double d1 = hx - mu1, d2 = wy - mu2;
+        const double p1 = l11 * d1 + l12 * d2;
+        const double p2 = l12 * d1 + l22 * d2;
+        const double fp = z * exp(-0.5 * (d1 * p1 + d2 * p2));
+        if (c < ndev)
+            fd += fp;
+        else
+            fe += fp;
+    }
+    return theta * fd + (1.0 - theta) * fe;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pixel term (add_elbo_log_term! elbo_objective.jl:274-327 + add_scaled_sfs! :383-385 + :391)
+// as a function of z = (A1, A2, B1, B2, f0, f1), and its accumulation in (c, y) space.
+//   E  = Ebg + A1 f0 + A2 f1
+//   V  = Vbg + B1 f0^2 + B2 f1^2 - (A1 f0 + A2 f1)^2         (calculate_G_s! :204)
+//   L  = x (log E - V / (2 E^2)) - iota E + pixconst,  pixconst = x log(iota) - lgamma(x + 1)
+struct PixelConsts {
+    double x, iota, pixconst;
+};
+
+// acc: per-thread accumulator slots, element a at acc[a * stride]
+template <int MODE>
+CEL_HD void pixel_accumulate(double* acc, int stride, const PixelConsts& pc, double Ebg, double Vbg, bool covered,
+                             const double* cb /*A1 A2 B1 B2*/, double f0, const double* g0, const double* h0,
+                             const GalRaw& gal) {
+    const double A1 = cb[0], A2 = cb[1], B1 = cb[2], B2 = cb[3];
+    const double f1 = gal.f;
+    const double m = covered ? (A1 * f0 + A2 * f1) : 0.0;
+    const double E = Ebg + m;
+    const double V = covered ? (Vbg + B1 * f0 * f0 + B2 * f1 * f1 - m * m) : Vbg;
+    const double iE = 1.0 / E;
+    const double iE2 = iE * iE;
+    acc[ACC_VAL * stride] += pc.x * (log(E) - 0.5 * V * iE2) - pc.iota * E + pc.pixconst;
+    if (MODE == 0 || !covered) return;
+
+    const double gE = pc.x * (iE + V * iE2 * iE) - pc.iota;     // combine_grad[2] * x - iota
+    const double gV = -0.5 * pc.x * iE2;                         // combine_grad[1] * x
+    const double Ez[6] = {f0, f1, 0.0, 0.0, A1, A2};
+    const double Vz[6] = {-2.0 * m * f0, -2.0 * m * f1, f0 * f0, f1 * f1, 2.0 * (B1 * f0 - m * A1),
+                          2.0 * (B2 * f1 - m * A2)};
+    double Lz[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) Lz[i] = gE * Ez[i] + gV * Vz[i];
+
+    // first order: G[k] = L_f1 r[k] + L_f0 g0[k];   C1[c] = L_c
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        double g = Lz[5] * gal.r[k];
+        if (k < 2) g += Lz[4] * g0[k];
+        acc[(ACC_G + k) * stride] += g;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[(ACC_C1 + c) * stride] += Lz[c];
+    if (MODE == 1) return;
+
+    const double LEE = -pc.x * (iE2 + 3.0 * V * iE2 * iE2);      // combine_hess[2,2] * x
+    const double LEV = pc.x * iE2 * iE;                           // combine_hess[1,2] * x
+    double Lzz[6][6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = i; j < 6; ++j) {
+            double ezz = 0.0, bpart = 0.0;
+            if ((i == 0 && j == 4) || (i == 1 && j == 5)) ezz = 1.0;
+            if (i == 2 && j == 4) bpart = 2.0 * f0;
+            if (i == 4 && j == 4) bpart = 2.0 * B1;
+            if (i == 3 && j == 5) bpart = 2.0 * f1;
+            if (i == 5 && j == 5) bpart = 2.0 * B2;
+            const double vzz = -2.0 * (Ez[i] * Ez[j] + m * ezz) + bpart;
+            Lzz[i][j] = LEE * Ez[i] * Ez[j] + LEV * (Ez[i] * Vz[j] + Vz[i] * Ez[j]) + gE * ezz + gV * vzz;
+        }
+    // HH[k][l] = L_f1 R[k][l] + L_f1f1 r_k r_l + (x block) L_f0 h0 + L_f0f0 g0 g0' + L_f0f1 (g0 r' + r g0')
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+#pragma unroll
+        for (int l = k; l < 6; ++l) {
+            double v = Lz[5] * gal.R[tri6(k, l)] + Lzz[5][5] * gal.r[k] * gal.r[l];
+            if (k < 2) v += Lzz[4][5] * g0[k] * gal.r[l];
+            if (l < 2) {
+                v += Lzz[4][5] * gal.r[k] * g0[l];
+                v += Lz[4] * h0[k + l] + Lzz[4][4] * g0[k] * g0[l];   // h0 packed xx, xy, yy
+            }
+            acc[(ACC_HH + tri6(k, l)) * stride] += v;
+        }
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int d = c; d < 4; ++d) acc[(ACC_CC + tri4(c, d)) * stride] += Lzz[c][d];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            double v = Lzz[c][5] * gal.r[k];
+            if (k < 2) v += Lzz[c][4] * g0[k];
+            acc[(ACC_CR + c * 6 + k) * stride] += v;
+        }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-(source, image) mixture set-up: load_bvn_mixtures! (fsm_util.jl:111-169), GalaxyCacheComponent
+// (:37-65), BvnComponent (BivariateNormals.jl:151-191), get_bvn_cov (:29-43); one call per component.
+// psf7: alphaBar, xiBar[2], tauBar col-major (4).  Writes a 6-double component record.
+CEL_HD void make_component(const double* psf7, double eta, double nuBar, double m1, double m2, double rho, double phi,
+                           double sigma, double* out) {
+    const double cp = cos(phi), sp = sin(phi);
+    const double ab_term = rho * rho - 1.0;
+    const double ss = sigma * sigma;
+    const double off = -ss * cp * sp * ab_term;
+    const double x11 = ss * (1.0 + ab_term * (sp * sp));
+    const double x22 = ss * (1.0 + ab_term * (cp * cp));
+    const double v11 = psf7[3] + nuBar * x11;
+    const double v21 = psf7[4] + nuBar * off;
+    const double v12 = psf7[5] + nuBar * off;
+    const double v22 = psf7[6] + nuBar * x22;
+    const double det = v11 * v22 - v12 * v21;
+    const double idet = 1.0 / det;
+    out[0] = psf7[1] + m1;
+    out[1] = psf7[2] + m2;
+    out[2] = v22 * idet;
+    out[3] = -v12 * idet;
+    out[4] = v11 * idet;
+    out[5] = (psf7[0] * eta) * (1.0 / (sqrt(det) * 6.283185307179586476925286766559));
+}
+
+// GalaxySigmaDerivs (BivariateNormals.jl:346-397) with nuBar = 1: J0[k][j] = dSigma_k/dshape_j,
+// T0[k][j][l] = d2 Sigma_k / dshape_j dshape_l, shape = (axis_ratio, angle, radius).
+CEL_HD void sigma_derivs(double rho, double phi, double sigma, double J0[3][3], double T0[3][3][3]) {
+    const double c = cos(phi), s = sin(phi);
+    const double cs = c * s, s2 = s * s, c2 = c * c;
+    const double rr = sigma * sigma;
+    const double ab_term = rho * rho - 1.0;
+    const double X11 = rr * (1.0 + ab_term * s2), X12 = -rr * cs * ab_term, X22 = rr * (1.0 + ab_term * c2);
+    const double a1 = 2.0 * rho * rr;
+    J0[0][0] = a1 * s2;
+    J0[1][0] = -a1 * cs;
+    J0[2][0] = a1 * c2;
+    const double a2 = rr * ab_term;
+    J0[0][1] = a2 * (2.0 * cs);
+    J0[1][1] = a2 * (s2 - c2);
+    J0[2][1] = a2 * (-2.0 * cs);
+    J0[0][2] = 2.0 * X11 / sigma;
+    J0[1][2] = 2.0 * X12 / sigma;
+    J0[2][2] = 2.0 * X22 / sigma;
+    const double t2 = 2.0 * rr;
+    T0[0][0][0] = s2 * t2;
+    T0[1][0][0] = -cs * t2;
+    T0[2][0][0] = c2 * t2;
+    const double t3 = t2 * rho;
+    T0[0][1][0] = T0[0][0][1] = 2.0 * cs * t3;
+    T0[1][1][0] = T0[1][0][1] = (s2 - c2) * t3;
+    T0[2][1][0] = T0[2][0][1] = -2.0 * cs * t3;
+    const double t4 = t2 * ab_term;
+    T0[0][1][1] = (c2 - s2) * t4;
+    T0[1][1][1] = 2.0 * cs * t4;
+    T0[2][1][1] = (s2 - c2) * t4;
+    for (int k = 0; k < 3; ++k) {
+        T0[k][2][0] = T0[k][0][2] = 2.0 * J0[k][0] / sigma;
+        T0[k][2][1] = T0[k][1][2] = 2.0 * J0[k][1] / sigma;
+    }
+    T0[0][2][2] = 2.0 * X11 / rr;
+    T0[1][2][2] = 2.0 * X12 / rr;
+    T0[2][2][2] = 2.0 * X22 / rr;
+}
+
+// Source brightness (source_brightness.jl:27-202): E_l[b][i] = exp(kappa_b . beta_i), E_ll[b][i] =
+// exp(lambda_b . beta_i) over beta = (flux_loc, flux_scale, color_mean 1..4, color_var 1..4).
+// Every derivative the reference builds with multiply_sfs! is E * kappa (x) kappa.
+CEL_HD void band_coefs(int b /*0..4*/, double kappa[10], double lambda[10]) {
+    for (int k = 0; k < 10; ++k) kappa[k] = lambda[k] = 0.0;
+    kappa[0] = 1.0;
+    kappa[1] = 0.5;
+    lambda[0] = 2.0;
+    lambda[1] = 2.0;
+    // colours: band 4 uses c3; band 5 c3,c4; band 2 uses -c2; band 1 uses -c2,-c1
+    const int use[5][4] = {{-1, -1, 0, 0}, {0, -1, 0, 0}, {0, 0, 0, 0}, {0, 0, 1, 0}, {0, 0, 1, 1}};
+    for (int m = 0; m < 4; ++m) {
+        const int u = use[b][m];
+        if (u != 0) {
+            kappa[2 + m] = (double)u;
+            kappa[6 + m] = 0.5;
+            lambda[2 + m] = 2.0 * u;
+            lambda[6 + m] = 2.0;
+        }
+    }
+}
+// canonical (0-based) index of brightness parameter k (0..9) of type i: brightness_standard_alignment
+CEL_HD int bright_id(int i, int k) {
+    return k == 0 ? 6 + i : (k == 1 ? 8 + i : (k < 6 ? 10 + (k - 2) + 4 * i : 18 + (k - 6) + 4 * i));
+}
+CEL_HD void brightness_values(const double* vs, double El[2][5], double Ell[2][5]) {
+    for (int i = 0; i < 2; ++i) {
+        double beta[10];
+        for (int k = 0; k < 10; ++k) beta[k] = vs[bright_id(i, k)];
+        for (int b = 0; b < 5; ++b) {
+            double ka[10], la[10];
+            band_coefs(b, ka, la);
+            double s1 = 0, s2 = 0;
+            for (int k = 0; k < 10; ++k) {
+                s1 += ka[k] * beta[k];
+                s2 += la[k] * beta[k];
+            }
+            El[i][b] = exp(s1);
+            Ell[i][b] = exp(s2);
+        }
+    }
+}
+
+}  // namespace celeste
+#endif

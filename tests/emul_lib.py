@@ -1,0 +1,47 @@
+"""ctypes binding of tests/host_emul/libceleste_emul.so: the product's kernel source run under a
+host emulation of the CUDA execution model (test infrastructure; lets kernel logic be checked
+against the oracle without a GPU)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from celeste_jl_b200.flatten import FlatImages, FlatPatches, csr_tasks, out_sizes
+
+DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_emul")
+SO = os.path.join(DIR, "libceleste_emul.so")
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is None:
+        subprocess.check_call(["make", "-C", DIR, "-s"])
+        _lib = C.CDLL(SO)
+        vp, i32 = C.c_void_p, C.c_int32
+        _lib.emul_elbo_batch.argtypes = [i32, vp, i32, vp, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, i32]
+    return _lib
+
+
+class EmulField:
+    def __init__(self, images, patches):
+        self.fi = FlatImages(images)
+        self.fp = FlatPatches(patches)
+
+    def elbo_batch(self, tasks, mode=2, chunk_pixels=512):
+        task_ptr, src, active_ptr, act, vp = csr_tasks(tasks)
+        n = len(tasks)
+        nd, nh = out_sizes(active_ptr)
+        v = np.zeros(n)
+        d = np.zeros(max(nd, 1))
+        h = np.zeros(max(nh, 1))
+        counters = np.zeros(2 * n, dtype=np.int64)
+        flags = np.zeros(n, dtype=np.int32)
+        p = lambda a: a.ctypes.data if a.size else None
+        st = load().emul_elbo_batch(self.fi.N, C.addressof(self.fi.arr), self.fp.S_tot, C.addressof(self.fp.arr),
+                                    n, p(task_ptr), p(src), p(active_ptr), p(act), p(vp), mode,
+                                    p(v), p(d), p(h), p(counters), p(flags), chunk_pixels)
+        assert st == 0, st
+        return {"v": v, "d": d[:nd] if mode >= 1 else d[:0], "h": h[:nh] if mode >= 2 else h[:0],
+                "counters": counters.reshape(n, 2), "flags": flags, "active_ptr": active_ptr}

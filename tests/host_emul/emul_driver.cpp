@@ -1,0 +1,124 @@
+// emul_driver.cpp -- TEST INFRASTRUCTURE.  Runs the product's kernel source
+// (celeste.jl_b200/csrc/celeste_kernels.cuh) under the host emulation layer with the same
+// launch sequence as celeste_abi.cu (prep -> setup -> pixel -> epilogue), so kernel logic can
+// be compared with the oracle without a GPU.  Built by tests/host_emul/Makefile; never shipped.
+#include "cuda_emul.h"
+
+#include "../../include/celeste_cuda.h"
+#include "../../celeste.jl_b200/csrc/celeste_kernels.cuh"
+
+using namespace celeste;
+
+namespace {
+void galaxy_prototypes(double eta[NPROTO], double nu[NPROTO]) {
+    const double dev_amp[8] = {4.26347652e-2, 2.40127183e-1, 6.85907632e-1, 1.51937350,
+                               2.83627243,    4.46467501,    5.72440830,    5.60989349};
+    const double dev_var[8] = {2.23759216e-4, 1.00220099e-3, 4.18731126e-3, 1.69432589e-2,
+                               6.84850479e-2, 2.87207080e-1, 1.33320254,    8.40215071};
+    const double exp_amp[6] = {2.34853813e-3, 3.07995260e-2, 2.23364214e-1, 1.17949102, 4.33873750, 5.99820770};
+    const double exp_var[6] = {1.20078965e-3, 8.84526493e-3, 3.91463084e-2,
+                               1.39976817e-1, 4.60962500e-1, 1.50159566};
+    double sd = 0, se = 0;
+    for (double a : dev_amp) sd += a;
+    for (double a : exp_amp) se += a;
+    for (int j = 0; j < 8; ++j) {
+        eta[j] = dev_amp[j] / sd;
+        nu[j] = dev_var[j] / (1.078031 * 1.078031);
+    }
+    for (int j = 0; j < 6; ++j) {
+        eta[8 + j] = exp_amp[j] / se;
+        nu[8 + j] = exp_var[j] / (0.928896 * 0.928896);
+    }
+}
+
+template <int MODE>
+void run(const PlanDev& pd, const FieldDev& fd, int n_blocks, int chunk_pixels, const double* vp, double* v, double* d,
+         double* h, long long* counters, int* flags) {
+    const size_t smem = ((size_t)NAcc<MODE>::value * PIX_THREADS + (size_t)MAX_COMPS * COMP_STRIDE) * sizeof(double);
+    cuda_emul::launch(setup_kernel, 2, 64, 0, pd, fd, vp);
+    if (n_blocks > 0) cuda_emul::launch(pixel_kernel<MODE>, n_blocks, PIX_THREADS, smem, pd, fd, chunk_pixels);
+    cuda_emul::launch(epilogue_kernel<MODE>, pd.n_tasks, EPI_THREADS, 0, pd, fd, vp, v, d, h, counters, flags);
+}
+}  // namespace
+
+extern "C" int emul_elbo_batch(int32_t N, const celeste_image* imgs, int32_t S_tot, const celeste_patch* patches,
+                               int32_t n_tasks, const int32_t* task_ptr, const int32_t* source_ids,
+                               const int32_t* active_ptr, const int32_t* active_idx, const double* vp, int32_t mode,
+                               double* v, double* d, double* h, int64_t* counters, int32_t* flags,
+                               int32_t chunk_pixels) {
+    galaxy_prototypes(c_proto_eta, c_proto_nu);
+    std::vector<ImageDev> images(N);
+    std::vector<std::vector<double>> pixconst(N);
+    for (int n = 0; n < N; ++n) {
+        const celeste_image& im = imgs[n];
+        pixconst[n].resize((size_t)im.H * im.W);
+        cuda_emul::launch(prep_image_kernel, 2, 32, 0, im.H, im.W, im.pixels, im.nelec_per_nmgy, im.log_iota,
+                          pixconst[n].data());
+        images[n] = ImageDev{im.H, im.W, im.band, im.pixels, im.sky, im.nelec_per_nmgy, pixconst[n].data()};
+    }
+    std::vector<PatchDev> pdv((size_t)S_tot * N);
+    for (size_t i = 0; i < pdv.size(); ++i) {
+        const celeste_patch& q = patches[i];
+        PatchDev p;
+        p.off_h = (int)q.bitmap_offset[0];
+        p.off_w = (int)q.bitmap_offset[1];
+        p.H2 = q.H2;
+        p.W2 = q.W2;
+        p.bitmap = q.active_pixel_bitmap;
+        for (int k = 0; k < 4; ++k) p.J[k] = q.wcs_jacobian[k];
+        p.wc[0] = q.world_center[0];
+        p.wc[1] = q.world_center[1];
+        p.pc[0] = q.pixel_center[0];
+        p.pc[1] = q.pixel_center[1];
+        p.K = q.K;
+        p.psf = q.psf;
+        p.coefs = q.itp_coefs;
+        p.n1 = q.itp_dims[0];
+        p.n2 = q.itp_dims[1];
+        pdv[i] = p;
+    }
+    const int n_slots = task_ptr[n_tasks];
+    std::vector<int> src_row(n_slots), act_slot(n_tasks), chunk_ptr((size_t)n_tasks * N + 1, 0);
+    std::vector<int2> blockmap;
+    for (int t = 0; t < n_tasks; ++t) {
+        if (active_ptr[t + 1] - active_ptr[t] != 1) return CELESTE_ERR_UNSUPPORTED;
+        act_slot[t] = task_ptr[t] + active_idx[active_ptr[t]] - 1;
+        for (int s = task_ptr[t]; s < task_ptr[t + 1]; ++s) src_row[s] = source_ids[s] - 1;
+    }
+    for (int t = 0; t < n_tasks; ++t)
+        for (int n = 0; n < N; ++n) {
+            const PatchDev& pa = pdv[(size_t)src_row[act_slot[t]] + (size_t)n * S_tot];
+            const long npix = (long)pa.H2 * pa.W2;
+            const int nchunk = (int)((npix + chunk_pixels - 1) / chunk_pixels);
+            const int tn = t * N + n;
+            chunk_ptr[tn + 1] = chunk_ptr[tn] + nchunk;
+            for (int c = 0; c < nchunk; ++c) blockmap.push_back(make_int2(tn, c));
+        }
+    std::vector<int> tp(task_ptr, task_ptr + n_tasks + 1);
+    std::vector<double> slotimg((size_t)n_slots * N * SLOTIMG_STRIDE), slotbr((size_t)n_slots * SLOTBR_STRIDE),
+        partials(blockmap.size() * NACC_MODE2 + 1);
+    PlanDev pd;
+    pd.n_tasks = n_tasks;
+    pd.N = N;
+    pd.S_tot = S_tot;
+    pd.n_slots = n_slots;
+    pd.task_ptr = tp.data();
+    pd.src_row = src_row.data();
+    pd.act_slot = act_slot.data();
+    pd.blockmap = blockmap.data();
+    pd.chunk_ptr = chunk_ptr.data();
+    pd.slotimg = slotimg.data();
+    pd.slotbr = slotbr.data();
+    pd.partials = partials.data();
+    FieldDev fd{images.data(), pdv.data()};
+    std::vector<long long> cnt(2 * (size_t)n_tasks);
+    const int nb = (int)blockmap.size();
+    if (mode == 0)
+        run<0>(pd, fd, nb, chunk_pixels, vp, v, d, h, cnt.data(), flags);
+    else if (mode == 1)
+        run<1>(pd, fd, nb, chunk_pixels, vp, v, d, h, cnt.data(), flags);
+    else
+        run<2>(pd, fd, nb, chunk_pixels, vp, v, d, h, cnt.data(), flags);
+    for (size_t i = 0; i < cnt.size(); ++i) counters[i] = cnt[i];
+    return 0;
+}
