@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""bench.py -- sources/sec of the ELBO(+gradient) hot path on synthetic 5-band SDSS-shaped fields.
+
+    python bench.py --gpus N --steps K --warmup W            # CUDA library (one rank per GPU; torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the CPU path (oracle port), rank 0 only
+
+Workload (BASELINE.json configs[3]): a synthetic stripe of F fields x 1000 sources, 5 bands, 2048 x 1489
+px/band; every source is one (ElboArgs, vp) task = the source + its find_neighbors neighbours, active_sources
+= [1] (ParallelRun.jl:236-253).  The stripe's tasks are sharded round-robin-by-cost across the N ranks (no
+data-path collective): total work is fixed => "scaling": "strong".  One step = one evaluation
+of every task (ELBO + gradient; the Hessian mode is measured beside it and reported under "hessian").
+Inputs are larger than L2 (each rank reads > 126 MB of distinct pixel/sky/constant planes per step).
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# ALGORITHMIC flop per pixel-visit (the contract figure of roofline.achieved)
+F_ACTIVE = {0: 570.0, 1: 2600.0, 2: 23700.0}
+F_INACTIVE = 548.0
+BYTES_PER_VISIT = 20.0      # f32 pixel + f32 sky + f64 constant + u8 mask + amortised per-source tables
+NOMINAL_FP64_TFLOPS = 37.0   # HGX B200 datasheet, 296 TF / 8
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--fields", type=int, default=10, help="fields in the stripe (1000 sources each)")
+    ap.add_argument("--sources-per-field", type=int, default=1000)
+    ap.add_argument("--cpu-sample", type=int, default=384, help="tasks per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-hessian", action="store_true")
+    return ap.parse_args()
+
+
+def build_stripe(n_fields, n_sources, device):
+    from celeste_jl_b200 import synthetic
+    return [synthetic.FieldDataset(n_sources, H=2048, W=1489, seed=42 + f, pixel_seed=1 + f, device=device)
+            for f in range(n_fields)]
+
+
+def shard_tasks(ds, rank, world):
+    """ParallelRun's cost model (sum of active pixels, ParallelRun.jl:45-56): tasks sorted by cost and dealt
+    greedily to the least-loaded rank."""
+    cost = np.array([sum(int(p.active_pixel_bitmap.sum()) for p in ds.patches[s, :]) for s in range(len(ds.catalog))])
+    order = np.argsort(-cost, kind="stable")
+    load = np.zeros(world)
+    mine = []
+    for s in order:
+        r = int(np.argmin(load))
+        load[r] += cost[s]
+        if r == rank:
+            mine.append(int(s))
+    return sorted(mine)
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=open(self.path, "w"),
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        try:
+            rows = [r.split(",") for r in open(self.path).read().strip().splitlines() if r.strip()]
+            sm = [float(r[1]) for r in rows]
+            out["samples"] = len(sm)
+            if sm:
+                out["sm_mhz"] = float(np.median(sm))
+                out["sm_max_mhz"] = float(rows[0][2])
+                out["power_w_max"] = max(float(r[3]) for r in rows)
+                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                for k, nm in enumerate(names):
+                    if any(r[5 + k].strip().lower().startswith("active") for r in rows):
+                        out["reasons"].append(nm)
+        except Exception as e:   # clocks are evidence, never fatal
+            out["error"] = str(e)
+        finally:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+        return out
+
+
+def load_oracle_for_timing():
+    """CPU baseline library: a -march=native build of oracle/ on this box when g++ is present (written to a temp
+    dir), else the portable prebuilt one.  This is the ONLY place bench.py executes oracle/."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    try:
+        out = os.path.join(tempfile.mkdtemp(prefix="celeste_oracle_"), "libceleste_oracle_native.so")
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-s", "native", f"OUT={out}"],
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        return oracle_lib, oracle_lib.load(out), "native"
+    except Exception:
+        return oracle_lib, oracle_lib.load(), "portable"
+
+
+def cpu_leg(ds, sample, mode, steps, warmup):
+    """Time the oracle (the reference's as-written algorithm, multithreaded over sources with a shared counter
+    like one_node_single_infer) on `sample` tasks of field 0, all host cores."""
+    oracle_lib, lib, build = load_oracle_for_timing()
+    cores = os.cpu_count() or 1
+    rows, act = ds.tasks(range(min(sample, len(ds.catalog))))
+    from celeste_jl_b200.flatten import csr_tasks
+    tasks = [(r, a, np.stack([ds.vp[i - 1] for i in r], axis=1)) for r, a in zip(rows, act)]
+    csr = csr_tasks(tasks)
+    of = oracle_lib.OracleField(ds.images, ds.patches, lib=lib)
+    for _ in range(max(1, min(warmup, 1))):
+        of.elbo_csr(*csr, mode=mode, n_threads=cores)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        out = of.elbo_csr(*csr, mode=mode, n_threads=cores)
+    dt = (time.perf_counter() - t0) / steps
+    visits = int(out["counters"].sum())
+    return {"value": len(tasks) / dt, "unit": "sources/s", "cores": cores, "kind": "port",
+            "sample": f"{len(tasks)} tasks of field 0 per step ({visits} pixel-visits), mode={'grad' if mode == 1 else 'hess'}, "
+                      f"oracle build={build}, {steps} steps",
+            "ms_per_step": dt * 1e3, "pixel_visits_per_s": visits / dt}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = (f"synthetic stripe: {args.fields} fields x {args.sources_per_field} sources, 5 bands, 2048x1489 px/band, "
+                f"K=2 PSF, catalog patches (radius<=25), find_neighbors tasks, Sa=1")
+    config = {"workload": workload, "mode": "ELBO+grad (mode 1); Hessian mode reported under 'hessian'",
+              "sharding": f"tasks dealt by active-pixel cost to {world} rank(s), no collective on the data path",
+              "l2": "inputs larger than L2 (no flush)", "fields": args.fields,
+              "sources": args.fields * args.sources_per_field}
+
+    if args.impl == "reference":
+        # reference arm: the reference's CPU algorithm (oracle port) on the box's host cores; rank 0 only
+        if rank != 0:
+            return
+        from celeste_jl_b200 import synthetic
+        ds = synthetic.FieldDataset(args.sources_per_field, H=2048, W=1489, seed=42, pixel_seed=1, device="cpu")
+        leg = cpu_leg(ds, args.cpu_sample, 1, args.steps, args.warmup)
+        line = {"impl": "reference", "metric": "sources/sec (ELBO+grad)", "value": leg["value"], "unit": "sources/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": leg["ms_per_step"],
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": config, "cpu_baseline": leg,
+                "e2e": {"value": leg["value"], "unit": "sources/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py --impl cuda needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import celeste_jl_b200 as cj
+    from celeste_jl_b200 import _lib
+
+    stripe = build_stripe(args.fields, args.sources_per_field, device=str(dev))
+    fields, plans, vps, n_tasks_total = [], [], [], 0
+    for ds in stripe:
+        mine = shard_tasks(ds, rank, world)
+        field = cj.DeviceField(ds.images, ds.patches, device=local_rank)
+        rows, act = ds.tasks(mine)
+        plan = field.make_plan(rows, act)
+        fields.append(field)
+        plans.append(plan)
+        vps.append(ds.vp_flat(rows))
+        n_tasks_total += len(mine)
+    stream = torch.cuda.current_stream()
+
+    # device-resident buffers (value) and pinned host buffers (e2e)
+    dev_bufs, host_bufs = [], []
+    for plan, vp in zip(plans, vps):
+        n = plan.n_tasks
+        dev_bufs.append({"vp": torch.from_numpy(vp).to(dev), "v": torch.zeros(n, dtype=torch.float64, device=dev),
+                         "d": torch.zeros(n * 44, dtype=torch.float64, device=dev),
+                         "h": torch.zeros(n * 44 * 44, dtype=torch.float64, device=dev),
+                         "c": torch.zeros(2 * n, dtype=torch.int64, device=dev),
+                         "f": torch.zeros(n, dtype=torch.int32, device=dev)})
+        hb = {"vp": torch.from_numpy(vp).pin_memory(), "v": torch.zeros(n, dtype=torch.float64).pin_memory(),
+              "d": torch.zeros(n * 44, dtype=torch.float64).pin_memory(),
+              "h": torch.zeros(n * 44 * 44, dtype=torch.float64).pin_memory(),
+              "counters": torch.zeros(2 * n, dtype=torch.int64).pin_memory(),
+              "flags": torch.zeros(n, dtype=torch.int32).pin_memory()}
+        host_bufs.append(hb)
+
+    def step_device(mode):
+        for plan, b in zip(plans, dev_bufs):
+            plan.run_device(b["vp"].data_ptr(), mode, b["v"].data_ptr(), b["d"].data_ptr(), b["h"].data_ptr(),
+                            b["c"].data_ptr(), b["f"].data_ptr(), stream=stream.cuda_stream)
+
+    def step_host(mode):
+        for plan, hb in zip(plans, host_bufs):
+            out = {"v": hb["v"].numpy(), "d": hb["d"].numpy() if mode >= 1 else np.zeros(0),
+                   "h": hb["h"].numpy() if mode >= 2 else np.zeros(0), "counters": hb["counters"].numpy(),
+                   "flags": hb["flags"].numpy()}
+            plan.run_host(hb["vp"].numpy(), mode, out=out)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def measure(mode, steps, warmup, sample_clocks):
+        for _ in range(warmup):
+            step_device(mode)
+        barrier()
+        sampler = ClockSampler(local_rank)
+        if sample_clocks and rank == 0:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            step_device(mode)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1) / steps
+        clocks = sampler.stop() if sample_clocks and rank == 0 else None
+        # dominant-kernel time, measured live with CUDA events around each pixel_kernel launch
+        for p in plans:
+            p.enable_timing(True)
+        pix_ms, set_ms, epi_ms = 0.0, 0.0, 0.0
+        reps = 3
+        for _ in range(reps):
+            step_device(mode)
+            torch.cuda.synchronize()
+            for p in plans:
+                a, b, c = p.kernel_times_ms()
+                set_ms += a
+                pix_ms += b
+                epi_ms += c
+        for p in plans:
+            p.enable_timing(False)
+        counts = np.zeros(2)
+        flags = 0
+        for b in dev_bufs:
+            counts += b["c"].cpu().numpy().reshape(-1, 2).sum(axis=0)
+            flags += int(b["f"].sum().item())
+        # e2e: public host-buffer call, H2D of vp and D2H of results inside the timed region
+        for _ in range(max(1, min(warmup, 2))):
+            step_host(mode)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step_host(mode)
+        torch.cuda.synchronize()
+        e2e_s = (time.perf_counter() - t0) / steps
+        barrier()
+        return {"ms": max_over_ranks(ms), "pix_ms": max_over_ranks(pix_ms / reps), "setup_ms": set_ms / reps,
+                "epi_ms": epi_ms / reps, "active": sum_over_ranks(counts[0]), "inactive": sum_over_ranks(counts[1]),
+                "flags": sum_over_ranks(flags), "e2e_s": max_over_ranks(e2e_s), "clocks": clocks}
+
+    peak = C_peak = None
+    import ctypes as C
+    pk = C.c_double(0.0)
+    _lib.check(_lib.load().celeste_fp64_peak(C.byref(pk), stream.cuda_stream))
+    peak = pk.value
+
+    total_sources = sum_over_ranks(n_tasks_total)
+    n_slots = sum(p.n_src for p in plans)
+    grad = measure(1, args.steps, args.warmup, True)
+    hess = None if args.no_hessian else measure(2, max(3, args.steps // 2), args.warmup, False)
+
+    def roofline(m, mode):
+        flop = m["active"] * F_ACTIVE[mode] + m["inactive"] * F_INACTIVE
+        ach = flop / (m["pix_ms"] * 1e-3) / 1e12
+        r = {"bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+             "traffic": None, "kernel": f"pixel_kernel<{mode}>", "kernel_ms_per_step": m["pix_ms"],
+             "kernel_share_of_step": m["pix_ms"] / m["ms"],
+             "algorithmic_flop_per_step": flop, "pixel_visits_active": m["active"], "pixel_visits_inactive": m["inactive"],
+             "peak_source": "measured live: celeste_fp64_peak (register DFMA chain); nominal 37 TFLOP/s",
+             "hbm": {"achieved_gbs": (m["active"] + m["inactive"]) * BYTES_PER_VISIT / (m["pix_ms"] * 1e-3) / 1e9,
+                     "peak_gbs": hbm_peak()}}
+        prof = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(prof):
+            try:
+                r["traffic"] = json.load(open(prof)).get(f"pixel_kernel<{mode}>")
+            except Exception:
+                pass
+        return r
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    def e2e(m, mode):
+        h2d = n_slots * 44 * 8
+        d2h = n_tasks_total * (8 + 16 + 4 + (44 * 8 if mode >= 1 else 0) + (44 * 44 * 8 if mode >= 2 else 0))
+        return {"value": total_sources / m["e2e_s"], "unit": "sources/s", "h2d_bytes_per_step": h2d * world,
+                "d2h_bytes_per_step": d2h * world, "ms_per_step": m["e2e_s"] * 1e3}
+
+    line = {"metric": "sources/sec (ELBO+grad)", "value": total_sources / (grad["ms"] * 1e-3), "unit": "sources/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": grad["ms"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config, "clocks": grad["clocks"], "e2e": e2e(grad, 1),
+            "gpu_launches": args.steps * sum(p.launches(1) for p in plans),
+            "roofline": roofline(grad, 1), "nonfinite_tasks": grad["flags"],
+            "pixel_visits_per_s": (grad["active"] + grad["inactive"]) / (grad["ms"] * 1e-3)}
+    if hess is not None:
+        line["hessian"] = {"value": total_sources / (hess["ms"] * 1e-3), "unit": "sources/s", "ms_per_step": hess["ms"],
+                           "e2e": e2e(hess, 2), "roofline": roofline(hess, 2)}
+    if world == 1 and not args.no_cpu_baseline:
+        cb = cpu_leg(stripe[0], args.cpu_sample, 1, 3, 1)
+        line["cpu_baseline"] = cb
+        if hess is not None:
+            line["hessian"]["cpu_baseline"] = cpu_leg(stripe[0], max(64, args.cpu_sample // 4), 2, 2, 1)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def hbm_peak():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        return 6650.0   # fallback stated in /opt/skills/guides/B200_PROFILING.md
+
+
+if __name__ == "__main__":
+    main()

@@ -11,7 +11,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libceleste_cuda.so")
+# CELESTE_CUDA_LIB selects another build of the same library (kernel-tuning variants); never a CPU path
+LIB_PATH = os.environ.get("CELESTE_CUDA_LIB") or os.path.join(_HERE, "libceleste_cuda.so")
 
 CELESTE_OK = 0
 CELESTE_ERR_NO_DEVICE = 1
@@ -56,7 +57,7 @@ EXPORTS = [
     "celeste_field_create", "celeste_patches_set", "celeste_elbo_batch", "celeste_elbo_single",
     "celeste_plan_create", "celeste_plan_destroy", "celeste_plan_launches",
     "celeste_elbo_plan_device", "celeste_elbo_plan_host", "celeste_field_destroy",
-    "celeste_fp64_peak",
+    "celeste_fp64_peak", "celeste_plan_enable_timing", "celeste_plan_kernel_times", "celeste_set_chunk_pixels",
 ]
 
 _lib = None
@@ -93,6 +94,9 @@ def load():
     lib.celeste_field_destroy.argtypes = [vp]
     lib.celeste_field_destroy.restype = None
     lib.celeste_fp64_peak.argtypes = [C.POINTER(C.c_double), vp]
+    lib.celeste_plan_enable_timing.argtypes = [vp, i32]
+    lib.celeste_plan_kernel_times.argtypes = [vp, C.POINTER(C.c_float * 3)]
+    lib.celeste_set_chunk_pixels.argtypes = [i32]
     _lib = lib
     return lib
 

@@ -102,6 +102,8 @@ int upload_constants() {
     return CELESTE_OK;
 }
 
+int g_chunk_pixels = 0;
+
 template <int MODE>
 size_t pixel_smem_bytes() {
     return ((size_t)NAcc<MODE>::value * PIX_THREADS + (size_t)MAX_COMPS * COMP_STRIDE) * sizeof(double);
@@ -160,8 +162,12 @@ struct celeste_plan {
     DevBuf<long long> counters_dev;
     DevBuf<int> flags_dev;
     cudaStream_t stream = nullptr;
+    bool timing = false;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     ~celeste_plan() {
         if (stream) cudaStreamDestroy(stream);
+        for (auto& e : ev)
+            if (e) cudaEventDestroy(e);
     }
 };
 
@@ -373,7 +379,7 @@ int celeste_plan_create(celeste_field* f, celeste_plan** out, int32_t n_tasks, c
         }
     }
     // block map: one block per (task, image, chunk of the active patch's pixels)
-    const int chunk_pixels = 4 * PIX_THREADS;
+    const int chunk_pixels = g_chunk_pixels > 0 ? g_chunk_pixels : 4 * PIX_THREADS;
     pl->chunk_pixels = chunk_pixels;
     std::vector<int> chunk_ptr((size_t)n_tasks * pl->N + 1, 0);
     std::vector<int2> blockmap;
@@ -401,6 +407,31 @@ int celeste_plan_create(celeste_field* f, celeste_plan** out, int32_t n_tasks, c
 }
 
 void celeste_plan_destroy(celeste_plan* p) { delete p; }
+
+int celeste_set_chunk_pixels(int32_t chunk_pixels) {
+    if (chunk_pixels < 0) return CELESTE_ERR_BAD_ARG;
+    g_chunk_pixels = chunk_pixels;
+    return CELESTE_OK;
+}
+
+int celeste_plan_enable_timing(celeste_plan* p, int32_t on) {
+    if (!p) return CELESTE_ERR_BAD_ARG;
+    if (on)
+        for (auto& e : p->ev)
+            if (!e) CUDA_TRY(cudaEventCreate(&e));
+    p->timing = on != 0;
+    return CELESTE_OK;
+}
+
+int celeste_plan_kernel_times(celeste_plan* p, float ms[3]) {
+    if (!p || !ms || !p->timing) {
+        set_detail("plan_kernel_times: timing not enabled");
+        return CELESTE_ERR_STATE;
+    }
+    CUDA_TRY(cudaEventSynchronize(p->ev[3]));
+    for (int i = 0; i < 3; ++i) CUDA_TRY(cudaEventElapsedTime(&ms[i], p->ev[i], p->ev[i + 1]));
+    return CELESTE_OK;
+}
 
 int celeste_plan_launches(const celeste_plan* p, int32_t mode) {
     (void)mode;
@@ -436,10 +467,14 @@ static int launch_mode(celeste_plan* p, const double* vp_dev, double* v, double*
     fd.patches = p->field->d_patches.p;
     const long total = (long)p->n_slots * p->N * MAX_COMPS;
     const int sblocks = (int)std::min<long>((total + 255) / 256, 148L * 16);
+    if (p->timing) CUDA_TRY(cudaEventRecord(p->ev[0], st));
     setup_kernel<<<sblocks, 256, 0, st>>>(pd, fd, vp_dev);
+    if (p->timing) CUDA_TRY(cudaEventRecord(p->ev[1], st));
     if (p->n_blocks > 0)
         pixel_kernel<MODE><<<p->n_blocks, PIX_THREADS, pixel_smem_bytes<MODE>(), st>>>(pd, fd, p->chunk_pixels);
+    if (p->timing) CUDA_TRY(cudaEventRecord(p->ev[2], st));
     epilogue_kernel<MODE><<<p->n_tasks, EPI_THREADS, 0, st>>>(pd, fd, vp_dev, v, d, h, counters, flags);
+    if (p->timing) CUDA_TRY(cudaEventRecord(p->ev[3], st));
     CUDA_TRY(cudaGetLastError());
     return CELESTE_OK;
 }

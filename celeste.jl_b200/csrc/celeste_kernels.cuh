@@ -129,7 +129,10 @@ __global__ void setup_kernel(PlanDev plan, FieldDev field, const double* __restr
 }
 
 // ------------------------------------------------------------------------------------------------
-constexpr int PIX_THREADS = 128;
+#ifndef CELESTE_PIX_THREADS
+#define CELESTE_PIX_THREADS 128
+#endif
+constexpr int PIX_THREADS = CELESTE_PIX_THREADS;   // threads per pixel-kernel block (multiple of 32)
 constexpr int MAX_NB_LIST = 64;
 
 template <int MODE>

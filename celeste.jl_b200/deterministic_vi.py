@@ -115,34 +115,36 @@ class ElboIntermediateVariables:
 class DeviceField:
     """Images + patch matrix of one inference box, resident in HBM (celeste_field)."""
 
-    def __init__(self, images: Sequence[Image], patches: np.ndarray, device: int = -1):
+    def __init__(self, images: Optional[Sequence[Image]], patches: Optional[np.ndarray], device: int = -1,
+                 flat_images=None, flat_patches=None):
+        """Either (images, patches) model objects, or pre-flattened descriptor arrays
+        (`flat_images.arr/.N`, `flat_patches.arr/.S_tot/.N`, e.g. golden fixtures)."""
         lib = _lib.load()
         ndev = C.c_int(0)
         _lib.check(lib.celeste_init(device, C.byref(ndev)))
-        self.images = list(images)
+        self.images = list(images) if images is not None else None
         self.patches = patches
-        self._flat_images = FlatImages(self.images)
+        self._flat_images = flat_images if flat_images is not None else FlatImages(self.images)
         self._handle = C.c_void_p()
         _lib.check(lib.celeste_field_create(C.byref(self._handle), self._flat_images.N, self._flat_images.arr))
         self._finalizer = weakref.finalize(self, lib.celeste_field_destroy, self._handle)
         self._row = {}
-        self.set_patches(patches)
+        self.set_patches(patches, flat_patches)
 
-    def set_patches(self, patches: np.ndarray):
+    def set_patches(self, patches: Optional[np.ndarray], flat_patches=None):
         lib = _lib.load()
-        fp = FlatPatches(patches)
+        fp = flat_patches if flat_patches is not None else FlatPatches(patches)
         _lib.check(lib.celeste_patches_set(self._handle, fp.S_tot, fp.N, fp.arr))
         self.patches = patches
-        self._row = {id(patches[s, 0]): s for s in range(patches.shape[0])} if patches.shape[1] else {}
+        self.S_tot = fp.S_tot
+        self._row = {}
+        if patches is not None and patches.shape[1]:
+            self._row = {id(patches[s, 0]): s for s in range(patches.shape[0])}
 
-    def row_of(self, patch: ImagePatch) -> Optional[int]:
-        return self._row.get(id(patch))
-
-    def elbo_batch(self, tasks, mode: int = _lib.MODE_HESS, check_finite: bool = True):
-        """tasks: list of (rows_1based, active_local_1based, vp 44 x S).  Returns dict of arrays."""
+    def elbo_csr(self, task_ptr, src, active_ptr, act, vp, mode: int = _lib.MODE_HESS, check_finite: bool = True):
+        """celeste_elbo_batch on raw CSR arrays (the layout include/celeste_cuda.h documents)."""
         lib = _lib.load()
-        task_ptr, src, active_ptr, act, vp = csr_tasks(tasks)
-        n = len(tasks)
+        n = len(task_ptr) - 1
         nd, nh = out_sizes(active_ptr)
         v = np.zeros(n)
         d = np.zeros(nd if mode >= 1 else 0)
@@ -157,6 +159,14 @@ class DeviceField:
         _lib.check(st, allow_nonfinite=not check_finite)
         return {"v": v, "d": d, "h": h, "counters": counters.reshape(n, 2), "flags": flags,
                 "active_ptr": active_ptr}
+
+    def row_of(self, patch: ImagePatch) -> Optional[int]:
+        return self._row.get(id(patch))
+
+    def elbo_batch(self, tasks, mode: int = _lib.MODE_HESS, check_finite: bool = True):
+        """tasks: list of (rows_1based, active_local_1based, vp 44 x S).  Returns dict of arrays."""
+        task_ptr, src, active_ptr, act, vp = csr_tasks(tasks)
+        return self.elbo_csr(task_ptr, src, active_ptr, act, vp, mode, check_finite)
 
     def make_plan(self, tasks_rows, tasks_active):
         return Plan(self, tasks_rows, tasks_active)
@@ -178,6 +188,15 @@ class Plan:
                                            self.task_ptr.ctypes.data, self.src.ctypes.data,
                                            self.active_ptr.ctypes.data, self.act.ctypes.data))
         self._finalizer = weakref.finalize(self, lib.celeste_plan_destroy, self._handle)
+
+    def enable_timing(self, on: bool = True):
+        _lib.check(_lib.load().celeste_plan_enable_timing(self._handle, int(on)))
+
+    def kernel_times_ms(self):
+        """(setup, pixel, epilogue) device milliseconds of the last evaluation (synchronises)."""
+        ms = (C.c_float * 3)()
+        _lib.check(_lib.load().celeste_plan_kernel_times(self._handle, C.byref(ms)))
+        return tuple(float(x) for x in ms)
 
     def launches(self, mode: int) -> int:
         return int(_lib.load().celeste_plan_launches(self._handle, mode))

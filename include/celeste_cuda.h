@@ -210,6 +210,17 @@ int celeste_elbo_plan_host(celeste_plan* p, const double* vp, int32_t mode,
                            double* v, double* d, double* h,
                            int64_t* counters, int32_t* flags);
 
+/*
+ * Optional instrumentation: when enabled, celeste_elbo_plan_device / _host bracket each of their
+ * kernels with CUDA events on the launch stream; celeste_plan_kernel_times synchronises on the last
+ * evaluation and returns its device times in milliseconds: ms[0] setup, ms[1] pixel (the hot kernel),
+ * ms[2] epilogue.  Used by bench.py for the roofline of the dominant kernel.
+ */
+int celeste_plan_enable_timing(celeste_plan* p, int32_t on);
+int celeste_plan_kernel_times(celeste_plan* p, float ms[3]);
+/* chunk size (pixels per pixel-kernel block) used by plans created afterwards; 0 restores the default */
+int celeste_set_chunk_pixels(int32_t chunk_pixels);
+
 void celeste_field_destroy(celeste_field* f);
 
 /*

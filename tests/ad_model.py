@@ -158,4 +158,4 @@ def elbo_ad(images, patches, vp, active_sources, hessian=True):
             else:
                 rows.append(torch.zeros(44 * Sa, dtype=T))
         Hm = torch.stack(rows).detach().numpy()
-    return float(val), g.detach().numpy().reshape(Sa, 44).T, Hm
+    return float(val.detach()), g.detach().numpy().reshape(Sa, 44).T, Hm

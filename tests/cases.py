@@ -1,0 +1,195 @@
+"""Named parity cases shared by the CPU (emulation), GPU and golden-vector tests.
+
+Each case returns (images, patches, tasks) with tasks = [(rows_1based, active_local_1based, vp 44 x S)].
+They map onto BASELINE.json `configs` and the edge cases the reference tests exercise
+(test/test_elbo.jl, test/test_images.jl): masked/NaN pixels, empty and clipped patches, neighbours,
+non-identity WCS, K != 2.
+"""
+import math
+
+import numpy as np
+
+import celeste_jl_b200 as cj
+from celeste_jl_b200 import synthetic
+from celeste_jl_b200.model import AffineWCS, ImagePatch, PsfComponent, get_sky_patches
+
+
+def _vpm(vp, rows):
+    return np.stack([vp[r - 1] for r in rows], axis=1)
+
+
+def _all_tasks(vp, neighbors=None):
+    S = len(vp)
+    tasks = []
+    for t in range(S):
+        nb = [s for s in range(S) if s != t] if neighbors is None else neighbors[t]
+        rows = [t + 1] + [s + 1 for s in nb]
+        tasks.append((rows, [1], _vpm(vp, rows)))
+    return tasks
+
+
+def case_star_1band():
+    """configs[0]: SampleData.gen_sample_star_dataset, 1 star, 1 band (r), 20 x 20 tile."""
+    images, patches, vp, _ = synthetic.gen_sample_star_dataset(bands=(3,), H=20, W=20)
+    return images, patches, _all_tasks(vp)
+
+
+def case_star_5band():
+    """test/SampleData.jl:161-173: the 20 x 23, 5-band star fixture of test_elbo.jl."""
+    images, patches, vp, _ = synthetic.gen_sample_star_dataset()
+    return images, patches, _all_tasks(vp)
+
+
+def case_galaxy():
+    images, patches, vp, _ = synthetic.gen_sample_galaxy_dataset()
+    return images, patches, _all_tasks(vp)
+
+
+def case_two_body():
+    """test/SampleData.jl:193-208 (two overlapping sources; each is the other's neighbour)."""
+    images, patches, vp, _ = synthetic.gen_two_body_dataset()
+    return images, patches, _all_tasks(vp)
+
+
+def case_config2():
+    """configs[1]: 3 sources (2 stars + 1 galaxy), 5 SDSS bands, 50 x 50 tiles."""
+    images, patches, vp, _ = synthetic.gen_config2_dataset()
+    return images, patches, _all_tasks(vp)
+
+
+def case_config2_rotated_wcs():
+    """configs[1] with a rotated / anisotropic wcs_jacobian (second WCS variant)."""
+    images, patches, vp, _ = synthetic.gen_config2_dataset(rotated_wcs=True)
+    return images, patches, _all_tasks(vp)
+
+
+def case_masked():
+    """NaN pixels (masked in SDSS frames, imaged_sources.jl:94-95 + elbo_objective.jl:459) and a
+    hand-edited bitmap whose NaN pixel stays 'active' (the second check must catch it)."""
+    images, patches, vp, catalog = synthetic.gen_two_body_dataset()
+    rng = np.random.default_rng(5)
+    for img in images:
+        m = rng.random(img.pixels.shape) < 0.08
+        img.pixels[m] = np.nan
+    patches = get_sky_patches(images, catalog)
+    # re-activate some NaN pixels in the bitmap of source 1, image 3
+    bm = patches[0, 2].active_pixel_bitmap
+    idx = np.argwhere(~bm)
+    for h2, w2 in idx[:5]:
+        bm[h2, w2] = True
+    # and knock out a block of good pixels
+    patches[1, 4].active_pixel_bitmap[3:6, 2:9] = False
+    return images, patches, _all_tasks(vp)
+
+
+def case_clipped_and_empty():
+    """Patches clipped by the image border and one source whose patch is entirely off one image
+    (empty 1:0 box, imaged_sources.jl:81-84); plus a 1-column patch (only the strict last column)."""
+    images = synthetic.blank_images(40, 36)
+    catalog = [synthetic.sample_ce([3.2, 4.1], False), synthetic.sample_ce([38.6, 33.9], True),
+               synthetic.sample_ce([20.3, 60.0], True), synthetic.sample_ce([19.0, 17.5], False)]
+    synthetic.gen_images(images, catalog, seed=3, device="cpu")
+    patches = get_sky_patches(images, catalog, radius_override_pix=9.0)
+    # source 3 is off-image in w: its box clamps to empty
+    assert patches[2, 0].active_pixel_bitmap.size == 0
+    # a degenerate single-column patch for source 4 in image 2
+    patches[3, 1] = ImagePatch(images[1], ((10, 28), (17, 17)))
+    vp = [cj.catalog_init_source(ce) for ce in catalog]
+    synthetic.perturb_params(vp)
+    return images, patches, _all_tasks(vp)
+
+
+def _case_psf(psf, bands, seed):
+    from celeste_jl_b200.model import render_psf
+    images = synthetic.blank_images(30, 30, bands=bands)
+    for im in images:
+        im.psf = psf
+        im.psf_stamp = render_psf(im.psf, (51, 51))
+        im._coefs_cache = None
+    catalog = [synthetic.sample_ce([14.2, 15.7], False), synthetic.sample_ce([18.9, 11.3], True)]
+    synthetic.gen_images(images, catalog, seed=seed, device="cpu")
+    patches = get_sky_patches(images, catalog)
+    vp = [cj.catalog_init_source(ce) for ce in catalog]
+    synthetic.perturb_params(vp)
+    return images, patches, _all_tasks(vp)
+
+
+def case_psf_k1():
+    """K = 1 PSF mixture (psf_K is a free parameter of ElboArgs, elbo_args.jl:197)."""
+    return _case_psf([PsfComponent(1.0, np.array([0.1, -0.05]), np.array([[2.0, 0.1], [0.1, 1.8]]))], (2, 4), 4)
+
+
+def case_psf_k3():
+    """K = 3 PSF mixture."""
+    return _case_psf([PsfComponent(0.6, np.array([0.0, 0.0]), np.array([[1.5, 0.0], [0.0, 1.5]])),
+                      PsfComponent(0.3, np.array([0.1, 0.1]), np.array([[4.0, 0.3], [0.3, 5.0]])),
+                      PsfComponent(0.1, np.array([-0.2, 0.0]), np.array([[12.0, -1.0], [-1.0, 10.0]]))], (1, 5), 7)
+
+
+def case_crowded(n_sources=90, seed=11):
+    """> 64 overlapping neighbours for one target (ParallelRun.jl:475 warns above 100): exercises the
+    neighbour-list overflow path of the pixel kernel."""
+    images = synthetic.blank_images(48, 48, bands=(3,))
+    rng = np.random.default_rng(seed)
+    catalog = []
+    for k in range(n_sources):
+        pos = [24 + rng.normal(0, 6), 24 + rng.normal(0, 6)]
+        catalog.append(synthetic.sample_ce(pos, bool(k % 3)))
+        catalog[-1].star_fluxes = catalog[-1].star_fluxes * 0.02
+        catalog[-1].gal_fluxes = catalog[-1].gal_fluxes * 0.02
+    synthetic.gen_images(images, catalog, seed=6, device="cpu")
+    patches = get_sky_patches(images, catalog, radius_override_pix=8.0)
+    vp = [cj.catalog_init_source(ce) for ce in catalog]
+    synthetic.perturb_params(vp)
+    tasks = _all_tasks(vp)
+    return images, patches, [tasks[0], tasks[37]]
+
+
+def case_small_field(n_sources=40, H=160, W=140, seed=42):
+    """A miniature of configs[2]: prior-drawn catalog, catalog-sized patches, find_neighbors tasks."""
+    ds = synthetic.FieldDataset(n_sources, H=H, W=W, seed=seed, device="cpu")
+    rows, act = ds.tasks()
+    tasks = [(r, a, _vpm(ds.vp, r)) for r, a in zip(rows, act)]
+    return ds.images, ds.patches, tasks
+
+
+CASES = {
+    "star_1band": case_star_1band,
+    "star_5band": case_star_5band,
+    "galaxy": case_galaxy,
+    "two_body": case_two_body,
+    "config2": case_config2,
+    "config2_rotated_wcs": case_config2_rotated_wcs,
+    "masked": case_masked,
+    "clipped_and_empty": case_clipped_and_empty,
+    "psf_k1": case_psf_k1,
+    "psf_k3": case_psf_k3,
+    "crowded": case_crowded,
+    "small_field": case_small_field,
+}
+
+_cache = {}
+
+
+def get(name):
+    if name not in _cache:
+        _cache[name] = CASES[name]()
+    return _cache[name]
+
+
+def assert_parity(ref, got, mode, label=""):
+    """The parity statement of SURVEY.md 8c: value |d|/|ref| <= 1e-8; gradient / Hessian component-wise
+    |d| <= 1e-8 * max(|ref_ij|, ||ref||_inf * 1e-6); counters and flags exact."""
+    assert np.array_equal(ref["counters"], got["counters"]), (label, ref["counters"], got["counters"])
+    assert np.array_equal(ref["flags"], got["flags"]), label
+    rv, gv = ref["v"], got["v"]
+    assert np.all(np.abs(rv - gv) <= 1e-8 * np.abs(rv)), (label, rv, gv)
+    if mode >= 1:
+        n = len(rv)
+        rd, gd = ref["d"].reshape(n, -1), got["d"].reshape(n, -1)
+        sc = np.abs(rd).max(axis=1, keepdims=True)
+        assert np.all(np.abs(rd - gd) <= 1e-8 * np.maximum(np.abs(rd), sc * 1e-6)), (label, np.abs(rd - gd).max())
+    if mode >= 2:
+        rh, gh = ref["h"].reshape(n, -1), got["h"].reshape(n, -1)
+        sc = np.abs(rh).max(axis=1, keepdims=True)
+        assert np.all(np.abs(rh - gh) <= 1e-8 * np.maximum(np.abs(rh), sc * 1e-6)), (label, np.abs(rh - gh).max())

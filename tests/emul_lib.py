@@ -25,13 +25,15 @@ def load():
 
 
 class EmulField:
-    def __init__(self, images, patches):
-        self.fi = FlatImages(images)
-        self.fp = FlatPatches(patches)
+    def __init__(self, images, patches, flat_images=None, flat_patches=None):
+        self.fi = flat_images if flat_images is not None else FlatImages(images)
+        self.fp = flat_patches if flat_patches is not None else FlatPatches(patches)
 
     def elbo_batch(self, tasks, mode=2, chunk_pixels=512):
-        task_ptr, src, active_ptr, act, vp = csr_tasks(tasks)
-        n = len(tasks)
+        return self.elbo_csr(*csr_tasks(tasks), mode=mode, chunk_pixels=chunk_pixels)
+
+    def elbo_csr(self, task_ptr, src, active_ptr, act, vp, mode=2, chunk_pixels=512):
+        n = len(task_ptr) - 1
         nd, nh = out_sizes(active_ptr)
         v = np.zeros(n)
         d = np.zeros(max(nd, 1))

@@ -39,9 +39,9 @@ def load(path=None):
 class OracleField:
     """Same call shape as cj.DeviceField.elbo_batch, evaluated by the CPU oracle."""
 
-    def __init__(self, images, patches, lib=None):
-        self.fi = FlatImages(images)
-        self.fp = FlatPatches(patches)
+    def __init__(self, images, patches, lib=None, flat_images=None, flat_patches=None):
+        self.fi = flat_images if flat_images is not None else FlatImages(images)
+        self.fp = flat_patches if flat_patches is not None else FlatPatches(patches)
         self.lib = lib or load()
 
     def elbo_batch(self, tasks, mode=2, n_threads=1):

@@ -1,0 +1,37 @@
+"""The product's kernel SOURCE (celeste.jl_b200/csrc/celeste_kernels.cuh), compiled for the host under
+tests/host_emul's emulation of the CUDA execution model, against the oracle -- CPU only.  This is not
+the product path (the product only runs these kernels on a GPU); it catches indexing / reduction /
+chain-rule bugs before GPU time is spent.  The real parity tests are tests/test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+import cases
+import emul_lib
+import oracle_lib
+
+FAST = ["star_1band", "two_body", "masked", "clipped_and_empty", "psf_k1", "psf_k3", "crowded"]
+
+
+@pytest.mark.parametrize("name", FAST)
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_emulated_kernels_match_oracle(name, mode):
+    images, patches, tasks = cases.get(name)
+    ref = oracle_lib.OracleField(images, patches).elbo_batch(tasks, mode=mode)
+    got = emul_lib.EmulField(images, patches).elbo_batch(tasks, mode=mode, chunk_pixels=512)
+    cases.assert_parity(ref, got, mode, name)
+
+
+@pytest.mark.parametrize("name", ["config2_rotated_wcs", "small_field"])
+def test_emulated_kernels_match_oracle_hessian(name):
+    images, patches, tasks = cases.get(name)
+    ref = oracle_lib.OracleField(images, patches).elbo_batch(tasks, mode=2, n_threads=4)
+    got = emul_lib.EmulField(images, patches).elbo_batch(tasks, mode=2, chunk_pixels=512)
+    cases.assert_parity(ref, got, 2, name)
+
+
+def test_chunking_does_not_change_counters_or_parity():
+    images, patches, tasks = cases.get("two_body")
+    ref = oracle_lib.OracleField(images, patches).elbo_batch(tasks, mode=2)
+    for chunk in (128, 200, 4096):
+        got = emul_lib.EmulField(images, patches).elbo_batch(tasks, mode=2, chunk_pixels=chunk)
+        cases.assert_parity(ref, got, 2, f"chunk={chunk}")

