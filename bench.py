@@ -36,12 +36,12 @@ NOMINAL_FP64_TFLOPS = 37.0   # HGX B200 datasheet, 296 TF / 8
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--fields", type=int, default=10, help="fields in the stripe (1000 sources each)")
     ap.add_argument("--sources-per-field", type=int, default=1000)
-    ap.add_argument("--cpu-sample", type=int, default=384, help="tasks per CPU-baseline step")
+    ap.add_argument("--cpu-sample", type=int, default=1000, help="tasks per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hessian", action="store_true")
     return ap.parse_args()
@@ -83,7 +83,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu), "-lms", "100"], stdout=open(self.path, "w"),
+                                          "-i", str(self.gpu), "-lms", "20"], stdout=open(self.path, "w"),
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -99,8 +99,13 @@ class ClockSampler:
             self.proc.kill()
         try:
             rows = [r.split(",") for r in open(self.path).read().strip().splitlines() if r.strip()]
-            sm = [float(r[1]) for r in rows]
-            out["samples"] = len(sm)
+            rows = [r for r in rows if len(r) >= 9]
+            # "under load" = samples drawing more than half of the peak power seen in the window
+            pmax = max((float(r[3]) for r in rows), default=0.0)
+            loaded = [r for r in rows if float(r[3]) >= 0.5 * pmax] or rows
+            sm = [float(r[1]) for r in loaded]
+            out["samples"] = len(rows)
+            out["samples_under_load"] = len(loaded)
             if sm:
                 out["sm_mhz"] = float(np.median(sm))
                 out["sm_max_mhz"] = float(rows[0][2])
@@ -195,16 +200,19 @@ def main():
     from celeste_jl_b200 import _lib
 
     stripe = build_stripe(args.fields, args.sources_per_field, device=str(dev))
-    fields, plans, vps, n_tasks_total = [], [], [], 0
-    for ds in stripe:
+    # one multi-field plan per rank: every task of this rank's shard, all fields, three launches per step
+    fields, all_rows, all_act, task_field, vp_parts = [], [], [], [], []
+    for fi, ds in enumerate(stripe):
         mine = shard_tasks(ds, rank, world)
-        field = cj.DeviceField(ds.images, ds.patches, device=local_rank)
+        fields.append(cj.DeviceField(ds.images, ds.patches, device=local_rank))
         rows, act = ds.tasks(mine)
-        plan = field.make_plan(rows, act)
-        fields.append(field)
-        plans.append(plan)
-        vps.append(ds.vp_flat(rows))
-        n_tasks_total += len(mine)
+        all_rows += rows
+        all_act += act
+        task_field += [fi] * len(rows)
+        vp_parts.append(ds.vp_flat(rows))
+    plans = [cj.Plan(fields, all_rows, all_act, task_field=task_field)]
+    vps = [np.concatenate(vp_parts)]
+    n_tasks_total = len(all_rows)
     stream = torch.cuda.current_stream()
 
     # device-resident buffers (value) and pinned host buffers (e2e)
@@ -255,12 +263,13 @@ def main():
         return float(t.item())
 
     def measure(mode, steps, warmup, sample_clocks):
-        for _ in range(warmup):
-            step_device(mode)
-        barrier()
         sampler = ClockSampler(local_rank)
         if sample_clocks and rank == 0:
             sampler.start()
+            time.sleep(0.3)
+        for _ in range(warmup):
+            step_device(mode)
+        barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(steps):
@@ -357,7 +366,7 @@ def main():
         cb = cpu_leg(stripe[0], args.cpu_sample, 1, 3, 1)
         line["cpu_baseline"] = cb
         if hess is not None:
-            line["hessian"]["cpu_baseline"] = cpu_leg(stripe[0], max(64, args.cpu_sample // 4), 2, 2, 1)
+            line["hessian"]["cpu_baseline"] = cpu_leg(stripe[0], args.cpu_sample, 2, 2, 1)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -58,6 +58,7 @@ EXPORTS = [
     "celeste_plan_create", "celeste_plan_destroy", "celeste_plan_launches",
     "celeste_elbo_plan_device", "celeste_elbo_plan_host", "celeste_field_destroy",
     "celeste_fp64_peak", "celeste_plan_enable_timing", "celeste_plan_kernel_times", "celeste_set_chunk_pixels",
+    "celeste_plan_create_multi",
 ]
 
 _lib = None
@@ -86,6 +87,7 @@ def load():
     lib.celeste_elbo_batch.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]
     lib.celeste_elbo_single.argtypes = [vp, i32, vp, i32, vp, vp, i32, vp, vp, vp, vp, vp]
     lib.celeste_plan_create.argtypes = [vp, C.POINTER(vp), i32, vp, vp, vp, vp]
+    lib.celeste_plan_create_multi.argtypes = [i32, C.POINTER(vp), C.POINTER(vp), i32, vp, vp, vp, vp, vp]
     lib.celeste_plan_destroy.argtypes = [vp]
     lib.celeste_plan_destroy.restype = None
     lib.celeste_plan_launches.argtypes = [vp, i32]

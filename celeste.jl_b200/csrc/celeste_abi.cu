@@ -9,6 +9,7 @@
 #include <cstdarg>
 #include <memory>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -110,9 +111,15 @@ size_t pixel_smem_bytes() {
 }
 
 int configure_kernels() {
-    CUDA_TRY(cudaFuncSetAttribute(pixel_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pixel_smem_bytes<0>()));
-    CUDA_TRY(cudaFuncSetAttribute(pixel_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pixel_smem_bytes<1>()));
-    CUDA_TRY(cudaFuncSetAttribute(pixel_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pixel_smem_bytes<2>()));
+#define CEL_CFG(M, K) \
+    CUDA_TRY(cudaFuncSetAttribute(pixel_kernel<M, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pixel_smem_bytes<M>()))
+    CEL_CFG(0, 0);
+    CEL_CFG(1, 0);
+    CEL_CFG(2, 0);
+    CEL_CFG(0, 2);
+    CEL_CFG(1, 2);
+    CEL_CFG(2, 2);
+#undef CEL_CFG
     return CELESTE_OK;
 }
 
@@ -146,16 +153,21 @@ struct celeste_field {
     DevBuf<uint8_t> bitmap_pool;
     DevBuf<double> double_pool;   // psf records + spline coefficient arrays
     unsigned long long patch_generation = 0;
+    int uniform_K = 0;   // K shared by every patch (0: mixed) -> selects the K-specialised pixel kernel
 };
 
 struct celeste_plan {
-    celeste_field* field = nullptr;
-    unsigned long long patch_generation = 0;
+    std::vector<celeste_field*> fields;
+    std::vector<unsigned long long> patch_generation;
+    int device = 0;
+    int uniform_K = 0;
+    DevBuf<FieldDev> d_fields;
+    DevBuf<int> task_field, slot_field;
     int n_tasks = 0, n_slots = 0, N = 0;
     int n_blocks = 0, chunk_pixels = 0;
     std::vector<int> h_task_ptr;
     DevBuf<int> task_ptr, src_row, act_slot, chunk_ptr;
-    DevBuf<int2> blockmap;
+    DevBuf<BlockHdr> blockmap;
     DevBuf<double> slotimg, slotbr, partials;
     // staging for the host-buffer entry point
     DevBuf<double> vp_dev, v_dev, d_dev, h_dev;
@@ -327,36 +339,62 @@ int celeste_patches_set(celeste_field* f, int32_t S_tot, int32_t N, const celest
     }
     CUDA_TRY(f->d_patches.upload(f->h_patches));
     f->S_tot = S_tot;
+    f->uniform_K = np ? p[0].K : 0;
+    for (size_t i = 0; i < np; ++i)
+        if (p[i].K != f->uniform_K) f->uniform_K = 0;
     f->patch_generation++;
     return CELESTE_OK;
 }
 
 void celeste_field_destroy(celeste_field* f) { delete f; }
 
-int celeste_plan_create(celeste_field* f, celeste_plan** out, int32_t n_tasks, const int32_t* task_ptr,
-                        const int32_t* source_ids, const int32_t* active_ptr, const int32_t* active_idx) {
-    if (!f || !out || n_tasks < 0 || !task_ptr || !active_ptr || (n_tasks > 0 && (!source_ids || !active_idx))) {
+int celeste_plan_create_multi(int32_t n_fields, celeste_field* const* fields, celeste_plan** out, int32_t n_tasks,
+                              const int32_t* task_field, const int32_t* task_ptr, const int32_t* source_ids,
+                              const int32_t* active_ptr, const int32_t* active_idx) {
+    if (n_fields < 1 || !fields || !out || n_tasks < 0 || !task_ptr || !active_ptr ||
+        (n_tasks > 0 && (!source_ids || !active_idx || (n_fields > 1 && !task_field)))) {
         set_detail("plan_create: bad arguments");
         return CELESTE_ERR_BAD_ARG;
     }
     *out = nullptr;
-    CUDA_TRY(cudaSetDevice(f->device));
+    for (int i = 0; i < n_fields; ++i)
+        if (!fields[i] || fields[i]->N != fields[0]->N || fields[i]->device != fields[0]->device) {
+            set_detail("plan_create: field %d is null or differs in image count / device from field 0", i);
+            return CELESTE_ERR_BAD_ARG;
+        }
+    CUDA_TRY(cudaSetDevice(fields[0]->device));
     std::unique_ptr<celeste_plan> pl(new (std::nothrow) celeste_plan);
     if (!pl) return CELESTE_ERR_ALLOC;
-    pl->field = f;
-    pl->patch_generation = f->patch_generation;
+    pl->fields.assign(fields, fields + n_fields);
+    pl->device = fields[0]->device;
+    pl->uniform_K = fields[0]->uniform_K;
+    std::vector<FieldDev> hf(n_fields);
+    for (int i = 0; i < n_fields; ++i) {
+        pl->patch_generation.push_back(fields[i]->patch_generation);
+        if (fields[i]->uniform_K != pl->uniform_K) pl->uniform_K = 0;
+        hf[i].images = fields[i]->d_images.p;
+        hf[i].patches = fields[i]->d_patches.p;
+        hf[i].S_tot = fields[i]->S_tot;
+        hf[i].pad = 0;
+    }
     pl->n_tasks = n_tasks;
-    pl->N = f->N;
+    pl->N = fields[0]->N;
     const int n_slots = task_ptr[n_tasks];
     pl->n_slots = n_slots;
     pl->h_task_ptr.assign(task_ptr, task_ptr + n_tasks + 1);
-    std::vector<int> src_row(n_slots), act_slot(n_tasks);
+    std::vector<int> src_row(n_slots), act_slot(n_tasks), tfield(n_tasks), sfield(n_slots);
     for (int t = 0; t < n_tasks; ++t) {
         const int s0 = task_ptr[t], s1 = task_ptr[t + 1];
         if (s0 < 0 || s1 < s0 || (t == 0 && s0 != 0)) {
             set_detail("plan_create: task_ptr not a prefix array at task %d", t);
             return CELESTE_ERR_BAD_ARG;
         }
+        const int fi = task_field ? task_field[t] : 0;
+        if (fi < 0 || fi >= n_fields) {
+            set_detail("plan_create: task %d names field %d of %d", t, fi, n_fields);
+            return CELESTE_ERR_BAD_ARG;
+        }
+        tfield[t] = fi;
         const int Sa = active_ptr[t + 1] - active_ptr[t];
         if (Sa != 1) {
             set_detail("plan_create: task %d has Sa=%d active sources; this build evaluates Sa == 1 "
@@ -371,29 +409,48 @@ int celeste_plan_create(celeste_field* f, celeste_plan** out, int32_t n_tasks, c
         act_slot[t] = s0 + a - 1;
         for (int s = s0; s < s1; ++s) {
             const int row = source_ids[s];
-            if (row < 1 || row > f->S_tot) {
-                set_detail("plan_create: task %d source id %d outside 1..%d", t, row, f->S_tot);
+            if (row < 1 || row > fields[fi]->S_tot) {
+                set_detail("plan_create: task %d source id %d outside 1..%d", t, row, fields[fi]->S_tot);
                 return CELESTE_ERR_BAD_ARG;
             }
             src_row[s] = row - 1;
+            sfield[s] = fi;
         }
     }
     // block map: one block per (task, image, chunk of the active patch's pixels)
-    const int chunk_pixels = g_chunk_pixels > 0 ? g_chunk_pixels : 4 * PIX_THREADS;
+    int chunk_pixels = g_chunk_pixels > 0 ? g_chunk_pixels : 4 * PIX_THREADS;
+    if (const char* env = std::getenv("CELESTE_CHUNK_PIXELS"))   // kernel-tuning knob
+        if (std::atoi(env) > 0) chunk_pixels = std::atoi(env);
     pl->chunk_pixels = chunk_pixels;
     std::vector<int> chunk_ptr((size_t)n_tasks * pl->N + 1, 0);
-    std::vector<int2> blockmap;
+    std::vector<BlockHdr> blockmap;
     for (int t = 0; t < n_tasks; ++t)
         for (int n = 0; n < pl->N; ++n) {
-            const PatchDev& pa = f->h_patches[(size_t)src_row[act_slot[t]] + (size_t)n * f->S_tot];
+            const celeste_field* f = fields[tfield[t]];
+            const size_t pidx = (size_t)src_row[act_slot[t]] + (size_t)n * f->S_tot;
+            const PatchDev& pa = f->h_patches[pidx];
             const long npix = (long)pa.H2 * pa.W2;
             const int nchunk = (int)((npix + chunk_pixels - 1) / chunk_pixels);
             const int tn = t * pl->N + n;
             chunk_ptr[tn + 1] = chunk_ptr[tn] + nchunk;
-            for (int c = 0; c < nchunk; ++c) blockmap.push_back(make_int2(tn, c));
+            for (int c = 0; c < nchunk; ++c) {
+                BlockHdr hd;
+                hd.tn = tn;
+                hd.chunk = c;
+                hd.aslot = act_slot[t];
+                hd.slot0 = task_ptr[t];
+                hd.slot1 = task_ptr[t + 1];
+                hd.patch = (int)pidx;
+                hd.n = n;
+                hd.field = tfield[t];
+                blockmap.push_back(hd);
+            }
         }
     pl->n_blocks = (int)blockmap.size();
     std::vector<int> tp(task_ptr, task_ptr + n_tasks + 1);
+    CUDA_TRY(pl->d_fields.upload(hf));
+    CUDA_TRY(pl->task_field.upload(tfield));
+    CUDA_TRY(pl->slot_field.upload(sfield));
     CUDA_TRY(pl->task_ptr.upload(tp));
     CUDA_TRY(pl->src_row.upload(src_row));
     CUDA_TRY(pl->act_slot.upload(act_slot));
@@ -404,6 +461,12 @@ int celeste_plan_create(celeste_field* f, celeste_plan** out, int32_t n_tasks, c
     CUDA_TRY(pl->partials.alloc((size_t)pl->n_blocks * NACC_MODE2));
     *out = pl.release();
     return CELESTE_OK;
+}
+
+int celeste_plan_create(celeste_field* f, celeste_plan** out, int32_t n_tasks, const int32_t* task_ptr,
+                        const int32_t* source_ids, const int32_t* active_ptr, const int32_t* active_idx) {
+    celeste_field* fields[1] = {f};
+    return celeste_plan_create_multi(1, fields, out, n_tasks, nullptr, task_ptr, source_ids, active_ptr, active_idx);
 }
 
 void celeste_plan_destroy(celeste_plan* p) { delete p; }
@@ -445,8 +508,11 @@ static PlanDev plan_dev(const celeste_plan* p) {
     PlanDev d;
     d.n_tasks = p->n_tasks;
     d.N = p->N;
-    d.S_tot = p->field->S_tot;
+    d.n_fields = (int)p->fields.size();
     d.n_slots = p->n_slots;
+    d.fields = p->d_fields.p;
+    d.task_field = p->task_field.p;
+    d.slot_field = p->slot_field.p;
     d.task_ptr = p->task_ptr.p;
     d.src_row = p->src_row.p;
     d.act_slot = p->act_slot.p;
@@ -462,18 +528,19 @@ template <int MODE>
 static int launch_mode(celeste_plan* p, const double* vp_dev, double* v, double* d, double* h, long long* counters,
                        int* flags, cudaStream_t st) {
     const PlanDev pd = plan_dev(p);
-    FieldDev fd;
-    fd.images = p->field->d_images.p;
-    fd.patches = p->field->d_patches.p;
     const long total = (long)p->n_slots * p->N * MAX_COMPS;
     const int sblocks = (int)std::min<long>((total + 255) / 256, 148L * 16);
     if (p->timing) CUDA_TRY(cudaEventRecord(p->ev[0], st));
-    setup_kernel<<<sblocks, 256, 0, st>>>(pd, fd, vp_dev);
+    setup_kernel<<<sblocks, 256, 0, st>>>(pd, vp_dev);
     if (p->timing) CUDA_TRY(cudaEventRecord(p->ev[1], st));
-    if (p->n_blocks > 0)
-        pixel_kernel<MODE><<<p->n_blocks, PIX_THREADS, pixel_smem_bytes<MODE>(), st>>>(pd, fd, p->chunk_pixels);
+    if (p->n_blocks > 0) {
+        if (p->uniform_K == 2)
+            pixel_kernel<MODE, 2><<<p->n_blocks, PIX_THREADS, pixel_smem_bytes<MODE>(), st>>>(pd, p->chunk_pixels);
+        else
+            pixel_kernel<MODE, 0><<<p->n_blocks, PIX_THREADS, pixel_smem_bytes<MODE>(), st>>>(pd, p->chunk_pixels);
+    }
     if (p->timing) CUDA_TRY(cudaEventRecord(p->ev[2], st));
-    epilogue_kernel<MODE><<<p->n_tasks, EPI_THREADS, 0, st>>>(pd, fd, vp_dev, v, d, h, counters, flags);
+    epilogue_kernel<MODE><<<p->n_tasks, EPI_THREADS, 0, st>>>(pd, vp_dev, v, d, h, counters, flags);
     if (p->timing) CUDA_TRY(cudaEventRecord(p->ev[3], st));
     CUDA_TRY(cudaGetLastError());
     return CELESTE_OK;
@@ -488,10 +555,11 @@ int celeste_elbo_plan_device(celeste_plan* p, const double* vp_dev, int32_t mode
         set_detail("elbo_plan_device: bad arguments (mode=%d)", mode);
         return CELESTE_ERR_BAD_ARG;
     }
-    if (p->patch_generation != p->field->patch_generation) {
-        set_detail("plan is stale: celeste_patches_set was called after celeste_plan_create");
-        return CELESTE_ERR_STATE;
-    }
+    for (size_t i = 0; i < p->fields.size(); ++i)
+        if (p->patch_generation[i] != p->fields[i]->patch_generation) {
+            set_detail("plan is stale: celeste_patches_set was called after celeste_plan_create");
+            return CELESTE_ERR_STATE;
+        }
     if (p->n_tasks == 0) return CELESTE_OK;
     cudaStream_t st = (cudaStream_t)cuda_stream;
     long long* c = reinterpret_cast<long long*>(counters_dev);
@@ -509,7 +577,7 @@ int celeste_elbo_plan_host(celeste_plan* p, const double* vp, int32_t mode, doub
         return CELESTE_ERR_BAD_ARG;
     }
     if (p->n_tasks == 0) return CELESTE_OK;
-    CUDA_TRY(cudaSetDevice(p->field->device));
+    CUDA_TRY(cudaSetDevice(p->device));
     if (!p->stream) CUDA_TRY(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     const size_t nt = p->n_tasks;
     CUDA_TRY(p->vp_dev.ensure((size_t)p->n_slots * NPARAM));

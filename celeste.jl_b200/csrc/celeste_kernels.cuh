@@ -48,22 +48,39 @@ constexpr int SLOTIMG_STRIDE = MAX_COMPS * COMP_STRIDE + 2;   // comps + m_pos
 // per slot: El[2][5], Ell[2][5], a[2], theta
 constexpr int SLOTBR_STRIDE = 24;
 
+struct FieldDev {
+    const ImageDev* images;
+    const PatchDev* patches;  // s + n * S_tot
+    int S_tot;
+    int pad;
+};
+
+// everything a pixel-kernel block needs to find its work, in one 32-byte load
+struct BlockHdr {
+    int tn;        // task * N + n
+    int chunk;     // chunk index inside the active patch
+    int aslot;     // slot of the active source
+    int slot0, slot1;   // slot range of the task
+    int patch;     // index of the active source's patch in FieldDev::patches
+    int n;         // image
+    int field;     // index into PlanDev::fields
+};
+
 struct PlanDev {
-    int n_tasks, N, S_tot, n_slots;
+    int n_tasks, N, n_fields, n_slots;
+    const FieldDev* fields;  // n_fields inference boxes share one plan (same N)
+    const int* task_field;   // n_tasks: field of each task
+    const int* slot_field;   // n_slots: field of each slot
     const int* task_ptr;     // n_tasks + 1 (slot ranges)
-    const int* src_row;      // n_slots: 0-based patch row of each slot
+    const int* src_row;      // n_slots: 0-based patch row of each slot (inside its field)
     const int* act_slot;     // n_tasks: slot of the (single) active source
-    const int2* blockmap;    // n_blocks: (task * N + n, chunk)
+    const BlockHdr* blockmap; // n_blocks
     const int* chunk_ptr;    // n_tasks * N + 1: first block of (task, n)
     double* slotimg;         // n_slots * N * SLOTIMG_STRIDE
     double* slotbr;          // n_slots * SLOTBR_STRIDE
     double* partials;        // n_blocks * NACC
 };
 
-struct FieldDev {
-    const ImageDev* images;
-    const PatchDev* patches;  // s + n * S_tot
-};
 
 __constant__ double c_proto_eta[NPROTO];
 __constant__ double c_proto_nu[NPROTO];
@@ -88,7 +105,7 @@ __global__ void prep_image_kernel(int H, int W, const float* __restrict__ pixels
 }
 
 // one thread per (slot, image, component)
-__global__ void setup_kernel(PlanDev plan, FieldDev field, const double* __restrict__ vp) {
+__global__ void setup_kernel(PlanDev plan, const double* __restrict__ vp) {
     const long total = (long)plan.n_slots * plan.N * MAX_COMPS;
     for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
         const int c = (int)(idx % MAX_COMPS);
@@ -96,7 +113,8 @@ __global__ void setup_kernel(PlanDev plan, FieldDev field, const double* __restr
         const int n = (int)(sn % plan.N);
         const int slot = (int)(sn / plan.N);
         const double* vs = vp + (size_t)NPARAM * slot;
-        const PatchDev& p = field.patches[plan.src_row[slot] + (size_t)n * plan.S_tot];
+        const FieldDev& field = plan.fields[plan.slot_field[slot]];
+        const PatchDev& p = field.patches[plan.src_row[slot] + (size_t)n * field.S_tot];
         double* rec = plan.slotimg + ((size_t)slot * plan.N + n) * SLOTIMG_STRIDE;
         // linear_world_to_pix, wcs_utils.jl:14-18
         const double d0 = vs[0] - p.wc[0], d1 = vs[1] - p.wc[1];
@@ -135,8 +153,17 @@ __global__ void setup_kernel(PlanDev plan, FieldDev field, const double* __restr
 constexpr int PIX_THREADS = CELESTE_PIX_THREADS;   // threads per pixel-kernel block (multiple of 32)
 constexpr int MAX_NB_LIST = 64;
 
-template <int MODE>
-__global__ void __launch_bounds__(PIX_THREADS) pixel_kernel(PlanDev plan, FieldDev field, int chunk_pixels) {
+#ifndef CELESTE_PIX_MINB_GRAD
+#define CELESTE_PIX_MINB_GRAD 6
+#endif
+#ifndef CELESTE_PIX_MINB_HESS
+#define CELESTE_PIX_MINB_HESS 3
+#endif
+// KT: PSF components per patch fixed at compile time (2 = the reference default psf_K, elbo_args.jl:197);
+// KT == 0 reads K from each patch at run time.
+template <int MODE, int KT>
+__global__ void __launch_bounds__(PIX_THREADS, MODE == 2 ? CELESTE_PIX_MINB_HESS : CELESTE_PIX_MINB_GRAD)
+    pixel_kernel(PlanDev plan, int chunk_pixels) {
     constexpr int NACC = NAcc<MODE>::value;
     CEL_DYNAMIC_SMEM(smem);
     double* acc = smem;                                    // NACC x PIX_THREADS
@@ -146,13 +173,13 @@ __global__ void __launch_bounds__(PIX_THREADS) pixel_kernel(PlanDev plan, FieldD
     __shared__ int s_nb_overflow;
 
     const int tid = threadIdx.x;
-    const int2 bm = plan.blockmap[blockIdx.x];
-    const int tn = bm.x, chunk = bm.y;
-    const int t = tn / plan.N, n = tn % plan.N;
-    const int slot0 = plan.task_ptr[t], slot1 = plan.task_ptr[t + 1];
-    const int aslot = plan.act_slot[t];
+    const BlockHdr bm = plan.blockmap[blockIdx.x];
+    const int chunk = bm.chunk, n = bm.n;
+    const int slot0 = bm.slot0, slot1 = bm.slot1;
+    const int aslot = bm.aslot;
+    const FieldDev field = plan.fields[bm.field];
     const ImageDev img = field.images[n];
-    const PatchDev pa = field.patches[plan.src_row[aslot] + (size_t)n * plan.S_tot];
+    const PatchDev pa = field.patches[bm.patch];
     const int npix = pa.H2 * pa.W2;
     const int first = chunk * chunk_pixels;
     const int last = min(first + chunk_pixels, npix);      // exclusive
@@ -182,7 +209,7 @@ __global__ void __launch_bounds__(PIX_THREADS) pixel_kernel(PlanDev plan, FieldD
             const int s = base + tid;
             bool hit = false;
             if (s < slot1 && s != aslot) {
-                const PatchDev& p = field.patches[plan.src_row[s] + (size_t)n * plan.S_tot];
+                const PatchDev& p = field.patches[plan.src_row[s] + (size_t)n * field.S_tot];
                 // rows off_h+1 .. off_h+H2, columns off_w+1 .. off_w+W2-1 (strict `w2 < W2`, elbo_objective.jl:349)
                 hit = (p.off_h + 1 <= bh_hi) && (p.off_h + p.H2 >= bh_lo) && (p.off_w + 1 <= bw_hi) &&
                       (p.off_w + p.W2 - 1 >= bw_lo);
@@ -210,7 +237,7 @@ __global__ void __launch_bounds__(PIX_THREADS) pixel_kernel(PlanDev plan, FieldD
 
     // value-only contribution of neighbour slot s at image pixel (h, w) (elbo_objective.jl:342-372, inactive branch)
     auto neighbour = [&](int s, int h, int w, double& Ebg, double& Vbg, double& cnt) {
-        const PatchDev& p = field.patches[plan.src_row[s] + (size_t)n * plan.S_tot];
+        const PatchDev& p = field.patches[plan.src_row[s] + (size_t)n * field.S_tot];
         const int h2 = h - p.off_h, w2 = w - p.off_w;
         if (h2 < 1 || h2 > p.H2 || w2 < 1 || w2 >= p.W2) return;
         if (!p.bitmap[(h2 - 1) + (size_t)(w2 - 1) * p.H2]) return;
@@ -220,7 +247,7 @@ __global__ void __launch_bounds__(PIX_THREADS) pixel_kernel(PlanDev plan, FieldD
         const double m1 = __ldg(rec + MAX_COMPS * COMP_STRIDE), m2 = __ldg(rec + MAX_COMPS * COMP_STRIDE + 1);
         double f0, gd[2], hd[3];
         star_eval<0>(LdGlobal(), p.coefs, p.n1, p.n2, (double)h - m1 + 26.0, (double)w - m2 + 26.0, f0, gd, hd);
-        const double f1 = gal_value(LdGlobal(), rec, p.K, __ldg(br + 22), (double)h, (double)w);
+        const double f1 = gal_value<KT>(LdGlobal(), rec, p.K, __ldg(br + 22), (double)h, (double)w);
         const double na1 = __ldg(br + 20), na2 = __ldg(br + 21);
         const double Es = na1 * __ldg(br + b) * f0 + na2 * __ldg(br + 5 + b) * f1;
         const double E2s = na1 * __ldg(br + 10 + b) * f0 * f0 + na2 * __ldg(br + 15 + b) * f1 * f1;
@@ -228,40 +255,65 @@ __global__ void __launch_bounds__(PIX_THREADS) pixel_kernel(PlanDev plan, FieldD
         Vbg += E2s - Es * Es;
     };
 
+    // per-pixel inputs are fetched one iteration ahead so their DRAM latency hides behind the FP64 work
+    // (all five loads are issued unconditionally -- the patch box is clamped to the image -- and nothing
+    // is tested until the values are consumed one iteration later)
+    struct PixIn {
+        unsigned char active;
+        float x, sky, iota;
+        double pixconst;
+    };
+    auto fetch = [&](int pix) {
+        PixIn in;
+        in.active = 0;
+        in.x = in.sky = in.iota = 0.f;
+        in.pixconst = 0.0;
+        if (pix < last) {
+            const int h2 = pix % pa.H2, w2 = pix / pa.H2;
+            const size_t ipix = (size_t)(pa.off_h + h2) + (size_t)(pa.off_w + w2) * img.H;
+            in.active = pa.bitmap[pix];
+            in.x = img.pixels[ipix];
+            in.sky = img.sky[ipix];
+            in.iota = img.iota[pa.off_h + h2];
+            in.pixconst = img.pixconst[ipix];
+        }
+        return in;
+    };
+    PixIn cur = fetch(first + tid);
     for (int pix = first + tid; pix < last; pix += PIX_THREADS) {
-        const int h2 = pix % pa.H2, w2 = pix / pa.H2;        // 0-based local
-        if (!pa.bitmap[pix]) continue;                       // elbo_objective.jl:445
-        const int h = pa.off_h + h2 + 1, w = pa.off_w + w2 + 1;   // 1-based image coordinates
-        const size_t ipix = (size_t)(h - 1) + (size_t)(w - 1) * img.H;
-        const float xf = img.pixels[ipix];
-        if (isnan(xf)) continue;                             // :459
-        PixelConsts pc;
-        pc.x = (double)xf;
-        pc.iota = (double)img.iota[h - 1];
-        pc.pixconst = img.pixconst[ipix];
-        double Ebg = (double)img.sky[ipix];                  // :374
-        double Vbg = 0.0;
-        double cnt_inactive = 0.0;
-        const int nnb = s_nb_count;
-        for (int i = 0; i < nnb; ++i) neighbour(s_nb[i], h, w, Ebg, Vbg, cnt_inactive);
-        if (s_nb_overflow) {
-            // rare: more overlapping neighbours than the list holds; scan the remaining slots in order
-            const int last_listed = s_nb[MAX_NB_LIST - 1];
-            for (int s = last_listed + 1; s < slot1; ++s)
-                if (s != aslot) neighbour(s, h, w, Ebg, Vbg, cnt_inactive);
+        const PixIn nxt = fetch(pix + PIX_THREADS);
+        if (cur.active && !isnan(cur.x)) {                       // elbo_objective.jl:445, :459
+            const int h2 = pix % pa.H2, w2 = pix / pa.H2;        // 0-based local
+            const int h = pa.off_h + h2 + 1, w = pa.off_w + w2 + 1;   // 1-based image coordinates
+            PixelConsts pc;
+            pc.x = (double)cur.x;
+            pc.iota = (double)cur.iota;
+            pc.pixconst = cur.pixconst;
+            double Ebg = (double)cur.sky;                        // :374
+            double Vbg = 0.0;
+            double cnt_inactive = 0.0;
+            const int nnb = s_nb_count;
+            for (int i = 0; i < nnb; ++i) neighbour(s_nb[i], h, w, Ebg, Vbg, cnt_inactive);
+            if (s_nb_overflow) {
+                // rare: more overlapping neighbours than the list holds; scan the remaining slots in order
+                const int last_listed = s_nb[MAX_NB_LIST - 1];
+                for (int s = last_listed + 1; s < slot1; ++s)
+                    if (s != aslot) neighbour(s, h, w, Ebg, Vbg, cnt_inactive);
+            }
+            const bool covered = (w2 + 1) < pa.W2;               // strict last column, :349
+            double f0 = 0.0, g0[2] = {0.0, 0.0}, h0[3] = {0.0, 0.0, 0.0};
+            GalRaw gal;
+            gal.f = 0.0;
+            if (covered) {
+                star_eval<MODE>(LdGlobal(), pa.coefs, pa.n1, pa.n2, (double)h - am1 + 26.0, (double)w - am2 + 26.0, f0,
+                                g0, h0);
+                gal_eval<MODE, KT>(LdShared(), s_comps, pa.K, c_proto_nu, theta, (double)h, (double)w, gal);
+                acc[ACC_CNT_ACTIVE * PIX_THREADS + tid] += 1.0;
+            }
+            acc[ACC_CNT_INACTIVE * PIX_THREADS + tid] += cnt_inactive;
+            pixel_accumulate<MODE>(acc + tid, PIX_THREADS, pc, Ebg, Vbg, covered, cb, f0, g0, h0, gal);
         }
-        const bool covered = (w2 + 1) < pa.W2;               // strict last column, :349
-        double f0 = 0.0, g0[2] = {0.0, 0.0}, h0[3] = {0.0, 0.0, 0.0};
-        GalRaw gal;
-        gal.f = 0.0;
-        if (covered) {
-            star_eval<MODE>(LdGlobal(), pa.coefs, pa.n1, pa.n2, (double)h - am1 + 26.0, (double)w - am2 + 26.0, f0, g0,
-                            h0);
-            gal_eval<MODE>(LdShared(), s_comps, pa.K, c_proto_nu, theta, (double)h, (double)w, gal);
-            acc[ACC_CNT_ACTIVE * PIX_THREADS + tid] += 1.0;
-        }
-        acc[ACC_CNT_INACTIVE * PIX_THREADS + tid] += cnt_inactive;
-        pixel_accumulate<MODE>(acc + tid, PIX_THREADS, pc, Ebg, Vbg, covered, cb, f0, g0, h0, gal);
+        cur = nxt;
     }
     __syncthreads();
 
@@ -283,7 +335,7 @@ constexpr int EPI_THREADS = 128;
 constexpr int NY = 10;   // intermediate variables: c (4) then y (6)
 
 template <int MODE>
-__global__ void __launch_bounds__(EPI_THREADS) epilogue_kernel(PlanDev plan, FieldDev field,
+__global__ void __launch_bounds__(EPI_THREADS) epilogue_kernel(PlanDev plan,
                                                                const double* __restrict__ vp, double* __restrict__ out_v,
                                                                double* __restrict__ out_d, double* __restrict__ out_h,
                                                                long long* __restrict__ out_counters,
@@ -302,6 +354,7 @@ __global__ void __launch_bounds__(EPI_THREADS) epilogue_kernel(PlanDev plan, Fie
     const int tid = threadIdx.x;
     const int t = blockIdx.x;
     const int aslot = plan.act_slot[t];
+    const FieldDev field = plan.fields[plan.task_field[t]];
     const double* vs = vp + (size_t)NPARAM * aslot;
     const double* br = plan.slotbr + (size_t)aslot * SLOTBR_STRIDE;
 
@@ -330,7 +383,7 @@ __global__ void __launch_bounds__(EPI_THREADS) epilogue_kernel(PlanDev plan, Fie
             s_cnt[1] += ysum[ACC_CNT_INACTIVE];
         }
         if (MODE >= 1) {
-            const PatchDev& p = field.patches[plan.src_row[aslot] + (size_t)n * plan.S_tot];
+            const PatchDev& p = field.patches[plan.src_row[aslot] + (size_t)n * field.S_tot];
             const int b = field.images[n].band - 1;
             for (int i = tid; i < NY * NLIVE; i += EPI_THREADS) (&Jy[0][0])[i] = 0.0;
             __syncthreads();

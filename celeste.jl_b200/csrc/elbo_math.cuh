@@ -28,6 +28,7 @@
 
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define CEL_HD __host__ __device__ __forceinline__
@@ -56,6 +57,61 @@ constexpr int NACC_MODE0 = 3, NACC_MODE1 = 13, NACC_MODE2 = 68;
 template <int MODE> struct NAcc { static constexpr int value = MODE == 0 ? NACC_MODE0 : (MODE == 1 ? NACC_MODE1 : NACC_MODE2); };
 CEL_HD constexpr int tri6(int k, int l) { return k * 6 - (k * (k - 1)) / 2 + (l - k); }   // k <= l < 6
 CEL_HD constexpr int tri4(int k, int l) { return k * 4 - (k * (k - 1)) / 2 + (l - k); }   // k <= l < 4
+
+// ---------------------------------------------------------------------------------------------
+// exp(x) for x <= 0 (the only arguments this path produces: -q/2 of a Gaussian, and the negative
+// branch of softpluslikeinv).  Cody-Waite reduction x = k ln2 + r, |r| <= ln2/2, degree-10
+// near-minimax polynomial (Chebyshev interpolant; max relative error 3.2e-16 measured against
+// 50-digit arithmetic, tools/fit_exp.py), Estrin evaluation for instruction-level parallelism,
+// exponent spliced in with integer arithmetic.  No slow path: x is clamped to >= -708 (the result is
+// then ~3e-308 instead of a denormal/zero, far below anything the ELBO can resolve).
+// On the device the coefficients sit in constant memory so every DFMA takes its constant as a
+// c[bank][offset] operand instead of two UMOVs.
+#define CEL_EXP_COEFS                                                                                         \
+    {1.0, 1.0000000000000067, 0.50000000000000056, 0.16666666666554314, 0.041666666666573066,                \
+     0.0083333333856992122, 0.001388888893251478, 0.00019841170230570286, 2.4801504313785541e-05,           \
+     2.7640197391694839e-06, 2.7626371065696354e-07}
+#if defined(__CUDACC__)
+__constant__ double c_expc[11] = CEL_EXP_COEFS;
+#endif
+CEL_HD double exp_nonpos(double x) {
+#if defined(__CUDA_ARCH__)
+    const double* C = c_expc;
+#else
+    static const double C[11] = CEL_EXP_COEFS;
+#endif
+    x = x < -708.0 ? -708.0 : x;
+    const double SHIFT = 6755399441055744.0;   // 1.5 * 2^52
+    const double kd = fma(x, 1.4426950408889634, SHIFT);
+    const double kf = kd - SHIFT;
+    double r = fma(kf, -6.93147180369123816490e-01, x);
+    r = fma(kf, -1.90821492927058770002e-10, r);
+    const double r2 = r * r;
+    const double a0 = fma(C[1], r, C[0]);
+    const double a1 = fma(C[3], r, C[2]);
+    const double a2 = fma(C[5], r, C[4]);
+    const double a3 = fma(C[7], r, C[6]);
+    const double a4 = fma(C[9], r, C[8]);
+    const double r4 = r2 * r2;
+    const double b0 = fma(a1, r2, a0);
+    const double b1 = fma(a3, r2, a2);
+    const double b2 = fma(C[10], r2, a4);
+    const double r8 = r4 * r4;
+    const double p = fma(b2, r8, fma(b1, r4, b0));
+#if defined(__CUDA_ARCH__)
+    const int k = __double2loint(kd);
+    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+#else
+    long long bits, kb;
+    memcpy(&kb, &kd, 8);
+    const int k = (int)(kb & 0xffffffffLL);
+    memcpy(&bits, &p, 8);
+    bits += (long long)k << 52;
+    double out;
+    memcpy(&out, &bits, 8);
+    return out;
+#endif
+}
 
 // ---------------------------------------------------------------------------------------------
 // Cubic B-spline (Interpolations.jl BSpline(Cubic(Line())), OnGrid; un-vendored dependency,
@@ -117,7 +173,7 @@ CEL_HD void star_eval(LD ld, const double* coefs, int n1, int n2, double ax, dou
     }
     // softpluslikeinv, fsm_util.jl:222
     if (v < 0) {
-        const double e = 1e-3 * exp(v);
+        const double e = 1e-3 * exp_nonpos(v);
         f0 = e;
         if (MODE >= 1) {
             g0[0] = e * gx;
@@ -153,73 +209,91 @@ struct GalRaw {
     double R[21];
 };
 
-template <int MODE, typename LD>
-CEL_HD void gal_eval(LD ld, const double* comps, int K, const double* nu /*14*/, double theta, double hx, double wy,
-                     GalRaw& o) {
-    double f = 0, ft = 0;
-    double ax1 = 0, ax2 = 0, tx1 = 0, tx2 = 0;           // sum w p, sum wd p
-    double u1 = 0, u2 = 0, u3 = 0;                       // sum w gS          (xx block: heat-equation identity)
-    double as1 = 0, as2 = 0, as3 = 0;                    // sum w nu gS
-    double ts1 = 0, ts2 = 0, ts3 = 0;                    // sum wd nu gS
-    double xs11 = 0, xs12 = 0, xs13 = 0, xs21 = 0, xs22 = 0, xs23 = 0;   // sum w nu (HxS + gx gS')
-    double ss11 = 0, ss12 = 0, ss13 = 0, ss22 = 0, ss23 = 0, ss33 = 0;   // sum w nu^2 (HSS + gS gS')
-    const int ncomp = NPROTO * K;
-    const int ndev = NPROTO_DEV * K;
-    for (int c = 0; c < ncomp; ++c) {
-        const double* cp = comps + c * COMP_STRIDE;
-        const double mu1 = ld(cp), mu2 = ld(cp + 1), l11 = ld(cp + 2), l12 = ld(cp + 3), l22 = ld(cp + 4),
-                     z = ld(cp + 5);
-        const bool dev = c < ndev;
-        const double thc = dev ? theta : 1.0 - theta;
-        const double d1 = hx - mu1, d2 = wy - mu2;
-        const double p1 = l11 * d1 + l12 * d2;
-        const double p2 = l12 * d1 + l22 * d2;
-        const double q = d1 * p1 + d2 * p2;
-        const double fp = z * exp(-0.5 * q);     // f_pre, BivariateNormals.jl:219
-        const double w = thc * fp;
-        f += w;
-        if (MODE >= 1) {
-            const double nuc = nu[c / K];
-            const double wd = dev ? fp : -fp;    // gal_frac_dev_dir * f_pre, fsm_util.jl:291
-            ft += wd;
-            ax1 += w * p1;
-            ax2 += w * p2;
-            const double a = p1 * p1, b = p1 * p2, cc = p2 * p2;
-            const double g1 = 0.5 * a - 0.5 * l11;   // bvn_sig_d, BivariateNormals.jl:267-272
-            const double g2 = b - l12;
-            const double g3 = 0.5 * cc - 0.5 * l22;
-            const double wn = w * nuc;
-            as1 += wn * g1;
-            as2 += wn * g2;
-            as3 += wn * g3;
-            if (MODE >= 2) {
-                const double wdn = wd * nuc;
-                tx1 += wd * p1;
-                tx2 += wd * p2;
-                ts1 += wdn * g1;
-                ts2 += wdn * g2;
-                ts3 += wdn * g3;
-                u1 += w * g1;
-                u2 += w * g2;
-                u3 += w * g3;
-                // bvn_xsig_h (BivariateNormals.jl:310-316) + g_x g_S', with g_x = -p
-                xs11 += wn * (p1 * (l11 - g1));
-                xs12 += wn * (p1 * (l12 - g2) + p2 * l11);
-                xs13 += wn * (p2 * l12 - p1 * g3);
-                xs21 += wn * (p1 * l12 - p2 * g1);
-                xs22 += wn * (p2 * (l12 - g2) + p1 * l22);
-                xs23 += wn * (p2 * (l22 - g3));
-                // bvn_sigsig_h (BivariateNormals.jl:293-306, dsiginv_dsig:168-183) + g_S g_S'
-                const double wnn = wn * nuc;
-                ss11 += wnn * (l11 * (0.5 * l11 - a) + g1 * g1);
-                ss12 += wnn * (l12 * (l11 - a) - b * l11 + g1 * g2);
-                ss13 += wnn * (l12 * (0.5 * l12 - b) + g1 * g3);
-                ss22 += wnn * (l22 * (l11 - a) + l12 * (l12 - 2.0 * b) - cc * l11 + g2 * g2);
-                ss23 += wnn * (l12 * (l22 - cc) - b * l22 + g2 * g3);
-                ss33 += wnn * (l22 * (0.5 * l22 - cc) + g3 * g3);
+// One group (DEV: the 8 de Vaucouleurs prototypes, else the 6 exponential ones) of the mixture.
+// KT > 0 fixes the PSF component count at compile time so the k loop unrolls and the K exp chains of
+// one prototype interleave; KT == 0 takes K at run time.
+struct GalAcc {
+    double f, ft, ax1, ax2, tx1, tx2, u1, u2, u3, as1, as2, as3, ts1, ts2, ts3;
+    double xs11, xs12, xs13, xs21, xs22, xs23, ss11, ss12, ss13, ss22, ss23, ss33;
+};
+
+template <int MODE, int KT, bool DEV, typename LD>
+CEL_HD void gal_group(LD ld, const double* comps, int Krt, const double* nu, double thc, double hx, double wy,
+                      GalAcc& A) {
+    const int K = KT > 0 ? KT : Krt;
+    const int j0 = DEV ? 0 : NPROTO_DEV, j1 = DEV ? NPROTO_DEV : NPROTO;
+    for (int j = j0; j < j1; ++j) {
+        const double nuc = nu[j];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const double* cp = comps + (j * K + k) * COMP_STRIDE;
+            const double mu1 = ld(cp), mu2 = ld(cp + 1), l11 = ld(cp + 2), l12 = ld(cp + 3), l22 = ld(cp + 4),
+                         z = ld(cp + 5);
+            const double d1 = hx - mu1, d2 = wy - mu2;
+            const double p1 = l11 * d1 + l12 * d2;
+            const double p2 = l12 * d1 + l22 * d2;
+            const double q = d1 * p1 + d2 * p2;
+            const double fp = z * exp_nonpos(-0.5 * q);     // f_pre, BivariateNormals.jl:219
+            const double w = thc * fp;
+            A.f += w;
+            if (MODE >= 1) {
+                const double wd = DEV ? fp : -fp;    // gal_frac_dev_dir * f_pre, fsm_util.jl:291
+                A.ft += wd;
+                A.ax1 += w * p1;
+                A.ax2 += w * p2;
+                const double a = p1 * p1, b = p1 * p2, cc = p2 * p2;
+                const double g1 = 0.5 * a - 0.5 * l11;   // bvn_sig_d, BivariateNormals.jl:267-272
+                const double g2 = b - l12;
+                const double g3 = 0.5 * cc - 0.5 * l22;
+                const double wn = w * nuc;
+                A.as1 += wn * g1;
+                A.as2 += wn * g2;
+                A.as3 += wn * g3;
+                if (MODE >= 2) {
+                    const double wdn = wd * nuc;
+                    A.tx1 += wd * p1;
+                    A.tx2 += wd * p2;
+                    A.ts1 += wdn * g1;
+                    A.ts2 += wdn * g2;
+                    A.ts3 += wdn * g3;
+                    A.u1 += w * g1;
+                    A.u2 += w * g2;
+                    A.u3 += w * g3;
+                    // bvn_xsig_h (BivariateNormals.jl:310-316) + g_x g_S', with g_x = -p
+                    A.xs11 += wn * (p1 * (l11 - g1));
+                    A.xs12 += wn * (p1 * (l12 - g2) + p2 * l11);
+                    A.xs13 += wn * (p2 * l12 - p1 * g3);
+                    A.xs21 += wn * (p1 * l12 - p2 * g1);
+                    A.xs22 += wn * (p2 * (l12 - g2) + p1 * l22);
+                    A.xs23 += wn * (p2 * (l22 - g3));
+                    // bvn_sigsig_h (BivariateNormals.jl:293-306, dsiginv_dsig:168-183) + g_S g_S'
+                    const double wnn = wn * nuc;
+                    A.ss11 += wnn * (l11 * (0.5 * l11 - a) + g1 * g1);
+                    A.ss12 += wnn * (l12 * (l11 - a) - b * l11 + g1 * g2);
+                    A.ss13 += wnn * (l12 * (0.5 * l12 - b) + g1 * g3);
+                    A.ss22 += wnn * (l22 * (l11 - a) + l12 * (l12 - 2.0 * b) - cc * l11 + g2 * g2);
+                    A.ss23 += wnn * (l12 * (l22 - cc) - b * l22 + g2 * g3);
+                    A.ss33 += wnn * (l22 * (0.5 * l22 - cc) + g3 * g3);
+                }
             }
         }
     }
+}
+
+template <int MODE, int KT, typename LD>
+CEL_HD void gal_eval(LD ld, const double* comps, int K, const double* nu /*14*/, double theta, double hx, double wy,
+                     GalRaw& o) {
+    GalAcc A;
+    A.f = A.ft = A.ax1 = A.ax2 = A.tx1 = A.tx2 = A.u1 = A.u2 = A.u3 = 0.0;
+    A.as1 = A.as2 = A.as3 = A.ts1 = A.ts2 = A.ts3 = 0.0;
+    A.xs11 = A.xs12 = A.xs13 = A.xs21 = A.xs22 = A.xs23 = 0.0;
+    A.ss11 = A.ss12 = A.ss13 = A.ss22 = A.ss23 = A.ss33 = 0.0;
+    gal_group<MODE, KT, true>(ld, comps, K, nu, theta, hx, wy, A);
+    gal_group<MODE, KT, false>(ld, comps, K, nu, 1.0 - theta, hx, wy, A);
+    const double f = A.f, ft = A.ft, ax1 = A.ax1, ax2 = A.ax2, tx1 = A.tx1, tx2 = A.tx2, u1 = A.u1, u2 = A.u2,
+                 u3 = A.u3, as1 = A.as1, as2 = A.as2, as3 = A.as3, ts1 = A.ts1, ts2 = A.ts2, ts3 = A.ts3;
+    const double xs11 = A.xs11, xs12 = A.xs12, xs13 = A.xs13, xs21 = A.xs21, xs22 = A.xs22, xs23 = A.xs23;
+    const double ss11 = A.ss11, ss12 = A.ss12, ss13 = A.ss13, ss22 = A.ss22, ss23 = A.ss23, ss33 = A.ss33;
     o.f = f;
     if (MODE >= 1) {
         o.r[0] = -ax1;
@@ -257,25 +331,27 @@ CEL_HD void gal_eval(LD ld, const double* comps, int K, const double* nu /*14*/,
 }
 
 // value-only mixture for a neighbour (is_active_source == false, fsm_util.jl:265)
-template <typename LD>
-CEL_HD double gal_value(LD ld, const double* comps, int K, double theta, double hx, double wy) {
-    double fd = 0, fe = 0;
-    const int ncomp = NPROTO * K;
-    const int ndev = NPROTO_DEV * K;
-    for (int c = 0; c < ncomp; ++c) {
-        const double* cp = comps + c * COMP_STRIDE;
-        const double mu1 = ld(cp), mu2 = ld(cp + 1), l11 = ld(cp + 2), l12 = ld(cp + 3), l22 = ld(cp + 4),
-                     z = ld(cp + 5);
-        const double d1 = hx - mu1, d2 = wy - mu2;
-        const double p1 = l11 * d1 + l12 * d2;
-        const double p2 = l12 * d1 + l22 * d2;
-        const double fp = z * exp(-0.5 * (d1 * p1 + d2 * p2));
-        if (c < ndev)
-            fd += fp;
-        else
-            fe += fp;
+template <int KT, typename LD>
+CEL_HD double gal_value(LD ld, const double* comps, int Krt, double theta, double hx, double wy) {
+    const int K = KT > 0 ? KT : Krt;
+    double fg[2] = {0.0, 0.0};
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+        const int j0 = g == 0 ? 0 : NPROTO_DEV, j1 = g == 0 ? NPROTO_DEV : NPROTO;
+        for (int j = j0; j < j1; ++j) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const double* cp = comps + (j * K + k) * COMP_STRIDE;
+                const double mu1 = ld(cp), mu2 = ld(cp + 1), l11 = ld(cp + 2), l12 = ld(cp + 3), l22 = ld(cp + 4),
+                             z = ld(cp + 5);
+                const double d1 = hx - mu1, d2 = wy - mu2;
+                const double p1 = l11 * d1 + l12 * d2;
+                const double p2 = l12 * d1 + l22 * d2;
+                fg[g] += z * exp_nonpos(-0.5 * (d1 * p1 + d2 * p2));
+            }
+        }
     }
-    return theta * fd + (1.0 - theta) * fe;
+    return theta * fg[0] + (1.0 - theta) * fg[1];
 }
 
 // ---------------------------------------------------------------------------------------------

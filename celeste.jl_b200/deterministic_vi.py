@@ -175,18 +175,24 @@ class DeviceField:
 class Plan:
     """A registered task list (celeste_plan): evaluate it repeatedly with new vp."""
 
-    def __init__(self, field: DeviceField, tasks_rows, tasks_active):
+    def __init__(self, field, tasks_rows, tasks_active, task_field=None):
+        """`field`: one DeviceField, or a list of them (celeste_plan_create_multi) with `task_field[t]`
+        the 0-based field of task t."""
         lib = _lib.load()
-        self.field = field
+        self.fields = list(field) if isinstance(field, (list, tuple)) else [field]
+        self.field = self.fields[0]
         dummy = [(r, a, np.zeros((44, len(r)))) for r, a in zip(tasks_rows, tasks_active)]
         self.task_ptr, self.src, self.active_ptr, self.act, _ = csr_tasks(dummy)
         self.n_tasks = len(dummy)
         self.n_src = int(self.task_ptr[-1])
         self.nd, self.nh = out_sizes(self.active_ptr)
         self._handle = C.c_void_p()
-        _lib.check(lib.celeste_plan_create(field._handle, C.byref(self._handle), self.n_tasks,
-                                           self.task_ptr.ctypes.data, self.src.ctypes.data,
-                                           self.active_ptr.ctypes.data, self.act.ctypes.data))
+        tf = np.zeros(self.n_tasks, dtype=np.int32) if task_field is None else np.asarray(task_field, dtype=np.int32)
+        assert tf.shape == (self.n_tasks,)
+        harr = (C.c_void_p * len(self.fields))(*[f._handle for f in self.fields])
+        _lib.check(lib.celeste_plan_create_multi(len(self.fields), harr, C.byref(self._handle), self.n_tasks,
+                                                 tf.ctypes.data, self.task_ptr.ctypes.data, self.src.ctypes.data,
+                                                 self.active_ptr.ctypes.data, self.act.ctypes.data))
         self._finalizer = weakref.finalize(self, lib.celeste_plan_destroy, self._handle)
 
     def enable_timing(self, on: bool = True):

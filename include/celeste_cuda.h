@@ -198,6 +198,15 @@ typedef struct celeste_plan celeste_plan;
 int celeste_plan_create(celeste_field* f, celeste_plan** out, int32_t n_tasks,
                         const int32_t* task_ptr, const int32_t* source_ids,
                         const int32_t* active_ptr, const int32_t* active_idx);
+/*
+ * One plan over the tasks of SEVERAL inference boxes (fields with the same image count N, e.g. the
+ * fields of a stripe handled by one process): task t belongs to fields[task_field[t]] (0-based) and
+ * its source ids index that field's patch matrix.  All tasks are evaluated by the same three kernel
+ * launches, so small boxes do not pay a launch tail each.
+ */
+int celeste_plan_create_multi(int32_t n_fields, celeste_field* const* fields, celeste_plan** out, int32_t n_tasks,
+                              const int32_t* task_field, const int32_t* task_ptr, const int32_t* source_ids,
+                              const int32_t* active_ptr, const int32_t* active_idx);
 void celeste_plan_destroy(celeste_plan* p);
 /* number of kernel launches one celeste_elbo_plan_device call enqueues */
 int celeste_plan_launches(const celeste_plan* p, int32_t mode);

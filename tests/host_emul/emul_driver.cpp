@@ -35,9 +35,16 @@ template <int MODE>
 void run(const PlanDev& pd, const FieldDev& fd, int n_blocks, int chunk_pixels, const double* vp, double* v, double* d,
          double* h, long long* counters, int* flags) {
     const size_t smem = ((size_t)NAcc<MODE>::value * PIX_THREADS + (size_t)MAX_COMPS * COMP_STRIDE) * sizeof(double);
-    cuda_emul::launch(setup_kernel, 2, 64, 0, pd, fd, vp);
-    if (n_blocks > 0) cuda_emul::launch(pixel_kernel<MODE>, n_blocks, PIX_THREADS, smem, pd, fd, chunk_pixels);
-    cuda_emul::launch(epilogue_kernel<MODE>, pd.n_tasks, EPI_THREADS, 0, pd, fd, vp, v, d, h, counters, flags);
+    cuda_emul::launch(setup_kernel, 2, 64, 0, pd, vp);
+    bool k2 = true;
+    for (int i = 0; i < fd.S_tot * pd.N; ++i) k2 = k2 && fd.patches[i].K == 2;
+    if (n_blocks > 0) {
+        if (k2)
+            cuda_emul::launch(pixel_kernel<MODE, 2>, n_blocks, PIX_THREADS, smem, pd, chunk_pixels);
+        else
+            cuda_emul::launch(pixel_kernel<MODE, 0>, n_blocks, PIX_THREADS, smem, pd, chunk_pixels);
+    }
+    cuda_emul::launch(epilogue_kernel<MODE>, pd.n_tasks, EPI_THREADS, 0, pd, vp, v, d, h, counters, flags);
 }
 }  // namespace
 
@@ -79,7 +86,7 @@ extern "C" int emul_elbo_batch(int32_t N, const celeste_image* imgs, int32_t S_t
     }
     const int n_slots = task_ptr[n_tasks];
     std::vector<int> src_row(n_slots), act_slot(n_tasks), chunk_ptr((size_t)n_tasks * N + 1, 0);
-    std::vector<int2> blockmap;
+    std::vector<BlockHdr> blockmap;
     for (int t = 0; t < n_tasks; ++t) {
         if (active_ptr[t + 1] - active_ptr[t] != 1) return CELESTE_ERR_UNSUPPORTED;
         act_slot[t] = task_ptr[t] + active_idx[active_ptr[t]] - 1;
@@ -92,16 +99,23 @@ extern "C" int emul_elbo_batch(int32_t N, const celeste_image* imgs, int32_t S_t
             const int nchunk = (int)((npix + chunk_pixels - 1) / chunk_pixels);
             const int tn = t * N + n;
             chunk_ptr[tn + 1] = chunk_ptr[tn] + nchunk;
-            for (int c = 0; c < nchunk; ++c) blockmap.push_back(make_int2(tn, c));
+            for (int c = 0; c < nchunk; ++c)
+                blockmap.push_back(BlockHdr{tn, c, act_slot[t], task_ptr[t], task_ptr[t + 1],
+                                            (int)((size_t)src_row[act_slot[t]] + (size_t)n * S_tot), n, 0});
         }
     std::vector<int> tp(task_ptr, task_ptr + n_tasks + 1);
     std::vector<double> slotimg((size_t)n_slots * N * SLOTIMG_STRIDE), slotbr((size_t)n_slots * SLOTBR_STRIDE),
         partials(blockmap.size() * NACC_MODE2 + 1);
     PlanDev pd;
+    FieldDev fd{images.data(), pdv.data(), S_tot, 0};
+    std::vector<int> tfield(n_tasks, 0), sfield(n_slots, 0);
     pd.n_tasks = n_tasks;
     pd.N = N;
-    pd.S_tot = S_tot;
+    pd.n_fields = 1;
     pd.n_slots = n_slots;
+    pd.fields = &fd;
+    pd.task_field = tfield.data();
+    pd.slot_field = sfield.data();
     pd.task_ptr = tp.data();
     pd.src_row = src_row.data();
     pd.act_slot = act_slot.data();
@@ -110,7 +124,6 @@ extern "C" int emul_elbo_batch(int32_t N, const celeste_image* imgs, int32_t S_t
     pd.slotimg = slotimg.data();
     pd.slotbr = slotbr.data();
     pd.partials = partials.data();
-    FieldDev fd{images.data(), pdv.data()};
     std::vector<long long> cnt(2 * (size_t)n_tasks);
     const int nb = (int)blockmap.size();
     if (mode == 0)

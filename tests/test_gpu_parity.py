@@ -104,6 +104,28 @@ def test_plan_device_path_matches_host_path(cj):
     assert plan.launches(2) == 3
 
 
+def test_multi_field_plan_equals_per_field_plans(cj):
+    """celeste_plan_create_multi: one plan over several inference boxes == the per-box plans, bit for bit."""
+    a = cases.get("small_field")
+    b = cases.get("config2")
+    c = cases.get("two_body")
+    fields, rows, act, tf, vps, single = [], [], [], [], [], []
+    for fi, (images, patches, tasks) in enumerate((a, b, c)):
+        f = cj.DeviceField(images, patches)
+        fields.append(f)
+        single.append(f.elbo_batch(tasks, mode=2))
+        for r, ac, vp in tasks:
+            rows.append(r)
+            act.append(ac)
+            tf.append(fi)
+            vps.append(vp.ravel(order="F"))
+    plan = cj.Plan(fields, rows, act, task_field=tf)
+    out = plan.run_host(np.concatenate(vps), 2)
+    for k in ("v", "d", "h"):
+        assert np.array_equal(out[k], np.concatenate([s[k] for s in single])), k
+    assert np.array_equal(out["counters"].reshape(-1, 2), np.concatenate([s["counters"] for s in single]))
+
+
 def test_deterministic_and_mode_consistent(cj):
     """Bit-identical across repeated launches (fixed-order reductions); the value does not depend on the mode."""
     images, patches, tasks = cases.get("small_field")
