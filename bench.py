@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=1000, help="tasks per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hessian", action="store_true")
+    ap.add_argument("--no-maximize", action="store_true", help="skip the config-5 leg (full Newton loop on field 0)")
     return ap.parse_args()
 
 
@@ -55,17 +56,10 @@ def build_stripe(n_fields, n_sources, device):
 
 def shard_tasks(ds, rank, world):
     """ParallelRun's cost model (sum of active pixels, ParallelRun.jl:45-56): tasks sorted by cost and dealt
-    greedily to the least-loaded rank."""
-    cost = np.array([sum(int(p.active_pixel_bitmap.sum()) for p in ds.patches[s, :]) for s in range(len(ds.catalog))])
-    order = np.argsort(-cost, kind="stable")
-    load = np.zeros(world)
-    mine = []
-    for s in order:
-        r = int(np.argmin(load))
-        load[r] += cost[s]
-        if r == rank:
-            mine.append(int(s))
-    return sorted(mine)
+    greedily to the least-loaded rank (celeste_jl_b200.parallel_run.shard_sources)."""
+    from celeste_jl_b200 import parallel_run
+    cost = [parallel_run.estimate_time(ds.patches[s, :]) for s in range(len(ds.catalog))]
+    return parallel_run.shard_sources(cost, rank, world)
 
 
 class ClockSampler:
@@ -195,7 +189,18 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout; keep stdout for the one JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     import celeste_jl_b200 as cj
     from celeste_jl_b200 import _lib
 
@@ -325,21 +330,48 @@ def main():
 
     def roofline(m, mode):
         flop = m["active"] * F_ACTIVE[mode] + m["inactive"] * F_INACTIVE
-        ach = flop / (m["pix_ms"] * 1e-3) / 1e12
-        r = {"bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+        ach = flop / (m["pix_ms"] * 1e-3) / 1e12          # aggregate over ranks (flop summed, time = max over ranks)
+        r = {"bound": "fp64", "achieved": ach, "peak": peak * world, "unit": "TFLOP/s", "frac": ach / (peak * world),
+             "peak_per_gpu": peak,
              "traffic": None, "kernel": f"pixel_kernel<{mode}>", "kernel_ms_per_step": m["pix_ms"],
              "kernel_share_of_step": m["pix_ms"] / m["ms"],
              "algorithmic_flop_per_step": flop, "pixel_visits_active": m["active"], "pixel_visits_inactive": m["inactive"],
              "peak_source": "measured live: celeste_fp64_peak (register DFMA chain); nominal 37 TFLOP/s",
              "hbm": {"achieved_gbs": (m["active"] + m["inactive"]) * BYTES_PER_VISIT / (m["pix_ms"] * 1e-3) / 1e9,
                      "peak_gbs": hbm_peak()}}
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel on this workload at N=1,
+        # from the committed `ncu --set full` capture (profiles/ncu_traffic.json); per rank the launch is 1/N of it
         prof = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(prof):
             try:
-                r["traffic"] = json.load(open(prof)).get(f"pixel_kernel<{mode}>")
+                t = json.load(open(prof)).get(f"pixel_kernel<{mode}>")
+                if t and t.get("sources") == int(total_sources):
+                    r["traffic"] = t["dram_bytes_per_launch"] / world
+                    r["traffic_source"] = t
             except Exception:
                 pass
         return r
+
+    # configs[4]: the full maximize! loop (ELBO + gradient + Hessian + KL, Newton trust region, 50 iterations max)
+    # on the 1000-source field 0, this rank's shard of the targets, all in lock-step on the GPU
+    maximize_leg = None
+    if not args.no_maximize:
+        from celeste_jl_b200 import parallel_run as pr
+        ds0 = stripe[0]
+        nmap = {s: ds0.neighbors[s] for s in range(len(ds0.catalog))}
+        barrier()
+        t0 = time.perf_counter()
+        _, res = pr.one_node_single_infer(ds0.catalog, ds0.patches, list(range(len(ds0.catalog))), nmap, ds0.images,
+                                          field=fields[0], include_kl=True, rank=rank, world=world)
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        maximize_leg = {"sources": int(sum_over_ranks(len(res.value))), "seconds": dt,
+                        "sources_per_s": sum_over_ranks(len(res.value)) / dt,
+                        "lockstep_iterations": int(max_over_ranks(res.total_steps)),
+                        "mean_newton_iterations": sum_over_ranks(float(res.iterations.sum())) / sum_over_ranks(len(res.value)),
+                        "converged_fraction": sum_over_ranks(float(res.converged.sum())) / sum_over_ranks(len(res.value)),
+                        "what": "ParallelRun.one_node_single_infer on field 0 (1000 sources): generic init, KL included, "
+                                "Newton trust region x_tol 1e-7 / f_tol 1e-6 / g_tol 1e-8 / 50 iterations"}
 
     if rank != 0:
         if world > 1:
@@ -362,6 +394,8 @@ def main():
     if hess is not None:
         line["hessian"] = {"value": total_sources / (hess["ms"] * 1e-3), "unit": "sources/s", "ms_per_step": hess["ms"],
                            "e2e": e2e(hess, 2), "roofline": roofline(hess, 2)}
+    if not args.no_maximize:
+        line["maximize"] = maximize_leg
     if world == 1 and not args.no_cpu_baseline:
         cb = cpu_leg(stripe[0], args.cpu_sample, 1, 3, 1)
         line["cpu_baseline"] = cb

@@ -59,33 +59,34 @@ CEL_HD constexpr int tri6(int k, int l) { return k * 6 - (k * (k - 1)) / 2 + (l 
 CEL_HD constexpr int tri4(int k, int l) { return k * 4 - (k * (k - 1)) / 2 + (l - k); }   // k <= l < 4
 
 // ---------------------------------------------------------------------------------------------
-// exp(x) for x <= 0 (the only arguments this path produces: -q/2 of a Gaussian, and the negative
-// branch of softpluslikeinv).  Cody-Waite reduction x = k ln2 + r, |r| <= ln2/2, degree-10
-// near-minimax polynomial (Chebyshev interpolant; max relative error 3.2e-16 measured against
-// 50-digit arithmetic, tools/fit_exp.py), Estrin evaluation for instruction-level parallelism,
-// exponent spliced in with integer arithmetic.  No slow path: x is clamped to >= -708 (the result is
-// then ~3e-308 instead of a denormal/zero, far below anything the ELBO can resolve).
+// exp(s*q) for s*q <= 0 (the only arguments this path produces: -q/2 of a Gaussian, and the negative
+// branch of softpluslikeinv), computed as 2^y with y = q * (s * log2 e):
+//   k = rint(y) by the 1.5*2^52 shift, f = y - k EXACTLY (no Cody-Waite constants needed), |f| <= 1/2,
+//   2^f by a degree-10 near-minimax polynomial (Chebyshev interpolant; max relative error 6.7e-16
+//   measured against 50-digit arithmetic, tools/fit_exp.py), Estrin order for instruction-level
+//   parallelism, exponent spliced in with integer arithmetic.
+// No slow path and no FP64 compare: the integer exponent is clamped at -1022 (the result is then
+// ~1e-308 instead of a denormal/zero, far below anything the ELBO can resolve).  The rounding of y
+// costs |y| * 1.1e-16 relative accuracy (1e-14 at q = 200, where the term is already e^-100).
 // On the device the coefficients sit in constant memory so every DFMA takes its constant as a
 // c[bank][offset] operand instead of two UMOVs.
-#define CEL_EXP_COEFS                                                                                         \
-    {1.0, 1.0000000000000067, 0.50000000000000056, 0.16666666666554314, 0.041666666666573066,                \
-     0.0083333333856992122, 0.001388888893251478, 0.00019841170230570286, 2.4801504313785541e-05,           \
-     2.7640197391694839e-06, 2.7626371065696354e-07}
+#define CEL_EXP2_COEFS                                                                                          \
+    {1.0, 0.69314718055994995, 0.24022650695910097, 0.055504108664447417, 0.0096181291076068709,               \
+     0.0013333558230215262, 0.00015403530441765088, 1.5252657229551429e-05, 1.3215442570224649e-06,            \
+     1.0208696429374313e-07, 7.0725894883963448e-09}
 #if defined(__CUDACC__)
-__constant__ double c_expc[11] = CEL_EXP_COEFS;
+__constant__ double c_expc[11] = CEL_EXP2_COEFS;
 #endif
-CEL_HD double exp_nonpos(double x) {
+CEL_HD double exp_scaled(double q, double s) {
 #if defined(__CUDA_ARCH__)
     const double* C = c_expc;
 #else
-    static const double C[11] = CEL_EXP_COEFS;
+    static const double C[11] = CEL_EXP2_COEFS;
 #endif
-    x = x < -708.0 ? -708.0 : x;
     const double SHIFT = 6755399441055744.0;   // 1.5 * 2^52
-    const double kd = fma(x, 1.4426950408889634, SHIFT);
-    const double kf = kd - SHIFT;
-    double r = fma(kf, -6.93147180369123816490e-01, x);
-    r = fma(kf, -1.90821492927058770002e-10, r);
+    const double y = q * (s * 1.4426950408889634074);
+    const double kd = y + SHIFT;
+    const double r = y - (kd - SHIFT);
     const double r2 = r * r;
     const double a0 = fma(C[1], r, C[0]);
     const double a1 = fma(C[3], r, C[2]);
@@ -99,12 +100,14 @@ CEL_HD double exp_nonpos(double x) {
     const double r8 = r4 * r4;
     const double p = fma(b2, r8, fma(b1, r4, b0));
 #if defined(__CUDA_ARCH__)
-    const int k = __double2loint(kd);
+    int k = __double2loint(kd);
+    k = k < -1022 ? -1022 : k;
     return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
 #else
     long long bits, kb;
     memcpy(&kb, &kd, 8);
-    const int k = (int)(kb & 0xffffffffLL);
+    int k = (int)(kb & 0xffffffffLL);
+    k = k < -1022 ? -1022 : k;
     memcpy(&bits, &p, 8);
     bits += (long long)k << 52;
     double out;
@@ -112,6 +115,7 @@ CEL_HD double exp_nonpos(double x) {
     return out;
 #endif
 }
+CEL_HD double exp_nonpos(double x) { return exp_scaled(x, 1.0); }
 
 // ---------------------------------------------------------------------------------------------
 // Cubic B-spline (Interpolations.jl BSpline(Cubic(Line())), OnGrid; un-vendored dependency,
@@ -233,7 +237,7 @@ CEL_HD void gal_group(LD ld, const double* comps, int Krt, const double* nu, dou
             const double p1 = l11 * d1 + l12 * d2;
             const double p2 = l12 * d1 + l22 * d2;
             const double q = d1 * p1 + d2 * p2;
-            const double fp = z * exp_nonpos(-0.5 * q);     // f_pre, BivariateNormals.jl:219
+            const double fp = z * exp_scaled(q, -0.5);       // f_pre, BivariateNormals.jl:219
             const double w = thc * fp;
             A.f += w;
             if (MODE >= 1) {
@@ -347,7 +351,7 @@ CEL_HD double gal_value(LD ld, const double* comps, int Krt, double theta, doubl
                 const double d1 = hx - mu1, d2 = wy - mu2;
                 const double p1 = l11 * d1 + l12 * d2;
                 const double p2 = l12 * d1 + l22 * d2;
-                fg[g] += z * exp_nonpos(-0.5 * (d1 * p1 + d2 * p2));
+                fg[g] += z * exp_scaled(d1 * p1 + d2 * p2, -0.5);
             }
         }
     }

@@ -1,0 +1,202 @@
+"""Batched Newton trust-region maximisation of the ELBO -- rows (f.1)/(f.2) of SURVEY.md section 8.
+
+Mirror of src/deterministic_vi/ElboMaximize.jl: `maximize!(ea, vp)` (:228-242) drives
+Optim.NewtonTrustRegion (initial_delta = 1, delta_hat = 1e9, :105-108) on the 41 free parameters with
+`Optim.Options(x_tol = 1e-7, f_tol = 1e-6, g_tol = 1e-8, iterations = 50)` (:95-103); each new iterate costs
+one `evaluate!` (:161-172) = to_bound! -> elbo (likelihood - KL) -> propagate_derivatives!.
+
+The reference optimises one source per thread, one ELBO evaluation at a time (~10 us of GPU work each).
+Here ALL sources of a batch step in lock-step: one iteration = one CUDA plan evaluation (value + gradient +
+Hessian for every source) + batched 41 x 41 eigen-decompositions (torch.linalg.eigh) for the trust-region
+subproblem; sources that have converged simply stop moving.  Everything stays on the device between
+iterations.
+
+Optim.jl is an un-vendored dependency (REQUIRE:13, >= 0.7.4): its NewtonTrustRegion is restated from the
+published algorithm (Nocedal & Wright, Alg. 4.1 for the radius update and the exact subproblem solution by
+the secular equation in the eigenbasis, incl. the hard case); iterates need not match Optim's bit for bit,
+the optimum and the stopping rules do.  PARITY UNPINNED for this row (no reference run is possible offline).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import constraint_transforms as ct
+from .kl import KLTerm
+
+ETA, RHO_LOWER, RHO_UPPER = 0.1, 0.25, 0.75     # Optim.NewtonTrustRegion defaults
+X_TOL, F_TOL, G_TOL, MAX_ITERS = 1e-7, 1e-6, 1e-8, 50
+INITIAL_DELTA, DELTA_HAT = 1.0, 1e9
+
+
+def solve_tr_subproblem(g: torch.Tensor, H: torch.Tensor, delta: torch.Tensor):
+    """min_s g's + 1/2 s'Hs  s.t. |s| <= delta, batched (B x n, B x n x n, B).
+    Returns (s, m = predicted change, interior flag)."""
+    B, n = g.shape
+    ev, Q = torch.linalg.eigh(H)                       # ascending
+    qg = torch.einsum("bij,bi->bj", Q, g)              # Q' g
+    d2 = delta * delta
+    lam_min = ev[:, 0]
+
+    def pnorm2(lam):                                   # |s(lam)|^2 = sum (qg_i / (ev_i + lam))^2
+        den = ev + lam[:, None]
+        return ((qg / den) ** 2).sum(dim=1)
+
+    zero = torch.zeros_like(delta)
+    pos_def = lam_min >= 1e-8
+    interior = pos_def & (pnorm2(torch.where(pos_def, zero, 1.0 - lam_min)) <= d2)
+    # boundary solution: find lam > max(0, -lam_min) with |s(lam)| = delta (secular equation, Newton on 1/|s|)
+    lam_lb = torch.clamp(-lam_min, min=0.0)
+    tiny = 1e-12 * (1.0 + ev.abs().max(dim=1).values)
+    # hard case: g orthogonal to the eigenspace of lam_min and |s(-lam_min)| < delta
+    scale = qg.abs().max(dim=1, keepdim=True).values + 1e-300
+    at_min = (ev - lam_min[:, None]).abs() <= 1e-12 * (1.0 + ev.abs())
+    ortho = ((qg.abs() <= 1e-12 * scale) | ~at_min).all(dim=1)
+    den_h = torch.where(at_min, torch.ones_like(ev), ev - lam_min[:, None])
+    s_h_coef = torch.where(at_min, torch.zeros_like(qg), -qg / den_h)
+    ph2 = (s_h_coef ** 2).sum(dim=1)
+    hard = (~interior) & ortho & (lam_min <= 1e-8) & (ph2 <= d2)
+    lam = lam_lb + tiny                                # start just above the pole: Newton on 1/|s| is monotone
+    for _ in range(60):
+        den = ev + lam[:, None]
+        p2 = ((qg / den) ** 2).sum(dim=1)
+        pn = torch.sqrt(p2)
+        # d|s|^2/dlam = -2 sum qg^2/(ev+lam)^3
+        dp2 = -2.0 * ((qg ** 2) / den ** 3).sum(dim=1)
+        # Newton on phi(lam) = 1/delta - 1/|s|:  lam += (|s| - delta)/delta * |s|^2 / (-0.5 dp2)
+        step = (pn - delta) / delta * p2 / (-0.5 * dp2 + 1e-300)
+        new = lam + step
+        new = torch.where(new <= lam_lb, 0.5 * (lam + lam_lb) + tiny, new)
+        done = (step.abs() <= 1e-12 * (1.0 + lam.abs()))
+        lam = torch.where(done | interior | hard, lam, new)
+    lam = torch.where(interior, zero, lam)
+    lam = torch.where(hard, -lam_min, lam)
+    den = ev + lam[:, None]
+    coef = -qg / torch.where(den.abs() < 1e-300, torch.full_like(den, 1e-300), den)
+    coef = torch.where(hard[:, None], s_h_coef, coef)
+    tau = torch.sqrt(torch.clamp(d2 - ph2, min=0.0))
+    coef[:, 0] = torch.where(hard, tau, coef[:, 0])   # move along the lowest eigenvector to the boundary
+    s = torch.einsum("bij,bj->bi", Q, coef)
+    m = (g * s).sum(dim=1) + 0.5 * torch.einsum("bi,bij,bj->b", s, H, s)
+    return s, m, interior
+
+
+@dataclass
+class MaximizeResult:
+    vp: np.ndarray            # n x 44 optimised bound parameters (active sources)
+    value: np.ndarray         # n  maximised ELBO (likelihood - KL)
+    iterations: np.ndarray    # n  Newton iterations taken
+    f_calls: np.ndarray       # n  ELBO evaluations
+    converged: np.ndarray     # n  bool
+    total_steps: int          # lock-step iterations of the batch (== plan evaluations - 1)
+
+
+class BatchMaximizer:
+    """maximize! for every task of a plan at once (Sa = 1 per task; neighbours frozen during the solve,
+    as inside one `maximize!` call of the reference)."""
+
+    def __init__(self, plan, vp_flat: np.ndarray, include_kl: bool = True, device: Optional[str] = None,
+                 loc_width: float = 1e-4, max_iters: int = MAX_ITERS, runner=None):
+        """`runner(self)` evaluates the plan's tasks at self.vp_all and fills self.v/d/h/flags; the default
+        launches the CUDA plan on the current stream.  (Tests inject a CPU checker here.)"""
+        self.plan = plan
+        self.runner = runner
+        self.dev = torch.device(device or "cuda")
+        self.n = plan.n_tasks
+        self.max_iters = max_iters
+        self.include_kl = include_kl
+        self.kl = KLTerm(self.dev) if include_kl else None
+        dt = torch.float64
+        self.vp_all = torch.as_tensor(vp_flat, dtype=dt, device=self.dev).reshape(-1, 44).clone()   # n_slots x 44
+        # slot of the active source of each task
+        task_ptr = plan.task_ptr.astype(np.int64)
+        act = plan.act.astype(np.int64)
+        self.aslot = torch.as_tensor(task_ptr[:-1] + act - 1, device=self.dev)
+        n = self.n
+        self.v = torch.zeros(n, dtype=dt, device=self.dev)
+        self.d = torch.zeros(n * 44, dtype=dt, device=self.dev)
+        self.h = torch.zeros(n * 44 * 44, dtype=dt, device=self.dev)
+        self.cnt = torch.zeros(2 * n, dtype=torch.int64, device=self.dev)
+        self.flags = torch.zeros(n, dtype=torch.int32, device=self.dev)
+        vp0 = self.vp_all[self.aslot]
+        self.lo, self.hi = ct.box_bounds(vp0, loc_width)          # position box fixed at the start (ElboMaximize.jl:68-71)
+        vp0 = ct.enforce(vp0, self.lo, self.hi)                   # enforce! :230
+        self.x = ct.to_free(vp0, self.lo, self.hi)                # to_free! :231
+        self.f_calls = 0
+
+    def evaluate(self, x: torch.Tensor):
+        """evaluate! (ElboMaximize.jl:161-172): negative ELBO, gradient and Hessian in free coordinates."""
+        bound = ct.to_bound(x, self.lo, self.hi)
+        self.vp_all[self.aslot] = bound
+        if self.runner is not None:
+            self.runner(self)
+        else:
+            self._run_plan(torch.cuda.current_stream())
+        v = self.v.clone()
+        g = self.d.reshape(self.n, 44).clone()
+        H = self.h.reshape(self.n, 44, 44).clone()
+        if self.include_kl:
+            kv, kg, kH = self.kl(bound, order=2)
+            v += kv
+            g += kg
+            H += kH
+        gf, Hf = ct.propagate_derivatives(x, self.lo, self.hi, g, H)
+        self.f_calls += 1
+        bad = self.flags != 0
+        return -v, -gf, -Hf, bad, bound
+
+    def _run_plan(self, stream):
+        self.plan.run_device(self.vp_all.data_ptr(), 2, self.v.data_ptr(), self.d.data_ptr(), self.h.data_ptr(),
+                             self.cnt.data_ptr(), self.flags.data_ptr(), stream=stream.cuda_stream)
+
+    def run(self) -> MaximizeResult:
+        n, dev = self.n, self.dev
+        x = self.x
+        f, g, H, bad, bound = self.evaluate(x)
+        delta = torch.full((n,), INITIAL_DELTA, dtype=torch.float64, device=dev)
+        active = ~bad & (g.abs().max(dim=1).values >= G_TOL)       # initial g_tol check
+        converged = ~bad & ~active
+        iters = torch.zeros(n, dtype=torch.int64, device=dev)
+        fcalls = torch.ones(n, dtype=torch.int64, device=dev)
+        steps = 0
+        for _ in range(self.max_iters):
+            if not bool(active.any()):
+                break
+            steps += 1
+            s, m, interior = solve_tr_subproblem(g, H, delta)
+            x_new = torch.where(active[:, None], x + s, x)
+            f_new, g_new, H_new, bad_new, _ = self.evaluate(x_new)
+            fcalls += active.to(torch.int64)
+            f_diff = f - f_new
+            eps = torch.finfo(torch.float64).eps
+            rho = torch.where(m.abs() <= eps, torch.ones_like(m),
+                              torch.where(m > 0, torch.full_like(m, RHO_LOWER - 1.0), f_diff / (-m)))
+            rho = torch.where(bad_new | ~torch.isfinite(f_new), torch.full_like(rho, RHO_LOWER - 1.0), rho)
+            shrink = rho < RHO_LOWER
+            grow = (rho > RHO_UPPER) & ~interior
+            delta = torch.where(active & shrink, delta * 0.25, delta)
+            delta = torch.where(active & grow, torch.clamp(2 * delta, max=DELTA_HAT), delta)
+            accept = active & (rho > ETA)
+            # convergence is assessed only on accepted steps (Optim assess_convergence for NewtonTrustRegion)
+            x_conv = (x_new - x).abs().max(dim=1).values < X_TOL
+            f_conv = (f_new - f).abs() <= F_TOL * f_new.abs()
+            g_conv = g_new.abs().max(dim=1).values < G_TOL
+            newly = accept & (x_conv | f_conv | g_conv)
+            a1, a2 = accept[:, None], accept[:, None, None]
+            x = torch.where(a1, x_new, x)
+            f = torch.where(accept, f_new, f)
+            g = torch.where(a1, g_new, g)
+            H = torch.where(a2, H_new, H)
+            iters += active.to(torch.int64)
+            converged = converged | newly
+            # a trust region collapsed to nothing cannot make progress any more
+            dead = active & (delta < 1e-14)
+            active = active & ~newly & ~dead
+        self.x = x
+        bound = ct.to_bound(x, self.lo, self.hi)                  # maximize! :239-240
+        self.vp_all[self.aslot] = bound
+        return MaximizeResult(bound.cpu().numpy(), (-f).cpu().numpy(), iters.cpu().numpy(), fcalls.cpu().numpy(),
+                              converged.cpu().numpy(), steps)

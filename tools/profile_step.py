@@ -1,4 +1,6 @@
-"""Minimal driver for ncu: one 1000-source field, a few evaluations per mode (no torch kernels in between)."""
+"""Driver for ncu captures: the SAME workload as bench.py (multi-field plan over the synthetic stripe),
+a few evaluations per mode, no torch kernels between them.
+    python tools/profile_step.py <fields> <modes e.g. 1,2> <reps>"""
 import os
 import sys
 import numpy as np
@@ -6,17 +8,23 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import celeste_jl_b200 as cj  # noqa: E402
-from celeste_jl_b200 import synthetic  # noqa: E402
+import bench  # noqa: E402
 
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
+n_fields = int(sys.argv[1]) if len(sys.argv) > 1 else 10
 modes = [int(m) for m in sys.argv[2].split(",")] if len(sys.argv) > 2 else [1, 2]
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
-ds = synthetic.FieldDataset(n, H=2048, W=1489, seed=42, pixel_seed=1)
-field = cj.DeviceField(ds.images, ds.patches)
-rows, act = ds.tasks()
-plan = field.make_plan(rows, act)
-vp = ds.vp_flat(rows)
+stripe = bench.build_stripe(n_fields, 1000, device=None)
+fields, rows, act, tf, vps = [], [], [], [], []
+for fi, ds in enumerate(stripe):
+    fields.append(cj.DeviceField(ds.images, ds.patches))
+    r, a = ds.tasks()
+    rows += r
+    act += a
+    tf += [fi] * len(r)
+    vps.append(ds.vp_flat(r))
+plan = cj.Plan(fields, rows, act, task_field=tf)
+vp = np.concatenate(vps)
 for mode in modes:
     for _ in range(reps):
         out = plan.run_host(vp, mode)
-    print("mode", mode, "v[0]", out["v"][0], "visits", out["counters"].sum(axis=0) if out["counters"].ndim > 1 else out["counters"].reshape(-1, 2).sum(axis=0))
+    print("mode", mode, "tasks", plan.n_tasks, "v[0]", out["v"][0], "visits", out["counters"].reshape(-1, 2).sum(axis=0))
