@@ -20,6 +20,7 @@
 
 #include "../../include/celeste_cuda.h"
 #include "celeste_kernels.cuh"
+#include "newton_kernels.cuh"
 
 using namespace celeste;
 
@@ -629,6 +630,21 @@ int celeste_elbo_single(celeste_field* f, int32_t S, const int32_t* source_ids, 
     const int32_t task_ptr[2] = {0, S};
     const int32_t active_ptr[2] = {0, Sa};
     return celeste_elbo_batch(f, 1, task_ptr, source_ids, active_ptr, active_idx, vp, mode, v, d, h, counters, flags);
+}
+
+int celeste_tr_subproblem(int32_t batch, int32_t n, const double* g_dev, const double* H_dev, const double* delta_dev,
+                          double* s_dev, double* m_dev, int32_t* interior_dev, void* cuda_stream) {
+    if (batch < 0 || n < 1 || n > TR_MAXN - 1 || !g_dev || !H_dev || !delta_dev || !s_dev || !m_dev || !interior_dev) {
+        set_detail("tr_subproblem: bad arguments (batch=%d n=%d, n must be 1..%d)", batch, n, TR_MAXN - 1);
+        return CELESTE_ERR_BAD_ARG;
+    }
+    if (batch == 0) return CELESTE_OK;
+    int st0 = ensure_device_ready();
+    if (st0 != CELESTE_OK) return st0;
+    tr_subproblem_kernel<<<batch, TR_THREADS, 0, (cudaStream_t)cuda_stream>>>(n, g_dev, H_dev, delta_dev, s_dev, m_dev,
+                                                                              interior_dev);
+    CUDA_TRY(cudaGetLastError());
+    return CELESTE_OK;
 }
 
 int celeste_fp64_peak(double* tflops_out, void* cuda_stream) {

@@ -7,9 +7,10 @@ one `evaluate!` (:161-172) = to_bound! -> elbo (likelihood - KL) -> propagate_de
 
 The reference optimises one source per thread, one ELBO evaluation at a time (~10 us of GPU work each).
 Here ALL sources of a batch step in lock-step: one iteration = one CUDA plan evaluation (value + gradient +
-Hessian for every source) + batched 41 x 41 eigen-decompositions (torch.linalg.eigh) for the trust-region
-subproblem; sources that have converged simply stop moving.  Everything stays on the device between
-iterations.
+Hessian for every source) + batched 41 x 41 eigen-decompositions for the trust-region
+subproblem (the library's tr_subproblem_kernel on a GPU; this module's torch code is the same algorithm
+for CPU tensors and the tests); sources that have converged simply stop moving.  Nothing leaves the device
+between iterations except the "anyone still active?" flag.
 
 Optim.jl is an un-vendored dependency (REQUIRE:13, >= 0.7.4): its NewtonTrustRegion is restated from the
 published algorithm (Nocedal & Wright, Alg. 4.1 for the radius update and the exact subproblem solution by
@@ -36,6 +37,20 @@ def solve_tr_subproblem(g: torch.Tensor, H: torch.Tensor, delta: torch.Tensor):
     """min_s g's + 1/2 s'Hs  s.t. |s| <= delta, batched (B x n, B x n x n, B).
     Returns (s, m = predicted change, interior flag)."""
     B, n = g.shape
+    dev_in = g.device
+    if dev_in.type == "cuda":
+        # cuSOLVER's batched FP64 eigensolver and LAPACK on the host both cost ~0.5 s per 1000 sources
+        # (100x the ELBO evaluation), so the device path is the library's own kernel
+        # (csrc/newton_kernels.cuh: one block per source, Jacobi + secular equation).
+        from . import _lib
+        g, H, delta = g.contiguous(), H.contiguous(), delta.contiguous()
+        s = torch.empty_like(g)
+        m = torch.empty_like(delta)
+        interior = torch.empty(B, dtype=torch.int32, device=dev_in)
+        _lib.check(_lib.load().celeste_tr_subproblem(B, n, g.data_ptr(), H.data_ptr(), delta.data_ptr(), s.data_ptr(),
+                                                     m.data_ptr(), interior.data_ptr(),
+                                                     torch.cuda.current_stream().cuda_stream))
+        return s, m, interior.bool()
     ev, Q = torch.linalg.eigh(H)                       # ascending
     qg = torch.einsum("bij,bi->bj", Q, g)              # Q' g
     d2 = delta * delta
@@ -126,11 +141,24 @@ class BatchMaximizer:
         vp0 = ct.enforce(vp0, self.lo, self.hi)                   # enforce! :230
         self.x = ct.to_free(vp0, self.lo, self.hi)                # to_free! :231
         self.f_calls = 0
+        self.profile = None        # set to {} to collect wall-clock per phase (synchronising; diagnostics only)
+
+    def _tick(self, name, t0):
+        if self.profile is not None:
+            import time
+            if self.dev.type == "cuda":
+                torch.cuda.synchronize()
+            self.profile[name] = self.profile.get(name, 0.0) + time.perf_counter() - t0
+            return time.perf_counter()
+        return t0
 
     def evaluate(self, x: torch.Tensor):
         """evaluate! (ElboMaximize.jl:161-172): negative ELBO, gradient and Hessian in free coordinates."""
+        import time
+        t0 = time.perf_counter() if self.profile is not None else 0.0
         bound = ct.to_bound(x, self.lo, self.hi)
         self.vp_all[self.aslot] = bound
+        t0 = self._tick("to_bound", t0)
         if self.runner is not None:
             self.runner(self)
         else:
@@ -138,12 +166,15 @@ class BatchMaximizer:
         v = self.v.clone()
         g = self.d.reshape(self.n, 44).clone()
         H = self.h.reshape(self.n, 44, 44).clone()
+        t0 = self._tick("elbo_plan", t0)
         if self.include_kl:
             kv, kg, kH = self.kl(bound, order=2)
             v += kv
             g += kg
             H += kH
+        t0 = self._tick("kl", t0)
         gf, Hf = ct.propagate_derivatives(x, self.lo, self.hi, g, H)
+        t0 = self._tick("propagate", t0)
         self.f_calls += 1
         bad = self.flags != 0
         return -v, -gf, -Hf, bad, bound
@@ -166,7 +197,10 @@ class BatchMaximizer:
             if not bool(active.any()):
                 break
             steps += 1
+            import time
+            t0 = time.perf_counter() if self.profile is not None else 0.0
             s, m, interior = solve_tr_subproblem(g, H, delta)
+            self._tick("tr_subproblem", t0)
             x_new = torch.where(active[:, None], x + s, x)
             f_new, g_new, H_new, bad_new, _ = self.evaluate(x_new)
             fcalls += active.to(torch.int64)

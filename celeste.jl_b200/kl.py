@@ -34,95 +34,65 @@ class KLTerm:
         self.logdet = torch.logdet(cov)                              # (2, 8)
         self.rad_mean, self.rad_var = float(p.gal_radius_px_mean), float(p.gal_radius_px_var)
         self.device = device
+        self._idx = {}
 
     def __call__(self, vp: torch.Tensor, order: int = 2):
-        """vp: B x 44.  Returns (v [B], g [B x 44] or None, H [B x 44 x 44] or None) of subtract_kl."""
+        """vp: B x 44.  Returns (v [B], g [B x 44] or None, H [B x 44 x 44] or None) of subtract_kl.
+
+        Per source type i the KL terms are  T_i = a_i (log a_i - log pi_i) + a_i G_i(r, s, c, v, k)  with
+        G_i = Q(k) + R(r, s) + sum_d k_d D_d(c, v); its 19 x 19 Hessian over the local ordering
+        (a, r, s, c[4], v[4], k[8]) is assembled from dense sub-blocks and scattered once."""
         B = vp.shape[0]
         dev, dt = vp.device, vp.dtype
         v = torch.zeros(B, dtype=dt, device=dev)
         g = torch.zeros((B, 44), dtype=dt, device=dev) if order >= 1 else None
         H = torch.zeros((B, 44, 44), dtype=dt, device=dev) if order >= 2 else None
-
-        def addH(i, j, val):          # symmetric scatter, i/j index tensors or ints broadcastable
-            H[:, i, j] += val
-            if not (isinstance(i, int) and isinstance(j, int) and i == j):
-                H[:, j, i] += val
-
         for i in range(2):
-            ia = 26 + i
-            a = vp[:, ia]
-            # --- kl_source_a
+            idx = self._local_index(i, dev)
+            th = vp[:, idx]                                   # B x 19
+            a, r, s = th[:, 0], th[:, 1], th[:, 2]
+            c, var, k = th[:, 3:7], th[:, 7:11], th[:, 11:19]
             la = torch.log(a) - self.log_is_star[i]
-            v -= a * la
-            if order >= 1:
-                g[:, ia] -= la + 1
-            if order >= 2:
-                H[:, ia, ia] -= 1 / a
-            # --- kl_source_k
-            ik = torch.arange(28 + 8 * i, 36 + 8 * i, device=dev)
-            k = vp[:, ik]
             lk = torch.log(k) - self.log_k[i]
-            Q = (k * lk).sum(dim=1)
-            v -= a * Q
-            if order >= 1:
-                g[:, ia] -= Q
-                g[:, ik] -= a[:, None] * (lk + 1)
-            if order >= 2:
-                H[:, ia, ik] -= lk + 1
-                H[:, ik, ia] -= lk + 1
-                H[:, ik, ik] -= a[:, None] / k
-            # --- kl_source_r
-            ir, isc = 6 + i, 8 + i
-            r, s = vp[:, ir], vp[:, isc]
             M, V = self.flux_mean[i], self.flux_var[i]
             R = 0.5 * (torch.log(V) - torch.log(s) + (s + (r - M) ** 2) / V - 1)
-            dRr, dRs = (r - M) / V, 0.5 * (1 / V - 1 / s)
-            v -= a * R
-            if order >= 1:
-                g[:, ia] -= R
-                g[:, ir] -= a * dRr
-                g[:, isc] -= a * dRs
-            if order >= 2:
-                addH(ia, ir, -dRr)
-                addH(ia, isc, -dRs)
-                H[:, ir, ir] -= a / V
-                H[:, isc, isc] -= a * 0.5 / s ** 2
-            # --- kl_source_c
-            ic = torch.arange(10 + 4 * i, 14 + 4 * i, device=dev)
-            iv = torch.arange(18 + 4 * i, 22 + 4 * i, device=dev)
-            c, var = vp[:, ic], vp[:, iv]
-            P = self.prec[i]                                              # (8, 4, 4)
-            delta = self.mu2[i][None] - c[:, None, :]                     # (B, 8, 4)
-            Pd = torch.einsum("djk,bdk->bdj", P, delta)                   # Lambda delta
-            diagP = torch.diagonal(P, dim1=1, dim2=2)                     # (8, 4)
+            P = self.prec[i]                                   # (8, 4, 4)
+            delta = self.mu2[i][None] - c[:, None, :]          # (B, 8, 4)
+            Pd = torch.einsum("djk,bdk->bdj", P, delta)
+            diagP = torch.diagonal(P, dim1=1, dim2=2)          # (8, 4)
             D = 0.5 * ((diagP[None] * var[:, None, :]).sum(-1) - 4 + (delta * Pd).sum(-1) + self.logdet[i][None]
-                       - torch.log(var).sum(-1, keepdim=True))           # (B, 8)
-            dDc = -Pd                                                     # (B, 8, 4)
-            dDv = 0.5 * (diagP[None] - 1 / var[:, None, :])               # (B, 8, 4)
-            kD = (k * D).sum(dim=1)
-            v -= a * kD
+                       - torch.log(var).sum(-1, keepdim=True))   # (B, 8)
+            G = (k * lk).sum(dim=1) + R + (k * D).sum(dim=1)
+            v -= a * (la + G)
             if order >= 1:
-                kdc = torch.einsum("bd,bdj->bj", k, dDc)
-                kdv = torch.einsum("bd,bdj->bj", k, dDv)
-                g[:, ia] -= kD
-                g[:, ik] -= a[:, None] * D
-                g[:, ic] -= a[:, None] * kdc
-                g[:, iv] -= a[:, None] * kdv
+                dDc, dDv = -Pd, 0.5 * (diagP[None] - 1 / var[:, None, :])      # (B, 8, 4)
+                Gg = torch.empty((B, 18), dtype=dt, device=dev)
+                Gg[:, 0] = (r - M) / V
+                Gg[:, 1] = 0.5 * (1 / V - 1 / s)
+                Gg[:, 2:6] = torch.einsum("bd,bdj->bj", k, dDc)
+                Gg[:, 6:10] = torch.einsum("bd,bdj->bj", k, dDv)
+                Gg[:, 10:18] = lk + 1 + D
+                gl = torch.empty((B, 19), dtype=dt, device=dev)
+                gl[:, 0] = la + 1 + G
+                gl[:, 1:] = a[:, None] * Gg
+                g[:, idx] -= gl
             if order >= 2:
-                H[:, ia, ik] -= D
-                H[:, ik, ia] -= D
-                H[:, ia, ic] -= kdc
-                H[:, ic, ia] -= kdc
-                H[:, ia, iv] -= kdv
-                H[:, iv, ia] -= kdv
-                kc = a[:, None, None] * dDc                               # (B, 8, 4): d2/dk dc
-                kv = a[:, None, None] * dDv
-                H[:, ik[:, None], ic[None, :]] -= kc
-                H[:, ic[:, None], ik[None, :]] -= kc.transpose(1, 2)
-                H[:, ik[:, None], iv[None, :]] -= kv
-                H[:, iv[:, None], ik[None, :]] -= kv.transpose(1, 2)
-                H[:, ic[:, None], ic[None, :]] -= a[:, None, None] * torch.einsum("bd,djk->bjk", k, P)
-                H[:, iv, iv] -= a[:, None] * k.sum(dim=1, keepdim=True) * 0.5 / var ** 2
+                GH = torch.zeros((B, 18, 18), dtype=dt, device=dev)
+                GH[:, 0, 0] = 1 / V
+                GH[:, 1, 1] = 0.5 / s ** 2
+                GH[:, 2:6, 2:6] = torch.einsum("bd,djk->bjk", k, P)
+                GH[:, 6:10, 6:10] = torch.diag_embed(k.sum(dim=1, keepdim=True) * 0.5 / var ** 2)
+                GH[:, 10:18, 10:18] = torch.diag_embed(1 / k)
+                GH[:, 10:18, 2:6] = dDc
+                GH[:, 2:6, 10:18] = dDc.transpose(1, 2)
+                GH[:, 10:18, 6:10] = dDv
+                GH[:, 6:10, 10:18] = dDv.transpose(1, 2)
+                Hl = torch.empty((B, 19, 19), dtype=dt, device=dev)
+                Hl[:, 0, 0] = 1 / a
+                Hl[:, 0, 1:] = Gg
+                Hl[:, 1:, 0] = Gg
+                Hl[:, 1:, 1:] = a[:, None, None] * GH
+                H[:, idx[:, None], idx[None, :]] -= Hl
         # --- source_e_log_prob
         x = vp[:, 5]
         v += -0.5 * (math.log(2 * math.pi) + math.log(self.rad_var) + (x - self.rad_mean) ** 2 / self.rad_var)
@@ -131,3 +101,12 @@ class KLTerm:
         if order >= 2:
             H[:, 5, 5] += -1 / self.rad_var
         return v, g, H
+
+    def _local_index(self, i, dev):
+        """canonical (0-based) ids of (a_i, flux_loc_i, flux_scale_i, color_mean[:, i], color_var[:, i], k[:, i])."""
+        key = (i, str(dev))
+        if key not in self._idx:
+            ids = [26 + i, 6 + i, 8 + i] + list(range(10 + 4 * i, 14 + 4 * i)) + list(range(18 + 4 * i, 22 + 4 * i)) \
+                + list(range(28 + 8 * i, 36 + 8 * i))
+            self._idx[key] = torch.tensor(ids, dtype=torch.long, device=dev)
+        return self._idx[key]

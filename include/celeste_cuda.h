@@ -233,6 +233,18 @@ int celeste_set_chunk_pixels(int32_t chunk_pixels);
 void celeste_field_destroy(celeste_field* f);
 
 /*
+ * Row f.2 (batched Newton trust region; the step ElboMaximize.maximize! delegates to Optim.NewtonTrustRegion,
+ * src/deterministic_vi/ElboMaximize.jl:105-108,235): for each of `batch` sources solve
+ *     min_s  g's + 1/2 s'Hs   subject to |s| <= delta
+ * exactly (Jacobi eigen-decomposition + secular equation, hard case included).  All pointers are DEVICE
+ * pointers; g: batch x n, H: batch x n x n (symmetric), delta: batch; outputs s: batch x n, m: batch
+ * (predicted change of the objective), interior: batch (1 when the unconstrained Newton step was taken).
+ * n <= 47 (41 free parameters in Celeste).  Asynchronous on `cuda_stream`.
+ */
+int celeste_tr_subproblem(int32_t batch, int32_t n, const double* g_dev, const double* H_dev, const double* delta_dev,
+                          double* s_dev, double* m_dev, int32_t* interior_dev, void* cuda_stream);
+
+/*
  * Measured FP64 FMA peak of the current device (a register-resident DFMA chain,
  * 2 flop per FMA), in TFLOP/s: the denominator of the roofline of this
  * FP64-pipe-bound path.  Runs on `cuda_stream`, synchronises.

@@ -21,6 +21,7 @@ def load():
         _lib = C.CDLL(SO)
         vp, i32 = C.c_void_p, C.c_int32
         _lib.emul_elbo_batch.argtypes = [i32, vp, i32, vp, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, i32]
+        _lib.emul_tr_subproblem.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp]
     return _lib
 
 
@@ -47,3 +48,18 @@ class EmulField:
         assert st == 0, st
         return {"v": v, "d": d[:nd] if mode >= 1 else d[:0], "h": h[:nh] if mode >= 2 else h[:0],
                 "counters": counters.reshape(n, 2), "flags": flags, "active_ptr": active_ptr}
+
+
+def tr_subproblem(g, H, delta):
+    """tr_subproblem_kernel under emulation: g B x n, H B x n x n, delta B -> (s, m, interior)."""
+    g = np.ascontiguousarray(g, dtype=np.float64)
+    H = np.ascontiguousarray(H, dtype=np.float64)
+    delta = np.ascontiguousarray(delta, dtype=np.float64)
+    B, n = g.shape
+    s = np.zeros((B, n))
+    m = np.zeros(B)
+    interior = np.zeros(B, dtype=np.int32)
+    st = load().emul_tr_subproblem(B, n, g.ctypes.data, H.ctypes.data, delta.ctypes.data, s.ctypes.data,
+                                   m.ctypes.data, interior.ctypes.data)
+    assert st == 0
+    return s, m, interior.astype(bool)

@@ -67,6 +67,8 @@ inline double __shfl_xor_sync(unsigned, double v, int o) {
     return r;
 }
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
+inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }
+inline bool __all_sync(unsigned m, bool pred) { return __ballot_sync(m, pred) == (threadIdx.x / 32 * 32 + 32 <= (unsigned)cuda_emul::ctx()->nthreads ? 0xffffffffu : ((1u << (cuda_emul::ctx()->nthreads % 32)) - 1u)); }
 inline double __ldg(const double* p) { return *p; }
 inline int atomicOr(int* p, int v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
 using std::isfinite;

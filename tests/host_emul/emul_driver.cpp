@@ -6,6 +6,7 @@
 
 #include "../../include/celeste_cuda.h"
 #include "../../celeste.jl_b200/csrc/celeste_kernels.cuh"
+#include "../../celeste.jl_b200/csrc/newton_kernels.cuh"
 
 using namespace celeste;
 
@@ -133,5 +134,11 @@ extern "C" int emul_elbo_batch(int32_t N, const celeste_image* imgs, int32_t S_t
     else
         run<2>(pd, fd, nb, chunk_pixels, vp, v, d, h, cnt.data(), flags);
     for (size_t i = 0; i < cnt.size(); ++i) counters[i] = cnt[i];
+    return 0;
+}
+
+extern "C" int emul_tr_subproblem(int32_t batch, int32_t n, const double* g, const double* H, const double* delta,
+                                  double* s, double* m, int32_t* interior) {
+    cuda_emul::launch(tr_subproblem_kernel, batch, TR_THREADS, 0, n, g, H, delta, s, m, interior);
     return 0;
 }

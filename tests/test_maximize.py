@@ -149,6 +149,32 @@ def test_tr_subproblem_optimality():
         assert m[b] <= 1e-12
 
 
+def test_tr_subproblem_kernel_under_emulation():
+    """csrc/newton_kernels.cuh (Jacobi + secular equation, one block per source) == the torch restatement,
+    on 41 x 41 problems like the free-space Hessians (positive definite, indefinite and a hard case)."""
+    import emul_lib
+    rng = np.random.default_rng(6)
+    n, B = 41, 10
+    A = rng.normal(size=(B, n, n))
+    H = A + A.transpose(0, 2, 1)
+    H[:4] = np.einsum("bij,bkj->bik", A[:4], A[:4]) + 0.5 * np.eye(n)
+    g = rng.normal(size=(B, n))
+    delta = rng.uniform(0.1, 10.0, B)
+    ev, Q = np.linalg.eigh(H[-1])
+    g[-1] = Q[:, 1:] @ rng.normal(size=n - 1) * 1e-3
+    delta[-1] = 5.0
+    s, m, interior = emul_lib.tr_subproblem(g, H, delta)
+    rs, rm, rint = em.solve_tr_subproblem(torch.tensor(g), torch.tensor(H), torch.tensor(delta))
+    assert np.array_equal(interior, rint.numpy())
+    assert np.allclose(m, rm.numpy(), rtol=1e-9, atol=1e-12)
+    for b in range(B):
+        assert np.linalg.norm(s[b]) <= delta[b] * (1 + 1e-9)
+        if b != B - 1:        # the hard-case step is unique only up to the sign/choice of the eigenvector
+            assert np.allclose(s[b], rs[b].numpy(), rtol=1e-7, atol=1e-9 * np.abs(rs[b].numpy()).max())
+        model = g[b] @ s[b] + 0.5 * s[b] @ H[b] @ s[b]
+        assert model == pytest.approx(m[b], rel=1e-9, abs=1e-11)
+
+
 class OracleRunner:
     """ELBO evaluator for BatchMaximizer on a machine without a GPU: the oracle (checker)."""
 
