@@ -229,3 +229,31 @@ def test_one_node_single_infer_improves_elbo(cj):
                                             max_iters=15)
     assert len(results) == 30 and all(np.isfinite(r.vs).all() for r in results)
     assert (res.f_calls >= 2).all()
+
+
+def test_joint_beats_single_on_overlapping_sources(cj):
+    """test/test_infer.jl:49-69: on three overlapping sources, joint inference (Cyclades sweeps with shared
+    variational parameters) reaches a higher ELBO of the whole scene than single inference (neighbours frozen at
+    their catalog initialisation).  The scene ELBO (all three sources active, Sa = 3, no KL) is scored by the
+    oracle, exactly like compute_obj_value (test_infer.jl:17-28)."""
+    from celeste_jl_b200 import parallel_run as pr, synthetic
+    from celeste_jl_b200.model import get_sky_patches, find_all_neighbors
+    images = synthetic.blank_images(60, 60)
+    catalog = [synthetic.sample_ce([26.3, 27.1], False), synthetic.sample_ce([31.8, 33.2], True),
+               synthetic.sample_ce([35.1, 25.4], False)]
+    for ce in catalog:
+        ce.star_fluxes = ce.star_fluxes * 0.2
+        ce.gal_fluxes = ce.gal_fluxes * 0.2
+    synthetic.gen_images(images, catalog, seed=21, device="cpu")
+    patches = get_sky_patches(images, catalog, radius_override_pix=20.0)
+    nb = find_all_neighbors(patches)
+    assert all(len(x) == 2 for x in nb)
+    nmap = {s: nb[s] for s in range(3)}
+    field = cj.DeviceField(images, patches)
+    single, _ = pr.one_node_single_infer(catalog, patches, [0, 1, 2], nmap, images, field=field)
+    joint, _ = pr.one_node_joint_infer(catalog, patches, [0, 1, 2], nmap, images, field=field)
+
+    def score(results):
+        v, _, _, _ = oracle_lib.oracle_elbo(images, patches, [r.vs for r in results], [1, 2, 3], mode=0)
+        return v
+    assert score(joint) > score(single)

@@ -1,0 +1,20 @@
+"""Small workload for compute-sanitizer (memcheck / racecheck): every kernel of the library once per mode."""
+import os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch
+import celeste_jl_b200 as cj
+from celeste_jl_b200 import elbo_maximize as em
+import cases
+for name in ("two_body", "clipped_and_empty", "psf_k3", "crowded"):
+    images, patches, tasks = cases.get(name)
+    f = cj.DeviceField(images, patches)
+    for mode in (0, 1, 2):
+        out = f.elbo_batch(tasks, mode=mode)
+    print(name, out["v"][:2])
+g = torch.randn(4, 41, dtype=torch.float64, device="cuda")
+A = torch.randn(4, 41, 41, dtype=torch.float64, device="cuda")
+s, m, interior = em.solve_tr_subproblem(g, A + A.transpose(1, 2), torch.ones(4, dtype=torch.float64, device="cuda"))
+torch.cuda.synchronize()
+print("tr", m.cpu().numpy())
