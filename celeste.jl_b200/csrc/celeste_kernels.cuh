@@ -168,6 +168,7 @@ __global__ void __launch_bounds__(PIX_THREADS, MODE == 2 ? CELESTE_PIX_MINB_HESS
     CEL_DYNAMIC_SMEM(smem);
     double* acc = smem;                                    // NACC x PIX_THREADS
     double* s_comps = acc + NACC * PIX_THREADS;           // MAX_COMPS * 6
+    __shared__ double s_exptab[8];
     __shared__ int s_nb[MAX_NB_LIST];
     __shared__ int s_nb_count;
     __shared__ int s_nb_overflow;
@@ -192,6 +193,11 @@ __global__ void __launch_bounds__(PIX_THREADS, MODE == 2 ? CELESTE_PIX_MINB_HESS
         s_nb_count = 0;
         s_nb_overflow = 0;
     }
+#ifdef CELESTE_HOST_EMULATION
+    if (tid < 8) s_exptab[tid] = h_exptab[tid];
+#else
+    if (tid < 8) s_exptab[tid] = c_exptab[tid];
+#endif
     __syncthreads();
 
     // neighbours whose patch in this image can touch this chunk's pixels (ordered compaction by warp 0,
@@ -247,7 +253,7 @@ __global__ void __launch_bounds__(PIX_THREADS, MODE == 2 ? CELESTE_PIX_MINB_HESS
         const double m1 = __ldg(rec + MAX_COMPS * COMP_STRIDE), m2 = __ldg(rec + MAX_COMPS * COMP_STRIDE + 1);
         double f0, gd[2], hd[3];
         star_eval<0>(LdGlobal(), p.coefs, p.n1, p.n2, (double)h - m1 + 26.0, (double)w - m2 + 26.0, f0, gd, hd);
-        const double f1 = gal_value<KT>(LdGlobal(), rec, p.K, __ldg(br + 22), (double)h, (double)w);
+        const double f1 = gal_value<KT>(LdGlobal(), rec, p.K, s_exptab, __ldg(br + 22), (double)h, (double)w);
         const double na1 = __ldg(br + 20), na2 = __ldg(br + 21);
         const double Es = na1 * __ldg(br + b) * f0 + na2 * __ldg(br + 5 + b) * f1;
         const double E2s = na1 * __ldg(br + 10 + b) * f0 * f0 + na2 * __ldg(br + 15 + b) * f1 * f1;
@@ -307,7 +313,7 @@ __global__ void __launch_bounds__(PIX_THREADS, MODE == 2 ? CELESTE_PIX_MINB_HESS
             if (covered) {
                 star_eval<MODE>(LdGlobal(), pa.coefs, pa.n1, pa.n2, (double)h - am1 + 26.0, (double)w - am2 + 26.0, f0,
                                 g0, h0);
-                gal_eval<MODE, KT>(LdShared(), s_comps, pa.K, c_proto_nu, theta, (double)h, (double)w, gal);
+                gal_eval<MODE, KT>(LdShared(), s_comps, pa.K, c_proto_nu, s_exptab, theta, (double)h, (double)w, gal);
                 acc[ACC_CNT_ACTIVE * PIX_THREADS + tid] += 1.0;
             }
             acc[ACC_CNT_INACTIVE * PIX_THREADS + tid] += cnt_inactive;
