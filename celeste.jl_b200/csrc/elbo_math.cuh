@@ -43,7 +43,7 @@ constexpr int NLIVE = 28;      // canonical ids 1..28 receive likelihood derivat
 constexpr int NPROTO = 14;     // 8 dev + 6 exp prototype components, light_source_model.jl:45-72
 constexpr int NPROTO_DEV = 8;
 constexpr int MAX_K = 4;       // PSF components supported per patch (reference default psf_K = 2)
-constexpr int COMP_STRIDE = 6; // doubles per component record
+constexpr int COMP_STRIDE = 8; // doubles per component record: mu1 mu2 L11 L12 L22 z L11/2 L22/2
 constexpr int MAX_COMPS = NPROTO * MAX_K;
 
 // accumulator layout in (c, y) space.  y order: x1 x2 S11 S12 S22 theta; c order: A1 A2 B1 B2
@@ -292,6 +292,19 @@ CEL_HD void gal_group(LD ld, const double* comps, int Krt, const double* nu, con
             const double p2 = l12 * d1 + l22 * d2;
             const double q = d1 * p1 + d2 * p2;
             const double fp = z * exp_scaled_tab(q, -0.5, etab);   // f_pre, BivariateNormals.jl:219
+            if (MODE == 1) {
+                // gradient only: accumulate UNWEIGHTED first-order sums; the caller scales the group by
+                // theta_i once and obtains d/dtheta from the difference of the two groups (fsm_util.jl:277-291)
+                const double hl11 = ld(cp + 6), hl22 = ld(cp + 7);
+                A.f += fp;
+                A.ax1 += fp * p1;
+                A.ax2 += fp * p2;
+                const double fn = fp * nuc;
+                A.as1 += fn * fma(0.5 * p1, p1, -hl11);     // bvn_sig_d, BivariateNormals.jl:267-272
+                A.as2 += fn * fma(p1, p2, -l12);
+                A.as3 += fn * fma(0.5 * p2, p2, -hl22);
+                continue;
+            }
             const double w = thc * fp;
             A.f += w;
             if (MODE >= 1) {
@@ -299,10 +312,11 @@ CEL_HD void gal_group(LD ld, const double* comps, int Krt, const double* nu, con
                 A.ft += wd;
                 A.ax1 += w * p1;
                 A.ax2 += w * p2;
+                const double hl11 = ld(cp + 6), hl22 = ld(cp + 7);
                 const double a = p1 * p1, b = p1 * p2, cc = p2 * p2;
-                const double g1 = 0.5 * a - 0.5 * l11;   // bvn_sig_d, BivariateNormals.jl:267-272
+                const double g1 = fma(0.5, a, -hl11);    // bvn_sig_d, BivariateNormals.jl:267-272
                 const double g2 = b - l12;
-                const double g3 = 0.5 * cc - 0.5 * l22;
+                const double g3 = fma(0.5, cc, -hl22);
                 const double wn = w * nuc;
                 A.as1 += wn * g1;
                 A.as2 += wn * g2;
@@ -326,12 +340,12 @@ CEL_HD void gal_group(LD ld, const double* comps, int Krt, const double* nu, con
                     A.xs23 += wn * (p2 * (l22 - g3));
                     // bvn_sigsig_h (BivariateNormals.jl:293-306, dsiginv_dsig:168-183) + g_S g_S'
                     const double wnn = wn * nuc;
-                    A.ss11 += wnn * (l11 * (0.5 * l11 - a) + g1 * g1);
+                    A.ss11 += wnn * (l11 * (hl11 - a) + g1 * g1);
                     A.ss12 += wnn * (l12 * (l11 - a) - b * l11 + g1 * g2);
                     A.ss13 += wnn * (l12 * (0.5 * l12 - b) + g1 * g3);
                     A.ss22 += wnn * (l22 * (l11 - a) + l12 * (l12 - 2.0 * b) - cc * l11 + g2 * g2);
                     A.ss23 += wnn * (l12 * (l22 - cc) - b * l22 + g2 * g3);
-                    A.ss33 += wnn * (l22 * (0.5 * l22 - cc) + g3 * g3);
+                    A.ss33 += wnn * (l22 * (hl22 - cc) + g3 * g3);
                 }
             }
         }
@@ -346,6 +360,21 @@ CEL_HD void gal_eval(LD ld, const double* comps, int K, const double* nu /*14*/,
     A.as1 = A.as2 = A.as3 = A.ts1 = A.ts2 = A.ts3 = 0.0;
     A.xs11 = A.xs12 = A.xs13 = A.xs21 = A.xs22 = A.xs23 = 0.0;
     A.ss11 = A.ss12 = A.ss13 = A.ss22 = A.ss23 = A.ss33 = 0.0;
+    if (MODE == 1) {
+        gal_group<MODE, KT, true>(ld, comps, K, nu, etab, theta, hx, wy, A);
+        GalAcc Bx;
+        Bx.f = Bx.ax1 = Bx.ax2 = Bx.as1 = Bx.as2 = Bx.as3 = 0.0;
+        gal_group<MODE, KT, false>(ld, comps, K, nu, etab, 1.0 - theta, hx, wy, Bx);
+        const double t0 = theta, t1 = 1.0 - theta;
+        o.f = t0 * A.f + t1 * Bx.f;
+        o.r[0] = -(t0 * A.ax1 + t1 * Bx.ax1);
+        o.r[1] = -(t0 * A.ax2 + t1 * Bx.ax2);
+        o.r[2] = t0 * A.as1 + t1 * Bx.as1;
+        o.r[3] = t0 * A.as2 + t1 * Bx.as2;
+        o.r[4] = t0 * A.as3 + t1 * Bx.as3;
+        o.r[5] = A.f - Bx.f;
+        return;
+    }
     gal_group<MODE, KT, true>(ld, comps, K, nu, etab, theta, hx, wy, A);
     gal_group<MODE, KT, false>(ld, comps, K, nu, etab, 1.0 - theta, hx, wy, A);
     const double f = A.f, ft = A.ft, ax1 = A.ax1, ax2 = A.ax2, tx1 = A.tx1, tx2 = A.tx2, u1 = A.u1, u2 = A.u2,
@@ -524,6 +553,8 @@ CEL_HD void make_component(const double* psf7, double eta, double nuBar, double 
     out[3] = -v12 * idet;
     out[4] = v11 * idet;
     out[5] = (psf7[0] * eta) * (1.0 / (sqrt(det) * 6.283185307179586476925286766559));
+    out[6] = 0.5 * out[2];
+    out[7] = 0.5 * out[4];
 }
 
 // GalaxySigmaDerivs (BivariateNormals.jl:346-397) with nuBar = 1: J0[k][j] = dSigma_k/dshape_j,

@@ -257,3 +257,31 @@ def test_joint_beats_single_on_overlapping_sources(cj):
         v, _, _, _ = oracle_lib.oracle_elbo(images, patches, [r.vs for r in results], [1, 2, 3], mode=0)
         return v
     assert score(joint) > score(single)
+
+
+def test_concurrent_callers_are_safe(cj):
+    """SURVEY 8b "Threading": elbo_likelihood is called concurrently from every Julia thread (one scratch object
+    per thread, ElboMaximize.jl:146-152).  Eight host threads hammer celeste_elbo_single on different ElboArgs of
+    one field; every result must equal the serial one bit for bit."""
+    import threading
+    images, patches, tasks = cases.get("small_field")
+    field = cj.DeviceField(images, patches)
+    serial = [field.elbo_batch([t], mode=2) for t in tasks]
+    errors = []
+
+    def worker(k):
+        try:
+            for rep in range(6):
+                for i in range(k, len(tasks), 8):
+                    out = field.elbo_batch([tasks[i]], mode=2)
+                    for key in ("v", "d", "h", "counters"):
+                        if not np.array_equal(out[key], serial[i][key]):
+                            errors.append((i, key))
+        except Exception as e:   # noqa: BLE001
+            errors.append(repr(e))
+    th = [threading.Thread(target=worker, args=(k,)) for k in range(8)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errors, errors[:3]
