@@ -121,6 +121,11 @@ int configure_kernels() {
     CEL_CFG(1, 2);
     CEL_CFG(2, 2);
 #undef CEL_CFG
+    {
+        const int psm = (int)(((size_t)NPAIR_ACC * PAIR_THREADS + 2 * (size_t)MAX_COMPS * COMP_STRIDE) * sizeof(double));
+        CUDA_TRY(cudaFuncSetAttribute(pair_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, psm));
+        CUDA_TRY(cudaFuncSetAttribute(pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, psm));
+    }
     return CELESTE_OK;
 }
 
@@ -167,9 +172,13 @@ struct celeste_plan {
     int n_tasks = 0, n_slots = 0, N = 0;
     int n_blocks = 0, chunk_pixels = 0;
     std::vector<int> h_task_ptr;
-    DevBuf<int> task_ptr, src_row, act_slot, chunk_ptr;
+    DevBuf<int> task_ptr, src_row, sub_ptr, sub_slot, chunk_ptr, pair_ptr;
+    DevBuf<long long> h_ptr;
     DevBuf<BlockHdr> blockmap;
-    DevBuf<double> slotimg, slotbr, partials;
+    DevBuf<PairHdr> pairmap;
+    DevBuf<double> slotimg, slotbr, partials, pair_partials;
+    int n_subs = 0, n_pairs = 0;
+    size_t h_total = 0;      // doubles in the Hessian output: sum over tasks of (44 Sa)^2
     // staging for the host-buffer entry point
     DevBuf<double> vp_dev, v_dev, d_dev, h_dev;
     DevBuf<long long> counters_dev;
@@ -383,7 +392,10 @@ int celeste_plan_create_multi(int32_t n_fields, celeste_field* const* fields, ce
     const int n_slots = task_ptr[n_tasks];
     pl->n_slots = n_slots;
     pl->h_task_ptr.assign(task_ptr, task_ptr + n_tasks + 1);
-    std::vector<int> src_row(n_slots), act_slot(n_tasks), tfield(n_tasks), sfield(n_slots);
+    std::vector<int> src_row(n_slots), tfield(n_tasks), sfield(n_slots);
+    std::vector<int> sub_ptr(n_tasks + 1, 0), sub_slot, sub_task, pair_ptr(n_tasks + 1, 0);
+    std::vector<long long> h_ptr(n_tasks + 1, 0);
+    std::vector<PairHdr> pairmap;
     for (int t = 0; t < n_tasks; ++t) {
         const int s0 = task_ptr[t], s1 = task_ptr[t + 1];
         if (s0 < 0 || s1 < s0 || (t == 0 && s0 != 0)) {
@@ -397,17 +409,27 @@ int celeste_plan_create_multi(int32_t n_fields, celeste_field* const* fields, ce
         }
         tfield[t] = fi;
         const int Sa = active_ptr[t + 1] - active_ptr[t];
-        if (Sa != 1) {
-            set_detail("plan_create: task %d has Sa=%d active sources; this build evaluates Sa == 1 "
-                       "(production, ParallelRun.jl:253,489) and leaves Sa > 1 on the reference path", t, Sa);
-            return CELESTE_ERR_UNSUPPORTED;
+        if (Sa < 1 || Sa > 8) {
+            set_detail("plan_create: task %d has Sa=%d active sources (supported: 1..8; production uses 1, "
+                       "ParallelRun.jl:253,489)", t, Sa);
+            return Sa < 1 ? CELESTE_ERR_BAD_ARG : CELESTE_ERR_UNSUPPORTED;
         }
-        const int a = active_idx[active_ptr[t]];
-        if (a < 1 || a > s1 - s0) {
-            set_detail("plan_create: task %d active index %d outside 1..%d", t, a, s1 - s0);
-            return CELESTE_ERR_BAD_ARG;
+        sub_ptr[t + 1] = sub_ptr[t] + Sa;
+        h_ptr[t + 1] = h_ptr[t] + (long long)(NPARAM * Sa) * (NPARAM * Sa);
+        for (int k = 0; k < Sa; ++k) {
+            const int a = active_idx[active_ptr[t] + k];
+            if (a < 1 || a > s1 - s0) {
+                set_detail("plan_create: task %d active index %d outside 1..%d", t, a, s1 - s0);
+                return CELESTE_ERR_BAD_ARG;
+            }
+            for (int k2 = 0; k2 < k; ++k2)
+                if (active_idx[active_ptr[t] + k2] == a) {
+                    set_detail("plan_create: task %d lists active source %d twice", t, a);
+                    return CELESTE_ERR_BAD_ARG;
+                }
+            sub_slot.push_back(s0 + a - 1);
+            sub_task.push_back(t);
         }
-        act_slot[t] = s0 + a - 1;
         for (int s = s0; s < s1; ++s) {
             const int row = source_ids[s];
             if (row < 1 || row > fields[fi]->S_tot) {
@@ -417,33 +439,60 @@ int celeste_plan_create_multi(int32_t n_fields, celeste_field* const* fields, ce
             src_row[s] = row - 1;
             sfield[s] = fi;
         }
+        pair_ptr[t + 1] = pair_ptr[t] + Sa * (Sa - 1) / 2;
     }
-    // block map: one block per (task, image, chunk of the active patch's pixels)
+    const int n_subs = (int)sub_slot.size();
+    pl->n_subs = n_subs;
+    pl->n_pairs = pair_ptr[n_tasks];
+    pl->h_total = (size_t)h_ptr[n_tasks];
+    for (int t = 0; t < n_tasks; ++t) {
+        const int Sa = sub_ptr[t + 1] - sub_ptr[t];
+        for (int ka = 0; ka < Sa; ++ka)
+            for (int kb = ka + 1; kb < Sa; ++kb)
+                for (int n = 0; n < pl->N; ++n) {
+                    PairHdr ph;
+                    ph.sub_a = sub_ptr[t] + ka;
+                    ph.sub_b = sub_ptr[t] + kb;
+                    ph.slot_a = sub_slot[ph.sub_a];
+                    ph.slot_b = sub_slot[ph.sub_b];
+                    ph.slot0 = task_ptr[t];
+                    ph.slot1 = task_ptr[t + 1];
+                    ph.n = n;
+                    ph.field = tfield[t];
+                    pairmap.push_back(ph);
+                }
+    }
+    // block map: one block per (active source of a task, image, chunk of its patch's pixels)
     int chunk_pixels = g_chunk_pixels > 0 ? g_chunk_pixels : 4 * PIX_THREADS;
     if (const char* env = std::getenv("CELESTE_CHUNK_PIXELS"))   // kernel-tuning knob
         if (std::atoi(env) > 0) chunk_pixels = std::atoi(env);
     pl->chunk_pixels = chunk_pixels;
-    std::vector<int> chunk_ptr((size_t)n_tasks * pl->N + 1, 0);
+    std::vector<int> chunk_ptr((size_t)n_subs * pl->N + 1, 0);
     std::vector<BlockHdr> blockmap;
-    for (int t = 0; t < n_tasks; ++t)
+    for (int u = 0; u < n_subs; ++u)
         for (int n = 0; n < pl->N; ++n) {
+            const int t = sub_task[u];
             const celeste_field* f = fields[tfield[t]];
-            const size_t pidx = (size_t)src_row[act_slot[t]] + (size_t)n * f->S_tot;
+            const size_t pidx = (size_t)src_row[sub_slot[u]] + (size_t)n * f->S_tot;
             const PatchDev& pa = f->h_patches[pidx];
             const long npix = (long)pa.H2 * pa.W2;
             const int nchunk = (int)((npix + chunk_pixels - 1) / chunk_pixels);
-            const int tn = t * pl->N + n;
+            const int tn = u * pl->N + n;
             chunk_ptr[tn + 1] = chunk_ptr[tn] + nchunk;
             for (int c = 0; c < nchunk; ++c) {
                 BlockHdr hd;
                 hd.tn = tn;
                 hd.chunk = c;
-                hd.aslot = act_slot[t];
+                hd.aslot = sub_slot[u];
                 hd.slot0 = task_ptr[t];
                 hd.slot1 = task_ptr[t + 1];
                 hd.patch = (int)pidx;
                 hd.n = n;
                 hd.field = tfield[t];
+                hd.sub0 = sub_ptr[t];
+                hd.sub = u;
+                hd.sub1 = sub_ptr[t + 1];
+                hd.pad = 0;
                 blockmap.push_back(hd);
             }
         }
@@ -454,7 +503,12 @@ int celeste_plan_create_multi(int32_t n_fields, celeste_field* const* fields, ce
     CUDA_TRY(pl->slot_field.upload(sfield));
     CUDA_TRY(pl->task_ptr.upload(tp));
     CUDA_TRY(pl->src_row.upload(src_row));
-    CUDA_TRY(pl->act_slot.upload(act_slot));
+    CUDA_TRY(pl->sub_ptr.upload(sub_ptr));
+    CUDA_TRY(pl->sub_slot.upload(sub_slot));
+    CUDA_TRY(pl->h_ptr.upload(h_ptr));
+    CUDA_TRY(pl->pair_ptr.upload(pair_ptr));
+    CUDA_TRY(pl->pairmap.upload(pairmap));
+    CUDA_TRY(pl->pair_partials.alloc(pairmap.size() * NPAIR_ACC));
     CUDA_TRY(pl->chunk_ptr.upload(chunk_ptr));
     CUDA_TRY(pl->blockmap.upload(blockmap));
     CUDA_TRY(pl->slotimg.alloc((size_t)n_slots * pl->N * SLOTIMG_STRIDE));
@@ -498,9 +552,8 @@ int celeste_plan_kernel_times(celeste_plan* p, float ms[3]) {
 }
 
 int celeste_plan_launches(const celeste_plan* p, int32_t mode) {
-    (void)mode;
     if (!p || p->n_tasks == 0) return 0;
-    return p->n_blocks > 0 ? 3 : 2;   // setup, pixel, epilogue
+    return (p->n_blocks > 0 ? 3 : 2) + ((mode == 2 && p->n_pairs > 0) ? 1 : 0);   // setup, pixel, [pair,] epilogue
 }
 
 }  // extern "C"
@@ -516,9 +569,16 @@ static PlanDev plan_dev(const celeste_plan* p) {
     d.slot_field = p->slot_field.p;
     d.task_ptr = p->task_ptr.p;
     d.src_row = p->src_row.p;
-    d.act_slot = p->act_slot.p;
+    d.n_subs = p->n_subs;
+    d.n_pairs = p->n_pairs;
+    d.sub_ptr = p->sub_ptr.p;
+    d.sub_slot = p->sub_slot.p;
+    d.h_ptr = p->h_ptr.p;
     d.blockmap = p->blockmap.p;
     d.chunk_ptr = p->chunk_ptr.p;
+    d.pairmap = p->pairmap.p;
+    d.pair_ptr = p->pair_ptr.p;
+    d.pair_partials = p->pair_partials.p;
     d.slotimg = p->slotimg.p;
     d.slotbr = p->slotbr.p;
     d.partials = p->partials.p;
@@ -539,6 +599,13 @@ static int launch_mode(celeste_plan* p, const double* vp_dev, double* v, double*
             pixel_kernel<MODE, 2><<<p->n_blocks, PIX_THREADS, pixel_smem_bytes<MODE>(), st>>>(pd, p->chunk_pixels);
         else
             pixel_kernel<MODE, 0><<<p->n_blocks, PIX_THREADS, pixel_smem_bytes<MODE>(), st>>>(pd, p->chunk_pixels);
+    }
+    if (MODE == 2 && p->n_pairs > 0) {     // Sa > 1 (unit tests): cross-source Hessian blocks
+        const size_t psm = ((size_t)NPAIR_ACC * PAIR_THREADS + 2 * (size_t)MAX_COMPS * COMP_STRIDE) * sizeof(double);
+        if (p->uniform_K == 2)
+            pair_kernel<2><<<p->n_pairs * p->N, PAIR_THREADS, psm, st>>>(pd);
+        else
+            pair_kernel<0><<<p->n_pairs * p->N, PAIR_THREADS, psm, st>>>(pd);
     }
     if (p->timing) CUDA_TRY(cudaEventRecord(p->ev[2], st));
     epilogue_kernel<MODE><<<p->n_tasks, EPI_THREADS, 0, st>>>(pd, vp_dev, v, d, h, counters, flags);
@@ -585,8 +652,9 @@ int celeste_elbo_plan_host(celeste_plan* p, const double* vp, int32_t mode, doub
     CUDA_TRY(p->v_dev.ensure(nt));
     CUDA_TRY(p->counters_dev.ensure(2 * nt));
     CUDA_TRY(p->flags_dev.ensure(nt));
-    if (mode >= 1) CUDA_TRY(p->d_dev.ensure(nt * NPARAM));
-    if (mode >= 2) CUDA_TRY(p->h_dev.ensure(nt * NPARAM * NPARAM));
+    const size_t nd = (size_t)p->n_subs * NPARAM, nh = p->h_total;
+    if (mode >= 1) CUDA_TRY(p->d_dev.ensure(nd));
+    if (mode >= 2) CUDA_TRY(p->h_dev.ensure(nh));
     cudaStream_t st = p->stream;
     CUDA_TRY(cudaMemcpyAsync(p->vp_dev.p, vp, (size_t)p->n_slots * NPARAM * sizeof(double), cudaMemcpyHostToDevice, st));
     int rc = celeste_elbo_plan_device(p, p->vp_dev.p, mode, p->v_dev.p, p->d_dev.p, p->h_dev.p,
@@ -594,9 +662,8 @@ int celeste_elbo_plan_host(celeste_plan* p, const double* vp, int32_t mode, doub
     if (rc != CELESTE_OK) return rc;
     std::vector<int> hflags(nt);
     CUDA_TRY(cudaMemcpyAsync(v, p->v_dev.p, nt * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (mode >= 1) CUDA_TRY(cudaMemcpyAsync(d, p->d_dev.p, nt * NPARAM * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (mode >= 2)
-        CUDA_TRY(cudaMemcpyAsync(h, p->h_dev.p, nt * NPARAM * NPARAM * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (mode >= 1) CUDA_TRY(cudaMemcpyAsync(d, p->d_dev.p, nd * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (mode >= 2) CUDA_TRY(cudaMemcpyAsync(h, p->h_dev.p, nh * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (counters)
         CUDA_TRY(cudaMemcpyAsync(counters, p->counters_dev.p, 2 * nt * sizeof(long long), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(hflags.data(), p->flags_dev.p, nt * sizeof(int), cudaMemcpyDeviceToHost, st));

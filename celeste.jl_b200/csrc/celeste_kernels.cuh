@@ -57,25 +57,41 @@ struct FieldDev {
 
 // everything a pixel-kernel block needs to find its work, in one 32-byte load
 struct BlockHdr {
-    int tn;        // task * N + n
+    int tn;        // sub * N + n   (sub = one active source of one task)
     int chunk;     // chunk index inside the active patch
-    int aslot;     // slot of the active source
+    int aslot;     // slot of this active source
     int slot0, slot1;   // slot range of the task
     int patch;     // index of the active source's patch in FieldDev::patches
     int n;         // image
     int field;     // index into PlanDev::fields
+    int sub0, sub, sub1;   // this task's active sources are subs [sub0, sub1); this block works for `sub`
+    int pad;
 };
 
+// one block of pair_kernel: the cross-source Hessian block of two active sources of one task in one image
+struct PairHdr {
+    int sub_a, sub_b;      // sub_a < sub_b (order of ea.active_sources)
+    int slot_a, slot_b;
+    int slot0, slot1;
+    int n, field;
+};
+constexpr int NPAIR_ACC = 100;   // (c, y)_a x (c, y)_b
+
 struct PlanDev {
-    int n_tasks, N, n_fields, n_slots;
+    int n_tasks, N, n_fields, n_slots, n_subs, n_pairs;
     const FieldDev* fields;  // n_fields inference boxes share one plan (same N)
     const int* task_field;   // n_tasks: field of each task
     const int* slot_field;   // n_slots: field of each slot
     const int* task_ptr;     // n_tasks + 1 (slot ranges)
     const int* src_row;      // n_slots: 0-based patch row of each slot (inside its field)
-    const int* act_slot;     // n_tasks: slot of the (single) active source
+    const int* sub_ptr;      // n_tasks + 1: active sources ("subs") of each task, ea.active_sources order
+    const int* sub_slot;     // n_subs: slot of each active source
+    const long long* h_ptr;  // n_tasks + 1: offset of each task's (44 Sa)^2 Hessian in the output
     const BlockHdr* blockmap; // n_blocks
-    const int* chunk_ptr;    // n_tasks * N + 1: first block of (task, n)
+    const int* chunk_ptr;    // n_subs * N + 1: first block of (sub, n)
+    const PairHdr* pairmap;  // n_pairs * N
+    const int* pair_ptr;     // n_tasks + 1: first pair of each task
+    double* pair_partials;   // n_pairs * N * NPAIR_ACC
     double* slotimg;         // n_slots * N * SLOTIMG_STRIDE
     double* slotbr;          // n_slots * SLOTBR_STRIDE
     double* partials;        // n_blocks * NACC
@@ -178,6 +194,8 @@ __global__ void __launch_bounds__(PIX_THREADS, MODE == 2 ? CELESTE_PIX_MINB_HESS
     const int chunk = bm.chunk, n = bm.n;
     const int slot0 = bm.slot0, slot1 = bm.slot1;
     const int aslot = bm.aslot;
+    const int sub0 = bm.sub0, sub = bm.sub, sub1 = bm.sub1;
+    const bool multi = (sub1 - sub0) > 1;                  // Sa > 1: unit tests only (elbo_objective.jl:429-434)
     const FieldDev field = plan.fields[bm.field];
     const ImageDev img = field.images[n];
     const PatchDev pa = field.patches[bm.patch];
@@ -242,12 +260,19 @@ __global__ void __launch_bounds__(PIX_THREADS, MODE == 2 ? CELESTE_PIX_MINB_HESS
     const double am1 = arec[MAX_COMPS * COMP_STRIDE], am2 = arec[MAX_COMPS * COMP_STRIDE + 1];
 
     // value-only contribution of neighbour slot s at image pixel (h, w) (elbo_objective.jl:342-372, inactive branch)
+    double cnt_other_active = 0.0;
     auto neighbour = [&](int s, int h, int w, double& Ebg, double& Vbg, double& cnt) {
         const PatchDev& p = field.patches[plan.src_row[s] + (size_t)n * field.S_tot];
         const int h2 = h - p.off_h, w2 = w - p.off_w;
         if (h2 < 1 || h2 > p.H2 || w2 < 1 || w2 >= p.W2) return;
         if (!p.bitmap[(h2 - 1) + (size_t)(w2 - 1) * p.H2]) return;
-        cnt += 1.0;
+        bool other_active = false;
+        if (multi)
+            for (int j = sub0; j < sub1; ++j) other_active |= (plan.sub_slot[j] == s);
+        if (other_active)
+            cnt_other_active += 1.0;     // counted as an ACTIVE pixel-visit (elbo_objective.jl:353-357)
+        else
+            cnt += 1.0;
         const double* rec = plan.slotimg + ((size_t)s * plan.N + n) * SLOTIMG_STRIDE;
         const double* br = plan.slotbr + (size_t)s * SLOTBR_STRIDE;
         const double m1 = __ldg(rec + MAX_COMPS * COMP_STRIDE), m2 = __ldg(rec + MAX_COMPS * COMP_STRIDE + 1);
@@ -298,6 +323,17 @@ __global__ void __launch_bounds__(PIX_THREADS, MODE == 2 ? CELESTE_PIX_MINB_HESS
             double Ebg = (double)cur.sky;                        // :374
             double Vbg = 0.0;
             double cnt_inactive = 0.0;
+            cnt_other_active = 0.0;
+            // Sa > 1: a pixel is visited once, by the first active source whose patch holds it
+            // (`already_visited`, elbo_objective.jl:450-455); later actives still take its derivatives
+            bool first_visit = true;
+            if (multi)
+                for (int j = sub0; j < sub; ++j) {
+                    const PatchDev& pj = field.patches[plan.src_row[plan.sub_slot[j]] + (size_t)n * field.S_tot];
+                    const int hj = h - pj.off_h, wj = w - pj.off_w;
+                    if (hj >= 1 && hj <= pj.H2 && wj >= 1 && wj <= pj.W2 && pj.bitmap[(hj - 1) + (size_t)(wj - 1) * pj.H2])
+                        first_visit = false;
+                }
             const int nnb = s_nb_count;
             for (int i = 0; i < nnb; ++i) neighbour(s_nb[i], h, w, Ebg, Vbg, cnt_inactive);
             if (s_nb_overflow) {
@@ -314,10 +350,12 @@ __global__ void __launch_bounds__(PIX_THREADS, MODE == 2 ? CELESTE_PIX_MINB_HESS
                 star_eval<MODE>(LdGlobal(), pa.coefs, pa.n1, pa.n2, (double)h - am1 + 26.0, (double)w - am2 + 26.0, f0,
                                 g0, h0);
                 gal_eval<MODE, KT>(LdShared(), s_comps, pa.K, c_proto_nu, s_exptab, theta, (double)h, (double)w, gal);
-                acc[ACC_CNT_ACTIVE * PIX_THREADS + tid] += 1.0;
             }
-            acc[ACC_CNT_INACTIVE * PIX_THREADS + tid] += cnt_inactive;
-            pixel_accumulate<MODE>(acc + tid, PIX_THREADS, pc, Ebg, Vbg, covered, cb, f0, g0, h0, gal);
+            if (first_visit) {
+                acc[ACC_CNT_ACTIVE * PIX_THREADS + tid] += (covered ? 1.0 : 0.0) + cnt_other_active;
+                acc[ACC_CNT_INACTIVE * PIX_THREADS + tid] += cnt_inactive;
+            }
+            pixel_accumulate<MODE>(acc + tid, PIX_THREADS, pc, Ebg, Vbg, covered, first_visit, cb, f0, g0, h0, gal);
         }
         cur = nxt;
     }
@@ -337,8 +375,152 @@ __global__ void __launch_bounds__(PIX_THREADS, MODE == 2 ? CELESTE_PIX_MINB_HESS
 }
 
 // ------------------------------------------------------------------------------------------------
+// Sa > 1 only (unit tests of the reference, test/test_elbo.jl:64-130,223-301): the Hessian block that couples
+// two active sources a, b of one task.  E_G and var_G are sums over sources, so the only coupling is through
+// combine_sfs_hessian! (SensitiveFloats.jl:114-126):
+//     H_ab += x * ( h12 (dV_a dE_b' + dE_a dV_b') + h22 dE_a dE_b' )
+// accumulated here in (c, y)_a x (c, y)_b space (10 x 10) over the pixels both sources cover.
+constexpr int PAIR_THREADS = 128;
+
+template <int KT>
+__global__ void __launch_bounds__(PAIR_THREADS) pair_kernel(PlanDev plan) {
+    CEL_DYNAMIC_SMEM(smem);
+    double* acc = smem;                                         // NPAIR_ACC x PAIR_THREADS
+    double* s_comps_a = acc + NPAIR_ACC * PAIR_THREADS;
+    double* s_comps_b = s_comps_a + MAX_COMPS * COMP_STRIDE;
+    __shared__ double s_exptab[8];
+    const int tid = threadIdx.x;
+    const PairHdr ph = plan.pairmap[blockIdx.x];
+    const int n = ph.n;
+    const FieldDev field = plan.fields[ph.field];
+    const ImageDev img = field.images[n];
+    const PatchDev pa = field.patches[plan.src_row[ph.slot_a] + (size_t)n * field.S_tot];
+    const PatchDev pb = field.patches[plan.src_row[ph.slot_b] + (size_t)n * field.S_tot];
+    for (int a = 0; a < NPAIR_ACC; ++a) acc[a * PAIR_THREADS + tid] = 0.0;
+    const double* reca = plan.slotimg + ((size_t)ph.slot_a * plan.N + n) * SLOTIMG_STRIDE;
+    const double* recb = plan.slotimg + ((size_t)ph.slot_b * plan.N + n) * SLOTIMG_STRIDE;
+    for (int i = tid; i < NPROTO * pa.K * COMP_STRIDE; i += PAIR_THREADS) s_comps_a[i] = reca[i];
+    for (int i = tid; i < NPROTO * pb.K * COMP_STRIDE; i += PAIR_THREADS) s_comps_b[i] = recb[i];
+#ifdef CELESTE_HOST_EMULATION
+    if (tid < 8) s_exptab[tid] = h_exptab[tid];
+#else
+    if (tid < 8) s_exptab[tid] = c_exptab[tid];
+#endif
+    __syncthreads();
+    const int b = img.band - 1;
+    const double* bra = plan.slotbr + (size_t)ph.slot_a * SLOTBR_STRIDE;
+    const double* brb = plan.slotbr + (size_t)ph.slot_b * SLOTBR_STRIDE;
+    const double cba[4] = {bra[20] * bra[b], bra[21] * bra[5 + b], bra[20] * bra[10 + b], bra[21] * bra[15 + b]};
+    const double cbb[4] = {brb[20] * brb[b], brb[21] * brb[5 + b], brb[20] * brb[10 + b], brb[21] * brb[15 + b]};
+    // pixels covered by both: rows off+1..off+H2, columns off+1..off+W2-1 (strict, elbo_objective.jl:349)
+    const int h_lo = max(pa.off_h, pb.off_h) + 1, h_hi = min(pa.off_h + pa.H2, pb.off_h + pb.H2);
+    const int w_lo = max(pa.off_w, pb.off_w) + 1, w_hi = min(pa.off_w + pa.W2 - 1, pb.off_w + pb.W2 - 1);
+    const int nh = h_hi - h_lo + 1, nw = w_hi - w_lo + 1;
+    const int npix = (nh > 0 && nw > 0) ? nh * nw : 0;
+    for (int pix = tid; pix < npix; pix += PAIR_THREADS) {
+        const int h = h_lo + pix % nh, w = w_lo + pix / nh;
+        if (!pa.bitmap[(h - pa.off_h - 1) + (size_t)(w - pa.off_w - 1) * pa.H2]) continue;
+        if (!pb.bitmap[(h - pb.off_h - 1) + (size_t)(w - pb.off_w - 1) * pb.H2]) continue;
+        const size_t ipix = (size_t)(h - 1) + (size_t)(w - 1) * img.H;
+        const float xf = img.pixels[ipix];
+        if (isnan(xf)) continue;
+        double E = (double)img.sky[ipix], V = 0.0;
+        double ea[10], va[10], eb[10], vb[10];
+        for (int which = 0; which < 2; ++which) {
+            const PatchDev& pp = which == 0 ? pa : pb;
+            const double* rec = which == 0 ? reca : recb;
+            const double* br = which == 0 ? bra : brb;
+            const double* cb = which == 0 ? cba : cbb;
+            double f0, g0[2], h0[3];
+            GalRaw gal;
+            star_eval<1>(LdGlobal(), pp.coefs, pp.n1, pp.n2, (double)h - rec[MAX_COMPS * COMP_STRIDE] + 26.0,
+                         (double)w - rec[MAX_COMPS * COMP_STRIDE + 1] + 26.0, f0, g0, h0);
+            gal_eval<1, KT>(LdShared(), which == 0 ? s_comps_a : s_comps_b, pp.K, c_proto_nu, s_exptab, br[22], (double)h,
+                            (double)w, gal);
+            const double A1 = cb[0], A2 = cb[1], B1 = cb[2], B2 = cb[3], f1 = gal.f;
+            const double m = A1 * f0 + A2 * f1;
+            E += m;
+            V += B1 * f0 * f0 + B2 * f1 * f1 - m * m;
+            double* e = which == 0 ? ea : eb;
+            double* v = which == 0 ? va : vb;
+            e[0] = f0;
+            e[1] = f1;
+            e[2] = e[3] = 0.0;
+            v[0] = -2.0 * m * f0;
+            v[1] = -2.0 * m * f1;
+            v[2] = f0 * f0;
+            v[3] = f1 * f1;
+            const double vf0 = 2.0 * (B1 * f0 - m * A1), vf1 = 2.0 * (B2 * f1 - m * A2);
+            for (int k = 0; k < 6; ++k) {
+                const double gk = k < 2 ? g0[k] : 0.0;
+                e[4 + k] = A1 * gk + A2 * gal.r[k];
+                v[4 + k] = vf0 * gk + vf1 * gal.r[k];
+            }
+        }
+        // every other source of the task: values only
+        for (int s = ph.slot0; s < ph.slot1; ++s) {
+            if (s == ph.slot_a || s == ph.slot_b) continue;
+            const PatchDev& p = field.patches[plan.src_row[s] + (size_t)n * field.S_tot];
+            const int h2 = h - p.off_h, w2 = w - p.off_w;
+            if (h2 < 1 || h2 > p.H2 || w2 < 1 || w2 >= p.W2) continue;
+            if (!p.bitmap[(h2 - 1) + (size_t)(w2 - 1) * p.H2]) continue;
+            const double* rec = plan.slotimg + ((size_t)s * plan.N + n) * SLOTIMG_STRIDE;
+            const double* br = plan.slotbr + (size_t)s * SLOTBR_STRIDE;
+            double f0, gd[2], hd[3];
+            star_eval<0>(LdGlobal(), p.coefs, p.n1, p.n2, (double)h - rec[MAX_COMPS * COMP_STRIDE] + 26.0,
+                         (double)w - rec[MAX_COMPS * COMP_STRIDE + 1] + 26.0, f0, gd, hd);
+            const double f1 = gal_value<KT>(LdGlobal(), rec, p.K, s_exptab, br[22], (double)h, (double)w);
+            const double Es = br[20] * br[b] * f0 + br[21] * br[5 + b] * f1;
+            E += Es;
+            V += br[20] * br[10 + b] * f0 * f0 + br[21] * br[15 + b] * f1 * f1 - Es * Es;
+        }
+        const double x = (double)xf;
+        const double iE = 1.0 / E, iE2 = iE * iE;
+        const double LEE = -x * (iE2 + 3.0 * V * iE2 * iE2);
+        const double LEV = x * iE2 * iE;
+        for (int i = 0; i < 10; ++i)
+            for (int j = 0; j < 10; ++j)
+                acc[(i * 10 + j) * PAIR_THREADS + tid] += LEE * ea[i] * eb[j] + LEV * (ea[i] * vb[j] + va[i] * eb[j]);
+    }
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31;
+    double* out = plan.pair_partials + (size_t)blockIdx.x * NPAIR_ACC;
+    for (int a = warp; a < NPAIR_ACC; a += PAIR_THREADS / 32) {
+        double t = 0.0;
+        for (int k = 0; k < PAIR_THREADS / 32; ++k) t += acc[a * PAIR_THREADS + lane + 32 * k];
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0) out[a] = t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 constexpr int EPI_THREADS = 128;
 constexpr int NY = 10;   // intermediate variables: c (4) then y (6)
+
+// d(c, y)/d(28 live parameters) for one (source, image): rows 0..3 c = (a1 E_l1, a2 E_l2, a1 E_ll1, a2 E_ll2),
+// rows 4..9 y = (x1 x2 S11 S12 S22 theta)
+__device__ inline void build_Jy(double (*Jy)[NLIVE], const PatchDev& p, int b, const double* br, const double J0[3][3]) {
+    for (int r = 0; r < NY; ++r)
+        for (int q = 0; q < NLIVE; ++q) Jy[r][q] = 0.0;
+    Jy[4][0] = -p.J[0];      // dx_a/dpos_b = -J[a][b]
+    Jy[4][1] = -p.J[2];
+    Jy[5][0] = -p.J[1];
+    Jy[5][1] = -p.J[3];
+    for (int k = 0; k < 3; ++k)
+        for (int j = 0; j < 3; ++j) Jy[6 + k][3 + j] = J0[k][j];
+    Jy[9][2] = 1.0;
+    double ka[10], la[10];
+    band_coefs(b, ka, la);
+    for (int i = 0; i < 2; ++i) {
+        const double ai = br[20 + i], El = br[i * 5 + b], Ell = br[10 + i * 5 + b];
+        Jy[i][26 + i] = El;
+        Jy[2 + i][26 + i] = Ell;
+        for (int k = 0; k < 10; ++k) {
+            Jy[i][bright_id(i, k)] = ai * El * ka[k];
+            Jy[2 + i][bright_id(i, k)] = ai * Ell * la[k];
+        }
+    }
+}
 
 template <int MODE>
 __global__ void __launch_bounds__(EPI_THREADS) epilogue_kernel(PlanDev plan,
@@ -347,156 +529,200 @@ __global__ void __launch_bounds__(EPI_THREADS) epilogue_kernel(PlanDev plan,
                                                                long long* __restrict__ out_counters,
                                                                int* __restrict__ out_flags) {
     constexpr int NACC = NAcc<MODE>::value;
-    __shared__ double ysum[NACC_MODE2];
+    __shared__ double ysum[NACC_MODE2 > NPAIR_ACC ? NACC_MODE2 : NPAIR_ACC];
     __shared__ double Jy[NY][NLIVE];
+    __shared__ double Jy2[NY][NLIVE];
     __shared__ double Hyy[NY][NY];
     __shared__ double Wm[NY][NLIVE];
     __shared__ double Hacc[NLIVE][NLIVE];
     __shared__ double gacc[NLIVE];
     __shared__ double s_val, s_cnt[2];
-    __shared__ double J0[3][3], T0[3][3][3];
+    __shared__ double J0[3][3], T0[3][3][3], J0b[3][3];
     __shared__ int s_bad;
 
     const int tid = threadIdx.x;
     const int t = blockIdx.x;
-    const int aslot = plan.act_slot[t];
+    const int sub0 = plan.sub_ptr[t], sub1 = plan.sub_ptr[t + 1];
+    const int Sa = sub1 - sub0;
+    const int P = NPARAM * Sa;
     const FieldDev field = plan.fields[plan.task_field[t]];
-    const double* vs = vp + (size_t)NPARAM * aslot;
-    const double* br = plan.slotbr + (size_t)aslot * SLOTBR_STRIDE;
+    double* Hout = MODE >= 2 ? out_h + plan.h_ptr[t] : nullptr;
 
-    for (int i = tid; i < NLIVE * NLIVE; i += EPI_THREADS) (&Hacc[0][0])[i] = 0.0;
-    if (tid < NLIVE) gacc[tid] = 0.0;
     if (tid == 0) {
         s_val = 0.0;
         s_cnt[0] = s_cnt[1] = 0.0;
         s_bad = 0;
-        if (MODE >= 1) sigma_derivs(vs[3], vs[4], vs[5], J0, T0);
     }
+    if (MODE >= 2 && Sa > 1)
+        for (int i = tid; i < P * P; i += EPI_THREADS) Hout[i] = 0.0;   // cross blocks are filled below
     __syncthreads();
+    int bad = 0;
 
-    for (int n = 0; n < plan.N; ++n) {
-        const int tn = t * plan.N + n;
-        const int c0 = plan.chunk_ptr[tn], c1 = plan.chunk_ptr[tn + 1];
-        for (int a = tid; a < NACC; a += EPI_THREADS) {
-            double s = 0.0;
-            for (int c = c0; c < c1; ++c) s += plan.partials[(size_t)c * NACC + a];
-            ysum[a] = s;
-        }
+    for (int sub = sub0; sub < sub1; ++sub) {
+        const int aslot = plan.sub_slot[sub];
+        const int ka = sub - sub0;
+        const double* vs = vp + (size_t)NPARAM * aslot;
+        const double* br = plan.slotbr + (size_t)aslot * SLOTBR_STRIDE;
+        for (int i = tid; i < NLIVE * NLIVE; i += EPI_THREADS) (&Hacc[0][0])[i] = 0.0;
+        if (tid < NLIVE) gacc[tid] = 0.0;
+        if (tid == 0 && MODE >= 1) sigma_derivs(vs[3], vs[4], vs[5], J0, T0);
         __syncthreads();
-        if (tid == 0) {
-            s_val += ysum[ACC_VAL];
-            s_cnt[0] += ysum[ACC_CNT_ACTIVE];
-            s_cnt[1] += ysum[ACC_CNT_INACTIVE];
-        }
-        if (MODE >= 1) {
-            const PatchDev& p = field.patches[plan.src_row[aslot] + (size_t)n * field.S_tot];
-            const int b = field.images[n].band - 1;
-            for (int i = tid; i < NY * NLIVE; i += EPI_THREADS) (&Jy[0][0])[i] = 0.0;
+
+        for (int n = 0; n < plan.N; ++n) {
+            const int tn = sub * plan.N + n;
+            const int c0 = plan.chunk_ptr[tn], c1 = plan.chunk_ptr[tn + 1];
+            for (int a = tid; a < NACC; a += EPI_THREADS) {
+                double s = 0.0;
+                for (int c = c0; c < c1; ++c) s += plan.partials[(size_t)c * NACC + a];
+                ysum[a] = s;
+            }
             __syncthreads();
             if (tid == 0) {
-                // y rows 4..9: x1 x2 S11 S12 S22 theta  (dx_a/dpos_b = -J[a][b])
-                Jy[4][0] = -p.J[0];
-                Jy[4][1] = -p.J[2];
-                Jy[5][0] = -p.J[1];
-                Jy[5][1] = -p.J[3];
-                for (int k = 0; k < 3; ++k)
-                    for (int j = 0; j < 3; ++j) Jy[6 + k][3 + j] = J0[k][j];
-                Jy[9][2] = 1.0;
-                double ka[10], la[10];
-                band_coefs(b, ka, la);
-                for (int i = 0; i < 2; ++i) {
-                    const double ai = br[20 + i], El = br[i * 5 + b], Ell = br[10 + i * 5 + b];
-                    Jy[i][26 + i] = El;
-                    Jy[2 + i][26 + i] = Ell;
-                    for (int k = 0; k < 10; ++k) {
-                        Jy[i][bright_id(i, k)] = ai * El * ka[k];
-                        Jy[2 + i][bright_id(i, k)] = ai * Ell * la[k];
+                s_val += ysum[ACC_VAL];
+                s_cnt[0] += ysum[ACC_CNT_ACTIVE];
+                s_cnt[1] += ysum[ACC_CNT_INACTIVE];
+            }
+            if (MODE >= 1) {
+                const PatchDev& p = field.patches[plan.src_row[aslot] + (size_t)n * field.S_tot];
+                const int b = field.images[n].band - 1;
+                if (tid == 0) build_Jy(Jy, p, b, br, J0);
+                if (MODE >= 2 && tid == 32) {
+                    for (int c = 0; c < 4; ++c)
+                        for (int d = c; d < 4; ++d) Hyy[c][d] = Hyy[d][c] = ysum[ACC_CC + tri4(c, d)];
+                    for (int c = 0; c < 4; ++c)
+                        for (int k = 0; k < 6; ++k) Hyy[c][4 + k] = Hyy[4 + k][c] = ysum[ACC_CR + c * 6 + k];
+                    for (int k = 0; k < 6; ++k)
+                        for (int l = k; l < 6; ++l) Hyy[4 + k][4 + l] = Hyy[4 + l][4 + k] = ysum[ACC_HH + tri6(k, l)];
+                }
+                __syncthreads();
+                if (tid < NLIVE) {
+                    double g = 0.0;
+                    for (int c = 0; c < 4; ++c) g += Jy[c][tid] * ysum[ACC_C1 + c];
+                    for (int k = 0; k < 6; ++k) g += Jy[4 + k][tid] * ysum[ACC_G + k];
+                    gacc[tid] += g;
+                }
+                if (MODE >= 2) {
+                    for (int i = tid; i < NY * NLIVE; i += EPI_THREADS) {
+                        const int r = i / NLIVE, q = i % NLIVE;
+                        double s = 0.0;
+                        for (int k = 0; k < NY; ++k) s += Hyy[r][k] * Jy[k][q];
+                        Wm[r][q] = s;
+                    }
+                    __syncthreads();
+                    for (int i = tid; i < NLIVE * NLIVE; i += EPI_THREADS) {
+                        const int pp = i / NLIVE, q = i % NLIVE;
+                        double s = 0.0;
+                        for (int r = 0; r < NY; ++r) s += Jy[r][pp] * Wm[r][q];
+                        Hacc[pp][q] += s;
+                    }
+                    __syncthreads();
+                    if (tid == 0) {
+                        // curvature of Sigma(shape): sum_k dL/dS_k * T0[k]   (transform_bvn_derivs_hessian!:481-488)
+                        for (int j = 0; j < 3; ++j)
+                            for (int l = 0; l < 3; ++l) {
+                                double s = 0.0;
+                                for (int k = 0; k < 3; ++k) s += ysum[ACC_G + 2 + k] * T0[k][j][l];
+                                Hacc[3 + j][3 + l] += s;
+                            }
+                        // curvature of c(a, beta): E * kappa kappa' and the (a, beta) cross terms
+                        double kap[10], lam[10];
+                        band_coefs(b, kap, lam);
+                        for (int i = 0; i < 2; ++i) {
+                            const double ai = br[20 + i], El = br[i * 5 + b], Ell = br[10 + i * 5 + b];
+                            const double cA = ysum[ACC_C1 + i], cB = ysum[ACC_C1 + 2 + i];
+                            for (int k = 0; k < 10; ++k) {
+                                const int pk = bright_id(i, k);
+                                const double cross = cA * El * kap[k] + cB * Ell * lam[k];
+                                Hacc[26 + i][pk] += cross;
+                                Hacc[pk][26 + i] += cross;
+                                for (int l = 0; l < 10; ++l)
+                                    Hacc[pk][bright_id(i, l)] +=
+                                        ai * (cA * El * kap[k] * kap[l] + cB * Ell * lam[k] * lam[l]);
+                            }
+                        }
                     }
                 }
-            }
-            if (MODE >= 2 && tid == 32) {
-                for (int c = 0; c < 4; ++c)
-                    for (int d = c; d < 4; ++d) Hyy[c][d] = Hyy[d][c] = ysum[ACC_CC + tri4(c, d)];
-                for (int c = 0; c < 4; ++c)
-                    for (int k = 0; k < 6; ++k) Hyy[c][4 + k] = Hyy[4 + k][c] = ysum[ACC_CR + c * 6 + k];
-                for (int k = 0; k < 6; ++k)
-                    for (int l = k; l < 6; ++l) Hyy[4 + k][4 + l] = Hyy[4 + l][4 + k] = ysum[ACC_HH + tri6(k, l)];
             }
             __syncthreads();
-            if (tid < NLIVE) {
-                double g = 0.0;
-                for (int c = 0; c < 4; ++c) g += Jy[c][tid] * ysum[ACC_C1 + c];
-                for (int k = 0; k < 6; ++k) g += Jy[4 + k][tid] * ysum[ACC_G + k];
-                gacc[tid] += g;
+        }
+
+        // this source's blocks, SensitiveFloat layout (p fastest); rows/cols 29..44 (ids.k) stay zero
+        if (MODE >= 1) {
+            for (int i = tid; i < NPARAM; i += EPI_THREADS) {
+                const double g = i < NLIVE ? gacc[i] : 0.0;
+                out_d[(size_t)NPARAM * sub + i] = g;
+                bad |= !isfinite(g);
             }
-            if (MODE >= 2) {
-                for (int i = tid; i < NY * NLIVE; i += EPI_THREADS) {
-                    const int r = i / NLIVE, q = i % NLIVE;
-                    double s = 0.0;
-                    for (int k = 0; k < NY; ++k) s += Hyy[r][k] * Jy[k][q];
-                    Wm[r][q] = s;
-                }
-                __syncthreads();
-                for (int i = tid; i < NLIVE * NLIVE; i += EPI_THREADS) {
-                    const int pp = i / NLIVE, q = i % NLIVE;
-                    double s = 0.0;
-                    for (int r = 0; r < NY; ++r) s += Jy[r][pp] * Wm[r][q];
-                    Hacc[pp][q] += s;
-                }
-                __syncthreads();
-                if (tid == 0) {
-                    // curvature of Sigma(shape): sum_k dL/dS_k * T0[k]   (transform_bvn_derivs_hessian!:481-488)
-                    for (int j = 0; j < 3; ++j)
-                        for (int l = 0; l < 3; ++l) {
-                            double s = 0.0;
-                            for (int k = 0; k < 3; ++k) s += ysum[ACC_G + 2 + k] * T0[k][j][l];
-                            Hacc[3 + j][3 + l] += s;
-                        }
-                    // curvature of c(a, beta): E * kappa kappa' and the (a, beta) cross terms
-                    double ka[10], la[10];
-                    band_coefs(b, ka, la);
-                    for (int i = 0; i < 2; ++i) {
-                        const double ai = br[20 + i], El = br[i * 5 + b], Ell = br[10 + i * 5 + b];
-                        const double cA = ysum[ACC_C1 + i], cB = ysum[ACC_C1 + 2 + i];
-                        for (int k = 0; k < 10; ++k) {
-                            const int pk = bright_id(i, k);
-                            const double cross = cA * El * ka[k] + cB * Ell * la[k];
-                            Hacc[26 + i][pk] += cross;
-                            Hacc[pk][26 + i] += cross;
-                            for (int l = 0; l < 10; ++l)
-                                Hacc[pk][bright_id(i, l)] += ai * (cA * El * ka[k] * ka[l] + cB * Ell * la[k] * la[l]);
-                        }
-                    }
-                }
+        }
+        if (MODE >= 2) {
+            for (int i = tid; i < NPARAM * NPARAM; i += EPI_THREADS) {
+                const int r = i % NPARAM, c = i / NPARAM;
+                double v = 0.0;
+                if (r < NLIVE && c < NLIVE) v = 0.5 * (Hacc[r][c] + Hacc[c][r]);   // exactly symmetric output
+                Hout[(size_t)(NPARAM * ka + r) + (size_t)(NPARAM * ka + c) * P] = v;
+                bad |= !isfinite(v);
             }
         }
         __syncthreads();
     }
 
-    // outputs, SensitiveFloat layout (p fastest); rows/cols 29..44 (ids.k) stay zero
-    int bad = 0;
+    // cross-source blocks (Sa > 1): H_ab = sum_n Jy_a' M_n Jy_b
+    if (MODE >= 2 && Sa > 1) {
+        int pair = plan.pair_ptr[t];
+        for (int ka = 0; ka < Sa; ++ka)
+            for (int kb = ka + 1; kb < Sa; ++kb, ++pair) {
+                const int sa = plan.sub_slot[sub0 + ka], sb = plan.sub_slot[sub0 + kb];
+                const double* vsa = vp + (size_t)NPARAM * sa;
+                const double* vsb = vp + (size_t)NPARAM * sb;
+                for (int i = tid; i < NLIVE * NLIVE; i += EPI_THREADS) (&Hacc[0][0])[i] = 0.0;
+                if (tid == 0) {
+                    sigma_derivs(vsa[3], vsa[4], vsa[5], J0, T0);
+                    double Ttmp[3][3][3];
+                    sigma_derivs(vsb[3], vsb[4], vsb[5], J0b, Ttmp);
+                }
+                __syncthreads();
+                for (int n = 0; n < plan.N; ++n) {
+                    const double* M = plan.pair_partials + ((size_t)pair * plan.N + n) * NPAIR_ACC;
+                    if (tid < NPAIR_ACC) ysum[tid] = M[tid];
+                    const int b = field.images[n].band - 1;
+                    if (tid == 0)
+                        build_Jy(Jy, field.patches[plan.src_row[sa] + (size_t)n * field.S_tot], b,
+                                 plan.slotbr + (size_t)sa * SLOTBR_STRIDE, J0);
+                    if (tid == 32)
+                        build_Jy(Jy2, field.patches[plan.src_row[sb] + (size_t)n * field.S_tot], b,
+                                 plan.slotbr + (size_t)sb * SLOTBR_STRIDE, J0b);
+                    __syncthreads();
+                    for (int i = tid; i < NY * NLIVE; i += EPI_THREADS) {
+                        const int r = i / NLIVE, q = i % NLIVE;
+                        double s = 0.0;
+                        for (int k = 0; k < NY; ++k) s += ysum[r * 10 + k] * Jy2[k][q];
+                        Wm[r][q] = s;
+                    }
+                    __syncthreads();
+                    for (int i = tid; i < NLIVE * NLIVE; i += EPI_THREADS) {
+                        const int pp = i / NLIVE, q = i % NLIVE;
+                        double s = 0.0;
+                        for (int r = 0; r < NY; ++r) s += Jy[r][pp] * Wm[r][q];
+                        Hacc[pp][q] += s;
+                    }
+                    __syncthreads();
+                }
+                for (int i = tid; i < NLIVE * NLIVE; i += EPI_THREADS) {
+                    const int r = i / NLIVE, c = i % NLIVE;
+                    const double v = Hacc[r][c];
+                    Hout[(size_t)(NPARAM * ka + r) + (size_t)(NPARAM * kb + c) * P] = v;
+                    Hout[(size_t)(NPARAM * kb + c) + (size_t)(NPARAM * ka + r) * P] = v;
+                    bad |= !isfinite(v);
+                }
+                __syncthreads();
+            }
+    }
+
     if (tid == 0) {
         out_v[t] = s_val;
         out_counters[2 * t] = (long long)(s_cnt[0] + 0.5);
         out_counters[2 * t + 1] = (long long)(s_cnt[1] + 0.5);
         bad |= !isfinite(s_val);
-    }
-    if (MODE >= 1) {
-        for (int i = tid; i < NPARAM; i += EPI_THREADS) {
-            const double g = i < NLIVE ? gacc[i] : 0.0;
-            out_d[(size_t)NPARAM * t + i] = g;
-            bad |= !isfinite(g);
-        }
-    }
-    if (MODE >= 2) {
-        double* H = out_h + (size_t)NPARAM * NPARAM * t;
-        for (int i = tid; i < NPARAM * NPARAM; i += EPI_THREADS) {
-            const int r = i % NPARAM, c = i / NPARAM;
-            double v = 0.0;
-            if (r < NLIVE && c < NLIVE) v = 0.5 * (Hacc[r][c] + Hacc[c][r]);   // exactly symmetric output
-            H[i] = v;
-            bad |= !isfinite(v);
-        }
     }
     if (bad) atomicOr(&s_bad, 1);
     __syncthreads();

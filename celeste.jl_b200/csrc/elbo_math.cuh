@@ -454,8 +454,8 @@ struct PixelConsts {
 // acc: per-thread accumulator slots, element a at acc[a * stride]
 template <int MODE>
 CEL_HD void pixel_accumulate(double* acc, int stride, const PixelConsts& pc, double Ebg, double Vbg, bool covered,
-                             const double* cb /*A1 A2 B1 B2*/, double f0, const double* g0, const double* h0,
-                             const GalRaw& gal) {
+                             bool add_value, const double* cb /*A1 A2 B1 B2*/, double f0, const double* g0,
+                             const double* h0, const GalRaw& gal) {
     const double A1 = cb[0], A2 = cb[1], B1 = cb[2], B2 = cb[3];
     const double f1 = gal.f;
     const double m = covered ? (A1 * f0 + A2 * f1) : 0.0;
@@ -463,7 +463,7 @@ CEL_HD void pixel_accumulate(double* acc, int stride, const PixelConsts& pc, dou
     const double V = covered ? (Vbg + B1 * f0 * f0 + B2 * f1 * f1 - m * m) : Vbg;
     const double iE = 1.0 / E;
     const double iE2 = iE * iE;
-    acc[ACC_VAL * stride] += pc.x * (log(E) - 0.5 * V * iE2) - pc.iota * E + pc.pixconst;
+    if (add_value) acc[ACC_VAL * stride] += pc.x * (log(E) - 0.5 * V * iE2) - pc.iota * E + pc.pixconst;
     if (MODE == 0 || !covered) return;
 
     const double gE = pc.x * (iE + V * iE2 * iE) - pc.iota;     // combine_grad[2] * x - iota

@@ -167,8 +167,11 @@ int celeste_patches_set(celeste_field* f, int32_t S_tot, int32_t N, const celest
  * d / h may be NULL when the mode does not produce them.
  *
  * Returns CELESTE_ERR_NONFINITE if any task produced a non-finite value (all
- * outputs are still written; inspect flags[]), CELESTE_ERR_UNSUPPORTED if a task
- * has Sa_t != 1 (this build keeps those on the reference path).
+ * outputs are still written; inspect flags[]).  1 <= Sa_t <= 8 (production uses 1,
+ * ParallelRun.jl:253,489; the reference's unit tests use 2): each pixel is visited
+ * once (`already_visited`, elbo_objective.jl:450-455), the Hessian carries the
+ * cross-source blocks of combine_sfs_hessian! (SensitiveFloats.jl:114-126);
+ * CELESTE_ERR_UNSUPPORTED for Sa_t > 8.
  */
 int celeste_elbo_batch(celeste_field* f, int32_t n_tasks,
                        const int32_t* task_ptr, const int32_t* source_ids,

@@ -45,6 +45,13 @@ void run(const PlanDev& pd, const FieldDev& fd, int n_blocks, int chunk_pixels, 
         else
             cuda_emul::launch(pixel_kernel<MODE, 0>, n_blocks, PIX_THREADS, smem, pd, chunk_pixels);
     }
+    if (MODE == 2 && pd.n_pairs > 0) {
+        const size_t psm = ((size_t)NPAIR_ACC * PAIR_THREADS + 2 * (size_t)MAX_COMPS * COMP_STRIDE) * sizeof(double);
+        if (k2)
+            cuda_emul::launch(pair_kernel<2>, pd.n_pairs * pd.N, PAIR_THREADS, psm, pd);
+        else
+            cuda_emul::launch(pair_kernel<0>, pd.n_pairs * pd.N, PAIR_THREADS, psm, pd);
+    }
     cuda_emul::launch(epilogue_kernel<MODE>, pd.n_tasks, EPI_THREADS, 0, pd, vp, v, d, h, counters, flags);
 }
 }  // namespace
@@ -86,27 +93,48 @@ extern "C" int emul_elbo_batch(int32_t N, const celeste_image* imgs, int32_t S_t
         pdv[i] = p;
     }
     const int n_slots = task_ptr[n_tasks];
-    std::vector<int> src_row(n_slots), act_slot(n_tasks), chunk_ptr((size_t)n_tasks * N + 1, 0);
+    std::vector<int> src_row(n_slots), sub_ptr(n_tasks + 1, 0), sub_slot, sub_task, pair_ptr(n_tasks + 1, 0);
+    std::vector<long long> h_ptr(n_tasks + 1, 0);
+    std::vector<PairHdr> pairmap;
     std::vector<BlockHdr> blockmap;
     for (int t = 0; t < n_tasks; ++t) {
-        if (active_ptr[t + 1] - active_ptr[t] != 1) return CELESTE_ERR_UNSUPPORTED;
-        act_slot[t] = task_ptr[t] + active_idx[active_ptr[t]] - 1;
+        const int Sa = active_ptr[t + 1] - active_ptr[t];
+        if (Sa < 1 || Sa > 8) return CELESTE_ERR_UNSUPPORTED;
+        sub_ptr[t + 1] = sub_ptr[t] + Sa;
+        h_ptr[t + 1] = h_ptr[t] + (long long)(NPARAM * Sa) * (NPARAM * Sa);
+        pair_ptr[t + 1] = pair_ptr[t] + Sa * (Sa - 1) / 2;
+        for (int k = 0; k < Sa; ++k) {
+            sub_slot.push_back(task_ptr[t] + active_idx[active_ptr[t] + k] - 1);
+            sub_task.push_back(t);
+        }
         for (int s = task_ptr[t]; s < task_ptr[t + 1]; ++s) src_row[s] = source_ids[s] - 1;
     }
-    for (int t = 0; t < n_tasks; ++t)
+    const int n_subs = (int)sub_slot.size();
+    for (int t = 0; t < n_tasks; ++t) {
+        const int Sa = sub_ptr[t + 1] - sub_ptr[t];
+        for (int ka = 0; ka < Sa; ++ka)
+            for (int kb = ka + 1; kb < Sa; ++kb)
+                for (int n = 0; n < N; ++n)
+                    pairmap.push_back(PairHdr{sub_ptr[t] + ka, sub_ptr[t] + kb, sub_slot[sub_ptr[t] + ka],
+                                              sub_slot[sub_ptr[t] + kb], task_ptr[t], task_ptr[t + 1], n, 0});
+    }
+    std::vector<int> chunk_ptr((size_t)n_subs * N + 1, 0);
+    for (int u = 0; u < n_subs; ++u)
         for (int n = 0; n < N; ++n) {
-            const PatchDev& pa = pdv[(size_t)src_row[act_slot[t]] + (size_t)n * S_tot];
+            const int t = sub_task[u];
+            const size_t pidx = (size_t)src_row[sub_slot[u]] + (size_t)n * S_tot;
+            const PatchDev& pa = pdv[pidx];
             const long npix = (long)pa.H2 * pa.W2;
             const int nchunk = (int)((npix + chunk_pixels - 1) / chunk_pixels);
-            const int tn = t * N + n;
+            const int tn = u * N + n;
             chunk_ptr[tn + 1] = chunk_ptr[tn] + nchunk;
             for (int c = 0; c < nchunk; ++c)
-                blockmap.push_back(BlockHdr{tn, c, act_slot[t], task_ptr[t], task_ptr[t + 1],
-                                            (int)((size_t)src_row[act_slot[t]] + (size_t)n * S_tot), n, 0});
+                blockmap.push_back(BlockHdr{tn, c, sub_slot[u], task_ptr[t], task_ptr[t + 1], (int)pidx, n, 0, sub_ptr[t], u,
+                                            sub_ptr[t + 1], 0});
         }
     std::vector<int> tp(task_ptr, task_ptr + n_tasks + 1);
     std::vector<double> slotimg((size_t)n_slots * N * SLOTIMG_STRIDE), slotbr((size_t)n_slots * SLOTBR_STRIDE),
-        partials(blockmap.size() * NACC_MODE2 + 1);
+        partials(blockmap.size() * NACC_MODE2 + 1), pair_partials(pairmap.size() * NPAIR_ACC + 1);
     PlanDev pd;
     FieldDev fd{images.data(), pdv.data(), S_tot, 0};
     std::vector<int> tfield(n_tasks, 0), sfield(n_slots, 0);
@@ -114,17 +142,24 @@ extern "C" int emul_elbo_batch(int32_t N, const celeste_image* imgs, int32_t S_t
     pd.N = N;
     pd.n_fields = 1;
     pd.n_slots = n_slots;
+    pd.n_subs = n_subs;
+    pd.n_pairs = (int)pairmap.size() / (N > 0 ? N : 1);
     pd.fields = &fd;
     pd.task_field = tfield.data();
     pd.slot_field = sfield.data();
     pd.task_ptr = tp.data();
     pd.src_row = src_row.data();
-    pd.act_slot = act_slot.data();
+    pd.sub_ptr = sub_ptr.data();
+    pd.sub_slot = sub_slot.data();
+    pd.h_ptr = h_ptr.data();
     pd.blockmap = blockmap.data();
     pd.chunk_ptr = chunk_ptr.data();
+    pd.pairmap = pairmap.data();
+    pd.pair_ptr = pair_ptr.data();
     pd.slotimg = slotimg.data();
     pd.slotbr = slotbr.data();
     pd.partials = partials.data();
+    pd.pair_partials = pair_partials.data();
     std::vector<long long> cnt(2 * (size_t)n_tasks);
     const int nb = (int)blockmap.size();
     if (mode == 0)

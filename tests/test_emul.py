@@ -35,3 +35,20 @@ def test_chunking_does_not_change_counters_or_parity():
     for chunk in (128, 200, 4096):
         got = emul_lib.EmulField(images, patches).elbo_batch(tasks, mode=2, chunk_pixels=chunk)
         cases.assert_parity(ref, got, 2, f"chunk={chunk}")
+
+
+@pytest.mark.parametrize("name,active", [("two_body", [1, 2]), ("two_body", [2, 1]), ("masked", [1, 2]),
+                                         ("clipped_and_empty", [4, 1, 2])])
+def test_emulated_kernels_multiple_active_sources(name, active):
+    """Sa > 1: dedupe of visited pixels, per-source passes and the pair kernel's cross-source Hessian blocks."""
+    images, patches, tasks = cases.get(name)
+    S = patches.shape[0]
+    vp = [None] * S
+    for rows, act, v in tasks:
+        for j, r in enumerate(rows):
+            vp[r - 1] = v[:, j]
+    tk = [(list(range(1, S + 1)), active, np.stack(vp, axis=1))]
+    for mode in (1, 2):
+        ref = oracle_lib.OracleField(images, patches).elbo_batch(tk, mode=mode)
+        got = emul_lib.EmulField(images, patches).elbo_batch(tk, mode=mode)
+        cases.assert_parity(ref, got, mode, f"{name} {active}")

@@ -69,12 +69,62 @@ def test_nonfinite_result_raises(cj):
     assert out["flags"].tolist() == [1, 0] and np.isfinite(out["v"][1])
 
 
-def test_sa2_is_refused_not_faked(cj):
+def _scene_vp(tasks, S):
+    vp = [None] * S
+    for rows, act, v in tasks:
+        for j, r in enumerate(rows):
+            vp[r - 1] = v[:, j]
+    return np.stack(vp, axis=1)
+
+
+@pytest.mark.parametrize("name,active", [("two_body", [1, 2]), ("two_body", [2, 1]), ("masked", [1, 2]),
+                                         ("config2", [1, 2, 3]), ("config2", [3, 1]), ("clipped_and_empty", [4, 1, 2]),
+                                         ("config2_rotated_wcs", [2, 3])])
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_cuda_matches_oracle_multiple_active_sources(cj, name, active, mode):
+    """Sa > 1 (the reference's own hot-path tests run with active_sources = [1, 2], SampleData.make_elbo_args):
+    each pixel visited once (`already_visited`), per-source gradient columns, full (44 Sa)^2 Hessian with the
+    cross-source blocks of combine_sfs_hessian!."""
+    images, patches, tasks = cases.get(name)
+    S = patches.shape[0]
+    tk = [(list(range(1, S + 1)), active, _scene_vp(tasks, S))]
+    ref = oracle_lib.OracleField(images, patches).elbo_batch(tk, mode=mode)
+    got = cj.DeviceField(images, patches).elbo_batch(tk, mode=mode)
+    cases.assert_parity(ref, got, mode, f"{name} {active}")
+
+
+def test_active_sources_partition_through_the_api(cj):
+    """test/test_elbo.jl:64-130 run through ElboArgs / elbo_likelihood on the GPU: order invariance, zero
+    derivative for a pixel-less source, block structure of the 88 x 88 Hessian."""
     from celeste_jl_b200 import synthetic
     images, patches, vp, _ = synthetic.gen_two_body_dataset()
-    ea = cj.ElboArgs(images, patches, [1, 2], include_kl=False)
+    P = 44
+    for n in range(5):
+        patches[1, n].active_pixel_bitmap[:] = False
+    no2 = cj.elbo_likelihood(cj.ElboArgs(images, patches, [1, 2], include_kl=False), vp)
+    assert not no2.d[:, 1].any()
+    patches[1, 4].active_pixel_bitmap[9:11, 9:11] = True
+    e12 = cj.elbo_likelihood(cj.ElboArgs(images, patches, [1, 2], include_kl=False), vp)
+    e21 = cj.elbo_likelihood(cj.ElboArgs(images, patches, [2, 1], include_kl=False), vp)
+    assert e12.v == pytest.approx(e21.v, rel=1e-13)
+    assert np.allclose(e12.d[:, 0], e21.d[:, 1], rtol=1e-10) and np.allclose(e12.d[:, 1], e21.d[:, 0], rtol=1e-10)
+    e1 = cj.elbo_likelihood(cj.ElboArgs(images, patches, [1], include_kl=False), vp)
+    e2 = cj.elbo_likelihood(cj.ElboArgs(images, patches, [2], include_kl=False), vp)
+    assert e1.v == pytest.approx(e12.v, rel=1e-13)
+    assert np.allclose(e12.d[:, 0], e1.d[:, 0], rtol=1e-10) and np.allclose(e12.d[:, 1], e2.d[:, 0], rtol=1e-10)
+    assert np.allclose(e12.h[:P, :P], e1.h, rtol=1e-10) and np.allclose(e12.h[P:, P:], e2.h, rtol=1e-10)
+    assert np.array_equal(e12.h, e12.h.T)
+
+
+def test_too_many_active_sources_is_refused(cj):
+    """More active sources than the library supports is a loud CELESTE_ERR_UNSUPPORTED (the reference's own guard
+    at elbo_args.jl:206 is for Sa > 5), never a silent fallback."""
+    images, patches, tasks = cases.get("crowded")
+    S = patches.shape[0]
+    vpm = np.stack([tasks[0][2][:, 0]] * S, axis=1)
+    field = cj.DeviceField(images, patches)
     with pytest.raises(cj._lib.CelesteError) as ei:
-        cj.elbo_likelihood(ea, vp)
+        field.elbo_batch([(list(range(1, S + 1)), list(range(1, 10)), vpm)], mode=1)
     assert ei.value.status == cj._lib.CELESTE_ERR_UNSUPPORTED
 
 
