@@ -112,8 +112,11 @@ size_t pixel_smem_bytes() {
 }
 
 int configure_kernels() {
-#define CEL_CFG(M, K) \
-    CUDA_TRY(cudaFuncSetAttribute(pixel_kernel<M, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pixel_smem_bytes<M>()))
+#define CEL_CFG(M, K)                                                                                                  \
+    CUDA_TRY(cudaFuncSetAttribute(pixel_kernel<M, K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,             \
+                                  (int)pixel_smem_bytes<M>()));                                                       \
+    CUDA_TRY(cudaFuncSetAttribute(pixel_kernel<M, K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,              \
+                                  (int)pixel_smem_bytes<M>()))
     CEL_CFG(0, 0);
     CEL_CFG(1, 0);
     CEL_CFG(2, 0);
@@ -595,10 +598,16 @@ static int launch_mode(celeste_plan* p, const double* vp_dev, double* v, double*
     setup_kernel<<<sblocks, 256, 0, st>>>(pd, vp_dev);
     if (p->timing) CUDA_TRY(cudaEventRecord(p->ev[1], st));
     if (p->n_blocks > 0) {
-        if (p->uniform_K == 2)
-            pixel_kernel<MODE, 2><<<p->n_blocks, PIX_THREADS, pixel_smem_bytes<MODE>(), st>>>(pd, p->chunk_pixels);
+        const bool multi = p->n_subs > p->n_tasks;
+        const size_t sm = pixel_smem_bytes<MODE>();
+        if (p->uniform_K == 2 && !multi)
+            pixel_kernel<MODE, 2, false><<<p->n_blocks, PIX_THREADS, sm, st>>>(pd, p->chunk_pixels);
+        else if (p->uniform_K == 2)
+            pixel_kernel<MODE, 2, true><<<p->n_blocks, PIX_THREADS, sm, st>>>(pd, p->chunk_pixels);
+        else if (!multi)
+            pixel_kernel<MODE, 0, false><<<p->n_blocks, PIX_THREADS, sm, st>>>(pd, p->chunk_pixels);
         else
-            pixel_kernel<MODE, 0><<<p->n_blocks, PIX_THREADS, pixel_smem_bytes<MODE>(), st>>>(pd, p->chunk_pixels);
+            pixel_kernel<MODE, 0, true><<<p->n_blocks, PIX_THREADS, sm, st>>>(pd, p->chunk_pixels);
     }
     if (MODE == 2 && p->n_pairs > 0) {     // Sa > 1 (unit tests): cross-source Hessian blocks
         const size_t psm = ((size_t)NPAIR_ACC * PAIR_THREADS + 2 * (size_t)MAX_COMPS * COMP_STRIDE) * sizeof(double);

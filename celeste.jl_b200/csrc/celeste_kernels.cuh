@@ -177,7 +177,8 @@ constexpr int MAX_NB_LIST = 64;
 #endif
 // KT: PSF components per patch fixed at compile time (2 = the reference default psf_K, elbo_args.jl:197);
 // KT == 0 reads K from each patch at run time.
-template <int MODE, int KT>
+// MULTI: some task of the plan has Sa > 1 (unit tests); false compiles the `already_visited` logic away.
+template <int MODE, int KT, bool MULTI>
 __global__ void __launch_bounds__(PIX_THREADS, MODE == 2 ? CELESTE_PIX_MINB_HESS : CELESTE_PIX_MINB_GRAD)
     pixel_kernel(PlanDev plan, int chunk_pixels) {
     constexpr int NACC = NAcc<MODE>::value;
@@ -195,7 +196,7 @@ __global__ void __launch_bounds__(PIX_THREADS, MODE == 2 ? CELESTE_PIX_MINB_HESS
     const int slot0 = bm.slot0, slot1 = bm.slot1;
     const int aslot = bm.aslot;
     const int sub0 = bm.sub0, sub = bm.sub, sub1 = bm.sub1;
-    const bool multi = (sub1 - sub0) > 1;                  // Sa > 1: unit tests only (elbo_objective.jl:429-434)
+    const bool multi = MULTI && (sub1 - sub0) > 1;         // Sa > 1: unit tests only (elbo_objective.jl:429-434)
     const FieldDev field = plan.fields[bm.field];
     const ImageDev img = field.images[n];
     const PatchDev pa = field.patches[bm.patch];
@@ -203,8 +204,22 @@ __global__ void __launch_bounds__(PIX_THREADS, MODE == 2 ? CELESTE_PIX_MINB_HESS
     const int first = chunk * chunk_pixels;
     const int last = min(first + chunk_pixels, npix);      // exclusive
 
+    // value / gradient modes keep their 3 / 13 accumulators in registers; the 68 of the Hessian mode live in
+    // per-thread shared-memory slots
+#ifndef CELESTE_REG_ACC
+#define CELESTE_REG_ACC 0   // measured: register accumulators spill at 80 regs and lose 4% (profiles/tuning_r01.md)
+#endif
+    constexpr bool REG_ACC = (MODE <= 1) && (CELESTE_REG_ACC != 0);
+    double racc[REG_ACC ? NACC : 1];
+    if (REG_ACC) {
 #pragma unroll
-    for (int a = 0; a < NACC; ++a) acc[a * PIX_THREADS + tid] = 0.0;
+        for (int a = 0; a < NACC; ++a) racc[a] = 0.0;
+    } else {
+#pragma unroll
+        for (int a = 0; a < NACC; ++a) acc[a * PIX_THREADS + tid] = 0.0;
+    }
+    double* const my_acc = REG_ACC ? racc : acc + tid;
+    constexpr int ACC_STRIDE = REG_ACC ? 1 : PIX_THREADS;
     const double* arec = plan.slotimg + ((size_t)aslot * plan.N + n) * SLOTIMG_STRIDE;
     for (int i = tid; i < NPROTO * pa.K * COMP_STRIDE; i += PIX_THREADS) s_comps[i] = arec[i];
     if (tid == 0) {
@@ -352,12 +367,16 @@ __global__ void __launch_bounds__(PIX_THREADS, MODE == 2 ? CELESTE_PIX_MINB_HESS
                 gal_eval<MODE, KT>(LdShared(), s_comps, pa.K, c_proto_nu, s_exptab, theta, (double)h, (double)w, gal);
             }
             if (first_visit) {
-                acc[ACC_CNT_ACTIVE * PIX_THREADS + tid] += (covered ? 1.0 : 0.0) + cnt_other_active;
-                acc[ACC_CNT_INACTIVE * PIX_THREADS + tid] += cnt_inactive;
+                my_acc[ACC_CNT_ACTIVE * ACC_STRIDE] += (covered ? 1.0 : 0.0) + cnt_other_active;
+                my_acc[ACC_CNT_INACTIVE * ACC_STRIDE] += cnt_inactive;
             }
-            pixel_accumulate<MODE>(acc + tid, PIX_THREADS, pc, Ebg, Vbg, covered, first_visit, cb, f0, g0, h0, gal);
+            pixel_accumulate<MODE>(my_acc, ACC_STRIDE, pc, Ebg, Vbg, covered, first_visit, cb, f0, g0, h0, gal);
         }
         cur = nxt;
+    }
+    if (REG_ACC) {
+#pragma unroll
+        for (int a = 0; a < NACC; ++a) acc[a * PIX_THREADS + tid] = racc[a];
     }
     __syncthreads();
 

@@ -312,7 +312,7 @@ CEL_HD void gal_group(LD ld, const double* comps, int Krt, const double* nu, con
                 A.ft += wd;
                 A.ax1 += w * p1;
                 A.ax2 += w * p2;
-                const double hl11 = ld(cp + 6), hl22 = ld(cp + 7);
+                const double hl11 = 0.5 * l11, hl22 = 0.5 * l22;   // (records 6, 7 hold them; cheaper to recompute here)
                 const double a = p1 * p1, b = p1 * p2, cc = p2 * p2;
                 const double g1 = fma(0.5, a, -hl11);    // bvn_sig_d, BivariateNormals.jl:267-272
                 const double g2 = b - l12;

@@ -287,13 +287,24 @@ def elbo_likelihood(ea: ElboArgs, vp: VariationalParams,
 
 def elbo(ea: ElboArgs, vp: VariationalParams,
          elbo_vars: Optional[ElboIntermediateVariables] = None) -> SensitiveFloat:
-    """elbo_objective.jl:482-492.  The KL term (elbo_kl.jl) is pixel-free host work that
-    stays with the caller; requesting it here is an error
-    rather than a silent omission."""
+    """elbo_objective.jl:482-492: likelihood on the GPU, then `subtract_kl_all_sources!` (elbo_kl.jl:214-225)
+    -- pixel-free, 44 numbers per active source -- added on the host exactly where the reference adds it."""
     for vs in vp:
         if not np.all(np.isfinite(vs)):
             raise AssertionError("vp contains NaNs or Infs")     # elbo_objective.jl:487
+    res = elbo_likelihood(ea, vp, elbo_vars)
     if ea.include_kl:
-        raise NotImplementedError("include_kl=true: subtract_kl_all_sources! (elbo_kl.jl:214) stays on the "
-                                  "host side of the boundary; construct ElboArgs(..., include_kl=False)")
-    return elbo_likelihood(ea, vp, elbo_vars)
+        import torch
+        from .kl import KLTerm
+        order = 2 if res.has_hessian else (1 if res.has_gradient else 0)
+        act = torch.tensor(np.stack([np.asarray(vp[s - 1], dtype=np.float64) for s in ea.active_sources]))
+        kv, kg, kH = KLTerm("cpu")(act, order=order)
+        res.v += float(kv.sum())
+        for sa in range(ea.Sa):                                   # add_sources_sf!, SensitiveFloats.jl:215-250
+            if res.has_gradient:
+                res.d[:, sa] += kg[sa].numpy()
+            if res.has_hessian:
+                res.h[44 * sa:44 * (sa + 1), 44 * sa:44 * (sa + 1)] += kH[sa].numpy()
+        if not (np.isfinite(res.v) and np.isfinite(res.d).all() and np.isfinite(res.h).all()):
+            raise _lib.NonFiniteError(_lib.CELESTE_ERR_NONFINITE, "ELBO contains Inf/NaNs")   # :490
+    return res

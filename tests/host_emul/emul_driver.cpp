@@ -41,9 +41,9 @@ void run(const PlanDev& pd, const FieldDev& fd, int n_blocks, int chunk_pixels, 
     for (int i = 0; i < fd.S_tot * pd.N; ++i) k2 = k2 && fd.patches[i].K == 2;
     if (n_blocks > 0) {
         if (k2)
-            cuda_emul::launch(pixel_kernel<MODE, 2>, n_blocks, PIX_THREADS, smem, pd, chunk_pixels);
+            cuda_emul::launch(pixel_kernel<MODE, 2, true>, n_blocks, PIX_THREADS, smem, pd, chunk_pixels);
         else
-            cuda_emul::launch(pixel_kernel<MODE, 0>, n_blocks, PIX_THREADS, smem, pd, chunk_pixels);
+            cuda_emul::launch(pixel_kernel<MODE, 0, true>, n_blocks, PIX_THREADS, smem, pd, chunk_pixels);
     }
     if (MODE == 2 && pd.n_pairs > 0) {
         const size_t psm = ((size_t)NPAIR_ACC * PAIR_THREADS + 2 * (size_t)MAX_COMPS * COMP_STRIDE) * sizeof(double);

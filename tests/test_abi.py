@@ -50,7 +50,7 @@ def test_sass_is_sm100a_fp64():
     out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out
     sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
-    funcs = [f for f in sass.split("Function : ") if f.startswith("_ZN7celeste12pixel_kernelILi2ELi2E")]
+    funcs = [f for f in sass.split("Function : ") if f.startswith("_ZN7celeste12pixel_kernelILi2ELi2ELb0E")]
     assert len(funcs) == 1 and funcs[0].count("DFMA") > 500
 
 

@@ -335,3 +335,28 @@ def test_concurrent_callers_are_safe(cj):
     for t in th:
         t.join()
     assert not errors, errors[:3]
+
+
+def test_elbo_with_kl_matches_autodiff_hessian_vector(cj):
+    """`elbo` = likelihood - KL with include_kl = true (the ElboArgs default, elbo_args.jl:197), two active
+    sources, checked the way test/test_elbo.jl:273-301 does: Hessian-vector product vs finite differences of
+    the gradient (1 %), plus KL pieces against the autograd checker."""
+    import newton_oracle as no
+    from celeste_jl_b200 import synthetic
+    images, patches, vp, _ = synthetic.gen_two_body_dataset()
+    for v in vp:
+        v[28:36] = v[36:44] = 1.0 / 8
+    ea = cj.ElboArgs(images, patches, [1, 2])
+    assert ea.include_kl
+    r0 = cj.elbo(ea, vp)
+    lik = cj.elbo_likelihood(cj.ElboArgs(images, patches, [1, 2], include_kl=False), vp)
+    kl = [no.kl_ad(v) for v in vp]
+    assert r0.v == pytest.approx(lik.v + kl[0][0] + kl[1][0], rel=1e-12)
+    assert np.allclose(r0.d[:, 1], lik.d[:, 1] + kl[1][1], rtol=1e-10, atol=1e-9)
+    eps = 1e-5
+    vp1 = [v + eps for v in vp]
+    d1 = cj.elbo(ea, vp1, cj.ElboIntermediateVariables(2, True, False)).d.ravel(order="F")
+    hv_fd = (d1 - r0.d.ravel(order="F")) / eps
+    hv = r0.h @ np.ones(88)
+    for i in range(20):
+        assert abs(hv_fd[i] - hv[i]) <= 0.01 * abs(hv[i])

@@ -13,6 +13,10 @@ for name in ("two_body", "clipped_and_empty", "psf_k3", "crowded"):
     for mode in (0, 1, 2):
         out = f.elbo_batch(tasks, mode=mode)
     print(name, out["v"][:2])
+images, patches, tasks = cases.get("config2")
+vpm = np.stack([tasks[0][2][:, 0], tasks[1][2][:, 0], tasks[2][2][:, 0]], axis=1)
+out = cj.DeviceField(images, patches).elbo_batch([([1, 2, 3], [3, 1, 2], vpm)], mode=2)
+print("Sa=3", out["v"], out["counters"])
 g = torch.randn(4, 41, dtype=torch.float64, device="cuda")
 A = torch.randn(4, 41, 41, dtype=torch.float64, device="cuda")
 s, m, interior = em.solve_tr_subproblem(g, A + A.transpose(1, 2), torch.ones(4, dtype=torch.float64, device="cuda"))
