@@ -132,26 +132,54 @@ def load_oracle_for_timing():
         return oracle_lib, oracle_lib.load(), "portable"
 
 
+def effective_cores():
+    """Host cores this process may really use: the cgroup CPU quota when there is one (the GPU boxes show 128
+    logical CPUs but cap the container at 16), else the affinity mask."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(round(int(q) / int(p)))))
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            p = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, int(round(q / p))))
+        except Exception:
+            pass
+    return n
+
+
 def cpu_leg(ds, sample, mode, steps, warmup):
     """Time the oracle (the reference's as-written algorithm, multithreaded over sources with a shared counter
-    like one_node_single_infer) on `sample` tasks of field 0, all host cores."""
+    like one_node_single_infer) on `sample` tasks of field 0, with all the host cores the box grants
+    (thread count = the better of 1x and 2x the core quota, picked by one trial step each)."""
     oracle_lib, lib, build = load_oracle_for_timing()
-    cores = os.cpu_count() or 1
+    cores = effective_cores()
     rows, act = ds.tasks(range(min(sample, len(ds.catalog))))
     from celeste_jl_b200.flatten import csr_tasks
     tasks = [(r, a, np.stack([ds.vp[i - 1] for i in r], axis=1)) for r, a in zip(rows, act)]
     csr = csr_tasks(tasks)
     of = oracle_lib.OracleField(ds.images, ds.patches, lib=lib)
-    for _ in range(max(1, min(warmup, 1))):
-        of.elbo_csr(*csr, mode=mode, n_threads=cores)
+    best = None
+    for nt in sorted({cores, 2 * cores}):
+        of.elbo_csr(*csr, mode=mode, n_threads=nt)
+        t0 = time.perf_counter()
+        of.elbo_csr(*csr, mode=mode, n_threads=nt)
+        dt = time.perf_counter() - t0
+        if best is None or dt < best[0]:
+            best = (dt, nt)
+    threads = best[1]
     t0 = time.perf_counter()
     for _ in range(steps):
-        out = of.elbo_csr(*csr, mode=mode, n_threads=cores)
+        out = of.elbo_csr(*csr, mode=mode, n_threads=threads)
     dt = (time.perf_counter() - t0) / steps
     visits = int(out["counters"].sum())
-    return {"value": len(tasks) / dt, "unit": "sources/s", "cores": cores, "kind": "port",
+    return {"value": len(tasks) / dt, "unit": "sources/s", "cores": cores, "threads": threads, "kind": "port",
             "sample": f"{len(tasks)} tasks of field 0 per step ({visits} pixel-visits), mode={'grad' if mode == 1 else 'hess'}, "
-                      f"oracle build={build}, {steps} steps",
+                      f"oracle build={build}, {steps} steps, {threads} threads on {cores} granted cores "
+                      f"({os.cpu_count()} logical CPUs visible)",
             "ms_per_step": dt * 1e3, "pixel_visits_per_s": visits / dt}
 
 
