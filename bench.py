@@ -361,7 +361,7 @@ def main():
         ach = flop / (m["pix_ms"] * 1e-3) / 1e12          # aggregate over ranks (flop summed, time = max over ranks)
         r = {"bound": "fp64", "achieved": ach, "peak": peak * world, "unit": "TFLOP/s", "frac": ach / (peak * world),
              "peak_per_gpu": peak,
-             "traffic": None, "kernel": f"pixel_kernel<{mode}>", "kernel_ms_per_step": m["pix_ms"],
+             "traffic": None, "kernel": ("task_kernel<1>" if mode == 1 else "pixel_kernel<2>"), "kernel_ms_per_step": m["pix_ms"],
              "kernel_share_of_step": m["pix_ms"] / m["ms"],
              "algorithmic_flop_per_step": flop, "pixel_visits_active": m["active"], "pixel_visits_inactive": m["inactive"],
              "peak_source": "measured live: celeste_fp64_peak (register DFMA chain); nominal 37 TFLOP/s",
@@ -372,7 +372,7 @@ def main():
         prof = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(prof):
             try:
-                t = json.load(open(prof)).get(f"pixel_kernel<{mode}>")
+                t = json.load(open(prof)).get("task_kernel<1>" if mode == 1 else "pixel_kernel<2>")
                 if t and t.get("sources") == int(total_sources):
                     r["traffic"] = t["dram_bytes_per_launch"] / world
                     r["traffic_source"] = t

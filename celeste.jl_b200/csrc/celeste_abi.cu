@@ -111,19 +111,31 @@ size_t pixel_smem_bytes() {
     return ((size_t)NAcc<MODE>::value * PIX_THREADS + (size_t)MAX_COMPS * COMP_STRIDE) * sizeof(double);
 }
 
+template <int MODE>
+size_t task_smem_bytes() {
+    return ((size_t)NAcc<MODE>::value * PIX_THREADS + (size_t)TASK_NIMG * MAX_COMPS * COMP_STRIDE) * sizeof(double);
+}
+
 int configure_kernels() {
 #define CEL_CFG(M, K)                                                                                                  \
     CUDA_TRY(cudaFuncSetAttribute(pixel_kernel<M, K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,             \
                                   (int)pixel_smem_bytes<M>()));                                                       \
     CUDA_TRY(cudaFuncSetAttribute(pixel_kernel<M, K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,              \
                                   (int)pixel_smem_bytes<M>()))
-    CEL_CFG(0, 0);
-    CEL_CFG(1, 0);
-    CEL_CFG(2, 0);
-    CEL_CFG(0, 2);
-    CEL_CFG(1, 2);
+    CEL_CFG(2, 0);      // pixel_kernel serves the Hessian mode only; value / gradient use task_kernel
     CEL_CFG(2, 2);
 #undef CEL_CFG
+#define CEL_TCFG(M, K, X) \
+    CUDA_TRY(cudaFuncSetAttribute(task_kernel<M, K, X>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)task_smem_bytes<M>()))
+    CEL_TCFG(0, 0, false);
+    CEL_TCFG(0, 0, true);
+    CEL_TCFG(0, 2, false);
+    CEL_TCFG(0, 2, true);
+    CEL_TCFG(1, 0, false);
+    CEL_TCFG(1, 0, true);
+    CEL_TCFG(1, 2, false);
+    CEL_TCFG(1, 2, true);
+#undef CEL_TCFG
     {
         const int psm = (int)(((size_t)NPAIR_ACC * PAIR_THREADS + 2 * (size_t)MAX_COMPS * COMP_STRIDE) * sizeof(double));
         CUDA_TRY(cudaFuncSetAttribute(pair_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, psm));
@@ -178,6 +190,9 @@ struct celeste_plan {
     DevBuf<int> task_ptr, src_row, sub_ptr, sub_slot, chunk_ptr, pair_ptr;
     DevBuf<long long> h_ptr;
     DevBuf<BlockHdr> blockmap;
+    DevBuf<TaskHdr> taskmap;          // value / gradient modes: one block per (sub, image group)
+    DevBuf<int> task_chunk_ptr;       // partial ranges of task_kernel: TASK_WARPS per (sub, image)
+    int n_taskblocks = 0;
     DevBuf<PairHdr> pairmap;
     DevBuf<double> slotimg, slotbr, partials, pair_partials;
     int n_subs = 0, n_pairs = 0;
@@ -499,6 +514,47 @@ int celeste_plan_create_multi(int32_t n_fields, celeste_field* const* fields, ce
                 blockmap.push_back(hd);
             }
         }
+    // value / gradient modes: task-level blocks (task_kernel), heaviest first so the launch tail is short
+    std::vector<TaskHdr> taskmap;
+    std::vector<long> taskcost;
+    for (int u = 0; u < n_subs; ++u) {
+        const int t = sub_task[u];
+        const celeste_field* f = fields[tfield[t]];
+        for (int n0 = 0; n0 < pl->N; n0 += TASK_NIMG) {
+            TaskHdr th;
+            th.tn0 = u * pl->N;
+            th.aslot = sub_slot[u];
+            th.slot0 = task_ptr[t];
+            th.slot1 = task_ptr[t + 1];
+            th.field = tfield[t];
+            th.sub0 = sub_ptr[t];
+            th.sub = u;
+            th.sub1 = sub_ptr[t + 1];
+            th.n0 = n0;
+            th.n1 = std::min(pl->N, n0 + TASK_NIMG);
+            th.pad0 = th.pad1 = 0;
+            long cost = 0;
+            for (int n = th.n0; n < th.n1; ++n) {
+                const PatchDev& pa = f->h_patches[(size_t)src_row[sub_slot[u]] + (size_t)n * f->S_tot];
+                cost += (long)pa.H2 * pa.W2 * (1 + (th.slot1 - th.slot0 - 1) / 4);
+            }
+            taskmap.push_back(th);
+            taskcost.push_back(cost);
+        }
+    }
+    {
+        std::vector<int> order(taskmap.size());
+        for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return taskcost[x] > taskcost[y]; });
+        std::vector<TaskHdr> sorted(taskmap.size());
+        for (size_t i = 0; i < order.size(); ++i) sorted[i] = taskmap[order[i]];
+        taskmap.swap(sorted);
+    }
+    pl->n_taskblocks = (int)taskmap.size();
+    std::vector<int> task_chunk_ptr((size_t)n_subs * pl->N + 1);
+    for (size_t i = 0; i < task_chunk_ptr.size(); ++i) task_chunk_ptr[i] = (int)(i * TASK_WARPS);
+    CUDA_TRY(pl->taskmap.upload(taskmap));
+    CUDA_TRY(pl->task_chunk_ptr.upload(task_chunk_ptr));
     pl->n_blocks = (int)blockmap.size();
     std::vector<int> tp(task_ptr, task_ptr + n_tasks + 1);
     CUDA_TRY(pl->d_fields.upload(hf));
@@ -516,7 +572,8 @@ int celeste_plan_create_multi(int32_t n_fields, celeste_field* const* fields, ce
     CUDA_TRY(pl->blockmap.upload(blockmap));
     CUDA_TRY(pl->slotimg.alloc((size_t)n_slots * pl->N * SLOTIMG_STRIDE));
     CUDA_TRY(pl->slotbr.alloc((size_t)n_slots * SLOTBR_STRIDE));
-    CUDA_TRY(pl->partials.alloc((size_t)pl->n_blocks * NACC_MODE2));
+    CUDA_TRY(pl->partials.alloc(std::max((size_t)pl->n_blocks * NACC_MODE2,
+                                          (size_t)n_subs * pl->N * TASK_WARPS * NACC_MODE1)));
     *out = pl.release();
     return CELESTE_OK;
 }
@@ -597,7 +654,28 @@ static int launch_mode(celeste_plan* p, const double* vp_dev, double* v, double*
     if (p->timing) CUDA_TRY(cudaEventRecord(p->ev[0], st));
     setup_kernel<<<sblocks, 256, 0, st>>>(pd, vp_dev);
     if (p->timing) CUDA_TRY(cudaEventRecord(p->ev[1], st));
-    if (p->n_blocks > 0) {
+    if constexpr (MODE <= 1) {
+        // value / gradient: task-level blocks, one partial per (sub, image, warp)
+        PlanDev pt = pd;
+        pt.chunk_ptr = p->task_chunk_ptr.p;
+        const bool multi = p->n_subs > p->n_tasks;
+        const size_t sm = task_smem_bytes<MODE>();
+        if (p->n_taskblocks > 0) {
+            if (p->uniform_K == 2 && !multi)
+                task_kernel<MODE, 2, false><<<p->n_taskblocks, PIX_THREADS, sm, st>>>(pt, p->taskmap.p);
+            else if (p->uniform_K == 2)
+                task_kernel<MODE, 2, true><<<p->n_taskblocks, PIX_THREADS, sm, st>>>(pt, p->taskmap.p);
+            else if (!multi)
+                task_kernel<MODE, 0, false><<<p->n_taskblocks, PIX_THREADS, sm, st>>>(pt, p->taskmap.p);
+            else
+                task_kernel<MODE, 0, true><<<p->n_taskblocks, PIX_THREADS, sm, st>>>(pt, p->taskmap.p);
+        }
+        if (p->timing) CUDA_TRY(cudaEventRecord(p->ev[2], st));
+        epilogue_kernel<MODE><<<p->n_tasks, EPI_THREADS, 0, st>>>(pt, vp_dev, v, d, h, counters, flags);
+        if (p->timing) CUDA_TRY(cudaEventRecord(p->ev[3], st));
+        CUDA_TRY(cudaGetLastError());
+        return CELESTE_OK;
+    } else if (p->n_blocks > 0) {
         const bool multi = p->n_subs > p->n_tasks;
         const size_t sm = pixel_smem_bytes<MODE>();
         if (p->uniform_K == 2 && !multi)

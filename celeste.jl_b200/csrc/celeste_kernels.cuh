@@ -3,7 +3,10 @@
 //   prep_image_kernel   once per image: pixconst = x log(iota) - lgamma(x + 1)   (elbo_objective.jl:292,391)
 //   setup_kernel        per evaluation: mixtures of every (task source, image)   (fsm_util.jl:111-169)
 //                       + per-source brightness moments                          (source_brightness.jl:27-202)
-//   pixel_kernel<MODE>  THE hot loop: one block per (task, image, pixel chunk)   (elbo_objective.jl:330-470)
+//   task_kernel<MODE>   THE hot loop, value / gradient modes: one block per (active source, <= 5 images),
+//                       warps never synchronise                                  (elbo_objective.jl:330-470)
+//   pixel_kernel<2>     THE hot loop, Hessian mode: one block per (active source, image, pixel chunk)
+//   pair_kernel         Sa > 1 only: cross-source Hessian blocks                 (SensitiveFloats.jl:114-126)
 //   epilogue_kernel<MODE> per task: fixed-order reduction of the chunk partials, raw -> parameter
 //                       chain rule, 44 x 44 SensitiveFloat output                (SensitiveFloats.jl:23-47)
 //
@@ -390,6 +393,214 @@ __global__ void __launch_bounds__(PIX_THREADS, MODE == 2 ? CELESTE_PIX_MINB_HESS
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (lane == 0) out[a] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// task_kernel<MODE <= 1>: value / gradient modes.  One block per (active source of a task, group of <= TASK_NIMG
+// images).  A typical patch is ~400 pixels = 12.5 warp-iterations, which a 4-warp block cannot split evenly
+// (3.25 per warp: a quarter of the block idles at the final barrier in pixel_kernel).  Here the warps of a block
+// walk through ALL images of the task without ever synchronising: the warp-iterations of image n are dealt
+// round-robin starting where image n-1 stopped, each warp reduces its own accumulators by shuffles when it leaves
+// an image and writes one partial per (sub, image, warp).  The per-block prologue (header, component records,
+// neighbour lists) is paid once per task instead of once per image.  The Hessian mode keeps pixel_kernel: its 68
+// accumulator slots per thread leave no shared memory for five images' component records.
+constexpr int TASK_NIMG = 5;
+constexpr int TASK_WARPS = PIX_THREADS / 32;
+constexpr int TASK_NB = 32;          // neighbour-list capacity per image (overflow falls back to a slot scan)
+
+struct TaskHdr {
+    int tn0;             // sub * N  (partials of (sub, n, warp) live at ((tn0 + n) * TASK_WARPS + warp))
+    int aslot, slot0, slot1;
+    int field;
+    int sub0, sub, sub1;
+    int n0, n1;          // image range of this block
+    int pad0, pad1;
+};
+
+template <int MODE, int KT, bool MULTI>
+__global__ void __launch_bounds__(PIX_THREADS, CELESTE_PIX_MINB_GRAD) task_kernel(PlanDev plan, const TaskHdr* __restrict__ taskmap) {
+    static_assert(MODE <= 1, "the Hessian mode uses pixel_kernel");
+    constexpr int NACC = NAcc<MODE>::value;
+    CEL_DYNAMIC_SMEM(smem);
+    double* acc = smem;                                     // NACC x PIX_THREADS
+    double* s_comps = acc + NACC * PIX_THREADS;             // TASK_NIMG x MAX_COMPS x COMP_STRIDE
+    __shared__ double s_exptab[8];
+    __shared__ int s_nb[TASK_NIMG][TASK_NB];
+    __shared__ int s_nb_count[TASK_NIMG];
+    __shared__ int s_nb_overflow[TASK_NIMG];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const TaskHdr th = taskmap[blockIdx.x];
+    const int slot0 = th.slot0, slot1 = th.slot1, aslot = th.aslot;
+    const int sub0 = th.sub0, sub = th.sub, sub1 = th.sub1;
+    const bool multi = MULTI && (sub1 - sub0) > 1;
+    const FieldDev field = plan.fields[th.field];
+    const int nimg = th.n1 - th.n0;
+
+#pragma unroll
+    for (int a = 0; a < NACC; ++a) acc[a * PIX_THREADS + tid] = 0.0;
+    {
+        // component records of all images of the group: one flat, coalesced copy (only the 14 K live records when K is known)
+        constexpr int per = (KT > 0 ? NPROTO * KT : MAX_COMPS) * COMP_STRIDE;   // mixed K: whole records
+        for (int i = tid; i < nimg * per; i += PIX_THREADS) {
+            const int k = i / per, r = i - k * per;
+            s_comps[k * MAX_COMPS * COMP_STRIDE + r] =
+                plan.slotimg[((size_t)aslot * plan.N + th.n0 + k) * SLOTIMG_STRIDE + r];
+        }
+    }
+#ifdef CELESTE_HOST_EMULATION
+    if (tid < 8) s_exptab[tid] = h_exptab[tid];
+#else
+    if (tid < 8) s_exptab[tid] = c_exptab[tid];
+#endif
+    // neighbour lists: warp w compacts (in slot order) the sources whose patch in image n0 + k meets the active patch
+    for (int k = warp; k < nimg; k += TASK_WARPS) {
+        const int n = th.n0 + k;
+        const PatchDev& pa = field.patches[plan.src_row[aslot] + (size_t)n * field.S_tot];
+        int count = 0, overflow = 0;
+        for (int base = slot0; base < slot1; base += 32) {
+            const int s = base + lane;
+            bool hit = false;
+            if (s < slot1 && s != aslot && pa.H2 > 0 && pa.W2 > 0) {
+                const PatchDev& p = field.patches[plan.src_row[s] + (size_t)n * field.S_tot];
+                hit = (p.off_h + 1 <= pa.off_h + pa.H2) && (p.off_h + p.H2 >= pa.off_h + 1) &&
+                      (p.off_w + 1 <= pa.off_w + pa.W2) && (p.off_w + p.W2 - 1 >= pa.off_w + 1);
+            }
+            const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+            const int pos = count + __popc(ballot & ((1u << lane) - 1u));
+            if (hit && pos < TASK_NB) s_nb[k][pos] = s;
+            if (count + __popc(ballot) > TASK_NB) overflow = 1;
+            count = min(count + __popc(ballot), TASK_NB);
+        }
+        if (lane == 0) {
+            s_nb_count[k] = count;
+            s_nb_overflow[k] = overflow;
+        }
+    }
+    __syncthreads();
+
+    const double* abr = plan.slotbr + (size_t)aslot * SLOTBR_STRIDE;
+    const double a1 = abr[20], a2 = abr[21], theta = abr[22];
+    int rot = 0;     // warp-iterations dealt so far (mod TASK_WARPS): where the next image starts
+
+    for (int k = 0; k < nimg; ++k) {
+        const int n = th.n0 + k;
+        const ImageDev img = field.images[n];
+        const PatchDev pa = field.patches[plan.src_row[aslot] + (size_t)n * field.S_tot];
+        const int npix = pa.H2 * pa.W2;
+        const int nit = (npix + 31) >> 5;
+        const double* comps_k = s_comps + k * MAX_COMPS * COMP_STRIDE;
+        const double* arec = plan.slotimg + ((size_t)aslot * plan.N + n) * SLOTIMG_STRIDE;
+        const double am1 = arec[MAX_COMPS * COMP_STRIDE], am2 = arec[MAX_COMPS * COMP_STRIDE + 1];
+        const int b = img.band - 1;
+        const double cb[4] = {a1 * abr[b], a2 * abr[5 + b], a1 * abr[10 + b], a2 * abr[15 + b]};
+
+        double cnt_other_active = 0.0;
+        auto neighbour = [&](int s, int h, int w, double& Ebg, double& Vbg, double& cnt) {
+            const PatchDev& p = field.patches[plan.src_row[s] + (size_t)n * field.S_tot];
+            const int h2 = h - p.off_h, w2 = w - p.off_w;
+            if (h2 < 1 || h2 > p.H2 || w2 < 1 || w2 >= p.W2) return;
+            if (!p.bitmap[(h2 - 1) + (size_t)(w2 - 1) * p.H2]) return;
+            bool other_active = false;
+            if (multi)
+                for (int j = sub0; j < sub1; ++j) other_active |= (plan.sub_slot[j] == s);
+            if (other_active)
+                cnt_other_active += 1.0;
+            else
+                cnt += 1.0;
+            const double* rec = plan.slotimg + ((size_t)s * plan.N + n) * SLOTIMG_STRIDE;
+            const double* br = plan.slotbr + (size_t)s * SLOTBR_STRIDE;
+            const double m1 = __ldg(rec + MAX_COMPS * COMP_STRIDE), m2 = __ldg(rec + MAX_COMPS * COMP_STRIDE + 1);
+            double f0, gd[2], hd[3];
+            star_eval<0>(LdGlobal(), p.coefs, p.n1, p.n2, (double)h - m1 + 26.0, (double)w - m2 + 26.0, f0, gd, hd);
+            const double f1 = gal_value<KT>(LdGlobal(), rec, p.K, s_exptab, __ldg(br + 22), (double)h, (double)w);
+            const double na1 = __ldg(br + 20), na2 = __ldg(br + 21);
+            const double Es = na1 * __ldg(br + b) * f0 + na2 * __ldg(br + 5 + b) * f1;
+            const double E2s = na1 * __ldg(br + 10 + b) * f0 * f0 + na2 * __ldg(br + 15 + b) * f1 * f1;
+            Ebg += Es;
+            Vbg += E2s - Es * Es;
+        };
+        struct PixIn {
+            unsigned char active;
+            float x, sky, iota;
+            double pixconst;
+        };
+        auto fetch = [&](int it) {
+            PixIn in;
+            in.active = 0;
+            in.x = in.sky = in.iota = 0.f;
+            in.pixconst = 0.0;
+            const int pix = it * 32 + lane;
+            if (it < nit && pix < npix) {
+                const int h2 = pix % pa.H2, w2 = pix / pa.H2;
+                const size_t ipix = (size_t)(pa.off_h + h2) + (size_t)(pa.off_w + w2) * img.H;
+                in.active = pa.bitmap[pix];
+                in.x = img.pixels[ipix];
+                in.sky = img.sky[ipix];
+                in.iota = img.iota[pa.off_h + h2];
+                in.pixconst = img.pixconst[ipix];
+            }
+            return in;
+        };
+        // this warp's iterations of image n: it = first, first + 4, ...  with (it + rot) % 4 == warp
+        const int first = (warp - rot + TASK_WARPS) % TASK_WARPS;
+        PixIn cur = fetch(first);
+        for (int it = first; it < nit; it += TASK_WARPS) {
+            const PixIn nxt = fetch(it + TASK_WARPS);
+            const int pix = it * 32 + lane;
+            if (cur.active && !isnan(cur.x)) {
+                const int h2 = pix % pa.H2, w2 = pix / pa.H2;
+                const int h = pa.off_h + h2 + 1, w = pa.off_w + w2 + 1;
+                PixelConsts pc;
+                pc.x = (double)cur.x;
+                pc.iota = (double)cur.iota;
+                pc.pixconst = cur.pixconst;
+                double Ebg = (double)cur.sky, Vbg = 0.0, cnt_inactive = 0.0;
+                cnt_other_active = 0.0;
+                bool first_visit = true;
+                if (multi)
+                    for (int j = sub0; j < sub; ++j) {
+                        const PatchDev& pj = field.patches[plan.src_row[plan.sub_slot[j]] + (size_t)n * field.S_tot];
+                        const int hj = h - pj.off_h, wj = w - pj.off_w;
+                        if (hj >= 1 && hj <= pj.H2 && wj >= 1 && wj <= pj.W2 && pj.bitmap[(hj - 1) + (size_t)(wj - 1) * pj.H2])
+                            first_visit = false;
+                    }
+                const int nnb = s_nb_count[k];
+                for (int i = 0; i < nnb; ++i) neighbour(s_nb[k][i], h, w, Ebg, Vbg, cnt_inactive);
+                if (s_nb_overflow[k]) {
+                    const int last_listed = s_nb[k][TASK_NB - 1];
+                    for (int s = last_listed + 1; s < slot1; ++s)
+                        if (s != aslot) neighbour(s, h, w, Ebg, Vbg, cnt_inactive);
+                }
+                const bool covered = (w2 + 1) < pa.W2;
+                double f0 = 0.0, g0[2] = {0.0, 0.0}, h0[3] = {0.0, 0.0, 0.0};
+                GalRaw gal;
+                gal.f = 0.0;
+                if (covered) {
+                    star_eval<MODE>(LdGlobal(), pa.coefs, pa.n1, pa.n2, (double)h - am1 + 26.0, (double)w - am2 + 26.0, f0,
+                                    g0, h0);
+                    gal_eval<MODE, KT>(LdShared(), comps_k, pa.K, c_proto_nu, s_exptab, theta, (double)h, (double)w, gal);
+                }
+                if (first_visit) {
+                    acc[ACC_CNT_ACTIVE * PIX_THREADS + tid] += (covered ? 1.0 : 0.0) + cnt_other_active;
+                    acc[ACC_CNT_INACTIVE * PIX_THREADS + tid] += cnt_inactive;
+                }
+                pixel_accumulate<MODE>(acc + tid, PIX_THREADS, pc, Ebg, Vbg, covered, first_visit, cb, f0, g0, h0, gal);
+            }
+            cur = nxt;
+        }
+        rot = (rot + nit) % TASK_WARPS;
+        // leave image n: this warp's partial (fixed shuffle order), then clear the slots
+        double* out = plan.partials + ((size_t)(th.tn0 + n) * TASK_WARPS + warp) * NACC;
+#pragma unroll
+        for (int a = 0; a < NACC; ++a) {
+            double v = acc[a * PIX_THREADS + tid];
+            acc[a * PIX_THREADS + tid] = 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) out[a] = v;
+        }
     }
 }
 

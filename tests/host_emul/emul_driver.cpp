@@ -33,6 +33,25 @@ void galaxy_prototypes(double eta[NPROTO], double nu[NPROTO]) {
 }
 
 template <int MODE>
+void run_task(PlanDev pd, const FieldDev& fd, const std::vector<TaskHdr>& taskmap, const std::vector<int>& tcp,
+              const double* vp, double* v, double* d, double* h, long long* counters, int* flags) {
+    if constexpr (MODE <= 1) {
+        const size_t smem = ((size_t)NAcc<MODE>::value * PIX_THREADS + (size_t)TASK_NIMG * MAX_COMPS * COMP_STRIDE) * sizeof(double);
+        cuda_emul::launch(setup_kernel, 2, 64, 0, pd, vp);
+        pd.chunk_ptr = tcp.data();
+        bool k2 = true;
+        for (int i = 0; i < fd.S_tot * pd.N; ++i) k2 = k2 && fd.patches[i].K == 2;
+        if (!taskmap.empty()) {
+            if (k2)
+                cuda_emul::launch(task_kernel<MODE, 2, true>, (int)taskmap.size(), PIX_THREADS, smem, pd, taskmap.data());
+            else
+                cuda_emul::launch(task_kernel<MODE, 0, true>, (int)taskmap.size(), PIX_THREADS, smem, pd, taskmap.data());
+        }
+        cuda_emul::launch(epilogue_kernel<MODE>, pd.n_tasks, EPI_THREADS, 0, pd, vp, v, d, h, counters, flags);
+    }
+}
+
+template <int MODE>
 void run(const PlanDev& pd, const FieldDev& fd, int n_blocks, int chunk_pixels, const double* vp, double* v, double* d,
          double* h, long long* counters, int* flags) {
     const size_t smem = ((size_t)NAcc<MODE>::value * PIX_THREADS + (size_t)MAX_COMPS * COMP_STRIDE) * sizeof(double);
@@ -133,8 +152,18 @@ extern "C" int emul_elbo_batch(int32_t N, const celeste_image* imgs, int32_t S_t
                                             sub_ptr[t + 1], 0});
         }
     std::vector<int> tp(task_ptr, task_ptr + n_tasks + 1);
+    std::vector<TaskHdr> taskmap;
+    for (int u = 0; u < n_subs; ++u)
+        for (int n0 = 0; n0 < N; n0 += TASK_NIMG) {
+            const int t = sub_task[u];
+            taskmap.push_back(TaskHdr{u * N, sub_slot[u], task_ptr[t], task_ptr[t + 1], 0, sub_ptr[t], u, sub_ptr[t + 1], n0,
+                                      std::min(N, n0 + TASK_NIMG), 0, 0});
+        }
+    std::vector<int> tcp((size_t)n_subs * N + 1);
+    for (size_t i = 0; i < tcp.size(); ++i) tcp[i] = (int)(i * TASK_WARPS);
     std::vector<double> slotimg((size_t)n_slots * N * SLOTIMG_STRIDE), slotbr((size_t)n_slots * SLOTBR_STRIDE),
-        partials(blockmap.size() * NACC_MODE2 + 1), pair_partials(pairmap.size() * NPAIR_ACC + 1);
+        partials(std::max(blockmap.size() * NACC_MODE2, (size_t)n_subs * N * TASK_WARPS * NACC_MODE1) + 1),
+        pair_partials(pairmap.size() * NPAIR_ACC + 1);
     PlanDev pd;
     FieldDev fd{images.data(), pdv.data(), S_tot, 0};
     std::vector<int> tfield(n_tasks, 0), sfield(n_slots, 0);
@@ -163,9 +192,9 @@ extern "C" int emul_elbo_batch(int32_t N, const celeste_image* imgs, int32_t S_t
     std::vector<long long> cnt(2 * (size_t)n_tasks);
     const int nb = (int)blockmap.size();
     if (mode == 0)
-        run<0>(pd, fd, nb, chunk_pixels, vp, v, d, h, cnt.data(), flags);
+        run_task<0>(pd, fd, taskmap, tcp, vp, v, d, h, cnt.data(), flags);
     else if (mode == 1)
-        run<1>(pd, fd, nb, chunk_pixels, vp, v, d, h, cnt.data(), flags);
+        run_task<1>(pd, fd, taskmap, tcp, vp, v, d, h, cnt.data(), flags);
     else
         run<2>(pd, fd, nb, chunk_pixels, vp, v, d, h, cnt.data(), flags);
     for (size_t i = 0; i < cnt.size(); ++i) counters[i] = cnt[i];
