@@ -58,7 +58,7 @@ EXPORTS = [
     "celeste_plan_create", "celeste_plan_destroy", "celeste_plan_launches",
     "celeste_elbo_plan_device", "celeste_elbo_plan_host", "celeste_field_destroy",
     "celeste_fp64_peak", "celeste_plan_enable_timing", "celeste_plan_kernel_times", "celeste_set_chunk_pixels",
-    "celeste_plan_create_multi", "celeste_tr_subproblem",
+    "celeste_plan_create_multi", "celeste_tr_subproblem", "celeste_plan_set_task_mask",
 ]
 
 _lib = None
@@ -99,6 +99,7 @@ def load():
     lib.celeste_plan_enable_timing.argtypes = [vp, i32]
     lib.celeste_plan_kernel_times.argtypes = [vp, C.POINTER(C.c_float * 3)]
     lib.celeste_set_chunk_pixels.argtypes = [i32]
+    lib.celeste_plan_set_task_mask.argtypes = [vp, vp]
     lib.celeste_tr_subproblem.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp, vp]
     _lib = lib
     return lib

@@ -202,6 +202,7 @@ struct celeste_plan {
     DevBuf<long long> counters_dev;
     DevBuf<int> flags_dev;
     cudaStream_t stream = nullptr;
+    const unsigned char* task_mask = nullptr;   // device pointer owned by the caller
     bool timing = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     ~celeste_plan() {
@@ -510,7 +511,7 @@ int celeste_plan_create_multi(int32_t n_fields, celeste_field* const* fields, ce
                 hd.sub0 = sub_ptr[t];
                 hd.sub = u;
                 hd.sub1 = sub_ptr[t + 1];
-                hd.pad = 0;
+                hd.task = t;
                 blockmap.push_back(hd);
             }
         }
@@ -532,7 +533,8 @@ int celeste_plan_create_multi(int32_t n_fields, celeste_field* const* fields, ce
             th.sub1 = sub_ptr[t + 1];
             th.n0 = n0;
             th.n1 = std::min(pl->N, n0 + TASK_NIMG);
-            th.pad0 = th.pad1 = 0;
+            th.task = t;
+            th.pad1 = 0;
             long cost = 0;
             for (int n = th.n0; n < th.n1; ++n) {
                 const PatchDev& pa = f->h_patches[(size_t)src_row[sub_slot[u]] + (size_t)n * f->S_tot];
@@ -585,6 +587,12 @@ int celeste_plan_create(celeste_field* f, celeste_plan** out, int32_t n_tasks, c
 }
 
 void celeste_plan_destroy(celeste_plan* p) { delete p; }
+
+int celeste_plan_set_task_mask(celeste_plan* p, const uint8_t* mask_dev) {
+    if (!p) return CELESTE_ERR_BAD_ARG;
+    p->task_mask = mask_dev;
+    return CELESTE_OK;
+}
 
 int celeste_set_chunk_pixels(int32_t chunk_pixels) {
     if (chunk_pixels < 0) return CELESTE_ERR_BAD_ARG;
@@ -639,6 +647,7 @@ static PlanDev plan_dev(const celeste_plan* p) {
     d.pairmap = p->pairmap.p;
     d.pair_ptr = p->pair_ptr.p;
     d.pair_partials = p->pair_partials.p;
+    d.task_mask = p->task_mask;
     d.slotimg = p->slotimg.p;
     d.slotbr = p->slotbr.p;
     d.partials = p->partials.p;

@@ -68,7 +68,7 @@ struct BlockHdr {
     int n;         // image
     int field;     // index into PlanDev::fields
     int sub0, sub, sub1;   // this task's active sources are subs [sub0, sub1); this block works for `sub`
-    int pad;
+    int task;
 };
 
 // one block of pair_kernel: the cross-source Hessian block of two active sources of one task in one image
@@ -95,6 +95,7 @@ struct PlanDev {
     const PairHdr* pairmap;  // n_pairs * N
     const int* pair_ptr;     // n_tasks + 1: first pair of each task
     double* pair_partials;   // n_pairs * N * NPAIR_ACC
+    const unsigned char* task_mask;   // optional (may be null): tasks with mask 0 are skipped, their outputs left untouched
     double* slotimg;         // n_slots * N * SLOTIMG_STRIDE
     double* slotbr;          // n_slots * SLOTBR_STRIDE
     double* partials;        // n_blocks * NACC
@@ -195,6 +196,7 @@ __global__ void __launch_bounds__(PIX_THREADS, MODE == 2 ? CELESTE_PIX_MINB_HESS
 
     const int tid = threadIdx.x;
     const BlockHdr bm = plan.blockmap[blockIdx.x];
+    if (plan.task_mask && !plan.task_mask[bm.task]) return;   // e.g. a source whose Newton iteration has converged
     const int chunk = bm.chunk, n = bm.n;
     const int slot0 = bm.slot0, slot1 = bm.slot1;
     const int aslot = bm.aslot;
@@ -415,7 +417,7 @@ struct TaskHdr {
     int field;
     int sub0, sub, sub1;
     int n0, n1;          // image range of this block
-    int pad0, pad1;
+    int task, pad1;
 };
 
 template <int MODE, int KT, bool MULTI>
@@ -432,6 +434,7 @@ __global__ void __launch_bounds__(PIX_THREADS, CELESTE_PIX_MINB_GRAD) task_kerne
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const TaskHdr th = taskmap[blockIdx.x];
+    if (plan.task_mask && !plan.task_mask[th.task]) return;
     const int slot0 = th.slot0, slot1 = th.slot1, aslot = th.aslot;
     const int sub0 = th.sub0, sub = th.sub, sub1 = th.sub1;
     const bool multi = MULTI && (sub1 - sub0) > 1;
@@ -772,6 +775,7 @@ __global__ void __launch_bounds__(EPI_THREADS) epilogue_kernel(PlanDev plan,
 
     const int tid = threadIdx.x;
     const int t = blockIdx.x;
+    if (plan.task_mask && !plan.task_mask[t]) return;
     const int sub0 = plan.sub_ptr[t], sub1 = plan.sub_ptr[t + 1];
     const int Sa = sub1 - sub0;
     const int P = NPARAM * Sa;

@@ -195,6 +195,10 @@ class Plan:
                                                  self.active_ptr.ctypes.data, self.act.ctypes.data))
         self._finalizer = weakref.finalize(self, lib.celeste_plan_destroy, self._handle)
 
+    def set_task_mask(self, mask_dev_ptr: int):
+        """celeste_plan_set_task_mask: device pointer to n_tasks bytes (0 = skip the task), or 0 to clear."""
+        _lib.check(_lib.load().celeste_plan_set_task_mask(self._handle, mask_dev_ptr or None))
+
     def enable_timing(self, on: bool = True):
         _lib.check(_lib.load().celeste_plan_enable_timing(self._handle, int(on)))
 

@@ -141,6 +141,9 @@ class BatchMaximizer:
         vp0 = ct.enforce(vp0, self.lo, self.hi)                   # enforce! :230
         self.x = ct.to_free(vp0, self.lo, self.hi)                # to_free! :231
         self.f_calls = 0
+        # device-side mask of sources still iterating: the kernels skip converged sources' tasks
+        self.mask = torch.ones(n, dtype=torch.uint8, device=self.dev)
+        self.use_mask = runner is None and hasattr(plan, "set_task_mask")
         self.profile = None        # set to {} to collect wall-clock per phase (synchronising; diagnostics only)
 
     def _tick(self, name, t0):
@@ -186,6 +189,15 @@ class BatchMaximizer:
     def run(self) -> MaximizeResult:
         n, dev = self.n, self.dev
         x = self.x
+        if self.use_mask:
+            self.plan.set_task_mask(self.mask.data_ptr())
+        try:
+            return self._run(n, dev, x)
+        finally:
+            if self.use_mask:
+                self.plan.set_task_mask(0)
+
+    def _run(self, n, dev, x):
         f, g, H, bad, bound = self.evaluate(x)
         delta = torch.full((n,), INITIAL_DELTA, dtype=torch.float64, device=dev)
         active = ~bad & (g.abs().max(dim=1).values >= G_TOL)       # initial g_tol check
@@ -202,6 +214,7 @@ class BatchMaximizer:
             s, m, interior = solve_tr_subproblem(g, H, delta)
             self._tick("tr_subproblem", t0)
             x_new = torch.where(active[:, None], x + s, x)
+            self.mask.copy_(active)          # inactive sources keep their last outputs; `accept` ignores them
             f_new, g_new, H_new, bad_new, _ = self.evaluate(x_new)
             fcalls += active.to(torch.int64)
             f_diff = f - f_new
@@ -230,6 +243,7 @@ class BatchMaximizer:
             dead = active & (delta < 1e-14)
             active = active & ~newly & ~dead
         self.x = x
+        self.mask.fill_(1)
         bound = ct.to_bound(x, self.lo, self.hi)                  # maximize! :239-240
         self.vp_all[self.aslot] = bound
         return MaximizeResult(bound.cpu().numpy(), (-f).cpu().numpy(), iters.cpu().numpy(), fcalls.cpu().numpy(),

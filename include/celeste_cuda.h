@@ -230,6 +230,12 @@ int celeste_elbo_plan_host(celeste_plan* p, const double* vp, int32_t mode,
  */
 int celeste_plan_enable_timing(celeste_plan* p, int32_t on);
 int celeste_plan_kernel_times(celeste_plan* p, float ms[3]);
+/*
+ * Optional per-task mask for the plan's evaluations: mask_dev is a DEVICE array of n_tasks bytes that the caller
+ * may rewrite between calls; tasks whose byte is 0 are skipped and their outputs left untouched (the batched
+ * Newton driver stops evaluating sources that have converged).  NULL removes the mask.
+ */
+int celeste_plan_set_task_mask(celeste_plan* p, const uint8_t* mask_dev);
 /* chunk size (pixels per pixel-kernel block) used by plans created afterwards; 0 restores the default */
 int celeste_set_chunk_pixels(int32_t chunk_pixels);
 

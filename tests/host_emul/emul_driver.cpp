@@ -149,7 +149,7 @@ extern "C" int emul_elbo_batch(int32_t N, const celeste_image* imgs, int32_t S_t
             chunk_ptr[tn + 1] = chunk_ptr[tn] + nchunk;
             for (int c = 0; c < nchunk; ++c)
                 blockmap.push_back(BlockHdr{tn, c, sub_slot[u], task_ptr[t], task_ptr[t + 1], (int)pidx, n, 0, sub_ptr[t], u,
-                                            sub_ptr[t + 1], 0});
+                                            sub_ptr[t + 1], t});
         }
     std::vector<int> tp(task_ptr, task_ptr + n_tasks + 1);
     std::vector<TaskHdr> taskmap;
@@ -157,7 +157,7 @@ extern "C" int emul_elbo_batch(int32_t N, const celeste_image* imgs, int32_t S_t
         for (int n0 = 0; n0 < N; n0 += TASK_NIMG) {
             const int t = sub_task[u];
             taskmap.push_back(TaskHdr{u * N, sub_slot[u], task_ptr[t], task_ptr[t + 1], 0, sub_ptr[t], u, sub_ptr[t + 1], n0,
-                                      std::min(N, n0 + TASK_NIMG), 0, 0});
+                                      std::min(N, n0 + TASK_NIMG), t, 0});
         }
     std::vector<int> tcp((size_t)n_subs * N + 1);
     for (size_t i = 0; i < tcp.size(); ++i) tcp[i] = (int)(i * TASK_WARPS);
@@ -189,6 +189,7 @@ extern "C" int emul_elbo_batch(int32_t N, const celeste_image* imgs, int32_t S_t
     pd.slotbr = slotbr.data();
     pd.partials = partials.data();
     pd.pair_partials = pair_partials.data();
+    pd.task_mask = nullptr;
     std::vector<long long> cnt(2 * (size_t)n_tasks);
     const int nb = (int)blockmap.size();
     if (mode == 0)

@@ -360,3 +360,34 @@ def test_elbo_with_kl_matches_autodiff_hessian_vector(cj):
     hv = r0.h @ np.ones(88)
     for i in range(20):
         assert abs(hv_fd[i] - hv[i]) <= 0.01 * abs(hv[i])
+
+
+def test_task_mask_skips_tasks_and_leaves_outputs(cj):
+    """celeste_plan_set_task_mask: masked tasks are not evaluated and their outputs stay untouched; unmasked tasks
+    are bit-identical to an unmasked run."""
+    import torch
+    images, patches, tasks = cases.get("small_field")
+    field = cj.DeviceField(images, patches)
+    plan = field.make_plan([t[0] for t in tasks], [t[1] for t in tasks])
+    vp = np.concatenate([t[2].ravel(order="F") for t in tasks])
+    n = plan.n_tasks
+    dev = torch.device("cuda")
+    vpd = torch.from_numpy(vp).to(dev)
+    for mode in (1, 2):
+        bufs = [torch.full((n,), -7.0, dtype=torch.float64, device=dev), torch.full((n * 44,), -7.0, dtype=torch.float64, device=dev),
+                torch.full((n * 44 * 44,), -7.0, dtype=torch.float64, device=dev), torch.zeros(2 * n, dtype=torch.int64, device=dev),
+                torch.zeros(n, dtype=torch.int32, device=dev)]
+        ref = plan.run_host(vp, mode)
+        mask = torch.ones(n, dtype=torch.uint8, device=dev)
+        mask[::3] = 0
+        plan.set_task_mask(mask.data_ptr())
+        plan.run_device(vpd.data_ptr(), mode, *[b.data_ptr() for b in bufs])
+        torch.cuda.synchronize()
+        plan.set_task_mask(0)
+        v, d = bufs[0].cpu().numpy(), bufs[1].cpu().numpy().reshape(n, 44)
+        keep = mask.cpu().numpy().astype(bool)
+        assert np.array_equal(v[keep], ref["v"][keep]) and np.array_equal(d[keep], ref["d"].reshape(n, 44)[keep])
+        assert (v[~keep] == -7.0).all() and (d[~keep] == -7.0).all()
+        if mode == 2:
+            h = bufs[2].cpu().numpy().reshape(n, -1)
+            assert np.array_equal(h[keep], ref["h"].reshape(n, -1)[keep]) and (h[~keep] == -7.0).all()
