@@ -58,8 +58,16 @@ EXPORTS = [
     "celeste_plan_create", "celeste_plan_destroy", "celeste_plan_launches",
     "celeste_elbo_plan_device", "celeste_elbo_plan_host", "celeste_field_destroy",
     "celeste_fp64_peak", "celeste_plan_enable_timing", "celeste_plan_kernel_times", "celeste_set_chunk_pixels",
-    "celeste_plan_create_multi", "celeste_tr_subproblem", "celeste_plan_set_task_mask",
+    "celeste_plan_create_multi", "celeste_tr_subproblem", "celeste_plan_set_task_mask", "celeste_newton_step",
 ]
+
+
+class celeste_newton_buffers(C.Structure):
+    """include/celeste_cuda.h: device pointers of one batched Newton trust-region solve."""
+    FIELDS = ["x", "f", "g", "H", "delta", "x_new", "m_pred", "interior", "active", "converged", "iters", "f_calls",
+              "lo", "hi", "v", "d", "h", "flags", "vp_all", "aslot", "prior"]
+    _fields_ = [(name, C.c_void_p) for name in FIELDS]
+
 
 _lib = None
 
@@ -100,7 +108,8 @@ def load():
     lib.celeste_plan_kernel_times.argtypes = [vp, C.POINTER(C.c_float * 3)]
     lib.celeste_set_chunk_pixels.argtypes = [i32]
     lib.celeste_plan_set_task_mask.argtypes = [vp, vp]
-    lib.celeste_tr_subproblem.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp, vp]
+    lib.celeste_tr_subproblem.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.celeste_newton_step.argtypes = [i32, i32, C.POINTER(celeste_newton_buffers), vp]
     _lib = lib
     return lib
 

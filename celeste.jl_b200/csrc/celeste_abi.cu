@@ -20,7 +20,7 @@
 
 #include "../../include/celeste_cuda.h"
 #include "celeste_kernels.cuh"
-#include "newton_kernels.cuh"
+#include "maximize_kernels.cuh"
 
 using namespace celeste;
 
@@ -796,7 +796,8 @@ int celeste_elbo_single(celeste_field* f, int32_t S, const int32_t* source_ids, 
 }
 
 int celeste_tr_subproblem(int32_t batch, int32_t n, const double* g_dev, const double* H_dev, const double* delta_dev,
-                          double* s_dev, double* m_dev, int32_t* interior_dev, void* cuda_stream) {
+                          const uint8_t* mask_dev, double* s_dev, double* m_dev, int32_t* interior_dev,
+                          void* cuda_stream) {
     if (batch < 0 || n < 1 || n > TR_MAXN - 1 || !g_dev || !H_dev || !delta_dev || !s_dev || !m_dev || !interior_dev) {
         set_detail("tr_subproblem: bad arguments (batch=%d n=%d, n must be 1..%d)", batch, n, TR_MAXN - 1);
         return CELESTE_ERR_BAD_ARG;
@@ -804,8 +805,50 @@ int celeste_tr_subproblem(int32_t batch, int32_t n, const double* g_dev, const d
     if (batch == 0) return CELESTE_OK;
     int st0 = ensure_device_ready();
     if (st0 != CELESTE_OK) return st0;
-    tr_subproblem_kernel<<<batch, TR_THREADS, 0, (cudaStream_t)cuda_stream>>>(n, g_dev, H_dev, delta_dev, s_dev, m_dev,
-                                                                              interior_dev);
+    tr_subproblem_kernel<<<batch, TR_THREADS, 0, (cudaStream_t)cuda_stream>>>(n, g_dev, H_dev, delta_dev, mask_dev, s_dev,
+                                                                              m_dev, interior_dev);
+    CUDA_TRY(cudaGetLastError());
+    return CELESTE_OK;
+}
+
+int celeste_newton_step(int32_t phase, int32_t batch, const celeste_newton_buffers* nb, void* cuda_stream) {
+    if (phase < 0 || phase > 2 || batch < 0 || !nb) {
+        set_detail("newton_step: bad arguments (phase=%d batch=%d)", phase, batch);
+        return CELESTE_ERR_BAD_ARG;
+    }
+    if (!nb->x || !nb->lo || !nb->hi || !nb->vp_all || !nb->aslot ||
+        (phase < 2 && (!nb->f || !nb->g || !nb->H || !nb->delta || !nb->x_new || !nb->m_pred || !nb->interior ||
+                       !nb->active || !nb->converged || !nb->iters || !nb->f_calls || !nb->v || !nb->d || !nb->h ||
+                       !nb->flags))) {
+        set_detail("newton_step: null buffer");
+        return CELESTE_ERR_BAD_ARG;
+    }
+    if (batch == 0) return CELESTE_OK;
+    int st0 = ensure_device_ready();
+    if (st0 != CELESTE_OK) return st0;
+    NewtonDev dev;
+    dev.x = nb->x;
+    dev.f = nb->f;
+    dev.g = nb->g;
+    dev.H = nb->H;
+    dev.delta = nb->delta;
+    dev.x_new = nb->x_new;
+    dev.m_pred = nb->m_pred;
+    dev.interior = nb->interior;
+    dev.active = nb->active;
+    dev.converged = nb->converged;
+    dev.iters = nb->iters;
+    dev.f_calls = nb->f_calls;
+    dev.lo = nb->lo;
+    dev.hi = nb->hi;
+    dev.v = nb->v;
+    dev.d = nb->d;
+    dev.h = nb->h;
+    dev.flags = nb->flags;
+    dev.vp_all = nb->vp_all;
+    dev.aslot = reinterpret_cast<const long long*>(nb->aslot);
+    dev.prior = nb->prior;
+    newton_step_kernel<<<batch, TR_THREADS, 0, (cudaStream_t)cuda_stream>>>(dev, phase);
     CUDA_TRY(cudaGetLastError());
     return CELESTE_OK;
 }

@@ -22,32 +22,38 @@ constexpr int TR_LD = TR_MAXN + 1;   // leading dimension (odd: conflict-free co
 constexpr int TR_THREADS = 128;
 constexpr int TR_MAX_SWEEPS = 14;
 
-__global__ void __launch_bounds__(TR_THREADS) tr_subproblem_kernel(int n, const double* __restrict__ g_all,
-                                                                   const double* __restrict__ H_all,
-                                                                   const double* __restrict__ delta_all,
-                                                                   double* __restrict__ s_all, double* __restrict__ m_all,
-                                                                   int* __restrict__ interior_all) {
-    __shared__ double A[TR_MAXN * TR_LD];
-    __shared__ double V[TR_MAXN * TR_LD];
-    __shared__ double rc[TR_MAXN / 2], rs[TR_MAXN / 2];
-    __shared__ int rp[TR_MAXN / 2], rq[TR_MAXN / 2];
-    __shared__ double ev[TR_MAXN], qg[TR_MAXN], coef[TR_MAXN], gsh[TR_MAXN];
-    __shared__ double red[TR_THREADS / 32];
+// shared-memory workspace of one subproblem (one block)
+struct TrShared {
+    double A[TR_MAXN * TR_LD];
+    double V[TR_MAXN * TR_LD];
+    double rc[TR_MAXN / 2], rs[TR_MAXN / 2];
+    int rp[TR_MAXN / 2], rq[TR_MAXN / 2];
+    double ev[TR_MAXN], qg[TR_MAXN], coef[TR_MAXN], gsh[TR_MAXN];
+    double red[TR_THREADS / 32];
+};
 
+// Solve the subproblem held in S (S.A: symmetric n x n matrix zero-padded to the even size np, S.gsh: gradient
+// zero-padded) with all TR_THREADS threads of the block; S.A is destroyed.  s_out (n doubles, shared or global),
+// *m_out and *interior_out are written by the block; the caller synchronises before reading them.
+__device__ inline void tr_solve_block(TrShared& S, int n, double delta, double* s_out, double* m_out, int* interior_out) {
+    double* A = S.A;
+    double* V = S.V;
+    double* rc = S.rc;
+    double* rs = S.rs;
+    int* rp = S.rp;
+    int* rq = S.rq;
+    double* ev = S.ev;
+    double* qg = S.qg;
+    double* coef = S.coef;
+    double* gsh = S.gsh;
+    double* red = S.red;
     const int tid = threadIdx.x;
-    const int b = blockIdx.x;
     const int np = (n + 1) & ~1;          // even padded size
     const int half = np / 2;
-    const double* H = H_all + (size_t)b * n * n;
-    const double* g = g_all + (size_t)b * n;
-
     for (int i = tid; i < np * np; i += TR_THREADS) {
         const int r = i / np, c = i % np;
-        // symmetrised load (the free-space Hessian is symmetric by construction; this guards round-off)
-        A[r * TR_LD + c] = (r < n && c < n) ? 0.5 * (H[(size_t)r * n + c] + H[(size_t)c * n + r]) : 0.0;
         V[r * TR_LD + c] = (r == c) ? 1.0 : 0.0;
     }
-    if (tid < np) gsh[tid] = tid < n ? g[tid] : 0.0;
     __syncthreads();
 
     // block-wide sum helper (fixed order)
@@ -110,27 +116,29 @@ __global__ void __launch_bounds__(TR_THREADS) tr_subproblem_kernel(int n, const 
                 rs[tid] = s;
             }
             __syncthreads();
-            // columns p, q of A and V:  (x_p, x_q) <- (c x_p - s x_q, s x_p + c x_q)
+            // A <- J' A J by 2 x 2 blocks: block (k', k) = rows (p', q') of pair k', columns (p, q) of pair k; each
+            // element is read and written once per round (column rotation k, then row rotation k', in registers)
+            for (int i = tid; i < half * half; i += TR_THREADS) {
+                const int k = i / half, kr = i - k * half;
+                const int p = rp[k], q = rq[k], pr = rp[kr], qr = rq[kr];
+                const double c = rc[k], s = rs[k], cr = rc[kr], sr = rs[kr];
+                const double a00 = A[pr * TR_LD + p], a01 = A[pr * TR_LD + q];
+                const double a10 = A[qr * TR_LD + p], a11 = A[qr * TR_LD + q];
+                const double b00 = c * a00 - s * a01, b01 = s * a00 + c * a01;     // columns
+                const double b10 = c * a10 - s * a11, b11 = s * a10 + c * a11;
+                A[pr * TR_LD + p] = cr * b00 - sr * b10;                             // rows
+                A[qr * TR_LD + p] = sr * b00 + cr * b10;
+                A[pr * TR_LD + q] = cr * b01 - sr * b11;
+                A[qr * TR_LD + q] = sr * b01 + cr * b11;
+            }
+            // V <- V J (columns only)
             for (int i = tid; i < half * np; i += TR_THREADS) {
                 const int k = i / np, r = i % np;
                 const int p = rp[k], q = rq[k];
                 const double c = rc[k], s = rs[k];
-                const double ap = A[r * TR_LD + p], aq = A[r * TR_LD + q];
-                A[r * TR_LD + p] = c * ap - s * aq;
-                A[r * TR_LD + q] = s * ap + c * aq;
                 const double vp = V[r * TR_LD + p], vq = V[r * TR_LD + q];
                 V[r * TR_LD + p] = c * vp - s * vq;
                 V[r * TR_LD + q] = s * vp + c * vq;
-            }
-            __syncthreads();
-            // rows p, q of A
-            for (int i = tid; i < half * np; i += TR_THREADS) {
-                const int k = i / np, cidx = i % np;
-                const int p = rp[k], q = rq[k];
-                const double c = rc[k], s = rs[k];
-                const double ap = A[p * TR_LD + cidx], aq = A[q * TR_LD + cidx];
-                A[p * TR_LD + cidx] = c * ap - s * aq;
-                A[q * TR_LD + cidx] = s * ap + c * aq;
             }
             __syncthreads();
         }
@@ -147,7 +155,6 @@ __global__ void __launch_bounds__(TR_THREADS) tr_subproblem_kernel(int n, const 
 
     // secular equation: warp 0, lanes hold entries j and j + 32
     if (tid < 32) {
-        const double delta = delta_all[b];
         const double d2 = delta * delta;
         const int j0 = tid, j1 = tid + 32;
         const bool h0 = j0 < n, h1 = j1 < n;
@@ -230,16 +237,40 @@ __global__ void __launch_bounds__(TR_THREADS) tr_subproblem_kernel(int n, const 
         if (h1) coef[j1] = c1;
         const double m = wsum((h0 ? q0 * c0 + 0.5 * e0 * c0 * c0 : 0.0) + (h1 ? q1 * c1 + 0.5 * e1 * c1 * c1 : 0.0));
         if (tid == 0) {
-            m_all[b] = m;
-            interior_all[b] = interior ? 1 : 0;
+            *m_out = m;
+            *interior_out = interior ? 1 : 0;
         }
     }
     __syncthreads();
     if (tid < n) {
         double t = 0.0;
         for (int j = 0; j < n; ++j) t += V[tid * TR_LD + j] * coef[j];
-        s_all[(size_t)b * n + tid] = t;
+        s_out[tid] = t;
     }
+}
+
+// mask (nullable): sources with mask[b] == 0 are skipped and their outputs left untouched
+__global__ void __launch_bounds__(TR_THREADS) tr_subproblem_kernel(int n, const double* __restrict__ g_all,
+                                                                   const double* __restrict__ H_all,
+                                                                   const double* __restrict__ delta_all,
+                                                                   const unsigned char* __restrict__ mask,
+                                                                   double* __restrict__ s_all, double* __restrict__ m_all,
+                                                                   int* __restrict__ interior_all) {
+    __shared__ TrShared S;
+    const int tid = threadIdx.x;
+    const int b = blockIdx.x;
+    if (mask && !mask[b]) return;
+    const int np = (n + 1) & ~1;
+    const double* H = H_all + (size_t)b * n * n;
+    const double* g = g_all + (size_t)b * n;
+    for (int i = tid; i < np * np; i += TR_THREADS) {
+        const int r = i / np, c = i % np;
+        // symmetrised load (the free-space Hessian is symmetric by construction; this guards round-off)
+        S.A[r * TR_LD + c] = (r < n && c < n) ? 0.5 * (H[(size_t)r * n + c] + H[(size_t)c * n + r]) : 0.0;
+    }
+    if (tid < np) S.gsh[tid] = tid < n ? g[tid] : 0.0;
+    __syncthreads();
+    tr_solve_block(S, n, delta_all[b], s_all + (size_t)b * n, m_all + b, interior_all + b);
 }
 
 }  // namespace celeste

@@ -7,10 +7,12 @@ one `evaluate!` (:161-172) = to_bound! -> elbo (likelihood - KL) -> propagate_de
 
 The reference optimises one source per thread, one ELBO evaluation at a time (~10 us of GPU work each).
 Here ALL sources of a batch step in lock-step: one iteration = one CUDA plan evaluation (value + gradient +
-Hessian for every source) + batched 41 x 41 eigen-decompositions for the trust-region
-subproblem (the library's tr_subproblem_kernel on a GPU; this module's torch code is the same algorithm
-for CPU tensors and the tests); sources that have converged simply stop moving.  Nothing leaves the device
-between iterations except the "anyone still active?" flag.
+Hessian for every source) + ONE newton_step_kernel launch (csrc/maximize_kernels.cuh: -KL, the 44 -> 41
+propagate_derivatives!, the trust-region update, the next 41 x 41 subproblem and to_bound! of the next
+candidate, one block per source); converged sources are masked out of both.  Nothing leaves the device
+between iterations except the "anyone still active?" flag.  This module's torch code (kl.py,
+constraint_transforms.py, solve_tr_subproblem, BatchMaximizer._run) is the same algorithm for CPU tensors:
+it is what the tests compare the kernels against and what runs when a test injects a CPU `runner`.
 
 Optim.jl is an un-vendored dependency (REQUIRE:13, >= 0.7.4): its NewtonTrustRegion is restated from the
 published algorithm (Nocedal & Wright, Alg. 4.1 for the radius update and the exact subproblem solution by
@@ -33,9 +35,10 @@ X_TOL, F_TOL, G_TOL, MAX_ITERS = 1e-7, 1e-6, 1e-8, 50
 INITIAL_DELTA, DELTA_HAT = 1.0, 1e9
 
 
-def solve_tr_subproblem(g: torch.Tensor, H: torch.Tensor, delta: torch.Tensor):
+def solve_tr_subproblem(g: torch.Tensor, H: torch.Tensor, delta: torch.Tensor, mask: Optional[torch.Tensor] = None):
     """min_s g's + 1/2 s'Hs  s.t. |s| <= delta, batched (B x n, B x n x n, B).
-    Returns (s, m = predicted change, interior flag)."""
+    Returns (s, m = predicted change, interior flag).  `mask` (uint8, CUDA only): sources with 0 are skipped
+    and get s = 0, m = 0."""
     B, n = g.shape
     dev_in = g.device
     if dev_in.type == "cuda":
@@ -44,11 +47,12 @@ def solve_tr_subproblem(g: torch.Tensor, H: torch.Tensor, delta: torch.Tensor):
         # (csrc/newton_kernels.cuh: one block per source, Jacobi + secular equation).
         from . import _lib
         g, H, delta = g.contiguous(), H.contiguous(), delta.contiguous()
-        s = torch.empty_like(g)
-        m = torch.empty_like(delta)
-        interior = torch.empty(B, dtype=torch.int32, device=dev_in)
-        _lib.check(_lib.load().celeste_tr_subproblem(B, n, g.data_ptr(), H.data_ptr(), delta.data_ptr(), s.data_ptr(),
-                                                     m.data_ptr(), interior.data_ptr(),
+        s = torch.zeros_like(g)
+        m = torch.zeros_like(delta)
+        interior = torch.zeros(B, dtype=torch.int32, device=dev_in)
+        _lib.check(_lib.load().celeste_tr_subproblem(B, n, g.data_ptr(), H.data_ptr(), delta.data_ptr(),
+                                                     mask.data_ptr() if mask is not None else None,
+                                                     s.data_ptr(), m.data_ptr(), interior.data_ptr(),
                                                      torch.cuda.current_stream().cuda_stream))
         return s, m, interior.bool()
     ev, Q = torch.linalg.eigh(H)                       # ascending
@@ -114,11 +118,15 @@ class BatchMaximizer:
     as inside one `maximize!` call of the reference)."""
 
     def __init__(self, plan, vp_flat: np.ndarray, include_kl: bool = True, device: Optional[str] = None,
-                 loc_width: float = 1e-4, max_iters: int = MAX_ITERS, runner=None):
+                 loc_width: float = 1e-4, max_iters: int = MAX_ITERS, runner=None, stepper=None,
+                 fused: Optional[bool] = None):
         """`runner(self)` evaluates the plan's tasks at self.vp_all and fills self.v/d/h/flags; the default
-        launches the CUDA plan on the current stream.  (Tests inject a CPU checker here.)"""
+        launches the CUDA plan on the current stream.  (Tests inject a CPU checker here.)
+        `stepper(phase, n, buffers)` runs newton_step_kernel; the default is the library on the current stream
+        (tests inject the host-emulated kernel).  `fused` = use newton_step_kernel (default on CUDA)."""
         self.plan = plan
         self.runner = runner
+        self.stepper = stepper
         self.dev = torch.device(device or "cuda")
         self.n = plan.n_tasks
         self.max_iters = max_iters
@@ -145,6 +153,9 @@ class BatchMaximizer:
         self.mask = torch.ones(n, dtype=torch.uint8, device=self.dev)
         self.use_mask = runner is None and hasattr(plan, "set_task_mask")
         self.profile = None        # set to {} to collect wall-clock per phase (synchronising; diagnostics only)
+        if fused is None:
+            fused = stepper is not None or (self.dev.type == "cuda" and runner is None)
+        self.fused = fused
 
     def _tick(self, name, t0):
         if self.profile is not None:
@@ -192,10 +203,64 @@ class BatchMaximizer:
         if self.use_mask:
             self.plan.set_task_mask(self.mask.data_ptr())
         try:
-            return self._run(n, dev, x)
+            return self._run_fused() if self.fused else self._run(n, dev, x)
         finally:
             if self.use_mask:
                 self.plan.set_task_mask(0)
+
+    def _step(self, phase):
+        if self.stepper is not None:
+            self.stepper(phase, self.n, self._buffers)
+            return
+        from . import _lib
+        _lib.check(_lib.load().celeste_newton_step(phase, self.n, self._buffers, torch.cuda.current_stream().cuda_stream))
+
+    def _evaluate_plan(self):
+        import time
+        t0 = time.perf_counter() if self.profile is not None else 0.0
+        if self.runner is not None:
+            self.runner(self)
+        else:
+            self._run_plan(torch.cuda.current_stream())
+        self.f_calls += 1
+        self._tick("elbo_plan", t0)
+
+    def _run_fused(self) -> MaximizeResult:
+        """The device-resident loop: per iteration one plan evaluation + one newton_step_kernel launch."""
+        import time
+        from . import _lib
+        n, dev, f64 = self.n, self.dev, torch.float64
+        z = lambda *shape, dtype=f64: torch.zeros(shape, dtype=dtype, device=dev)
+        st = dict(x=self.x.contiguous(), f=z(n), g=z(n, ct.N_FREE), H=z(n, ct.N_FREE, ct.N_FREE), delta=z(n),
+                  x_new=z(n, ct.N_FREE), m_pred=z(n), interior=z(n, dtype=torch.int32), active=self.mask,
+                  converged=z(n, dtype=torch.uint8), iters=z(n, dtype=torch.int32), f_calls=z(n, dtype=torch.int32),
+                  lo=self.lo.contiguous(), hi=self.hi.contiguous(), v=self.v, d=self.d, h=self.h, flags=self.flags,
+                  vp_all=self.vp_all, aslot=self.aslot.contiguous(),
+                  prior=self.kl.packed() if self.include_kl else None)
+        self._st = st                                          # keeps the tensors alive while the kernels run
+        self._buffers = _lib.celeste_newton_buffers(**{k: (t.data_ptr() if t is not None else None) for k, t in st.items()})
+        self.mask.fill_(1)
+        self._step(2)                                          # vp_all[aslot] <- to_bound(x)
+        self._evaluate_plan()
+        t0 = time.perf_counter() if self.profile is not None else 0.0
+        self._step(0)
+        self._tick("newton_step", t0)
+        steps = 0
+        for _ in range(self.max_iters):
+            if not bool(self.mask.any()):
+                break
+            steps += 1
+            self._evaluate_plan()
+            t0 = time.perf_counter() if self.profile is not None else 0.0
+            self._step(1)
+            self._tick("newton_step", t0)
+        self._step(2)                                          # maximize! :239-240
+        self.x = st["x"]
+        bound = self.vp_all[self.aslot]
+        res = MaximizeResult(bound.cpu().numpy(), (-st["f"]).cpu().numpy(), st["iters"].cpu().numpy().astype(np.int64),
+                             st["f_calls"].cpu().numpy().astype(np.int64), st["converged"].cpu().numpy().astype(bool), steps)
+        self.mask.fill_(1)
+        return res
 
     def _run(self, n, dev, x):
         f, g, H, bad, bound = self.evaluate(x)
@@ -211,10 +276,10 @@ class BatchMaximizer:
             steps += 1
             import time
             t0 = time.perf_counter() if self.profile is not None else 0.0
-            s, m, interior = solve_tr_subproblem(g, H, delta)
+            self.mask.copy_(active)          # inactive sources keep their last outputs; `accept` ignores them
+            s, m, interior = solve_tr_subproblem(g, H, delta, self.mask if dev.type == "cuda" else None)
             self._tick("tr_subproblem", t0)
             x_new = torch.where(active[:, None], x + s, x)
-            self.mask.copy_(active)          # inactive sources keep their last outputs; `accept` ignores them
             f_new, g_new, H_new, bad_new, _ = self.evaluate(x_new)
             fcalls += active.to(torch.int64)
             f_diff = f - f_new

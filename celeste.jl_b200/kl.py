@@ -36,6 +36,15 @@ class KLTerm:
         self.device = device
         self._idx = {}
 
+    def packed(self) -> torch.Tensor:
+        """The prior as the flat 360-double array newton_step_kernel reads (csrc/maximize_kernels.cuh, PR_*):
+        log pi_a[2], flux_mean[2], flux_var[2], log pi_k[2][8], mu[2][8][4], precision[2][8][4][4], logdet[2][8],
+        radius mean, radius var."""
+        rad = torch.tensor([self.rad_mean, self.rad_var], dtype=torch.float64, device=self.device)
+        return torch.cat([self.log_is_star.reshape(-1), self.flux_mean.reshape(-1), self.flux_var.reshape(-1),
+                          self.log_k.reshape(-1), self.mu2.reshape(-1), self.prec.reshape(-1), self.logdet.reshape(-1),
+                          rad]).contiguous()
+
     def __call__(self, vp: torch.Tensor, order: int = 2):
         """vp: B x 44.  Returns (v [B], g [B x 44] or None, H [B x 44 x 44] or None) of subtract_kl.
 

@@ -248,10 +248,53 @@ void celeste_field_destroy(celeste_field* f);
  * exactly (Jacobi eigen-decomposition + secular equation, hard case included).  All pointers are DEVICE
  * pointers; g: batch x n, H: batch x n x n (symmetric), delta: batch; outputs s: batch x n, m: batch
  * (predicted change of the objective), interior: batch (1 when the unconstrained Newton step was taken).
+ * mask_dev (nullable): batch bytes; sources with a zero byte are skipped and their outputs left untouched.
  * n <= 47 (41 free parameters in Celeste).  Asynchronous on `cuda_stream`.
  */
 int celeste_tr_subproblem(int32_t batch, int32_t n, const double* g_dev, const double* H_dev, const double* delta_dev,
-                          double* s_dev, double* m_dev, int32_t* interior_dev, void* cuda_stream);
+                          const uint8_t* mask_dev, double* s_dev, double* m_dev, int32_t* interior_dev,
+                          void* cuda_stream);
+
+/*
+ * Rows f.1 + f.2 + f.3 fused: one lock-step iteration of ElboMaximize.maximize! (src/deterministic_vi/
+ * ElboMaximize.jl:228-242; evaluate! :161-172; Optim.NewtonTrustRegion options :95-108) for `batch` sources at
+ * once, everything that is not the likelihood itself:
+ *   -KL (elbo_kl.jl:143-154) added to the plan's 44-space value / gradient / Hessian, propagate_derivatives!
+ *   (ConstraintTransforms.jl:373-396) to the 41 free coordinates, the trust-region accept / radius / convergence
+ *   update, and -- for sources still iterating -- the next subproblem solve, the candidate x + s and to_bound!
+ *   (:189-196) of the candidate written into vp_all, ready for the next plan evaluation.
+ * All pointers are DEVICE pointers owned by the caller (sizes in units of `batch` = B):
+ */
+typedef struct celeste_newton_buffers {
+    double* x;            /* B x 41  accepted iterate (free coordinates)                           in/out */
+    double* f;            /* B       objective -ELBO at x                                          in/out */
+    double* g;            /* B x 41  its gradient                                                  in/out */
+    double* H;            /* B x 41 x 41  its Hessian                                              in/out */
+    double* delta;        /* B       trust-region radius                                           in/out */
+    double* x_new;        /* B x 41  candidate under evaluation                                    in/out */
+    double* m_pred;       /* B       change the subproblem predicted for the candidate             in/out */
+    int32_t* interior;    /* B       1 when that candidate was the unconstrained Newton step       in/out */
+    uint8_t* active;      /* B       1 while the source iterates; usable as celeste_plan_set_task_mask    */
+    uint8_t* converged;   /* B       1 once an x / f / g tolerance was met                         out    */
+    int32_t* iters;       /* B       iterations taken                                              out    */
+    int32_t* f_calls;     /* B       ELBO evaluations consumed                                     out    */
+    const double* lo;     /* B x 26  box lower bounds (ElboMaximize.jl:70-85)                             */
+    const double* hi;     /* B x 26  box upper bounds                                                     */
+    const double* v;      /* B       plan outputs at the candidate (celeste_elbo_plan_device, mode 2)     */
+    const double* d;      /* B x 44                                                                       */
+    const double* h;      /* B x 44 x 44                                                                  */
+    const int32_t* flags; /* B                                                                            */
+    double* vp_all;       /* n_slots x 44  the plan's bound parameters; row aslot[b] belongs to source b  */
+    const int64_t* aslot; /* B                                                                            */
+    const double* prior;  /* 360 doubles (kl.KLTerm.packed layout, see maximize_kernels.cuh) or NULL: no KL */
+} celeste_newton_buffers;
+/*
+ * phase 0: the plan was evaluated at to_bound(x): initialise f, g, H, delta = 1, active, and emit the first
+ * candidate.  phase 1: the plan was evaluated at the candidate: accept / reject, update, emit the next
+ * candidate for sources still active.  phase 2: write to_bound(x) of every source into vp_all (maximize! :239).
+ * Asynchronous on `cuda_stream`.
+ */
+int celeste_newton_step(int32_t phase, int32_t batch, const celeste_newton_buffers* buffers, void* cuda_stream);
 
 /*
  * Measured FP64 FMA peak of the current device (a register-resident DFMA chain,

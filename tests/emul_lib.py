@@ -22,6 +22,7 @@ def load():
         vp, i32 = C.c_void_p, C.c_int32
         _lib.emul_elbo_batch.argtypes = [i32, vp, i32, vp, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, i32]
         _lib.emul_tr_subproblem.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp]
+        _lib.emul_newton_step.argtypes = [i32, i32, vp]
     return _lib
 
 
@@ -63,3 +64,9 @@ def tr_subproblem(g, H, delta):
                                    m.ctypes.data, interior.ctypes.data)
     assert st == 0
     return s, m, interior.astype(bool)
+
+
+def newton_stepper(phase, n, buffers):
+    """newton_step_kernel under emulation, as the `stepper` hook of elbo_maximize.BatchMaximizer (CPU tensors)."""
+    st = load().emul_newton_step(phase, n, C.addressof(buffers))
+    assert st == 0

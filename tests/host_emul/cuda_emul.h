@@ -29,6 +29,8 @@
 struct uint3_emul { unsigned x, y, z; };
 struct int2 { int x, y; };
 inline int2 make_int2(int x, int y) { return int2{x, y}; }
+struct int4 { int x, y, z, w; };
+inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
 
 namespace cuda_emul {
 struct BlockCtx {

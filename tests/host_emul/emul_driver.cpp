@@ -6,7 +6,7 @@
 
 #include "../../include/celeste_cuda.h"
 #include "../../celeste.jl_b200/csrc/celeste_kernels.cuh"
-#include "../../celeste.jl_b200/csrc/newton_kernels.cuh"
+#include "../../celeste.jl_b200/csrc/maximize_kernels.cuh"
 
 using namespace celeste;
 
@@ -204,6 +204,35 @@ extern "C" int emul_elbo_batch(int32_t N, const celeste_image* imgs, int32_t S_t
 
 extern "C" int emul_tr_subproblem(int32_t batch, int32_t n, const double* g, const double* H, const double* delta,
                                   double* s, double* m, int32_t* interior) {
-    cuda_emul::launch(tr_subproblem_kernel, batch, TR_THREADS, 0, n, g, H, delta, s, m, interior);
+    cuda_emul::launch(tr_subproblem_kernel, batch, TR_THREADS, 0, n, g, H, delta, (const unsigned char*)nullptr, s, m,
+                      interior);
+    return 0;
+}
+
+// newton_step_kernel under emulation; the buffers are host arrays
+extern "C" int emul_newton_step(int32_t phase, int32_t batch, const celeste_newton_buffers* nb) {
+    NewtonDev dev;
+    dev.x = nb->x;
+    dev.f = nb->f;
+    dev.g = nb->g;
+    dev.H = nb->H;
+    dev.delta = nb->delta;
+    dev.x_new = nb->x_new;
+    dev.m_pred = nb->m_pred;
+    dev.interior = nb->interior;
+    dev.active = nb->active;
+    dev.converged = nb->converged;
+    dev.iters = nb->iters;
+    dev.f_calls = nb->f_calls;
+    dev.lo = nb->lo;
+    dev.hi = nb->hi;
+    dev.v = nb->v;
+    dev.d = nb->d;
+    dev.h = nb->h;
+    dev.flags = nb->flags;
+    dev.vp_all = nb->vp_all;
+    dev.aslot = reinterpret_cast<const long long*>(nb->aslot);
+    dev.prior = nb->prior;
+    cuda_emul::launch(newton_step_kernel, batch, TR_THREADS, 0, dev, phase);
     return 0;
 }

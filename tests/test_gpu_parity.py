@@ -267,6 +267,16 @@ def test_batch_maximizer_cuda_matches_checker(cj):
     assert np.array_equal(gpu.iterations, cpu.iterations) and np.array_equal(gpu.converged, cpu.converged)
     assert np.allclose(gpu.value, cpu.value, rtol=1e-8)
     assert np.allclose(gpu.vp, cpu.vp, rtol=1e-6, atol=1e-8)
+    # the default on CUDA is the device-resident loop (newton_step_kernel); the torch driver over the same plan
+    # (tr_subproblem_kernel + torch KL / transforms) must walk the same iterates
+    bm = em.BatchMaximizer(plan, vp, include_kl=True, max_iters=12)
+    assert bm.fused
+    unfused = em.BatchMaximizer(plan, vp, include_kl=True, max_iters=12, fused=False).run()
+    assert np.array_equal(gpu.iterations, unfused.iterations) and np.array_equal(gpu.f_calls, unfused.f_calls)
+    assert np.allclose(gpu.value, unfused.value, rtol=1e-9) and np.allclose(gpu.vp, unfused.vp, rtol=1e-6, atol=1e-8)
+    nokl = em.BatchMaximizer(plan, vp, include_kl=False, max_iters=6).run()
+    nokl_ref = em.BatchMaximizer(plan, vp, include_kl=False, max_iters=6, fused=False).run()
+    assert np.allclose(nokl.value, nokl_ref.value, rtol=1e-9) and np.array_equal(nokl.iterations, nokl_ref.iterations)
 
 
 def test_one_node_single_infer_improves_elbo(cj):

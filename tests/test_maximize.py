@@ -258,3 +258,130 @@ def test_single_source_optimization_leaves_neighbours_alone():
     after = bm.vp_all.numpy()
     assert not np.allclose(after[0], vp[1])
     assert np.array_equal(after[1], vp[0]) and np.array_equal(after[2], vp[2])
+
+
+def _newton_buffers(n, x, lo, hi, v, d, h, flags, vp_all, aslot, prior):
+    """numpy-backed celeste_newton_buffers + the dict that keeps the arrays alive."""
+    from celeste_jl_b200 import _lib
+    st = dict(x=x, f=np.zeros(n), g=np.zeros((n, 41)), H=np.zeros((n, 41, 41)), delta=np.zeros(n),
+              x_new=np.zeros((n, 41)), m_pred=np.zeros(n), interior=np.zeros(n, dtype=np.int32),
+              active=np.ones(n, dtype=np.uint8), converged=np.zeros(n, dtype=np.uint8), iters=np.zeros(n, dtype=np.int32),
+              f_calls=np.zeros(n, dtype=np.int32), lo=lo, hi=hi, v=v, d=d, h=h, flags=flags, vp_all=vp_all, aslot=aslot,
+              prior=prior)
+    for k, a in st.items():
+        assert a is None or a.flags["C_CONTIGUOUS"], k
+    buf = _lib.celeste_newton_buffers(**{k: (a.ctypes.data if a is not None else None) for k, a in st.items()})
+    return buf, st
+
+
+@pytest.mark.parametrize("include_kl", [True, False])
+def test_newton_step_kernel_under_emulation(include_kl):
+    """csrc/maximize_kernels.cuh, one step at a time, against the torch restatements it fuses: phase 0 =
+    -KL + propagate_derivatives! + first subproblem + to_bound! of the candidate; phase 1 = the trust-region
+    update (accepted and rejected steps, radius, convergence flags) + the next candidate."""
+    import emul_lib
+    rng = np.random.default_rng(11)
+    n = 6
+    vp = torch.tensor(_sample_vp(n, seed=12))
+    lo, hi = ct.box_bounds(vp, 1e-4)
+    x = ct.to_free(ct.enforce(vp, lo, hi), lo, hi) + torch.tensor(rng.normal(0, 0.2, (n, 41)))
+    kl = KLTerm("cpu")
+
+    def evaluation(seed, pd_shift):
+        r = np.random.default_rng(seed)
+        A = r.normal(size=(n, 44, 44))
+        h = -(np.einsum("bij,bkj->bik", A, A) + pd_shift * np.eye(44))      # ELBO Hessians are mostly negative definite
+        return r.normal(size=n) * 100, r.normal(size=(n, 44)), h
+
+    def torch_eval(xx, v, d, h):
+        b = ct.to_bound(xx, lo, hi)
+        tv, tg, tH = torch.tensor(v), torch.tensor(d), torch.tensor(h)
+        if include_kl:
+            kv, kg, kH = kl(b, order=2)
+            tv, tg, tH = tv + kv, tg + kg, tH + kH
+        gf, Hf = ct.propagate_derivatives(xx, lo, hi, tg, tH)
+        return -tv, -gf, -Hf, b
+
+    v, d, h = evaluation(1, 5.0)
+    flags = np.zeros(n, dtype=np.int32)
+    flags[-1] = 1                                                            # a non-finite evaluation: never active
+    vp_all = np.zeros((2 * n, 44))
+    aslot = np.arange(n, dtype=np.int64) * 2
+    xs = x.numpy().copy()
+    prior = kl.packed().numpy() if include_kl else None
+    buf, st = _newton_buffers(n, xs, lo.numpy().copy(), hi.numpy().copy(), v, d, h.copy(), flags, vp_all, aslot, prior)
+    step = lambda ph: emul_lib.newton_stepper(ph, n, buf)
+
+    step(2)
+    assert np.allclose(vp_all[aslot], ct.to_bound(x, lo, hi).numpy(), rtol=1e-14, atol=1e-300)
+    assert not vp_all[1::2].any()
+    # ---- phase 0
+    step(0)
+    f0, g0, H0, _ = torch_eval(x, v, d, h)
+    assert np.allclose(st["f"], f0.numpy(), rtol=1e-13)
+    assert np.allclose(st["g"], g0.numpy(), rtol=1e-10, atol=1e-12 * np.abs(g0.numpy()).max())
+    assert np.allclose(st["H"], H0.numpy(), rtol=1e-9, atol=1e-11 * np.abs(H0.numpy()).max())
+    assert np.array_equal(st["H"], st["H"].transpose(0, 2, 1))
+    assert np.array_equal(st["active"], [1] * (n - 1) + [0]) and not st["converged"].any()
+    assert np.array_equal(st["delta"], np.ones(n)) and np.array_equal(st["f_calls"], [1] * n)
+    delta = torch.ones(n, dtype=torch.float64)
+    s, m, interior = em.solve_tr_subproblem(g0, H0, delta)
+    ok = slice(0, n - 1)
+    assert np.allclose(st["x_new"][ok], (x + s).numpy()[ok], rtol=1e-7, atol=1e-9)
+    assert np.allclose(st["m_pred"][ok], m.numpy()[ok], rtol=1e-8)
+    assert np.array_equal(st["interior"][ok].astype(bool), interior.numpy()[ok])
+    assert np.allclose(vp_all[aslot][ok], ct.to_bound(torch.tensor(st["x_new"]), lo, hi).numpy()[ok], rtol=1e-13)
+    # ---- phase 1: craft evaluations so that some steps are accepted and some rejected
+    x_new = torch.tensor(st["x_new"].copy())
+    v1, d1, h1 = evaluation(2, 5.0)
+    m_pred = st["m_pred"].copy()
+    # source 0: rho ~ 1 (accept, radius grows unless interior); source 1: worse value (reject, radius shrinks);
+    # source 2: tiny improvement relative to the prediction (accept needs rho > 0.1: reject)
+    f_target = np.array([f0[0] + m_pred[0], f0[1] + 1.0, f0[2] + 0.05 * m_pred[2], f0[3] + 0.5 * m_pred[3],
+                         f0[4] + 0.2 * m_pred[4], 0.0])
+    klv = kl(ct.to_bound(x_new, lo, hi), order=0)[0].numpy() if include_kl else np.zeros(n)
+    v1[:] = -f_target - klv
+    st["v"][:] = v1
+    st["d"][:] = d1
+    st["h"][:] = h1
+    x_before, f_before, H_before = st["x"].copy(), st["f"].copy(), st["H"].copy()
+    step(1)
+    f1, g1, H1, _ = torch_eval(x_new, v1, d1, h1)
+    rho = (f_before[:n - 1] - f1.numpy()[:n - 1]) / (-m_pred[:n - 1])
+    for b in range(n - 1):
+        accept = rho[b] > em.ETA
+        if accept:
+            assert np.allclose(st["x"][b], x_new[b].numpy()) and st["f"][b] == pytest.approx(float(f1[b]), rel=1e-13)
+            assert np.allclose(st["H"][b], H1[b].numpy(), rtol=1e-9, atol=1e-11 * np.abs(H1[b].numpy()).max())
+        else:
+            assert np.array_equal(st["x"][b], x_before[b]) and st["f"][b] == f_before[b]
+            assert np.array_equal(st["H"][b], H_before[b])
+        grows = rho[b] > em.RHO_UPPER and not bool(interior[b])
+        assert st["delta"][b] == (0.25 if rho[b] < em.RHO_LOWER else (2.0 if grows else 1.0))
+        assert st["iters"][b] == 1 and st["f_calls"][b] == 2
+    assert (rho[:5] > em.ETA).tolist() == [True, False, False, True, True]
+    assert st["iters"][-1] == 0 and st["active"][-1] == 0
+    # the next candidate comes from the ACCEPTED state with the updated radius
+    s2, m2, int2 = em.solve_tr_subproblem(torch.tensor(st["g"]), torch.tensor(st["H"]), torch.tensor(st["delta"]))
+    act = st["active"].astype(bool)
+    assert act[:5].all()
+    assert np.allclose(st["x_new"][act], (torch.tensor(st["x"]) + s2).numpy()[act], rtol=1e-7, atol=1e-9)
+    assert np.allclose(st["m_pred"][act], m2.numpy()[act], rtol=1e-8)
+
+
+def test_fused_maximize_under_emulation_matches_torch_driver():
+    """The device-resident loop (newton_step_kernel, emulated) and the torch lock-step driver walk the same
+    iterates: same stopping behaviour, same optimum (test/test_optimization.jl:61-67 data)."""
+    import emul_lib
+    images, patches, vp, _ = synthetic.gen_sample_galaxy_dataset()
+    pl = PlanLike([[1]], [[1]])
+    kw = dict(include_kl=True, device="cpu", loc_width=1.0, max_iters=12)
+    ref = em.BatchMaximizer(pl, np.concatenate(vp), runner=OracleRunner(images, patches, pl), **kw).run()
+    bm = em.BatchMaximizer(pl, np.concatenate(vp), runner=OracleRunner(images, patches, pl),
+                           stepper=emul_lib.newton_stepper, **kw)
+    assert bm.fused
+    res = bm.run()
+    assert res.total_steps == ref.total_steps and np.array_equal(res.iterations, ref.iterations)
+    assert np.array_equal(res.f_calls, ref.f_calls) and np.array_equal(res.converged, ref.converged)
+    assert res.value[0] == pytest.approx(ref.value[0], rel=1e-9)
+    assert np.allclose(res.vp, ref.vp, rtol=1e-6, atol=1e-8)

@@ -17,11 +17,11 @@ for r in rows:
     vps.append(dvi.generic_init_source(ds.catalog[r[0] - 1].pos))
     vps += [dvi.catalog_init_source(ds.catalog[k - 1]) for k in r[1:]]
 vp = np.concatenate(vps)
-for prof in (None, {}):
-    bm = em.BatchMaximizer(plan, vp, include_kl=True)
+for prof, fused in ((None, True), ({}, True), (None, False), ({}, False)):
+    bm = em.BatchMaximizer(plan, vp, include_kl=True, fused=fused)
     bm.profile = prof
     torch.cuda.synchronize(); t0 = time.perf_counter()
     res = bm.run()
     torch.cuda.synchronize(); dt = time.perf_counter() - t0
     print(f"n={n} total {dt:.3f}s steps {res.total_steps} mean iters {res.iterations.mean():.1f} converged {res.converged.mean():.3f} "
-          f"src/s {n/dt:.1f}", prof)
+          f"src/s {n/dt:.1f} fused={fused}", prof)
