@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=1000, help="tasks per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hessian", action="store_true")
+    ap.add_argument("--no-render", action="store_true", help="skip the full-image expectation render leg (row f.4)")
     ap.add_argument("--no-maximize", action="store_true", help="skip the config-5 leg (full Newton loop on field 0)")
     return ap.parse_args()
 
@@ -376,6 +377,13 @@ def main():
                 if t and t.get("sources") == int(total_sources):
                     r["traffic"] = t["dram_bytes_per_launch"] / world
                     r["traffic_source"] = t
+                    if "executed_flop_per_launch" in t:
+                        # what the kernel EXECUTES (SASS DFMA x 2 + DMUL + DADD from the ncu capture) at the live
+                        # kernel time: the reformulation needs fewer flops than SURVEY 8d's contract count, so
+                        # `frac` (algorithmic) can exceed this -- and, for the Hessian, 1
+                        ex = t["executed_flop_per_launch"] / (m["pix_ms"] * 1e-3) / 1e12
+                        r["executed"] = {"tflops": ex, "frac_of_dfma_peak": ex / (peak * world),
+                                         "fp64_pipe_active_pct_ncu": t.get("fp64_pipe_active_pct")}
             except Exception:
                 pass
         return r
@@ -407,6 +415,22 @@ def main():
                         "what": "one_node_single_infer semantics on the whole stripe: generic init, KL included, Newton "
                                 "trust region x_tol 1e-7 / f_tol 1e-6 / g_tol 1e-8 / 50 iterations, converged sources masked"}
 
+    # row f.4: the value-only full-image render (fill_celeste_expectation!) of field 0, through the C ABI with host
+    # buffers (122 MB of float64 expectation images come back per call); rank 0 only, informational
+    render_leg = None
+    if rank == 0 and not args.no_render:
+        ds0 = stripe[0]
+        vp0 = np.stack(ds0.vp, axis=1)
+        rows0 = np.arange(1, vp0.shape[1] + 1)
+        fields[0].render_expectation(rows0[:8], vp0[:, :8])                          # warm-up
+        t0 = time.perf_counter()
+        imgs = fields[0].render_expectation(rows0, vp0)
+        dt = time.perf_counter() - t0
+        npix = sum(int(a.size) for a in imgs)
+        render_leg = {"seconds_e2e": dt, "sources": int(vp0.shape[1]), "image_pixels": npix,
+                      "megapixels_per_s_e2e": npix / dt / 1e6,
+                      "what": "celeste_render_expectation: E_G - sky on every pixel of the 5 images of field 0, host buffers"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -430,6 +454,8 @@ def main():
                            "e2e": e2e(hess, 2), "roofline": roofline(hess, 2)}
     if not args.no_maximize:
         line["maximize"] = maximize_leg
+    if render_leg is not None:
+        line["render"] = render_leg
     if world == 1 and not args.no_cpu_baseline:
         cb = cpu_leg(stripe[0], args.cpu_sample, 1, 3, 1)
         line["cpu_baseline"] = cb

@@ -13,7 +13,8 @@ from . import _lib, model, flatten, deterministic_vi, parallel_run, constraint_t
 from .model import (AffineWCS, CatalogEntry, Image, ImagePatch, PsfComponent, ids, get_sky_patches,  # noqa: F401
                     find_neighbors, find_all_neighbors)
 from .deterministic_vi import (DeviceField, ElboArgs, ElboIntermediateVariables, Plan, SensitiveFloat,  # noqa: F401
-                               catalog_init_source, elbo, elbo_likelihood, generic_init_source, init_sources)
+                               catalog_init_source, elbo, elbo_likelihood, fill_celeste_expectation,
+                               generic_init_source, init_sources)
 
 __all__ = ["model", "deterministic_vi", "flatten", "ElboArgs", "elbo", "elbo_likelihood", "SensitiveFloat",
            "DeviceField", "Plan", "Image", "ImagePatch", "PsfComponent", "CatalogEntry", "ids"]

@@ -59,6 +59,7 @@ EXPORTS = [
     "celeste_elbo_plan_device", "celeste_elbo_plan_host", "celeste_field_destroy",
     "celeste_fp64_peak", "celeste_plan_enable_timing", "celeste_plan_kernel_times", "celeste_set_chunk_pixels",
     "celeste_plan_create_multi", "celeste_tr_subproblem", "celeste_plan_set_task_mask", "celeste_newton_step",
+    "celeste_render_expectation",
 ]
 
 
@@ -109,6 +110,7 @@ def load():
     lib.celeste_set_chunk_pixels.argtypes = [i32]
     lib.celeste_plan_set_task_mask.argtypes = [vp, vp]
     lib.celeste_tr_subproblem.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.celeste_render_expectation.argtypes = [vp, i32, vp, vp, vp]
     lib.celeste_newton_step.argtypes = [i32, i32, C.POINTER(celeste_newton_buffers), vp]
     _lib = lib
     return lib

@@ -795,6 +795,83 @@ int celeste_elbo_single(celeste_field* f, int32_t S, const int32_t* source_ids, 
     return celeste_elbo_batch(f, 1, task_ptr, source_ids, active_ptr, active_idx, vp, mode, v, d, h, counters, flags);
 }
 
+int celeste_render_expectation(celeste_field* f, int32_t S, const int32_t* source_ids, const double* vp,
+                               double* const* out) {
+    if (!f || S < 0 || !out || (S > 0 && (!source_ids || !vp))) {
+        set_detail("render_expectation: bad arguments (S=%d)", S);
+        return CELESTE_ERR_BAD_ARG;
+    }
+    const int N = f->N;
+    for (int n = 0; n < N; ++n)
+        if (!out[n]) {
+            set_detail("render_expectation: out[%d] is null", n);
+            return CELESTE_ERR_BAD_ARG;
+        }
+    if (S == 0) {
+        for (int n = 0; n < N; ++n)
+            std::memset(out[n], 0, (size_t)f->h_images[n].H * f->h_images[n].W * sizeof(double));
+        return CELESTE_OK;
+    }
+    // the S sources as the slots of a one-task plan (reuses setup_kernel: load_bvn_mixtures! + load_source_brightnesses)
+    const int32_t task_ptr[2] = {0, S}, active_ptr[2] = {0, 1}, act[1] = {1};
+    celeste_plan* raw = nullptr;
+    int rc = celeste_plan_create(f, &raw, 1, task_ptr, source_ids, active_ptr, act);
+    if (rc != CELESTE_OK) return rc;
+    std::unique_ptr<celeste_plan, void (*)(celeste_plan*)> pl(raw, celeste_plan_destroy);
+    CUDA_TRY(cudaSetDevice(f->device));
+    if (!pl->stream) CUDA_TRY(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
+    cudaStream_t st = pl->stream;
+    CUDA_TRY(pl->vp_dev.ensure((size_t)S * NPARAM));
+    CUDA_TRY(cudaMemcpyAsync(pl->vp_dev.p, vp, (size_t)S * NPARAM * sizeof(double), cudaMemcpyHostToDevice, st));
+    const PlanDev pd = plan_dev(pl.get());
+    {
+        const long total = (long)pl->n_slots * N * MAX_COMPS;
+        const int sblocks = (int)std::min<long>((total + 255) / 256, 148L * 16);
+        setup_kernel<<<sblocks, 256, 0, st>>>(pd, pl->vp_dev.p);
+    }
+    std::vector<int> imgH(N), imgW(N);
+    for (int n = 0; n < N; ++n) {
+        imgH[n] = f->h_images[n].H;
+        imgW[n] = f->h_images[n].W;
+    }
+    std::vector<RenderTile> tiles;
+    std::vector<int> tile_slots;
+    build_render_tiles(N, imgH.data(), imgW.data(), S,
+                       [&](int s, int n, int& oh, int& ow, int& H2, int& W2) {
+                           const PatchDev& p = f->h_patches[(size_t)(source_ids[s] - 1) + (size_t)n * f->S_tot];
+                           oh = p.off_h;
+                           ow = p.off_w;
+                           H2 = p.H2;
+                           W2 = p.W2;
+                       },
+                       tiles, tile_slots);
+    DevBuf<RenderTile> d_tiles;
+    DevBuf<int> d_slots;
+    CUDA_TRY(d_tiles.upload(tiles));
+    CUDA_TRY(d_slots.upload(tile_slots));
+    std::vector<DevBuf<double>> d_out(N);
+    std::vector<double*> h_ptrs(N);
+    for (int n = 0; n < N; ++n) {
+        const size_t cnt = (size_t)imgH[n] * imgW[n];
+        CUDA_TRY(d_out[n].alloc(cnt));
+        CUDA_TRY(cudaMemsetAsync(d_out[n].p, 0, cnt * sizeof(double), st));     // pixels no source covers: E_G - sky = 0
+        h_ptrs[n] = d_out[n].p;
+    }
+    DevBuf<double*> d_ptrs;
+    CUDA_TRY(d_ptrs.upload(h_ptrs));
+    if (!tiles.empty()) {
+        if (pl->uniform_K == 2)
+            render_kernel<2><<<(unsigned)tiles.size(), RENDER_THREADS, 0, st>>>(pd, d_tiles.p, d_slots.p, d_ptrs.p);
+        else
+            render_kernel<0><<<(unsigned)tiles.size(), RENDER_THREADS, 0, st>>>(pd, d_tiles.p, d_slots.p, d_ptrs.p);
+        CUDA_TRY(cudaGetLastError());
+    }
+    for (int n = 0; n < N; ++n)
+        CUDA_TRY(cudaMemcpyAsync(out[n], d_out[n].p, (size_t)imgH[n] * imgW[n] * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return CELESTE_OK;
+}
+
 int celeste_tr_subproblem(int32_t batch, int32_t n, const double* g_dev, const double* H_dev, const double* delta_dev,
                           const uint8_t* mask_dev, double* s_dev, double* m_dev, int32_t* interior_dev,
                           void* cuda_stream) {

@@ -23,6 +23,9 @@
 #define CEL_DYNAMIC_SMEM(name) double* name = ::cuda_emul::dynamic_smem()
 #endif
 
+#include <algorithm>
+#include <vector>
+
 #include "elbo_math.cuh"
 
 namespace celeste {
@@ -755,6 +758,25 @@ __device__ inline void build_Jy(double (*Jy)[NLIVE], const PatchDev& p, int b, c
     }
 }
 
+// inverse of bright_id: canonical (0-based) parameter q -> (type i, brightness parameter k); false if q is none
+__device__ inline bool bright_of(int q, int& i, int& k) {
+    if (q < 6 || q >= 26) return false;
+    if (q < 8) {
+        i = q - 6;
+        k = 0;
+    } else if (q < 10) {
+        i = q - 8;
+        k = 1;
+    } else if (q < 18) {
+        i = (q - 10) >> 2;
+        k = 2 + ((q - 10) & 3);
+    } else {
+        i = (q - 18) >> 2;
+        k = 6 + ((q - 18) & 3);
+    }
+    return true;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(EPI_THREADS) epilogue_kernel(PlanDev plan,
                                                                const double* __restrict__ vp, double* __restrict__ out_v,
@@ -771,6 +793,7 @@ __global__ void __launch_bounds__(EPI_THREADS) epilogue_kernel(PlanDev plan,
     __shared__ double gacc[NLIVE];
     __shared__ double s_val, s_cnt[2];
     __shared__ double J0[3][3], T0[3][3][3], J0b[3][3];
+    __shared__ double s_kap[10], s_lam[10];
     __shared__ int s_bad;
 
     const int tid = threadIdx.x;
@@ -805,10 +828,17 @@ __global__ void __launch_bounds__(EPI_THREADS) epilogue_kernel(PlanDev plan,
         for (int n = 0; n < plan.N; ++n) {
             const int tn = sub * plan.N + n;
             const int c0 = plan.chunk_ptr[tn], c1 = plan.chunk_ptr[tn + 1];
+            const PatchDev& p = field.patches[plan.src_row[aslot] + (size_t)n * field.S_tot];
+            const int b = field.images[n].band - 1;
+            // phase 1: fixed-order sum of the chunk partials; clear Jy; band coefficients
             for (int a = tid; a < NACC; a += EPI_THREADS) {
                 double s = 0.0;
                 for (int c = c0; c < c1; ++c) s += plan.partials[(size_t)c * NACC + a];
                 ysum[a] = s;
+            }
+            if (MODE >= 1) {
+                for (int i = tid; i < NY * NLIVE; i += EPI_THREADS) (&Jy[0][0])[i] = 0.0;
+                if (tid == EPI_THREADS - 1) band_coefs(b, s_kap, s_lam);
             }
             __syncthreads();
             if (tid == 0) {
@@ -817,18 +847,34 @@ __global__ void __launch_bounds__(EPI_THREADS) epilogue_kernel(PlanDev plan,
                 s_cnt[1] += ysum[ACC_CNT_INACTIVE];
             }
             if (MODE >= 1) {
-                const PatchDev& p = field.patches[plan.src_row[aslot] + (size_t)n * field.S_tot];
-                const int b = field.images[n].band - 1;
-                if (tid == 0) build_Jy(Jy, p, b, br, J0);
-                if (MODE >= 2 && tid == 32) {
-                    for (int c = 0; c < 4; ++c)
-                        for (int d = c; d < 4; ++d) Hyy[c][d] = Hyy[d][c] = ysum[ACC_CC + tri4(c, d)];
-                    for (int c = 0; c < 4; ++c)
-                        for (int k = 0; k < 6; ++k) Hyy[c][4 + k] = Hyy[4 + k][c] = ysum[ACC_CR + c * 6 + k];
-                    for (int k = 0; k < 6; ++k)
-                        for (int l = k; l < 6; ++l) Hyy[4 + k][4 + l] = Hyy[4 + l][4 + k] = ysum[ACC_HH + tri6(k, l)];
+                // phase 2: the non-zero entries of Jy (same values as build_Jy), one thread each; Hyy from ysum
+                if (tid < 4) {
+                    Jy[4 + (tid >> 1)][tid & 1] = -p.J[(tid & 1) * 2 + (tid >> 1)];     // dx_a/dpos_b = -J[a][b]
+                } else if (tid < 13) {
+                    const int k = (tid - 4) / 3, j = (tid - 4) % 3;
+                    Jy[6 + k][3 + j] = J0[k][j];
+                } else if (tid == 13) {
+                    Jy[9][2] = 1.0;
+                } else if (tid >= 32 && tid < 52) {
+                    const int i = (tid - 32) / 10, k = (tid - 32) % 10;
+                    const double ai = br[20 + i], El = br[i * 5 + b], Ell = br[10 + i * 5 + b];
+                    Jy[i][bright_id(i, k)] = ai * El * s_kap[k];
+                    Jy[2 + i][bright_id(i, k)] = ai * Ell * s_lam[k];
+                } else if (tid == 52 || tid == 53) {
+                    const int i = tid - 52;
+                    Jy[i][26 + i] = br[i * 5 + b];
+                    Jy[2 + i][26 + i] = br[10 + i * 5 + b];
+                }
+                if (MODE >= 2 && tid >= 64) {
+                    for (int e = tid - 64; e < NY * NY; e += EPI_THREADS - 64) {
+                        const int r = e / NY, c = e % NY;
+                        const int lo = r < c ? r : c, hi = r < c ? c : r;
+                        Hyy[r][c] = hi < 4 ? ysum[ACC_CC + tri4(lo, hi)]
+                                           : (lo < 4 ? ysum[ACC_CR + lo * 6 + (hi - 4)] : ysum[ACC_HH + tri6(lo - 4, hi - 4)]);
+                    }
                 }
                 __syncthreads();
+                // phase 3: gradient; W = Hyy Jy
                 if (tid < NLIVE) {
                     double g = 0.0;
                     for (int c = 0; c < 4; ++c) g += Jy[c][tid] * ysum[ACC_C1 + c];
@@ -843,37 +889,28 @@ __global__ void __launch_bounds__(EPI_THREADS) epilogue_kernel(PlanDev plan,
                         Wm[r][q] = s;
                     }
                     __syncthreads();
+                    // phase 4: Hacc += Jy' W + the curvature of Sigma(shape) + the curvature of c(a, beta), per entry
                     for (int i = tid; i < NLIVE * NLIVE; i += EPI_THREADS) {
                         const int pp = i / NLIVE, q = i % NLIVE;
                         double s = 0.0;
                         for (int r = 0; r < NY; ++r) s += Jy[r][pp] * Wm[r][q];
-                        Hacc[pp][q] += s;
-                    }
-                    __syncthreads();
-                    if (tid == 0) {
-                        // curvature of Sigma(shape): sum_k dL/dS_k * T0[k]   (transform_bvn_derivs_hessian!:481-488)
-                        for (int j = 0; j < 3; ++j)
-                            for (int l = 0; l < 3; ++l) {
-                                double s = 0.0;
-                                for (int k = 0; k < 3; ++k) s += ysum[ACC_G + 2 + k] * T0[k][j][l];
-                                Hacc[3 + j][3 + l] += s;
-                            }
-                        // curvature of c(a, beta): E * kappa kappa' and the (a, beta) cross terms
-                        double kap[10], lam[10];
-                        band_coefs(b, kap, lam);
-                        for (int i = 0; i < 2; ++i) {
-                            const double ai = br[20 + i], El = br[i * 5 + b], Ell = br[10 + i * 5 + b];
-                            const double cA = ysum[ACC_C1 + i], cB = ysum[ACC_C1 + 2 + i];
-                            for (int k = 0; k < 10; ++k) {
-                                const int pk = bright_id(i, k);
-                                const double cross = cA * El * kap[k] + cB * Ell * lam[k];
-                                Hacc[26 + i][pk] += cross;
-                                Hacc[pk][26 + i] += cross;
-                                for (int l = 0; l < 10; ++l)
-                                    Hacc[pk][bright_id(i, l)] +=
-                                        ai * (cA * El * kap[k] * kap[l] + cB * Ell * lam[k] * lam[l]);
-                            }
+                        if (pp >= 3 && pp < 6 && q >= 3 && q < 6) {
+                            // sum_k dL/dS_k * T0[k]   (transform_bvn_derivs_hessian!:481-488)
+                            for (int k = 0; k < 3; ++k) s += ysum[ACC_G + 2 + k] * T0[k][pp - 3][q - 3];
                         }
+                        int ip, kp, iq, kq;
+                        const bool bp = bright_of(pp, ip, kp), bq = bright_of(q, iq, kq);
+                        if (bp && bq && ip == iq) {
+                            // E * kappa kappa'
+                            const double ai = br[20 + ip], El = br[ip * 5 + b], Ell = br[10 + ip * 5 + b];
+                            s += ai * (ysum[ACC_C1 + ip] * El * s_kap[kp] * s_kap[kq] +
+                                       ysum[ACC_C1 + 2 + ip] * Ell * s_lam[kp] * s_lam[kq]);
+                        } else if ((bp && q == 26 + ip) || (bq && pp == 26 + iq)) {
+                            // the (a, beta) cross terms
+                            const int i2 = bp ? ip : iq, k2 = bp ? kp : kq;
+                            s += ysum[ACC_C1 + i2] * br[i2 * 5 + b] * s_kap[k2] + ysum[ACC_C1 + 2 + i2] * br[10 + i2 * 5 + b] * s_lam[k2];
+                        }
+                        Hacc[pp][q] += s;
                     }
                 }
             }
@@ -961,6 +998,107 @@ __global__ void __launch_bounds__(EPI_THREADS) epilogue_kernel(PlanDev plan,
     if (bad) atomicOr(&s_bad, 1);
     __syncthreads();
     if (tid == 0) out_flags[t] = s_bad ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// render_kernel: the value-only full-image render -- what bin/write_celeste_expectation.jl:111-156
+// (fill_celeste_expectation!) computes by calling add_pixel_term! in value mode on EVERY pixel of every image:
+//     out[h, w] = E_G - sky = sum over the sources whose patch covers (h, w) of  a1 E_l1 f0 + a2 E_l2 f1
+// with the same in-patch test as the ELBO (strict w2 < W2, bitmap; elbo_objective.jl:349) and the sources added in
+// task order onto the sky (:374) exactly as there.  Pixel-centric: one block per non-empty 32 x 8 image tile
+// (32 consecutive rows = one coalesced warp access of the column-major image), the tile's source list binned on
+// the host from the patch boxes; the component records of one source at a time go through shared memory.
+constexpr int RT_H = 32, RT_W = 8, RENDER_THREADS = RT_H * RT_W;
+
+struct RenderTile {
+    int n;            // image
+    int h0, w0;       // 0-based origin of the tile
+    int begin, end;   // range into tile_slots (ascending slot order)
+};
+
+// host side: bin the S slots' patches of image n into tiles (CSR).  geo(s) -> off_h, off_w, H2, W2.
+template <typename Geo>
+inline void build_render_tiles(int N, const int* imgH, const int* imgW, int S, Geo geo, std::vector<RenderTile>& tiles,
+                               std::vector<int>& tile_slots) {
+    tiles.clear();
+    tile_slots.clear();
+    for (int n = 0; n < N; ++n) {
+        const int H = imgH[n], W = imgW[n];
+        const int th_n = (H + RT_H - 1) / RT_H, tw_n = (W + RT_W - 1) / RT_W;
+        std::vector<int> count((size_t)th_n * tw_n + 1, 0);
+        auto range = [&](int s, int& t0, int& t1, int& u0, int& u1) {
+            int oh, ow, H2, W2;
+            geo(s, n, oh, ow, H2, W2);
+            const int hlo = std::max(oh + 1, 1), hhi = std::min(oh + H2, H);
+            const int wlo = std::max(ow + 1, 1), whi = std::min(ow + W2 - 1, W);     // strict w2 < W2
+            if (hlo > hhi || wlo > whi) return false;
+            t0 = (hlo - 1) / RT_H;
+            t1 = (hhi - 1) / RT_H;
+            u0 = (wlo - 1) / RT_W;
+            u1 = (whi - 1) / RT_W;
+            return true;
+        };
+        int t0, t1, u0, u1;
+        for (int s = 0; s < S; ++s)
+            if (range(s, t0, t1, u0, u1))
+                for (int u = u0; u <= u1; ++u)
+                    for (int t = t0; t <= t1; ++t) count[(size_t)t + (size_t)u * th_n + 1]++;
+        for (size_t i = 1; i < count.size(); ++i) count[i] += count[i - 1];
+        const int base = (int)tile_slots.size();
+        tile_slots.resize(base + count.back());
+        std::vector<int> fill(count.begin(), count.end() - 1);
+        for (int s = 0; s < S; ++s)
+            if (range(s, t0, t1, u0, u1))
+                for (int u = u0; u <= u1; ++u)
+                    for (int t = t0; t <= t1; ++t) tile_slots[base + fill[(size_t)t + (size_t)u * th_n]++] = s;
+        for (int u = 0; u < tw_n; ++u)
+            for (int t = 0; t < th_n; ++t) {
+                const size_t i = (size_t)t + (size_t)u * th_n;
+                if (count[i + 1] > count[i]) tiles.push_back(RenderTile{n, t * RT_H, u * RT_W, base + count[i], base + count[i + 1]});
+            }
+    }
+}
+
+template <int KT>
+__global__ void __launch_bounds__(RENDER_THREADS) render_kernel(PlanDev plan, const RenderTile* __restrict__ tiles,
+                                                                const int* __restrict__ tile_slots,
+                                                                double* const* __restrict__ out) {
+    __shared__ double s_comps[MAX_COMPS * COMP_STRIDE];
+    __shared__ double s_exptab[8];
+    const int tid = threadIdx.x;
+    const RenderTile t = tiles[blockIdx.x];
+    const FieldDev field = plan.fields[0];
+    const ImageDev img = field.images[t.n];
+    const int h = t.h0 + (tid % RT_H) + 1, w = t.w0 + (tid / RT_H) + 1;      // 1-based image coordinates
+    const bool inside = h <= img.H && w <= img.W;
+    const size_t ipix = (size_t)(h - 1) + (size_t)(w - 1) * img.H;
+    const double sky = inside ? (double)img.sky[ipix] : 0.0;
+    double E = sky;                                                          // E_G.v += sky (:374); sources on top
+    const int b = img.band - 1;
+#ifdef CELESTE_HOST_EMULATION
+    if (tid < 8) s_exptab[tid] = h_exptab[tid];
+#else
+    if (tid < 8) s_exptab[tid] = c_exptab[tid];
+#endif
+    for (int i = t.begin; i < t.end; ++i) {
+        const int s = tile_slots[i];
+        const PatchDev& p = field.patches[plan.src_row[s] + (size_t)t.n * field.S_tot];
+        const double* rec = plan.slotimg + ((size_t)s * plan.N + t.n) * SLOTIMG_STRIDE;
+        const int nrec = NPROTO * (KT > 0 ? KT : p.K) * COMP_STRIDE;
+        __syncthreads();                                                     // the previous source's records are consumed
+        for (int j = tid; j < nrec; j += RENDER_THREADS) s_comps[j] = rec[j];
+        __syncthreads();
+        const int h2 = h - p.off_h, w2 = w - p.off_w;
+        if (!inside || h2 < 1 || h2 > p.H2 || w2 < 1 || w2 >= p.W2) continue;
+        if (!p.bitmap[(h2 - 1) + (size_t)(w2 - 1) * p.H2]) continue;
+        const double* br = plan.slotbr + (size_t)s * SLOTBR_STRIDE;
+        const double m1 = rec[MAX_COMPS * COMP_STRIDE], m2 = rec[MAX_COMPS * COMP_STRIDE + 1];
+        double f0, gd[2], hd[3];
+        star_eval<0>(LdGlobal(), p.coefs, p.n1, p.n2, (double)h - m1 + 26.0, (double)w - m2 + 26.0, f0, gd, hd);
+        const double f1 = gal_value<KT>(LdShared(), s_comps, p.K, s_exptab, br[22], (double)h, (double)w);
+        E += br[20] * br[b] * f0 + br[21] * br[5 + b] * f1;
+    }
+    if (inside) out[t.n][ipix] = E - sky;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -171,6 +171,33 @@ class DeviceField:
     def make_plan(self, tasks_rows, tasks_active):
         return Plan(self, tasks_rows, tasks_active)
 
+    def render_expectation(self, rows, vp) -> List[np.ndarray]:
+        """celeste_render_expectation: for every image the H x W float64 array of E_G - sky (nanomaggies) summed
+        over the sources `rows` (1-based rows of the patch matrix) at variational parameters vp (44 x S)."""
+        lib = _lib.load()
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        vpm = np.asfortranarray(vp, dtype=np.float64)
+        S = len(rows)
+        assert vpm.shape == (44, S) or S == 0
+        fi = self._flat_images
+        outs = [np.zeros((fi.arr[n].H, fi.arr[n].W), dtype=np.float64, order="F") for n in range(fi.N)]
+        ptrs = (C.c_void_p * max(fi.N, 1))(*[o.ctypes.data for o in outs])
+        _lib.check(lib.celeste_render_expectation(self._handle, S, rows.ctypes.data if S else None,
+                                                  vpm.ctypes.data if S else None, ptrs))
+        return outs
+
+
+def fill_celeste_expectation(images: Sequence[Image], patches: np.ndarray, vps, field: Optional[DeviceField] = None):
+    """bin/write_celeste_expectation.jl:111-156 (fill_celeste_expectation!): add the model's expected source flux
+    (nanomaggies) of ALL sources to every pixel of every image, `image.pixels[h, w] += E_G - sky[h, w]`
+    (Float32 pixels as in the reference).  vps: the S variational parameter vectors, in patch-row order."""
+    field = field or DeviceField(images, patches)
+    S = patches.shape[0]
+    add = field.render_expectation(np.arange(1, S + 1), np.stack(vps, axis=1) if S else np.zeros((44, 0)))
+    for im, a in zip(images, add):
+        im.pixels = (im.pixels.astype(np.float64) + a).astype(np.float32)     # Float32 += Float64, rounded once
+    return images
+
 
 class Plan:
     """A registered task list (celeste_plan): evaluate it repeatedly with new vp."""

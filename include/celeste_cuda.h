@@ -242,6 +242,18 @@ int celeste_set_chunk_pixels(int32_t chunk_pixels);
 void celeste_field_destroy(celeste_field* f);
 
 /*
+ * Row f.4, the value-only full-image render: fill_celeste_expectation! (bin/write_celeste_expectation.jl:111-156),
+ * which calls add_pixel_term! (elbo_objective.jl:330-392) in value mode on EVERY pixel of every image of the
+ * field.  For image n (n = 0..N-1), out[n] (HOST, H x W doubles, column-major like the image) receives
+ *     E_G(h, w) - sky(h, w) = sum over the S sources whose patch covers (h, w)  [same in-patch test as the ELBO,
+ *                             incl. the strict w2 < W2 of :349]  of  a_star E_l_star f_star + a_gal E_l_gal f_gal
+ * in nanomaggies, sources added in the order given (the reference then does image.pixels[h, w] += that).
+ * source_ids: 1-based rows of the patch matrix; vp: 44 x S column-major.  Synchronous.
+ */
+int celeste_render_expectation(celeste_field* f, int32_t S, const int32_t* source_ids, const double* vp,
+                               double* const* out);
+
+/*
  * Row f.2 (batched Newton trust region; the step ElboMaximize.maximize! delegates to Optim.NewtonTrustRegion,
  * src/deterministic_vi/ElboMaximize.jl:105-108,235): for each of `batch` sources solve
  *     min_s  g's + 1/2 s'Hs   subject to |s| <= delta

@@ -1114,6 +1114,72 @@ int oracle_elbo_batch(int32_t N, const celeste_image* imgs, int32_t S_tot, const
     return 0;
 }
 
+// fill_celeste_expectation! (bin/write_celeste_expectation.jl:111-156): ElboArgs(images, patches, [1]) with
+// value-only scratch, then for EVERY pixel of every image add_pixel_term! and `pixels[h, w] += E_G.v - sky[h, w]`.
+// out[n] (H x W doubles, column-major) receives that increment.  Worker threads split each image by columns.
+int oracle_render_expectation(int32_t N, const celeste_image* imgs, int32_t S_tot, const celeste_patch* patches,
+                              int32_t S, const int32_t* source_ids, const double* vp, double* const* out,
+                              int32_t n_threads) {
+    Ea ea;
+    ea.S = S;
+    ea.Sa = S > 0 ? 1 : 0;
+    ea.N = N;
+    ea.images = imgs;
+    ea.vp = vp;
+    ea.patches.resize((size_t)S * N);
+    for (int n = 0; n < N; ++n)
+        for (int s = 0; s < S; ++s) ea.patches[s + (size_t)n * S] = &patches[(size_t)(source_ids[s] - 1) + (size_t)n * S_tot];
+    ea.psf_K = S > 0 && N > 0 ? ea.patches[0]->K : 2;
+    if (S > 0) ea.active_sources.push_back(0);                     // active_sources = [1]
+    std::vector<SourceBrightness> sbs;
+    load_source_brightnesses(ea, sbs);                             // derivative flags do not change the values
+    for (int n = 0; n < N; ++n) {
+        const celeste_image& img = imgs[n];
+        Mixtures mx;
+        mx.K = ea.psf_K;
+        mx.S = S;
+        mx.gal.resize((size_t)ea.psf_K * 8 * 2 * S);
+        load_bvn_mixtures(mx, ea, n, false, false);
+        std::atomic<int> next{1};
+        auto worker = [&]() {
+            ElboVars ev(std::max(ea.Sa, 1), false, false);
+            for (;;) {
+                const int w = next.fetch_add(1);
+                if (w > img.W) break;
+                for (int h = 1; h <= img.H; ++h) {
+                    // the E_G part of add_pixel_term! (:340-374)
+                    zero(ev.E_G);
+                    zero(ev.var_G);
+                    for (int s = 0; s < S; ++s) {
+                        const celeste_patch* p = ea.patch(s, n);
+                        const int64_t h2 = h - p->bitmap_offset[0], w2 = w - p->bitmap_offset[1];
+                        if (1 <= h2 && h2 <= p->H2 && 1 <= w2 && w2 < p->W2 &&
+                            p->active_pixel_bitmap[(h2 - 1) + (size_t)(w2 - 1) * p->H2]) {
+                            const bool is_active = ea.find_active(s) >= 0;
+                            const PatchView pv = view(p);
+                            star_light_density(ev.fs0m, pv, h, w, ea.vs(s) + ID_POS0, is_active);
+                            Mixtures& mref = mx;
+                            populate_gal_fsm(ev.fs1m, ev.bd, s, h, w, is_active, pv.J, mref);
+                            accumulate_source_pixel_brightness(ea, ev, sbs[s], img.band - 1, s, is_active);
+                        }
+                    }
+                    const double sky = (double)img_sky(img, h, w);
+                    ev.E_G.v += sky;
+                    out[n][(size_t)(h - 1) + (size_t)(w - 1) * img.H] = ev.E_G.v - sky;
+                }
+            }
+        };
+        if (n_threads <= 1) {
+            worker();
+        } else {
+            std::vector<std::thread> th;
+            for (int i = 0; i < n_threads; ++i) th.emplace_back(worker);
+            for (auto& x : th) x.join();
+        }
+    }
+    return 0;
+}
+
 // get_bvn_cov closed form (test/test_elbo.jl:45-61): out = (S11, S12, S22)
 void oracle_get_bvn_cov(double ab, double angle, double scale, double* out) {
     double c[2][2];

@@ -159,3 +159,34 @@ def elbo_ad(images, patches, vp, active_sources, hessian=True):
                 rows.append(torch.zeros(44 * Sa, dtype=T))
         Hm = torch.stack(rows).detach().numpy()
     return float(val.detach()), g.detach().numpy().reshape(Sa, 44).T, Hm
+
+
+def render_value(images, patches, vp_list):
+    """Independent restatement of fill_celeste_expectation! (bin/write_celeste_expectation.jl:111-156): per image
+    the H x W array of E_G - sky, i.e. the summed expected source flux (nmgy) with the ELBO's in-patch test."""
+    S, N = patches.shape
+    bright = [_brightness(torch.tensor(vs, dtype=T)) for vs in vp_list]
+    outs = []
+    for n in range(N):
+        img = images[n]
+        out = np.zeros((img.H, img.W))
+        b = img.b - 1
+        for s in range(S):
+            p = patches[s, n]
+            H2, W2 = p.active_pixel_bitmap.shape
+            if H2 == 0 or W2 <= 1:
+                continue
+            o = p.bitmap_offset
+            h2, w2 = np.nonzero(p.active_pixel_bitmap[:, :W2 - 1])          # strict last column
+            hs, ws = h2 + o[0], w2 + o[1]
+            ok = (hs >= 0) & (hs < img.H) & (ws >= 0) & (ws < img.W)
+            hs, ws = hs[ok], ws[ok]
+            if len(hs) == 0:
+                continue
+            vs = torch.tensor(vp_list[s], dtype=T)
+            f0, f1 = _densities(p, vs, torch.tensor(hs + 1.0, dtype=T), torch.tensor(ws + 1.0, dtype=T))
+            El, _ = bright[s]
+            Es = vs[ids.is_star[0]] * El[b][0] * f0 + vs[ids.is_star[1]] * El[b][1] * f1
+            np.add.at(out, (hs, ws), Es.numpy())
+        outs.append(out)
+    return outs

@@ -193,3 +193,26 @@ def assert_parity(ref, got, mode, label=""):
         rh, gh = ref["h"].reshape(n, -1), got["h"].reshape(n, -1)
         sc = np.abs(rh).max(axis=1, keepdims=True)
         assert np.all(np.abs(rh - gh) <= 1e-8 * np.maximum(np.abs(rh), sc * 1e-6)), (label, np.abs(rh - gh).max())
+
+
+def all_vp(patches, tasks):
+    """44 x S matrix of the variational parameters of every source of a case (rows in patch order)."""
+    S = patches.shape[0]
+    vp = [None] * S
+    for rows, act, v in tasks:
+        for j, r in enumerate(rows):
+            vp[r - 1] = np.asarray(v)[:, j]
+    assert all(x is not None for x in vp)
+    return np.stack(vp, axis=1)
+
+
+def assert_render_parity(ref, got, what="", rtol=1e-12):
+    """E_G - sky images: |delta| <= rtol * max|ref| per image (the subtraction of the Float32 sky leaves an
+    absolute error of a few ulp of the sky level)."""
+    assert len(ref) == len(got)
+    for n, (r, g) in enumerate(zip(ref, got)):
+        assert r.shape == g.shape
+        scale = max(np.abs(r).max(), 1.0)
+        err = np.abs(r - g).max()
+        assert err <= rtol * scale, f"{what} image {n}: max |delta| {err:.3e} vs scale {scale:.3e}"
+        assert np.array_equal(r == 0.0, g == 0.0) or np.abs(r[(r == 0.0) != (g == 0.0)]).max() <= rtol * scale

@@ -23,6 +23,7 @@ def load():
         _lib.emul_elbo_batch.argtypes = [i32, vp, i32, vp, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, i32]
         _lib.emul_tr_subproblem.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp]
         _lib.emul_newton_step.argtypes = [i32, i32, vp]
+        _lib.emul_render_expectation.argtypes = [i32, vp, i32, vp, i32, vp, vp, vp]
     return _lib
 
 
@@ -70,3 +71,10 @@ def newton_stepper(phase, n, buffers):
     """newton_step_kernel under emulation, as the `stepper` hook of elbo_maximize.BatchMaximizer (CPU tensors)."""
     st = load().emul_newton_step(phase, n, C.addressof(buffers))
     assert st == 0
+
+
+def render_expectation(images, patches, rows, vp):
+    """render_kernel (+ setup_kernel, host tile binning) under emulation."""
+    from oracle_lib import _render
+    fi, fp = FlatImages(images), FlatPatches(patches)
+    return _render(load().emul_render_expectation, fi, fp, rows, vp)

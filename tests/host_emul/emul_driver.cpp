@@ -236,3 +236,75 @@ extern "C" int emul_newton_step(int32_t phase, int32_t batch, const celeste_newt
     cuda_emul::launch(newton_step_kernel, batch, TR_THREADS, 0, dev, phase);
     return 0;
 }
+
+// render_kernel under emulation (one field, slots = the S sources in order)
+extern "C" int emul_render_expectation(int32_t N, const celeste_image* imgs, int32_t S_tot, const celeste_patch* patches,
+                                       int32_t S, const int32_t* source_ids, const double* vp, double* const* out) {
+    galaxy_prototypes(c_proto_eta, c_proto_nu);
+    std::vector<ImageDev> images(N);
+    std::vector<int> imgH(N), imgW(N);
+    for (int n = 0; n < N; ++n) {
+        const celeste_image& im = imgs[n];
+        images[n] = ImageDev{im.H, im.W, im.band, im.pixels, im.sky, im.nelec_per_nmgy, nullptr};
+        imgH[n] = im.H;
+        imgW[n] = im.W;
+        std::fill(out[n], out[n] + (size_t)im.H * im.W, 0.0);
+    }
+    if (S == 0) return 0;
+    std::vector<PatchDev> pdv((size_t)S_tot * N);
+    for (size_t i = 0; i < pdv.size(); ++i) {
+        const celeste_patch& q = patches[i];
+        PatchDev p;
+        p.off_h = (int)q.bitmap_offset[0];
+        p.off_w = (int)q.bitmap_offset[1];
+        p.H2 = q.H2;
+        p.W2 = q.W2;
+        p.bitmap = q.active_pixel_bitmap;
+        for (int k = 0; k < 4; ++k) p.J[k] = q.wcs_jacobian[k];
+        p.wc[0] = q.world_center[0];
+        p.wc[1] = q.world_center[1];
+        p.pc[0] = q.pixel_center[0];
+        p.pc[1] = q.pixel_center[1];
+        p.K = q.K;
+        p.psf = q.psf;
+        p.coefs = q.itp_coefs;
+        p.n1 = q.itp_dims[0];
+        p.n2 = q.itp_dims[1];
+        pdv[i] = p;
+    }
+    std::vector<int> src_row(S), sfield(S, 0);
+    for (int s = 0; s < S; ++s) src_row[s] = source_ids[s] - 1;
+    std::vector<double> slotimg((size_t)S * N * SLOTIMG_STRIDE), slotbr((size_t)S * SLOTBR_STRIDE);
+    FieldDev fd{images.data(), pdv.data(), S_tot, 0};
+    PlanDev pd{};
+    pd.n_tasks = 1;
+    pd.N = N;
+    pd.n_fields = 1;
+    pd.n_slots = S;
+    pd.fields = &fd;
+    pd.slot_field = sfield.data();
+    pd.src_row = src_row.data();
+    pd.slotimg = slotimg.data();
+    pd.slotbr = slotbr.data();
+    cuda_emul::launch(setup_kernel, 2, 64, 0, pd, vp);
+    std::vector<RenderTile> tiles;
+    std::vector<int> tile_slots;
+    build_render_tiles(N, imgH.data(), imgW.data(), S,
+                       [&](int s, int n, int& oh, int& ow, int& H2, int& W2) {
+                           const PatchDev& p = pdv[(size_t)src_row[s] + (size_t)n * S_tot];
+                           oh = p.off_h;
+                           ow = p.off_w;
+                           H2 = p.H2;
+                           W2 = p.W2;
+                       },
+                       tiles, tile_slots);
+    bool k2 = true;
+    for (size_t i = 0; i < pdv.size(); ++i) k2 = k2 && pdv[i].K == 2;
+    if (!tiles.empty()) {
+        if (k2)
+            cuda_emul::launch(render_kernel<2>, (int)tiles.size(), RENDER_THREADS, 0, pd, tiles.data(), tile_slots.data(), out);
+        else
+            cuda_emul::launch(render_kernel<0>, (int)tiles.size(), RENDER_THREADS, 0, pd, tiles.data(), tile_slots.data(), out);
+    }
+    return 0;
+}

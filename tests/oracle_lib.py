@@ -30,6 +30,7 @@ def load(path=None):
     lib.oracle_spline_eval.restype = None
     lib.oracle_galaxy_prototypes.argtypes = [vp, vp]
     lib.oracle_galaxy_prototypes.restype = None
+    lib.oracle_render_expectation.argtypes = [i32, vp, i32, vp, i32, vp, vp, vp, i32]
     lib.oracle_calculate_G_s_probe.argtypes = [i32, vp, i32, vp, i32, vp, vp, i32, vp, vp, vp]
     if path is None:
         _lib = lib
@@ -62,6 +63,23 @@ class OracleField:
                                         p(v), p(d), p(h), p(counters), p(flags), n_threads)
         assert st == 0
         return {"v": v, "d": d, "h": h, "counters": counters.reshape(n, 2), "flags": flags, "active_ptr": active_ptr}
+
+
+def _render(fn, fi, fp, rows, vp, *extra):
+    rows = np.ascontiguousarray(rows, dtype=np.int32)
+    vpm = np.asfortranarray(vp, dtype=np.float64)
+    outs = [np.zeros((fi.arr[n].H, fi.arr[n].W), dtype=np.float64, order="F") for n in range(fi.N)]
+    ptrs = (C.c_void_p * max(fi.N, 1))(*[o.ctypes.data for o in outs])
+    st = fn(fi.N, C.addressof(fi.arr), fp.S_tot, C.addressof(fp.arr), len(rows), rows.ctypes.data if len(rows) else None,
+            vpm.ctypes.data if len(rows) else None, ptrs, *extra)
+    assert st == 0
+    return outs
+
+
+def oracle_render_expectation(images, patches, rows, vp, n_threads=8):
+    """fill_celeste_expectation! by the oracle: per image the H x W array of E_G - sky."""
+    of = OracleField(images, patches)
+    return _render(of.lib.oracle_render_expectation, of.fi, of.fp, rows, vp, n_threads)
 
 
 def oracle_elbo(images, patches, vp, active_sources, mode=2):

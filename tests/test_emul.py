@@ -52,3 +52,24 @@ def test_emulated_kernels_multiple_active_sources(name, active):
         ref = oracle_lib.OracleField(images, patches).elbo_batch(tk, mode=mode)
         got = emul_lib.EmulField(images, patches).elbo_batch(tk, mode=mode)
         cases.assert_parity(ref, got, mode, f"{name} {active}")
+
+
+@pytest.mark.parametrize("name", ["two_body", "masked", "clipped_and_empty", "psf_k3", "config2_rotated_wcs", "small_field"])
+def test_emulated_render_kernel_matches_oracle(name):
+    """Row f.4: render_kernel + the host tile binning (fill_celeste_expectation!, bin/write_celeste_expectation.jl:
+    111-156) against the oracle's per-pixel add_pixel_term! loop; subsets and reorderings of the source list too."""
+    images, patches, tasks = cases.get(name)
+    vp = cases.all_vp(patches, tasks)
+    S = patches.shape[0]
+    rows = np.arange(1, S + 1)
+    ref = oracle_lib.oracle_render_expectation(images, patches, rows, vp)
+    got = emul_lib.render_expectation(images, patches, rows, vp)
+    cases.assert_render_parity(ref, got, name)
+    assert any(np.abs(r).max() > 0 for r in ref)
+    if S >= 2:
+        sub = rows[::-1][: max(1, S // 2)]
+        ref = oracle_lib.oracle_render_expectation(images, patches, sub, vp[:, sub - 1])
+        got = emul_lib.render_expectation(images, patches, sub, vp[:, sub - 1])
+        cases.assert_render_parity(ref, got, name + " subset")
+    empty = emul_lib.render_expectation(images, patches, rows[:0], vp[:, :0])
+    assert all(not e.any() for e in empty)

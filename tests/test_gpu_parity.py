@@ -401,3 +401,63 @@ def test_task_mask_skips_tasks_and_leaves_outputs(cj):
         if mode == 2:
             h = bufs[2].cpu().numpy().reshape(n, -1)
             assert np.array_equal(h[keep], ref["h"].reshape(n, -1)[keep]) and (h[~keep] == -7.0).all()
+
+
+@pytest.mark.parametrize("name", ["star_1band", "two_body", "masked", "clipped_and_empty", "psf_k1", "psf_k3",
+                                  "config2_rotated_wcs", "crowded", "small_field"])
+def test_render_expectation_matches_oracle(cj, name):
+    """Row f.4: celeste_render_expectation (fill_celeste_expectation!, bin/write_celeste_expectation.jl:111-156)
+    against the oracle's add_pixel_term!-on-every-pixel loop: all sources, a reversed subset, and none."""
+    images, patches, tasks = cases.get(name)
+    vp = cases.all_vp(patches, tasks)
+    S = patches.shape[0]
+    rows = np.arange(1, S + 1)
+    field = cj.DeviceField(images, patches)
+    cases.assert_render_parity(oracle_lib.oracle_render_expectation(images, patches, rows, vp),
+                               field.render_expectation(rows, vp), name)
+    sub = rows[::-1][: max(1, S // 2)]
+    cases.assert_render_parity(oracle_lib.oracle_render_expectation(images, patches, sub, vp[:, sub - 1]),
+                               field.render_expectation(sub, vp[:, sub - 1]), name + " subset")
+    assert all(not e.any() for e in field.render_expectation(rows[:0], vp[:, :0]))
+
+
+def test_fill_celeste_expectation_api(cj):
+    """The reference-facing call: image.pixels[h, w] += E_G - sky for every pixel (Float32 pixels)."""
+    import copy
+    images, patches, tasks = cases.get("config2_rotated_wcs")
+    vp = cases.all_vp(patches, tasks)
+    before = [im.pixels.copy() for im in images]
+    imgs = copy.deepcopy(images)
+    cj.fill_celeste_expectation(imgs, patches, [vp[:, s] for s in range(vp.shape[1])])
+    ref = oracle_lib.oracle_render_expectation(images, patches, np.arange(1, vp.shape[1] + 1), vp)
+    for im, b, r in zip(imgs, before, ref):
+        assert im.pixels.dtype == np.float32
+        want = (b.astype(np.float64) + r).astype(np.float32)
+        ok = ~np.isnan(want)
+        assert np.array_equal(np.isnan(im.pixels), ~ok)
+        assert np.allclose(im.pixels[ok], want[ok], rtol=2e-7, atol=0)
+        assert (im.pixels[ok] != b[ok]).any()
+
+
+def test_render_full_size_sample_and_properties(cj, field1000):
+    """configs[2] scale (5 x 2048 x 1489, 1000 sources): a 24-source subset against the oracle on the full
+    images; additivity over a split of the source list; zero wherever no patch reaches; non-negative."""
+    ds, field = field1000
+    vp = np.stack(ds.vp, axis=1)
+    rows = np.arange(1, 1001)
+    full = field.render_expectation(rows, vp)
+    pick = np.sort(np.random.default_rng(5).choice(1000, 24, replace=False)) + 1
+    cases.assert_render_parity(oracle_lib.oracle_render_expectation(ds.images, ds.patches, pick, vp[:, pick - 1], n_threads=16),
+                               field.render_expectation(pick, vp[:, pick - 1]), "field1000 subset")
+    a = field.render_expectation(rows[:500], vp[:, :500])
+    b = field.render_expectation(rows[500:], vp[:, 500:])
+    for n in range(len(full)):
+        assert np.allclose(a[n] + b[n], full[n], rtol=1e-11, atol=1e-11 * full[n].max())
+        assert (full[n] >= -1e-12 * full[n].max()).all()
+        cover = np.zeros(full[n].shape, dtype=bool)
+        for s in range(1000):
+            p = ds.patches[s, n]
+            H2, W2 = p.active_pixel_bitmap.shape
+            o = p.bitmap_offset
+            cover[max(o[0], 0):o[0] + H2, max(o[1], 0):o[1] + W2 - 1] = True
+        assert not full[n][~cover].any() and full[n][cover].any()

@@ -235,3 +235,21 @@ def test_oracle_threads_agree():
     b = of.elbo_batch(tasks, mode=2, n_threads=4)
     for k in ("v", "d", "h", "counters", "flags"):
         assert np.array_equal(a[k], b[k])
+
+
+@pytest.mark.parametrize("name", ["two_body", "clipped_and_empty", "config2_rotated_wcs", "psf_k3"])
+def test_oracle_render_matches_independent_restatement(name):
+    """Row f.4 checker: the oracle's fill_celeste_expectation! (add_pixel_term! on every pixel) against the torch
+    restatement of the model (tests/ad_model.py) -- and it is additive over sources."""
+    import ad_model
+    images, patches, tasks = cases.get(name)
+    vp = cases.all_vp(patches, tasks)
+    S = patches.shape[0]
+    rows = np.arange(1, S + 1)
+    got = oracle_lib.oracle_render_expectation(images, patches, rows, vp, n_threads=4)
+    ref = ad_model.render_value(images, patches, [vp[:, s] for s in range(S)])
+    cases.assert_render_parity(ref, got, name, rtol=1e-11)
+    parts = [oracle_lib.oracle_render_expectation(images, patches, rows[s:s + 1], vp[:, s:s + 1]) for s in range(S)]
+    for n in range(len(images)):
+        total = sum(p[n] for p in parts)
+        assert np.allclose(total, got[n], rtol=1e-12, atol=1e-12 * max(np.abs(got[n]).max(), 1.0))

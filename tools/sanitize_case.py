@@ -22,3 +22,14 @@ A = torch.randn(4, 41, 41, dtype=torch.float64, device="cuda")
 s, m, interior = em.solve_tr_subproblem(g, A + A.transpose(1, 2), torch.ones(4, dtype=torch.float64, device="cuda"))
 torch.cuda.synchronize()
 print("tr", m.cpu().numpy())
+# row f.4 render kernel and the fused Newton step (f.1-f.3)
+images, patches, tasks = cases.get("clipped_and_empty")
+vp = cases.all_vp(patches, tasks)
+r = cj.DeviceField(images, patches).render_expectation(np.arange(1, vp.shape[1] + 1), vp)
+print("render", [float(a.sum()) for a in r])
+from celeste_jl_b200 import synthetic
+ds = synthetic.FieldDataset(6, H=90, W=80, seed=3, device="cpu")
+rows, act = ds.tasks()
+plan = cj.Plan(cj.DeviceField(ds.images, ds.patches), rows, act)
+res = em.BatchMaximizer(plan, ds.vp_flat(rows), include_kl=True, max_iters=3).run()
+print("newton", res.value[:3], res.iterations)
