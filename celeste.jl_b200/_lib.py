@@ -41,6 +41,13 @@ class celeste_patch(C.Structure):
                 ("psf", C.c_void_p), ("itp_coefs", C.c_void_p), ("itp_dims", C.c_int32 * 2)]
 
 
+class celeste_patch_spec(C.Structure):
+    _fields_ = [("bitmap_offset", C.c_int64 * 2), ("H2", C.c_int32), ("W2", C.c_int32),
+                ("wcs_jacobian", C.c_double * 4), ("world_center", C.c_double * 2),
+                ("pixel_center", C.c_double * 2), ("K", C.c_int32), ("grid_n", C.c_int32),
+                ("psf", C.c_void_p), ("grid_psf", C.c_void_p)]
+
+
 class CelesteError(RuntimeError):
     def __init__(self, status: int, msg: str, detail: str = ""):
         super().__init__(f"celeste_cuda status {status}: {msg}" + (f" [{detail}]" if detail else ""))
@@ -59,7 +66,7 @@ EXPORTS = [
     "celeste_elbo_plan_device", "celeste_elbo_plan_host", "celeste_field_destroy",
     "celeste_fp64_peak", "celeste_plan_enable_timing", "celeste_plan_kernel_times", "celeste_set_chunk_pixels",
     "celeste_plan_create_multi", "celeste_tr_subproblem", "celeste_plan_set_task_mask", "celeste_newton_step",
-    "celeste_render_expectation",
+    "celeste_render_expectation", "celeste_patches_build", "celeste_patch_readback", "celeste_find_neighbors",
 ]
 
 
@@ -111,6 +118,9 @@ def load():
     lib.celeste_plan_set_task_mask.argtypes = [vp, vp]
     lib.celeste_tr_subproblem.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.celeste_render_expectation.argtypes = [vp, i32, vp, vp, vp]
+    lib.celeste_patches_build.argtypes = [vp, i32, i32, C.POINTER(celeste_patch_spec)]
+    lib.celeste_patch_readback.argtypes = [vp, i32, i32, vp, vp, vp]
+    lib.celeste_find_neighbors.argtypes = [vp, vp, vp, C.c_int64, C.POINTER(C.c_int64)]
     lib.celeste_newton_step.argtypes = [i32, i32, C.POINTER(celeste_newton_buffers), vp]
     _lib = lib
     return lib

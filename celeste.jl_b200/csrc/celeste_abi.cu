@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <tuple>
 #include <mutex>
 #include <new>
 #include <string>
@@ -21,6 +22,7 @@
 #include "../../include/celeste_cuda.h"
 #include "celeste_kernels.cuh"
 #include "maximize_kernels.cuh"
+#include "patch_kernels.cuh"
 
 using namespace celeste;
 
@@ -372,6 +374,180 @@ int celeste_patches_set(celeste_field* f, int32_t S_tot, int32_t N, const celest
     for (size_t i = 0; i < np; ++i)
         if (p[i].K != f->uniform_K) f->uniform_K = 0;
     f->patch_generation++;
+    return CELESTE_OK;
+}
+
+int celeste_patches_build(celeste_field* f, int32_t S_tot, int32_t N, const celeste_patch_spec* specs) {
+    if (!f || S_tot < 0 || N != f->N || (S_tot > 0 && N > 0 && !specs)) {
+        set_detail("patches_build: bad arguments (N=%d, field N=%d)", N, f ? f->N : -1);
+        return CELESTE_ERR_BAD_ARG;
+    }
+    CUDA_TRY(cudaSetDevice(f->device));
+    const size_t np = (size_t)S_tot * N;
+    // pools: bitmaps (filled on the device); doubles = psf records + raw stamps (uploaded) + coefficient arrays (built)
+    std::vector<double> hd;
+    std::vector<size_t> bm_off(np), psf_off(np), coef_off(np);
+    size_t bm_total = 0;
+    struct JobKey {
+        const double* raw;
+        const double* psf;
+        int K, n;
+        bool operator<(const JobKey& o) const {
+            return std::tie(raw, psf, K, n) < std::tie(o.raw, o.psf, o.K, o.n);
+        }
+    };
+    std::map<JobKey, size_t> job_of;                 // unique stamps -> job index
+    struct JobHost {
+        size_t raw_off, psf_off, coef_off;
+        bool has_raw;
+        int K, n;
+    };
+    std::vector<JobHost> jobs;
+    std::vector<size_t> patch_job(np);
+    for (size_t i = 0; i < np; ++i) {
+        const celeste_patch_spec& q = specs[i];
+        const int n = i / (size_t)S_tot;
+        const ImageDev& im = f->h_images[n];
+        if (q.H2 < 0 || q.W2 < 0 || q.K < 1 || q.K > MAX_K || !q.psf || q.grid_n < 3 || q.grid_n > PB_MAX_GRID) {
+            set_detail("patches_build: patch %zu malformed (H2=%d W2=%d K=%d grid_n=%d; K 1..%d, grid_n 3..%d)", i, q.H2, q.W2,
+                       q.K, q.grid_n, MAX_K, PB_MAX_GRID);
+            return (q.K > MAX_K || q.grid_n > PB_MAX_GRID) ? CELESTE_ERR_UNSUPPORTED : CELESTE_ERR_BAD_ARG;
+        }
+        if ((size_t)q.H2 * q.W2 > 0 && (q.bitmap_offset[0] < 0 || q.bitmap_offset[1] < 0 || q.bitmap_offset[0] + q.H2 > im.H ||
+                                        q.bitmap_offset[1] + q.W2 > im.W)) {
+            set_detail("patches_build: patch %zu: the box must be clamped to the image (clamp_box, imaged_sources.jl:10-14)", i);
+            return CELESTE_ERR_BAD_ARG;
+        }
+        bm_off[i] = bm_total;
+        bm_total += (size_t)q.H2 * q.W2;
+        psf_off[i] = hd.size();
+        hd.insert(hd.end(), q.psf, q.psf + 7 * (size_t)q.K);
+        const JobKey key{q.grid_psf, q.grid_psf ? nullptr : q.psf, q.grid_psf ? 0 : q.K, q.grid_n};
+        auto it = job_of.find(key);
+        if (it == job_of.end()) {
+            JobHost j;
+            j.has_raw = q.grid_psf != nullptr;
+            j.K = q.K;
+            j.n = q.grid_n;
+            j.psf_off = psf_off[i];
+            j.raw_off = hd.size();
+            if (j.has_raw) hd.insert(hd.end(), q.grid_psf, q.grid_psf + (size_t)q.grid_n * q.grid_n);
+            j.coef_off = 0;
+            job_of[key] = jobs.size();
+            patch_job[i] = jobs.size();
+            jobs.push_back(j);
+        } else {
+            patch_job[i] = it->second;
+        }
+    }
+    for (auto& j : jobs) {                            // coefficient arrays behind everything uploaded
+        j.coef_off = hd.size();
+        hd.resize(hd.size() + (size_t)(j.n + 2) * (j.n + 2), 0.0);
+    }
+    CUDA_TRY(f->bitmap_pool.alloc(std::max<size_t>(bm_total, 1)));
+    CUDA_TRY(f->double_pool.upload(hd));
+    f->h_patches.resize(np);
+    std::vector<BitmapJob> bjobs;
+    for (size_t i = 0; i < np; ++i) {
+        const celeste_patch_spec& q = specs[i];
+        const JobHost& j = jobs[patch_job[i]];
+        PatchDev d;
+        d.off_h = (int)q.bitmap_offset[0];
+        d.off_w = (int)q.bitmap_offset[1];
+        d.H2 = q.H2;
+        d.W2 = q.W2;
+        d.bitmap = f->bitmap_pool.p + bm_off[i];
+        for (int k = 0; k < 4; ++k) d.J[k] = q.wcs_jacobian[k];
+        d.wc[0] = q.world_center[0];
+        d.wc[1] = q.world_center[1];
+        d.pc[0] = q.pixel_center[0];
+        d.pc[1] = q.pixel_center[1];
+        d.K = q.K;
+        d.psf = f->double_pool.p + psf_off[i];
+        d.coefs = f->double_pool.p + j.coef_off;
+        d.n1 = d.n2 = j.n + 2;
+        f->h_patches[i] = d;
+        if ((size_t)q.H2 * q.W2 > 0)
+            bjobs.push_back(BitmapJob{(int)(i / (size_t)std::max(S_tot, 1)), d.off_h, d.off_w, d.H2, d.W2,
+                                      f->bitmap_pool.p + bm_off[i]});
+    }
+    std::vector<SplineJob> sjobs;
+    int max_n = 3;
+    for (const auto& j : jobs) {
+        sjobs.push_back(SplineJob{j.has_raw ? f->double_pool.p + j.raw_off : nullptr, f->double_pool.p + j.psf_off, j.K, j.n,
+                                  f->double_pool.p + j.coef_off});
+        max_n = std::max(max_n, j.n);
+    }
+    DevBuf<SplineJob> d_sjobs;
+    DevBuf<BitmapJob> d_bjobs;
+    CUDA_TRY(d_sjobs.upload(sjobs));
+    CUDA_TRY(d_bjobs.upload(bjobs));
+    if (!sjobs.empty()) {
+        const size_t sm = ((size_t)max_n * max_n + (size_t)(max_n + 2) * max_n) * sizeof(double);
+        spline_build_kernel<<<(unsigned)sjobs.size(), PB_THREADS, sm>>>(d_sjobs.p);
+        CUDA_TRY(cudaGetLastError());
+    }
+    if (!bjobs.empty()) {
+        bitmap_build_kernel<<<(unsigned)bjobs.size(), 128>>>(f->d_images.p, d_bjobs.p);
+        CUDA_TRY(cudaGetLastError());
+    }
+    CUDA_TRY(f->d_patches.upload(f->h_patches));
+    CUDA_TRY(cudaDeviceSynchronize());
+    f->S_tot = S_tot;
+    f->uniform_K = np ? specs[0].K : 0;
+    for (size_t i = 0; i < np; ++i)
+        if (specs[i].K != f->uniform_K) f->uniform_K = 0;
+    f->patch_generation++;
+    return CELESTE_OK;
+}
+
+int celeste_patch_readback(celeste_field* f, int32_t s, int32_t n, int32_t* dims_out, uint8_t* bitmap, double* coefs) {
+    if (!f || !dims_out || s < 0 || s >= f->S_tot || n < 0 || n >= f->N) {
+        set_detail("patch_readback: bad arguments (s=%d n=%d)", s, n);
+        return CELESTE_ERR_BAD_ARG;
+    }
+    CUDA_TRY(cudaSetDevice(f->device));
+    const PatchDev& p = f->h_patches[(size_t)s + (size_t)n * f->S_tot];
+    dims_out[0] = p.H2;
+    dims_out[1] = p.W2;
+    dims_out[2] = p.n1;
+    dims_out[3] = p.n2;
+    if (bitmap && (size_t)p.H2 * p.W2 > 0)
+        CUDA_TRY(cudaMemcpy(bitmap, p.bitmap, (size_t)p.H2 * p.W2, cudaMemcpyDeviceToHost));
+    if (coefs) CUDA_TRY(cudaMemcpy(coefs, p.coefs, (size_t)p.n1 * p.n2 * sizeof(double), cudaMemcpyDeviceToHost));
+    return CELESTE_OK;
+}
+
+int celeste_find_neighbors(celeste_field* f, int32_t* nbr_ptr, int32_t* nbr, int64_t capacity, int64_t* needed_out) {
+    if (!f || !nbr_ptr || capacity < 0 || (capacity > 0 && !nbr)) {
+        set_detail("find_neighbors: bad arguments");
+        return CELESTE_ERR_BAD_ARG;
+    }
+    CUDA_TRY(cudaSetDevice(f->device));
+    const int S = f->S_tot;
+    nbr_ptr[0] = 0;
+    if (needed_out) *needed_out = 0;
+    if (S == 0) return CELESTE_OK;
+    DevBuf<int> d_counts, d_ptr, d_out;
+    CUDA_TRY(d_counts.alloc(S));
+    const int wpb = 4, blocks = (S + wpb - 1) / wpb;
+    neighbor_kernel<<<blocks, wpb * 32>>>(f->d_patches.p, S, f->N, 0, d_counts.p, nullptr, nullptr);
+    CUDA_TRY(cudaGetLastError());
+    std::vector<int> counts(S), ptr(S + 1, 0);
+    CUDA_TRY(cudaMemcpy(counts.data(), d_counts.p, S * sizeof(int), cudaMemcpyDeviceToHost));
+    for (int t = 0; t < S; ++t) ptr[t + 1] = ptr[t] + counts[t];
+    for (int t = 0; t <= S; ++t) nbr_ptr[t] = ptr[t];
+    if (needed_out) *needed_out = ptr[S];
+    if (ptr[S] > capacity) {
+        set_detail("find_neighbors: %d entries needed, capacity %lld", ptr[S], (long long)capacity);
+        return CELESTE_ERR_BAD_ARG;
+    }
+    if (ptr[S] == 0) return CELESTE_OK;
+    CUDA_TRY(d_ptr.upload(ptr));
+    CUDA_TRY(d_out.alloc(ptr[S]));
+    neighbor_kernel<<<blocks, wpb * 32>>>(f->d_patches.p, S, f->N, 1, nullptr, d_ptr.p, d_out.p);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(nbr, d_out.p, (size_t)ptr[S] * sizeof(int), cudaMemcpyDeviceToHost));
     return CELESTE_OK;
 }
 

@@ -391,13 +391,28 @@ __global__ void __launch_bounds__(PIX_THREADS, MODE == 2 ? CELESTE_PIX_MINB_HESS
     // fixed-order block reduction: warp w reduces accumulators a = w, w + 4, ...
     const int warp = tid >> 5, lane = tid & 31;
     double* out = plan.partials + (size_t)blockIdx.x * NACC;
-    for (int a = warp; a < NACC; a += PIX_THREADS / 32) {
-        double s = 0.0;
+    // (all of a warp's accumulators in flight at once: the block is short, so this tail must not be a chain of
+    //  dependent shared-memory loads and shuffles per accumulator)
+    constexpr int NW = PIX_THREADS / 32, PER = (NACC + NW - 1) / NW;
+    double s[PER];
 #pragma unroll
-        for (int k = 0; k < PIX_THREADS / 32; ++k) s += acc[a * PIX_THREADS + lane + 32 * k];
+    for (int i = 0; i < PER; ++i) {
+        const int a = warp + NW * i;
+        s[i] = 0.0;
+        if (a < NACC) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) out[a] = s;
+            for (int k = 0; k < NW; ++k) s[i] += acc[a * PIX_THREADS + lane + 32 * k];
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int i = 0; i < PER; ++i) s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < PER; ++i)
+            if (warp + NW * i < NACC) out[warp + NW * i] = s[i];
     }
 }
 

@@ -116,9 +116,10 @@ class DeviceField:
     """Images + patch matrix of one inference box, resident in HBM (celeste_field)."""
 
     def __init__(self, images: Optional[Sequence[Image]], patches: Optional[np.ndarray], device: int = -1,
-                 flat_images=None, flat_patches=None):
+                 flat_images=None, flat_patches=None, specs: Optional[np.ndarray] = None):
         """Either (images, patches) model objects, or pre-flattened descriptor arrays
-        (`flat_images.arr/.N`, `flat_patches.arr/.S_tot/.N`, e.g. golden fixtures)."""
+        (`flat_images.arr/.N`, `flat_patches.arr/.S_tot/.N`, e.g. golden fixtures), or (images, specs): an
+        S x N matrix of model.PatchSpec from which the device builds bitmaps and PSF splines itself."""
         lib = _lib.load()
         ndev = C.c_int(0)
         _lib.check(lib.celeste_init(device, C.byref(ndev)))
@@ -129,7 +130,47 @@ class DeviceField:
         _lib.check(lib.celeste_field_create(C.byref(self._handle), self._flat_images.N, self._flat_images.arr))
         self._finalizer = weakref.finalize(self, lib.celeste_field_destroy, self._handle)
         self._row = {}
-        self.set_patches(patches, flat_patches)
+        if specs is not None:
+            self.build_patches(specs)
+        else:
+            self.set_patches(patches, flat_patches)
+
+    def build_patches(self, specs: np.ndarray):
+        """celeste_patches_build: ImagePatch construction on the device (imaged_sources.jl:80-117) from
+        model.PatchSpec objects; no bitmap / spline coefficient leaves or enters the host."""
+        from .flatten import FlatPatchSpecs
+        fs = FlatPatchSpecs(specs)
+        _lib.check(_lib.load().celeste_patches_build(self._handle, fs.S_tot, fs.N, fs.arr))
+        self.patches = None
+        self.specs = specs
+        self.S_tot = fs.S_tot
+        self._row = {id(specs[s, 0]): s for s in range(specs.shape[0])} if specs.shape[1] else {}
+
+    def patch_readback(self, s: int, n: int):
+        """(active_pixel_bitmap H2 x W2 bool, itp coefficient array n1 x n2) of patch (s, n) (0-based) as resident on
+        the device."""
+        lib = _lib.load()
+        dims = (C.c_int32 * 4)()
+        _lib.check(lib.celeste_patch_readback(self._handle, s, n, dims, None, None))
+        H2, W2, n1, n2 = dims
+        bm = np.zeros((H2, W2), dtype=np.uint8, order="F")
+        co = np.zeros((n1, n2), dtype=np.float64, order="F")
+        _lib.check(lib.celeste_patch_readback(self._handle, s, n, dims, bm.ctypes.data if bm.size else None, co.ctypes.data))
+        return bm.astype(bool), co
+
+    def find_all_neighbors(self) -> List[List[int]]:
+        """celeste_find_neighbors: model.find_all_neighbors (imaged_sources.jl:232-244) evaluated on the device's
+        patch matrix; 0-based indices."""
+        lib = _lib.load()
+        ptr = np.zeros(self.S_tot + 1, dtype=np.int32)
+        need = C.c_int64(0)
+        st = lib.celeste_find_neighbors(self._handle, ptr.ctypes.data, None, 0, C.byref(need))
+        if need.value == 0:
+            _lib.check(st)
+            return [[] for _ in range(self.S_tot)]
+        nbr = np.zeros(need.value, dtype=np.int32)
+        _lib.check(lib.celeste_find_neighbors(self._handle, ptr.ctypes.data, nbr.ctypes.data, need.value, C.byref(need)))
+        return [nbr[ptr[t]:ptr[t + 1]].tolist() for t in range(self.S_tot)]
 
     def set_patches(self, patches: Optional[np.ndarray], flat_patches=None):
         lib = _lib.load()

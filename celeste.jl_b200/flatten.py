@@ -10,7 +10,7 @@ from typing import List, Sequence
 
 import numpy as np
 
-from ._lib import celeste_image, celeste_patch
+from ._lib import celeste_image, celeste_patch, celeste_patch_spec
 from .model import Image, ImagePatch
 
 
@@ -67,6 +67,45 @@ class FlatPatches:
                 a.psf = psf.ctypes.data
                 a.itp_coefs = coefs.ctypes.data
                 a.itp_dims[0], a.itp_dims[1] = coefs.shape
+
+
+class FlatPatchSpecs:
+    """S_tot x N PatchSpec matrix as a column-major `celeste_patch_spec` array (celeste_patches_build)."""
+
+    def __init__(self, specs: np.ndarray):
+        assert specs.ndim == 2
+        self.S_tot, self.N = specs.shape
+        self.arr = (celeste_patch_spec * max(self.S_tot * self.N, 1))()
+        self._keep = []
+        stamps = {}                                           # id(array) -> contiguous copy (identical pointers dedupe)
+        psfs = {}
+        for n in range(self.N):
+            for s in range(self.S_tot):
+                p = specs[s, n]
+                a = self.arr[s + n * self.S_tot]
+                key = id(p.psf)
+                if key not in psfs:
+                    psfs[key] = np.ascontiguousarray(np.concatenate([pc.flat7() for pc in p.psf]), dtype=np.float64)
+                psf = psfs[key]
+                a.bitmap_offset[0] = int(p.bitmap_offset[0])
+                a.bitmap_offset[1] = int(p.bitmap_offset[1])
+                a.H2, a.W2 = int(p.H2), int(p.W2)
+                J = np.asarray(p.wcs_jacobian, dtype=np.float64)
+                a.wcs_jacobian[0], a.wcs_jacobian[1] = J[0, 0], J[1, 0]
+                a.wcs_jacobian[2], a.wcs_jacobian[3] = J[0, 1], J[1, 1]
+                a.world_center[0], a.world_center[1] = p.world_center
+                a.pixel_center[0], a.pixel_center[1] = p.pixel_center
+                a.K = len(p.psf)
+                a.grid_n = int(p.grid_n)
+                a.psf = psf.ctypes.data
+                if p.grid_psf is not None:
+                    k2 = id(p.grid_psf)
+                    if k2 not in stamps:
+                        stamps[k2] = np.asfortranarray(p.grid_psf, dtype=np.float64)
+                    a.grid_psf = stamps[k2].ctypes.data
+                else:
+                    a.grid_psf = None
+        self._keep += list(stamps.values()) + list(psfs.values())
 
 
 def csr_tasks(tasks):

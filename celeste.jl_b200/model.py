@@ -297,6 +297,42 @@ class ImagePatch:
         return self.active_pixel_bitmap.shape
 
 
+class PatchSpec:
+    """What the host contributes to ImagePatch(img, box) when the device builds the rest
+    (celeste_patches_build): the clamped box, the WCS linearisation at its centre (imaged_sources.jl:83-90) and
+    where the PSF stamp comes from -- `grid_psf` = img.psfmap(centre) raw, or None to rasterise img.psf on the
+    device (render_psf).  No bitmap, no spline coefficients."""
+
+    def __init__(self, img: Image, box: Box, raw_stamp: bool = True):
+        box = clamp_box(box, (img.H, img.W))
+        self.box = box
+        self.pixel_center = np.array([(box[0][0] + box[0][1]) / 2, (box[1][0] + box[1][1]) / 2])
+        self.world_center = img.wcs.pix_to_world(self.pixel_center)
+        self.wcs_jacobian = np.array(img.wcs.A, dtype=np.float64)
+        self.psf = img.psf
+        self.bitmap_offset = np.array([box[0][0] - 1, box[1][0] - 1], dtype=np.int64)
+        self.H2 = max(box[0][1] - box[0][0] + 1, 0)
+        self.W2 = max(box[1][1] - box[1][0] + 1, 0)
+        self.grid_psf = img.psf_stamp if raw_stamp else None       # ConstantPSFMap: one array per image, shared
+        self.grid_n = img.psf_stamp.shape[0]
+
+
+def get_sky_patch_specs(images: Sequence[Image], catalog: Sequence[CatalogEntry], radius_override_pix=float("nan"),
+                        raw_stamp: bool = True):
+    """get_sky_patches (imaged_sources.jl:165-183) up to the point where pixels / the PSF stamp are touched:
+    S x N object array of PatchSpec for DeviceField.build_patches."""
+    S, N = len(catalog), len(images)
+    specs = np.empty((S, N), dtype=object)
+    for n in range(N):
+        for s in range(S):
+            if math.isnan(radius_override_pix):
+                box = box_from_catalog(images[n], catalog[s], width_scale=1.2)
+            else:
+                box = box_around_point(images[n].wcs, catalog[s].pos, radius_override_pix)
+            specs[s, n] = PatchSpec(images[n], box, raw_stamp)
+    return specs
+
+
 def box_around_point(wcs: AffineWCS, world_center, pixel_radius) -> Box:
     """imaged_sources.jl:126-136."""
     pc = wcs.world_to_pix(world_center)

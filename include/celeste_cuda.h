@@ -242,6 +242,43 @@ int celeste_set_chunk_pixels(int32_t chunk_pixels);
 void celeste_field_destroy(celeste_field* f);
 
 /*
+ * Row f.4, ImagePatch construction on the device: what the ImagePatch(img, box) constructor
+ * (src/model/imaged_sources.jl:80-117) computes from pixels and from the PSF stamp,
+ *     active_pixel_bitmap = !isnan(pixels in box)  (:92-95),
+ *     itp_psf = cubic B-spline of softpluslike(normalise(max(psfmap(center), 0) + 1e-6))  (:97-107),
+ * built here from the images already resident in the field.  The host keeps the box arithmetic and the WCS
+ * linearisation (clamp_box :10-14, pixel_center / world_center / pixel_world_jacobian :86-90; WCS.jl is a host
+ * library) and passes them per patch.  `grid_psf`: the raw psfmap stamp at the patch centre (grid_n x grid_n doubles,
+ * column-major, HOST pointer; identical pointers are processed once) or NULL to rasterise the K-component mixture
+ * `psf` (render_psf, src/model/psf_model.jl:61-75).  3 <= grid_n <= 54 (51 in the reference).
+ * Same effect as celeste_patches_set with host-built bitmaps and coefficient arrays.
+ */
+typedef struct celeste_patch_spec {
+    int64_t bitmap_offset[2];   /* first(box[d]) - 1 of the clamped box                       */
+    int32_t H2, W2;             /* size of the clamped box (0 allowed)                        */
+    double wcs_jacobian[4];     /* column-major 2 x 2                                         */
+    double world_center[2];
+    double pixel_center[2];
+    int32_t K;
+    int32_t grid_n;
+    const double* psf;          /* K x 7: alphaBar, xiBar[2], tauBar[4] (column-major)        */
+    const double* grid_psf;     /* grid_n x grid_n raw stamp, or NULL                         */
+} celeste_patch_spec;
+int celeste_patches_build(celeste_field* f, int32_t S_tot, int32_t N, const celeste_patch_spec* specs /* S_tot x N col-major */);
+
+/* Inspection: copy patch (s, n) (0-based) back to the host.  dims_out = {H2, W2, n1, n2}; bitmap (H2*W2 bytes) and
+ * coefs (n1*n2 doubles) may be NULL to query the sizes only. */
+int celeste_patch_readback(celeste_field* f, int32_t s, int32_t n, int32_t* dims_out, uint8_t* bitmap, double* coefs);
+
+/*
+ * find_neighbors (src/model/imaged_sources.jl:232-244) for every source of the field's patch matrix at once:
+ * nbr_ptr (S_tot + 1) and nbr (0-based source indices, ascending per target) in CSR form.  If `capacity` is too
+ * small nothing is written to nbr, *needed_out receives the required length and CELESTE_ERR_BAD_ARG is returned
+ * (call with capacity 0 first to size the buffer).
+ */
+int celeste_find_neighbors(celeste_field* f, int32_t* nbr_ptr, int32_t* nbr, int64_t capacity, int64_t* needed_out);
+
+/*
  * Row f.4, the value-only full-image render: fill_celeste_expectation! (bin/write_celeste_expectation.jl:111-156),
  * which calls add_pixel_term! (elbo_objective.jl:330-392) in value mode on EVERY pixel of every image of the
  * field.  For image n (n = 0..N-1), out[n] (HOST, H x W doubles, column-major like the image) receives

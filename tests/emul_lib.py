@@ -23,6 +23,9 @@ def load():
         _lib.emul_elbo_batch.argtypes = [i32, vp, i32, vp, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, i32]
         _lib.emul_tr_subproblem.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp]
         _lib.emul_newton_step.argtypes = [i32, i32, vp]
+        _lib.emul_spline_build.argtypes = [i32, vp, i32, vp, vp]
+        _lib.emul_bitmap_build.argtypes = [i32, i32, vp, i32, i32, i32, i32, vp]
+        _lib.emul_find_neighbors.argtypes = [i32, i32, vp, vp, vp]
         _lib.emul_render_expectation.argtypes = [i32, vp, i32, vp, i32, vp, vp, vp]
     return _lib
 
@@ -78,3 +81,36 @@ def render_expectation(images, patches, rows, vp):
     from oracle_lib import _render
     fi, fp = FlatImages(images), FlatPatches(patches)
     return _render(load().emul_render_expectation, fi, fp, rows, vp)
+
+
+def spline_build(grid_n, raw=None, psf=None):
+    """spline_build_kernel under emulation: raw stamp (n x n) or PSF mixture (list of PsfComponent) -> (n+2)^2 coefficients."""
+    coefs = np.zeros((grid_n + 2, grid_n + 2), order="F")
+    rawa = np.asfortranarray(raw, dtype=np.float64) if raw is not None else None
+    psfa = np.ascontiguousarray(np.concatenate([pc.flat7() for pc in psf]), dtype=np.float64) if psf is not None else np.zeros(7)
+    load().emul_spline_build(grid_n, rawa.ctypes.data if rawa is not None else None, len(psf) if psf is not None else 0,
+                             psfa.ctypes.data, coefs.ctypes.data)
+    return coefs
+
+
+def bitmap_build(pixels, off_h, off_w, H2, W2):
+    px = np.asfortranarray(pixels, dtype=np.float32)
+    bm = np.zeros((H2, W2), dtype=np.uint8, order="F")
+    load().emul_bitmap_build(px.shape[0], px.shape[1], px.ctypes.data, off_h, off_w, H2, W2, bm.ctypes.data if bm.size else None)
+    return bm.astype(bool)
+
+
+def find_all_neighbors(patches):
+    """neighbor_kernel under emulation on an S x N matrix of objects with bitmap_offset and shape / (H2, W2)."""
+    S, N = patches.shape
+    boxes = np.zeros((N, S, 4), dtype=np.int32)
+    for n in range(N):
+        for s in range(S):
+            p = patches[s, n]
+            H2, W2 = (p.H2, p.W2) if hasattr(p, "H2") else p.active_pixel_bitmap.shape
+            boxes[n, s] = [p.bitmap_offset[0], p.bitmap_offset[1], H2, W2]
+    ptr = np.zeros(S + 1, dtype=np.int32)
+    need = load().emul_find_neighbors(S, N, boxes.ctypes.data, ptr.ctypes.data, None)
+    nbr = np.zeros(max(need, 1), dtype=np.int32)
+    load().emul_find_neighbors(S, N, boxes.ctypes.data, ptr.ctypes.data, nbr.ctypes.data)
+    return [nbr[ptr[t]:ptr[t + 1]].tolist() for t in range(S)]

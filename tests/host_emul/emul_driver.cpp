@@ -7,6 +7,7 @@
 #include "../../include/celeste_cuda.h"
 #include "../../celeste.jl_b200/csrc/celeste_kernels.cuh"
 #include "../../celeste.jl_b200/csrc/maximize_kernels.cuh"
+#include "../../celeste.jl_b200/csrc/patch_kernels.cuh"
 
 using namespace celeste;
 
@@ -307,4 +308,43 @@ extern "C" int emul_render_expectation(int32_t N, const celeste_image* imgs, int
             cuda_emul::launch(render_kernel<0>, (int)tiles.size(), RENDER_THREADS, 0, pd, tiles.data(), tile_slots.data(), out);
     }
     return 0;
+}
+
+// patch_kernels.cuh under emulation -----------------------------------------------------------------------------
+extern "C" int emul_spline_build(int32_t grid_n, const double* raw, int32_t K, const double* psf, double* coefs) {
+    SplineJob job{raw, psf, K, grid_n, coefs};
+    const size_t sm = ((size_t)grid_n * grid_n + (size_t)(grid_n + 2) * grid_n) * sizeof(double);
+    cuda_emul::launch(spline_build_kernel, 1, PB_THREADS, sm, (const SplineJob*)&job);
+    return 0;
+}
+
+extern "C" int emul_bitmap_build(int32_t H, int32_t W, const float* pixels, int32_t off_h, int32_t off_w, int32_t H2,
+                                 int32_t W2, uint8_t* bitmap) {
+    ImageDev img{H, W, 1, pixels, nullptr, nullptr, nullptr};
+    BitmapJob job{0, off_h, off_w, H2, W2, bitmap};
+    cuda_emul::launch(bitmap_build_kernel, 1, 128, 0, (const ImageDev*)&img, (const BitmapJob*)&job);
+    return 0;
+}
+
+// boxes: S x N x 4 ints (off_h, off_w, H2, W2), index (s + n * S) * 4.  Returns the CSR length; nbr may be null.
+extern "C" int emul_find_neighbors(int32_t S, int32_t N, const int32_t* boxes, int32_t* nbr_ptr, int32_t* nbr) {
+    std::vector<PatchDev> pdv((size_t)S * N);
+    for (size_t i = 0; i < pdv.size(); ++i) {
+        PatchDev p{};
+        p.off_h = boxes[4 * i];
+        p.off_w = boxes[4 * i + 1];
+        p.H2 = boxes[4 * i + 2];
+        p.W2 = boxes[4 * i + 3];
+        pdv[i] = p;
+    }
+    std::vector<int> counts(S, 0), ptr(S + 1, 0);
+    const int wpb = 4, blocks = (S + wpb - 1) / wpb;
+    if (S > 0) cuda_emul::launch(neighbor_kernel, blocks, wpb * 32, 0, (const PatchDev*)pdv.data(), S, N, 0, counts.data(),
+                                 (const int*)nullptr, (int*)nullptr);
+    for (int t = 0; t < S; ++t) ptr[t + 1] = ptr[t] + counts[t];
+    for (int t = 0; t <= S; ++t) nbr_ptr[t] = ptr[t];
+    if (nbr && ptr[S] > 0)
+        cuda_emul::launch(neighbor_kernel, blocks, wpb * 32, 0, (const PatchDev*)pdv.data(), S, N, 1, (int*)nullptr,
+                          (const int*)ptr.data(), nbr);
+    return ptr[S];
 }

@@ -73,3 +73,49 @@ def test_emulated_render_kernel_matches_oracle(name):
         cases.assert_render_parity(ref, got, name + " subset")
     empty = emul_lib.render_expectation(images, patches, rows[:0], vp[:, :0])
     assert all(not e.any() for e in empty)
+
+
+def test_emulated_patch_construction_kernels():
+    """Row f.4, ImagePatch construction on the device (csrc/patch_kernels.cuh) against the host model
+    (model.py: render_psf / psf_spline_coefs / ImagePatch / find_all_neighbors, imaged_sources.jl:80-117,232-244)."""
+    from celeste_jl_b200 import model
+    from celeste_jl_b200 import synthetic
+    rng = np.random.default_rng(3)
+    # spline of a raw stamp, incl. negative entries (max(., 0)) and a non-51 size
+    for n in (51, 21, 4):
+        raw = rng.normal(0.2, 1.0, (n, n)) ** 2 * np.exp(-0.1 * ((np.arange(n)[:, None] - n / 2) ** 2 + (np.arange(n)[None, :] - n / 2) ** 2))
+        raw[rng.random((n, n)) < 0.05] = -0.3
+        want = model.psf_spline_coefs(raw)
+        got = emul_lib.spline_build(n, raw=raw)
+        assert np.allclose(got, want, rtol=1e-12, atol=1e-12 * np.abs(want).max())
+    # spline from the mixture itself (render_psf on the device), K = 1, 2, 3
+    images, patches, _ = cases.get("psf_k3")
+    for psf in (images[0].psf, cases.get("two_body")[0][0].psf, cases.get("psf_k1")[0][0].psf):
+        want = model.psf_spline_coefs(model.render_psf(psf, (51, 51)))
+        got = emul_lib.spline_build(51, psf=psf)
+        assert np.allclose(got, want, rtol=1e-11, atol=1e-12 * np.abs(want).max())
+    # the interpolant reproduces the (transformed) grid at the grid points (SURVEY 8c must-hold self-check)
+    stamp = model.render_psf(images[0].psf, (51, 51))
+    g = np.maximum(stamp, 0) + 1e-6
+    g = model.softpluslike(g / g.sum())
+    co = emul_lib.spline_build(51, raw=stamp)
+    rec = (co[:-2, :-2] + co[2:, :-2] + co[:-2, 2:] + co[2:, 2:]) / 36 + (co[1:-1, :-2] + co[1:-1, 2:] + co[:-2, 1:-1] + co[2:, 1:-1]) / 9 \
+        + co[1:-1, 1:-1] * 4 / 9
+    assert np.allclose(rec, g, rtol=1e-11, atol=1e-11)
+    # bitmaps
+    nan_seen = False
+    images, patches, _ = cases.get("masked")
+    for s in range(patches.shape[0]):
+        for n in range(patches.shape[1]):
+            p = patches[s, n]
+            H2, W2 = p.active_pixel_bitmap.shape
+            o = p.bitmap_offset
+            got = emul_lib.bitmap_build(images[n].pixels, int(o[0]), int(o[1]), H2, W2)
+            want = ~np.isnan(images[n].pixels[o[0]:o[0] + H2, o[1]:o[1] + W2])      # imaged_sources.jl:94-95
+            assert np.array_equal(got, want)
+            nan_seen = nan_seen or (~want).any()
+    assert nan_seen
+    # neighbours
+    for name in ("clipped_and_empty", "crowded", "small_field"):
+        _, patches, _ = cases.get(name)
+        assert emul_lib.find_all_neighbors(patches) == model.find_all_neighbors(patches)

@@ -461,3 +461,71 @@ def test_render_full_size_sample_and_properties(cj, field1000):
             o = p.bitmap_offset
             cover[max(o[0], 0):o[0] + H2, max(o[1], 0):o[1] + W2 - 1] = True
         assert not full[n][~cover].any() and full[n][cover].any()
+
+
+@pytest.mark.parametrize("name,raw", [("clipped_and_empty", True), ("psf_k3", False), ("config2_rotated_wcs", False),
+                                      ("two_body", True), ("small_field", True)])
+def test_device_built_patches_match_host_patches(cj, name, raw):
+    """Row f.4: celeste_patches_build (ImagePatch construction on the device, imaged_sources.jl:80-117) against the
+    host-built patch matrix: identical bitmaps, spline coefficients to rounding, the same ELBO / gradient / Hessian,
+    and celeste_find_neighbors == find_neighbors (imaged_sources.jl:232-244)."""
+    from celeste_jl_b200 import model
+    images, patches, tasks = cases.get(name)
+    S, N = patches.shape
+    specs = np.empty((S, N), dtype=object)
+    for s in range(S):
+        for n in range(N):
+            specs[s, n] = model.PatchSpec(images[n], patches[s, n].box, raw_stamp=raw)
+    fd = cj.DeviceField(images, None, specs=specs)
+    fh = cj.DeviceField(images, patches)
+    for s in range(S):
+        for n in range(N):
+            p = patches[s, n]
+            bm, co = fd.patch_readback(s, n)
+            assert np.array_equal(bm, p.active_pixel_bitmap)
+            assert np.allclose(co, p.itp_coefs, rtol=1e-11, atol=1e-12 * np.abs(p.itp_coefs).max())
+            bm2, co2 = fh.patch_readback(s, n)
+            assert np.array_equal(bm2, p.active_pixel_bitmap) and np.array_equal(co2, p.itp_coefs)
+    got = fd.elbo_batch(tasks, mode=2)
+    ref = fh.elbo_batch(tasks, mode=2)
+    cases.assert_parity(ref, got, 2, name + " device-built patches")
+    nb = model.find_all_neighbors(patches)
+    assert fd.find_all_neighbors() == nb and fh.find_all_neighbors() == nb
+
+
+def test_device_built_bitmaps_follow_nan_pixels(cj):
+    """active_pixel_bitmap = !isnan(pixels) (imaged_sources.jl:92-95) from the images resident on the device."""
+    from celeste_jl_b200 import model
+    images, patches, _ = cases.get("masked")
+    S, N = patches.shape
+    specs = np.empty((S, N), dtype=object)
+    for s in range(S):
+        for n in range(N):
+            specs[s, n] = model.PatchSpec(images[n], patches[s, n].box)
+    fd = cj.DeviceField(images, None, specs=specs)
+    seen = False
+    for s in range(S):
+        for n in range(N):
+            o, (H2, W2) = patches[s, n].bitmap_offset, patches[s, n].active_pixel_bitmap.shape
+            want = ~np.isnan(images[n].pixels[o[0]:o[0] + H2, o[1]:o[1] + W2])
+            bm, _ = fd.patch_readback(s, n)
+            assert np.array_equal(bm, want)
+            seen = seen or (~want).any()
+    assert seen
+
+
+def test_patches_build_rejects_unclamped_boxes_and_big_stamps(cj):
+    from celeste_jl_b200 import model, _lib
+    images, patches, _ = cases.get("two_body")
+    specs = np.empty((1, len(images)), dtype=object)
+    for n in range(len(images)):
+        specs[0, n] = model.PatchSpec(images[n], patches[0, n].box)
+    specs[0, 0].H2 = images[0].H + 5                      # reaches outside the image
+    with pytest.raises(_lib.CelesteError) as e:
+        cj.DeviceField(images, None, specs=specs)
+    assert e.value.status == _lib.CELESTE_ERR_BAD_ARG
+    specs[0, 0] = model.PatchSpec(images[0], patches[0, 0].box)
+    specs[0, 0].grid_n = 99
+    with pytest.raises(_lib.CelesteError) as e:
+        cj.DeviceField(images, None, specs=specs)
+    assert e.value.status == _lib.CELESTE_ERR_UNSUPPORTED
