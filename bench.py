@@ -50,9 +50,23 @@ def parse():
 
 
 def build_stripe(n_fields, n_sources, device):
+    """The synthetic stripe.  CELESTE_STRIPE_CACHE=<dir> keeps a pickle of it between processes of one
+    tuning session (same seeds, same arrays; nothing about the measured path changes)."""
+    import pickle
     from celeste_jl_b200 import synthetic
-    return [synthetic.FieldDataset(n_sources, H=2048, W=1489, seed=42 + f, pixel_seed=1 + f, device=device)
-            for f in range(n_fields)]
+    cache = os.environ.get("CELESTE_STRIPE_CACHE")
+    path = os.path.join(cache, f"stripe_{n_fields}x{n_sources}.pkl") if cache else None
+    if path and os.path.exists(path):
+        with open(path, "rb") as f:
+            return pickle.load(f)
+    stripe = [synthetic.FieldDataset(n_sources, H=2048, W=1489, seed=42 + f, pixel_seed=1 + f, device=device)
+              for f in range(n_fields)]
+    if path and int(os.environ.get("RANK", "0")) == 0:
+        os.makedirs(cache, exist_ok=True)
+        with open(path + ".tmp", "wb") as f:
+            pickle.dump(stripe, f, protocol=4)
+        os.replace(path + ".tmp", path)
+    return stripe
 
 
 def shard_tasks(ds, rank, world):
@@ -357,12 +371,16 @@ def main():
     grad = measure(1, args.steps, args.warmup, True)
     hess = None if args.no_hessian else measure(2, max(3, args.steps // 2), args.warmup, False)
 
+    def kernel_key(mode):
+        name = plans[0].kernel_name(mode) if plans else ("march_kernel" if mode < 2 else "pixel_kernel")
+        return f"{name}<{mode}>"
+
     def roofline(m, mode):
         flop = m["active"] * F_ACTIVE[mode] + m["inactive"] * F_INACTIVE
         ach = flop / (m["pix_ms"] * 1e-3) / 1e12          # aggregate over ranks (flop summed, time = max over ranks)
         r = {"bound": "fp64", "achieved": ach, "peak": peak * world, "unit": "TFLOP/s", "frac": ach / (peak * world),
              "peak_per_gpu": peak,
-             "traffic": None, "kernel": ("task_kernel<1>" if mode == 1 else "pixel_kernel<2>"), "kernel_ms_per_step": m["pix_ms"],
+             "traffic": None, "kernel": kernel_key(mode), "kernel_ms_per_step": m["pix_ms"],
              "kernel_share_of_step": m["pix_ms"] / m["ms"],
              "algorithmic_flop_per_step": flop, "pixel_visits_active": m["active"], "pixel_visits_inactive": m["inactive"],
              "peak_source": "measured live: celeste_fp64_peak (register DFMA chain); nominal 37 TFLOP/s",
@@ -373,7 +391,7 @@ def main():
         prof = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(prof):
             try:
-                t = json.load(open(prof)).get("task_kernel<1>" if mode == 1 else "pixel_kernel<2>")
+                t = json.load(open(prof)).get(kernel_key(mode))
                 if t and t.get("sources") == int(total_sources):
                     r["traffic"] = t["dram_bytes_per_launch"] / world
                     r["traffic_source"] = t

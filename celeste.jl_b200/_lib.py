@@ -67,6 +67,7 @@ EXPORTS = [
     "celeste_fp64_peak", "celeste_plan_enable_timing", "celeste_plan_kernel_times", "celeste_set_chunk_pixels",
     "celeste_plan_create_multi", "celeste_tr_subproblem", "celeste_plan_set_task_mask", "celeste_newton_step",
     "celeste_render_expectation", "celeste_patches_build", "celeste_patch_readback", "celeste_find_neighbors",
+    "celeste_plan_kernel_name",
 ]
 
 
@@ -107,6 +108,7 @@ def load():
     lib.celeste_plan_destroy.argtypes = [vp]
     lib.celeste_plan_destroy.restype = None
     lib.celeste_plan_launches.argtypes = [vp, i32]
+    lib.celeste_plan_kernel_name.argtypes = [vp, i32, C.c_char_p]
     lib.celeste_elbo_plan_device.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, vp]
     lib.celeste_elbo_plan_host.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
     lib.celeste_field_destroy.argtypes = [vp]

@@ -21,6 +21,7 @@
 
 #include "../../include/celeste_cuda.h"
 #include "celeste_kernels.cuh"
+#include "march_kernels.cuh"
 #include "maximize_kernels.cuh"
 #include "patch_kernels.cuh"
 
@@ -138,6 +139,8 @@ int configure_kernels() {
     CEL_TCFG(1, 2, false);
     CEL_TCFG(1, 2, true);
 #undef CEL_TCFG
+    CUDA_TRY(cudaFuncSetAttribute(march_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)march_smem_bytes()));
+    CUDA_TRY(cudaFuncSetAttribute(march_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)march_smem_bytes()));
     {
         const int psm = (int)(((size_t)NPAIR_ACC * PAIR_THREADS + 2 * (size_t)MAX_COMPS * COMP_STRIDE) * sizeof(double));
         CUDA_TRY(cudaFuncSetAttribute(pair_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, psm));
@@ -195,6 +198,12 @@ struct celeste_plan {
     DevBuf<TaskHdr> taskmap;          // value / gradient modes: one block per (sub, image group)
     DevBuf<int> task_chunk_ptr;       // partial ranges of task_kernel: TASK_WARPS per (sub, image)
     int n_taskblocks = 0;
+    // march_kernel (value / gradient, Sa = 1, K = 2): one block per (sub, group of MARCH_NIMG images)
+    DevBuf<TaskHdr> marchmap;
+    DevBuf<long long> bg_ptr;
+    DevBuf<double> bg;
+    int n_marchblocks = 0, march_groups = 0;
+    bool use_march = false;
     DevBuf<PairHdr> pairmap;
     DevBuf<double> slotimg, slotbr, partials, pair_partials;
     int n_subs = 0, n_pairs = 0;
@@ -729,6 +738,36 @@ int celeste_plan_create_multi(int32_t n_fields, celeste_field* const* fields, ce
         taskmap.swap(sorted);
     }
     pl->n_taskblocks = (int)taskmap.size();
+    // march_kernel serves the production shape (Sa = 1 everywhere, K = 2); CELESTE_GRAD_KERNEL=task keeps task_kernel
+    // (kernel-tuning / A-B knob)
+    {
+        const char* env = std::getenv("CELESTE_GRAD_KERNEL");
+        const bool want = !(env && std::strcmp(env, "task") == 0);
+        pl->use_march = want && pl->uniform_K == 2 && n_subs == n_tasks;
+    }
+    if (pl->use_march) {
+        const int ngroups = (pl->N + MARCH_NIMG - 1) / MARCH_NIMG;
+        pl->march_groups = ngroups;
+        static_assert(TASK_NIMG == MARCH_NIMG, "march_kernel reuses task_kernel's (sub, image group) blocks");
+        const std::vector<TaskHdr>& mm = taskmap;   // same blocks, same heaviest-first order
+        std::vector<long long> bg_ptr((size_t)n_subs * pl->N, -1);
+        long long bg_total = 0;
+        for (int u = 0; u < n_subs; ++u) {
+            const int t = sub_task[u];
+            if (task_ptr[t + 1] - task_ptr[t] < 2) continue;
+            const celeste_field* f = fields[tfield[t]];
+            for (int n = 0; n < pl->N; ++n) {
+                const PatchDev& pa = f->h_patches[(size_t)src_row[sub_slot[u]] + (size_t)n * f->S_tot];
+                if (pa.H2 <= 0 || pa.W2 <= 0) continue;
+                bg_ptr[(size_t)u * pl->N + n] = bg_total;
+                bg_total += 2LL * pa.H2 * pa.W2;
+            }
+        }
+        pl->n_marchblocks = (int)mm.size();
+        CUDA_TRY(pl->marchmap.upload(mm));
+        CUDA_TRY(pl->bg_ptr.upload(bg_ptr));
+        CUDA_TRY(pl->bg.alloc((size_t)bg_total));
+    }
     std::vector<int> task_chunk_ptr((size_t)n_subs * pl->N + 1);
     for (size_t i = 0; i < task_chunk_ptr.size(); ++i) task_chunk_ptr[i] = (int)(i * TASK_WARPS);
     CUDA_TRY(pl->taskmap.upload(taskmap));
@@ -750,8 +789,8 @@ int celeste_plan_create_multi(int32_t n_fields, celeste_field* const* fields, ce
     CUDA_TRY(pl->blockmap.upload(blockmap));
     CUDA_TRY(pl->slotimg.alloc((size_t)n_slots * pl->N * SLOTIMG_STRIDE));
     CUDA_TRY(pl->slotbr.alloc((size_t)n_slots * SLOTBR_STRIDE));
-    CUDA_TRY(pl->partials.alloc(std::max((size_t)pl->n_blocks * NACC_MODE2,
-                                          (size_t)n_subs * pl->N * TASK_WARPS * NACC_MODE1)));
+    CUDA_TRY(pl->partials.alloc(std::max({(size_t)pl->n_blocks * NACC_MODE2, (size_t)n_subs * pl->N * TASK_WARPS * NACC_MODE1,
+                                           (size_t)n_subs * pl->march_groups * NT_ACC})));
     *out = pl.release();
     return CELESTE_OK;
 }
@@ -800,6 +839,12 @@ int celeste_plan_launches(const celeste_plan* p, int32_t mode) {
     return (p->n_blocks > 0 ? 3 : 2) + ((mode == 2 && p->n_pairs > 0) ? 1 : 0);   // setup, pixel, [pair,] epilogue
 }
 
+int celeste_plan_kernel_name(const celeste_plan* p, int32_t mode, char* buf) {
+    if (!p || !buf || mode < 0 || mode > 2) return CELESTE_ERR_BAD_ARG;
+    std::snprintf(buf, 32, "%s", mode == 2 ? "pixel_kernel" : (p->use_march ? "march_kernel" : "task_kernel"));
+    return CELESTE_OK;
+}
+
 }  // extern "C"
 
 static PlanDev plan_dev(const celeste_plan* p) {
@@ -827,6 +872,8 @@ static PlanDev plan_dev(const celeste_plan* p) {
     d.slotimg = p->slotimg.p;
     d.slotbr = p->slotbr.p;
     d.partials = p->partials.p;
+    d.bg_ptr = p->bg_ptr.p;
+    d.bg = p->bg.p;
     return d;
 }
 
@@ -840,6 +887,16 @@ static int launch_mode(celeste_plan* p, const double* vp_dev, double* v, double*
     setup_kernel<<<sblocks, 256, 0, st>>>(pd, vp_dev);
     if (p->timing) CUDA_TRY(cudaEventRecord(p->ev[1], st));
     if constexpr (MODE <= 1) {
+        if (p->use_march) {
+            // value / gradient, production shape: row walks with the exp recurrence (march_kernels.cuh)
+            if (p->n_marchblocks > 0)
+                march_kernel<MODE><<<p->n_marchblocks, MARCH_THREADS, march_smem_bytes(), st>>>(pd, p->marchmap.p, p->march_groups);
+            if (p->timing) CUDA_TRY(cudaEventRecord(p->ev[2], st));
+            march_epilogue_kernel<MODE><<<p->n_tasks, MEPI_THREADS, 0, st>>>(pd, vp_dev, p->march_groups, v, d, counters, flags);
+            if (p->timing) CUDA_TRY(cudaEventRecord(p->ev[3], st));
+            CUDA_TRY(cudaGetLastError());
+            return CELESTE_OK;
+        }
         // value / gradient: task-level blocks, one partial per (sub, image, warp)
         PlanDev pt = pd;
         pt.chunk_ptr = p->task_chunk_ptr.p;

@@ -50,7 +50,7 @@ struct PatchDev {
 };
 
 // per (task source slot, image) scratch written by setup_kernel
-constexpr int SLOTIMG_STRIDE = MAX_COMPS * COMP_STRIDE + 2;   // comps + m_pos
+constexpr int SLOTIMG_STRIDE = MAX_COMPS * COMP_STRIDE + 2 + MAX_COMPS;   // comps + m_pos + exp(-L22) per component
 // per slot: El[2][5], Ell[2][5], a[2], theta
 constexpr int SLOTBR_STRIDE = 24;
 
@@ -102,6 +102,8 @@ struct PlanDev {
     double* slotimg;         // n_slots * N * SLOTIMG_STRIDE
     double* slotbr;          // n_slots * SLOTBR_STRIDE
     double* partials;        // n_blocks * NACC
+    const long long* bg_ptr; // n_subs * N: offset of the (E_bg, V_bg) planes of (sub, image) in bg, -1 if the task has no neighbour
+    double* bg;              // march_kernel's per-task background buffer
 };
 
 
@@ -147,6 +149,7 @@ __global__ void setup_kernel(PlanDev plan, const double* __restrict__ vp) {
             const int j = c / p.K, k = c % p.K;
             make_component(p.psf + 7 * k, c_proto_eta[j], c_proto_nu[j], m1, m2, vs[3], vs[4], vs[5],
                            rec + c * COMP_STRIDE);
+            rec[MAX_COMPS * COMP_STRIDE + 2 + c] = exp(-rec[c * COMP_STRIDE + 4]);   // column ratio of march_kernel
         }
         if (c == 0) {
             rec[MAX_COMPS * COMP_STRIDE + 0] = m1;

@@ -1,0 +1,681 @@
+// march_kernels.cuh -- the value / gradient hot loop of the ELBO (add_pixel_term!, elbo_objective.jl:330-392)
+// re-organised around the pixel GRID instead of the pixel: each thread walks along one row of the active
+// source's patch (consecutive columns w, w+1, ...) and carries every Gaussian component with it.
+//
+// Why: on a regular grid the quadratic form of a bivariate normal (eval_bvn_pdf!, BivariateNormals.jl:208-222)
+// changes by a LINEAR amount from one column to the next,
+//       q(w + 1) - q(w) = 2 p2(w) + L22,      p2(w + 1) - p2(w) = L22,       p = Lambda (x - mu),
+// so   f(w + 1) = f(w) r(w),   r(w + 1) = r(w) c,   c = exp(-L22),   r(w0) = exp(-(p2(w0) + L22 / 2)):
+// after an exact start (two exp per component) every further pixel costs two multiplications per component
+// instead of a quadratic form and an exp (20 of the 33 FP64 instructions a component costs in gradient mode).
+// The cubic B-spline of the star (star_light_density!, fsm_util.jl:225-248) has the same structure: along a row
+// the fractional offsets -- hence all eight weights -- are constant and the 4 x 4 tap window slides by one
+// column, so one new column of 4 taps per pixel replaces 16.
+// A walk is restarted exactly after at most MARCH_MAXSEG pixels, which bounds the accumulated rounding error
+// (relative ~ n^2/2 ulp after n steps: < 1e-13 at n = 16, five orders below the 1e-8 parity tolerance).
+//
+// Neighbouring sources (value only, elbo_objective.jl:38-40,69) are walked the same way over the intersection
+// of their patch with the active patch, one neighbour at a time, into a per-task background buffer
+// (E_bg, V_bg per active pixel) that the walk of the active source then reads.
+//
+// Gradients leave the block in TASK space -- world position (the -J' of each image already applied), raw
+// covariance, raw gal_frac_dev, and the four c-scalars of each BAND -- so that all images of a task reduce
+// into one 29-vector and march_epilogue_kernel applies the remaining chain rule once per source.
+//
+// Handles Sa = 1 and K = 2 (production: ParallelRun.jl:253,489, elbo_args.jl:197); every other plan keeps
+// task_kernel.  Same arithmetic as there up to reassociation.
+#ifndef CELESTE_MARCH_KERNELS_CUH
+#define CELESTE_MARCH_KERNELS_CUH
+
+#include "celeste_kernels.cuh"
+
+namespace celeste {
+
+#ifndef CELESTE_MARCH_MAXSEG
+#define CELESTE_MARCH_MAXSEG 16
+#endif
+#ifndef CELESTE_MARCH_MINB
+#define CELESTE_MARCH_MINB 2
+#endif
+#ifndef CELESTE_MARCH_THREADS
+#define CELESTE_MARCH_THREADS 128
+#endif
+constexpr int MARCH_THREADS = CELESTE_MARCH_THREADS;   // multiple of 32
+constexpr int MARCH_NIMG = 5;
+constexpr int MARCH_MAXSEG = CELESTE_MARCH_MAXSEG;
+constexpr int NC2 = NPROTO * 2;       // components of a K = 2 source
+constexpr int MREC = 8;               // staged component record: L11 L12 L22 c | mu1 mu2 z -
+// per (source, image) constants staged in shared memory
+constexpr int SI_CB = 0;              // A1 A2 B1 B2
+constexpr int SI_M = 4;               // m_pos
+constexpr int SI_WX = 6, SI_DWX = 10, SI_WY = 14, SI_DWY = 18;   // spline weights at the patch's fractional offsets
+constexpr int SI_J = 22;              // wcs_jacobian
+constexpr int SI_THETA = 26;
+constexpr int SI_STRIDE = 28;
+// task-space accumulators
+constexpr int TA_VAL = 0, TA_CNT_ACTIVE = 1, TA_CNT_INACTIVE = 2, TA_POS = 3, TA_SIG = 5, TA_THETA = 8, TA_BAND = 9;
+constexpr int NT_ACC = TA_BAND + 4 * 5;   // 29
+
+struct MarchBox {     // intersection of a neighbour's patch with the active patch, 1-based image coordinates
+    int h0, w0, nh, nw;
+};
+
+// stage the K = 2 component records of (slot, image) for marching; one thread per component
+__device__ inline void march_stage_records(const double* rec, double* dst, int c) {
+    const double* cp = rec + c * COMP_STRIDE;
+    double* o = dst + c * MREC;
+    o[0] = cp[2];
+    o[1] = cp[3];
+    o[2] = cp[4];
+    o[3] = rec[MAX_COMPS * COMP_STRIDE + 2 + c];   // exp(-L22), written by setup_kernel
+    o[4] = cp[0];
+    o[5] = cp[1];
+    o[6] = cp[5];
+    o[7] = 0.0;
+}
+
+// per-(source, image) constants: brightness scalars, m_pos, spline weights, Jacobian
+template <int MODE>
+__device__ inline void march_stage_srcimg(const PlanDev& plan, const PatchDev& p, int slot, int n, int band0, double* si) {
+    const double* rec = plan.slotimg + ((size_t)slot * plan.N + n) * SLOTIMG_STRIDE;
+    const double* br = plan.slotbr + (size_t)slot * SLOTBR_STRIDE;
+    const double a1 = br[20], a2 = br[21];
+    si[SI_CB + 0] = a1 * br[band0];
+    si[SI_CB + 1] = a2 * br[5 + band0];
+    si[SI_CB + 2] = a1 * br[10 + band0];
+    si[SI_CB + 3] = a2 * br[15 + band0];
+    const double m1 = rec[MAX_COMPS * COMP_STRIDE], m2 = rec[MAX_COMPS * COMP_STRIDE + 1];
+    si[SI_M] = m1;
+    si[SI_M + 1] = m2;
+    const double ax = (double)(p.off_h + 1) - m1 + 26.0, ay = (double)(p.off_w + 1) - m2 + 26.0;
+    double dd[4];
+    cubic_weights<(MODE >= 1 ? 1 : 0)>(ax - floor(ax), si + SI_WX, si + SI_DWX, dd);
+    cubic_weights<(MODE >= 1 ? 1 : 0)>(ay - floor(ay), si + SI_WY, si + SI_DWY, dd);
+    for (int i = 0; i < 4; ++i) si[SI_J + i] = p.J[i];
+    si[SI_THETA] = br[22];
+    si[SI_THETA + 1] = 0.0;
+}
+
+// exact start of a walk at image pixel (hh, ww): f = z exp(-q/2) and the column ratio r for every component
+__device__ __forceinline__ void march_start(const double* recs, const double* etab, double hh, double ww, double* fp,
+                                            double* rr) {
+#pragma unroll
+    for (int c = 0; c < NC2; ++c) {
+        const double* o = recs + c * MREC;
+        const double l11 = o[0], l12 = o[1], l22 = o[2], mu1 = o[4], mu2 = o[5], z = o[6];
+        const double d1 = hh - mu1, d2 = ww - mu2;
+        const double p1 = l11 * d1 + l12 * d2;
+        const double p2 = l12 * d1 + l22 * d2;
+        const double q = d1 * p1 + d2 * p2;
+        fp[c] = z * exp_scaled_tab(q, -0.5, etab);
+        // exp(-(q(w+1) - q(w)) / 2); the argument may be positive (walking towards the centre): bounded so that
+        // r stays finite however large the patch is
+        rr[c] = exp_scaled_tab(fmin(-(p2 + 0.5 * l22), 700.0), 1.0, etab);
+    }
+}
+
+// unit tables of a block (shared memory): walks are numbered image by image, rows fastest
+struct MarchUnits {
+    int ubeg[MARCH_NIMG + 1];
+    int nseg[MARCH_NIMG];
+    MarchBox box[MARCH_NIMG];
+};
+
+// One block per (active source of a task, group of <= MARCH_NIMG images).
+template <int MODE>
+__global__ void __launch_bounds__(MARCH_THREADS, CELESTE_MARCH_MINB)
+    march_kernel(PlanDev plan, const TaskHdr* __restrict__ taskmap, int ngroups) {
+    static_assert(MODE <= 1, "the Hessian mode uses pixel_kernel");
+    constexpr int NUA = MODE == 0 ? 1 : NACC_MODE1;   // (c, y)-space accumulators of the current walk
+    CEL_DYNAMIC_SMEM(smem);
+    double* tacc = smem;                                   // NT_ACC x MARCH_THREADS
+    double* s_arec = tacc + NT_ACC * MARCH_THREADS;        // MARCH_NIMG x NC2 x MREC   (active source)
+    double* s_nrec = s_arec + MARCH_NIMG * NC2 * MREC;     // MARCH_NIMG x NC2 x MREC   (current neighbour)
+    double* s_asi = s_nrec + MARCH_NIMG * NC2 * MREC;      // MARCH_NIMG x SI_STRIDE
+    double* s_nsi = s_asi + MARCH_NIMG * SI_STRIDE;        // MARCH_NIMG x SI_STRIDE
+    __shared__ double s_exptab[8];
+    __shared__ MarchUnits s_au, s_nu;                      // walks of the active source / of the current neighbour
+    __shared__ unsigned s_hasbg;
+
+    const int tid = threadIdx.x;
+    const TaskHdr th = taskmap[blockIdx.x];
+    if (plan.task_mask && !plan.task_mask[th.task]) return;
+    const int slot0 = th.slot0, slot1 = th.slot1, aslot = th.aslot;
+    const FieldDev field = plan.fields[th.field];
+    const int nimg = th.n1 - th.n0;
+    const PatchDev* apatch = field.patches + plan.src_row[aslot];   // + n * S_tot
+    const long long* bgp = plan.bg_ptr + (size_t)th.sub * plan.N;
+
+#pragma unroll
+    for (int a = 0; a < NT_ACC; ++a) tacc[a * MARCH_THREADS + tid] = 0.0;
+    for (int i = tid; i < nimg * NC2; i += MARCH_THREADS) {
+        const int k = i / NC2, c = i - k * NC2;
+        march_stage_records(plan.slotimg + ((size_t)aslot * plan.N + th.n0 + k) * SLOTIMG_STRIDE, s_arec + k * NC2 * MREC, c);
+    }
+    if (tid < nimg) {
+        const int k = tid, n = th.n0 + k;
+        march_stage_srcimg<MODE>(plan, apatch[(size_t)n * field.S_tot], aslot, n, field.images[n].band - 1, s_asi + k * SI_STRIDE);
+    }
+#ifdef CELESTE_HOST_EMULATION
+    if (tid < 8) s_exptab[tid] = h_exptab[tid];
+#else
+    if (tid < 8) s_exptab[tid] = c_exptab[tid];
+#endif
+    if (tid == MARCH_THREADS - 1) {
+        // walks of the active source: every row of every image, cut into nseg column segments.  nseg minimises
+        // warp-rounds x (segment length + cost of an exact start, ~1.7 pixels)
+        int rows = 0, maxw = 0;
+        for (int k = 0; k < nimg; ++k) {
+            const PatchDev& pa = apatch[(size_t)(th.n0 + k) * field.S_tot];
+            if (pa.H2 > 0 && pa.W2 > 0) {
+                rows += pa.H2;
+                maxw = max(maxw, pa.W2);
+            }
+        }
+        const int nmin = max(1, (maxw + MARCH_MAXSEG - 1) / MARCH_MAXSEG);
+        long best = -1;
+        int nseg = nmin;
+        for (int cand = nmin; cand < nmin + 4; ++cand) {
+            const int L = (maxw + cand - 1) / cand;
+            const long cost = (long)((rows * cand + 31) / 32) * (10 * L + 17);
+            if (best < 0 || cost < best) {
+                best = cost;
+                nseg = cand;
+            }
+        }
+        s_au.ubeg[0] = 0;
+        for (int k = 0; k < MARCH_NIMG; ++k) {
+            int units = 0;
+            if (k < nimg) {
+                const PatchDev& pa = apatch[(size_t)(th.n0 + k) * field.S_tot];
+                if (pa.H2 > 0 && pa.W2 > 0) units = pa.H2 * nseg;
+            }
+            s_au.nseg[k] = nseg;
+            s_au.ubeg[k + 1] = s_au.ubeg[k] + units;
+        }
+        // background buffers: the images some other source of the task can reach
+        unsigned hb = 0;
+        for (int k = 0; k < nimg; ++k) {
+            const int n = th.n0 + k;
+            const PatchDev& pa = apatch[(size_t)n * field.S_tot];
+            if (pa.H2 <= 0 || pa.W2 <= 0 || bgp[n] < 0) continue;
+            bool any = false;
+            for (int s = slot0; s < slot1 && !any; ++s) {
+                if (s == aslot) continue;
+                const PatchDev& p = field.patches[plan.src_row[s] + (size_t)n * field.S_tot];
+                any = (p.off_h + 1 <= pa.off_h + pa.H2) && (p.off_h + p.H2 >= pa.off_h + 1) &&
+                      (p.off_w + 1 <= pa.off_w + pa.W2) && (p.off_w + p.W2 - 1 >= pa.off_w + 1);
+            }
+            if (any) hb |= 1u << k;
+        }
+        s_hasbg = hb;
+    }
+    __syncthreads();
+    const unsigned hasbg = s_hasbg;
+
+    // ---- neighbours, one at a time in slot order: E_bg += E_s, V_bg += E2_s - E_s^2 over the shared pixels -------
+    if (hasbg) {
+        for (int k = 0; k < nimg; ++k)
+            if ((hasbg >> k) & 1u) {
+                const int n = th.n0 + k;
+                const PatchDev& pa = apatch[(size_t)n * field.S_tot];
+                double* bg = plan.bg + bgp[n];
+                const int tot = 2 * pa.H2 * pa.W2;
+                for (int i = tid; i < tot; i += MARCH_THREADS) bg[i] = 0.0;
+            }
+        for (int s = slot0; s < slot1; ++s) {
+            if (s == aslot) continue;
+            __syncthreads();      // the previous neighbour's sums (or the zeros) are in place; s_nu / s_nrec are free
+            if (tid == 0) {
+                s_nu.ubeg[0] = 0;
+                for (int k = 0; k < MARCH_NIMG; ++k) {
+                    int units = 0;
+                    MarchBox bx{0, 0, 0, 0};
+                    int nsg = 1;
+                    if (k < nimg && ((hasbg >> k) & 1u)) {
+                        const int n = th.n0 + k;
+                        const PatchDev& pa = apatch[(size_t)n * field.S_tot];
+                        const PatchDev& p = field.patches[plan.src_row[s] + (size_t)n * field.S_tot];
+                        // active pixels: rows off+1..off+H2, columns off+1..off+W2; the neighbour covers columns
+                        // off+1..off+W2-1 only (strict `w2 < W2`, elbo_objective.jl:349)
+                        const int h_lo = max(pa.off_h, p.off_h) + 1, h_hi = min(pa.off_h + pa.H2, p.off_h + p.H2);
+                        const int w_lo = max(pa.off_w, p.off_w) + 1, w_hi = min(pa.off_w + pa.W2, p.off_w + p.W2 - 1);
+                        if (h_hi >= h_lo && w_hi >= w_lo) {
+                            bx = MarchBox{h_lo, w_lo, h_hi - h_lo + 1, w_hi - w_lo + 1};
+                            nsg = (bx.nw + MARCH_MAXSEG - 1) / MARCH_MAXSEG;
+                            units = bx.nh * nsg;
+                        }
+                    }
+                    s_nu.box[k] = bx;
+                    s_nu.nseg[k] = nsg;
+                    s_nu.ubeg[k + 1] = s_nu.ubeg[k] + units;
+                }
+            }
+            __syncthreads();
+            const int total = s_nu.ubeg[MARCH_NIMG];
+            if (total == 0) continue;                      // uniform over the block
+            for (int i = tid; i < nimg * NC2; i += MARCH_THREADS) {
+                const int k = i / NC2, c = i - k * NC2;
+                if (s_nu.ubeg[k + 1] > s_nu.ubeg[k])
+                    march_stage_records(plan.slotimg + ((size_t)s * plan.N + th.n0 + k) * SLOTIMG_STRIDE, s_nrec + k * NC2 * MREC, c);
+            }
+            if (tid < nimg && s_nu.ubeg[tid + 1] > s_nu.ubeg[tid]) {
+                const int k = tid, n = th.n0 + k;
+                march_stage_srcimg<0>(plan, field.patches[plan.src_row[s] + (size_t)n * field.S_tot], s, n,
+                                      field.images[n].band - 1, s_nsi + k * SI_STRIDE);
+            }
+            __syncthreads();
+            double cnt_inactive = 0.0;
+            for (int u = tid; u < total; u += MARCH_THREADS) {
+                int k = 0;
+#pragma unroll
+                for (int kk = 1; kk < MARCH_NIMG; ++kk) k += (u >= s_nu.ubeg[kk]) ? 1 : 0;
+                const int n = th.n0 + k;
+                const int ul = u - s_nu.ubeg[k];
+                const MarchBox bx = s_nu.box[k];
+                const int nsg = s_nu.nseg[k];
+                const int seg = ul / bx.nh, row = ul - seg * bx.nh;
+                const int segw = (bx.nw + nsg - 1) / nsg;
+                const int c0 = seg * segw, len = min(segw, bx.nw - c0);
+                if (len <= 0) continue;
+                const int h = bx.h0 + row, w0 = bx.w0 + c0;     // 1-based image coordinates
+                const PatchDev& pa = apatch[(size_t)n * field.S_tot];
+                const PatchDev& p = field.patches[plan.src_row[s] + (size_t)n * field.S_tot];
+                const int aH2 = pa.H2, aW2 = pa.W2, nH2 = p.H2, imgH = field.images[n].H, n1 = p.n1, n2 = p.n2;
+                const double* coefs = p.coefs;
+                const double* si = s_nsi + k * SI_STRIDE;
+                const double* recs = s_nrec + k * NC2 * MREC;
+                double fp[NC2], rr[NC2];
+                march_start(recs, s_exptab, (double)h, (double)w0, fp, rr);
+                // star: sliding window of row-interpolated columns
+                const double ax = (double)h - si[SI_M] + 26.0, ay0 = (double)w0 - si[SI_M + 1] + 26.0;
+                const int ixf = (int)floor(ax), iy0 = (int)floor(ay0);
+                const bool fast = ixf >= 1 && ixf <= n1 - 3 && iy0 >= 1 && iy0 + len - 1 <= n2 - 3;
+                double R0 = 0.0, R1 = 0.0, R2 = 0.0;
+                const double* ccol = coefs + (size_t)(iy0 - 1) * n1 + (ixf - 1);
+                if (fast) {
+                    const double wx0 = si[SI_WX], wx1 = si[SI_WX + 1], wx2 = si[SI_WX + 2], wx3 = si[SI_WX + 3];
+                    R0 = wx0 * __ldg(ccol) + wx1 * __ldg(ccol + 1) + wx2 * __ldg(ccol + 2) + wx3 * __ldg(ccol + 3);
+                    ccol += n1;
+                    R1 = wx0 * __ldg(ccol) + wx1 * __ldg(ccol + 1) + wx2 * __ldg(ccol + 2) + wx3 * __ldg(ccol + 3);
+                    ccol += n1;
+                    R2 = wx0 * __ldg(ccol) + wx1 * __ldg(ccol + 1) + wx2 * __ldg(ccol + 2) + wx3 * __ldg(ccol + 3);
+                    ccol += n1;
+                }
+                const int ah2 = h - pa.off_h - 1, nh2 = h - p.off_h - 1;
+                const uint8_t* abit = pa.bitmap + ah2 + (size_t)(w0 - pa.off_w - 1) * aH2;
+                const uint8_t* nbit = p.bitmap + nh2 + (size_t)(w0 - p.off_w - 1) * nH2;
+                const float* px = field.images[n].pixels + (size_t)(h - 1) + (size_t)(w0 - 1) * imgH;
+                double* bgE = plan.bg + bgp[n] + ah2 + (size_t)(w0 - pa.off_w - 1) * aH2;
+                const size_t bgplane = (size_t)aH2 * aW2;
+                const double theta = si[SI_THETA];
+                for (int i = 0; i < len; ++i) {
+                    const bool valid = *abit && *nbit && !isnan(*px);
+                    abit += aH2;
+                    nbit += nH2;
+                    px += imgH;
+                    double R3 = 0.0;
+                    if (fast) {
+                        R3 = si[SI_WX] * __ldg(ccol) + si[SI_WX + 1] * __ldg(ccol + 1) + si[SI_WX + 2] * __ldg(ccol + 2) +
+                             si[SI_WX + 3] * __ldg(ccol + 3);
+                        ccol += n1;
+                    }
+                    double Fd = 0.0, Fe = 0.0;
+#pragma unroll
+                    for (int c = 0; c < NC2; ++c) {
+                        if (c < NPROTO_DEV * 2)
+                            Fd += fp[c];
+                        else
+                            Fe += fp[c];
+                        fp[c] *= rr[c];
+                        rr[c] *= recs[c * MREC + 3];
+                    }
+                    if (valid) {
+                        double f0;
+                        if (fast) {
+                            const double v = si[SI_WY] * R0 + si[SI_WY + 1] * R1 + si[SI_WY + 2] * R2 + si[SI_WY + 3] * R3;
+                            f0 = v < 0 ? 1e-3 * exp_nonpos(v) : 1e-3 * (v + 1.0);     // softpluslikeinv, fsm_util.jl:222
+                        } else {
+                            double gd[2], hd[3];
+                            star_eval<0>(LdGlobal(), coefs, n1, n2, ax, ay0 + (double)i, f0, gd, hd);
+                        }
+                        const double f1 = theta * Fd + (1.0 - theta) * Fe;
+                        const double Es = si[SI_CB] * f0 + si[SI_CB + 1] * f1;
+                        const double E2s = si[SI_CB + 2] * f0 * f0 + si[SI_CB + 3] * f1 * f1;
+                        bgE[0] += Es;
+                        bgE[bgplane] += E2s - Es * Es;
+                        cnt_inactive += 1.0;                                          // elbo_objective.jl:353-357
+                    }
+                    bgE += aH2;
+                    R0 = R1;
+                    R1 = R2;
+                    R2 = R3;
+                }
+            }
+            tacc[TA_CNT_INACTIVE * MARCH_THREADS + tid] += cnt_inactive;
+        }
+        __syncthreads();          // every neighbour's sums are visible to the walk of the active source
+    }
+
+    // ---- the active source -----------------------------------------------------------------------------------
+    const int total = s_au.ubeg[MARCH_NIMG];
+    for (int u = tid; u < total; u += MARCH_THREADS) {
+        int k = 0;
+#pragma unroll
+        for (int kk = 1; kk < MARCH_NIMG; ++kk) k += (u >= s_au.ubeg[kk]) ? 1 : 0;
+        const int n = th.n0 + k;
+        const int nseg = s_au.nseg[k];
+        const PatchDev& pa = apatch[(size_t)n * field.S_tot];
+        const int H2 = pa.H2, W2 = pa.W2, n1 = pa.n1, n2 = pa.n2;
+        const double* coefs = pa.coefs;
+        const ImageDev& img = field.images[n];
+        const int imgH = img.H, band0 = img.band - 1;
+        const int ul = u - s_au.ubeg[k];
+        const int seg = ul / H2, h2 = ul - seg * H2;
+        const int segw = (W2 + nseg - 1) / nseg;
+        const int c0 = seg * segw, len = min(segw, W2 - c0);
+        if (len <= 0) continue;
+        const int ncov = min(len, W2 - 1 - c0);                   // pixels before the (uncovered) last column, :349
+        const int h = pa.off_h + h2 + 1, w0 = pa.off_w + c0 + 1;     // 1-based image coordinates
+        const double* si = s_asi + k * SI_STRIDE;
+        const double* recs = s_arec + k * NC2 * MREC;
+        double fp[NC2], rr[NC2];
+        march_start(recs, s_exptab, (double)h, (double)w0, fp, rr);
+        const double d1a = (double)h - recs[4], d1b = (double)h - recs[MREC + 4];       // x1 - mu1 of PSF component 0 / 1
+        double d2a = (double)w0 - recs[5], d2b = (double)w0 - recs[MREC + 5];
+        // star
+        const double ax = (double)h - si[SI_M] + 26.0, ay0 = (double)w0 - si[SI_M + 1] + 26.0;
+        const int ixf = (int)floor(ax), iy0 = (int)floor(ay0);
+        const bool fast = ixf >= 1 && ixf <= n1 - 3 && iy0 >= 1 && iy0 + len - 1 <= n2 - 3;
+        double R0 = 0.0, R1 = 0.0, R2 = 0.0, D0 = 0.0, D1 = 0.0, D2 = 0.0;
+        const double* ccol = coefs + (size_t)(iy0 - 1) * n1 + (ixf - 1);
+        if (fast) {
+#pragma unroll
+            for (int b = 0; b < 3; ++b) {
+                const double q0 = __ldg(ccol), q1 = __ldg(ccol + 1), q2 = __ldg(ccol + 2), q3 = __ldg(ccol + 3);
+                const double r = si[SI_WX] * q0 + si[SI_WX + 1] * q1 + si[SI_WX + 2] * q2 + si[SI_WX + 3] * q3;
+                double d = 0.0;
+                if (MODE >= 1) d = si[SI_DWX] * q0 + si[SI_DWX + 1] * q1 + si[SI_DWX + 2] * q2 + si[SI_DWX + 3] * q3;
+                ccol += n1;
+                if (b == 0) {
+                    R0 = r;
+                    D0 = d;
+                } else if (b == 1) {
+                    R1 = r;
+                    D1 = d;
+                } else {
+                    R2 = r;
+                    D2 = d;
+                }
+            }
+        }
+        const bool bgk = (hasbg >> k) & 1u;
+        const size_t pix0 = (size_t)h2 + (size_t)c0 * H2;
+        const uint8_t* abit = pa.bitmap + pix0;
+        const size_t ipix0 = (size_t)(h - 1) + (size_t)(w0 - 1) * imgH;
+        const float* px = img.pixels + ipix0;
+        const float* psky = img.sky + ipix0;
+        const double* ppc = img.pixconst + ipix0;
+        const double* bgE = plan.bg + (bgk ? bgp[n] : 0) + pix0;
+        const size_t bgplane = (size_t)H2 * W2;
+        const double iota = (double)img.iota[h - 1];
+        const double theta = si[SI_THETA];
+        const double cb[4] = {si[SI_CB], si[SI_CB + 1], si[SI_CB + 2], si[SI_CB + 3]};
+        double ua[NUA];
+#pragma unroll
+        for (int a = 0; a < NUA; ++a) ua[a] = 0.0;
+        double cnt_active = 0.0;
+
+        // per-pixel inputs are fetched one step ahead so their latency hides behind the FP64 work
+        struct PixIn {
+            unsigned char active;
+            float x, sky;
+            double pixconst, bE, bV;
+        };
+        auto fetch = [&](bool ok) {
+            PixIn in;
+            in.active = 0;
+            in.x = in.sky = 0.f;
+            in.pixconst = in.bE = in.bV = 0.0;
+            if (ok) {
+                in.active = *abit;
+                in.x = *px;
+                in.sky = *psky;
+                in.pixconst = *ppc;
+                if (bgk) {
+                    in.bE = bgE[0];
+                    in.bV = bgE[bgplane];
+                }
+                abit += H2;
+                bgE += H2;
+                px += imgH;
+                psky += imgH;
+                ppc += imgH;
+            }
+            return in;
+        };
+        PixIn cur = fetch(true);
+        for (int i = 0; i < len; ++i) {
+            const PixIn nxt = fetch(i + 1 < len);
+            const bool live = cur.active && !isnan(cur.x);          // elbo_objective.jl:445, :459
+            double R3 = 0.0, D3 = 0.0;
+            if (fast) {
+                const double q0 = __ldg(ccol), q1 = __ldg(ccol + 1), q2 = __ldg(ccol + 2), q3 = __ldg(ccol + 3);
+                R3 = si[SI_WX] * q0 + si[SI_WX + 1] * q1 + si[SI_WX + 2] * q2 + si[SI_WX + 3] * q3;
+                if (MODE >= 1) D3 = si[SI_DWX] * q0 + si[SI_DWX + 1] * q1 + si[SI_DWX + 2] * q2 + si[SI_DWX + 3] * q3;
+                ccol += n1;
+            }
+            if (live && i < ncov) {
+                // mixture (populate_gal_fsm!, fsm_util.jl:194-219): unweighted sums of the two prototype groups
+                double F[2] = {0.0, 0.0}, AX1[2] = {0.0, 0.0}, AX2[2] = {0.0, 0.0}, AS1[2] = {0.0, 0.0}, AS2[2] = {0.0, 0.0},
+                       AS3[2] = {0.0, 0.0};
+#pragma unroll
+                for (int j = 0; j < NPROTO; ++j) {
+                    const int g = j < NPROTO_DEV ? 0 : 1;
+#pragma unroll
+                    for (int kk = 0; kk < 2; ++kk) {
+                        const int c = j * 2 + kk;
+                        const double* o = recs + c * MREC;
+                        const double f = fp[c];
+                        F[g] += f;
+                        if (MODE >= 1) {
+                            const double l11 = o[0], l12 = o[1], l22 = o[2];
+                            const double d1 = kk == 0 ? d1a : d1b, d2 = kk == 0 ? d2a : d2b;
+                            const double p1 = fma(l12, d2, l11 * d1);
+                            const double p2 = fma(l22, d2, l12 * d1);
+                            AX1[g] = fma(f, p1, AX1[g]);
+                            AX2[g] = fma(f, p2, AX2[g]);
+                            const double fn = f * c_proto_nu[j];
+                            AS1[g] = fma(fn, fma(p1, p1, -l11), AS1[g]);      // 2 x bvn_sig_d[1], BivariateNormals.jl:267-272
+                            AS2[g] = fma(fn, fma(p1, p2, -l12), AS2[g]);
+                            AS3[g] = fma(fn, fma(p2, p2, -l22), AS3[g]);      // 2 x bvn_sig_d[3]
+                        }
+                        fp[c] = f * rr[c];
+                        rr[c] *= o[3];
+                    }
+                }
+                const double t0 = theta, t1 = 1.0 - theta;
+                GalRaw gal;
+                gal.f = t0 * F[0] + t1 * F[1];
+                if (MODE >= 1) {
+                    gal.r[0] = -(t0 * AX1[0] + t1 * AX1[1]);
+                    gal.r[1] = -(t0 * AX2[0] + t1 * AX2[1]);
+                    gal.r[2] = 0.5 * (t0 * AS1[0] + t1 * AS1[1]);
+                    gal.r[3] = t0 * AS2[0] + t1 * AS2[1];
+                    gal.r[4] = 0.5 * (t0 * AS3[0] + t1 * AS3[1]);
+                    gal.r[5] = F[0] - F[1];                                   // gal_frac_dev, fsm_util.jl:277-291
+                }
+                // star (star_light_density!, fsm_util.jl:225-248)
+                double f0, g0[2] = {0.0, 0.0}, h0[3] = {0.0, 0.0, 0.0};
+                if (fast) {
+                    const double wy0 = si[SI_WY], wy1 = si[SI_WY + 1], wy2 = si[SI_WY + 2], wy3 = si[SI_WY + 3];
+                    const double v = wy0 * R0 + wy1 * R1 + wy2 * R2 + wy3 * R3;
+                    double gx = 0.0, gy = 0.0;
+                    if (MODE >= 1) {
+                        gx = wy0 * D0 + wy1 * D1 + wy2 * D2 + wy3 * D3;
+                        gy = si[SI_DWY] * R0 + si[SI_DWY + 1] * R1 + si[SI_DWY + 2] * R2 + si[SI_DWY + 3] * R3;
+                    }
+                    if (v < 0) {                                              // softpluslikeinv, fsm_util.jl:222
+                        const double e = 1e-3 * exp_nonpos(v);
+                        f0 = e;
+                        g0[0] = e * gx;
+                        g0[1] = e * gy;
+                    } else {
+                        f0 = 1e-3 * (v + 1.0);
+                        g0[0] = 1e-3 * gx;
+                        g0[1] = 1e-3 * gy;
+                    }
+                } else {
+                    star_eval<MODE>(LdGlobal(), coefs, n1, n2, ax, ay0 + (double)i, f0, g0, h0);
+                }
+                PixelConsts pc;
+                pc.x = (double)cur.x;
+                pc.iota = iota;
+                pc.pixconst = cur.pixconst;
+                cnt_active += 1.0;
+                pixel_accumulate<MODE>(ua, 1, pc, (double)cur.sky + cur.bE, cur.bV, true, true, cb, f0, g0, h0, gal);
+            } else {
+#pragma unroll
+                for (int c = 0; c < NC2; ++c) {
+                    fp[c] *= rr[c];
+                    rr[c] *= recs[c * MREC + 3];
+                }
+                if (live) {
+                    // last column of the patch: the source does not cover it (value of the background only)
+                    PixelConsts pc;
+                    pc.x = (double)cur.x;
+                    pc.iota = iota;
+                    pc.pixconst = cur.pixconst;
+                    GalRaw gal;
+                    gal.f = 0.0;
+                    const double g0[2] = {0.0, 0.0}, h0[3] = {0.0, 0.0, 0.0};
+                    pixel_accumulate<MODE>(ua, 1, pc, (double)cur.sky + cur.bE, cur.bV, false, true, cb, 0.0, g0, h0, gal);
+                }
+            }
+            d2a += 1.0;
+            d2b += 1.0;
+            R0 = R1;
+            R1 = R2;
+            R2 = R3;
+            D0 = D1;
+            D1 = D2;
+            D2 = D3;
+            cur = nxt;
+        }
+        // leave the walk: (c, y) space of this image -> task space
+        double* ta = tacc + tid;
+        ta[TA_VAL * MARCH_THREADS] += ua[ACC_VAL];
+        ta[TA_CNT_ACTIVE * MARCH_THREADS] += cnt_active;
+        if (MODE >= 1) {
+            const double gx1 = ua[ACC_G], gx2 = ua[ACC_G + 1];
+            ta[(TA_POS + 0) * MARCH_THREADS] -= si[SI_J + 0] * gx1 + si[SI_J + 1] * gx2;     // dx_a/dpos_b = -J[a + 2 b]
+            ta[(TA_POS + 1) * MARCH_THREADS] -= si[SI_J + 2] * gx1 + si[SI_J + 3] * gx2;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) ta[(TA_SIG + q) * MARCH_THREADS] += ua[ACC_G + 2 + q];
+            ta[TA_THETA * MARCH_THREADS] += ua[ACC_G + 5];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) ta[(TA_BAND + 4 * band0 + q) * MARCH_THREADS] += ua[ACC_C1 + q];
+        }
+    }
+    __syncthreads();
+
+    // fixed-order block reduction, all of a warp's accumulators in flight
+    const int warp = tid >> 5, lane = tid & 31;
+    constexpr int NA = MODE == 0 ? TA_POS : NT_ACC;
+    constexpr int NW = MARCH_THREADS / 32, PER = (NA + NW - 1) / NW;
+    double* out = plan.partials + ((size_t)th.sub * ngroups + th.n0 / MARCH_NIMG) * NT_ACC;
+    double sred[PER];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int a = warp + NW * i;
+        sred[i] = 0.0;
+        if (a < NA) {
+#pragma unroll
+            for (int q = 0; q < NW; ++q) sred[i] += tacc[a * MARCH_THREADS + lane + 32 * q];
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int i = 0; i < PER; ++i) sred[i] += __shfl_xor_sync(0xffffffffu, sred[i], o);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < PER; ++i)
+            if (warp + NW * i < NA) out[warp + NW * i] = sred[i];
+    }
+}
+
+constexpr size_t march_smem_bytes() {
+    return ((size_t)NT_ACC * MARCH_THREADS + 2 * (size_t)MARCH_NIMG * NC2 * MREC + 2 * (size_t)MARCH_NIMG * SI_STRIDE) * sizeof(double);
+}
+
+// ------------------------------------------------------------------------------------------------
+// The rest of the chain rule, once per source: task space -> the 28 live canonical parameters
+// (what epilogue_kernel's Jy does per image).  One warp per task.
+constexpr int MEPI_THREADS = 64;
+
+template <int MODE>
+__global__ void __launch_bounds__(MEPI_THREADS) march_epilogue_kernel(PlanDev plan, const double* __restrict__ vp, int ngroups,
+                                                                      double* __restrict__ out_v, double* __restrict__ out_d,
+                                                                      long long* __restrict__ out_counters,
+                                                                      int* __restrict__ out_flags) {
+    __shared__ double ysum[NT_ACC];
+    __shared__ double J0[3][3], T0[3][3][3];
+    __shared__ int s_bad;
+    const int tid = threadIdx.x;
+    const int t = blockIdx.x;
+    if (plan.task_mask && !plan.task_mask[t]) return;
+    const int sub = plan.sub_ptr[t];                 // Sa == 1
+    const int aslot = plan.sub_slot[sub];
+    const double* vs = vp + (size_t)NPARAM * aslot;
+    const double* br = plan.slotbr + (size_t)aslot * SLOTBR_STRIDE;
+    constexpr int NA = MODE == 0 ? TA_POS : NT_ACC;
+    if (tid < NA) {
+        double s = 0.0;
+        for (int g = 0; g < ngroups; ++g) s += plan.partials[((size_t)sub * ngroups + g) * NT_ACC + tid];
+        ysum[tid] = s;
+    }
+    if (tid == 32 && MODE >= 1) sigma_derivs(vs[3], vs[4], vs[5], J0, T0);
+    if (tid == 0) s_bad = 0;
+    __syncthreads();
+    int bad = 0;
+    if (MODE >= 1 && tid < NPARAM) {
+        const int q = tid;
+        double g = 0.0;
+        int i, k;
+        if (q < 2) {
+            g = ysum[TA_POS + q];
+        } else if (q == 2) {
+            g = ysum[TA_THETA];
+        } else if (q < 6) {
+            for (int r = 0; r < 3; ++r) g += J0[r][q - 3] * ysum[TA_SIG + r];
+        } else if (bright_of(q, i, k)) {
+            // c = (a1 E_l1, a2 E_l2, a1 E_ll1, a2 E_ll2) of each band; every derivative is E * kappa (source_brightness.jl:45-202)
+            for (int b = 0; b < 5; ++b) {
+                double ka[10], la[10];
+                band_coefs(b, ka, la);
+                g += br[20 + i] * (br[i * 5 + b] * ka[k] * ysum[TA_BAND + 4 * b + i] +
+                                   br[10 + i * 5 + b] * la[k] * ysum[TA_BAND + 4 * b + 2 + i]);
+            }
+        } else if (q == 26 || q == 27) {
+            i = q - 26;
+            for (int b = 0; b < 5; ++b)
+                g += br[i * 5 + b] * ysum[TA_BAND + 4 * b + i] + br[10 + i * 5 + b] * ysum[TA_BAND + 4 * b + 2 + i];
+        }
+        out_d[(size_t)NPARAM * sub + q] = g;
+        bad |= !isfinite(g);
+    }
+    if (tid == 0) {
+        out_v[t] = ysum[TA_VAL];
+        out_counters[2 * t] = (long long)(ysum[TA_CNT_ACTIVE] + 0.5);
+        out_counters[2 * t + 1] = (long long)(ysum[TA_CNT_INACTIVE] + 0.5);
+        bad |= !isfinite(ysum[TA_VAL]);
+    }
+    if (bad) atomicOr(&s_bad, 1);
+    __syncthreads();
+    if (tid == 0) out_flags[t] = s_bad ? 1 : 0;
+}
+
+}  // namespace celeste
+#endif

@@ -279,6 +279,12 @@ class Plan:
     def launches(self, mode: int) -> int:
         return int(_lib.load().celeste_plan_launches(self._handle, mode))
 
+    def kernel_name(self, mode: int) -> str:
+        """Which kernel carries the pixel loop of `mode` (march_kernel / task_kernel / pixel_kernel)."""
+        buf = C.create_string_buffer(32)
+        _lib.check(_lib.load().celeste_plan_kernel_name(self._handle, mode, buf))
+        return buf.value.decode()
+
     def run_host(self, vp_flat: np.ndarray, mode: int, out=None, check_finite=True):
         lib = _lib.load()
         n = self.n_tasks

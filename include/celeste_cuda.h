@@ -213,6 +213,13 @@ int celeste_plan_create_multi(int32_t n_fields, celeste_field* const* fields, ce
 void celeste_plan_destroy(celeste_plan* p);
 /* number of kernel launches one celeste_elbo_plan_device call enqueues */
 int celeste_plan_launches(const celeste_plan* p, int32_t mode);
+/*
+ * Name of the kernel that carries the pixel loop of `mode` for this plan, written to buf (<= 31 chars + NUL):
+ * "march_kernel" (value / gradient, every task Sa = 1 and every patch K = 2 -- the production shape:
+ * ParallelRun.jl:253,489, elbo_args.jl:197), "task_kernel" (value / gradient otherwise, or when the process
+ * was started with CELESTE_GRAD_KERNEL=task), "pixel_kernel" (Hessian).  For profiling / bench reports.
+ */
+int celeste_plan_kernel_name(const celeste_plan* p, int32_t mode, char* buf);
 int celeste_elbo_plan_device(celeste_plan* p, const double* vp_dev, int32_t mode,
                              double* v_dev, double* d_dev, double* h_dev,
                              int64_t* counters_dev, int32_t* flags_dev,

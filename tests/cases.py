@@ -153,6 +153,19 @@ def case_small_field(n_sources=40, H=160, W=140, seed=42):
     return ds.images, ds.patches, tasks
 
 
+def case_wide_patch():
+    """Patches wider than the 51 x 51 PSF stamp (un-capped SEP boxes, detection.jl:153-158): the spline is evaluated
+    in its clamped edge cells (fsm_util.jl:236 does no bounds handling), rows need several exact restarts of the
+    march kernel's walks, and the neighbour overlaps only part of the rows."""
+    images = synthetic.blank_images(90, 84, bands=(2, 4))
+    catalog = [synthetic.sample_ce([44.3, 40.8], True), synthetic.sample_ce([61.9, 57.2], False)]
+    synthetic.gen_images(images, catalog, seed=9, device="cpu")
+    patches = get_sky_patches(images, catalog, radius_override_pix=38.0)
+    vp = [cj.catalog_init_source(ce) for ce in catalog]
+    synthetic.perturb_params(vp)
+    return images, patches, _all_tasks(vp)
+
+
 CASES = {
     "star_1band": case_star_1band,
     "star_5band": case_star_5band,
@@ -166,6 +179,7 @@ CASES = {
     "psf_k3": case_psf_k3,
     "crowded": case_crowded,
     "small_field": case_small_field,
+    "wide_patch": case_wide_patch,
 }
 
 _cache = {}

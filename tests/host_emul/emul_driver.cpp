@@ -6,6 +6,7 @@
 
 #include "../../include/celeste_cuda.h"
 #include "../../celeste.jl_b200/csrc/celeste_kernels.cuh"
+#include "../../celeste.jl_b200/csrc/march_kernels.cuh"
 #include "../../celeste.jl_b200/csrc/maximize_kernels.cuh"
 #include "../../celeste.jl_b200/csrc/patch_kernels.cuh"
 
@@ -33,10 +34,39 @@ void galaxy_prototypes(double eta[NPROTO], double nu[NPROTO]) {
     }
 }
 
+int g_grad_kernel = 1;   // 1: march_kernel where the product would use it (Sa = 1, K = 2); 0: always task_kernel
+
 template <int MODE>
 void run_task(PlanDev pd, const FieldDev& fd, const std::vector<TaskHdr>& taskmap, const std::vector<int>& tcp,
               const double* vp, double* v, double* d, double* h, long long* counters, int* flags) {
     if constexpr (MODE <= 1) {
+        bool all_k2 = true;
+        for (int i = 0; i < fd.S_tot * pd.N; ++i) all_k2 = all_k2 && fd.patches[i].K == 2;
+        if (g_grad_kernel == 1 && all_k2 && pd.n_subs == pd.n_tasks) {
+            // same launch sequence as celeste_abi.cu's march path
+            const int ngroups = (pd.N + MARCH_NIMG - 1) / MARCH_NIMG;
+            std::vector<long long> bg_ptr((size_t)pd.n_subs * pd.N, -1);
+            long long bg_total = 0;
+            for (int u = 0; u < pd.n_subs; ++u) {
+                const int t = u;
+                if (pd.task_ptr[t + 1] - pd.task_ptr[t] < 2) continue;
+                for (int n = 0; n < pd.N; ++n) {
+                    const PatchDev& pa = fd.patches[(size_t)pd.src_row[pd.sub_slot[u]] + (size_t)n * fd.S_tot];
+                    if (pa.H2 <= 0 || pa.W2 <= 0) continue;
+                    bg_ptr[(size_t)u * pd.N + n] = bg_total;
+                    bg_total += 2LL * pa.H2 * pa.W2;
+                }
+            }
+            std::vector<double> bg((size_t)bg_total + 1, 1e300);     // poisoned: the kernel must zero what it reads
+            pd.bg_ptr = bg_ptr.data();
+            pd.bg = bg.data();
+            cuda_emul::launch(setup_kernel, 2, 64, 0, pd, vp);
+            if (!taskmap.empty())
+                cuda_emul::launch(march_kernel<MODE>, (int)taskmap.size(), MARCH_THREADS, march_smem_bytes(), pd, taskmap.data(),
+                                  ngroups);
+            cuda_emul::launch(march_epilogue_kernel<MODE>, pd.n_tasks, MEPI_THREADS, 0, pd, vp, ngroups, v, d, counters, flags);
+            return;
+        }
         const size_t smem = ((size_t)NAcc<MODE>::value * PIX_THREADS + (size_t)TASK_NIMG * MAX_COMPS * COMP_STRIDE) * sizeof(double);
         cuda_emul::launch(setup_kernel, 2, 64, 0, pd, vp);
         pd.chunk_ptr = tcp.data();
@@ -163,7 +193,8 @@ extern "C" int emul_elbo_batch(int32_t N, const celeste_image* imgs, int32_t S_t
     std::vector<int> tcp((size_t)n_subs * N + 1);
     for (size_t i = 0; i < tcp.size(); ++i) tcp[i] = (int)(i * TASK_WARPS);
     std::vector<double> slotimg((size_t)n_slots * N * SLOTIMG_STRIDE), slotbr((size_t)n_slots * SLOTBR_STRIDE),
-        partials(std::max(blockmap.size() * NACC_MODE2, (size_t)n_subs * N * TASK_WARPS * NACC_MODE1) + 1),
+        partials(std::max({blockmap.size() * NACC_MODE2, (size_t)n_subs * N * TASK_WARPS * NACC_MODE1,
+                           (size_t)n_subs * ((N + MARCH_NIMG - 1) / MARCH_NIMG) * NT_ACC}) + 1),
         pair_partials(pairmap.size() * NPAIR_ACC + 1);
     PlanDev pd;
     FieldDev fd{images.data(), pdv.data(), S_tot, 0};
@@ -191,6 +222,8 @@ extern "C" int emul_elbo_batch(int32_t N, const celeste_image* imgs, int32_t S_t
     pd.partials = partials.data();
     pd.pair_partials = pair_partials.data();
     pd.task_mask = nullptr;
+    pd.bg_ptr = nullptr;
+    pd.bg = nullptr;
     std::vector<long long> cnt(2 * (size_t)n_tasks);
     const int nb = (int)blockmap.size();
     if (mode == 0)
@@ -200,6 +233,11 @@ extern "C" int emul_elbo_batch(int32_t N, const celeste_image* imgs, int32_t S_t
     else
         run<2>(pd, fd, nb, chunk_pixels, vp, v, d, h, cnt.data(), flags);
     for (size_t i = 0; i < cnt.size(); ++i) counters[i] = cnt[i];
+    return 0;
+}
+
+extern "C" int emul_set_grad_kernel(int32_t which) {
+    g_grad_kernel = which;
     return 0;
 }
 

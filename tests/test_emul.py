@@ -29,6 +29,34 @@ def test_emulated_kernels_match_oracle_hessian(name):
     cases.assert_parity(ref, got, 2, name)
 
 
+@pytest.mark.parametrize("name", ["two_body", "masked", "clipped_and_empty", "crowded", "config2_rotated_wcs", "small_field",
+                                  "wide_patch"])
+def test_march_kernel_matches_oracle_and_task_kernel(name):
+    """march_kernels.cuh (row walks with the exp recurrence; the product's value / gradient path for Sa = 1, K = 2)
+    against the oracle at the 1e-8 parity statement, and against task_kernel (direct evaluation of every pixel) at
+    1e-11: the recurrence is restarted exactly every <= 16 pixels, so the two differ by accumulated rounding only."""
+    images, patches, tasks = cases.get(name)
+    lib = emul_lib.load()
+    for mode in (0, 1):
+        ref = oracle_lib.OracleField(images, patches).elbo_batch(tasks, mode=mode, n_threads=4)
+        try:
+            lib.emul_set_grad_kernel(0)
+            direct = emul_lib.EmulField(images, patches).elbo_batch(tasks, mode=mode)
+        finally:
+            lib.emul_set_grad_kernel(1)
+        march = emul_lib.EmulField(images, patches).elbo_batch(tasks, mode=mode)
+        cases.assert_parity(ref, march, mode, name)
+        cases.assert_parity(ref, direct, mode, name)
+        assert np.array_equal(march["counters"], direct["counters"])
+        fin = np.isfinite(direct["v"])
+        assert np.all(np.abs(march["v"] - direct["v"])[fin] <= 1e-11 * np.abs(direct["v"])[fin])
+        if mode == 1:
+            n = len(tasks)
+            a, b = march["d"].reshape(n, -1), direct["d"].reshape(n, -1)
+            sc = np.abs(b).max(axis=1, keepdims=True)
+            assert np.all(np.abs(a - b) <= 1e-11 * np.maximum(np.abs(b), sc * 1e-3)), np.abs(a - b).max()
+
+
 def test_chunking_does_not_change_counters_or_parity():
     images, patches, tasks = cases.get("two_body")
     ref = oracle_lib.OracleField(images, patches).elbo_batch(tasks, mode=2)

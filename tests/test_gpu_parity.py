@@ -185,9 +185,42 @@ def test_deterministic_and_mode_consistent(cj):
     for k in ("v", "d", "h"):
         assert np.array_equal(a[k], b[k])
     g = field.elbo_batch(tasks, mode=1)
+    g2 = field.elbo_batch(tasks, mode=1)
     v0 = field.elbo_batch(tasks, mode=0)
-    assert np.allclose(g["v"], a["v"], rtol=1e-13) and np.allclose(v0["v"], a["v"], rtol=1e-13)
-    assert np.allclose(g["d"], a["d"], rtol=1e-12, atol=0)
+    assert np.array_equal(g["v"], g2["v"]) and np.array_equal(g["d"], g2["d"])
+    # value / gradient modes walk the rows with the exp recurrence (march_kernel), the Hessian mode evaluates every
+    # pixel directly (pixel_kernel): equal up to the recurrence's accumulated rounding
+    assert np.allclose(g["v"], a["v"], rtol=1e-11) and np.allclose(v0["v"], a["v"], rtol=1e-11)
+    n = len(tasks)
+    gd, ad = g["d"].reshape(n, -1), a["d"].reshape(n, -1)
+    sc = np.abs(ad).max(axis=1, keepdims=True)
+    assert np.all(np.abs(gd - ad) <= 1e-10 * np.maximum(np.abs(ad), sc * 1e-3)), np.abs(gd - ad).max()
+
+
+@pytest.mark.parametrize("name", ["two_body", "masked", "clipped_and_empty", "crowded", "config2", "small_field", "wide_patch"])
+def test_march_kernel_matches_task_kernel(cj, name, monkeypatch):
+    """The two value / gradient kernels of the library -- march_kernel (row walks, exp recurrence; the default for
+    Sa = 1, K = 2) and task_kernel (direct evaluation; CELESTE_GRAD_KERNEL=task) -- agree to 1e-11, have identical
+    pixel-visit counters, and both meet the parity statement against the oracle."""
+    images, patches, tasks = cases.get(name)
+    field = cj.DeviceField(images, patches)
+    for mode in (0, 1):
+        ref = oracle_lib.OracleField(images, patches).elbo_batch(tasks, mode=mode, n_threads=8)
+        monkeypatch.setenv("CELESTE_GRAD_KERNEL", "task")
+        direct = field.elbo_batch(tasks, mode=mode)
+        monkeypatch.delenv("CELESTE_GRAD_KERNEL")
+        march = field.elbo_batch(tasks, mode=mode)
+        cases.assert_parity(ref, direct, mode, name + " task_kernel")
+        cases.assert_parity(ref, march, mode, name + " march_kernel")
+        assert np.array_equal(march["counters"], direct["counters"])
+        fin = np.isfinite(direct["v"])
+        assert np.all(np.abs(march["v"] - direct["v"])[fin] <= 1e-11 * np.abs(direct["v"])[fin])
+        if mode == 1:
+            n = len(tasks)
+            a, b = march["d"].reshape(n, -1), direct["d"].reshape(n, -1)
+            sc = np.abs(b).max(axis=1, keepdims=True)
+            assert np.all(np.abs(a - b) <= 1e-11 * np.maximum(np.abs(b), sc * 1e-3)), np.abs(a - b).max()
+            assert not np.array_equal(a, b) or not np.any(b), "CELESTE_GRAD_KERNEL did not switch kernels"
 
 
 @pytest.fixture(scope="module")
