@@ -200,9 +200,10 @@ struct celeste_plan {
     int n_taskblocks = 0;
     // march_kernel (value / gradient, Sa = 1, K = 2): one block per (sub, group of MARCH_NIMG images)
     DevBuf<TaskHdr> marchmap;
+    DevBuf<int> march_part_ptr;      // n_subs + 1: the partial vectors (= blocks) of each sub
     DevBuf<long long> bg_ptr;
     DevBuf<double> bg;
-    int n_marchblocks = 0, march_groups = 0;
+    int n_marchblocks = 0;
     bool use_march = false;
     DevBuf<PairHdr> pairmap;
     DevBuf<double> slotimg, slotbr, partials, pair_partials;
@@ -746,10 +747,18 @@ int celeste_plan_create_multi(int32_t n_fields, celeste_field* const* fields, ce
         pl->use_march = want && pl->uniform_K == 2 && n_subs == n_tasks;
     }
     if (pl->use_march) {
-        const int ngroups = (pl->N + MARCH_NIMG - 1) / MARCH_NIMG;
-        pl->march_groups = ngroups;
-        static_assert(TASK_NIMG == MARCH_NIMG, "march_kernel reuses task_kernel's (sub, image group) blocks");
-        const std::vector<TaskHdr>& mm = taskmap;   // same blocks, same heaviest-first order
+        long split = 6000;                         // pixels of a source above which it gets one block per image
+        if (const char* env = std::getenv("CELESTE_MARCH_SPLIT"))   // kernel-tuning knob
+            if (std::atol(env) > 0) split = std::atol(env);
+        std::vector<TaskHdr> mm;
+        std::vector<int> part_ptr;
+        build_march_blocks(n_subs, pl->N, sub_task.data(), sub_slot.data(), task_ptr, tfield.data(), sub_ptr.data(),
+                           [&](int u, int n) {
+                               const celeste_field* f = fields[tfield[sub_task[u]]];
+                               const PatchDev& pa = f->h_patches[(size_t)src_row[sub_slot[u]] + (size_t)n * f->S_tot];
+                               return (long)pa.H2 * pa.W2;
+                           },
+                           split, mm, part_ptr);
         std::vector<long long> bg_ptr((size_t)n_subs * pl->N, -1);
         long long bg_total = 0;
         for (int u = 0; u < n_subs; ++u) {
@@ -765,6 +774,7 @@ int celeste_plan_create_multi(int32_t n_fields, celeste_field* const* fields, ce
         }
         pl->n_marchblocks = (int)mm.size();
         CUDA_TRY(pl->marchmap.upload(mm));
+        CUDA_TRY(pl->march_part_ptr.upload(part_ptr));
         CUDA_TRY(pl->bg_ptr.upload(bg_ptr));
         CUDA_TRY(pl->bg.alloc((size_t)bg_total));
     }
@@ -790,7 +800,7 @@ int celeste_plan_create_multi(int32_t n_fields, celeste_field* const* fields, ce
     CUDA_TRY(pl->slotimg.alloc((size_t)n_slots * pl->N * SLOTIMG_STRIDE));
     CUDA_TRY(pl->slotbr.alloc((size_t)n_slots * SLOTBR_STRIDE));
     CUDA_TRY(pl->partials.alloc(std::max({(size_t)pl->n_blocks * NACC_MODE2, (size_t)n_subs * pl->N * TASK_WARPS * NACC_MODE1,
-                                           (size_t)n_subs * pl->march_groups * NT_ACC})));
+                                           (size_t)pl->n_marchblocks * NT_ACC})));
     *out = pl.release();
     return CELESTE_OK;
 }
@@ -890,9 +900,9 @@ static int launch_mode(celeste_plan* p, const double* vp_dev, double* v, double*
         if (p->use_march) {
             // value / gradient, production shape: row walks with the exp recurrence (march_kernels.cuh)
             if (p->n_marchblocks > 0)
-                march_kernel<MODE><<<p->n_marchblocks, MARCH_THREADS, march_smem_bytes(), st>>>(pd, p->marchmap.p, p->march_groups);
+                march_kernel<MODE><<<p->n_marchblocks, MARCH_THREADS, march_smem_bytes(), st>>>(pd, p->marchmap.p);
             if (p->timing) CUDA_TRY(cudaEventRecord(p->ev[2], st));
-            march_epilogue_kernel<MODE><<<p->n_tasks, MEPI_THREADS, 0, st>>>(pd, vp_dev, p->march_groups, v, d, counters, flags);
+            march_epilogue_kernel<MODE><<<p->n_tasks, MEPI_THREADS, 0, st>>>(pd, vp_dev, p->march_part_ptr.p, v, d, counters, flags);
             if (p->timing) CUDA_TRY(cudaEventRecord(p->ev[3], st));
             CUDA_TRY(cudaGetLastError());
             return CELESTE_OK;

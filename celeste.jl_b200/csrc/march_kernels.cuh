@@ -29,13 +29,19 @@
 
 #include "celeste_kernels.cuh"
 
+#ifdef CELESTE_HOST_EMULATION
+#define CEL_PREFETCH_L1(p) ((void)(p))
+#else
+#define CEL_PREFETCH_L1(p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p))
+#endif
+
 namespace celeste {
 
 #ifndef CELESTE_MARCH_MAXSEG
 #define CELESTE_MARCH_MAXSEG 16
 #endif
 #ifndef CELESTE_MARCH_MINB
-#define CELESTE_MARCH_MINB 2
+#define CELESTE_MARCH_MINB 3
 #endif
 #ifndef CELESTE_MARCH_THREADS
 #define CELESTE_MARCH_THREADS 128
@@ -96,23 +102,51 @@ __device__ inline void march_stage_srcimg(const PlanDev& plan, const PatchDev& p
     si[SI_THETA + 1] = 0.0;
 }
 
-// exact start of a walk at image pixel (hh, ww): f = z exp(-q/2) and the column ratio r for every component
-__device__ __forceinline__ void march_start(const double* recs, const double* etab, double hh, double ww, double* fp,
+// A walk is carried by a PAIR of adjacent lanes: lane parity kk = PSF component (K = 2), so each lane keeps the 14
+// prototype components of one PSF component in registers (28 doubles of state instead of 56: twice the warps per
+// SM).  Every iteration advances two columns: both lanes accumulate their half of the mixture sums of both
+// pixels, exchange one pixel's sums by a shuffle, and each lane finishes ITS pixel (star, pixel term) -- no work is
+// duplicated.  All loops are warp-uniform (iteration counts are maxima over the warp), so shuffles use full masks.
+constexpr int NPW = 16;                         // pairs (walks) per warp
+constexpr int NPAIR = MARCH_THREADS / 2;        // walks in flight per block
+
+// exact start at image pixel (hh, ww): f = z exp(-q/2) and the column ratio r for the 14 components of PSF
+// component kk (records c = 2 j + kk)
+__device__ __forceinline__ void march_start(const double* recs_k, const double* etab, double hh, double ww, double* fp,
                                             double* rr) {
 #pragma unroll
-    for (int c = 0; c < NC2; ++c) {
-        const double* o = recs + c * MREC;
+    for (int j = 0; j < NPROTO; ++j) {
+        const double* o = recs_k + j * 2 * MREC;
         const double l11 = o[0], l12 = o[1], l22 = o[2], mu1 = o[4], mu2 = o[5], z = o[6];
         const double d1 = hh - mu1, d2 = ww - mu2;
         const double p1 = l11 * d1 + l12 * d2;
         const double p2 = l12 * d1 + l22 * d2;
         const double q = d1 * p1 + d2 * p2;
-        fp[c] = z * exp_scaled_tab(q, -0.5, etab);
+        fp[j] = z * exp_scaled_tab(q, -0.5, etab);
         // exp(-(q(w+1) - q(w)) / 2); the argument may be positive (walking towards the centre): bounded so that
         // r stays finite however large the patch is
-        rr[c] = exp_scaled_tab(fmin(-(p2 + 0.5 * l22), 700.0), 1.0, etab);
+        rr[j] = exp_scaled_tab(fmin(-(p2 + 0.5 * l22), 700.0), 1.0, etab);
     }
 }
+
+__device__ __forceinline__ int warp_max_int(int v) {
+    double d = (double)v;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d = fmax(d, __shfl_xor_sync(0xffffffffu, d, o));
+    return (int)d;
+}
+
+// pointers and geometry of one image and of the active source's patch in it (shared memory)
+struct MarchImg {
+    const float* pixels;
+    const float* sky;
+    const double* pixconst;
+    const float* iota;
+    const uint8_t* bitmap;
+    const double* coefs;
+    double* bg;                 // (E_bg, V_bg) planes of this (sub, image), or null
+    int H2, W2, off_h, off_w, imgH, n1, n2, band0;
+};
 
 // unit tables of a block (shared memory): walks are numbered image by image, rows fastest
 struct MarchUnits {
@@ -124,20 +158,22 @@ struct MarchUnits {
 // One block per (active source of a task, group of <= MARCH_NIMG images).
 template <int MODE>
 __global__ void __launch_bounds__(MARCH_THREADS, CELESTE_MARCH_MINB)
-    march_kernel(PlanDev plan, const TaskHdr* __restrict__ taskmap, int ngroups) {
+    march_kernel(PlanDev plan, const TaskHdr* __restrict__ taskmap) {
     static_assert(MODE <= 1, "the Hessian mode uses pixel_kernel");
     constexpr int NUA = MODE == 0 ? 1 : NACC_MODE1;   // (c, y)-space accumulators of the current walk
+    constexpr int NS = MODE == 0 ? 2 : 7;             // mixture sums per pixel: F_dev F_exp | AX1 AX2 AS1 AS2 AS3
     CEL_DYNAMIC_SMEM(smem);
-    double* tacc = smem;                                   // NT_ACC x MARCH_THREADS
-    double* s_arec = tacc + NT_ACC * MARCH_THREADS;        // MARCH_NIMG x NC2 x MREC   (active source)
-    double* s_nrec = s_arec + MARCH_NIMG * NC2 * MREC;     // MARCH_NIMG x NC2 x MREC   (current neighbour)
-    double* s_asi = s_nrec + MARCH_NIMG * NC2 * MREC;      // MARCH_NIMG x SI_STRIDE
-    double* s_nsi = s_asi + MARCH_NIMG * SI_STRIDE;        // MARCH_NIMG x SI_STRIDE
+    double* tacc = smem;                                   // NT_ACC x MARCH_THREADS: task-space sums of this thread
+    double* uacc = tacc + NT_ACC * MARCH_THREADS;          // NUA x MARCH_THREADS: (c, y)-space sums of the current walk
+    double* s_rec = uacc + NACC_MODE1 * MARCH_THREADS;     // MARCH_NIMG x NC2 x MREC: the source being walked
+    double* s_si = s_rec + MARCH_NIMG * NC2 * MREC;        // MARCH_NIMG x SI_STRIDE
     __shared__ double s_exptab[8];
     __shared__ MarchUnits s_au, s_nu;                      // walks of the active source / of the current neighbour
+    __shared__ MarchImg s_img[MARCH_NIMG];
     __shared__ unsigned s_hasbg;
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, kk = tid & 1;
+    const int pair0 = (tid >> 5) * NPW;                    // first walk slot of this warp
     const TaskHdr th = taskmap[blockIdx.x];
     if (plan.task_mask && !plan.task_mask[th.task]) return;
     const int slot0 = th.slot0, slot1 = th.slot1, aslot = th.aslot;
@@ -148,14 +184,8 @@ __global__ void __launch_bounds__(MARCH_THREADS, CELESTE_MARCH_MINB)
 
 #pragma unroll
     for (int a = 0; a < NT_ACC; ++a) tacc[a * MARCH_THREADS + tid] = 0.0;
-    for (int i = tid; i < nimg * NC2; i += MARCH_THREADS) {
-        const int k = i / NC2, c = i - k * NC2;
-        march_stage_records(plan.slotimg + ((size_t)aslot * plan.N + th.n0 + k) * SLOTIMG_STRIDE, s_arec + k * NC2 * MREC, c);
-    }
-    if (tid < nimg) {
-        const int k = tid, n = th.n0 + k;
-        march_stage_srcimg<MODE>(plan, apatch[(size_t)n * field.S_tot], aslot, n, field.images[n].band - 1, s_asi + k * SI_STRIDE);
-    }
+#pragma unroll
+    for (int a = 0; a < NUA; ++a) uacc[a * MARCH_THREADS + tid] = 0.0;
 #ifdef CELESTE_HOST_EMULATION
     if (tid < 8) s_exptab[tid] = h_exptab[tid];
 #else
@@ -163,7 +193,7 @@ __global__ void __launch_bounds__(MARCH_THREADS, CELESTE_MARCH_MINB)
 #endif
     if (tid == MARCH_THREADS - 1) {
         // walks of the active source: every row of every image, cut into nseg column segments.  nseg minimises
-        // warp-rounds x (segment length + cost of an exact start, ~1.7 pixels)
+        // warp-rounds x (iterations of two columns + cost of an exact start, ~2 columns)
         int rows = 0, maxw = 0;
         for (int k = 0; k < nimg; ++k) {
             const PatchDev& pa = apatch[(size_t)(th.n0 + k) * field.S_tot];
@@ -177,7 +207,7 @@ __global__ void __launch_bounds__(MARCH_THREADS, CELESTE_MARCH_MINB)
         int nseg = nmin;
         for (int cand = nmin; cand < nmin + 4; ++cand) {
             const int L = (maxw + cand - 1) / cand;
-            const long cost = (long)((rows * cand + 31) / 32) * (10 * L + 17);
+            const long cost = (long)((rows * cand + NPW - 1) / NPW) * (10 * ((L + 1) / 2) + 6);
             if (best < 0 || cost < best) {
                 best = cost;
                 nseg = cand;
@@ -257,79 +287,89 @@ __global__ void __launch_bounds__(MARCH_THREADS, CELESTE_MARCH_MINB)
             for (int i = tid; i < nimg * NC2; i += MARCH_THREADS) {
                 const int k = i / NC2, c = i - k * NC2;
                 if (s_nu.ubeg[k + 1] > s_nu.ubeg[k])
-                    march_stage_records(plan.slotimg + ((size_t)s * plan.N + th.n0 + k) * SLOTIMG_STRIDE, s_nrec + k * NC2 * MREC, c);
+                    march_stage_records(plan.slotimg + ((size_t)s * plan.N + th.n0 + k) * SLOTIMG_STRIDE, s_rec + k * NC2 * MREC, c);
             }
             if (tid < nimg && s_nu.ubeg[tid + 1] > s_nu.ubeg[tid]) {
                 const int k = tid, n = th.n0 + k;
                 march_stage_srcimg<0>(plan, field.patches[plan.src_row[s] + (size_t)n * field.S_tot], s, n,
-                                      field.images[n].band - 1, s_nsi + k * SI_STRIDE);
+                                      field.images[n].band - 1, s_si + k * SI_STRIDE);
             }
             __syncthreads();
             double cnt_inactive = 0.0;
-            for (int u = tid; u < total; u += MARCH_THREADS) {
+            for (int ub = pair0; ub < total; ub += NPAIR) {        // warp-uniform
+                const int u = ub + (lane >> 1);
+                const bool has = u < total;
                 int k = 0;
 #pragma unroll
-                for (int kk = 1; kk < MARCH_NIMG; ++kk) k += (u >= s_nu.ubeg[kk]) ? 1 : 0;
+                for (int q = 1; q < MARCH_NIMG; ++q) k += (has && u >= s_nu.ubeg[q]) ? 1 : 0;
                 const int n = th.n0 + k;
-                const int ul = u - s_nu.ubeg[k];
                 const MarchBox bx = s_nu.box[k];
                 const int nsg = s_nu.nseg[k];
-                const int seg = ul / bx.nh, row = ul - seg * bx.nh;
+                const int ul = has ? u - s_nu.ubeg[k] : 0;
+                const int nh = max(bx.nh, 1);
+                const int seg = ul / nh, row = ul - seg * nh;
                 const int segw = (bx.nw + nsg - 1) / nsg;
-                const int c0 = seg * segw, len = min(segw, bx.nw - c0);
-                if (len <= 0) continue;
+                const int c0 = seg * segw;
+                const int len = has ? max(min(segw, bx.nw - c0), 0) : 0;
+                const int nit = warp_max_int((len + 1) >> 1);
+                if (nit == 0) continue;
                 const int h = bx.h0 + row, w0 = bx.w0 + c0;     // 1-based image coordinates
                 const PatchDev& pa = apatch[(size_t)n * field.S_tot];
                 const PatchDev& p = field.patches[plan.src_row[s] + (size_t)n * field.S_tot];
                 const int aH2 = pa.H2, aW2 = pa.W2, nH2 = p.H2, imgH = field.images[n].H, n1 = p.n1, n2 = p.n2;
                 const double* coefs = p.coefs;
-                const double* si = s_nsi + k * SI_STRIDE;
-                const double* recs = s_nrec + k * NC2 * MREC;
-                double fp[NC2], rr[NC2];
+                const double* si = s_si + k * SI_STRIDE;
+                const double* recs = s_rec + (k * NC2 + kk) * MREC;      // this lane's PSF component
+                double fp[NPROTO], rr[NPROTO];
                 march_start(recs, s_exptab, (double)h, (double)w0, fp, rr);
-                // star: sliding window of row-interpolated columns
+                // star: sliding window of row-interpolated columns, own pixels are columns kk, kk + 2, ...
                 const double ax = (double)h - si[SI_M] + 26.0, ay0 = (double)w0 - si[SI_M + 1] + 26.0;
                 const int ixf = (int)floor(ax), iy0 = (int)floor(ay0);
-                const bool fast = ixf >= 1 && ixf <= n1 - 3 && iy0 >= 1 && iy0 + len - 1 <= n2 - 3;
-                double R0 = 0.0, R1 = 0.0, R2 = 0.0;
-                const double* ccol = coefs + (size_t)(iy0 - 1) * n1 + (ixf - 1);
-                if (fast) {
+                const bool fast = len > 0 && ixf >= 1 && ixf <= n1 - 3 && iy0 >= 1 && iy0 + len - 1 <= n2 - 3;
+                double R0 = 0.0, R1 = 0.0;
+                const double* ccol = coefs + (size_t)(fast ? iy0 - 1 + kk : 0) * n1 + (fast ? ixf - 1 : 0);
+                if (fast && kk < len) {
                     const double wx0 = si[SI_WX], wx1 = si[SI_WX + 1], wx2 = si[SI_WX + 2], wx3 = si[SI_WX + 3];
                     R0 = wx0 * __ldg(ccol) + wx1 * __ldg(ccol + 1) + wx2 * __ldg(ccol + 2) + wx3 * __ldg(ccol + 3);
                     ccol += n1;
                     R1 = wx0 * __ldg(ccol) + wx1 * __ldg(ccol + 1) + wx2 * __ldg(ccol + 2) + wx3 * __ldg(ccol + 3);
                     ccol += n1;
-                    R2 = wx0 * __ldg(ccol) + wx1 * __ldg(ccol + 1) + wx2 * __ldg(ccol + 2) + wx3 * __ldg(ccol + 3);
-                    ccol += n1;
                 }
                 const int ah2 = h - pa.off_h - 1, nh2 = h - p.off_h - 1;
-                const uint8_t* abit = pa.bitmap + ah2 + (size_t)(w0 - pa.off_w - 1) * aH2;
-                const uint8_t* nbit = p.bitmap + nh2 + (size_t)(w0 - p.off_w - 1) * nH2;
-                const float* px = field.images[n].pixels + (size_t)(h - 1) + (size_t)(w0 - 1) * imgH;
-                double* bgE = plan.bg + bgp[n] + ah2 + (size_t)(w0 - pa.off_w - 1) * aH2;
+                const int acol = w0 - pa.off_w - 1 + kk, ncol = w0 - p.off_w - 1 + kk;      // own first column, 0-based
+                const uint8_t* abit = pa.bitmap + ah2 + (size_t)acol * aH2;
+                const uint8_t* nbit = p.bitmap + nh2 + (size_t)ncol * nH2;
+                const float* px = field.images[n].pixels + (size_t)(h - 1) + (size_t)(w0 - 1 + kk) * imgH;
+                double* bgE = plan.bg + (has ? bgp[n] : 0) + ah2 + (size_t)acol * aH2;
                 const size_t bgplane = (size_t)aH2 * aW2;
                 const double theta = si[SI_THETA];
-                for (int i = 0; i < len; ++i) {
-                    const bool valid = *abit && *nbit && !isnan(*px);
-                    abit += aH2;
-                    nbit += nH2;
-                    px += imgH;
-                    double R3 = 0.0;
-                    if (fast) {
-                        R3 = si[SI_WX] * __ldg(ccol) + si[SI_WX + 1] * __ldg(ccol + 1) + si[SI_WX + 2] * __ldg(ccol + 2) +
-                             si[SI_WX + 3] * __ldg(ccol + 3);
+                for (int t = 0; t < nit; ++t) {
+                    const bool own = 2 * t + kk < len;
+                    bool valid = false;
+                    if (own) valid = *abit && *nbit && !isnan(*px);
+                    double R2 = 0.0, R3 = 0.0;
+                    if (fast && own) {
+                        const double wx0 = si[SI_WX], wx1 = si[SI_WX + 1], wx2 = si[SI_WX + 2], wx3 = si[SI_WX + 3];
+                        R2 = wx0 * __ldg(ccol) + wx1 * __ldg(ccol + 1) + wx2 * __ldg(ccol + 2) + wx3 * __ldg(ccol + 3);
+                        ccol += n1;
+                        R3 = wx0 * __ldg(ccol) + wx1 * __ldg(ccol + 1) + wx2 * __ldg(ccol + 2) + wx3 * __ldg(ccol + 3);
                         ccol += n1;
                     }
-                    double Fd = 0.0, Fe = 0.0;
+                    // this lane's half of the mixture value of both pixels
+                    double S[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
 #pragma unroll
-                    for (int c = 0; c < NC2; ++c) {
-                        if (c < NPROTO_DEV * 2)
-                            Fd += fp[c];
-                        else
-                            Fe += fp[c];
-                        fp[c] *= rr[c];
-                        rr[c] *= recs[c * MREC + 3];
+                    for (int pix = 0; pix < 2; ++pix) {
+#pragma unroll
+                        for (int j = 0; j < NPROTO; ++j) {
+                            S[pix][j < NPROTO_DEV ? 0 : 1] += fp[j];
+                            fp[j] *= rr[j];
+                            rr[j] *= recs[j * 2 * MREC + 3];
+                        }
                     }
+                    // the partner's half of MY pixel
+                    double Fd = kk == 0 ? S[0][0] : S[1][0], Fe = kk == 0 ? S[0][1] : S[1][1];
+                    Fd += __shfl_xor_sync(0xffffffffu, kk == 0 ? S[1][0] : S[0][0], 1);
+                    Fe += __shfl_xor_sync(0xffffffffu, kk == 0 ? S[1][1] : S[0][1], 1);
                     if (valid) {
                         double f0;
                         if (fast) {
@@ -337,7 +377,7 @@ __global__ void __launch_bounds__(MARCH_THREADS, CELESTE_MARCH_MINB)
                             f0 = v < 0 ? 1e-3 * exp_nonpos(v) : 1e-3 * (v + 1.0);     // softpluslikeinv, fsm_util.jl:222
                         } else {
                             double gd[2], hd[3];
-                            star_eval<0>(LdGlobal(), coefs, n1, n2, ax, ay0 + (double)i, f0, gd, hd);
+                            star_eval<0>(LdGlobal(), coefs, n1, n2, ax, ay0 + (double)(2 * t + kk), f0, gd, hd);
                         }
                         const double f1 = theta * Fd + (1.0 - theta) * Fe;
                         const double Es = si[SI_CB] * f0 + si[SI_CB + 1] * f1;
@@ -346,176 +386,152 @@ __global__ void __launch_bounds__(MARCH_THREADS, CELESTE_MARCH_MINB)
                         bgE[bgplane] += E2s - Es * Es;
                         cnt_inactive += 1.0;                                          // elbo_objective.jl:353-357
                     }
-                    bgE += aH2;
-                    R0 = R1;
-                    R1 = R2;
-                    R2 = R3;
+                    abit += 2 * aH2;
+                    nbit += 2 * nH2;
+                    px += 2 * imgH;
+                    bgE += 2 * aH2;
+                    R0 = R2;
+                    R1 = R3;
                 }
             }
             tacc[TA_CNT_INACTIVE * MARCH_THREADS + tid] += cnt_inactive;
         }
-        __syncthreads();          // every neighbour's sums are visible to the walk of the active source
+        __syncthreads();          // every neighbour's sums are visible to the walk of the active source; s_rec is free
     }
+    for (int i = tid; i < nimg * NC2; i += MARCH_THREADS) {
+        const int k = i / NC2, c = i - k * NC2;
+        march_stage_records(plan.slotimg + ((size_t)aslot * plan.N + th.n0 + k) * SLOTIMG_STRIDE, s_rec + k * NC2 * MREC, c);
+    }
+    if (tid < nimg) {
+        const int k = tid, n = th.n0 + k;
+        const PatchDev& pa = apatch[(size_t)n * field.S_tot];
+        const ImageDev& img = field.images[n];
+        march_stage_srcimg<MODE>(plan, pa, aslot, n, img.band - 1, s_si + k * SI_STRIDE);
+        MarchImg mi;
+        mi.pixels = img.pixels;
+        mi.sky = img.sky;
+        mi.pixconst = img.pixconst;
+        mi.iota = img.iota;
+        mi.bitmap = pa.bitmap;
+        mi.coefs = pa.coefs;
+        mi.bg = ((hasbg >> k) & 1u) ? plan.bg + bgp[n] : nullptr;
+        mi.H2 = pa.H2;
+        mi.W2 = pa.W2;
+        mi.off_h = pa.off_h;
+        mi.off_w = pa.off_w;
+        mi.imgH = img.H;
+        mi.n1 = pa.n1;
+        mi.n2 = pa.n2;
+        mi.band0 = img.band - 1;
+        s_img[k] = mi;
+    }
+    __syncthreads();
 
     // ---- the active source -----------------------------------------------------------------------------------
+    // (pointers and geometry of the images live in shared memory and are re-read where used: the walk keeps its
+    //  registers for the 28 doubles of component state and the 14 mixture sums)
     const int total = s_au.ubeg[MARCH_NIMG];
-    for (int u = tid; u < total; u += MARCH_THREADS) {
+    for (int ub = pair0; ub < total; ub += NPAIR) {                // warp-uniform
+        const int u = ub + (lane >> 1);
+        const bool has = u < total;
         int k = 0;
 #pragma unroll
-        for (int kk = 1; kk < MARCH_NIMG; ++kk) k += (u >= s_au.ubeg[kk]) ? 1 : 0;
-        const int n = th.n0 + k;
+        for (int q = 1; q < MARCH_NIMG; ++q) k += (has && u >= s_au.ubeg[q]) ? 1 : 0;
+        const MarchImg& mi = s_img[k];
+        const int H2 = max(mi.H2, 1), W2 = mi.W2;
         const int nseg = s_au.nseg[k];
-        const PatchDev& pa = apatch[(size_t)n * field.S_tot];
-        const int H2 = pa.H2, W2 = pa.W2, n1 = pa.n1, n2 = pa.n2;
-        const double* coefs = pa.coefs;
-        const ImageDev& img = field.images[n];
-        const int imgH = img.H, band0 = img.band - 1;
-        const int ul = u - s_au.ubeg[k];
+        const int ul = has ? u - s_au.ubeg[k] : 0;
         const int seg = ul / H2, h2 = ul - seg * H2;
         const int segw = (W2 + nseg - 1) / nseg;
-        const int c0 = seg * segw, len = min(segw, W2 - c0);
-        if (len <= 0) continue;
+        const int c0 = seg * segw;
+        const int len = has ? max(min(segw, W2 - c0), 0) : 0;
+        const int nit = warp_max_int((len + 1) >> 1);
+        if (nit == 0) continue;
         const int ncov = min(len, W2 - 1 - c0);                   // pixels before the (uncovered) last column, :349
-        const int h = pa.off_h + h2 + 1, w0 = pa.off_w + c0 + 1;     // 1-based image coordinates
-        const double* si = s_asi + k * SI_STRIDE;
-        const double* recs = s_arec + k * NC2 * MREC;
-        double fp[NC2], rr[NC2];
+        const int h = mi.off_h + h2 + 1, w0 = mi.off_w + c0 + 1;     // 1-based image coordinates
+        const double* si = s_si + k * SI_STRIDE;
+        const double* recs = s_rec + (k * NC2 + kk) * MREC;          // this lane's PSF component
+        double fp[NPROTO], rr[NPROTO];
         march_start(recs, s_exptab, (double)h, (double)w0, fp, rr);
-        const double d1a = (double)h - recs[4], d1b = (double)h - recs[MREC + 4];       // x1 - mu1 of PSF component 0 / 1
-        double d2a = (double)w0 - recs[5], d2b = (double)w0 - recs[MREC + 5];
-        // star
-        const double ax = (double)h - si[SI_M] + 26.0, ay0 = (double)w0 - si[SI_M + 1] + 26.0;
-        const int ixf = (int)floor(ax), iy0 = (int)floor(ay0);
-        const bool fast = ixf >= 1 && ixf <= n1 - 3 && iy0 >= 1 && iy0 + len - 1 <= n2 - 3;
-        double R0 = 0.0, R1 = 0.0, R2 = 0.0, D0 = 0.0, D1 = 0.0, D2 = 0.0;
-        const double* ccol = coefs + (size_t)(iy0 - 1) * n1 + (ixf - 1);
-        if (fast) {
+        const double d1 = (double)h - recs[4];                        // x1 - mu1 of this PSF component
+        double d2 = (double)w0 - recs[5];
+        // star: own pixels are columns kk, kk + 2, ... of the segment
+        bool fast;
+        int coff;                                                     // offset of the next spline column in coefs
+        {
+            const int ixf = (int)floor((double)h - si[SI_M] + 26.0), iy0 = (int)floor((double)w0 - si[SI_M + 1] + 26.0);
+            fast = len > 0 && ixf >= 1 && ixf <= mi.n1 - 3 && iy0 >= 1 && iy0 + len - 1 <= mi.n2 - 3;
+            coff = fast ? (iy0 - 1 + kk) * mi.n1 + (ixf - 1) : 0;
+        }
+        double R0 = 0.0, R1 = 0.0, D0 = 0.0, D1 = 0.0;
+        if (fast && kk < len) {
 #pragma unroll
-            for (int b = 0; b < 3; ++b) {
+            for (int b = 0; b < 2; ++b) {
+                const double* ccol = mi.coefs + coff;
                 const double q0 = __ldg(ccol), q1 = __ldg(ccol + 1), q2 = __ldg(ccol + 2), q3 = __ldg(ccol + 3);
                 const double r = si[SI_WX] * q0 + si[SI_WX + 1] * q1 + si[SI_WX + 2] * q2 + si[SI_WX + 3] * q3;
                 double d = 0.0;
                 if (MODE >= 1) d = si[SI_DWX] * q0 + si[SI_DWX + 1] * q1 + si[SI_DWX + 2] * q2 + si[SI_DWX + 3] * q3;
-                ccol += n1;
+                coff += mi.n1;
                 if (b == 0) {
                     R0 = r;
                     D0 = d;
-                } else if (b == 1) {
+                } else {
                     R1 = r;
                     D1 = d;
-                } else {
-                    R2 = r;
-                    D2 = d;
                 }
             }
         }
-        const bool bgk = (hasbg >> k) & 1u;
-        const size_t pix0 = (size_t)h2 + (size_t)c0 * H2;
-        const uint8_t* abit = pa.bitmap + pix0;
-        const size_t ipix0 = (size_t)(h - 1) + (size_t)(w0 - 1) * imgH;
-        const float* px = img.pixels + ipix0;
-        const float* psky = img.sky + ipix0;
-        const double* ppc = img.pixconst + ipix0;
-        const double* bgE = plan.bg + (bgk ? bgp[n] : 0) + pix0;
-        const size_t bgplane = (size_t)H2 * W2;
-        const double iota = (double)img.iota[h - 1];
-        const double theta = si[SI_THETA];
-        const double cb[4] = {si[SI_CB], si[SI_CB + 1], si[SI_CB + 2], si[SI_CB + 3]};
-        double ua[NUA];
-#pragma unroll
-        for (int a = 0; a < NUA; ++a) ua[a] = 0.0;
+        int pix = h2 + (c0 + kk) * H2;                                // own pixel inside the patch
+        int ipix = (h - 1) + (w0 - 1 + kk) * mi.imgH;                 // ... and inside the image
+        double* ua = uacc + tid;
         double cnt_active = 0.0;
 
-        // per-pixel inputs are fetched one step ahead so their latency hides behind the FP64 work
-        struct PixIn {
-            unsigned char active;
-            float x, sky;
-            double pixconst, bE, bV;
-        };
-        auto fetch = [&](bool ok) {
-            PixIn in;
-            in.active = 0;
-            in.x = in.sky = 0.f;
-            in.pixconst = in.bE = in.bV = 0.0;
-            if (ok) {
-                in.active = *abit;
-                in.x = *px;
-                in.sky = *psky;
-                in.pixconst = *ppc;
-                if (bgk) {
-                    in.bE = bgE[0];
-                    in.bV = bgE[bgplane];
+        for (int t = 0; t < nit; ++t) {
+            const int iown = 2 * t + kk;
+            const bool own = iown < len;
+            // this lane's pixel: inputs (the next iteration's lines are requested now, so these loads hit L1) ...
+            unsigned char bit = 0;
+            float xf = 0.f, skyf = 0.f;
+            double pconst = 0.0, bE = 0.0, bV = 0.0;
+            double f0 = 0.0, g0[2] = {0.0, 0.0}, h0[3] = {0.0, 0.0, 0.0};
+            if (own) {
+                if (iown + 2 < len) {
+                    const int nx = ipix + 2 * mi.imgH;
+                    CEL_PREFETCH_L1(mi.pixels + nx);
+                    CEL_PREFETCH_L1(mi.sky + nx);
+                    CEL_PREFETCH_L1(mi.pixconst + nx);
                 }
-                abit += H2;
-                bgE += H2;
-                px += imgH;
-                psky += imgH;
-                ppc += imgH;
-            }
-            return in;
-        };
-        PixIn cur = fetch(true);
-        for (int i = 0; i < len; ++i) {
-            const PixIn nxt = fetch(i + 1 < len);
-            const bool live = cur.active && !isnan(cur.x);          // elbo_objective.jl:445, :459
-            double R3 = 0.0, D3 = 0.0;
-            if (fast) {
-                const double q0 = __ldg(ccol), q1 = __ldg(ccol + 1), q2 = __ldg(ccol + 2), q3 = __ldg(ccol + 3);
-                R3 = si[SI_WX] * q0 + si[SI_WX + 1] * q1 + si[SI_WX + 2] * q2 + si[SI_WX + 3] * q3;
-                if (MODE >= 1) D3 = si[SI_DWX] * q0 + si[SI_DWX + 1] * q1 + si[SI_DWX + 2] * q2 + si[SI_DWX + 3] * q3;
-                ccol += n1;
-            }
-            if (live && i < ncov) {
-                // mixture (populate_gal_fsm!, fsm_util.jl:194-219): unweighted sums of the two prototype groups
-                double F[2] = {0.0, 0.0}, AX1[2] = {0.0, 0.0}, AX2[2] = {0.0, 0.0}, AS1[2] = {0.0, 0.0}, AS2[2] = {0.0, 0.0},
-                       AS3[2] = {0.0, 0.0};
-#pragma unroll
-                for (int j = 0; j < NPROTO; ++j) {
-                    const int g = j < NPROTO_DEV ? 0 : 1;
-#pragma unroll
-                    for (int kk = 0; kk < 2; ++kk) {
-                        const int c = j * 2 + kk;
-                        const double* o = recs + c * MREC;
-                        const double f = fp[c];
-                        F[g] += f;
-                        if (MODE >= 1) {
-                            const double l11 = o[0], l12 = o[1], l22 = o[2];
-                            const double d1 = kk == 0 ? d1a : d1b, d2 = kk == 0 ? d2a : d2b;
-                            const double p1 = fma(l12, d2, l11 * d1);
-                            const double p2 = fma(l22, d2, l12 * d1);
-                            AX1[g] = fma(f, p1, AX1[g]);
-                            AX2[g] = fma(f, p2, AX2[g]);
-                            const double fn = f * c_proto_nu[j];
-                            AS1[g] = fma(fn, fma(p1, p1, -l11), AS1[g]);      // 2 x bvn_sig_d[1], BivariateNormals.jl:267-272
-                            AS2[g] = fma(fn, fma(p1, p2, -l12), AS2[g]);
-                            AS3[g] = fma(fn, fma(p2, p2, -l22), AS3[g]);      // 2 x bvn_sig_d[3]
-                        }
-                        fp[c] = f * rr[c];
-                        rr[c] *= o[3];
-                    }
+                bit = mi.bitmap[pix];
+                xf = mi.pixels[ipix];
+                skyf = mi.sky[ipix];
+                pconst = mi.pixconst[ipix];
+                if (mi.bg) {
+                    bE = mi.bg[pix];
+                    bV = mi.bg[pix + H2 * W2];
                 }
-                const double t0 = theta, t1 = 1.0 - theta;
-                GalRaw gal;
-                gal.f = t0 * F[0] + t1 * F[1];
-                if (MODE >= 1) {
-                    gal.r[0] = -(t0 * AX1[0] + t1 * AX1[1]);
-                    gal.r[1] = -(t0 * AX2[0] + t1 * AX2[1]);
-                    gal.r[2] = 0.5 * (t0 * AS1[0] + t1 * AS1[1]);
-                    gal.r[3] = t0 * AS2[0] + t1 * AS2[1];
-                    gal.r[4] = 0.5 * (t0 * AS3[0] + t1 * AS3[1]);
-                    gal.r[5] = F[0] - F[1];                                   // gal_frac_dev, fsm_util.jl:277-291
-                }
-                // star (star_light_density!, fsm_util.jl:225-248)
-                double f0, g0[2] = {0.0, 0.0}, h0[3] = {0.0, 0.0, 0.0};
+                // ... and star (star_light_density!, fsm_util.jl:225-248): two new columns of the sliding window
                 if (fast) {
+                    const double* ccol = mi.coefs + coff;
+                    const int n1 = mi.n1;
+                    const double q0 = __ldg(ccol), q1 = __ldg(ccol + 1), q2 = __ldg(ccol + 2), q3 = __ldg(ccol + 3);
+                    const double q4 = __ldg(ccol + n1), q5 = __ldg(ccol + n1 + 1), q6 = __ldg(ccol + n1 + 2), q7 = __ldg(ccol + n1 + 3);
+                    const double R2 = si[SI_WX] * q0 + si[SI_WX + 1] * q1 + si[SI_WX + 2] * q2 + si[SI_WX + 3] * q3;
+                    const double R3 = si[SI_WX] * q4 + si[SI_WX + 1] * q5 + si[SI_WX + 2] * q6 + si[SI_WX + 3] * q7;
                     const double wy0 = si[SI_WY], wy1 = si[SI_WY + 1], wy2 = si[SI_WY + 2], wy3 = si[SI_WY + 3];
                     const double v = wy0 * R0 + wy1 * R1 + wy2 * R2 + wy3 * R3;
                     double gx = 0.0, gy = 0.0;
                     if (MODE >= 1) {
+                        const double D2 = si[SI_DWX] * q0 + si[SI_DWX + 1] * q1 + si[SI_DWX + 2] * q2 + si[SI_DWX + 3] * q3;
+                        const double D3 = si[SI_DWX] * q4 + si[SI_DWX + 1] * q5 + si[SI_DWX + 2] * q6 + si[SI_DWX + 3] * q7;
                         gx = wy0 * D0 + wy1 * D1 + wy2 * D2 + wy3 * D3;
                         gy = si[SI_DWY] * R0 + si[SI_DWY + 1] * R1 + si[SI_DWY + 2] * R2 + si[SI_DWY + 3] * R3;
+                        D0 = D2;
+                        D1 = D3;
                     }
-                    if (v < 0) {                                              // softpluslikeinv, fsm_util.jl:222
+                    R0 = R2;
+                    R1 = R3;
+                    if (v < 0) {                                          // softpluslikeinv, fsm_util.jl:222
                         const double e = 1e-3 * exp_nonpos(v);
                         f0 = e;
                         g0[0] = e * gx;
@@ -525,65 +541,107 @@ __global__ void __launch_bounds__(MARCH_THREADS, CELESTE_MARCH_MINB)
                         g0[0] = 1e-3 * gx;
                         g0[1] = 1e-3 * gy;
                     }
-                } else {
-                    star_eval<MODE>(LdGlobal(), coefs, n1, n2, ax, ay0 + (double)i, f0, g0, h0);
-                }
-                PixelConsts pc;
-                pc.x = (double)cur.x;
-                pc.iota = iota;
-                pc.pixconst = cur.pixconst;
-                cnt_active += 1.0;
-                pixel_accumulate<MODE>(ua, 1, pc, (double)cur.sky + cur.bE, cur.bV, true, true, cb, f0, g0, h0, gal);
-            } else {
-#pragma unroll
-                for (int c = 0; c < NC2; ++c) {
-                    fp[c] *= rr[c];
-                    rr[c] *= recs[c * MREC + 3];
-                }
-                if (live) {
-                    // last column of the patch: the source does not cover it (value of the background only)
-                    PixelConsts pc;
-                    pc.x = (double)cur.x;
-                    pc.iota = iota;
-                    pc.pixconst = cur.pixconst;
-                    GalRaw gal;
-                    gal.f = 0.0;
-                    const double g0[2] = {0.0, 0.0}, h0[3] = {0.0, 0.0, 0.0};
-                    pixel_accumulate<MODE>(ua, 1, pc, (double)cur.sky + cur.bE, cur.bV, false, true, cb, 0.0, g0, h0, gal);
                 }
             }
-            d2a += 1.0;
-            d2b += 1.0;
-            R0 = R1;
-            R1 = R2;
-            R2 = R3;
-            D0 = D1;
-            D1 = D2;
-            D2 = D3;
-            cur = nxt;
+            // this lane's half (PSF component kk) of the mixture sums of both pixels (columns 2t and 2t + 1)
+            // (populate_gal_fsm!, fsm_util.jl:194-219); S = F_dev F_exp | AX1 AX2 AS1 AS2 AS3 (theta-weighted)
+            double S[2][NS];
+#pragma unroll
+            for (int q = 0; q < NS; ++q) S[0][q] = S[1][q] = 0.0;
+            const double theta = si[SI_THETA];
+#pragma unroll
+            for (int j = 0; j < NPROTO; ++j) {
+                const double* o = recs + j * 2 * MREC;
+                const double cc = o[3];
+                const double fa = fp[j];
+                const double ra = rr[j];
+                const double fb = fa * ra;               // column 2t + 1
+                const double rb = ra * cc;
+                fp[j] = fb * rb;                         // column 2t + 2
+                rr[j] = rb * cc;
+                S[0][j < NPROTO_DEV ? 0 : 1] += fa;
+                S[1][j < NPROTO_DEV ? 0 : 1] += fb;
+                if (MODE >= 1) {
+                    const double l11 = o[0], l12 = o[1], l22 = o[2];
+                    const double p1a = fma(l12, d2, l11 * d1), p1b = p1a + l12;
+                    const double p2a = fma(l22, d2, l12 * d1), p2b = p2a + l22;
+                    const double tw = j < NPROTO_DEV ? theta : 1.0 - theta;
+                    const double wa = fa * tw, wb = fb * tw;
+                    S[0][2] = fma(wa, p1a, S[0][2]);
+                    S[1][2] = fma(wb, p1b, S[1][2]);
+                    S[0][3] = fma(wa, p2a, S[0][3]);
+                    S[1][3] = fma(wb, p2b, S[1][3]);
+                    const double na = wa * c_proto_nu[j], nb = wb * c_proto_nu[j];
+                    S[0][4] = fma(na, fma(p1a, p1a, -l11), S[0][4]);      // 2 x bvn_sig_d[1], BivariateNormals.jl:267-272
+                    S[1][4] = fma(nb, fma(p1b, p1b, -l11), S[1][4]);
+                    S[0][5] = fma(na, fma(p1a, p2a, -l12), S[0][5]);
+                    S[1][5] = fma(nb, fma(p1b, p2b, -l12), S[1][5]);
+                    S[0][6] = fma(na, fma(p2a, p2a, -l22), S[0][6]);      // 2 x bvn_sig_d[3]
+                    S[1][6] = fma(nb, fma(p2b, p2b, -l22), S[1][6]);
+                }
+            }
+            d2 += 2.0;
+            // the partner's half of MY pixel (lane kk finishes the pixel of column 2 t + kk)
+            double T[NS];
+#pragma unroll
+            for (int q = 0; q < NS; ++q)
+                T[q] = (kk == 0 ? S[0][q] : S[1][q]) + __shfl_xor_sync(0xffffffffu, kk == 0 ? S[1][q] : S[0][q], 1);
+
+            if (own && bit && !isnan(xf)) {                          // elbo_objective.jl:445, :459
+                PixelConsts pc;
+                pc.x = (double)xf;
+                pc.iota = (double)mi.iota[h - 1];
+                pc.pixconst = pconst;
+                GalRaw gal;
+                const bool covered = iown < ncov;      // the last column of the patch is not covered by its own source (:349)
+                gal.f = theta * T[0] + (1.0 - theta) * T[1];
+                if (MODE >= 1) {
+                    gal.r[0] = -T[2];
+                    gal.r[1] = -T[3];
+                    gal.r[2] = 0.5 * T[4];
+                    gal.r[3] = T[5];
+                    gal.r[4] = 0.5 * T[6];
+                    gal.r[5] = T[0] - T[1];                               // gal_frac_dev, fsm_util.jl:277-291
+                }
+                if (covered) {
+                    if (!fast)
+                        star_eval<MODE>(LdGlobal(), mi.coefs, mi.n1, mi.n2, (double)h - si[SI_M] + 26.0,
+                                        (double)(w0 + iown) - si[SI_M + 1] + 26.0, f0, g0, h0);
+                    cnt_active += 1.0;
+                }
+                const double cb[4] = {si[SI_CB], si[SI_CB + 1], si[SI_CB + 2], si[SI_CB + 3]};
+                pixel_accumulate<MODE>(ua, MARCH_THREADS, pc, (double)skyf + bE, bV, covered, true, cb, f0, g0, h0, gal);
+            }
+            pix += 2 * H2;
+            ipix += 2 * mi.imgH;
+            coff += 2 * mi.n1;
         }
+        const int band0 = mi.band0;
         // leave the walk: (c, y) space of this image -> task space
         double* ta = tacc + tid;
-        ta[TA_VAL * MARCH_THREADS] += ua[ACC_VAL];
+        ta[TA_VAL * MARCH_THREADS] += ua[ACC_VAL * MARCH_THREADS];
+        ua[ACC_VAL * MARCH_THREADS] = 0.0;
         ta[TA_CNT_ACTIVE * MARCH_THREADS] += cnt_active;
         if (MODE >= 1) {
-            const double gx1 = ua[ACC_G], gx2 = ua[ACC_G + 1];
+            const double gx1 = ua[ACC_G * MARCH_THREADS], gx2 = ua[(ACC_G + 1) * MARCH_THREADS];
             ta[(TA_POS + 0) * MARCH_THREADS] -= si[SI_J + 0] * gx1 + si[SI_J + 1] * gx2;     // dx_a/dpos_b = -J[a + 2 b]
             ta[(TA_POS + 1) * MARCH_THREADS] -= si[SI_J + 2] * gx1 + si[SI_J + 3] * gx2;
 #pragma unroll
-            for (int q = 0; q < 3; ++q) ta[(TA_SIG + q) * MARCH_THREADS] += ua[ACC_G + 2 + q];
-            ta[TA_THETA * MARCH_THREADS] += ua[ACC_G + 5];
+            for (int q = 0; q < 3; ++q) ta[(TA_SIG + q) * MARCH_THREADS] += ua[(ACC_G + 2 + q) * MARCH_THREADS];
+            ta[TA_THETA * MARCH_THREADS] += ua[(ACC_G + 5) * MARCH_THREADS];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) ta[(TA_BAND + 4 * band0 + q) * MARCH_THREADS] += ua[ACC_C1 + q];
+            for (int q = 0; q < 4; ++q) ta[(TA_BAND + 4 * band0 + q) * MARCH_THREADS] += ua[(ACC_C1 + q) * MARCH_THREADS];
+#pragma unroll
+            for (int q = ACC_G; q < NACC_MODE1; ++q) ua[q * MARCH_THREADS] = 0.0;
         }
     }
     __syncthreads();
 
     // fixed-order block reduction, all of a warp's accumulators in flight
-    const int warp = tid >> 5, lane = tid & 31;
+    const int warp = tid >> 5;
     constexpr int NA = MODE == 0 ? TA_POS : NT_ACC;
     constexpr int NW = MARCH_THREADS / 32, PER = (NA + NW - 1) / NW;
-    double* out = plan.partials + ((size_t)th.sub * ngroups + th.n0 / MARCH_NIMG) * NT_ACC;
+    double* out = plan.partials + (size_t)th.pad1 * NT_ACC;       // pad1: this block's slot in the partials
     double sred[PER];
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
@@ -606,8 +664,54 @@ __global__ void __launch_bounds__(MARCH_THREADS, CELESTE_MARCH_MINB)
     }
 }
 
+// Host side: the blocks of a plan.  One block per (sub, group of <= MARCH_NIMG images); a source whose patches hold
+// more than `split_pixels` pixels gets one block per image so that no single block is a long tail of the launch.
+// Each block owns one NT_ACC-vector of plan.partials (TaskHdr::pad1); part_ptr[sub] .. part_ptr[sub + 1] are the
+// blocks of a sub, in image order.  pixels(sub, n) -> H2 * W2 of the active patch.
+template <typename Pix>
+inline void build_march_blocks(int n_subs, int N, const int* sub_task, const int* sub_slot, const int* task_ptr,
+                               const int* task_field, const int* sub_ptr, Pix pixels, long split_pixels,
+                               std::vector<TaskHdr>& blocks, std::vector<int>& part_ptr) {
+    blocks.clear();
+    part_ptr.assign((size_t)n_subs + 1, 0);
+    std::vector<long> cost;
+    for (int u = 0; u < n_subs; ++u) {
+        const int t = sub_task[u];
+        long tot = 0;
+        for (int n = 0; n < N; ++n) tot += pixels(u, n);
+        const int step = tot > split_pixels ? 1 : MARCH_NIMG;
+        for (int n0 = 0; n0 < N; n0 += step) {
+            TaskHdr th;
+            th.tn0 = u * N;
+            th.aslot = sub_slot[u];
+            th.slot0 = task_ptr[t];
+            th.slot1 = task_ptr[t + 1];
+            th.field = task_field ? task_field[t] : 0;
+            th.sub0 = sub_ptr[t];
+            th.sub = u;
+            th.sub1 = sub_ptr[t + 1];
+            th.n0 = n0;
+            th.n1 = std::min(N, n0 + step);
+            th.task = t;
+            th.pad1 = (int)blocks.size();
+            long c = 0;
+            for (int n = th.n0; n < th.n1; ++n) c += pixels(u, n) * (1 + (th.slot1 - th.slot0 - 1) / 4);
+            blocks.push_back(th);
+            cost.push_back(c);
+        }
+        part_ptr[u + 1] = (int)blocks.size();
+    }
+    // heaviest first, so the launch tail is short; the partial slot (pad1) keeps the per-sub order
+    std::vector<int> order(blocks.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cost[x] > cost[y]; });
+    std::vector<TaskHdr> sorted(blocks.size());
+    for (size_t i = 0; i < order.size(); ++i) sorted[i] = blocks[order[i]];
+    blocks.swap(sorted);
+}
+
 constexpr size_t march_smem_bytes() {
-    return ((size_t)NT_ACC * MARCH_THREADS + 2 * (size_t)MARCH_NIMG * NC2 * MREC + 2 * (size_t)MARCH_NIMG * SI_STRIDE) * sizeof(double);
+    return ((size_t)(NT_ACC + NACC_MODE1) * MARCH_THREADS + (size_t)MARCH_NIMG * NC2 * MREC + (size_t)MARCH_NIMG * SI_STRIDE) * sizeof(double);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -616,7 +720,8 @@ constexpr size_t march_smem_bytes() {
 constexpr int MEPI_THREADS = 64;
 
 template <int MODE>
-__global__ void __launch_bounds__(MEPI_THREADS) march_epilogue_kernel(PlanDev plan, const double* __restrict__ vp, int ngroups,
+__global__ void __launch_bounds__(MEPI_THREADS) march_epilogue_kernel(PlanDev plan, const double* __restrict__ vp,
+                                                                      const int* __restrict__ part_ptr,
                                                                       double* __restrict__ out_v, double* __restrict__ out_d,
                                                                       long long* __restrict__ out_counters,
                                                                       int* __restrict__ out_flags) {
@@ -633,7 +738,7 @@ __global__ void __launch_bounds__(MEPI_THREADS) march_epilogue_kernel(PlanDev pl
     constexpr int NA = MODE == 0 ? TA_POS : NT_ACC;
     if (tid < NA) {
         double s = 0.0;
-        for (int g = 0; g < ngroups; ++g) s += plan.partials[((size_t)sub * ngroups + g) * NT_ACC + tid];
+        for (int g = part_ptr[sub]; g < part_ptr[sub + 1]; ++g) s += plan.partials[(size_t)g * NT_ACC + tid];   // fixed order
         ysum[tid] = s;
     }
     if (tid == 32 && MODE >= 1) sigma_derivs(vs[3], vs[4], vs[5], J0, T0);

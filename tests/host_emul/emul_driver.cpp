@@ -34,6 +34,7 @@ void galaxy_prototypes(double eta[NPROTO], double nu[NPROTO]) {
     }
 }
 
+long g_march_split = 6000;   // pixels above which a source gets one march block per image (emul_set_grad_kernel(2) lowers it)
 int g_grad_kernel = 1;   // 1: march_kernel where the product would use it (Sa = 1, K = 2); 0: always task_kernel
 
 template <int MODE>
@@ -44,7 +45,17 @@ void run_task(PlanDev pd, const FieldDev& fd, const std::vector<TaskHdr>& taskma
         for (int i = 0; i < fd.S_tot * pd.N; ++i) all_k2 = all_k2 && fd.patches[i].K == 2;
         if (g_grad_kernel == 1 && all_k2 && pd.n_subs == pd.n_tasks) {
             // same launch sequence as celeste_abi.cu's march path
-            const int ngroups = (pd.N + MARCH_NIMG - 1) / MARCH_NIMG;
+            std::vector<int> sub_task(pd.n_subs), part_ptr;
+            for (int u = 0; u < pd.n_subs; ++u) sub_task[u] = u;
+            std::vector<TaskHdr> mm;
+            build_march_blocks(pd.n_subs, pd.N, sub_task.data(), pd.sub_slot, pd.task_ptr, (const int*)nullptr, pd.sub_ptr,
+                               [&](int u, int n) {
+                                   const PatchDev& pa = fd.patches[(size_t)pd.src_row[pd.sub_slot[u]] + (size_t)n * fd.S_tot];
+                                   return (long)pa.H2 * pa.W2;
+                               },
+                               g_march_split, mm, part_ptr);
+            std::vector<double> mpart(mm.size() * NT_ACC + 1);
+            pd.partials = mpart.data();
             std::vector<long long> bg_ptr((size_t)pd.n_subs * pd.N, -1);
             long long bg_total = 0;
             for (int u = 0; u < pd.n_subs; ++u) {
@@ -61,10 +72,10 @@ void run_task(PlanDev pd, const FieldDev& fd, const std::vector<TaskHdr>& taskma
             pd.bg_ptr = bg_ptr.data();
             pd.bg = bg.data();
             cuda_emul::launch(setup_kernel, 2, 64, 0, pd, vp);
-            if (!taskmap.empty())
-                cuda_emul::launch(march_kernel<MODE>, (int)taskmap.size(), MARCH_THREADS, march_smem_bytes(), pd, taskmap.data(),
-                                  ngroups);
-            cuda_emul::launch(march_epilogue_kernel<MODE>, pd.n_tasks, MEPI_THREADS, 0, pd, vp, ngroups, v, d, counters, flags);
+            if (!mm.empty())
+                cuda_emul::launch(march_kernel<MODE>, (int)mm.size(), MARCH_THREADS, march_smem_bytes(), pd, (const TaskHdr*)mm.data());
+            cuda_emul::launch(march_epilogue_kernel<MODE>, pd.n_tasks, MEPI_THREADS, 0, pd, vp, (const int*)part_ptr.data(), v, d,
+                              counters, flags);
             return;
         }
         const size_t smem = ((size_t)NAcc<MODE>::value * PIX_THREADS + (size_t)TASK_NIMG * MAX_COMPS * COMP_STRIDE) * sizeof(double);
@@ -194,7 +205,7 @@ extern "C" int emul_elbo_batch(int32_t N, const celeste_image* imgs, int32_t S_t
     for (size_t i = 0; i < tcp.size(); ++i) tcp[i] = (int)(i * TASK_WARPS);
     std::vector<double> slotimg((size_t)n_slots * N * SLOTIMG_STRIDE), slotbr((size_t)n_slots * SLOTBR_STRIDE),
         partials(std::max({blockmap.size() * NACC_MODE2, (size_t)n_subs * N * TASK_WARPS * NACC_MODE1,
-                           (size_t)n_subs * ((N + MARCH_NIMG - 1) / MARCH_NIMG) * NT_ACC}) + 1),
+                           (size_t)1}) + 1),
         pair_partials(pairmap.size() * NPAIR_ACC + 1);
     PlanDev pd;
     FieldDev fd{images.data(), pdv.data(), S_tot, 0};
@@ -236,8 +247,10 @@ extern "C" int emul_elbo_batch(int32_t N, const celeste_image* imgs, int32_t S_t
     return 0;
 }
 
+// 0: task_kernel, 1: march_kernel, 2: march_kernel with every source split into one block per image
 extern "C" int emul_set_grad_kernel(int32_t which) {
-    g_grad_kernel = which;
+    g_grad_kernel = which == 0 ? 0 : 1;
+    g_march_split = which == 2 ? 1 : 6000;
     return 0;
 }
 

@@ -34,7 +34,8 @@ def test_emulated_kernels_match_oracle_hessian(name):
 def test_march_kernel_matches_oracle_and_task_kernel(name):
     """march_kernels.cuh (row walks with the exp recurrence; the product's value / gradient path for Sa = 1, K = 2)
     against the oracle at the 1e-8 parity statement, and against task_kernel (direct evaluation of every pixel) at
-    1e-11: the recurrence is restarted exactly every <= 16 pixels, so the two differ by accumulated rounding only."""
+    1e-11: the recurrence is restarted exactly every <= 16 pixels, so the two differ by accumulated rounding only.
+    A walk is carried by a pair of lanes (one PSF component each) that exchange half of their sums by shuffles."""
     images, patches, tasks = cases.get(name)
     lib = emul_lib.load()
     for mode in (0, 1):
@@ -45,7 +46,13 @@ def test_march_kernel_matches_oracle_and_task_kernel(name):
         finally:
             lib.emul_set_grad_kernel(1)
         march = emul_lib.EmulField(images, patches).elbo_batch(tasks, mode=mode)
+        try:
+            lib.emul_set_grad_kernel(2)          # every source split into one block per image
+            split = emul_lib.EmulField(images, patches).elbo_batch(tasks, mode=mode)
+        finally:
+            lib.emul_set_grad_kernel(1)
         cases.assert_parity(ref, march, mode, name)
+        cases.assert_parity(ref, split, mode, name + " (one block per image)")
         cases.assert_parity(ref, direct, mode, name)
         assert np.array_equal(march["counters"], direct["counters"])
         fin = np.isfinite(direct["v"])
