@@ -199,7 +199,7 @@ struct celeste_plan {
     DevBuf<int> task_chunk_ptr;       // partial ranges of task_kernel: TASK_WARPS per (sub, image)
     int n_taskblocks = 0;
     // march_kernel (value / gradient, Sa = 1, K = 2): one block per (sub, group of MARCH_NIMG images)
-    DevBuf<TaskHdr> marchmap;
+    DevBuf<MarchHdr> marchmap;
     DevBuf<int> march_part_ptr;      // n_subs + 1: the partial vectors (= blocks) of each sub
     DevBuf<long long> bg_ptr;
     DevBuf<double> bg;
@@ -747,16 +747,19 @@ int celeste_plan_create_multi(int32_t n_fields, celeste_field* const* fields, ce
         pl->use_march = want && pl->uniform_K == 2 && n_subs == n_tasks;
     }
     if (pl->use_march) {
-        long split = 6000;                         // pixels of a source above which it gets one block per image
+        long split = 1000000000;                   // pixels of a source above which it gets one block per image (off by default)
         if (const char* env = std::getenv("CELESTE_MARCH_SPLIT"))   // kernel-tuning knob
             if (std::atol(env) > 0) split = std::atol(env);
-        std::vector<TaskHdr> mm;
+        std::vector<MarchHdr> mm;
         std::vector<int> part_ptr;
-        build_march_blocks(n_subs, pl->N, sub_task.data(), sub_slot.data(), task_ptr, tfield.data(), sub_ptr.data(),
-                           [&](int u, int n) {
-                               const celeste_field* f = fields[tfield[sub_task[u]]];
-                               const PatchDev& pa = f->h_patches[(size_t)src_row[sub_slot[u]] + (size_t)n * f->S_tot];
-                               return (long)pa.H2 * pa.W2;
+        build_march_blocks(n_subs, pl->N, sub_task.data(), sub_slot.data(), task_ptr, tfield.data(),
+                           [&](int slot, int n, int& oh, int& ow, int& H2, int& W2) {
+                               const celeste_field* f = fields[sfield[slot]];
+                               const PatchDev& pa = f->h_patches[(size_t)src_row[slot] + (size_t)n * f->S_tot];
+                               oh = pa.off_h;
+                               ow = pa.off_w;
+                               H2 = pa.H2;
+                               W2 = pa.W2;
                            },
                            split, mm, part_ptr);
         std::vector<long long> bg_ptr((size_t)n_subs * pl->N, -1);

@@ -155,26 +155,38 @@ struct MarchUnits {
     MarchBox box[MARCH_NIMG];
 };
 
+// Everything a block needs to find its work; built on the host from the patch geometry (build_march_blocks).
+struct MarchHdr {
+    int aslot, slot0, slot1;     // slot of the active source; slot range of its task
+    int field, sub, task;
+    int n0, n1;                  // image range of this block
+    int pidx;                    // this block's NT_ACC-vector in plan.partials
+    int nseg;                    // column segments per row
+    unsigned hasbg;              // bit k: some other source of the task reaches image n0 + k (background buffer in use)
+    int ubeg[MARCH_NIMG + 1];    // first walk of each image (walks are numbered image by image, rows fastest)
+};
+
 // One block per (active source of a task, group of <= MARCH_NIMG images).
 template <int MODE>
 __global__ void __launch_bounds__(MARCH_THREADS, CELESTE_MARCH_MINB)
-    march_kernel(PlanDev plan, const TaskHdr* __restrict__ taskmap) {
+    march_kernel(PlanDev plan, const MarchHdr* __restrict__ blocks) {
     static_assert(MODE <= 1, "the Hessian mode uses pixel_kernel");
     constexpr int NUA = MODE == 0 ? 1 : NACC_MODE1;   // (c, y)-space accumulators of the current walk
     constexpr int NS = MODE == 0 ? 2 : 7;             // mixture sums per pixel: F_dev F_exp | AX1 AX2 AS1 AS2 AS3
     CEL_DYNAMIC_SMEM(smem);
     double* tacc = smem;                                   // NT_ACC x MARCH_THREADS: task-space sums of this thread
-    double* uacc = tacc + NT_ACC * MARCH_THREADS;          // NUA x MARCH_THREADS: (c, y)-space sums of the current walk
-    double* s_rec = uacc + NACC_MODE1 * MARCH_THREADS;     // MARCH_NIMG x NC2 x MREC: the source being walked
+    double* s_rec = tacc + NT_ACC * MARCH_THREADS;         // MARCH_NIMG x NC2 x MREC: the source being walked
     double* s_si = s_rec + MARCH_NIMG * NC2 * MREC;        // MARCH_NIMG x SI_STRIDE
     __shared__ double s_exptab[8];
-    __shared__ MarchUnits s_au, s_nu;                      // walks of the active source / of the current neighbour
+    __shared__ MarchUnits s_nu;                            // walks of the current neighbour
     __shared__ MarchImg s_img[MARCH_NIMG];
-    __shared__ unsigned s_hasbg;
+    __shared__ MarchHdr s_hdr;
 
     const int tid = threadIdx.x, lane = tid & 31, kk = tid & 1;
     const int pair0 = (tid >> 5) * NPW;                    // first walk slot of this warp
-    const TaskHdr th = taskmap[blockIdx.x];
+    if (tid < (int)(sizeof(MarchHdr) / sizeof(int))) reinterpret_cast<int*>(&s_hdr)[tid] = reinterpret_cast<const int*>(blocks + blockIdx.x)[tid];
+    __syncthreads();
+    const MarchHdr& th = s_hdr;
     if (plan.task_mask && !plan.task_mask[th.task]) return;
     const int slot0 = th.slot0, slot1 = th.slot1, aslot = th.aslot;
     const FieldDev field = plan.fields[th.field];
@@ -184,64 +196,12 @@ __global__ void __launch_bounds__(MARCH_THREADS, CELESTE_MARCH_MINB)
 
 #pragma unroll
     for (int a = 0; a < NT_ACC; ++a) tacc[a * MARCH_THREADS + tid] = 0.0;
-#pragma unroll
-    for (int a = 0; a < NUA; ++a) uacc[a * MARCH_THREADS + tid] = 0.0;
 #ifdef CELESTE_HOST_EMULATION
     if (tid < 8) s_exptab[tid] = h_exptab[tid];
 #else
     if (tid < 8) s_exptab[tid] = c_exptab[tid];
 #endif
-    if (tid == MARCH_THREADS - 1) {
-        // walks of the active source: every row of every image, cut into nseg column segments.  nseg minimises
-        // warp-rounds x (iterations of two columns + cost of an exact start, ~2 columns)
-        int rows = 0, maxw = 0;
-        for (int k = 0; k < nimg; ++k) {
-            const PatchDev& pa = apatch[(size_t)(th.n0 + k) * field.S_tot];
-            if (pa.H2 > 0 && pa.W2 > 0) {
-                rows += pa.H2;
-                maxw = max(maxw, pa.W2);
-            }
-        }
-        const int nmin = max(1, (maxw + MARCH_MAXSEG - 1) / MARCH_MAXSEG);
-        long best = -1;
-        int nseg = nmin;
-        for (int cand = nmin; cand < nmin + 4; ++cand) {
-            const int L = (maxw + cand - 1) / cand;
-            const long cost = (long)((rows * cand + NPW - 1) / NPW) * (10 * ((L + 1) / 2) + 6);
-            if (best < 0 || cost < best) {
-                best = cost;
-                nseg = cand;
-            }
-        }
-        s_au.ubeg[0] = 0;
-        for (int k = 0; k < MARCH_NIMG; ++k) {
-            int units = 0;
-            if (k < nimg) {
-                const PatchDev& pa = apatch[(size_t)(th.n0 + k) * field.S_tot];
-                if (pa.H2 > 0 && pa.W2 > 0) units = pa.H2 * nseg;
-            }
-            s_au.nseg[k] = nseg;
-            s_au.ubeg[k + 1] = s_au.ubeg[k] + units;
-        }
-        // background buffers: the images some other source of the task can reach
-        unsigned hb = 0;
-        for (int k = 0; k < nimg; ++k) {
-            const int n = th.n0 + k;
-            const PatchDev& pa = apatch[(size_t)n * field.S_tot];
-            if (pa.H2 <= 0 || pa.W2 <= 0 || bgp[n] < 0) continue;
-            bool any = false;
-            for (int s = slot0; s < slot1 && !any; ++s) {
-                if (s == aslot) continue;
-                const PatchDev& p = field.patches[plan.src_row[s] + (size_t)n * field.S_tot];
-                any = (p.off_h + 1 <= pa.off_h + pa.H2) && (p.off_h + p.H2 >= pa.off_h + 1) &&
-                      (p.off_w + 1 <= pa.off_w + pa.W2) && (p.off_w + p.W2 - 1 >= pa.off_w + 1);
-            }
-            if (any) hb |= 1u << k;
-        }
-        s_hasbg = hb;
-    }
-    __syncthreads();
-    const unsigned hasbg = s_hasbg;
+    const unsigned hasbg = th.hasbg;
 
     // ---- neighbours, one at a time in slot order: E_bg += E_s, V_bg += E2_s - E_s^2 over the shared pixels -------
     if (hasbg) {
@@ -430,17 +390,17 @@ __global__ void __launch_bounds__(MARCH_THREADS, CELESTE_MARCH_MINB)
     // ---- the active source -----------------------------------------------------------------------------------
     // (pointers and geometry of the images live in shared memory and are re-read where used: the walk keeps its
     //  registers for the 28 doubles of component state and the 14 mixture sums)
-    const int total = s_au.ubeg[MARCH_NIMG];
+    const int total = th.ubeg[MARCH_NIMG];
     for (int ub = pair0; ub < total; ub += NPAIR) {                // warp-uniform
         const int u = ub + (lane >> 1);
         const bool has = u < total;
         int k = 0;
 #pragma unroll
-        for (int q = 1; q < MARCH_NIMG; ++q) k += (has && u >= s_au.ubeg[q]) ? 1 : 0;
+        for (int q = 1; q < MARCH_NIMG; ++q) k += (has && u >= th.ubeg[q]) ? 1 : 0;
         const MarchImg& mi = s_img[k];
         const int H2 = max(mi.H2, 1), W2 = mi.W2;
-        const int nseg = s_au.nseg[k];
-        const int ul = has ? u - s_au.ubeg[k] : 0;
+        const int nseg = th.nseg;
+        const int ul = has ? u - th.ubeg[k] : 0;
         const int seg = ul / H2, h2 = ul - seg * H2;
         const int segw = (W2 + nseg - 1) / nseg;
         const int c0 = seg * segw;
@@ -484,8 +444,8 @@ __global__ void __launch_bounds__(MARCH_THREADS, CELESTE_MARCH_MINB)
         }
         int pix = h2 + (c0 + kk) * H2;                                // own pixel inside the patch
         int ipix = (h - 1) + (w0 - 1 + kk) * mi.imgH;                 // ... and inside the image
-        double* ua = uacc + tid;
-        double cnt_active = 0.0;
+        double* ta = tacc + tid;
+        double cnt_active = 0.0, val = 0.0;
 
         for (int t = 0; t < nit; ++t) {
             const int iown = 2 * t + kk;
@@ -501,6 +461,10 @@ __global__ void __launch_bounds__(MARCH_THREADS, CELESTE_MARCH_MINB)
                     CEL_PREFETCH_L1(mi.pixels + nx);
                     CEL_PREFETCH_L1(mi.sky + nx);
                     CEL_PREFETCH_L1(mi.pixconst + nx);
+                    if (fast) {
+                        CEL_PREFETCH_L1(mi.coefs + coff + 2 * mi.n1);
+                        CEL_PREFETCH_L1(mi.coefs + coff + 3 * mi.n1 + 3);
+                    }
                 }
                 bit = mi.bitmap[pix];
                 xf = mi.pixels[ipix];
@@ -610,30 +574,29 @@ __global__ void __launch_bounds__(MARCH_THREADS, CELESTE_MARCH_MINB)
                     cnt_active += 1.0;
                 }
                 const double cb[4] = {si[SI_CB], si[SI_CB + 1], si[SI_CB + 2], si[SI_CB + 3]};
-                pixel_accumulate<MODE>(ua, MARCH_THREADS, pc, (double)skyf + bE, bV, covered, true, cb, f0, g0, h0, gal);
+                double la[NUA];
+#pragma unroll
+                for (int q = 0; q < NUA; ++q) la[q] = 0.0;
+                pixel_accumulate<MODE>(la, 1, pc, (double)skyf + bE, bV, covered, true, cb, f0, g0, h0, gal);
+                val += la[ACC_VAL];
+                if (MODE >= 1 && covered) {
+                    // (c, y) space of this image -> task space: dx_a/dpos_b = -J[a + 2 b]; the c-scalars go to their band
+                    ta[(TA_POS + 0) * MARCH_THREADS] -= si[SI_J + 0] * la[ACC_G] + si[SI_J + 1] * la[ACC_G + 1];
+                    ta[(TA_POS + 1) * MARCH_THREADS] -= si[SI_J + 2] * la[ACC_G] + si[SI_J + 3] * la[ACC_G + 1];
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) ta[(TA_SIG + q) * MARCH_THREADS] += la[ACC_G + 2 + q];
+                    ta[TA_THETA * MARCH_THREADS] += la[ACC_G + 5];
+                    double* tb = ta + (TA_BAND + 4 * mi.band0) * MARCH_THREADS;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) tb[q * MARCH_THREADS] += la[ACC_C1 + q];
+                }
             }
             pix += 2 * H2;
             ipix += 2 * mi.imgH;
             coff += 2 * mi.n1;
         }
-        const int band0 = mi.band0;
-        // leave the walk: (c, y) space of this image -> task space
-        double* ta = tacc + tid;
-        ta[TA_VAL * MARCH_THREADS] += ua[ACC_VAL * MARCH_THREADS];
-        ua[ACC_VAL * MARCH_THREADS] = 0.0;
+        ta[TA_VAL * MARCH_THREADS] += val;
         ta[TA_CNT_ACTIVE * MARCH_THREADS] += cnt_active;
-        if (MODE >= 1) {
-            const double gx1 = ua[ACC_G * MARCH_THREADS], gx2 = ua[(ACC_G + 1) * MARCH_THREADS];
-            ta[(TA_POS + 0) * MARCH_THREADS] -= si[SI_J + 0] * gx1 + si[SI_J + 1] * gx2;     // dx_a/dpos_b = -J[a + 2 b]
-            ta[(TA_POS + 1) * MARCH_THREADS] -= si[SI_J + 2] * gx1 + si[SI_J + 3] * gx2;
-#pragma unroll
-            for (int q = 0; q < 3; ++q) ta[(TA_SIG + q) * MARCH_THREADS] += ua[(ACC_G + 2 + q) * MARCH_THREADS];
-            ta[TA_THETA * MARCH_THREADS] += ua[(ACC_G + 5) * MARCH_THREADS];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) ta[(TA_BAND + 4 * band0 + q) * MARCH_THREADS] += ua[(ACC_C1 + q) * MARCH_THREADS];
-#pragma unroll
-            for (int q = ACC_G; q < NACC_MODE1; ++q) ua[q * MARCH_THREADS] = 0.0;
-        }
     }
     __syncthreads();
 
@@ -641,7 +604,7 @@ __global__ void __launch_bounds__(MARCH_THREADS, CELESTE_MARCH_MINB)
     const int warp = tid >> 5;
     constexpr int NA = MODE == 0 ? TA_POS : NT_ACC;
     constexpr int NW = MARCH_THREADS / 32, PER = (NA + NW - 1) / NW;
-    double* out = plan.partials + (size_t)th.pad1 * NT_ACC;       // pad1: this block's slot in the partials
+    double* out = plan.partials + (size_t)th.pidx * NT_ACC;
     double sred[PER];
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
@@ -666,52 +629,95 @@ __global__ void __launch_bounds__(MARCH_THREADS, CELESTE_MARCH_MINB)
 
 // Host side: the blocks of a plan.  One block per (sub, group of <= MARCH_NIMG images); a source whose patches hold
 // more than `split_pixels` pixels gets one block per image so that no single block is a long tail of the launch.
-// Each block owns one NT_ACC-vector of plan.partials (TaskHdr::pad1); part_ptr[sub] .. part_ptr[sub + 1] are the
-// blocks of a sub, in image order.  pixels(sub, n) -> H2 * W2 of the active patch.
-template <typename Pix>
+// Each block owns one NT_ACC-vector of plan.partials (pidx); part_ptr[sub] .. part_ptr[sub + 1] are the blocks of a
+// sub, in image order.  geo(slot, n, off_h, off_w, H2, W2) -> the patch box of a slot in image n.
+// nseg (column segments per row) minimises  block-rounds x (iterations of two columns + an exact start, ~0.6
+// iterations): all warps of a block then leave the walk loop together instead of idling at its final barrier.
+template <typename Geo>
 inline void build_march_blocks(int n_subs, int N, const int* sub_task, const int* sub_slot, const int* task_ptr,
-                               const int* task_field, const int* sub_ptr, Pix pixels, long split_pixels,
-                               std::vector<TaskHdr>& blocks, std::vector<int>& part_ptr) {
+                               const int* task_field, Geo geo, long split_pixels, std::vector<MarchHdr>& blocks,
+                               std::vector<int>& part_ptr) {
     blocks.clear();
     part_ptr.assign((size_t)n_subs + 1, 0);
     std::vector<long> cost;
     for (int u = 0; u < n_subs; ++u) {
         const int t = sub_task[u];
+        const int aslot = sub_slot[u], slot0 = task_ptr[t], slot1 = task_ptr[t + 1];
         long tot = 0;
-        for (int n = 0; n < N; ++n) tot += pixels(u, n);
+        for (int n = 0; n < N; ++n) {
+            int oh, ow, H2, W2;
+            geo(aslot, n, oh, ow, H2, W2);
+            tot += (long)std::max(H2, 0) * std::max(W2, 0);
+        }
         const int step = tot > split_pixels ? 1 : MARCH_NIMG;
         for (int n0 = 0; n0 < N; n0 += step) {
-            TaskHdr th;
-            th.tn0 = u * N;
-            th.aslot = sub_slot[u];
-            th.slot0 = task_ptr[t];
-            th.slot1 = task_ptr[t + 1];
+            MarchHdr th{};
+            th.aslot = aslot;
+            th.slot0 = slot0;
+            th.slot1 = slot1;
             th.field = task_field ? task_field[t] : 0;
-            th.sub0 = sub_ptr[t];
             th.sub = u;
-            th.sub1 = sub_ptr[t + 1];
+            th.task = t;
             th.n0 = n0;
             th.n1 = std::min(N, n0 + step);
-            th.task = t;
-            th.pad1 = (int)blocks.size();
+            th.pidx = (int)blocks.size();
+            int rows = 0, maxw = 0;
             long c = 0;
-            for (int n = th.n0; n < th.n1; ++n) c += pixels(u, n) * (1 + (th.slot1 - th.slot0 - 1) / 4);
+            th.hasbg = 0;
+            for (int n = th.n0; n < th.n1; ++n) {
+                int oh, ow, H2, W2;
+                geo(aslot, n, oh, ow, H2, W2);
+                if (H2 <= 0 || W2 <= 0) continue;
+                rows += H2;
+                maxw = std::max(maxw, W2);
+                c += (long)H2 * W2 * (1 + (slot1 - slot0 - 1) / 4);
+                for (int s = slot0; s < slot1; ++s) {
+                    if (s == aslot) continue;
+                    int ph, pw, pH2, pW2;
+                    geo(s, n, ph, pw, pH2, pW2);
+                    // rows off+1..off+H2 of both; columns off+1..off+W2 of the active patch, off+1..off+W2-1 of the
+                    // neighbour (strict `w2 < W2`, elbo_objective.jl:349)
+                    if ((ph + 1 <= oh + H2) && (ph + pH2 >= oh + 1) && (pw + 1 <= ow + W2) && (pw + pW2 - 1 >= ow + 1))
+                        th.hasbg |= 1u << (n - th.n0);
+                }
+            }
+            const int nmin = std::max(1, (maxw + MARCH_MAXSEG - 1) / MARCH_MAXSEG);
+            long best = -1;
+            th.nseg = nmin;
+            for (int cand = nmin; cand < nmin + 6; ++cand) {
+                const int L = (maxw + cand - 1) / cand;
+                const long cst = (long)((rows * cand + NPAIR - 1) / NPAIR) * (10 * ((L + 1) / 2) + 6);
+                if (best < 0 || cst < best) {
+                    best = cst;
+                    th.nseg = cand;
+                }
+            }
+            th.ubeg[0] = 0;
+            for (int k = 0; k < MARCH_NIMG; ++k) {
+                int units = 0;
+                if (th.n0 + k < th.n1) {
+                    int oh, ow, H2, W2;
+                    geo(aslot, th.n0 + k, oh, ow, H2, W2);
+                    if (H2 > 0 && W2 > 0) units = H2 * th.nseg;
+                }
+                th.ubeg[k + 1] = th.ubeg[k] + units;
+            }
             blocks.push_back(th);
             cost.push_back(c);
         }
         part_ptr[u + 1] = (int)blocks.size();
     }
-    // heaviest first, so the launch tail is short; the partial slot (pad1) keeps the per-sub order
+    // heaviest first, so the launch tail is short; pidx keeps the per-sub order of the partial vectors
     std::vector<int> order(blocks.size());
     for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
     std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cost[x] > cost[y]; });
-    std::vector<TaskHdr> sorted(blocks.size());
+    std::vector<MarchHdr> sorted(blocks.size());
     for (size_t i = 0; i < order.size(); ++i) sorted[i] = blocks[order[i]];
     blocks.swap(sorted);
 }
 
 constexpr size_t march_smem_bytes() {
-    return ((size_t)(NT_ACC + NACC_MODE1) * MARCH_THREADS + (size_t)MARCH_NIMG * NC2 * MREC + (size_t)MARCH_NIMG * SI_STRIDE) * sizeof(double);
+    return ((size_t)NT_ACC * MARCH_THREADS + (size_t)MARCH_NIMG * NC2 * MREC + (size_t)MARCH_NIMG * SI_STRIDE) * sizeof(double);
 }
 
 // ------------------------------------------------------------------------------------------------

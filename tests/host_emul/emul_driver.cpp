@@ -47,11 +47,14 @@ void run_task(PlanDev pd, const FieldDev& fd, const std::vector<TaskHdr>& taskma
             // same launch sequence as celeste_abi.cu's march path
             std::vector<int> sub_task(pd.n_subs), part_ptr;
             for (int u = 0; u < pd.n_subs; ++u) sub_task[u] = u;
-            std::vector<TaskHdr> mm;
-            build_march_blocks(pd.n_subs, pd.N, sub_task.data(), pd.sub_slot, pd.task_ptr, (const int*)nullptr, pd.sub_ptr,
-                               [&](int u, int n) {
-                                   const PatchDev& pa = fd.patches[(size_t)pd.src_row[pd.sub_slot[u]] + (size_t)n * fd.S_tot];
-                                   return (long)pa.H2 * pa.W2;
+            std::vector<MarchHdr> mm;
+            build_march_blocks(pd.n_subs, pd.N, sub_task.data(), pd.sub_slot, pd.task_ptr, (const int*)nullptr,
+                               [&](int slot, int n, int& oh, int& ow, int& H2, int& W2) {
+                                   const PatchDev& pa = fd.patches[(size_t)pd.src_row[slot] + (size_t)n * fd.S_tot];
+                                   oh = pa.off_h;
+                                   ow = pa.off_w;
+                                   H2 = pa.H2;
+                                   W2 = pa.W2;
                                },
                                g_march_split, mm, part_ptr);
             std::vector<double> mpart(mm.size() * NT_ACC + 1);
@@ -73,7 +76,7 @@ void run_task(PlanDev pd, const FieldDev& fd, const std::vector<TaskHdr>& taskma
             pd.bg = bg.data();
             cuda_emul::launch(setup_kernel, 2, 64, 0, pd, vp);
             if (!mm.empty())
-                cuda_emul::launch(march_kernel<MODE>, (int)mm.size(), MARCH_THREADS, march_smem_bytes(), pd, (const TaskHdr*)mm.data());
+                cuda_emul::launch(march_kernel<MODE>, (int)mm.size(), MARCH_THREADS, march_smem_bytes(), pd, (const MarchHdr*)mm.data());
             cuda_emul::launch(march_epilogue_kernel<MODE>, pd.n_tasks, MEPI_THREADS, 0, pd, vp, (const int*)part_ptr.data(), v, d,
                               counters, flags);
             return;
