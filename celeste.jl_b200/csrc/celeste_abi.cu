@@ -141,6 +141,13 @@ int configure_kernels() {
 #undef CEL_TCFG
     CUDA_TRY(cudaFuncSetAttribute(march_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)march_smem_bytes()));
     CUDA_TRY(cudaFuncSetAttribute(march_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)march_smem_bytes()));
+    if (const char* env = std::getenv("CELESTE_MARCH_CARVEOUT")) {     // kernel-tuning knob: shared-memory share of L1, percent
+        const int pct = std::atoi(env);
+        if (pct >= 0 && pct <= 100) {
+            CUDA_TRY(cudaFuncSetAttribute(march_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+            CUDA_TRY(cudaFuncSetAttribute(march_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        }
+    }
     {
         const int psm = (int)(((size_t)NPAIR_ACC * PAIR_THREADS + 2 * (size_t)MAX_COMPS * COMP_STRIDE) * sizeof(double));
         CUDA_TRY(cudaFuncSetAttribute(pair_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, psm));

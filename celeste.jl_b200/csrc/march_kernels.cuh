@@ -1,18 +1,23 @@
 // march_kernels.cuh -- the value / gradient hot loop of the ELBO (add_pixel_term!, elbo_objective.jl:330-392)
-// re-organised around the pixel GRID instead of the pixel: each thread walks along one row of the active
-// source's patch (consecutive columns w, w+1, ...) and carries every Gaussian component with it.
+// re-organised around the pixel GRID instead of the pixel: a walk moves along one row of the active source's patch
+// (consecutive columns w, w+1, ...) and carries every Gaussian component with it.
 //
 // Why: on a regular grid the quadratic form of a bivariate normal (eval_bvn_pdf!, BivariateNormals.jl:208-222)
 // changes by a LINEAR amount from one column to the next,
 //       q(w + 1) - q(w) = 2 p2(w) + L22,      p2(w + 1) - p2(w) = L22,       p = Lambda (x - mu),
 // so   f(w + 1) = f(w) r(w),   r(w + 1) = r(w) c,   c = exp(-L22),   r(w0) = exp(-(p2(w0) + L22 / 2)):
 // after an exact start (two exp per component) every further pixel costs two multiplications per component
-// instead of a quadratic form and an exp (20 of the 33 FP64 instructions a component costs in gradient mode).
-// The cubic B-spline of the star (star_light_density!, fsm_util.jl:225-248) has the same structure: along a row
-// the fractional offsets -- hence all eight weights -- are constant and the 4 x 4 tap window slides by one
-// column, so one new column of 4 taps per pixel replaces 16.
-// A walk is restarted exactly after at most MARCH_MAXSEG pixels, which bounds the accumulated rounding error
-// (relative ~ n^2/2 ulp after n steps: < 1e-13 at n = 16, five orders below the 1e-8 parity tolerance).
+// instead of a quadratic form and an exp (20 of the 33 FP64 instructions a component costs in task_kernel's
+// gradient mode).  The cubic B-spline of the star (star_light_density!, fsm_util.jl:225-248) has the same
+// structure: along a row the fractional offsets -- hence all eight weights -- are constant and the 4 x 4 tap window
+// slides, so new columns of 4 taps replace 16 taps per pixel.
+// A walk is restarted exactly after at most MARCH_MAXSEG pixels (51 = the catalog patch cap,
+// imaged_sources.jl:173-176), which bounds the accumulated rounding error: relative ~ n^2/2 ulp after n steps,
+// 1.4e-13 at n = 51 -- five orders below the 1e-8 parity tolerance (measured against task_kernel: <= 5e-13).
+//
+// A walk is carried by a PAIR of adjacent lanes, one PSF component (K = 2) each: 28 doubles of state per lane.
+// Every iteration advances two columns; the lanes exchange half of their mixture sums by one shuffle per sum and
+// each finishes one of the two pixels (star, pixel term), so nothing is computed twice.
 //
 // Neighbouring sources (value only, elbo_objective.jl:38-40,69) are walked the same way over the intersection
 // of their patch with the active patch, one neighbour at a time, into a per-task background buffer
@@ -23,7 +28,7 @@
 // into one 29-vector and march_epilogue_kernel applies the remaining chain rule once per source.
 //
 // Handles Sa = 1 and K = 2 (production: ParallelRun.jl:253,489, elbo_args.jl:197); every other plan keeps
-// task_kernel.  Same arithmetic as there up to reassociation.
+// task_kernel.  Same arithmetic as there up to reassociation and the recurrence's rounding.
 #ifndef CELESTE_MARCH_KERNELS_CUH
 #define CELESTE_MARCH_KERNELS_CUH
 
@@ -38,7 +43,7 @@
 namespace celeste {
 
 #ifndef CELESTE_MARCH_MAXSEG
-#define CELESTE_MARCH_MAXSEG 16
+#define CELESTE_MARCH_MAXSEG 51
 #endif
 #ifndef CELESTE_MARCH_MINB
 #define CELESTE_MARCH_MINB 3
