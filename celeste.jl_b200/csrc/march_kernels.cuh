@@ -310,8 +310,13 @@ __global__ void __launch_bounds__(MARCH_THREADS, CELESTE_MARCH_MINB)
                 const double theta = si[SI_THETA];
                 for (int t = 0; t < nit; ++t) {
                     const bool own = 2 * t + kk < len;
-                    bool valid = false;
-                    if (own) valid = *abit && *nbit && !isnan(*px);
+                    unsigned char ab = 0, nb = 0;
+                    float xv = 0.f;
+                    if (own) {
+                        ab = *abit;
+                        nb = *nbit;
+                        xv = *px;
+                    }
                     double R2 = 0.0, R3 = 0.0;
                     if (fast && own) {
                         const double wx0 = si[SI_WX], wx1 = si[SI_WX + 1], wx2 = si[SI_WX + 2], wx3 = si[SI_WX + 3];
@@ -335,7 +340,7 @@ __global__ void __launch_bounds__(MARCH_THREADS, CELESTE_MARCH_MINB)
                     double Fd = kk == 0 ? S[0][0] : S[1][0], Fe = kk == 0 ? S[0][1] : S[1][1];
                     Fd += __shfl_xor_sync(0xffffffffu, kk == 0 ? S[1][0] : S[0][0], 1);
                     Fe += __shfl_xor_sync(0xffffffffu, kk == 0 ? S[1][1] : S[0][1], 1);
-                    if (valid) {
+                    if (ab && nb && !isnan(xv)) {
                         double f0;
                         if (fast) {
                             const double v = si[SI_WY] * R0 + si[SI_WY + 1] * R1 + si[SI_WY + 2] * R2 + si[SI_WY + 3] * R3;
@@ -455,61 +460,20 @@ __global__ void __launch_bounds__(MARCH_THREADS, CELESTE_MARCH_MINB)
         for (int t = 0; t < nit; ++t) {
             const int iown = 2 * t + kk;
             const bool own = iown < len;
-            // this lane's pixel: inputs (the next iteration's lines are requested now, so these loads hit L1) ...
-            unsigned char bit = 0;
-            float xf = 0.f, skyf = 0.f;
-            double pconst = 0.0, bE = 0.0, bV = 0.0;
-            double f0 = 0.0, g0[2] = {0.0, 0.0}, h0[3] = {0.0, 0.0, 0.0};
+            // this lane's pixel (column 2t + kk): its inputs are requested now and read after the mixture sums, whose
+            // ~1000 instructions hide the latency without holding a register
             if (own) {
-                if (iown + 2 < len) {
-                    const int nx = ipix + 2 * mi.imgH;
-                    CEL_PREFETCH_L1(mi.pixels + nx);
-                    CEL_PREFETCH_L1(mi.sky + nx);
-                    CEL_PREFETCH_L1(mi.pixconst + nx);
-                    if (fast) {
-                        CEL_PREFETCH_L1(mi.coefs + coff + 2 * mi.n1);
-                        CEL_PREFETCH_L1(mi.coefs + coff + 3 * mi.n1 + 3);
-                    }
-                }
-                bit = mi.bitmap[pix];
-                xf = mi.pixels[ipix];
-                skyf = mi.sky[ipix];
-                pconst = mi.pixconst[ipix];
+                CEL_PREFETCH_L1(mi.pixels + ipix);
+                CEL_PREFETCH_L1(mi.sky + ipix);
+                CEL_PREFETCH_L1(mi.pixconst + ipix);
+                CEL_PREFETCH_L1(mi.bitmap + pix);
                 if (mi.bg) {
-                    bE = mi.bg[pix];
-                    bV = mi.bg[pix + H2 * W2];
+                    CEL_PREFETCH_L1(mi.bg + pix);
+                    CEL_PREFETCH_L1(mi.bg + pix + H2 * W2);
                 }
-                // ... and star (star_light_density!, fsm_util.jl:225-248): two new columns of the sliding window
                 if (fast) {
-                    const double* ccol = mi.coefs + coff;
-                    const int n1 = mi.n1;
-                    const double q0 = __ldg(ccol), q1 = __ldg(ccol + 1), q2 = __ldg(ccol + 2), q3 = __ldg(ccol + 3);
-                    const double q4 = __ldg(ccol + n1), q5 = __ldg(ccol + n1 + 1), q6 = __ldg(ccol + n1 + 2), q7 = __ldg(ccol + n1 + 3);
-                    const double R2 = si[SI_WX] * q0 + si[SI_WX + 1] * q1 + si[SI_WX + 2] * q2 + si[SI_WX + 3] * q3;
-                    const double R3 = si[SI_WX] * q4 + si[SI_WX + 1] * q5 + si[SI_WX + 2] * q6 + si[SI_WX + 3] * q7;
-                    const double wy0 = si[SI_WY], wy1 = si[SI_WY + 1], wy2 = si[SI_WY + 2], wy3 = si[SI_WY + 3];
-                    const double v = wy0 * R0 + wy1 * R1 + wy2 * R2 + wy3 * R3;
-                    double gx = 0.0, gy = 0.0;
-                    if (MODE >= 1) {
-                        const double D2 = si[SI_DWX] * q0 + si[SI_DWX + 1] * q1 + si[SI_DWX + 2] * q2 + si[SI_DWX + 3] * q3;
-                        const double D3 = si[SI_DWX] * q4 + si[SI_DWX + 1] * q5 + si[SI_DWX + 2] * q6 + si[SI_DWX + 3] * q7;
-                        gx = wy0 * D0 + wy1 * D1 + wy2 * D2 + wy3 * D3;
-                        gy = si[SI_DWY] * R0 + si[SI_DWY + 1] * R1 + si[SI_DWY + 2] * R2 + si[SI_DWY + 3] * R3;
-                        D0 = D2;
-                        D1 = D3;
-                    }
-                    R0 = R2;
-                    R1 = R3;
-                    if (v < 0) {                                          // softpluslikeinv, fsm_util.jl:222
-                        const double e = 1e-3 * exp_nonpos(v);
-                        f0 = e;
-                        g0[0] = e * gx;
-                        g0[1] = e * gy;
-                    } else {
-                        f0 = 1e-3 * (v + 1.0);
-                        g0[0] = 1e-3 * gx;
-                        g0[1] = 1e-3 * gy;
-                    }
+                    CEL_PREFETCH_L1(mi.coefs + coff);
+                    CEL_PREFETCH_L1(mi.coefs + coff + mi.n1 + 3);
                 }
             }
             // this lane's half (PSF component kk) of the mixture sums of both pixels (columns 2t and 2t + 1)
@@ -556,6 +520,52 @@ __global__ void __launch_bounds__(MARCH_THREADS, CELESTE_MARCH_MINB)
             for (int q = 0; q < NS; ++q)
                 T[q] = (kk == 0 ? S[0][q] : S[1][q]) + __shfl_xor_sync(0xffffffffu, kk == 0 ? S[1][q] : S[0][q], 1);
 
+            unsigned char bit = 0;
+            float xf = 0.f, skyf = 0.f;
+            double pconst = 0.0, bE = 0.0, bV = 0.0;
+            double f0 = 0.0, g0[2] = {0.0, 0.0}, h0[3] = {0.0, 0.0, 0.0};
+            if (own) {
+                bit = mi.bitmap[pix];
+                xf = mi.pixels[ipix];
+                skyf = mi.sky[ipix];
+                pconst = mi.pixconst[ipix];
+                if (mi.bg) {
+                    bE = mi.bg[pix];
+                    bV = mi.bg[pix + H2 * W2];
+                }
+                // ... and star (star_light_density!, fsm_util.jl:225-248): two new columns of the sliding window
+                if (fast) {
+                    const double* ccol = mi.coefs + coff;
+                    const int n1 = mi.n1;
+                    const double q0 = __ldg(ccol), q1 = __ldg(ccol + 1), q2 = __ldg(ccol + 2), q3 = __ldg(ccol + 3);
+                    const double q4 = __ldg(ccol + n1), q5 = __ldg(ccol + n1 + 1), q6 = __ldg(ccol + n1 + 2), q7 = __ldg(ccol + n1 + 3);
+                    const double R2 = si[SI_WX] * q0 + si[SI_WX + 1] * q1 + si[SI_WX + 2] * q2 + si[SI_WX + 3] * q3;
+                    const double R3 = si[SI_WX] * q4 + si[SI_WX + 1] * q5 + si[SI_WX + 2] * q6 + si[SI_WX + 3] * q7;
+                    const double wy0 = si[SI_WY], wy1 = si[SI_WY + 1], wy2 = si[SI_WY + 2], wy3 = si[SI_WY + 3];
+                    const double v = wy0 * R0 + wy1 * R1 + wy2 * R2 + wy3 * R3;
+                    double gx = 0.0, gy = 0.0;
+                    if (MODE >= 1) {
+                        const double D2 = si[SI_DWX] * q0 + si[SI_DWX + 1] * q1 + si[SI_DWX + 2] * q2 + si[SI_DWX + 3] * q3;
+                        const double D3 = si[SI_DWX] * q4 + si[SI_DWX + 1] * q5 + si[SI_DWX + 2] * q6 + si[SI_DWX + 3] * q7;
+                        gx = wy0 * D0 + wy1 * D1 + wy2 * D2 + wy3 * D3;
+                        gy = si[SI_DWY] * R0 + si[SI_DWY + 1] * R1 + si[SI_DWY + 2] * R2 + si[SI_DWY + 3] * R3;
+                        D0 = D2;
+                        D1 = D3;
+                    }
+                    R0 = R2;
+                    R1 = R3;
+                    if (v < 0) {                                          // softpluslikeinv, fsm_util.jl:222
+                        const double e = 1e-3 * exp_nonpos(v);
+                        f0 = e;
+                        g0[0] = e * gx;
+                        g0[1] = e * gy;
+                    } else {
+                        f0 = 1e-3 * (v + 1.0);
+                        g0[0] = 1e-3 * gx;
+                        g0[1] = 1e-3 * gy;
+                    }
+                }
+            }
             if (own && bit && !isnan(xf)) {                          // elbo_objective.jl:445, :459
                 PixelConsts pc;
                 pc.x = (double)xf;
