@@ -172,6 +172,179 @@ static const double h_exptab[8] = CEL_EXP2_TAB;
 #endif
 
 // ---------------------------------------------------------------------------------------------
+// log(E) for the pixel term (add_elbo_log_term!, elbo_objective.jl:288-292), table-driven: E = 2^k m, m in [1, 2),
+// i = top 7 mantissa bits, c_i = 1 + (i + 1/2)/128;  log E = k ln 2 - log(inv_i) + log1p(r),  r = fma(m, inv_i, -1)
+// with inv_i = fl(1 / c_i) (the identity is exact for the STORED inv_i; logc_i = -log(inv_i) rounded once),
+// |r| <= 2^-8, log1p by a degree-7 Taylor polynomial (|r|^8 / 8 < 1e-20).  About 20 instructions instead of the
+// ~80 of the library routine (which divides); absolute error ~1e-16 (tools/fit_exp.py-style check against 50-digit
+// arithmetic: <= 2e-14 relative to max(|log E|, 1e-3)).  Non-positive, subnormal, infinite and NaN arguments take
+// the library routine, so the non-finite flag behaves as before.
+// Table: 128 x (inv_i, logc_i).
+#define CEL_LOG_TAB { \
+    0.9961089494163424, 0.003898640415657309, \
+    0.9884169884169884, 0.01165061721997525, \
+    0.9808429118773946, 0.019342962843130987, \
+    0.973384030418251, 0.026976587698202083, \
+    0.9660377358490566, 0.03455238150665973, \
+    0.9588014981273408, 0.042071213920687044, \
+    0.9516728624535316, 0.049533935122276676, \
+    0.9446494464944649, 0.05694137640013845, \
+    0.9377289377289377, 0.06429435070539725, \
+    0.9309090909090909, 0.07159365318700882, \
+    0.924187725631769, 0.078840061707776, \
+    0.9175627240143369, 0.08603433734180316, \
+    0.9110320284697508, 0.09317722485418334, \
+    0.9045936395759717, 0.10026945316367517, \
+    0.8982456140350877, 0.10731173578908804, \
+    0.89198606271777, 0.11430477128005863, \
+    0.8858131487889274, 0.12124924363286965, \
+    0.8797250859106529, 0.12814582269193006, \
+    0.8737201365187713, 0.13499516453750482, \
+    0.8677966101694915, 0.1417979118602574, \
+    0.8619528619528619, 0.1485546943231372, \
+    0.8561872909698997, 0.15526612891112396, \
+    0.8504983388704319, 0.16193282026931324, \
+    0.8448844884488449, 0.16855536102980664, \
+    0.839344262295082, 0.17513433212784915, \
+    0.8338762214983714, 0.18167030310763463, \
+    0.8284789644012945, 0.18816383241818294, \
+    0.8231511254019293, 0.19461546769967167, \
+    0.8178913738019169, 0.2010257460605908, \
+    0.8126984126984127, 0.2073951943460706, \
+    0.807570977917981, 0.21372432939771818, \
+    0.8025078369905956, 0.22001365830528213, \
+    0.7975077881619937, 0.2262636786504534, \
+    0.7925696594427245, 0.232474878743094, \
+    0.7876923076923077, 0.238647737850175, \
+    0.7828746177370031, 0.24478272641769092, \
+    0.7781155015197568, 0.25088030628580943, \
+    0.7734138972809668, 0.2569409308975004, \
+    0.7687687687687688, 0.26296504550088134, \
+    0.764179104477612, 0.26895308734550394, \
+    0.7596439169139466, 0.2749054858727992, \
+    0.7551622418879056, 0.2808226629008878, \
+    0.750733137829912, 0.2867050328039543, \
+    0.7463556851311953, 0.29255300268637746, \
+    0.7420289855072464, 0.2983669725517973, \
+    0.7377521613832853, 0.3041473354672968, \
+    0.7335243553008596, 0.3098944777228647, \
+    0.7293447293447294, 0.3156087789863033, \
+    0.7252124645892352, 0.32129061245373425, \
+    0.7211267605633803, 0.3269403449958533, \
+    0.7170868347338936, 0.3325583373000766, \
+    0.713091922005571, 0.3381449440087164, \
+    0.7091412742382271, 0.34370051385331846, \
+    0.7052341597796143, 0.3492253897852883, \
+    0.7013698630136986, 0.354719909102929, \
+    0.6975476839237057, 0.3601844035750078, \
+    0.6937669376693767, 0.3656191995609647, \
+    0.6900269541778976, 0.37102461812787263, \
+    0.6863270777479893, 0.376400975164253, \
+    0.6826666666666666, 0.3817485814908484, \
+    0.6790450928381963, 0.3870677429684483, \
+    0.6754617414248021, 0.3923587606028639, \
+    0.6719160104986877, 0.3976219306471385, \
+    0.6684073107049608, 0.4028575447010835, \
+    0.6649350649350649, 0.4080658898082217, \
+    0.661498708010336, 0.41324724855021927, \
+    0.6580976863753213, 0.41840189913888387, \
+    0.6547314578005116, 0.4235301155058032, \
+    0.6513994910941476, 0.42863216738969867, \
+    0.6481012658227848, 0.4337083204215594, \
+    0.6448362720403022, 0.43875883620762796, \
+    0.6416040100250626, 0.44378397241030104, \
+    0.6384039900249376, 0.4487839828270067, \
+    0.6352357320099256, 0.4537591174671205, \
+    0.6320987654320988, 0.4587096226269767, \
+    0.628992628992629, 0.46363574096303256, \
+    0.6259168704156479, 0.46853771156323926, \
+    0.6228710462287105, 0.4734157700166721, \
+    0.6198547215496368, 0.47827014848147026, \
+    0.6168674698795181, 0.48310107575113576, \
+    0.6139088729016786, 0.48790877731923904, \
+    0.6109785202863962, 0.4926934754425752, \
+    0.6080760095011877, 0.4974553892028189, \
+    0.6052009456264775, 0.5021947345667155, \
+    0.6023529411764705, 0.5069117244448544, \
+    0.5995316159250585, 0.5116065687490621, \
+    0.5967365967365967, 0.5162794744484545, \
+    0.5939675174013921, 0.5209306456241853, \
+    0.5912240184757506, 0.5255602835229274, \
+    0.5885057471264368, 0.5301685866091216, \
+    0.585812356979405, 0.5347557506160276, \
+    0.5831435079726651, 0.5393219685956089, \
+    0.5804988662131519, 0.5438674309672835, \
+    0.5778781038374717, 0.5483923255655733, \
+    0.5752808988764045, 0.5528968376866776, \
+    0.5727069351230425, 0.5573811501340064, \
+    0.5701559020044543, 0.5618454432626918, \
+    0.5676274944567627, 0.5662898950231159, \
+    0.565121412803532, 0.5707146810034716, \
+    0.5626373626373626, 0.575119974471388, \
+    0.5601750547045952, 0.5795059464146423, \
+    0.5577342047930284, 0.5838727655809826, \
+    0.5553145336225597, 0.588220598517086, \
+    0.5529157667386609, 0.5925496096066716, \
+    0.5505376344086022, 0.5968599611077938, \
+    0.5481798715203426, 0.6011518131893347, \
+    0.5458422174840085, 0.6054253239667169, \
+    0.5435244161358811, 0.6096806495368553, \
+    0.5412262156448203, 0.6139179440123704, \
+    0.5389473684210526, 0.6181373595550788, \
+    0.5366876310272537, 0.6223390464087787, \
+    0.534446764091858, 0.6265231529313529, \
+    0.5322245322245323, 0.6306898256261987, \
+    0.5300207039337475, 0.6348392091730102, \
+    0.5278350515463918, 0.6389714464579207, \
+    0.5256673511293635, 0.6430866786030273, \
+    0.523517382413088, 0.6471850449953095, \
+    0.5213849287169042, 0.6512666833149582, \
+    0.5192697768762677, 0.6553317295631277, \
+    0.5171717171717172, 0.6593803180891278, \
+    0.5150905432595574, 0.6634125816170662, \
+    0.5130260521042084, 0.6674286512719563, \
+    0.5109780439121756, 0.6714286566053024, \
+    0.5089463220675944, 0.6754127256201768, \
+    0.5069306930693069, 0.6793809847957973, \
+    0.504930966469428, 0.6833335591116206, \
+    0.5029469548133595, 0.6872705720709603, \
+    0.5009784735812133, 0.691192145724142 }
+#if defined(__CUDACC__)
+__device__ const double g_logtab[256] = CEL_LOG_TAB;
+#endif
+#if !defined(__CUDACC__)
+static const double h_logtab[256] = CEL_LOG_TAB;
+#endif
+CEL_HD double log_tab(double E, const double* tab) {
+#if defined(__CUDA_ARCH__)
+    const int hi = __double2hiint(E);
+#else
+    long long bits;
+    memcpy(&bits, &E, 8);
+    const int hi = (int)(bits >> 32);
+#endif
+    if ((unsigned)(hi - 0x00100000) >= 0x7fe00000u) return log(E);      // E <= 0, subnormal, Inf, NaN
+    const int idx = (hi >> 13) & 0x7f;
+    const int k = (hi >> 20) - 1023;
+#if defined(__CUDA_ARCH__)
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(E));
+#else
+    long long mb = (bits & 0x000fffffffffffffLL) | 0x3ff0000000000000LL;
+    double m;
+    memcpy(&m, &mb, 8);
+#endif
+    const double inv = tab[2 * idx], logc = tab[2 * idx + 1];
+    const double r = fma(m, inv, -1.0);
+    double p = fma(r, 1.0 / 7.0, -1.0 / 6.0);
+    p = fma(p, r, 0.2);
+    p = fma(p, r, -0.25);
+    p = fma(p, r, 1.0 / 3.0);
+    p = fma(p, r, -0.5);
+    p = fma(p, r * r, r);
+    return fma((double)k, 0.693147180559945309417232121458, logc + p);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Cubic B-spline (Interpolations.jl BSpline(Cubic(Line())), OnGrid; un-vendored dependency,
 // REQUIRE:21): weights at fractional offset f for taps i-1..i+2, with first/second derivatives.
 template <int MODE>
@@ -455,7 +628,7 @@ struct PixelConsts {
 template <int MODE>
 CEL_HD void pixel_accumulate(double* acc, int stride, const PixelConsts& pc, double Ebg, double Vbg, bool covered,
                              bool add_value, const double* cb /*A1 A2 B1 B2*/, double f0, const double* g0,
-                             const double* h0, const GalRaw& gal) {
+                             const double* h0, const GalRaw& gal, const double* logtab = nullptr) {
     const double A1 = cb[0], A2 = cb[1], B1 = cb[2], B2 = cb[3];
     const double f1 = gal.f;
     const double m = covered ? (A1 * f0 + A2 * f1) : 0.0;
@@ -463,7 +636,7 @@ CEL_HD void pixel_accumulate(double* acc, int stride, const PixelConsts& pc, dou
     const double V = covered ? (Vbg + B1 * f0 * f0 + B2 * f1 * f1 - m * m) : Vbg;
     const double iE = 1.0 / E;
     const double iE2 = iE * iE;
-    if (add_value) acc[ACC_VAL * stride] += pc.x * (log(E) - 0.5 * V * iE2) - pc.iota * E + pc.pixconst;
+    if (add_value) acc[ACC_VAL * stride] += pc.x * ((logtab ? log_tab(E, logtab) : log(E)) - 0.5 * V * iE2) - pc.iota * E + pc.pixconst;
     if (MODE == 0 || !covered) return;
 
     const double gE = pc.x * (iE + V * iE2 * iE) - pc.iota;     // combine_grad[2] * x - iota

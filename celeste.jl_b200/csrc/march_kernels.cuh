@@ -183,6 +183,7 @@ __global__ void __launch_bounds__(MARCH_THREADS, CELESTE_MARCH_MINB)
     double* s_rec = tacc + NT_ACC * MARCH_THREADS;         // MARCH_NIMG x NC2 x MREC: the source being walked
     double* s_si = s_rec + MARCH_NIMG * NC2 * MREC;        // MARCH_NIMG x SI_STRIDE
     __shared__ double s_exptab[8];
+    __shared__ double s_logtab[256];
     __shared__ MarchUnits s_nu;                            // walks of the current neighbour
     __shared__ MarchImg s_img[MARCH_NIMG];
     __shared__ MarchHdr s_hdr;
@@ -203,8 +204,10 @@ __global__ void __launch_bounds__(MARCH_THREADS, CELESTE_MARCH_MINB)
     for (int a = 0; a < NT_ACC; ++a) tacc[a * MARCH_THREADS + tid] = 0.0;
 #ifdef CELESTE_HOST_EMULATION
     if (tid < 8) s_exptab[tid] = h_exptab[tid];
+    for (int i = tid; i < 256; i += MARCH_THREADS) s_logtab[i] = h_logtab[i];
 #else
     if (tid < 8) s_exptab[tid] = c_exptab[tid];
+    for (int i = tid; i < 256; i += MARCH_THREADS) s_logtab[i] = g_logtab[i];
 #endif
     const unsigned hasbg = th.hasbg;
 
@@ -592,7 +595,7 @@ __global__ void __launch_bounds__(MARCH_THREADS, CELESTE_MARCH_MINB)
                 double la[NUA];
 #pragma unroll
                 for (int q = 0; q < NUA; ++q) la[q] = 0.0;
-                pixel_accumulate<MODE>(la, 1, pc, (double)skyf + bE, bV, covered, true, cb, f0, g0, h0, gal);
+                pixel_accumulate<MODE>(la, 1, pc, (double)skyf + bE, bV, covered, true, cb, f0, g0, h0, gal, s_logtab);
                 val += la[ACC_VAL];
                 if (MODE >= 1 && covered) {
                     // (c, y) space of this image -> task space: dx_a/dpos_b = -J[a + 2 b]; the c-scalars go to their band
