@@ -901,10 +901,10 @@ template <int MODE>
 static int launch_mode(celeste_plan* p, const double* vp_dev, double* v, double* d, double* h, long long* counters,
                        int* flags, cudaStream_t st) {
     const PlanDev pd = plan_dev(p);
-    const long total = (long)p->n_slots * p->N * MAX_COMPS;
-    const int sblocks = (int)std::min<long>((total + 255) / 256, 148L * 16);
+    const long total = (long)p->n_slots * p->N * MAX_K;
+    const int sblocks = (int)std::max<long>(1, std::min<long>((total + 127) / 128, 148L * 16));
     if (p->timing) CUDA_TRY(cudaEventRecord(p->ev[0], st));
-    setup_kernel<<<sblocks, 256, 0, st>>>(pd, vp_dev);
+    setup_kernel<<<sblocks, 128, 0, st>>>(pd, vp_dev);
     if (p->timing) CUDA_TRY(cudaEventRecord(p->ev[1], st));
     if constexpr (MODE <= 1) {
         if (p->use_march) {
@@ -1078,9 +1078,9 @@ int celeste_render_expectation(celeste_field* f, int32_t S, const int32_t* sourc
     CUDA_TRY(cudaMemcpyAsync(pl->vp_dev.p, vp, (size_t)S * NPARAM * sizeof(double), cudaMemcpyHostToDevice, st));
     const PlanDev pd = plan_dev(pl.get());
     {
-        const long total = (long)pl->n_slots * N * MAX_COMPS;
-        const int sblocks = (int)std::min<long>((total + 255) / 256, 148L * 16);
-        setup_kernel<<<sblocks, 256, 0, st>>>(pd, pl->vp_dev.p);
+        const long total = (long)pl->n_slots * N * MAX_K;
+        const int sblocks = (int)std::max<long>(1, std::min<long>((total + 127) / 128, 148L * 16));
+        setup_kernel<<<sblocks, 128, 0, st>>>(pd, pl->vp_dev.p);
     }
     std::vector<int> imgH(N), imgW(N);
     for (int n = 0; n < N; ++n) {

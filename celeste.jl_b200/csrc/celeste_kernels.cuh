@@ -129,12 +129,13 @@ __global__ void prep_image_kernel(int H, int W, const float* __restrict__ pixels
     }
 }
 
-// one thread per (slot, image, component)
+// one thread per (slot, image, PSF component): the 14 prototype components of that PSF component share the
+// source's XiXi (one sin / cos per thread instead of one per component)
 __global__ void setup_kernel(PlanDev plan, const double* __restrict__ vp) {
-    const long total = (long)plan.n_slots * plan.N * MAX_COMPS;
+    const long total = (long)plan.n_slots * plan.N * MAX_K;
     for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-        const int c = (int)(idx % MAX_COMPS);
-        const long sn = idx / MAX_COMPS;
+        const int k = (int)(idx % MAX_K);
+        const long sn = idx / MAX_K;
         const int n = (int)(sn % plan.N);
         const int slot = (int)(sn / plan.N);
         const double* vs = vp + (size_t)NPARAM * slot;
@@ -145,13 +146,17 @@ __global__ void setup_kernel(PlanDev plan, const double* __restrict__ vp) {
         const double d0 = vs[0] - p.wc[0], d1 = vs[1] - p.wc[1];
         const double m1 = (p.J[0] * d0 + p.J[2] * d1) + p.pc[0];
         const double m2 = (p.J[1] * d0 + p.J[3] * d1) + p.pc[1];
-        if (c < NPROTO * p.K) {
-            const int j = c / p.K, k = c % p.K;
-            make_component(p.psf + 7 * k, c_proto_eta[j], c_proto_nu[j], m1, m2, vs[3], vs[4], vs[5],
-                           rec + c * COMP_STRIDE);
-            rec[MAX_COMPS * COMP_STRIDE + 2 + c] = exp(-rec[c * COMP_STRIDE + 4]);   // column ratio of march_kernel
+        if (k < p.K) {
+            double x11, off, x22;
+            galaxy_xixi(vs[3], vs[4], vs[5], x11, off, x22);
+            const double* psf7 = p.psf + 7 * k;
+            for (int j = 0; j < NPROTO; ++j) {
+                const int c = j * p.K + k;
+                make_component_xi(psf7, c_proto_eta[j], c_proto_nu[j], m1, m2, x11, off, x22, rec + c * COMP_STRIDE);
+                rec[MAX_COMPS * COMP_STRIDE + 2 + c] = exp(-rec[c * COMP_STRIDE + 4]);   // column ratio of march_kernel
+            }
         }
-        if (c == 0) {
+        if (k == 0) {
             rec[MAX_COMPS * COMP_STRIDE + 0] = m1;
             rec[MAX_COMPS * COMP_STRIDE + 1] = m2;
             if (n == 0) {

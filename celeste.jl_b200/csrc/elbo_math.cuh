@@ -706,14 +706,17 @@ CEL_HD void pixel_accumulate(double* acc, int stride, const PixelConsts& pc, dou
 // Per-(source, image) mixture set-up: load_bvn_mixtures! (fsm_util.jl:111-169), GalaxyCacheComponent
 // (:37-65), BvnComponent (BivariateNormals.jl:151-191), get_bvn_cov (:29-43); one call per component.
 // psf7: alphaBar, xiBar[2], tauBar col-major (4).  Writes a 6-double component record.
-CEL_HD void make_component(const double* psf7, double eta, double nuBar, double m1, double m2, double rho, double phi,
-                           double sigma, double* out) {
+// XiXi(rho, phi, sigma) of get_bvn_cov (BivariateNormals.jl:29-43): the same for every component and image of a source
+CEL_HD void galaxy_xixi(double rho, double phi, double sigma, double& x11, double& off, double& x22) {
     const double cp = cos(phi), sp = sin(phi);
     const double ab_term = rho * rho - 1.0;
     const double ss = sigma * sigma;
-    const double off = -ss * cp * sp * ab_term;
-    const double x11 = ss * (1.0 + ab_term * (sp * sp));
-    const double x22 = ss * (1.0 + ab_term * (cp * cp));
+    off = -ss * cp * sp * ab_term;
+    x11 = ss * (1.0 + ab_term * (sp * sp));
+    x22 = ss * (1.0 + ab_term * (cp * cp));
+}
+CEL_HD void make_component_xi(const double* psf7, double eta, double nuBar, double m1, double m2, double x11, double off,
+                              double x22, double* out) {
     const double v11 = psf7[3] + nuBar * x11;
     const double v21 = psf7[4] + nuBar * off;
     const double v12 = psf7[5] + nuBar * off;
@@ -728,6 +731,12 @@ CEL_HD void make_component(const double* psf7, double eta, double nuBar, double 
     out[5] = (psf7[0] * eta) * (1.0 / (sqrt(det) * 6.283185307179586476925286766559));
     out[6] = 0.5 * out[2];
     out[7] = 0.5 * out[4];
+}
+CEL_HD void make_component(const double* psf7, double eta, double nuBar, double m1, double m2, double rho, double phi,
+                           double sigma, double* out) {
+    double x11, off, x22;
+    galaxy_xixi(rho, phi, sigma, x11, off, x22);
+    make_component_xi(psf7, eta, nuBar, m1, m2, x11, off, x22, out);
 }
 
 // GalaxySigmaDerivs (BivariateNormals.jl:346-397) with nuBar = 1: J0[k][j] = dSigma_k/dshape_j,

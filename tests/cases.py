@@ -166,6 +166,20 @@ def case_wide_patch():
     return images, patches, _all_tasks(vp)
 
 
+def case_seven_images():
+    """N = 7 images (two exposures of bands 3 and 4 on top of the five SDSS bands, as a multi-epoch box has): the
+    march kernel splits a source into two image groups whose partial sums meet in the epilogue, and two images share
+    a band's accumulators."""
+    images = synthetic.blank_images(44, 40, bands=(1, 2, 3, 4, 5, 3, 4))
+    catalog = [synthetic.sample_ce([20.7, 18.2], False), synthetic.sample_ce([25.1, 23.3], True),
+               synthetic.sample_ce([12.4, 27.9], True)]
+    synthetic.gen_images(images, catalog, seed=13, device="cpu")
+    patches = get_sky_patches(images, catalog, radius_override_pix=10.0)
+    vp = [cj.catalog_init_source(ce) for ce in catalog]
+    synthetic.perturb_params(vp)
+    return images, patches, _all_tasks(vp)
+
+
 CASES = {
     "star_1band": case_star_1band,
     "star_5band": case_star_5band,
@@ -180,6 +194,7 @@ CASES = {
     "crowded": case_crowded,
     "small_field": case_small_field,
     "wide_patch": case_wide_patch,
+    "seven_images": case_seven_images,
 }
 
 _cache = {}

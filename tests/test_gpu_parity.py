@@ -197,7 +197,8 @@ def test_deterministic_and_mode_consistent(cj):
     assert np.all(np.abs(gd - ad) <= 1e-10 * np.maximum(np.abs(ad), sc * 1e-3)), np.abs(gd - ad).max()
 
 
-@pytest.mark.parametrize("name", ["two_body", "masked", "clipped_and_empty", "crowded", "config2", "small_field", "wide_patch"])
+@pytest.mark.parametrize("name", ["two_body", "masked", "clipped_and_empty", "crowded", "config2", "small_field", "wide_patch",
+                                  "seven_images"])
 def test_march_kernel_matches_task_kernel(cj, name, monkeypatch):
     """The two value / gradient kernels of the library -- march_kernel (row walks, exp recurrence; the default for
     Sa = 1, K = 2) and task_kernel (direct evaluation; CELESTE_GRAD_KERNEL=task) -- agree to 1e-11, have identical
@@ -210,8 +211,12 @@ def test_march_kernel_matches_task_kernel(cj, name, monkeypatch):
         direct = field.elbo_batch(tasks, mode=mode)
         monkeypatch.delenv("CELESTE_GRAD_KERNEL")
         march = field.elbo_batch(tasks, mode=mode)
+        monkeypatch.setenv("CELESTE_MARCH_SPLIT", "1")                 # every source: one block per image
+        split = field.elbo_batch(tasks, mode=mode)
+        monkeypatch.delenv("CELESTE_MARCH_SPLIT")
         cases.assert_parity(ref, direct, mode, name + " task_kernel")
         cases.assert_parity(ref, march, mode, name + " march_kernel")
+        cases.assert_parity(ref, split, mode, name + " march_kernel, one block per image")
         assert np.array_equal(march["counters"], direct["counters"])
         fin = np.isfinite(direct["v"])
         assert np.all(np.abs(march["v"] - direct["v"])[fin] <= 1e-11 * np.abs(direct["v"])[fin])
