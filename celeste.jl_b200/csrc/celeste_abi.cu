@@ -752,10 +752,38 @@ int celeste_plan_create_multi(int32_t n_fields, celeste_field* const* fields, ce
         const char* env = std::getenv("CELESTE_GRAD_KERNEL");
         const bool want = !(env && std::strcmp(env, "task") == 0);
         pl->use_march = want && pl->uniform_K == 2 && n_subs == n_tasks;
+        // march_kernel indexes pixels with 32-bit integers (registers are what limits it): larger images or patches
+        // keep task_kernel
+        for (int i = 0; i < n_fields && pl->use_march; ++i) {
+            for (const ImageDev& im : fields[i]->h_images)
+                if ((long long)im.H * im.W >= (1LL << 31)) pl->use_march = false;
+            for (const PatchDev& pa : fields[i]->h_patches)
+                if ((long long)pa.H2 * pa.W2 >= (1LL << 29)) pl->use_march = false;
+        }
     }
     if (pl->use_march) {
-        long split = 1000000000;                   // pixels of a source above which it gets one block per image (off by default)
-        if (const char* env = std::getenv("CELESTE_MARCH_SPLIT"))   // kernel-tuning knob
+        // A source normally gets ONE block (all its images: best packing of its rows into the block's walk slots).
+        // When the plan is small against the GPU, the heaviest sources would then be the whole tail of the launch
+        // (a 51 x 51 x 5-pixel source alone on an SM runs for longer than the rest of a 1000-source plan), so sources
+        // above `split` patch pixels are cut into smaller image groups: split = the plan's pixels per resident block
+        // slot (SMs x 3; CELESTE_MARCH_SPLIT_PCT scales it), never below 1500.  CELESTE_MARCH_SPLIT=<pixels> overrides
+        // (kernel-tuning knobs).
+        long split;
+        {
+            long total_px = 0;
+            for (int u = 0; u < n_subs; ++u) {
+                const celeste_field* f = fields[tfield[sub_task[u]]];
+                for (int n = 0; n < pl->N; ++n) {
+                    const PatchDev& pa = f->h_patches[(size_t)src_row[sub_slot[u]] + (size_t)n * f->S_tot];
+                    total_px += (long)std::max(pa.H2, 0) * std::max(pa.W2, 0);
+                }
+            }
+            int sms = 148;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
+            const long alpha_pct = std::getenv("CELESTE_MARCH_SPLIT_PCT") ? std::atol(std::getenv("CELESTE_MARCH_SPLIT_PCT")) : 100;
+            split = std::max(1500L, total_px * std::max(1L, alpha_pct) / (100L * sms * CELESTE_MARCH_MINB));
+        }
+        if (const char* env = std::getenv("CELESTE_MARCH_SPLIT"))
             if (std::atol(env) > 0) split = std::atol(env);
         std::vector<MarchHdr> mm;
         std::vector<int> part_ptr;

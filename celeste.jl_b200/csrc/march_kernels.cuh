@@ -646,7 +646,8 @@ __global__ void __launch_bounds__(MARCH_THREADS, CELESTE_MARCH_MINB)
 }
 
 // Host side: the blocks of a plan.  One block per (sub, group of <= MARCH_NIMG images); a source whose patches hold
-// more than `split_pixels` pixels gets one block per image so that no single block is a long tail of the launch.
+// more than `split_pixels` pixels is cut into smaller image groups (down to one block per image) so that no single
+// block is a long tail of the launch.
 // Each block owns one NT_ACC-vector of plan.partials (pidx); part_ptr[sub] .. part_ptr[sub + 1] are the blocks of a
 // sub, in image order.  geo(slot, n, off_h, off_w, H2, W2) -> the patch box of a slot in image n.
 // nseg (column segments per row) minimises  block-rounds x (iterations of two columns + an exact start, ~0.6
@@ -667,7 +668,13 @@ inline void build_march_blocks(int n_subs, int N, const int* sub_task, const int
             geo(aslot, n, oh, ow, H2, W2);
             tot += (long)std::max(H2, 0) * std::max(W2, 0);
         }
-        const int step = tot > split_pixels ? 1 : MARCH_NIMG;
+        // images per block: all of them (<= MARCH_NIMG) unless the source is heavier than split_pixels; then as many
+        // as keep a block under that limit (at least one)
+        int step = MARCH_NIMG;
+        if (tot > split_pixels && N > 0) {
+            const long per_image = std::max(1L, tot / N);
+            step = (int)std::max(1L, std::min((long)MARCH_NIMG, split_pixels / per_image));
+        }
         for (int n0 = 0; n0 < N; n0 += step) {
             MarchHdr th{};
             th.aslot = aslot;
