@@ -7,7 +7,7 @@ import torch
 import celeste_jl_b200 as cj
 from celeste_jl_b200 import elbo_maximize as em
 import cases
-for name in ("two_body", "clipped_and_empty", "psf_k3", "crowded"):
+for name in ("two_body", "clipped_and_empty", "psf_k3", "crowded", "masked", "wide_patch", "seven_images"):
     images, patches, tasks = cases.get(name)
     f = cj.DeviceField(images, patches)
     for mode in (0, 1, 2):
