@@ -884,6 +884,7 @@ int celeste_plan_kernel_times(celeste_plan* p, float ms[3]) {
 
 int celeste_plan_launches(const celeste_plan* p, int32_t mode) {
     if (!p || p->n_tasks == 0) return 0;
+    if (mode <= 1 && p->use_march) return 2;                                       // march, epilogue
     return (p->n_blocks > 0 ? 3 : 2) + ((mode == 2 && p->n_pairs > 0) ? 1 : 0);   // setup, pixel, [pair,] epilogue
 }
 
@@ -932,19 +933,23 @@ static int launch_mode(celeste_plan* p, const double* vp_dev, double* v, double*
     const long total = (long)p->n_slots * p->N * MAX_K;
     const int sblocks = (int)std::max<long>(1, std::min<long>((total + 127) / 128, 148L * 16));
     if (p->timing) CUDA_TRY(cudaEventRecord(p->ev[0], st));
-    setup_kernel<<<sblocks, 128, 0, st>>>(pd, vp_dev);
-    if (p->timing) CUDA_TRY(cudaEventRecord(p->ev[1], st));
     if constexpr (MODE <= 1) {
         if (p->use_march) {
-            // value / gradient, production shape: row walks with the exp recurrence (march_kernels.cuh)
+            // value / gradient, production shape: row walks with the exp recurrence (march_kernels.cuh).  The blocks
+            // build their sources' mixtures themselves: no set-up launch.
+            if (p->timing) CUDA_TRY(cudaEventRecord(p->ev[1], st));
             if (p->n_marchblocks > 0)
-                march_kernel<MODE><<<p->n_marchblocks, MARCH_THREADS, march_smem_bytes(), st>>>(pd, p->marchmap.p);
+                march_kernel<MODE><<<p->n_marchblocks, MARCH_THREADS, march_smem_bytes(), st>>>(pd, p->marchmap.p, vp_dev);
             if (p->timing) CUDA_TRY(cudaEventRecord(p->ev[2], st));
             march_epilogue_kernel<MODE><<<p->n_tasks, MEPI_THREADS, 0, st>>>(pd, vp_dev, p->march_part_ptr.p, v, d, counters, flags);
             if (p->timing) CUDA_TRY(cudaEventRecord(p->ev[3], st));
             CUDA_TRY(cudaGetLastError());
             return CELESTE_OK;
         }
+    }
+    setup_kernel<<<sblocks, 128, 0, st>>>(pd, vp_dev);
+    if (p->timing) CUDA_TRY(cudaEventRecord(p->ev[1], st));
+    if constexpr (MODE <= 1) {
         // value / gradient: task-level blocks, one partial per (sub, image, warp)
         PlanDev pt = pd;
         pt.chunk_ptr = p->task_chunk_ptr.p;

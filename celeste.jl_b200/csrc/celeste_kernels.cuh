@@ -50,7 +50,7 @@ struct PatchDev {
 };
 
 // per (task source slot, image) scratch written by setup_kernel
-constexpr int SLOTIMG_STRIDE = MAX_COMPS * COMP_STRIDE + 2 + MAX_COMPS;   // comps + m_pos + exp(-L22) per component
+constexpr int SLOTIMG_STRIDE = MAX_COMPS * COMP_STRIDE + 2;   // comps + m_pos
 // per slot: El[2][5], Ell[2][5], a[2], theta
 constexpr int SLOTBR_STRIDE = 24;
 
@@ -153,7 +153,6 @@ __global__ void setup_kernel(PlanDev plan, const double* __restrict__ vp) {
             for (int j = 0; j < NPROTO; ++j) {
                 const int c = j * p.K + k;
                 make_component_xi(psf7, c_proto_eta[j], c_proto_nu[j], m1, m2, x11, off, x22, rec + c * COMP_STRIDE);
-                rec[MAX_COMPS * COMP_STRIDE + 2 + c] = exp(-rec[c * COMP_STRIDE + 4]);   // column ratio of march_kernel
             }
         }
         if (k == 0) {

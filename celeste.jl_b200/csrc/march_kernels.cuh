@@ -71,31 +71,51 @@ struct MarchBox {     // intersection of a neighbour's patch with the active pat
     int h0, w0, nh, nw;
 };
 
-// stage the K = 2 component records of (slot, image) for marching; one thread per component
-__device__ inline void march_stage_records(const double* rec, double* dst, int c) {
-    const double* cp = rec + c * COMP_STRIDE;
+// m_pos of a source in an image: linear_world_to_pix, wcs_utils.jl:14-18 (the same expression as setup_kernel)
+__device__ __forceinline__ void march_m_pos(const PatchDev& p, const double* vs, double& m1, double& m2) {
+    const double d0 = vs[0] - p.wc[0], d1 = vs[1] - p.wc[1];
+    m1 = (p.J[0] * d0 + p.J[2] * d1) + p.pc[0];
+    m2 = (p.J[1] * d0 + p.J[3] * d1) + p.pc[1];
+}
+
+// Component record c = 2 j + k of (source, image) for marching, computed in place from the source's parameters --
+// load_bvn_mixtures! (fsm_util.jl:111-169) with exactly setup_kernel's arithmetic -- plus the column ratio
+// exp(-L22).  xixi: the source's XiXi (galaxy_xixi: one sin / cos per source and block, by one thread).  The march path needs no set-up launch and no 2 KB-per-(source, image) scratch round trip through HBM.
+// One thread per component.
+__device__ inline void march_make_record(const PatchDev& p, const double* vs, const double* xixi, double* dst, int c) {
+    const int j = c >> 1, k = c & 1;
+    double m1, m2, t[COMP_STRIDE];
+    march_m_pos(p, vs, m1, m2);
+    make_component_xi(p.psf + 7 * k, c_proto_eta[j], c_proto_nu[j], m1, m2, xixi[0], xixi[1], xixi[2], t);
     double* o = dst + c * MREC;
-    o[0] = cp[2];
-    o[1] = cp[3];
-    o[2] = cp[4];
-    o[3] = rec[MAX_COMPS * COMP_STRIDE + 2 + c];   // exp(-L22), written by setup_kernel
-    o[4] = cp[0];
-    o[5] = cp[1];
-    o[6] = cp[5];
+    o[0] = t[2];
+    o[1] = t[3];
+    o[2] = t[4];
+    o[3] = exp(-t[4]);
+    o[4] = t[0];
+    o[5] = t[1];
+    o[6] = t[5];
     o[7] = 0.0;
 }
 
-// per-(source, image) constants: brightness scalars, m_pos, spline weights, Jacobian
+// per-(source, image) constants: brightness scalars of the image's band (source_brightness.jl:27-202, the sums in
+// brightness_values' order), m_pos, spline weights, Jacobian
 template <int MODE>
-__device__ inline void march_stage_srcimg(const PlanDev& plan, const PatchDev& p, int slot, int n, int band0, double* si) {
-    const double* rec = plan.slotimg + ((size_t)slot * plan.N + n) * SLOTIMG_STRIDE;
-    const double* br = plan.slotbr + (size_t)slot * SLOTBR_STRIDE;
-    const double a1 = br[20], a2 = br[21];
-    si[SI_CB + 0] = a1 * br[band0];
-    si[SI_CB + 1] = a2 * br[5 + band0];
-    si[SI_CB + 2] = a1 * br[10 + band0];
-    si[SI_CB + 3] = a2 * br[15 + band0];
-    const double m1 = rec[MAX_COMPS * COMP_STRIDE], m2 = rec[MAX_COMPS * COMP_STRIDE + 1];
+__device__ inline void march_stage_srcimg(const PatchDev& p, const double* vs, int band0, double* si) {
+    double ka[10], la[10];
+    band_coefs(band0, ka, la);
+    for (int i = 0; i < 2; ++i) {
+        double s1 = 0, s2 = 0;
+        for (int k = 0; k < 10; ++k) {
+            const double beta = vs[bright_id(i, k)];
+            s1 += ka[k] * beta;
+            s2 += la[k] * beta;
+        }
+        si[SI_CB + i] = vs[26 + i] * exp(s1);
+        si[SI_CB + 2 + i] = vs[26 + i] * exp(s2);
+    }
+    double m1, m2;
+    march_m_pos(p, vs, m1, m2);
     si[SI_M] = m1;
     si[SI_M + 1] = m2;
     const double ax = (double)(p.off_h + 1) - m1 + 26.0, ay = (double)(p.off_w + 1) - m2 + 26.0;
@@ -103,7 +123,7 @@ __device__ inline void march_stage_srcimg(const PlanDev& plan, const PatchDev& p
     cubic_weights<(MODE >= 1 ? 1 : 0)>(ax - floor(ax), si + SI_WX, si + SI_DWX, dd);
     cubic_weights<(MODE >= 1 ? 1 : 0)>(ay - floor(ay), si + SI_WY, si + SI_DWY, dd);
     for (int i = 0; i < 4; ++i) si[SI_J + i] = p.J[i];
-    si[SI_THETA] = br[22];
+    si[SI_THETA] = vs[2];
     si[SI_THETA + 1] = 0.0;
 }
 
@@ -174,7 +194,7 @@ struct MarchHdr {
 // One block per (active source of a task, group of <= MARCH_NIMG images).
 template <int MODE>
 __global__ void __launch_bounds__(MARCH_THREADS, CELESTE_MARCH_MINB)
-    march_kernel(PlanDev plan, const MarchHdr* __restrict__ blocks) {
+    march_kernel(PlanDev plan, const MarchHdr* __restrict__ blocks, const double* __restrict__ vp) {
     static_assert(MODE <= 1, "the Hessian mode uses pixel_kernel");
     constexpr int NUA = MODE == 0 ? 1 : NACC_MODE1;   // (c, y)-space accumulators of the current walk
     constexpr int NS = MODE == 0 ? 2 : 7;             // mixture sums per pixel: F_dev F_exp | AX1 AX2 AS1 AS2 AS3
@@ -187,10 +207,15 @@ __global__ void __launch_bounds__(MARCH_THREADS, CELESTE_MARCH_MINB)
     __shared__ MarchUnits s_nu;                            // walks of the current neighbour
     __shared__ MarchImg s_img[MARCH_NIMG];
     __shared__ MarchHdr s_hdr;
+    __shared__ double s_xixi[2][4];                        // XiXi of the active source / of the current neighbour
 
     const int tid = threadIdx.x, lane = tid & 31, kk = tid & 1;
     const int pair0 = (tid >> 5) * NPW;                    // first walk slot of this warp
     if (tid < (int)(sizeof(MarchHdr) / sizeof(int))) reinterpret_cast<int*>(&s_hdr)[tid] = reinterpret_cast<const int*>(blocks + blockIdx.x)[tid];
+    if (tid == MARCH_THREADS - 1) {
+        const double* vs = vp + (size_t)NPARAM * blocks[blockIdx.x].aslot;
+        galaxy_xixi(vs[3], vs[4], vs[5], s_xixi[0][0], s_xixi[0][1], s_xixi[0][2]);
+    }
     __syncthreads();
     const MarchHdr& th = s_hdr;
     if (plan.task_mask && !plan.task_mask[th.task]) return;
@@ -224,6 +249,10 @@ __global__ void __launch_bounds__(MARCH_THREADS, CELESTE_MARCH_MINB)
         for (int s = slot0; s < slot1; ++s) {
             if (s == aslot) continue;
             __syncthreads();      // the previous neighbour's sums (or the zeros) are in place; s_nu / s_nrec are free
+            if (tid == (MARCH_THREADS > 32 ? 32 : 1)) {
+                const double* vs = vp + (size_t)NPARAM * s;
+                galaxy_xixi(vs[3], vs[4], vs[5], s_xixi[1][0], s_xixi[1][1], s_xixi[1][2]);
+            }
             if (tid == 0) {
                 s_nu.ubeg[0] = 0;
                 for (int k = 0; k < MARCH_NIMG; ++k) {
@@ -255,11 +284,12 @@ __global__ void __launch_bounds__(MARCH_THREADS, CELESTE_MARCH_MINB)
             for (int i = tid; i < nimg * NC2; i += MARCH_THREADS) {
                 const int k = i / NC2, c = i - k * NC2;
                 if (s_nu.ubeg[k + 1] > s_nu.ubeg[k])
-                    march_stage_records(plan.slotimg + ((size_t)s * plan.N + th.n0 + k) * SLOTIMG_STRIDE, s_rec + k * NC2 * MREC, c);
+                    march_make_record(field.patches[plan.src_row[s] + (size_t)(th.n0 + k) * field.S_tot], vp + (size_t)NPARAM * s,
+                                      s_xixi[1], s_rec + k * NC2 * MREC, c);
             }
             if (tid < nimg && s_nu.ubeg[tid + 1] > s_nu.ubeg[tid]) {
                 const int k = tid, n = th.n0 + k;
-                march_stage_srcimg<0>(plan, field.patches[plan.src_row[s] + (size_t)n * field.S_tot], s, n,
+                march_stage_srcimg<0>(field.patches[plan.src_row[s] + (size_t)n * field.S_tot], vp + (size_t)NPARAM * s,
                                       field.images[n].band - 1, s_si + k * SI_STRIDE);
             }
             __syncthreads();
@@ -373,13 +403,13 @@ __global__ void __launch_bounds__(MARCH_THREADS, CELESTE_MARCH_MINB)
     }
     for (int i = tid; i < nimg * NC2; i += MARCH_THREADS) {
         const int k = i / NC2, c = i - k * NC2;
-        march_stage_records(plan.slotimg + ((size_t)aslot * plan.N + th.n0 + k) * SLOTIMG_STRIDE, s_rec + k * NC2 * MREC, c);
+        march_make_record(apatch[(size_t)(th.n0 + k) * field.S_tot], vp + (size_t)NPARAM * aslot, s_xixi[0], s_rec + k * NC2 * MREC, c);
     }
     if (tid < nimg) {
         const int k = tid, n = th.n0 + k;
         const PatchDev& pa = apatch[(size_t)n * field.S_tot];
         const ImageDev& img = field.images[n];
-        march_stage_srcimg<MODE>(plan, pa, aslot, n, img.band - 1, s_si + k * SI_STRIDE);
+        march_stage_srcimg<MODE>(pa, vp + (size_t)NPARAM * aslot, img.band - 1, s_si + k * SI_STRIDE);
         MarchImg mi;
         mi.pixels = img.pixels;
         mi.sky = img.sky;
@@ -758,6 +788,7 @@ __global__ void __launch_bounds__(MEPI_THREADS) march_epilogue_kernel(PlanDev pl
                                                                       int* __restrict__ out_flags) {
     __shared__ double ysum[NT_ACC];
     __shared__ double J0[3][3], T0[3][3][3];
+    __shared__ double s_El[2][5], s_Ell[2][5];
     __shared__ int s_bad;
     const int tid = threadIdx.x;
     const int t = blockIdx.x;
@@ -765,8 +796,8 @@ __global__ void __launch_bounds__(MEPI_THREADS) march_epilogue_kernel(PlanDev pl
     const int sub = plan.sub_ptr[t];                 // Sa == 1
     const int aslot = plan.sub_slot[sub];
     const double* vs = vp + (size_t)NPARAM * aslot;
-    const double* br = plan.slotbr + (size_t)aslot * SLOTBR_STRIDE;
     constexpr int NA = MODE == 0 ? TA_POS : NT_ACC;
+    if (tid == 33 && MODE >= 1) brightness_values(vs, s_El, s_Ell);
     if (tid < NA) {
         double s = 0.0;
         for (int g = part_ptr[sub]; g < part_ptr[sub + 1]; ++g) s += plan.partials[(size_t)g * NT_ACC + tid];   // fixed order
@@ -791,13 +822,13 @@ __global__ void __launch_bounds__(MEPI_THREADS) march_epilogue_kernel(PlanDev pl
             for (int b = 0; b < 5; ++b) {
                 double ka[10], la[10];
                 band_coefs(b, ka, la);
-                g += br[20 + i] * (br[i * 5 + b] * ka[k] * ysum[TA_BAND + 4 * b + i] +
-                                   br[10 + i * 5 + b] * la[k] * ysum[TA_BAND + 4 * b + 2 + i]);
+                g += vs[26 + i] * (s_El[i][b] * ka[k] * ysum[TA_BAND + 4 * b + i] +
+                                   s_Ell[i][b] * la[k] * ysum[TA_BAND + 4 * b + 2 + i]);
             }
         } else if (q == 26 || q == 27) {
             i = q - 26;
             for (int b = 0; b < 5; ++b)
-                g += br[i * 5 + b] * ysum[TA_BAND + 4 * b + i] + br[10 + i * 5 + b] * ysum[TA_BAND + 4 * b + 2 + i];
+                g += s_El[i][b] * ysum[TA_BAND + 4 * b + i] + s_Ell[i][b] * ysum[TA_BAND + 4 * b + 2 + i];
         }
         out_d[(size_t)NPARAM * sub + q] = g;
         bad |= !isfinite(g);

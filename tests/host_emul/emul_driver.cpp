@@ -74,9 +74,9 @@ void run_task(PlanDev pd, const FieldDev& fd, const std::vector<TaskHdr>& taskma
             std::vector<double> bg((size_t)bg_total + 1, 1e300);     // poisoned: the kernel must zero what it reads
             pd.bg_ptr = bg_ptr.data();
             pd.bg = bg.data();
-            cuda_emul::launch(setup_kernel, 2, 64, 0, pd, vp);
             if (!mm.empty())
-                cuda_emul::launch(march_kernel<MODE>, (int)mm.size(), MARCH_THREADS, march_smem_bytes(), pd, (const MarchHdr*)mm.data());
+                cuda_emul::launch(march_kernel<MODE>, (int)mm.size(), MARCH_THREADS, march_smem_bytes(), pd, (const MarchHdr*)mm.data(),
+                                  vp);
             cuda_emul::launch(march_epilogue_kernel<MODE>, pd.n_tasks, MEPI_THREADS, 0, pd, vp, (const int*)part_ptr.data(), v, d,
                               counters, flags);
             return;
