@@ -732,7 +732,8 @@ inline void build_march_blocks(int n_subs, int N, const int* sub_task, const int
                     geo(s, n, ph, pw, pH2, pW2);
                     // rows off+1..off+H2 of both; columns off+1..off+W2 of the active patch, off+1..off+W2-1 of the
                     // neighbour (strict `w2 < W2`, elbo_objective.jl:349)
-                    if ((ph + 1 <= oh + H2) && (ph + pH2 >= oh + 1) && (pw + 1 <= ow + W2) && (pw + pW2 - 1 >= ow + 1))
+                    if (pH2 > 0 && pW2 > 1 && (ph + 1 <= oh + H2) && (ph + pH2 >= oh + 1) && (pw + 1 <= ow + W2) &&
+                        (pw + pW2 - 1 >= ow + 1))
                         th.hasbg |= 1u << (n - th.n0);
                 }
             }

@@ -22,6 +22,7 @@ def load():
         vp, i32 = C.c_void_p, C.c_int32
         _lib.emul_elbo_batch.argtypes = [i32, vp, i32, vp, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, i32]
         _lib.emul_set_grad_kernel.argtypes = [i32]
+        _lib.emul_march_blocks.argtypes = [i32, i32, vp, i32, vp, vp, C.c_int64, i32, vp, vp]
         _lib.emul_tr_subproblem.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp]
         _lib.emul_newton_step.argtypes = [i32, i32, vp]
         _lib.emul_spline_build.argtypes = [i32, vp, i32, vp, vp]
@@ -115,3 +116,18 @@ def find_all_neighbors(patches):
     nbr = np.zeros(max(need, 1), dtype=np.int32)
     load().emul_find_neighbors(S, N, boxes.ctypes.data, ptr.ctypes.data, nbr.ctypes.data)
     return [nbr[ptr[t]:ptr[t + 1]].tolist() for t in range(S)]
+
+
+def march_blocks(patches, tasks, split=10**9):
+    """build_march_blocks (host half of march_kernels.cuh) -> (list of block dicts, part_ptr)."""
+    fp = FlatPatches(patches)
+    task_ptr, src, _active_ptr, _act, _vp = csr_tasks(tasks)
+    n = len(task_ptr) - 1
+    cap = 64 * max(n, 1) * max(fp.N, 1)
+    out = np.zeros(12 * cap, dtype=np.int32)
+    part = np.zeros(n + 1, dtype=np.int32)
+    nb = load().emul_march_blocks(fp.N, fp.S_tot, C.addressof(fp.arr), n, task_ptr.ctypes.data, src.ctypes.data, int(split), cap,
+                                  out.ctypes.data, part.ctypes.data)
+    assert nb >= 0, nb
+    keys = ["aslot", "slot0", "slot1", "n0", "n1", "pidx", "nseg", "hasbg", "walks", "sub", "task", "npair"]
+    return [dict(zip(keys, out[12 * i:12 * i + 12].tolist())) for i in range(nb)], part

@@ -257,6 +257,41 @@ extern "C" int emul_set_grad_kernel(int32_t which) {
     return 0;
 }
 
+// build_march_blocks (the host half of march_kernels.cuh, shared with celeste_abi.cu) on its own: one task per
+// source list, Sa = 1, active source first.  out: 12 ints per block (aslot, slot0, slot1, n0, n1, pidx, nseg, hasbg,
+// and ubeg[1..4] are not needed by the checker: it gets ubeg[MARCH_NIMG] as `walks`) -- see tests/test_march_blocks.py.
+extern "C" int emul_march_blocks(int32_t N, int32_t S_tot, const celeste_patch* patches, int32_t n_tasks,
+                                 const int32_t* task_ptr, const int32_t* source_ids, int64_t split, int32_t capacity,
+                                 int32_t* out, int32_t* part_ptr_out) {
+    const int n_slots = task_ptr[n_tasks];
+    std::vector<int> sub_task(n_tasks), sub_slot(n_tasks), src_row(n_slots);
+    for (int t = 0; t < n_tasks; ++t) {
+        sub_task[t] = t;
+        sub_slot[t] = task_ptr[t];            // the active source is the first slot of its task
+    }
+    for (int s = 0; s < n_slots; ++s) src_row[s] = source_ids[s] - 1;
+    std::vector<MarchHdr> mm;
+    std::vector<int> part_ptr;
+    build_march_blocks(n_tasks, N, sub_task.data(), sub_slot.data(), task_ptr, (const int*)nullptr,
+                       [&](int slot, int n, int& oh, int& ow, int& H2, int& W2) {
+                           const celeste_patch& q = patches[(size_t)src_row[slot] + (size_t)n * S_tot];
+                           oh = (int)q.bitmap_offset[0];
+                           ow = (int)q.bitmap_offset[1];
+                           H2 = q.H2;
+                           W2 = q.W2;
+                       },
+                       (long)split, mm, part_ptr);
+    for (int t = 0; t <= n_tasks; ++t) part_ptr_out[t] = part_ptr[t];
+    if ((int)mm.size() > capacity) return -(int)mm.size();
+    for (size_t i = 0; i < mm.size(); ++i) {
+        const MarchHdr& h = mm[i];
+        int32_t* o = out + 12 * i;
+        o[0] = h.aslot; o[1] = h.slot0; o[2] = h.slot1; o[3] = h.n0; o[4] = h.n1; o[5] = h.pidx; o[6] = h.nseg;
+        o[7] = (int32_t)h.hasbg; o[8] = h.ubeg[MARCH_NIMG]; o[9] = h.sub; o[10] = h.task; o[11] = NPAIR;
+    }
+    return (int)mm.size();
+}
+
 extern "C" int emul_tr_subproblem(int32_t batch, int32_t n, const double* g, const double* H, const double* delta,
                                   double* s, double* m, int32_t* interior) {
     cuda_emul::launch(tr_subproblem_kernel, batch, TR_THREADS, 0, n, g, H, delta, (const unsigned char*)nullptr, s, m,
