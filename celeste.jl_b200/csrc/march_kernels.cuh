@@ -137,8 +137,18 @@ constexpr int NPAIR = MARCH_THREADS / 2;        // walks in flight per block
 
 // exact start at image pixel (hh, ww): f = z exp(-q/2) and the column ratio r for the 14 components of PSF
 // component kk (records c = 2 j + kk)
-__device__ __forceinline__ void march_start(const double* recs_k, const double* etab, double hh, double ww, double* fp,
+// Returns true if some component was put to sleep: a Gaussian that is below ~1e-282 of its peak at the start
+// (q / 2 > 650) cannot be carried by the recurrence -- its value is not representable, and the product of its column
+// ratios towards the centre would overflow -- so it gets f = r = 0 (it contributes exactly nothing) and the caller
+// restarts the walk after MARCH_CAREFUL_COLS columns, until no component sleeps.  Within that many columns a
+// sleeping component stays below exp(-80) of its peak for every precision L22 <= 34 (Gaussians down to 0.17 px
+// wide); sharper ones do not occur behind a sampled PSF.  Catalog-sized patches of SDSS-like PSFs never get here
+// (q / 2 <= 450 at the corner of a 51 x 51 patch for a 1.2 px PSF core).
+constexpr int MARCH_CAREFUL_COLS = 4;
+constexpr double MARCH_Q_SLEEP = 1300.0;
+__device__ __forceinline__ bool march_start(const double* recs_k, const double* etab, double hh, double ww, double* fp,
                                             double* rr) {
+    bool asleep = false;
 #pragma unroll
     for (int j = 0; j < NPROTO; ++j) {
         const double* o = recs_k + j * 2 * MREC;
@@ -147,11 +157,16 @@ __device__ __forceinline__ void march_start(const double* recs_k, const double* 
         const double p1 = l11 * d1 + l12 * d2;
         const double p2 = l12 * d1 + l22 * d2;
         const double q = d1 * p1 + d2 * p2;
-        fp[j] = z * exp_scaled_tab(q, -0.5, etab);
-        // exp(-(q(w+1) - q(w)) / 2); the argument may be positive (walking towards the centre): bounded so that
-        // r stays finite however large the patch is
-        rr[j] = exp_scaled_tab(fmin(-(p2 + 0.5 * l22), 700.0), 1.0, etab);
+        // exp(-(q(w+1) - q(w)) / 2); the argument may be positive (walking towards the centre)
+        const double ra = -(p2 + 0.5 * l22);
+        const bool sleep = !(q <= MARCH_Q_SLEEP) || !(ra <= 700.0);      // (NaN parameters sleep too: the value term stays NaN through E)
+        asleep |= sleep;
+        const double f = z * exp_scaled_tab(q, -0.5, etab);
+        const double r = exp_scaled_tab(fmin(ra, 700.0), 1.0, etab);
+        fp[j] = sleep ? 0.0 : f;
+        rr[j] = sleep ? 0.0 : r;
     }
+    return asleep;
 }
 
 __device__ __forceinline__ int warp_max_int(int v) {
@@ -319,7 +334,6 @@ __global__ void __launch_bounds__(MARCH_THREADS, CELESTE_MARCH_MINB)
                 const double* si = s_si + k * SI_STRIDE;
                 const double* recs = s_rec + (k * NC2 + kk) * MREC;      // this lane's PSF component
                 double fp[NPROTO], rr[NPROTO];
-                march_start(recs, s_exptab, (double)h, (double)w0, fp, rr);
                 // star: sliding window of row-interpolated columns, own pixels are columns kk, kk + 2, ...
                 const double ax = (double)h - si[SI_M] + 26.0, ay0 = (double)w0 - si[SI_M + 1] + 26.0;
                 const int ixf = (int)floor(ax), iy0 = (int)floor(ay0);
@@ -341,7 +355,14 @@ __global__ void __launch_bounds__(MARCH_THREADS, CELESTE_MARCH_MINB)
                 double* bgE = plan.bg + (has ? bgp[n] : 0) + ah2 + (size_t)acol * aH2;
                 const size_t bgplane = (size_t)aH2 * aW2;
                 const double theta = si[SI_THETA];
-                for (int t = 0; t < nit; ++t) {
+                int t = 0;
+                while (t < nit) {
+                // (re)start the recurrence exactly at column 2t; a walk with sleeping components restarts every few columns
+                // (the decision is taken for the whole warp, so that every loop around the shuffles stays warp-uniform)
+                const bool asleep = march_start(recs, s_exptab, (double)h, (double)(w0 + 2 * t), fp, rr);
+                const bool careful = __ballot_sync(0xffffffffu, asleep && len > 0) != 0u;
+                const int tend = careful ? min(nit, t + MARCH_CAREFUL_COLS / 2) : nit;
+                for (; t < tend; ++t) {
                     const bool own = 2 * t + kk < len;
                     unsigned char ab = 0, nb = 0;
                     float xv = 0.f;
@@ -395,6 +416,7 @@ __global__ void __launch_bounds__(MARCH_THREADS, CELESTE_MARCH_MINB)
                     bgE += 2 * aH2;
                     R0 = R2;
                     R1 = R3;
+                }
                 }
             }
             tacc[TA_CNT_INACTIVE * MARCH_THREADS + tid] += cnt_inactive;
@@ -455,7 +477,6 @@ __global__ void __launch_bounds__(MARCH_THREADS, CELESTE_MARCH_MINB)
         const double* si = s_si + k * SI_STRIDE;
         const double* recs = s_rec + (k * NC2 + kk) * MREC;          // this lane's PSF component
         double fp[NPROTO], rr[NPROTO];
-        march_start(recs, s_exptab, (double)h, (double)w0, fp, rr);
         const double d1 = (double)h - recs[4];                        // x1 - mu1 of this PSF component
         double d2 = (double)w0 - recs[5];
         // star: own pixels are columns kk, kk + 2, ... of the segment
@@ -490,7 +511,14 @@ __global__ void __launch_bounds__(MARCH_THREADS, CELESTE_MARCH_MINB)
         double* ta = tacc + tid;
         double cnt_active = 0.0, val = 0.0;
 
-        for (int t = 0; t < nit; ++t) {
+        int t = 0;
+        while (t < nit) {
+        // (re)start the recurrence exactly at column 2t; a walk with sleeping components restarts every few columns
+        // (the decision is taken for the whole warp, so that every loop around the shuffles stays warp-uniform)
+        const bool asleep = march_start(recs, s_exptab, (double)h, (double)(w0 + 2 * t), fp, rr);
+        const bool careful = __ballot_sync(0xffffffffu, asleep && len > 0) != 0u;
+        const int tend = careful ? min(nit, t + MARCH_CAREFUL_COLS / 2) : nit;
+        for (; t < tend; ++t) {
             const int iown = 2 * t + kk;
             const bool own = iown < len;
             // this lane's pixel (column 2t + kk): its inputs are requested now and read after the mixture sums, whose
@@ -642,6 +670,7 @@ __global__ void __launch_bounds__(MARCH_THREADS, CELESTE_MARCH_MINB)
             pix += 2 * H2;
             ipix += 2 * mi.imgH;
             coff += 2 * mi.n1;
+        }
         }
         ta[TA_VAL * MARCH_THREADS] += val;
         ta[TA_CNT_ACTIVE * MARCH_THREADS] += cnt_active;

@@ -166,6 +166,33 @@ def case_wide_patch():
     return images, patches, _all_tasks(vp)
 
 
+def case_sharp_psf():
+    """A PSF with a sub-pixel core (variance 0.2 px^2) on patches of radius 30: at the patch edge the Gaussian
+    components of the core are below the smallest double (exp(-q/2), q > 1490).  Direct evaluation does not care; a
+    recurrence that starts a row there must not carry the underflowed value towards the centre."""
+    psf = [PsfComponent(0.7, np.array([0.05, -0.1]), np.array([[0.2, 0.02], [0.02, 0.25]])),
+           PsfComponent(0.3, np.array([0.0, 0.0]), np.array([[3.0, 0.0], [0.0, 3.2]]))]
+    from celeste_jl_b200.model import render_psf
+    images = synthetic.blank_images(72, 70, bands=(2, 3))
+    for im in images:
+        im.psf = psf
+        im.psf_stamp = render_psf(im.psf, (51, 51))
+        im._coefs_cache = None
+    catalog = [synthetic.sample_ce([36.4, 34.7], True), synthetic.sample_ce([41.2, 30.1], False)]
+    synthetic.gen_images(images, catalog, seed=21, device="cpu")
+    patches = get_sky_patches(images, catalog, radius_override_pix=30.0)
+    vp = [cj.catalog_init_source(ce) for ce in catalog]
+    synthetic.perturb_params(vp)
+    for v in vp:
+        v[ids_radius()] = 0.05          # a nearly unresolved galaxy: its narrowest components are the PSF core itself
+    return images, patches, _all_tasks(vp)
+
+
+def ids_radius():
+    from celeste_jl_b200.model import ids
+    return ids.gal_radius_px - 1 if isinstance(ids.gal_radius_px, int) else ids.gal_radius_px[0] - 1
+
+
 def case_seven_images():
     """N = 7 images (two exposures of bands 3 and 4 on top of the five SDSS bands, as a multi-epoch box has): the
     march kernel splits a source into two image groups whose partial sums meet in the epilogue, and two images share
@@ -195,6 +222,7 @@ CASES = {
     "small_field": case_small_field,
     "wide_patch": case_wide_patch,
     "seven_images": case_seven_images,
+    "sharp_psf": case_sharp_psf,
 }
 
 _cache = {}

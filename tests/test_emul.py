@@ -9,7 +9,7 @@ import cases
 import emul_lib
 import oracle_lib
 
-FAST = ["star_1band", "two_body", "masked", "clipped_and_empty", "psf_k1", "psf_k3", "crowded"]
+FAST = ["star_1band", "two_body", "masked", "clipped_and_empty", "psf_k1", "psf_k3", "crowded", "sharp_psf"]
 
 
 @pytest.mark.parametrize("name", FAST)
@@ -30,7 +30,7 @@ def test_emulated_kernels_match_oracle_hessian(name):
 
 
 @pytest.mark.parametrize("name", ["two_body", "masked", "clipped_and_empty", "crowded", "config2_rotated_wcs", "small_field",
-                                  "wide_patch", "seven_images"])
+                                  "wide_patch", "seven_images", "sharp_psf"])
 def test_march_kernel_matches_oracle_and_task_kernel(name):
     """march_kernels.cuh (row walks with the exp recurrence; the product's value / gradient path for Sa = 1, K = 2)
     against the oracle at the 1e-8 parity statement, and against task_kernel (direct evaluation of every pixel) at

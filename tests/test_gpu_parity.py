@@ -198,7 +198,7 @@ def test_deterministic_and_mode_consistent(cj):
 
 
 @pytest.mark.parametrize("name", ["two_body", "masked", "clipped_and_empty", "crowded", "config2", "small_field", "wide_patch",
-                                  "seven_images"])
+                                  "seven_images", "sharp_psf"])
 def test_march_kernel_matches_task_kernel(cj, name, monkeypatch):
     """The two value / gradient kernels of the library -- march_kernel (row walks, exp recurrence; the default for
     Sa = 1, K = 2) and task_kernel (direct evaluation; CELESTE_GRAD_KERNEL=task) -- agree to 1e-11, have identical
