@@ -159,7 +159,7 @@ __device__ __forceinline__ bool march_start(const double* recs_k, const double* 
         const double q = d1 * p1 + d2 * p2;
         // exp(-(q(w+1) - q(w)) / 2); the argument may be positive (walking towards the centre)
         const double ra = -(p2 + 0.5 * l22);
-        const bool sleep = !(q <= MARCH_Q_SLEEP) || !(ra <= 700.0);      // (NaN parameters sleep too: the value term stays NaN through E)
+        const bool sleep = q > MARCH_Q_SLEEP || ra > 700.0;      // (false for NaN: non-finite parameters keep propagating)
         asleep |= sleep;
         const double f = z * exp_scaled_tab(q, -0.5, etab);
         const double r = exp_scaled_tab(fmin(ra, 700.0), 1.0, etab);

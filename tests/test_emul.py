@@ -64,6 +64,21 @@ def test_march_kernel_matches_oracle_and_task_kernel(name):
             assert np.all(np.abs(a - b) <= 1e-11 * np.maximum(np.abs(b), sc * 1e-3)), np.abs(a - b).max()
 
 
+@pytest.mark.parametrize("idx", [0, 2, 3, 5, 10, 26])
+def test_march_kernel_propagates_nonfinite_parameters(idx):
+    """A NaN anywhere in the active source's parameters must come out as a flagged, non-finite result (the reference
+    throws in assert_all_finite, elbo_args.jl:145-149) -- in particular it must not be swallowed by the rule that puts
+    underflowed components to sleep."""
+    images, patches, tasks = cases.get("two_body")
+    bad = [(r, a, v.copy()) for r, a, v in tasks]
+    bad[0][2][idx, 0] = np.nan
+    for mode in (0, 1):
+        ref = oracle_lib.OracleField(images, patches).elbo_batch(bad, mode=mode)
+        got = emul_lib.EmulField(images, patches).elbo_batch(bad, mode=mode)
+        assert ref["flags"].tolist() == [1, 0] and got["flags"].tolist() == [1, 0]
+        assert not np.isfinite(got["v"][0]) and np.isfinite(got["v"][1])
+
+
 def test_chunking_does_not_change_counters_or_parity():
     images, patches, tasks = cases.get("two_body")
     ref = oracle_lib.OracleField(images, patches).elbo_batch(tasks, mode=2)
