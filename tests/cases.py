@@ -207,6 +207,33 @@ def case_seven_images():
     return images, patches, _all_tasks(vp)
 
 
+def random_extreme_scene(seed):
+    """A small random scene whose sources sit at the corners of the parameter box (ElboMaximize.jl:63-93) and well off
+    their patch centres: radius 0.02 .. 60 px, axis ratio down to 0.02, gal_frac_dev and is_star at 0 / 1, patches of
+    radius 4 .. 28 px, 1-2 bands, 1-3 sources that are each other's neighbours.  Not in CASES (stress tests draw it)."""
+    from celeste_jl_b200.model import ids
+    rng = np.random.default_rng(seed)
+    H, W = int(rng.integers(30, 60)), int(rng.integers(30, 60))
+    bands = tuple(sorted(rng.choice([1, 2, 3, 4, 5], size=int(rng.integers(1, 3)), replace=False).tolist()))
+    images = synthetic.blank_images(H, W, bands=bands)
+    S = int(rng.integers(1, 4))
+    catalog = [synthetic.sample_ce([rng.uniform(3, H - 3), rng.uniform(3, W - 3)], bool(rng.integers(0, 2))) for _ in range(S)]
+    synthetic.gen_images(images, catalog, seed=seed, device="cpu")
+    patches = get_sky_patches(images, catalog, radius_override_pix=float(rng.uniform(4, 28)))
+    vp = [cj.catalog_init_source(ce) for ce in catalog]
+    synthetic.perturb_params(vp)
+    for v in vp:
+        v[ids.gal_radius_px] = float(np.exp(rng.uniform(np.log(0.02), np.log(60.0))))
+        v[ids.gal_axis_ratio] = float(rng.choice([0.02, 0.3, 0.99, rng.uniform(0.05, 1.0)]))
+        v[ids.gal_angle] = float(rng.uniform(-4, 8))
+        v[ids.gal_frac_dev] = float(rng.choice([0.0, 1.0, 0.01, 0.99, rng.uniform()]))
+        a = float(rng.choice([0.0, 1.0, 1e-4, 0.9999, rng.uniform()]))
+        v[ids.is_star[0]], v[ids.is_star[1]] = a, 1 - a
+        v[ids.pos[0]] += rng.normal(0, 6)
+        v[ids.pos[1]] += rng.normal(0, 6)
+    return images, patches, _all_tasks(vp)
+
+
 CASES = {
     "star_1band": case_star_1band,
     "star_5band": case_star_5band,

@@ -79,6 +79,17 @@ def test_march_kernel_propagates_nonfinite_parameters(idx):
         assert not np.isfinite(got["v"][0]) and np.isfinite(got["v"][1])
 
 
+@pytest.mark.parametrize("seed", [0, 3, 7, 12, 19, 23, 31, 38])
+def test_march_kernel_at_the_corners_of_the_parameter_box(seed):
+    """Random small scenes with extreme source parameters (cases.random_extreme_scene): the recurrence of march_kernel
+    against the oracle at the parity statement, value and gradient."""
+    images, patches, tasks = cases.random_extreme_scene(seed)
+    for mode in (0, 1):
+        ref = oracle_lib.OracleField(images, patches).elbo_batch(tasks, mode=mode, n_threads=4)
+        got = emul_lib.EmulField(images, patches).elbo_batch(tasks, mode=mode)
+        cases.assert_parity(ref, got, mode, f"seed {seed}")
+
+
 def test_chunking_does_not_change_counters_or_parity():
     images, patches, tasks = cases.get("two_body")
     ref = oracle_lib.OracleField(images, patches).elbo_batch(tasks, mode=2)
