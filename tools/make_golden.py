@@ -1,6 +1,6 @@
 """Generate tests/golden/*.npz: flat ABI-level inputs + oracle outputs for the small parity cases.
 
-    python tools/make_golden.py
+    python tools/make_golden.py [case ...]
 
 The generating code path is: tests/cases.py (synthetic inputs, seeded) -> flatten -> oracle
 (oracle/libceleste_oracle.so) in modes 0/1/2.  Commit the outputs; tests/test_golden.py checks the
@@ -18,11 +18,12 @@ import golden_io  # noqa: E402
 import oracle_lib  # noqa: E402
 from celeste_jl_b200.flatten import csr_tasks  # noqa: E402
 
-GOLDEN = ["star_1band", "two_body", "config2", "config2_rotated_wcs", "masked", "clipped_and_empty", "psf_k3"]
+GOLDEN = ["star_1band", "two_body", "config2", "config2_rotated_wcs", "masked", "clipped_and_empty", "psf_k3",
+          "seven_images", "sharp_psf"]
 
 if __name__ == "__main__":
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
-    for name in GOLDEN:
+    for name in (sys.argv[1:] or GOLDEN):          # python tools/make_golden.py [case ...]
         images, patches, tasks = cases.get(name)
         of = oracle_lib.OracleField(images, patches)
         csr = csr_tasks(tasks)
