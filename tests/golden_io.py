@@ -98,3 +98,97 @@ def load(path):
         if f"out{mode}_v" in z:
             outs[mode] = {k: z[f"out{mode}_{k}"] for k in ("v", "d", "h", "counters", "flags")}
     return fi, fp, csr, outs
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Reference-side dumps (tools/julia/dump_golden.jl): one self-describing little-endian file per case.
+# Records: [int32 name_len][name][int32 dtype 0=f64 1=f32 2=i64 3=u8][int32 ndim][int64 dims...][column-major data]
+_CELGOLD_DT = {0: np.dtype("<f8"), 1: np.dtype("<f4"), 2: np.dtype("<i8"), 3: np.dtype("u1")}
+
+
+def read_celgold(path):
+    """-> {name: ndarray (Fortran order, as Julia wrote it)}."""
+    import struct
+    b = open(path, "rb").read()
+    pos, out = 0, {}
+    while pos < len(b):
+        (ln,) = struct.unpack_from("<i", b, pos)
+        pos += 4
+        name = b[pos:pos + ln].decode()
+        pos += ln
+        dt, nd = struct.unpack_from("<ii", b, pos)
+        pos += 8
+        dims = struct.unpack_from("<" + "q" * nd, b, pos)
+        pos += 8 * nd
+        cnt = int(np.prod(dims)) if nd else 1
+        a = np.frombuffer(b, dtype=_CELGOLD_DT[dt], count=cnt, offset=pos).reshape(dims, order="F")
+        pos += cnt * _CELGOLD_DT[dt].itemsize
+        out[name] = a
+    return out
+
+
+def write_celgold(path, records):
+    """The Python twin of dump_golden.jl's `rec` (used by the tests to exercise the reader without Julia)."""
+    import struct
+    code = {np.dtype("float64"): 0, np.dtype("float32"): 1, np.dtype("int64"): 2, np.dtype("uint8"): 3}
+    with open(path, "wb") as f:
+        for name, a in records:
+            a = np.asarray(a)
+            if a.ndim == 0:
+                a = a.reshape(1)
+            f.write(struct.pack("<i", len(name)) + name.encode())
+            f.write(struct.pack("<ii", code[a.dtype], a.ndim))
+            f.write(struct.pack("<" + "q" * a.ndim, *a.shape))
+            f.write(np.asfortranarray(a).tobytes(order="F"))
+
+
+def load_julia_dump(path):
+    """A dump_golden.jl file -> (flat_images, flat_patches, csr, {mode: reference outputs}, extras).
+    Images get log_iota = log(Float32 iota) in Float32 like elbo_objective.jl:292."""
+    z = read_celgold(path)
+    N, S = int(z["N"][0]), int(z["S"][0])
+    fi, fp = _Flat(), _Flat()
+    fi.N, fi.arr, fi._keep = N, (celeste_image * max(N, 1))(), []
+    for n in range(N):
+        H, W, band = (int(x) for x in z[f"img{n + 1}_meta"])
+        px = np.asfortranarray(z[f"img{n + 1}_pixels"], dtype=np.float32)
+        sky = np.asfortranarray(z[f"img{n + 1}_sky"], dtype=np.float32)
+        iota = np.ascontiguousarray(z[f"img{n + 1}_iota"], dtype=np.float32)
+        li = np.log(iota).astype(np.float32).astype(np.float64)
+        fi._keep += [px, sky, iota, li]
+        a = fi.arr[n]
+        a.H, a.W, a.band = H, W, band
+        a.pixels, a.sky, a.nelec_per_nmgy, a.log_iota = px.ctypes.data, sky.ctypes.data, iota.ctypes.data, li.ctypes.data
+    fp.S_tot, fp.N, fp.arr, fp._keep = S, N, (celeste_patch * max(S * N, 1))(), []
+    for n in range(N):
+        for s in range(S):
+            key = f"p{s + 1}_{n + 1}"
+            q = fp.arr[s + n * S]
+            bm = np.asfortranarray(z[key + "_bitmap"], dtype=np.uint8)
+            psf = np.asfortranarray(z[key + "_psf"], dtype=np.float64)
+            co = np.asfortranarray(z[key + "_itp_coefs"], dtype=np.float64)
+            fp._keep += [bm, psf, co]
+            q.bitmap_offset[0], q.bitmap_offset[1] = (int(x) for x in z[key + "_offset"])
+            q.H2, q.W2 = bm.shape if bm.ndim == 2 else (0, 0)
+            q.K = psf.shape[1]
+            q.active_pixel_bitmap = bm.ctypes.data if bm.size else None
+            q.psf = psf.ctypes.data
+            q.itp_coefs = co.ctypes.data
+            q.itp_dims[0], q.itp_dims[1] = co.shape
+            J = z[key + "_wcs_jacobian"]
+            q.wcs_jacobian[0], q.wcs_jacobian[1], q.wcs_jacobian[2], q.wcs_jacobian[3] = J[0, 0], J[1, 0], J[0, 1], J[1, 1]
+            q.world_center[0], q.world_center[1] = z[key + "_world_center"]
+            q.pixel_center[0], q.pixel_center[1] = z[key + "_pixel_center"]
+    act = np.asarray(z["active_sources"], dtype=np.int32)
+    csr = (np.array([0, S], dtype=np.int32), np.arange(1, S + 1, dtype=np.int32), np.array([0, len(act)], dtype=np.int32),
+           act, np.asfortranarray(z["vp"], dtype=np.float64).ravel(order="F"))
+    outs = {}
+    for mode in (0, 1, 2):
+        if f"out{mode}_v" in z:
+            outs[mode] = {"v": np.asarray(z[f"out{mode}_v"], dtype=np.float64).reshape(1),
+                          "d": z[f"out{mode}_d"].ravel(order="F") if mode >= 1 else np.zeros(0),
+                          "h": z[f"out{mode}_h"].ravel(order="F") if mode >= 2 else np.zeros(0),
+                          "counters": np.asarray(z[f"out{mode}_counters"], dtype=np.int64).reshape(1, 2),
+                          "flags": np.zeros(1, dtype=np.int32)}
+    extras = {k: z[k] for k in ("elbo_kl_v", "elbo_kl_d", "elbo_kl_h") if k in z}
+    return fi, fp, csr, outs, extras

@@ -7,7 +7,7 @@ import torch
 import celeste_jl_b200 as cj
 from celeste_jl_b200 import elbo_maximize as em
 import cases
-for name in ("two_body", "clipped_and_empty", "psf_k3", "crowded", "masked", "wide_patch", "seven_images"):
+for name in ("two_body", "clipped_and_empty", "psf_k3", "crowded", "masked", "wide_patch", "seven_images", "sharp_psf"):
     images, patches, tasks = cases.get(name)
     f = cj.DeviceField(images, patches)
     for mode in (0, 1, 2):
@@ -33,3 +33,11 @@ rows, act = ds.tasks()
 plan = cj.Plan(cj.DeviceField(ds.images, ds.patches), rows, act)
 res = em.BatchMaximizer(plan, ds.vp_flat(rows), include_kl=True, max_iters=3).run()
 print("newton", res.value[:3], res.iterations)
+# one full-size 1000-source plan (configs[2]); the dataset is rendered on the CPU so that only this library's kernels are instrumented
+ds = synthetic.FieldDataset(1000, H=2048, W=1489, seed=42, device="cpu")
+rows, act = ds.tasks()
+plan = cj.Plan(cj.DeviceField(ds.images, ds.patches), rows, act)
+vpf = ds.vp_flat(rows)
+for mode in (0, 1, 2):
+    out = plan.run_host(vpf, mode)
+    print("field1000 mode", mode, float(out["v"].sum()), int(out["counters"].sum()), int(out["flags"].sum()))
