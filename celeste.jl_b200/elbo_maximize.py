@@ -119,11 +119,14 @@ class BatchMaximizer:
 
     def __init__(self, plan, vp_flat: np.ndarray, include_kl: bool = True, device: Optional[str] = None,
                  loc_width: float = 1e-4, max_iters: int = MAX_ITERS, runner=None, stepper=None,
-                 fused: Optional[bool] = None):
+                 fused: Optional[bool] = None, box=None):
         """`runner(self)` evaluates the plan's tasks at self.vp_all and fills self.v/d/h/flags; the default
         launches the CUDA plan on the current stream.  (Tests inject a CPU checker here.)
         `stepper(phase, n, buffers)` runs newton_step_kernel; the default is the library on the current stream
-        (tests inject the host-emulated kernel).  `fused` = use newton_step_kernel (default on CUDA)."""
+        (tests inject the host-emulated kernel).  `fused` = use newton_step_kernel (default on CUDA).
+        `box` = (lo, hi), n x 26 bounds built earlier by ct.box_bounds: a caller that optimises the same source
+        several times (joint inference) passes the box of the FIRST visit so that the position constraint does not
+        follow the source (one ElboConfig per target for all sweeps, ParallelRun.jl:99-101)."""
         self.plan = plan
         self.runner = runner
         self.stepper = stepper
@@ -145,7 +148,11 @@ class BatchMaximizer:
         self.cnt = torch.zeros(2 * n, dtype=torch.int64, device=self.dev)
         self.flags = torch.zeros(n, dtype=torch.int32, device=self.dev)
         vp0 = self.vp_all[self.aslot]
-        self.lo, self.hi = ct.box_bounds(vp0, loc_width)          # position box fixed at the start (ElboMaximize.jl:68-71)
+        if box is None:
+            self.lo, self.hi = ct.box_bounds(vp0, loc_width)      # position box fixed at the start (ElboMaximize.jl:68-71)
+        else:
+            self.lo = torch.as_tensor(box[0], dtype=dt, device=self.dev).reshape(self.n, ct.N_BOX).contiguous()
+            self.hi = torch.as_tensor(box[1], dtype=dt, device=self.dev).reshape(self.n, ct.N_BOX).contiguous()
         vp0 = ct.enforce(vp0, self.lo, self.hi)                   # enforce! :230
         self.x = ct.to_free(vp0, self.lo, self.hi)                # to_free! :231
         self.f_calls = 0

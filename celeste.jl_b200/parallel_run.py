@@ -191,23 +191,68 @@ def one_node_single_infer(catalog, patches, target_sources, neighbor_map, images
         vps += [dvi.catalog_init_source(catalog[n - 1]) for n in r[1:]]
     bm = BatchMaximizer(plan, np.concatenate(vps), include_kl=include_kl, max_iters=max_iters)
     res = bm.run()
-    out = [OptimizedSource(catalog[s].pos[0], catalog[s].pos[1], res.vp[k]) for k, s in enumerate(mine)]
+    out = [OptimizedSource(catalog[s].pos[0], catalog[s].pos[1], res.vp[k], bad_sky(catalog[s], images))
+           for k, s in enumerate(mine)]
     return out, res
 
 
+def assign_components(components: List[List[int]], cost_of: Callable[[int], float], n_ranks: int) -> List[List[List[int]]]:
+    """shard_batch keeping the component structure: [rank][component][source]."""
+    ccost = [sum(cost_of(s) for s in comp) for comp in components]
+    order = sorted(range(len(components)), key=lambda i: -ccost[i])
+    assign = load_balance([ccost[i] for i in order], n_ranks)
+    return [[components[order[i]] for i in idx] for idx in assign]
+
+
+def bad_sky(ce, images) -> bool:
+    """ParallelRun.bad_sky (:437-461): in the i band, the claimed sky (sky x iota at the source's pixel, in
+    electrons) is more than 5 photons below the median of the pixels in a 50-pixel box around the source."""
+    from .model import box_around_point, clamp_box
+    img = next((im for im in images if im.b == 4), None)
+    if img is None:
+        return False
+    pc = img.wcs.world_to_pix(ce.pos)
+    h = max(1, min(int(np.rint(pc[0])), img.H))
+    w = max(1, min(int(np.rint(pc[1])), img.W))
+    claimed_sky = float(np.asarray(img.sky)[h - 1, w - 1]) * float(img.nelec_per_nmgy[h - 1])
+    (h0, h1), (w0, w1) = clamp_box(box_around_point(img.wcs, ce.pos, 50.0), (img.H, img.W))
+    px = np.asarray(img.pixels)[h0 - 1:h1, w0 - 1:w1]
+    px = px[~np.isnan(px)]
+    if px.size == 0:
+        return False
+    return bool(claimed_sky + 5 < float(np.median(px)))
+
+
 def one_node_joint_infer(catalog, patches, target_sources, neighbor_map, images, field=None, include_kl=True,
-                         n_iters=3, batch_size=60, seed=42, max_iters=50):
+                         n_iters=3, batch_size=60, seed=42, max_iters=50, rank=0, world=1, group=None,
+                         make_maximizer=None):
     """ParallelRun.one_node_joint_infer (:135-196) + process_sources_dynamic! (:302-370): targets share their
     variational parameters (`ts_vp`, :99-113, 249-252), are visited in Cyclades batches of mutually
     non-conflicting connected components, `num_joint_vi_iters` (= 3, config.jl:20) sweeps.  The reference
     optimises the sources of one component one after another on a thread; here round r optimises the r-th
     source of EVERY component of the batch in one lock-step BatchMaximizer run (sources of different
-    components never share pixels, so this is the same serial-equivalent schedule).  Indices are 0-based."""
+    components never share pixels, so this is the same serial-equivalent schedule).
+
+    world > 1 (one process per GPU): the components of a batch are dealt to the ranks by cost (a component never
+    straddles ranks, so no two GPUs ever touch overlapping patches), every rank optimises its components, and the
+    updated parameters are exchanged once per batch -- the reference's thread barrier at the end of a batch
+    (:321-324) -- by `allgather_vp` (44 doubles per source).  Every rank returns the full result.
+
+    Each target keeps ONE constraint box for all sweeps: built from its initial parameters like the reference's
+    per-target ElboConfig in cfg_vec (:99-101, "configurations must persist so location constraints do not
+    shift"), not re-centred on the previous sweep's optimum.
+
+    `make_maximizer(todo, rows, act, vps, box)` -> object with .run() (tests inject a CPU checker); default: the
+    CUDA plan + BatchMaximizer.  Indices are 0-based."""
+    import torch
+    from . import constraint_transforms as ct
     from . import deterministic_vi as dvi
     from .elbo_maximize import BatchMaximizer
-    field = field or dvi.DeviceField(images, patches)
     tset = set(target_sources)
     ts_vp = {s: dvi.generic_init_source(catalog[s].pos) for s in target_sources}           # setup_vecs :99-113
+    init = torch.as_tensor(np.stack([ts_vp[s] for s in target_sources]), dtype=torch.float64)
+    lo_all, hi_all = ct.box_bounds(init)                                                    # one box per target, kept
+    box_of = {s: (lo_all[k].numpy().copy(), hi_all[k].numpy().copy()) for k, s in enumerate(target_sources)}
     frozen = {}
 
     def vp_of(s):
@@ -219,19 +264,40 @@ def one_node_joint_infer(catalog, patches, target_sources, neighbor_map, images,
     nmap = {s: [n for n in neighbor_map[s]] for s in target_sources}
     batches = partition_cyclades_dynamic(list(target_sources), {s: [n for n in nmap[s] if n in tset] for s in nmap},
                                          batch_size=batch_size, seed=seed)
+    cost_cache = {}
+
+    def cost_of(s):
+        if s not in cost_cache:
+            cost_cache[s] = estimate_time(patches[s, :])
+        return cost_cache[s]
     plans = {}
+    if make_maximizer is None:
+        field = field or dvi.DeviceField(images, patches)
+
+        def make_maximizer(todo, rows, act, vps, box):
+            if todo not in plans:
+                plans[todo] = dvi.Plan(field, rows, act)
+            return BatchMaximizer(plans[todo], vps, include_kl=include_kl, max_iters=max_iters, box=box)
     stats = []
     for _ in range(n_iters):
         for comps in batches:
-            for r in range(max(len(c) for c in comps)):
-                todo = tuple(c[r] for c in comps if len(c) > r)
-                if todo not in plans:
-                    rows, act = _task_rows(todo, neighbor_map)
-                    plans[todo] = (dvi.Plan(field, rows, act), rows)
-                plan, rows = plans[todo]
+            mine = assign_components(comps, cost_of, world)[rank] if world > 1 else comps
+            for r in range(max((len(c) for c in mine), default=0)):
+                todo = tuple(c[r] for c in mine if len(c) > r)
+                rows, act = _task_rows(todo, neighbor_map)
                 vps = np.concatenate([vp_of(n - 1) for rr in rows for n in rr])
-                res = BatchMaximizer(plan, vps, include_kl=include_kl, max_iters=max_iters).run()
+                box = (np.stack([box_of[s][0] for s in todo]), np.stack([box_of[s][1] for s in todo]))
+                res = make_maximizer(todo, rows, act, vps, box).run()
                 for k, s in enumerate(todo):
                     ts_vp[s][:] = res.vp[k]
                 stats.append(res)
-    return [OptimizedSource(catalog[s].pos[0], catalog[s].pos[1], ts_vp[s]) for s in target_sources], stats
+            if world > 1:
+                # batch barrier (:321-324): everyone learns the parameters the other ranks just optimised
+                ids_mine = [s for c in mine for s in c]
+                local = np.stack([ts_vp[s] for s in ids_mine], axis=1) if ids_mine else np.zeros((44, 0))
+                table = allgather_vp(ids_mine, local, len(catalog), group=group)
+                for c in comps:
+                    for s in c:
+                        ts_vp[s][:] = table[:, s]
+    return [OptimizedSource(catalog[s].pos[0], catalog[s].pos[1], ts_vp[s], bad_sky(catalog[s], images))
+            for s in target_sources], stats

@@ -110,3 +110,71 @@ def test_two_rank_gloo_shard_and_reduce(tmp_path):
     res = json.loads(line)
     assert res["ok_vp"] and 0 < res["n_mine"] < 60
     assert abs(res["total"] - res["full"]) <= 1e-12 * abs(res["full"])
+
+
+def test_bad_sky_flags_underestimated_background():
+    """ParallelRun.jl:437-461: claimed sky (electrons) + 5 < median of the 50-pixel box in the i band."""
+    ds = synthetic.FieldDataset(3, H=140, W=120, seed=2, device="cpu")
+    assert not any(pr.bad_sky(ce, ds.images) for ce in ds.catalog)
+    img = next(im for im in ds.images if im.b == 4)
+    img.pixels = img.pixels + np.float32(40.0)          # 40 unexplained electrons per pixel
+    assert all(pr.bad_sky(ce, ds.images) for ce in ds.catalog)
+    assert not pr.bad_sky(ds.catalog[0], [im for im in ds.images if im.b != 4])
+
+
+JOINT_WORKER = r'''
+import os, sys, json
+import numpy as np
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+import torch.distributed as dist
+from celeste_jl_b200 import parallel_run as pr, synthetic, elbo_maximize as em
+from test_maximize import OracleRunner, PlanLike
+world = int(os.environ.get("WORLD_SIZE", "1"))
+if world > 1:
+    dist.init_process_group("gloo")
+rank = dist.get_rank() if world > 1 else 0
+ds = synthetic.FieldDataset(14, H=70, W=64, seed=31, device="cpu")
+nmap = {s: ds.neighbors[s] for s in range(len(ds.catalog))}
+boxes = []
+def make(todo, rows, act, vps, box):
+    pl = PlanLike(rows, act)
+    boxes.append((todo, box[0][:, :2].copy()))
+    return em.BatchMaximizer(pl, vps, include_kl=True, device="cpu", max_iters=4, box=box,
+                             runner=OracleRunner(ds.images, ds.patches, pl))
+res, stats = pr.one_node_joint_infer(ds.catalog, ds.patches, list(range(14)), nmap, ds.images, n_iters=2, batch_size=7,
+                                     max_iters=4, rank=rank, world=world, make_maximizer=make)
+first = {}
+same_box = True
+for todo, lo in boxes:
+    for k, s in enumerate(todo):
+        if s in first:
+            same_box &= bool(np.array_equal(first[s], lo[k]))
+        else:
+            first[s] = lo[k]
+if rank == 0:
+    print(json.dumps({"vp": np.stack([r.vs for r in res]).tolist(), "same_box": same_box, "visited": len(first),
+                      "runs": len(stats)}))
+if world > 1:
+    dist.destroy_process_group()
+'''
+
+
+def test_joint_infer_two_ranks_equals_one_rank_and_keeps_its_boxes(tmp_path):
+    """one_node_joint_infer with rank / world (components of a Cyclades batch dealt to ranks, vp all-gather at the
+    batch barrier, ParallelRun.jl:321-324) gives the same catalog as the single-process run; and every target is
+    optimised inside the SAME position box on every sweep (ParallelRun.jl:99-101).  Evaluator: the oracle."""
+    import json
+    script = tmp_path / "joint_worker.py"
+    script.write_text(JOINT_WORKER)
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    one = subprocess.run([sys.executable, str(script), ROOT], capture_output=True, text=True, env=env, timeout=900)
+    assert one.returncode == 0, one.stderr[-2000:]
+    two = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29519", str(script), ROOT],
+                         capture_output=True, text=True, env=env, timeout=900)
+    assert two.returncode == 0, two.stderr[-2000:]
+    a = json.loads([l for l in one.stdout.splitlines() if l.startswith("{")][-1])
+    b = json.loads([l for l in two.stdout.splitlines() if l.startswith("{")][-1])
+    assert a["same_box"] and b["same_box"] and a["visited"] == 14
+    assert b["runs"] <= a["runs"]
+    assert np.allclose(np.array(a["vp"]), np.array(b["vp"]), rtol=1e-9, atol=1e-12)
