@@ -22,6 +22,7 @@
 #include "../../include/celeste_cuda.h"
 #include "celeste_kernels.cuh"
 #include "march_kernels.cuh"
+#include "unit_kernels.cuh"
 #include "maximize_kernels.cuh"
 #include "patch_kernels.cuh"
 
@@ -141,6 +142,9 @@ int configure_kernels() {
 #undef CEL_TCFG
     CUDA_TRY(cudaFuncSetAttribute(march_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)march_smem_bytes()));
     CUDA_TRY(cudaFuncSetAttribute(march_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)march_smem_bytes()));
+    CUDA_TRY(cudaFuncSetAttribute(unit_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)unit_smem_bytes<0>()));
+    CUDA_TRY(cudaFuncSetAttribute(unit_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)unit_smem_bytes<1>()));
+    CUDA_TRY(cudaFuncSetAttribute(unit_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)unit_smem_bytes<2>()));
     if (const char* env = std::getenv("CELESTE_MARCH_CARVEOUT")) {     // kernel-tuning knob: shared-memory share of L1, percent
         const int pct = std::atoi(env);
         if (pct >= 0 && pct <= 100) {
@@ -212,6 +216,15 @@ struct celeste_plan {
     DevBuf<double> bg;
     int n_marchblocks = 0;
     bool use_march = false;
+    // unit_kernel (Hessian mode of the production shape; value / gradient with CELESTE_GRAD_KERNEL=unit): one warp per
+    // (sub, image) unit pulled from a device-side queue
+    DevBuf<UnitHdr> unitmap;
+    DevBuf<int> unit_chunk_ptr;      // identity: one partial vector per (sub, image)
+    DevBuf<int> unit_queue;
+    DevBuf<double> unit_scratch;     // per resident warp: E_bg | V_bg | L5 planes of the largest active patch
+    int n_units = 0, unit_grid = 0;
+    long long unit_maxpix = 1;
+    bool use_unit_hess = false, use_unit_grad = false;
     DevBuf<PairHdr> pairmap;
     DevBuf<double> slotimg, slotbr, partials, pair_partials;
     int n_subs = 0, n_pairs = 0;
@@ -816,6 +829,45 @@ int celeste_plan_create_multi(int32_t n_fields, celeste_field* const* fields, ce
         CUDA_TRY(pl->bg_ptr.upload(bg_ptr));
         CUDA_TRY(pl->bg.alloc((size_t)bg_total));
     }
+    if (pl->use_march) {
+        // same shape condition as march_kernel; CELESTE_HESS_KERNEL=pixel keeps pixel_kernel<2> (A/B knob)
+        const char* henv = std::getenv("CELESTE_HESS_KERNEL");
+        pl->use_unit_hess = !(henv && std::strcmp(henv, "pixel") == 0);
+    }
+    {
+        const char* genv = std::getenv("CELESTE_GRAD_KERNEL");
+        pl->use_unit_grad = genv && std::strcmp(genv, "unit") == 0 && pl->uniform_K == 2 && n_subs == n_tasks;
+    }
+    if (pl->use_unit_hess || pl->use_unit_grad) {
+        std::vector<UnitHdr> um;
+        build_unit_list(n_subs, pl->N, sub_task.data(), sub_slot.data(), task_ptr, tfield.data(),
+                        [&](int slot, int n, int& oh, int& ow, int& H2, int& W2) {
+                            const celeste_field* f = fields[sfield[slot]];
+                            const PatchDev& pa = f->h_patches[(size_t)src_row[slot] + (size_t)n * f->S_tot];
+                            oh = pa.off_h;
+                            ow = pa.off_w;
+                            H2 = pa.H2;
+                            W2 = pa.W2;
+                        },
+                        um, pl->unit_maxpix);
+        pl->n_units = (int)um.size();
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
+        int grid = sms * CELESTE_UNIT_MINB;
+        if (const char* env = std::getenv("CELESTE_UNIT_GRID"))
+            if (std::atoi(env) > 0) grid = std::atoi(env);
+        grid = std::min(grid, std::max(1, (pl->n_units + UNIT_WARPS - 1) / UNIT_WARPS));
+        // scratch: 3 planes of the largest active patch per resident warp; very large patches shrink the grid
+        const long long per_block = 3LL * pl->unit_maxpix * UNIT_WARPS * (long long)sizeof(double);
+        grid = (int)std::max(1LL, std::min<long long>(grid, (4LL << 30) / std::max(1LL, per_block)));
+        pl->unit_grid = grid;
+        std::vector<int> ident((size_t)n_subs * pl->N + 1);
+        for (size_t i = 0; i < ident.size(); ++i) ident[i] = (int)i;
+        CUDA_TRY(pl->unitmap.upload(um));
+        CUDA_TRY(pl->unit_chunk_ptr.upload(ident));
+        CUDA_TRY(pl->unit_queue.alloc(1));
+        CUDA_TRY(pl->unit_scratch.alloc((size_t)grid * UNIT_WARPS * 3 * (size_t)pl->unit_maxpix));
+    }
     std::vector<int> task_chunk_ptr((size_t)n_subs * pl->N + 1);
     for (size_t i = 0; i < task_chunk_ptr.size(); ++i) task_chunk_ptr[i] = (int)(i * TASK_WARPS);
     CUDA_TRY(pl->taskmap.upload(taskmap));
@@ -838,7 +890,7 @@ int celeste_plan_create_multi(int32_t n_fields, celeste_field* const* fields, ce
     CUDA_TRY(pl->slotimg.alloc((size_t)n_slots * pl->N * SLOTIMG_STRIDE));
     CUDA_TRY(pl->slotbr.alloc((size_t)n_slots * SLOTBR_STRIDE));
     CUDA_TRY(pl->partials.alloc(std::max({(size_t)pl->n_blocks * NACC_MODE2, (size_t)n_subs * pl->N * TASK_WARPS * NACC_MODE1,
-                                           (size_t)pl->n_marchblocks * NT_ACC})));
+                                           (size_t)pl->n_marchblocks * NT_ACC, (size_t)pl->n_units * NACC_MODE2})));
     *out = pl.release();
     return CELESTE_OK;
 }
@@ -884,13 +936,16 @@ int celeste_plan_kernel_times(celeste_plan* p, float ms[3]) {
 
 int celeste_plan_launches(const celeste_plan* p, int32_t mode) {
     if (!p || p->n_tasks == 0) return 0;
+    if ((mode <= 1 && p->use_unit_grad) || (mode == 2 && p->use_unit_hess)) return 3;   // slotbr, unit, epilogue
     if (mode <= 1 && p->use_march) return 2;                                       // march, epilogue
     return (p->n_blocks > 0 ? 3 : 2) + ((mode == 2 && p->n_pairs > 0) ? 1 : 0);   // setup, pixel, [pair,] epilogue
 }
 
 int celeste_plan_kernel_name(const celeste_plan* p, int32_t mode, char* buf) {
     if (!p || !buf || mode < 0 || mode > 2) return CELESTE_ERR_BAD_ARG;
-    std::snprintf(buf, 32, "%s", mode == 2 ? "pixel_kernel" : (p->use_march ? "march_kernel" : "task_kernel"));
+    const char* nm = mode == 2 ? (p->use_unit_hess ? "unit_kernel" : "pixel_kernel")
+                               : (p->use_unit_grad ? "unit_kernel" : (p->use_march ? "march_kernel" : "task_kernel"));
+    std::snprintf(buf, 32, "%s", nm);
     return CELESTE_OK;
 }
 
@@ -933,6 +988,22 @@ static int launch_mode(celeste_plan* p, const double* vp_dev, double* v, double*
     const long total = (long)p->n_slots * p->N * MAX_K;
     const int sblocks = (int)std::max<long>(1, std::min<long>((total + 127) / 128, 148L * 16));
     if (p->timing) CUDA_TRY(cudaEventRecord(p->ev[0], st));
+    if ((MODE <= 1 && p->use_unit_grad) || (MODE == 2 && p->use_unit_hess)) {
+        // one warp per (sub, image) unit from a device-side queue (unit_kernels.cuh); the epilogue is the general one
+        PlanDev pu = pd;
+        pu.chunk_ptr = p->unit_chunk_ptr.p;
+        CUDA_TRY(cudaMemsetAsync(p->unit_queue.p, 0, sizeof(int), st));
+        if (MODE >= 1) slotbr_kernel<<<(p->n_subs + 127) / 128, 128, 0, st>>>(pu, vp_dev);
+        if (p->timing) CUDA_TRY(cudaEventRecord(p->ev[1], st));
+        if (p->n_units > 0)
+            unit_kernel<MODE><<<p->unit_grid, UNIT_THREADS, unit_smem_bytes<MODE>(), st>>>(
+                pu, p->unitmap.p, p->n_units, p->unit_queue.p, p->unit_scratch.p, 3 * p->unit_maxpix, p->unit_maxpix, vp_dev);
+        if (p->timing) CUDA_TRY(cudaEventRecord(p->ev[2], st));
+        epilogue_kernel<MODE><<<p->n_tasks, EPI_THREADS, 0, st>>>(pu, vp_dev, v, d, h, counters, flags);
+        if (p->timing) CUDA_TRY(cudaEventRecord(p->ev[3], st));
+        CUDA_TRY(cudaGetLastError());
+        return CELESTE_OK;
+    }
     if constexpr (MODE <= 1) {
         if (p->use_march) {
             // value / gradient, production shape: row walks with the exp recurrence (march_kernels.cuh).  The blocks

@@ -176,6 +176,27 @@ __global__ void setup_kernel(PlanDev plan, const double* __restrict__ vp) {
     }
 }
 
+// Brightness moments of the ACTIVE sources only (what epilogue_kernel reads from slotbr): the kernels that build their
+// own mixtures (unit_kernel) need nothing else from setup_kernel.  One thread per sub.
+__global__ void slotbr_kernel(PlanDev plan, const double* __restrict__ vp) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= plan.n_subs) return;
+    const int slot = plan.sub_slot[u];
+    const double* vs = vp + (size_t)NPARAM * slot;
+    double El[2][5], Ell[2][5];
+    brightness_values(vs, El, Ell);
+    double* br = plan.slotbr + (size_t)slot * SLOTBR_STRIDE;
+    for (int i = 0; i < 2; ++i)
+        for (int b = 0; b < 5; ++b) {
+            br[i * 5 + b] = El[i][b];
+            br[10 + i * 5 + b] = Ell[i][b];
+        }
+    br[20] = vs[26];
+    br[21] = vs[27];
+    br[22] = vs[2];
+    br[23] = 0.0;
+}
+
 // ------------------------------------------------------------------------------------------------
 #ifndef CELESTE_PIX_THREADS
 #define CELESTE_PIX_THREADS 128

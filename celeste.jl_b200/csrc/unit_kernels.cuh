@@ -1,0 +1,794 @@
+// unit_kernels.cuh -- the ELBO hot loop (add_pixel_term!, elbo_objective.jl:330-392) with ONE WARP per
+// (active source, image) "unit", pulled from a device-side queue (heaviest first): the Hessian mode of the
+// production shape (Sa = 1, K = 2; ElboMaximize.jl:150-152 always asks for the Hessian).
+//
+// The reference -- and pixel_kernel<2> -- push every one of the 28 Gaussian components of every pixel through the
+// second-order chain rule (27 sums, ~96 FP64 per component-pixel).  Here the second-order work is split by what is
+// LINEAR in the components and what is not:
+//
+//   H_(c,y) = sum_pix [ Jz' Lzz Jz  +  L4 d2f0  ]        (needs only the 7 first-order mixture sums per pixel)
+//           + sum_pix   L5(pix) d2f1(pix)                 (linear in the components)
+//
+//  phase A  walks the rows of the patch exactly like march_kernel (a lane PAIR per walk, exp recurrence along the
+//           row, 17 FP64 per component-pixel for f1 and its 6 first derivatives), finishes the pixel term with its
+//           full second-order part EXCEPT L5 d2f1, and stores L5 = dL/df1 of every pixel in a per-warp scratch plane.
+//  phase B  re-walks the patch with one LANE PER COMPONENT: f_c(pix) by the same recurrence (2 multiplications),
+//           v = L5(pix) f_c(pix), and the five row moments sum v d2^b; at the end of a row they are folded into the
+//           15 moments D[a][b] = sum L5 f_c d1^a d2^b (a + b <= 4, d = x - mu_c).  ~12 FP64 per component-pixel.
+//  fold     every second-order mixture sum of gal_group<2> (bvn_xsig_h / bvn_sigsig_h, BivariateNormals.jl:293-316)
+//           is f_c times a polynomial of degree <= 4 in Lambda_c d: its L5-weighted pixel sum is a fixed linear
+//           combination of the component's 15 moments (hess_moments.inc, generated with sympy by
+//           tools/gen_hess_moments.py), evaluated ONCE per component and reduced over the warp by shuffles.
+//
+// About 1.2 k FP64 per pixel instead of 2.9 k, mathematically the same function (floating-point reassociation
+// plus the recurrence's rounding, ~1e-13 relative).
+//
+// Output: one NAcc<MODE>-vector of (c, y)-space sums per (sub, image) in plan.partials -- the layout
+// epilogue_kernel<MODE> consumes (chunk_ptr = identity), so the raw -> parameter chain rule is unchanged.
+// Warps never synchronise with each other; neighbours are walked first into the warp's scratch planes
+// (E_bg, V_bg) as in march_kernel.  MODE 0 / 1 instantiate the same walk without phase B.
+#ifndef CELESTE_UNIT_KERNELS_CUH
+#define CELESTE_UNIT_KERNELS_CUH
+
+#include "march_kernels.cuh"
+
+namespace celeste {
+
+#ifndef CELESTE_UNIT_MINB
+#define CELESTE_UNIT_MINB 3
+#endif
+constexpr int UNIT_WARPS = 4;
+constexpr int UNIT_THREADS = 32 * UNIT_WARPS;
+// per-(source, image) constants of the warp (shared memory): march's SI_* plus the second-derivative spline weights
+constexpr int SU_DDWX = 28, SU_DDWY = 32, SU_STRIDE = 36;
+// compact per-thread accumulator slots (shared memory, stride 32): G 6 | C1 4 | HH 21 | CC 7 live | CR 24.
+// ACC index (elbo_math.cuh) = slot + 3 for slot < 38, slot + 6 for the CR block; ACC_CC + 7..9 are identically
+// zero (L is linear in V, so d2L/dB dB = 0).
+constexpr int UA_G = 0, UA_C1 = 6, UA_HH = 10, UA_CC = 31, UA_CR = 38;
+template <int MODE> struct NUAcc { static constexpr int value = MODE == 0 ? 0 : (MODE == 1 ? 10 : 62); };
+CEL_HD constexpr int unit_acc_index(int slot) { return slot < UA_CR ? slot + 3 : slot + 6; }
+
+struct UnitHdr {        // one (sub, image) unit; built on the host (build_unit_list), heaviest first
+    int aslot, slot0, slot1;
+    int field, sub, task;
+    int n;              // image
+    int nseg;           // column segments per row of the active patch (phase A)
+    int hasbg;          // some other source of the task reaches this image
+    int pidx;           // partial vector of this unit (sub * N + n)
+    int pad0, pad1;
+};
+
+// geometry and pointers of the unit's image / active patch (per-warp shared memory)
+struct UnitImg {
+    const float* pixels;
+    const float* sky;
+    const double* pixconst;
+    const float* iota;
+    const uint8_t* bitmap;
+    const double* coefs;
+    double* scratch;        // E_bg | V_bg (2 x H2 W2) ... L5 at + 2 maxpix
+    int H2, W2, off_h, off_w, imgH, n1, n2, band0;
+};
+
+template <int MODE> struct UnitWarpDoubles {
+    static constexpr size_t value = (size_t)NUAcc<MODE>::value * 32 + (size_t)NC2 * MREC + SU_STRIDE + (sizeof(UnitImg) + 7) / 8;
+};
+template <int MODE>
+constexpr size_t unit_smem_bytes() { return UnitWarpDoubles<MODE>::value * UNIT_WARPS * sizeof(double); }
+
+// per-(source, image) constants: march_stage_srcimg plus the second-derivative spline weights (MODE 2)
+template <int MODE>
+__device__ inline void unit_stage_srcimg(const PatchDev& p, const double* vs, int band0, double* si) {
+    march_stage_srcimg<(MODE >= 1 ? 1 : 0)>(p, vs, band0, si);
+    if (MODE >= 2) {
+        const double ax = (double)(p.off_h + 1) - si[SI_M] + 26.0, ay = (double)(p.off_w + 1) - si[SI_M + 1] + 26.0;
+        double w[4], dw[4];
+        cubic_weights<2>(ax - floor(ax), w, dw, si + SU_DDWX);
+        cubic_weights<2>(ay - floor(ay), w, dw, si + SU_DDWY);
+    }
+}
+
+// The pixel term (add_elbo_log_term! + add_scaled_sfs!, elbo_objective.jl:274-327, :383-391) of one covered or
+// uncovered active pixel: the same expressions as pixel_accumulate<MODE> (elbo_math.cuh) without the
+// L5 * d2f1 part of the Hessian, which phase B supplies.  acc: this thread's slots (stride 32).  Returns L5.
+template <int MODE>
+__device__ __forceinline__ double unit_pixel_term(double* acc, const PixelConsts& pc, double Ebg, double Vbg, bool covered,
+                                                  const double* cb, double f0, const double* g0, const double* h0, double f1,
+                                                  const double* r, double& val, const double* logtab) {
+    const double A1 = cb[0], A2 = cb[1], B1 = cb[2], B2 = cb[3];
+    const double m = covered ? (A1 * f0 + A2 * f1) : 0.0;
+    const double E = Ebg + m;
+    const double V = covered ? (Vbg + B1 * f0 * f0 + B2 * f1 * f1 - m * m) : Vbg;
+    const double iE = 1.0 / E;
+    const double iE2 = iE * iE;
+    val += pc.x * (log_tab(E, logtab) - 0.5 * V * iE2) - pc.iota * E + pc.pixconst;
+    if (MODE == 0 || !covered) return 0.0;
+    constexpr int S = 32;
+    const double gE = pc.x * (iE + V * iE2 * iE) - pc.iota;
+    const double gV = -0.5 * pc.x * iE2;
+    const double Ez[6] = {f0, f1, 0.0, 0.0, A1, A2};
+    const double Vz[6] = {-2.0 * m * f0, -2.0 * m * f1, f0 * f0, f1 * f1, 2.0 * (B1 * f0 - m * A1), 2.0 * (B2 * f1 - m * A2)};
+    double Lz[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) Lz[i] = gE * Ez[i] + gV * Vz[i];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        double g = Lz[5] * r[k];
+        if (k < 2) g += Lz[4] * g0[k];
+        acc[(UA_G + k) * S] += g;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[(UA_C1 + c) * S] += Lz[c];
+    if (MODE == 1) return 0.0;
+
+    const double LEE = -pc.x * (iE2 + 3.0 * V * iE2 * iE2);
+    const double LEV = pc.x * iE2 * iE;
+    double Lzz[6][6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = i; j < 6; ++j) {
+            double ezz = 0.0, bpart = 0.0;
+            if ((i == 0 && j == 4) || (i == 1 && j == 5)) ezz = 1.0;
+            if (i == 2 && j == 4) bpart = 2.0 * f0;
+            if (i == 4 && j == 4) bpart = 2.0 * B1;
+            if (i == 3 && j == 5) bpart = 2.0 * f1;
+            if (i == 5 && j == 5) bpart = 2.0 * B2;
+            const double vzz = -2.0 * (Ez[i] * Ez[j] + m * ezz) + bpart;
+            Lzz[i][j] = LEE * Ez[i] * Ez[j] + LEV * (Ez[i] * Vz[j] + Vz[i] * Ez[j]) + gE * ezz + gV * vzz;
+        }
+    // Jz' Lzz Jz + L4 d2f0: everything except L5 d2f1
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+#pragma unroll
+        for (int l = k; l < 6; ++l) {
+            double v = Lzz[5][5] * r[k] * r[l];
+            if (k < 2) v += Lzz[4][5] * g0[k] * r[l];
+            if (l < 2) {
+                v += Lzz[4][5] * r[k] * g0[l];
+                v += Lz[4] * h0[k + l] + Lzz[4][4] * g0[k] * g0[l];
+            }
+            acc[(UA_HH + tri6(k, l)) * S] += v;
+        }
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int d = c; d < 4; ++d) acc[(UA_CC + tri4(c, d)) * S] += Lzz[c][d];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            double v = Lzz[c][5] * r[k];
+            if (k < 2) v += Lzz[c][4] * g0[k];
+            acc[(UA_CR + c * 6 + k) * S] += v;
+        }
+    return Lz[5];
+}
+
+// One component's share of the 20 second-order mixture sums from its 15 L5-weighted moments (see the file header)
+__device__ __forceinline__ void unit_moments_to_sums(double l11, double l12, double l22, const double* D, double* OUT) {
+    const double D00 = D[0], D01 = D[1], D02 = D[2], D03 = D[3], D04 = D[4];
+    const double D10 = D[5], D11 = D[6], D12 = D[7], D13 = D[8];
+    const double D20 = D[9], D21 = D[10], D22 = D[11];
+    const double D30 = D[12], D31 = D[13];
+    const double D40 = D[14];
+#include "hess_moments.inc"
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(UNIT_THREADS, CELESTE_UNIT_MINB)
+    unit_kernel(PlanDev plan, const UnitHdr* __restrict__ units, int n_units, int* __restrict__ queue,
+                double* __restrict__ scratch, long long scratch_stride, long long maxpix, const double* __restrict__ vp) {
+    constexpr int NUA = NUAcc<MODE>::value;
+    constexpr int NS = MODE == 0 ? 2 : 7;
+    constexpr int NACC = NAcc<MODE>::value;
+    CEL_DYNAMIC_SMEM(smem);
+    __shared__ double s_exptab[8];
+    __shared__ double s_logtab[256];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, kk = tid & 1;
+    double* wbase = smem + (size_t)warp * UnitWarpDoubles<MODE>::value;
+    double* acc = wbase + lane;                             // NUA x 32
+    double* s_rec = wbase + (size_t)NUA * 32;               // NC2 x MREC
+    double* s_si = s_rec + NC2 * MREC;                      // SU_STRIDE
+    UnitImg& mi = *reinterpret_cast<UnitImg*>(s_si + SU_STRIDE);
+    double* my_scratch = scratch + ((size_t)blockIdx.x * UNIT_WARPS + warp) * (size_t)scratch_stride;
+#ifdef CELESTE_HOST_EMULATION
+    if (tid < 8) s_exptab[tid] = h_exptab[tid];
+    for (int i = tid; i < 256; i += UNIT_THREADS) s_logtab[i] = h_logtab[i];
+#else
+    if (tid < 8) s_exptab[tid] = c_exptab[tid];
+    for (int i = tid; i < 256; i += UNIT_THREADS) s_logtab[i] = g_logtab[i];
+#endif
+    __syncthreads();
+
+    for (;;) {
+        int u = 0;
+        if (lane == 0) u = atomicAdd(queue, 1);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= n_units) break;
+        const UnitHdr uh = units[u];
+        if (plan.task_mask && !plan.task_mask[uh.task]) continue;
+        const FieldDev field = plan.fields[uh.field];
+        const int n = uh.n, aslot = uh.aslot;
+        const PatchDev* prow = field.patches + (size_t)n * field.S_tot;       // patches of image n, by source row
+        const PatchDev& pa = prow[plan.src_row[aslot]];
+        const int band0 = field.images[n].band - 1;
+        __syncwarp();                                       // the previous unit's shared data is consumed
+#pragma unroll
+        for (int a = 0; a < NUA; ++a) acc[a * 32] = 0.0;
+        if (lane == 30) {
+            const ImageDev& img = field.images[n];
+            mi.pixels = img.pixels;
+            mi.sky = img.sky;
+            mi.pixconst = img.pixconst;
+            mi.iota = img.iota;
+            mi.bitmap = pa.bitmap;
+            mi.coefs = pa.coefs;
+            mi.scratch = my_scratch;
+            mi.H2 = pa.H2;
+            mi.W2 = pa.W2;
+            mi.off_h = pa.off_h;
+            mi.off_w = pa.off_w;
+            mi.imgH = img.H;
+            mi.n1 = pa.n1;
+            mi.n2 = pa.n2;
+            mi.band0 = band0;
+        }
+        double cnt_inactive = 0.0, cnt_active = 0.0, val = 0.0;
+
+        // ---- neighbours, one at a time in slot order: E_bg += E_s, V_bg += E2_s - E_s^2 over the shared pixels ----
+        if (uh.hasbg) {
+            {
+                const int tot = 2 * pa.H2 * pa.W2;
+                for (int i = lane; i < tot; i += 32) my_scratch[i] = 0.0;
+            }
+            for (int s = uh.slot0; s < uh.slot1; ++s) {
+                if (s == aslot) continue;
+                const PatchDev& p = prow[plan.src_row[s]];
+                // active pixels: rows off+1..off+H2, columns off+1..off+W2; the neighbour covers columns
+                // off+1..off+W2-1 only (strict `w2 < W2`, elbo_objective.jl:349)
+                const int h_lo = max(pa.off_h, p.off_h) + 1, h_hi = min(pa.off_h + pa.H2, p.off_h + p.H2);
+                const int w_lo = max(pa.off_w, p.off_w) + 1, w_hi = min(pa.off_w + pa.W2, p.off_w + p.W2 - 1);
+                if (h_hi < h_lo || w_hi < w_lo) continue;            // warp-uniform
+                const int bnh = h_hi - h_lo + 1, bnw = w_hi - w_lo + 1;
+                __syncwarp();                                        // the previous neighbour's walks are done with s_rec / s_si
+                if (lane < NC2) {
+                    const double* vs = vp + (size_t)NPARAM * s;
+                    double xx[3];
+                    galaxy_xixi(vs[3], vs[4], vs[5], xx[0], xx[1], xx[2]);
+                    march_make_record(p, vs, xx, s_rec, lane);
+                }
+                if (lane == NC2) march_stage_srcimg<0>(p, vp + (size_t)NPARAM * s, band0, s_si);
+                __syncwarp();
+                const int nsg = (bnw + MARCH_MAXSEG - 1) / MARCH_MAXSEG;
+                const int total = bnh * nsg;
+                const int segw = (bnw + nsg - 1) / nsg;
+                for (int ub = 0; ub < total; ub += NPW) {            // warp-uniform
+                    const int uu = ub + (lane >> 1);
+                    const bool has = uu < total;
+                    const int ul = has ? uu : 0;
+                    const int seg = ul / bnh, row = ul - seg * bnh;
+                    const int c0 = seg * segw;
+                    const int len = has ? max(min(segw, bnw - c0), 0) : 0;
+                    const int nit = warp_max_int((len + 1) >> 1);
+                    if (nit == 0) continue;
+                    const int h = h_lo + row, w0 = w_lo + c0;       // 1-based image coordinates
+                    const int aH2 = pa.H2, aW2 = pa.W2, nH2 = p.H2, imgH = mi.imgH, n1 = p.n1, n2 = p.n2;
+                    const double* coefs = p.coefs;
+                    const double* si = s_si;
+                    const double* recs = s_rec + kk * MREC;          // this lane's PSF component
+                    double fp[NPROTO], rr[NPROTO];
+                    const double ax = (double)h - si[SI_M] + 26.0, ay0 = (double)w0 - si[SI_M + 1] + 26.0;
+                    const int ixf = (int)floor(ax), iy0 = (int)floor(ay0);
+                    const bool fast = len > 0 && ixf >= 1 && ixf <= n1 - 3 && iy0 >= 1 && iy0 + len - 1 <= n2 - 3;
+                    double R0 = 0.0, R1 = 0.0;
+                    const double* ccol = coefs + (size_t)(fast ? iy0 - 1 + kk : 0) * n1 + (fast ? ixf - 1 : 0);
+                    if (fast && kk < len) {
+                        const double wx0 = si[SI_WX], wx1 = si[SI_WX + 1], wx2 = si[SI_WX + 2], wx3 = si[SI_WX + 3];
+                        R0 = wx0 * __ldg(ccol) + wx1 * __ldg(ccol + 1) + wx2 * __ldg(ccol + 2) + wx3 * __ldg(ccol + 3);
+                        ccol += n1;
+                        R1 = wx0 * __ldg(ccol) + wx1 * __ldg(ccol + 1) + wx2 * __ldg(ccol + 2) + wx3 * __ldg(ccol + 3);
+                        ccol += n1;
+                    }
+                    const int ah2 = h - pa.off_h - 1, nh2 = h - p.off_h - 1;
+                    const int acol = w0 - pa.off_w - 1 + kk, ncol = w0 - p.off_w - 1 + kk;      // own first column, 0-based
+                    const uint8_t* abit = pa.bitmap + ah2 + (size_t)acol * aH2;
+                    const uint8_t* nbit = p.bitmap + nh2 + (size_t)ncol * nH2;
+                    const float* px = mi.pixels + (size_t)(h - 1) + (size_t)(w0 - 1 + kk) * imgH;
+                    double* bgE = my_scratch + ah2 + (size_t)acol * aH2;
+                    const size_t bgplane = (size_t)aH2 * aW2;
+                    const double theta = si[SI_THETA];
+                    int t = 0;
+                    while (t < nit) {
+                        const bool asleep = march_start(recs, s_exptab, (double)h, (double)(w0 + 2 * t), fp, rr);
+                        const bool careful = __ballot_sync(0xffffffffu, asleep && len > 0) != 0u;
+                        const int tend = careful ? min(nit, t + MARCH_CAREFUL_COLS / 2) : nit;
+                        for (; t < tend; ++t) {
+                            const bool own = 2 * t + kk < len;
+                            unsigned char ab = 0, nb = 0;
+                            float xv = 0.f;
+                            if (own) {
+                                ab = *abit;
+                                nb = *nbit;
+                                xv = *px;
+                            }
+                            double R2 = 0.0, R3 = 0.0;
+                            if (fast && own) {
+                                const double wx0 = si[SI_WX], wx1 = si[SI_WX + 1], wx2 = si[SI_WX + 2], wx3 = si[SI_WX + 3];
+                                R2 = wx0 * __ldg(ccol) + wx1 * __ldg(ccol + 1) + wx2 * __ldg(ccol + 2) + wx3 * __ldg(ccol + 3);
+                                ccol += n1;
+                                R3 = wx0 * __ldg(ccol) + wx1 * __ldg(ccol + 1) + wx2 * __ldg(ccol + 2) + wx3 * __ldg(ccol + 3);
+                                ccol += n1;
+                            }
+                            double S[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+                            for (int pix = 0; pix < 2; ++pix) {
+#pragma unroll
+                                for (int j = 0; j < NPROTO; ++j) {
+                                    S[pix][j < NPROTO_DEV ? 0 : 1] += fp[j];
+                                    fp[j] *= rr[j];
+                                    rr[j] *= recs[j * 2 * MREC + 3];
+                                }
+                            }
+                            double Fd = kk == 0 ? S[0][0] : S[1][0], Fe = kk == 0 ? S[0][1] : S[1][1];
+                            Fd += __shfl_xor_sync(0xffffffffu, kk == 0 ? S[1][0] : S[0][0], 1);
+                            Fe += __shfl_xor_sync(0xffffffffu, kk == 0 ? S[1][1] : S[0][1], 1);
+                            if (ab && nb && !isnan(xv)) {
+                                double f0;
+                                if (fast) {
+                                    const double v = si[SI_WY] * R0 + si[SI_WY + 1] * R1 + si[SI_WY + 2] * R2 + si[SI_WY + 3] * R3;
+                                    f0 = v < 0 ? 1e-3 * exp_nonpos(v) : 1e-3 * (v + 1.0);     // softpluslikeinv, fsm_util.jl:222
+                                } else {
+                                    double gd[2], hd[3];
+                                    star_eval<0>(LdGlobal(), coefs, n1, n2, ax, ay0 + (double)(2 * t + kk), f0, gd, hd);
+                                }
+                                const double f1 = theta * Fd + (1.0 - theta) * Fe;
+                                const double Es = si[SI_CB] * f0 + si[SI_CB + 1] * f1;
+                                const double E2s = si[SI_CB + 2] * f0 * f0 + si[SI_CB + 3] * f1 * f1;
+                                bgE[0] += Es;
+                                bgE[bgplane] += E2s - Es * Es;
+                                cnt_inactive += 1.0;                                          // elbo_objective.jl:353-357
+                            }
+                            abit += 2 * aH2;
+                            nbit += 2 * nH2;
+                            px += 2 * imgH;
+                            bgE += 2 * aH2;
+                            R0 = R2;
+                            R1 = R3;
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();          // every neighbour's sums are visible to the walk of the active source; s_rec is free
+        if (lane < NC2) {
+            const double* vs = vp + (size_t)NPARAM * aslot;
+            double xx[3];
+            galaxy_xixi(vs[3], vs[4], vs[5], xx[0], xx[1], xx[2]);      // XiXi: one sin / cos per record lane, in parallel
+            march_make_record(pa, vs, xx, s_rec, lane);
+        }
+        if (lane == NC2) unit_stage_srcimg<MODE>(pa, vp + (size_t)NPARAM * aslot, band0, s_si);
+        __syncwarp();
+
+        // ---- phase A: the active source, row walks by lane pairs ------------------------------------------------
+        const int H2c = max(mi.H2, 1), W2 = mi.W2;
+        const int nseg = uh.nseg;
+        const int total = (mi.H2 > 0 && W2 > 0) ? mi.H2 * nseg : 0;
+        const int segw = (W2 + nseg - 1) / nseg;
+        double* l5plane = my_scratch + 2 * maxpix;
+        for (int ub = 0; ub < total; ub += NPW) {                      // warp-uniform
+            const int uu = ub + (lane >> 1);
+            const bool has = uu < total;
+            const int ul = has ? uu : 0;
+            const int seg = ul / H2c, h2 = ul - seg * H2c;
+            const int c0 = seg * segw;
+            const int len = has ? max(min(segw, W2 - c0), 0) : 0;
+            const int nit = warp_max_int((len + 1) >> 1);
+            if (nit == 0) continue;
+            const int ncov = min(len, W2 - 1 - c0);                   // pixels before the (uncovered) last column, :349
+            const int h = mi.off_h + h2 + 1, w0 = mi.off_w + c0 + 1;  // 1-based image coordinates
+            const double* si = s_si;
+            const double* recs = s_rec + kk * MREC;                   // this lane's PSF component
+            double fp[NPROTO], rr[NPROTO];
+            const double d1 = (double)h - recs[4];                    // x1 - mu1 of this PSF component
+            double d2 = (double)w0 - recs[5];
+            bool fast;
+            int coff;
+            {
+                const int ixf = (int)floor((double)h - si[SI_M] + 26.0), iy0 = (int)floor((double)w0 - si[SI_M + 1] + 26.0);
+                fast = len > 0 && ixf >= 1 && ixf <= mi.n1 - 3 && iy0 >= 1 && iy0 + len - 1 <= mi.n2 - 3;
+                coff = fast ? (iy0 - 1 + kk) * mi.n1 + (ixf - 1) : 0;
+            }
+            double R0 = 0.0, R1 = 0.0, D0 = 0.0, D1 = 0.0, Q0 = 0.0, Q1 = 0.0;   // row-interpolated value / d / d2 columns
+            if (fast && kk < len) {
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    const double* ccol = mi.coefs + coff;
+                    const double q0 = __ldg(ccol), q1 = __ldg(ccol + 1), q2 = __ldg(ccol + 2), q3 = __ldg(ccol + 3);
+                    const double r = si[SI_WX] * q0 + si[SI_WX + 1] * q1 + si[SI_WX + 2] * q2 + si[SI_WX + 3] * q3;
+                    double d = 0.0, dd = 0.0;
+                    if (MODE >= 1) d = si[SI_DWX] * q0 + si[SI_DWX + 1] * q1 + si[SI_DWX + 2] * q2 + si[SI_DWX + 3] * q3;
+                    if (MODE >= 2) dd = si[SU_DDWX] * q0 + si[SU_DDWX + 1] * q1 + si[SU_DDWX + 2] * q2 + si[SU_DDWX + 3] * q3;
+                    coff += mi.n1;
+                    if (b == 0) {
+                        R0 = r;
+                        D0 = d;
+                        Q0 = dd;
+                    } else {
+                        R1 = r;
+                        D1 = d;
+                        Q1 = dd;
+                    }
+                }
+            }
+            int pix = h2 + (c0 + kk) * H2c;                           // own pixel inside the patch
+            int ipix = (h - 1) + (w0 - 1 + kk) * mi.imgH;             // ... and inside the image
+
+            int t = 0;
+            while (t < nit) {
+                const bool asleep = march_start(recs, s_exptab, (double)h, (double)(w0 + 2 * t), fp, rr);
+                const bool careful = __ballot_sync(0xffffffffu, asleep && len > 0) != 0u;
+                const int tend = careful ? min(nit, t + MARCH_CAREFUL_COLS / 2) : nit;
+                for (; t < tend; ++t) {
+                    const int iown = 2 * t + kk;
+                    const bool own = iown < len;
+                    if (own) {
+                        CEL_PREFETCH_L1(mi.pixels + ipix);
+                        CEL_PREFETCH_L1(mi.sky + ipix);
+                        CEL_PREFETCH_L1(mi.pixconst + ipix);
+                        CEL_PREFETCH_L1(mi.bitmap + pix);
+                        if (fast) {
+                            CEL_PREFETCH_L1(mi.coefs + coff);
+                            CEL_PREFETCH_L1(mi.coefs + coff + mi.n1 + 3);
+                        }
+                    }
+                    // this lane's half (PSF component kk) of the mixture sums of both pixels (columns 2t and 2t + 1)
+                    double S[2][NS];
+#pragma unroll
+                    for (int q = 0; q < NS; ++q) S[0][q] = S[1][q] = 0.0;
+                    const double theta = si[SI_THETA];
+#pragma unroll
+                    for (int j = 0; j < NPROTO; ++j) {
+                        const double* o = recs + j * 2 * MREC;
+                        const double cc = o[3];
+                        const double fa = fp[j];
+                        const double ra = rr[j];
+                        const double fb = fa * ra;               // column 2t + 1
+                        const double rb = ra * cc;
+                        fp[j] = fb * rb;                         // column 2t + 2
+                        rr[j] = rb * cc;
+                        S[0][j < NPROTO_DEV ? 0 : 1] += fa;
+                        S[1][j < NPROTO_DEV ? 0 : 1] += fb;
+                        if (MODE >= 1) {
+                            const double l11 = o[0], l12 = o[1], l22 = o[2];
+                            const double p1a = fma(l12, d2, l11 * d1), p1b = p1a + l12;
+                            const double p2a = fma(l22, d2, l12 * d1), p2b = p2a + l22;
+                            const double tw = j < NPROTO_DEV ? theta : 1.0 - theta;
+                            const double wa = fa * tw, wb = fb * tw;
+                            S[0][2] = fma(wa, p1a, S[0][2]);
+                            S[1][2] = fma(wb, p1b, S[1][2]);
+                            S[0][3] = fma(wa, p2a, S[0][3]);
+                            S[1][3] = fma(wb, p2b, S[1][3]);
+                            const double na = wa * c_proto_nu[j], nb = wb * c_proto_nu[j];
+                            S[0][4] = fma(na, fma(p1a, p1a, -l11), S[0][4]);      // 2 x bvn_sig_d[1], BivariateNormals.jl:267-272
+                            S[1][4] = fma(nb, fma(p1b, p1b, -l11), S[1][4]);
+                            S[0][5] = fma(na, fma(p1a, p2a, -l12), S[0][5]);
+                            S[1][5] = fma(nb, fma(p1b, p2b, -l12), S[1][5]);
+                            S[0][6] = fma(na, fma(p2a, p2a, -l22), S[0][6]);      // 2 x bvn_sig_d[3]
+                            S[1][6] = fma(nb, fma(p2b, p2b, -l22), S[1][6]);
+                        }
+                    }
+                    d2 += 2.0;
+                    double T[NS];
+#pragma unroll
+                    for (int q = 0; q < NS; ++q)
+                        T[q] = (kk == 0 ? S[0][q] : S[1][q]) + __shfl_xor_sync(0xffffffffu, kk == 0 ? S[1][q] : S[0][q], 1);
+
+                    unsigned char bit = 0;
+                    float xf = 0.f, skyf = 0.f;
+                    double pconst = 0.0, bE = 0.0, bV = 0.0;
+                    double f0 = 0.0, g0[2] = {0.0, 0.0}, h0[3] = {0.0, 0.0, 0.0};
+                    if (own) {
+                        bit = mi.bitmap[pix];
+                        xf = mi.pixels[ipix];
+                        skyf = mi.sky[ipix];
+                        pconst = mi.pixconst[ipix];
+                        if (uh.hasbg) {
+                            bE = mi.scratch[pix];
+                            bV = mi.scratch[pix + H2c * W2];
+                        }
+                        if (fast) {
+                            const double* ccol = mi.coefs + coff;
+                            const int n1 = mi.n1;
+                            const double q0 = __ldg(ccol), q1 = __ldg(ccol + 1), q2 = __ldg(ccol + 2), q3 = __ldg(ccol + 3);
+                            const double q4 = __ldg(ccol + n1), q5 = __ldg(ccol + n1 + 1), q6 = __ldg(ccol + n1 + 2), q7 = __ldg(ccol + n1 + 3);
+                            const double R2 = si[SI_WX] * q0 + si[SI_WX + 1] * q1 + si[SI_WX + 2] * q2 + si[SI_WX + 3] * q3;
+                            const double R3 = si[SI_WX] * q4 + si[SI_WX + 1] * q5 + si[SI_WX + 2] * q6 + si[SI_WX + 3] * q7;
+                            const double wy0 = si[SI_WY], wy1 = si[SI_WY + 1], wy2 = si[SI_WY + 2], wy3 = si[SI_WY + 3];
+                            const double v = wy0 * R0 + wy1 * R1 + wy2 * R2 + wy3 * R3;
+                            double gx = 0.0, gy = 0.0, hxx = 0.0, hxy = 0.0, hyy = 0.0;
+                            if (MODE >= 1) {
+                                const double D2 = si[SI_DWX] * q0 + si[SI_DWX + 1] * q1 + si[SI_DWX + 2] * q2 + si[SI_DWX + 3] * q3;
+                                const double D3 = si[SI_DWX] * q4 + si[SI_DWX + 1] * q5 + si[SI_DWX + 2] * q6 + si[SI_DWX + 3] * q7;
+                                gx = wy0 * D0 + wy1 * D1 + wy2 * D2 + wy3 * D3;
+                                gy = si[SI_DWY] * R0 + si[SI_DWY + 1] * R1 + si[SI_DWY + 2] * R2 + si[SI_DWY + 3] * R3;
+                                if (MODE >= 2) {
+                                    const double Q2 = si[SU_DDWX] * q0 + si[SU_DDWX + 1] * q1 + si[SU_DDWX + 2] * q2 + si[SU_DDWX + 3] * q3;
+                                    const double Q3 = si[SU_DDWX] * q4 + si[SU_DDWX + 1] * q5 + si[SU_DDWX + 2] * q6 + si[SU_DDWX + 3] * q7;
+                                    hxx = wy0 * Q0 + wy1 * Q1 + wy2 * Q2 + wy3 * Q3;
+                                    hxy = si[SI_DWY] * D0 + si[SI_DWY + 1] * D1 + si[SI_DWY + 2] * D2 + si[SI_DWY + 3] * D3;
+                                    hyy = si[SU_DDWY] * R0 + si[SU_DDWY + 1] * R1 + si[SU_DDWY + 2] * R2 + si[SU_DDWY + 3] * R3;
+                                    Q0 = Q2;
+                                    Q1 = Q3;
+                                }
+                                D0 = D2;
+                                D1 = D3;
+                            }
+                            R0 = R2;
+                            R1 = R3;
+                            if (v < 0) {                                          // softpluslikeinv, fsm_util.jl:222
+                                const double e = 1e-3 * exp_nonpos(v);
+                                f0 = e;
+                                g0[0] = e * gx;
+                                g0[1] = e * gy;
+                                if (MODE >= 2) {
+                                    h0[0] = e * (gx * gx + hxx);
+                                    h0[1] = e * (gx * gy + hxy);
+                                    h0[2] = e * (gy * gy + hyy);
+                                }
+                            } else {
+                                f0 = 1e-3 * (v + 1.0);
+                                g0[0] = 1e-3 * gx;
+                                g0[1] = 1e-3 * gy;
+                                if (MODE >= 2) {
+                                    h0[0] = 1e-3 * hxx;
+                                    h0[1] = 1e-3 * hxy;
+                                    h0[2] = 1e-3 * hyy;
+                                }
+                            }
+                        }
+                    }
+                    double l5 = 0.0;
+                    if (own && bit && !isnan(xf)) {                          // elbo_objective.jl:445, :459
+                        PixelConsts pc;
+                        pc.x = (double)xf;
+                        pc.iota = (double)mi.iota[h - 1];
+                        pc.pixconst = pconst;
+                        const bool covered = iown < ncov;      // the last column of the patch is not covered by its own source (:349)
+                        const double f1 = theta * T[0] + (1.0 - theta) * T[1];
+                        double r[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+                        if (MODE >= 1) {
+                            r[0] = -T[2];
+                            r[1] = -T[3];
+                            r[2] = 0.5 * T[4];
+                            r[3] = T[5];
+                            r[4] = 0.5 * T[6];
+                            r[5] = T[0] - T[1];                                   // gal_frac_dev, fsm_util.jl:277-291
+                        }
+                        if (covered) {
+                            if (!fast)
+                                star_eval<MODE>(LdGlobal(), mi.coefs, mi.n1, mi.n2, (double)h - si[SI_M] + 26.0,
+                                                (double)(w0 + iown) - si[SI_M + 1] + 26.0, f0, g0, h0);
+                            cnt_active += 1.0;
+                        }
+                        const double cb[4] = {si[SI_CB], si[SI_CB + 1], si[SI_CB + 2], si[SI_CB + 3]};
+                        l5 = unit_pixel_term<MODE>(acc, pc, (double)skyf + bE, bV, covered, cb, f0, g0, h0, f1, r, val, s_logtab);
+                    }
+                    if (MODE >= 2 && own) l5plane[pix] = l5;
+                    pix += 2 * H2c;
+                    ipix += 2 * mi.imgH;
+                    coff += 2 * mi.n1;
+                }
+            }
+        }
+
+        // ---- phase B: L5-weighted moments, one lane per component --------------------------------------------------
+        if (MODE >= 2) {
+            __syncwarp();                                            // the L5 plane is complete
+            double OUT[20];
+#pragma unroll
+            for (int q = 0; q < 20; ++q) OUT[q] = 0.0;
+            const int ncols = W2 - 1;                                // covered columns (:349)
+            if (lane < NC2 && mi.H2 > 0 && ncols > 0) {
+                const double* o = s_rec + lane * MREC;
+                const double l11 = o[0], l12 = o[1], l22 = o[2], cc = o[3], mu1 = o[4], mu2 = o[5], z = o[6];
+                double Dm[15];
+#pragma unroll
+                for (int q = 0; q < 15; ++q) Dm[q] = 0.0;
+                const int nsb = (ncols + MARCH_MAXSEG - 1) / MARCH_MAXSEG;
+                const int sw = (ncols + nsb - 1) / nsb;
+                for (int h2 = 0; h2 < mi.H2; ++h2) {
+                    const double d1 = (double)(mi.off_h + h2 + 1) - mu1;
+                    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0;
+                    for (int c0 = 0; c0 < ncols; c0 += sw) {
+                        const int c1 = min(c0 + sw, ncols);
+                        int c = c0;
+                        while (c < c1) {
+                            // exact (re)start of the recurrence at column c (the rule of march_start)
+                            double d2 = (double)(mi.off_w + c + 1) - mu2;
+                            const double p1 = l11 * d1 + l12 * d2;
+                            const double p2 = l12 * d1 + l22 * d2;
+                            const double q = d1 * p1 + d2 * p2;
+                            const double ra = -(p2 + 0.5 * l22);
+                            const bool sleep = q > MARCH_Q_SLEEP || ra > 700.0;
+                            double f = sleep ? 0.0 : z * exp_scaled_tab(q, -0.5, s_exptab);
+                            double r = sleep ? 0.0 : exp_scaled_tab(fmin(ra, 700.0), 1.0, s_exptab);
+                            const int cend = sleep ? min(c1, c + MARCH_CAREFUL_COLS) : c1;
+                            const double* lp = l5plane + h2 + (size_t)c * H2c;
+                            for (; c < cend; ++c) {
+                                const double v = f * *lp;
+                                const double v1 = v * d2;
+                                s0 += v;
+                                const double v2 = v1 * d2;
+                                s1 += v1;
+                                const double v3 = v2 * d2;
+                                s2 += v2;
+                                s3 += v3;
+                                s4 = fma(v3, d2, s4);
+                                f *= r;
+                                r *= cc;
+                                d2 += 1.0;
+                                lp += H2c;
+                            }
+                        }
+                    }
+                    // D[a][b] += d1^a s_b; index order 00 01 02 03 04 | 10 11 12 13 | 20 21 22 | 30 31 | 40
+                    const double e1 = d1, e2 = d1 * d1, e3 = e2 * d1, e4 = e2 * e2;
+                    Dm[0] += s0;
+                    Dm[1] += s1;
+                    Dm[2] += s2;
+                    Dm[3] += s3;
+                    Dm[4] += s4;
+                    Dm[5] = fma(e1, s0, Dm[5]);
+                    Dm[6] = fma(e1, s1, Dm[6]);
+                    Dm[7] = fma(e1, s2, Dm[7]);
+                    Dm[8] = fma(e1, s3, Dm[8]);
+                    Dm[9] = fma(e2, s0, Dm[9]);
+                    Dm[10] = fma(e2, s1, Dm[10]);
+                    Dm[11] = fma(e2, s2, Dm[11]);
+                    Dm[12] = fma(e3, s0, Dm[12]);
+                    Dm[13] = fma(e3, s1, Dm[13]);
+                    Dm[14] = fma(e4, s0, Dm[14]);
+                }
+                unit_moments_to_sums(l11, l12, l22, Dm, OUT);
+                // weights of the component: thc (u), thc nu (xs), thc nu^2 (ss), sg (tx), sg nu (ts)
+                const int j = lane >> 1;
+                const double theta = s_si[SI_THETA];
+                const double thc = j < NPROTO_DEV ? theta : 1.0 - theta;
+                const double sg = j < NPROTO_DEV ? 1.0 : -1.0;
+                const double nu = c_proto_nu[j];
+#pragma unroll
+                for (int q = 0; q < 3; ++q) OUT[q] *= thc;
+#pragma unroll
+                for (int q = 3; q < 9; ++q) OUT[q] *= thc * nu;
+#pragma unroll
+                for (int q = 9; q < 15; ++q) OUT[q] *= thc * nu * nu;
+#pragma unroll
+                for (int q = 15; q < 17; ++q) OUT[q] *= sg;
+#pragma unroll
+                for (int q = 17; q < 20; ++q) OUT[q] *= sg * nu;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int q = 0; q < 20; ++q) OUT[q] += __shfl_xor_sync(0xffffffffu, OUT[q], o);
+            }
+            if (lane == 0) {
+                // R of GalRaw (elbo_math.cuh gal_eval): xx = (2 u1, u2, 2 u3); x-Sigma = xs; x-theta = -tx; Sigma-Sigma = ss;
+                // Sigma-theta = ts
+                acc[(UA_HH + tri6(0, 0)) * 32] += 2.0 * OUT[0];
+                acc[(UA_HH + tri6(0, 1)) * 32] += OUT[1];
+                acc[(UA_HH + tri6(1, 1)) * 32] += 2.0 * OUT[2];
+                acc[(UA_HH + tri6(0, 2)) * 32] += OUT[3];
+                acc[(UA_HH + tri6(0, 3)) * 32] += OUT[4];
+                acc[(UA_HH + tri6(0, 4)) * 32] += OUT[5];
+                acc[(UA_HH + tri6(1, 2)) * 32] += OUT[6];
+                acc[(UA_HH + tri6(1, 3)) * 32] += OUT[7];
+                acc[(UA_HH + tri6(1, 4)) * 32] += OUT[8];
+                acc[(UA_HH + tri6(2, 2)) * 32] += OUT[9];
+                acc[(UA_HH + tri6(2, 3)) * 32] += OUT[10];
+                acc[(UA_HH + tri6(2, 4)) * 32] += OUT[11];
+                acc[(UA_HH + tri6(3, 3)) * 32] += OUT[12];
+                acc[(UA_HH + tri6(3, 4)) * 32] += OUT[13];
+                acc[(UA_HH + tri6(4, 4)) * 32] += OUT[14];
+                acc[(UA_HH + tri6(0, 5)) * 32] -= OUT[15];
+                acc[(UA_HH + tri6(1, 5)) * 32] -= OUT[16];
+                acc[(UA_HH + tri6(2, 5)) * 32] += OUT[17];
+                acc[(UA_HH + tri6(3, 5)) * 32] += OUT[18];
+                acc[(UA_HH + tri6(4, 5)) * 32] += OUT[19];
+            }
+        }
+        __syncwarp();
+
+        // ---- fixed-order warp reduction -> the unit's partial vector -------------------------------------------------
+        double* out = plan.partials + (size_t)uh.pidx * NACC;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            val += __shfl_xor_sync(0xffffffffu, val, o);
+            cnt_active += __shfl_xor_sync(0xffffffffu, cnt_active, o);
+            cnt_inactive += __shfl_xor_sync(0xffffffffu, cnt_inactive, o);
+        }
+        if (lane == 0) {
+            out[ACC_VAL] = val;
+            out[ACC_CNT_ACTIVE] = cnt_active;
+            out[ACC_CNT_INACTIVE] = cnt_inactive;
+        }
+        if (MODE == 2 && lane < 3) out[ACC_CC + 7 + lane] = 0.0;
+        for (int a = lane; a < NUA; a += 32) {
+            const double* row = wbase + (size_t)a * 32;
+            double s = 0.0;
+#pragma unroll 8
+            for (int i = 0; i < 32; ++i) s += row[(lane + i) & 31];
+            out[unit_acc_index(a)] = s;
+        }
+    }
+}
+
+// Host side: the unit list of a plan (every (sub, image), heaviest first) and each unit's column segmentation.
+// geo(slot, n, off_h, off_w, H2, W2) -> the patch box of a slot in image n.
+template <typename Geo>
+inline void build_unit_list(int n_subs, int N, const int* sub_task, const int* sub_slot, const int* task_ptr,
+                            const int* task_field, Geo geo, std::vector<UnitHdr>& units, long long& maxpix) {
+    units.clear();
+    maxpix = 1;
+    std::vector<long> cost;
+    for (int u = 0; u < n_subs; ++u) {
+        const int t = sub_task[u];
+        const int aslot = sub_slot[u], slot0 = task_ptr[t], slot1 = task_ptr[t + 1];
+        for (int n = 0; n < N; ++n) {
+            int oh, ow, H2, W2;
+            geo(aslot, n, oh, ow, H2, W2);
+            UnitHdr uh{};
+            uh.aslot = aslot;
+            uh.slot0 = slot0;
+            uh.slot1 = slot1;
+            uh.field = task_field ? task_field[t] : 0;
+            uh.sub = u;
+            uh.task = t;
+            uh.n = n;
+            uh.pidx = u * N + n;
+            uh.hasbg = 0;
+            long c = 0;
+            uh.nseg = 1;
+            if (H2 > 0 && W2 > 0) {
+                maxpix = std::max(maxpix, (long long)H2 * W2);
+                c = (long)H2 * W2 * 4;
+                for (int s = slot0; s < slot1; ++s) {
+                    if (s == aslot) continue;
+                    int ph, pw, pH2, pW2;
+                    geo(s, n, ph, pw, pH2, pW2);
+                    if (pH2 > 0 && pW2 > 1) {
+                        const int h_lo = std::max(oh, ph) + 1, h_hi = std::min(oh + H2, ph + pH2);
+                        const int w_lo = std::max(ow, pw) + 1, w_hi = std::min(ow + W2, pw + pW2 - 1);
+                        if (h_hi >= h_lo && w_hi >= w_lo) {
+                            uh.hasbg = 1;
+                            c += (long)(h_hi - h_lo + 1) * (w_hi - w_lo + 1);
+                        }
+                    }
+                }
+                // column segments per row: minimise rounds of 16 walks x (iterations of two columns + an exact start)
+                const int nmin = std::max(1, (W2 + MARCH_MAXSEG - 1) / MARCH_MAXSEG);
+                long best = -1;
+                for (int cand = nmin; cand < nmin + 8; ++cand) {
+                    const int L = (W2 + cand - 1) / cand;
+                    const long cst = (long)((H2 * cand + NPW - 1) / NPW) * (10 * ((L + 1) / 2) + 5);
+                    if (best < 0 || cst < best) {
+                        best = cst;
+                        uh.nseg = cand;
+                    }
+                }
+            }
+            units.push_back(uh);
+            cost.push_back(c);
+        }
+    }
+    std::vector<int> order(units.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cost[x] > cost[y]; });
+    std::vector<UnitHdr> sorted(units.size());
+    for (size_t i = 0; i < order.size(); ++i) sorted[i] = units[order[i]];
+    units.swap(sorted);
+}
+
+}  // namespace celeste
+#endif

@@ -68,6 +68,16 @@ inline double __shfl_xor_sync(unsigned, double v, int o) {
     c->warp_bar[w]->arrive_and_wait();
     return r;
 }
+inline int __shfl_sync(unsigned, int v, int src) {
+    auto* c = cuda_emul::ctx();
+    const int w = threadIdx.x / 32;
+    c->xchg_i[threadIdx.x] = v;
+    c->warp_bar[w]->arrive_and_wait();
+    const int r = c->xchg_i[w * 32 + src];
+    c->warp_bar[w]->arrive_and_wait();
+    return r;
+}
+inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
 inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }
 inline bool __all_sync(unsigned m, bool pred) { return __ballot_sync(m, pred) == (threadIdx.x / 32 * 32 + 32 <= (unsigned)cuda_emul::ctx()->nthreads ? 0xffffffffu : ((1u << (cuda_emul::ctx()->nthreads % 32)) - 1u)); }

@@ -7,6 +7,7 @@
 #include "../../include/celeste_cuda.h"
 #include "../../celeste.jl_b200/csrc/celeste_kernels.cuh"
 #include "../../celeste.jl_b200/csrc/march_kernels.cuh"
+#include "../../celeste.jl_b200/csrc/unit_kernels.cuh"
 #include "../../celeste.jl_b200/csrc/maximize_kernels.cuh"
 #include "../../celeste.jl_b200/csrc/patch_kernels.cuh"
 
@@ -37,12 +38,49 @@ void galaxy_prototypes(double eta[NPROTO], double nu[NPROTO]) {
 long g_march_split = 6000;   // pixels above which a source gets one march block per image (emul_set_grad_kernel(2) lowers it)
 int g_grad_kernel = 1;   // 1: march_kernel where the product would use it (Sa = 1, K = 2); 0: always task_kernel
 
+int g_hess_kernel = 1;   // 1: unit_kernel<2> where the product would use it (Sa = 1, K = 2); 0: always pixel_kernel<2>
+
+// same launch sequence as celeste_abi.cu's unit path: setup (brightness moments for the epilogue), unit_kernel, epilogue
+template <int MODE>
+void run_unit(PlanDev pd, const FieldDev& fd, const double* vp, double* v, double* d, double* h, long long* counters,
+              int* flags) {
+    std::vector<int> sub_task(pd.n_subs);
+    for (int u = 0; u < pd.n_subs; ++u) sub_task[u] = u;
+    std::vector<UnitHdr> units;
+    long long maxpix = 1;
+    build_unit_list(pd.n_subs, pd.N, sub_task.data(), pd.sub_slot, pd.task_ptr, (const int*)nullptr,
+                    [&](int slot, int n, int& oh, int& ow, int& H2, int& W2) {
+                        const PatchDev& pa = fd.patches[(size_t)pd.src_row[slot] + (size_t)n * fd.S_tot];
+                        oh = pa.off_h;
+                        ow = pa.off_w;
+                        H2 = pa.H2;
+                        W2 = pa.W2;
+                    },
+                    units, maxpix);
+    const int grid = 2;
+    std::vector<double> part((size_t)pd.n_subs * pd.N * NAcc<MODE>::value + 1, 1e300);   // poisoned
+    std::vector<double> scratch((size_t)grid * UNIT_WARPS * 3 * maxpix + 1, 1e300);
+    std::vector<int> cp((size_t)pd.n_subs * pd.N + 1);
+    for (size_t i = 0; i < cp.size(); ++i) cp[i] = (int)i;
+    pd.partials = part.data();
+    pd.chunk_ptr = cp.data();
+    int queue = 0;
+    cuda_emul::launch(setup_kernel, 2, 64, 0, pd, vp);
+    cuda_emul::launch(unit_kernel<MODE>, grid, UNIT_THREADS, unit_smem_bytes<MODE>(), pd, (const UnitHdr*)units.data(),
+                      (int)units.size(), &queue, scratch.data(), (long long)(3 * maxpix), maxpix, vp);
+    cuda_emul::launch(epilogue_kernel<MODE>, pd.n_tasks, EPI_THREADS, 0, pd, vp, v, d, h, counters, flags);
+}
+
 template <int MODE>
 void run_task(PlanDev pd, const FieldDev& fd, const std::vector<TaskHdr>& taskmap, const std::vector<int>& tcp,
               const double* vp, double* v, double* d, double* h, long long* counters, int* flags) {
     if constexpr (MODE <= 1) {
         bool all_k2 = true;
         for (int i = 0; i < fd.S_tot * pd.N; ++i) all_k2 = all_k2 && fd.patches[i].K == 2;
+        if (g_grad_kernel == 3 && all_k2 && pd.n_subs == pd.n_tasks) {
+            run_unit<MODE>(pd, fd, vp, v, d, h, counters, flags);
+            return;
+        }
         if (g_grad_kernel == 1 && all_k2 && pd.n_subs == pd.n_tasks) {
             // same launch sequence as celeste_abi.cu's march path
             std::vector<int> sub_task(pd.n_subs), part_ptr;
@@ -244,16 +282,28 @@ extern "C" int emul_elbo_batch(int32_t N, const celeste_image* imgs, int32_t S_t
         run_task<0>(pd, fd, taskmap, tcp, vp, v, d, h, cnt.data(), flags);
     else if (mode == 1)
         run_task<1>(pd, fd, taskmap, tcp, vp, v, d, h, cnt.data(), flags);
-    else
-        run<2>(pd, fd, nb, chunk_pixels, vp, v, d, h, cnt.data(), flags);
+    else {
+        bool all_k2 = true;
+        for (size_t i = 0; i < pdv.size(); ++i) all_k2 = all_k2 && pdv[i].K == 2;
+        if (g_hess_kernel == 1 && all_k2 && n_subs == n_tasks)
+            run_unit<2>(pd, fd, vp, v, d, h, cnt.data(), flags);
+        else
+            run<2>(pd, fd, nb, chunk_pixels, vp, v, d, h, cnt.data(), flags);
+    }
     for (size_t i = 0; i < cnt.size(); ++i) counters[i] = cnt[i];
     return 0;
 }
 
-// 0: task_kernel, 1: march_kernel, 2: march_kernel with every source split into one block per image
+// 0: task_kernel, 1: march_kernel, 2: march_kernel with every source split into one block per image, 3: unit_kernel
 extern "C" int emul_set_grad_kernel(int32_t which) {
-    g_grad_kernel = which == 0 ? 0 : 1;
+    g_grad_kernel = which == 0 ? 0 : (which == 3 ? 3 : 1);
     g_march_split = which == 2 ? 1 : 6000;
+    return 0;
+}
+
+// 0: pixel_kernel<2>, 1: unit_kernel<2> (where the product uses it)
+extern "C" int emul_set_hess_kernel(int32_t which) {
+    g_hess_kernel = which ? 1 : 0;
     return 0;
 }
 

@@ -93,9 +93,80 @@ def test_march_kernel_at_the_corners_of_the_parameter_box(seed):
 def test_chunking_does_not_change_counters_or_parity():
     images, patches, tasks = cases.get("two_body")
     ref = oracle_lib.OracleField(images, patches).elbo_batch(tasks, mode=2)
-    for chunk in (128, 200, 4096):
-        got = emul_lib.EmulField(images, patches).elbo_batch(tasks, mode=2, chunk_pixels=chunk)
-        cases.assert_parity(ref, got, 2, f"chunk={chunk}")
+    lib = emul_lib.load()
+    try:
+        lib.emul_set_hess_kernel(0)              # pixel_kernel<2> (the chunked kernel)
+        for chunk in (128, 200, 4096):
+            got = emul_lib.EmulField(images, patches).elbo_batch(tasks, mode=2, chunk_pixels=chunk)
+            cases.assert_parity(ref, got, 2, f"chunk={chunk}")
+    finally:
+        lib.emul_set_hess_kernel(1)
+
+
+def _tight(ref, got, mode, label, rtol):
+    rv, gv = ref["v"], got["v"]
+    fin = np.isfinite(rv)
+    assert np.all(np.abs(rv - gv)[fin] <= rtol * np.abs(rv)[fin]), (label, np.abs(rv - gv).max())
+    n = len(rv)
+    for key, need in (("d", 1), ("h", 2)):
+        if mode >= need:
+            r, g = ref[key].reshape(n, -1), got[key].reshape(n, -1)
+            sc = np.abs(r).max(axis=1, keepdims=True)
+            err = np.abs(r - g) / np.maximum(np.maximum(np.abs(r), sc * 1e-3), 1e-300)
+            assert np.nanmax(err) <= rtol, (label, key, np.nanmax(err))
+
+
+@pytest.mark.parametrize("name", ["star_1band", "galaxy", "two_body", "masked", "clipped_and_empty", "crowded",
+                                  "config2_rotated_wcs", "small_field", "wide_patch", "seven_images", "sharp_psf"])
+def test_unit_kernel_matches_oracle_and_pixel_kernel(name):
+    """unit_kernels.cuh -- the Hessian of the production shape as (phase A) row walks with the first-order mixture sums
+    + (phase B) L5-weighted moments of every component folded by closed forms -- against the oracle's dense per-pixel
+    chain rule at the parity statement AND at 1e-10 (floor 1e-3 of the row scale), and against pixel_kernel<2>
+    (direct evaluation): identical pixel-visit counters.  Modes 0 / 1 of the same kernel too."""
+    images, patches, tasks = cases.get(name)
+    lib = emul_lib.load()
+    ref = oracle_lib.OracleField(images, patches).elbo_batch(tasks, mode=2, n_threads=4)
+    unit = emul_lib.EmulField(images, patches).elbo_batch(tasks, mode=2)
+    try:
+        lib.emul_set_hess_kernel(0)
+        direct = emul_lib.EmulField(images, patches).elbo_batch(tasks, mode=2)
+    finally:
+        lib.emul_set_hess_kernel(1)
+    cases.assert_parity(ref, unit, 2, name + " unit_kernel")
+    cases.assert_parity(ref, direct, 2, name + " pixel_kernel")
+    _tight(ref, unit, 2, name, 1e-10)
+    assert np.array_equal(unit["counters"], direct["counters"])
+    assert not np.array_equal(unit["h"], direct["h"]) or not unit["h"].any(), "the switch did not change kernels"
+    try:
+        lib.emul_set_grad_kernel(3)
+        for mode in (0, 1):
+            r = oracle_lib.OracleField(images, patches).elbo_batch(tasks, mode=mode, n_threads=4)
+            g = emul_lib.EmulField(images, patches).elbo_batch(tasks, mode=mode)
+            cases.assert_parity(r, g, mode, name + f" unit_kernel mode {mode}")
+            _tight(r, g, mode, name, 1e-11)
+    finally:
+        lib.emul_set_grad_kernel(1)
+
+
+@pytest.mark.parametrize("idx", [0, 2, 3, 5, 10, 26])
+def test_unit_kernel_propagates_nonfinite_parameters(idx):
+    images, patches, tasks = cases.get("two_body")
+    bad = [(r, a, v.copy()) for r, a, v in tasks]
+    bad[0][2][idx, 0] = np.nan
+    ref = oracle_lib.OracleField(images, patches).elbo_batch(bad, mode=2)
+    got = emul_lib.EmulField(images, patches).elbo_batch(bad, mode=2)
+    assert ref["flags"].tolist() == [1, 0] and got["flags"].tolist() == [1, 0]
+    assert np.isfinite(got["v"][1]) and np.isfinite(got["h"].reshape(2, -1)[1]).all()
+
+
+@pytest.mark.parametrize("seed", [0, 3, 7, 12, 19, 23, 31, 38])
+def test_unit_kernel_at_the_corners_of_the_parameter_box(seed):
+    """cases.random_extreme_scene through unit_kernel<2>: the moment formulation at radius 0.02 .. 60 px, axis ratio
+    0.02, sources far off their patch centres."""
+    images, patches, tasks = cases.random_extreme_scene(seed)
+    ref = oracle_lib.OracleField(images, patches).elbo_batch(tasks, mode=2, n_threads=4)
+    got = emul_lib.EmulField(images, patches).elbo_batch(tasks, mode=2)
+    cases.assert_parity(ref, got, 2, f"seed {seed}")
 
 
 @pytest.mark.parametrize("name,active", [("two_body", [1, 2]), ("two_body", [2, 1]), ("masked", [1, 2]),
