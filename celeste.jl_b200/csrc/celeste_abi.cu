@@ -142,9 +142,9 @@ int configure_kernels() {
 #undef CEL_TCFG
     CUDA_TRY(cudaFuncSetAttribute(march_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)march_smem_bytes()));
     CUDA_TRY(cudaFuncSetAttribute(march_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)march_smem_bytes()));
-    CUDA_TRY(cudaFuncSetAttribute(unit_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)unit_smem_bytes<0>()));
-    CUDA_TRY(cudaFuncSetAttribute(unit_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)unit_smem_bytes<1>()));
-    CUDA_TRY(cudaFuncSetAttribute(unit_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)unit_smem_bytes<2>()));
+    CUDA_TRY(cudaFuncSetAttribute(unit_walk_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)unit_smem_bytes<0>()));
+    CUDA_TRY(cudaFuncSetAttribute(unit_walk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)unit_smem_bytes<1>()));
+    CUDA_TRY(cudaFuncSetAttribute(unit_walk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)unit_smem_bytes<2>()));
     if (const char* env = std::getenv("CELESTE_MARCH_CARVEOUT")) {     // kernel-tuning knob: shared-memory share of L1, percent
         const int pct = std::atoi(env);
         if (pct >= 0 && pct <= 100) {
@@ -218,13 +218,16 @@ struct celeste_plan {
     bool use_march = false;
     // unit_kernel (Hessian mode of the production shape; value / gradient with CELESTE_GRAD_KERNEL=unit): one warp per
     // (sub, image) unit pulled from a device-side queue
-    DevBuf<UnitHdr> unitmap;
+    DevBuf<UnitHdr> unitmap, unitmap_bg;   // every unit, heaviest first; the units with a neighbour, by shared pixels
     DevBuf<int> unit_chunk_ptr;      // identity: one partial vector per (sub, image)
-    DevBuf<int> unit_queue;
-    DevBuf<double> unit_scratch;     // per resident warp: E_bg | V_bg | L5 planes of the largest active patch
-    int n_units = 0, unit_grid = 0;
+    DevBuf<int> unit_queue;          // one counter per kernel of the sequence
+    DevBuf<long long> l5_ptr;
+    DevBuf<double> l5;               // L5 = dL/df1 of every active pixel (phase A -> phase B)
+    DevBuf<PixRec> pix;              // pixel records of every unit in walk order (packed once, unit_pack_kernel)
+    int n_units = 0, n_units_bg = 0, sms = 148;
     long long unit_maxpix = 1;
     bool use_unit_hess = false, use_unit_grad = false;
+    bool need_pack = false;          // pix is filled on the first evaluation (needs the uploaded plan arrays)
     DevBuf<PairHdr> pairmap;
     DevBuf<double> slotimg, slotbr, partials, pair_partials;
     int n_subs = 0, n_pairs = 0;
@@ -851,22 +854,32 @@ int celeste_plan_create_multi(int32_t n_fields, celeste_field* const* fields, ce
                         },
                         um, pl->unit_maxpix);
         pl->n_units = (int)um.size();
-        int sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
-        int grid = sms * CELESTE_UNIT_MINB;
-        if (const char* env = std::getenv("CELESTE_UNIT_GRID"))
-            if (std::atoi(env) > 0) grid = std::atoi(env);
-        grid = std::min(grid, std::max(1, (pl->n_units + UNIT_WARPS - 1) / UNIT_WARPS));
-        // scratch: 3 planes of the largest active patch per resident warp; very large patches shrink the grid
-        const long long per_block = 3LL * pl->unit_maxpix * UNIT_WARPS * (long long)sizeof(double);
-        grid = (int)std::max(1LL, std::min<long long>(grid, (4LL << 30) / std::max(1LL, per_block)));
-        pl->unit_grid = grid;
+        cudaDeviceGetAttribute(&pl->sms, cudaDevAttrMultiProcessorCount, pl->device);
+        std::vector<UnitHdr> ub;
+        for (const UnitHdr& x : um)
+            if (x.hasbg) ub.push_back(x);
+        std::stable_sort(ub.begin(), ub.end(), [](const UnitHdr& a, const UnitHdr& b) { return a.nbpix > b.nbpix; });
+        pl->n_units_bg = (int)ub.size();
+        std::vector<long long> l5_ptr((size_t)n_subs * pl->N, 0);
+        long long l5_total = 0;
+        for (int u = 0; u < n_subs; ++u) {
+            const celeste_field* f = fields[tfield[sub_task[u]]];
+            for (int n = 0; n < pl->N; ++n) {
+                const PatchDev& pa = f->h_patches[(size_t)src_row[sub_slot[u]] + (size_t)n * f->S_tot];
+                l5_ptr[(size_t)u * pl->N + n] = l5_total;
+                l5_total += (long long)std::max(pa.H2, 0) * std::max(pa.W2, 0);
+            }
+        }
         std::vector<int> ident((size_t)n_subs * pl->N + 1);
         for (size_t i = 0; i < ident.size(); ++i) ident[i] = (int)i;
         CUDA_TRY(pl->unitmap.upload(um));
+        CUDA_TRY(pl->unitmap_bg.upload(ub));
         CUDA_TRY(pl->unit_chunk_ptr.upload(ident));
-        CUDA_TRY(pl->unit_queue.alloc(1));
-        CUDA_TRY(pl->unit_scratch.alloc((size_t)grid * UNIT_WARPS * 3 * (size_t)pl->unit_maxpix));
+        CUDA_TRY(pl->unit_queue.alloc(4));
+        CUDA_TRY(pl->l5_ptr.upload(l5_ptr));
+        CUDA_TRY(pl->l5.alloc(pl->use_unit_hess ? (size_t)l5_total : 0));
+        CUDA_TRY(pl->pix.alloc((size_t)l5_total));
+        pl->need_pack = true;
     }
     std::vector<int> task_chunk_ptr((size_t)n_subs * pl->N + 1);
     for (size_t i = 0; i < task_chunk_ptr.size(); ++i) task_chunk_ptr[i] = (int)(i * TASK_WARPS);
@@ -936,7 +949,8 @@ int celeste_plan_kernel_times(celeste_plan* p, float ms[3]) {
 
 int celeste_plan_launches(const celeste_plan* p, int32_t mode) {
     if (!p || p->n_tasks == 0) return 0;
-    if ((mode <= 1 && p->use_unit_grad) || (mode == 2 && p->use_unit_hess)) return 3;   // slotbr, unit, epilogue
+    if ((mode <= 1 && p->use_unit_grad) || (mode == 2 && p->use_unit_hess))       // [slotbr,] [bg,] walk, [moment,] epilogue
+        return (mode >= 1 ? 1 : 0) + (p->n_units_bg > 0 ? 1 : 0) + 1 + (mode == 2 ? 1 : 0) + 1;
     if (mode <= 1 && p->use_march) return 2;                                       // march, epilogue
     return (p->n_blocks > 0 ? 3 : 2) + ((mode == 2 && p->n_pairs > 0) ? 1 : 0);   // setup, pixel, [pair,] epilogue
 }
@@ -978,6 +992,9 @@ static PlanDev plan_dev(const celeste_plan* p) {
     d.partials = p->partials.p;
     d.bg_ptr = p->bg_ptr.p;
     d.bg = p->bg.p;
+    d.l5_ptr = p->l5_ptr.p;
+    d.l5 = p->l5.p;
+    d.pix = p->pix.p;
     return d;
 }
 
@@ -992,12 +1009,26 @@ static int launch_mode(celeste_plan* p, const double* vp_dev, double* v, double*
         // one warp per (sub, image) unit from a device-side queue (unit_kernels.cuh); the epilogue is the general one
         PlanDev pu = pd;
         pu.chunk_ptr = p->unit_chunk_ptr.p;
-        CUDA_TRY(cudaMemsetAsync(p->unit_queue.p, 0, sizeof(int), st));
+        if (p->need_pack) {
+            if (p->n_units > 0) unit_pack_kernel<<<p->n_units, 128, 0, st>>>(pu, p->unitmap.p, p->n_units, p->pix.p);
+            p->need_pack = false;
+        }
+        CUDA_TRY(cudaMemsetAsync(p->unit_queue.p, 0, 4 * sizeof(int), st));
         if (MODE >= 1) slotbr_kernel<<<(p->n_subs + 127) / 128, 128, 0, st>>>(pu, vp_dev);
         if (p->timing) CUDA_TRY(cudaEventRecord(p->ev[1], st));
-        if (p->n_units > 0)
-            unit_kernel<MODE><<<p->unit_grid, UNIT_THREADS, unit_smem_bytes<MODE>(), st>>>(
-                pu, p->unitmap.p, p->n_units, p->unit_queue.p, p->unit_scratch.p, 3 * p->unit_maxpix, p->unit_maxpix, vp_dev);
+        auto grid_for = [&](int n_units, int minb) {
+            return std::max(1, std::min(p->sms * minb, (n_units + UNIT_WARPS - 1) / UNIT_WARPS));
+        };
+        if (p->n_units_bg > 0)
+            unit_bg_kernel<<<grid_for(p->n_units_bg, CELESTE_UNIT_BG_MINB), UNIT_THREADS, unit_bg_smem_bytes(), st>>>(
+                pu, p->unitmap_bg.p, p->n_units_bg, p->unit_queue.p, vp_dev, NAcc<MODE>::value);
+        if (p->n_units > 0) {
+            unit_walk_kernel<MODE><<<grid_for(p->n_units, CELESTE_UNIT_MINB), UNIT_THREADS, unit_smem_bytes<MODE>(), st>>>(
+                pu, p->unitmap.p, p->n_units, p->unit_queue.p + 1, vp_dev);
+            if (MODE == 2)
+                unit_moment_kernel<<<grid_for(p->n_units, CELESTE_UNIT_MOM_MINB), UNIT_THREADS, unit_moment_smem_bytes(), st>>>(
+                    pu, p->unitmap.p, p->n_units, p->unit_queue.p + 2, vp_dev);
+        }
         if (p->timing) CUDA_TRY(cudaEventRecord(p->ev[2], st));
         epilogue_kernel<MODE><<<p->n_tasks, EPI_THREADS, 0, st>>>(pu, vp_dev, v, d, h, counters, flags);
         if (p->timing) CUDA_TRY(cudaEventRecord(p->ev[3], st));

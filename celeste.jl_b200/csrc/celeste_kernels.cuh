@@ -83,6 +83,7 @@ struct PairHdr {
 };
 constexpr int NPAIR_ACC = 100;   // (c, y)_a x (c, y)_b
 
+struct PixRec;
 struct PlanDev {
     int n_tasks, N, n_fields, n_slots, n_subs, n_pairs;
     const FieldDev* fields;  // n_fields inference boxes share one plan (same N)
@@ -103,7 +104,10 @@ struct PlanDev {
     double* slotbr;          // n_slots * SLOTBR_STRIDE
     double* partials;        // n_blocks * NACC
     const long long* bg_ptr; // n_subs * N: offset of the (E_bg, V_bg) planes of (sub, image) in bg, -1 if the task has no neighbour
-    double* bg;              // march_kernel's per-task background buffer
+    double* bg;              // march_kernel's / unit kernels' per-(sub, image) background planes (E_bg, V_bg)
+    const long long* l5_ptr; // n_subs * N: first pixel of (sub, image) in pix / l5 (unit kernels; walk order)
+    double* l5;              // L5 = dL/df1 of every pixel of every unit (Hessian mode: phase A -> phase B)
+    const struct PixRec* pix; // packed pixel records of every unit (unit_pack_kernel)
 };
 
 

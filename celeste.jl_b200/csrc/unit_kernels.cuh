@@ -25,8 +25,14 @@
 //
 // Output: one NAcc<MODE>-vector of (c, y)-space sums per (sub, image) in plan.partials -- the layout
 // epilogue_kernel<MODE> consumes (chunk_ptr = identity), so the raw -> parameter chain rule is unchanged.
-// Warps never synchronise with each other; neighbours are walked first into the warp's scratch planes
-// (E_bg, V_bg) as in march_kernel.  MODE 0 / 1 instantiate the same walk without phase B.
+//
+// Three kernels on one stream, each a persistent grid whose warps pull units from a device-side queue and never
+// synchronise with each other:
+//   unit_bg_kernel      neighbours (value only) of the units that have any -> (E_bg, V_bg) planes in plan.bg
+//   unit_walk_kernel<M> phase A (MODE 0 / 1: the whole value / gradient evaluation)
+//   unit_moment_kernel  phase B + fold (MODE 2 only)
+// A fused single kernel was measured first (profiles/ncu_unit_kernel_hess_r02_v1.txt): 10 k SASS instructions with the
+// twelve warps of an SM spread over three different loops -- 31 % of its warp samples were instruction-cache misses.
 #ifndef CELESTE_UNIT_KERNELS_CUH
 #define CELESTE_UNIT_KERNELS_CUH
 
@@ -36,6 +42,12 @@ namespace celeste {
 
 #ifndef CELESTE_UNIT_MINB
 #define CELESTE_UNIT_MINB 3
+#endif
+#ifndef CELESTE_UNIT_BG_MINB
+#define CELESTE_UNIT_BG_MINB 3
+#endif
+#ifndef CELESTE_UNIT_MOM_MINB
+#define CELESTE_UNIT_MOM_MINB 5
 #endif
 constexpr int UNIT_WARPS = 4;
 constexpr int UNIT_THREADS = 32 * UNIT_WARPS;
@@ -55,19 +67,25 @@ struct UnitHdr {        // one (sub, image) unit; built on the host (build_unit_
     int nseg;           // column segments per row of the active patch (phase A)
     int hasbg;          // some other source of the task reaches this image
     int pidx;           // partial vector of this unit (sub * N + n)
-    int pad0, pad1;
+    int nbpix;          // pixels shared with neighbours (cost of the unit in unit_bg_kernel)
+    int pad1;
+};
+
+// One active pixel as the walk reads it: 16 bytes, stored per unit in WALK ORDER (row-major inside the patch: a row
+// walk reads consecutive records), packed once per plan by unit_pack_kernel.  x = NaN marks a pixel that is masked
+// (NaN in the image, elbo_objective.jl:459) or not in the active bitmap (:445).
+struct PixRec {
+    float x, sky;
+    double pixconst;      // x log(iota) - lgamma(x + 1)
 };
 
 // geometry and pointers of the unit's image / active patch (per-warp shared memory)
 struct UnitImg {
-    const float* pixels;
-    const float* sky;
-    const double* pixconst;
+    const PixRec* pix;      // H2 x W2 records, row-major
     const float* iota;
-    const uint8_t* bitmap;
     const double* coefs;
-    double* scratch;        // E_bg | V_bg (2 x H2 W2) ... L5 at + 2 maxpix
-    int H2, W2, off_h, off_w, imgH, n1, n2, band0;
+    const double* bg;       // (E_bg, V_bg) pairs of the unit, row-major like pix, or null
+    int H2, W2, off_h, off_w, n1, n2, band0, pad;
 };
 
 template <int MODE> struct UnitWarpDoubles {
@@ -75,6 +93,8 @@ template <int MODE> struct UnitWarpDoubles {
 };
 template <int MODE>
 constexpr size_t unit_smem_bytes() { return UnitWarpDoubles<MODE>::value * UNIT_WARPS * sizeof(double); }
+constexpr size_t unit_bg_smem_bytes() { return (size_t)(NC2 * MREC + SU_STRIDE) * UNIT_WARPS * sizeof(double); }
+constexpr size_t unit_moment_smem_bytes() { return (size_t)(NC2 * MREC) * UNIT_WARPS * sizeof(double); }
 
 // per-(source, image) constants: march_stage_srcimg plus the second-derivative spline weights (MODE 2)
 template <int MODE>
@@ -121,47 +141,75 @@ __device__ __forceinline__ double unit_pixel_term(double* acc, const PixelConsts
     for (int c = 0; c < 4; ++c) acc[(UA_C1 + c) * S] += Lz[c];
     if (MODE == 1) return 0.0;
 
+    // Second order.  With e = dE/dz, v = dV/dz (z = A1 A2 B1 B2 f0 f1) the Hessian of the pixel term in z is
+    //     Lzz = e b' + b e' + S,     b = (LEE / 2 - gV) e + LEV v,
+    // a symmetric rank-2 matrix plus the six sparse entries S = (gE - 2 gV m) Ezz + gV Bpart (L is linear in V, so there
+    // is no v v' term; combine_sfs_hessian!, SensitiveFloats.jl:99-126, written out).  Pushed through
+    // Jz = d z / d(c, y) -- identity on c, g0 (x only) for f0, r for f1 -- the dense part stays rank 2:
+    //     H_(c,y) = et bt' + bt et' + Jz' S Jz,   et = Jz' e,   bt = Jz' b.
     const double LEE = -pc.x * (iE2 + 3.0 * V * iE2 * iE2);
     const double LEV = pc.x * iE2 * iE;
-    double Lzz[6][6];
+    const double ha = 0.5 * LEE - gV;
+    double b[6];
 #pragma unroll
-    for (int i = 0; i < 6; ++i)
+    for (int i = 0; i < 6; ++i) b[i] = (i == 2 || i == 3) ? LEV * Vz[i] : fma(ha, Ez[i], LEV * Vz[i]);
+    double ey[6], by[6];
 #pragma unroll
-        for (int j = i; j < 6; ++j) {
-            double ezz = 0.0, bpart = 0.0;
-            if ((i == 0 && j == 4) || (i == 1 && j == 5)) ezz = 1.0;
-            if (i == 2 && j == 4) bpart = 2.0 * f0;
-            if (i == 4 && j == 4) bpart = 2.0 * B1;
-            if (i == 3 && j == 5) bpart = 2.0 * f1;
-            if (i == 5 && j == 5) bpart = 2.0 * B2;
-            const double vzz = -2.0 * (Ez[i] * Ez[j] + m * ezz) + bpart;
-            Lzz[i][j] = LEE * Ez[i] * Ez[j] + LEV * (Ez[i] * Vz[j] + Vz[i] * Ez[j]) + gE * ezz + gV * vzz;
+    for (int k = 0; k < 6; ++k) {
+        ey[k] = A2 * r[k];
+        by[k] = b[5] * r[k];
+        if (k < 2) {
+            ey[k] = fma(A1, g0[k], ey[k]);
+            by[k] = fma(b[4], g0[k], by[k]);
         }
-    // Jz' Lzz Jz + L4 d2f0: everything except L5 d2f1
+    }
+    const double sig = gE - 2.0 * gV * m;           // Ezz entries (A1, f0), (A2, f1)
+    const double s24 = 2.0 * gV * f0, s35 = 2.0 * gV * f1, s44 = 2.0 * gV * B1, s55 = 2.0 * gV * B2;
+    double gr[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) gr[k] = s55 * r[k];
 #pragma unroll
     for (int k = 0; k < 6; ++k)
 #pragma unroll
         for (int l = k; l < 6; ++l) {
-            double v = Lzz[5][5] * r[k] * r[l];
-            if (k < 2) v += Lzz[4][5] * g0[k] * r[l];
+            double a = acc[(UA_HH + tri6(k, l)) * S];
+            a = fma(ey[k], by[l], a);
+            a = fma(by[k], ey[l], a);
+            a = fma(gr[k], r[l], a);
             if (l < 2) {
-                v += Lzz[4][5] * r[k] * g0[l];
-                v += Lz[4] * h0[k + l] + Lzz[4][4] * g0[k] * g0[l];
+                a = fma(s44 * g0[k], g0[l], a);
+                a = fma(Lz[4], h0[k + l], a);              // h0 packed xx, xy, yy
             }
-            acc[(UA_HH + tri6(k, l)) * S] += v;
+            acc[(UA_HH + tri6(k, l)) * S] = a;
         }
+    acc[(UA_CC + tri4(0, 0)) * S] += 2.0 * f0 * b[0];
+    acc[(UA_CC + tri4(0, 1)) * S] += fma(f0, b[1], f1 * b[0]);
+    acc[(UA_CC + tri4(0, 2)) * S] += f0 * b[2];
+    acc[(UA_CC + tri4(0, 3)) * S] += f0 * b[3];
+    acc[(UA_CC + tri4(1, 1)) * S] += 2.0 * f1 * b[1];
+    acc[(UA_CC + tri4(1, 2)) * S] += f1 * b[2];
+    acc[(UA_CC + tri4(1, 3)) * S] += f1 * b[3];
 #pragma unroll
-    for (int c = 0; c < 2; ++c)
-#pragma unroll
-        for (int d = c; d < 4; ++d) acc[(UA_CC + tri4(c, d)) * S] += Lzz[c][d];
-#pragma unroll
-    for (int c = 0; c < 4; ++c)
-#pragma unroll
-        for (int k = 0; k < 6; ++k) {
-            double v = Lzz[c][5] * r[k];
-            if (k < 2) v += Lzz[c][4] * g0[k];
-            acc[(UA_CR + c * 6 + k) * S] += v;
+    for (int k = 0; k < 6; ++k) {
+        double c0 = acc[(UA_CR + 0 * 6 + k) * S], c1 = acc[(UA_CR + 1 * 6 + k) * S];
+        double c2 = acc[(UA_CR + 2 * 6 + k) * S], c3 = acc[(UA_CR + 3 * 6 + k) * S];
+        c0 = fma(f0, by[k], c0);
+        c0 = fma(b[0], ey[k], c0);
+        c1 = fma(f1, by[k], c1);
+        c1 = fma(b[1], ey[k], c1);
+        c1 = fma(sig, r[k], c1);
+        c2 = fma(b[2], ey[k], c2);
+        c3 = fma(b[3], ey[k], c3);
+        c3 = fma(s35, r[k], c3);
+        if (k < 2) {
+            c0 = fma(sig, g0[k], c0);
+            c2 = fma(s24, g0[k], c2);
         }
+        acc[(UA_CR + 0 * 6 + k) * S] = c0;
+        acc[(UA_CR + 1 * 6 + k) * S] = c1;
+        acc[(UA_CR + 2 * 6 + k) * S] = c2;
+        acc[(UA_CR + 3 * 6 + k) * S] = c3;
+    }
     return Lz[5];
 }
 
@@ -175,32 +223,46 @@ __device__ __forceinline__ void unit_moments_to_sums(double l11, double l12, dou
 #include "hess_moments.inc"
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(UNIT_THREADS, CELESTE_UNIT_MINB)
-    unit_kernel(PlanDev plan, const UnitHdr* __restrict__ units, int n_units, int* __restrict__ queue,
-                double* __restrict__ scratch, long long scratch_stride, long long maxpix, const double* __restrict__ vp) {
-    constexpr int NUA = NUAcc<MODE>::value;
-    constexpr int NS = MODE == 0 ? 2 : 7;
-    constexpr int NACC = NAcc<MODE>::value;
+// Once per plan: the pixel records of every unit.  One block per unit.
+__global__ void unit_pack_kernel(PlanDev plan, const UnitHdr* __restrict__ units, int n_units, PixRec* __restrict__ out) {
+    const int u = blockIdx.x;
+    if (u >= n_units) return;
+    const UnitHdr uh = units[u];
+    const FieldDev field = plan.fields[uh.field];
+    const ImageDev img = field.images[uh.n];
+    const PatchDev& pa = field.patches[plan.src_row[uh.aslot] + (size_t)uh.n * field.S_tot];
+    const int H2 = pa.H2, W2 = pa.W2;
+    PixRec* dst = out + plan.l5_ptr[uh.pidx];
+    for (int i = threadIdx.x; i < H2 * W2; i += blockDim.x) {
+        const int h2 = i / W2, w2 = i - h2 * W2;
+        const size_t ipix = (size_t)(pa.off_h + h2) + (size_t)(pa.off_w + w2) * img.H;
+        PixRec r;
+        r.x = pa.bitmap[h2 + (size_t)w2 * H2] ? img.pixels[ipix] : nanf("");
+        r.sky = img.sky[ipix];
+        r.pixconst = img.pixconst[ipix];
+        dst[i] = r;
+    }
+}
+
+// Neighbouring sources (value only, elbo_objective.jl:38-40,69): E_bg += E_s, V_bg += E2_s - E_s^2 over the pixels a
+// neighbour shares with the active patch, one neighbour at a time in slot order (fixed summation order), into the
+// unit's (E_bg, V_bg) planes in plan.bg.  One warp per unit that has a neighbour; the walk is march_kernel's.
+__global__ void __launch_bounds__(UNIT_THREADS, CELESTE_UNIT_BG_MINB)
+    unit_bg_kernel(PlanDev plan, const UnitHdr* __restrict__ units, int n_units, int* __restrict__ queue,
+                   const double* __restrict__ vp, int nacc /* doubles per partial vector: NAcc<mode> */) {
     CEL_DYNAMIC_SMEM(smem);
     __shared__ double s_exptab[8];
-    __shared__ double s_logtab[256];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, kk = tid & 1;
-    double* wbase = smem + (size_t)warp * UnitWarpDoubles<MODE>::value;
-    double* acc = wbase + lane;                             // NUA x 32
-    double* s_rec = wbase + (size_t)NUA * 32;               // NC2 x MREC
-    double* s_si = s_rec + NC2 * MREC;                      // SU_STRIDE
-    UnitImg& mi = *reinterpret_cast<UnitImg*>(s_si + SU_STRIDE);
-    double* my_scratch = scratch + ((size_t)blockIdx.x * UNIT_WARPS + warp) * (size_t)scratch_stride;
+    (void)kk;
 #ifdef CELESTE_HOST_EMULATION
     if (tid < 8) s_exptab[tid] = h_exptab[tid];
-    for (int i = tid; i < 256; i += UNIT_THREADS) s_logtab[i] = h_logtab[i];
 #else
     if (tid < 8) s_exptab[tid] = c_exptab[tid];
-    for (int i = tid; i < 256; i += UNIT_THREADS) s_logtab[i] = g_logtab[i];
 #endif
+    double* wbase = smem + (size_t)warp * (NC2 * MREC + SU_STRIDE);
+    double* s_rec = wbase;
+    double* s_si = s_rec + NC2 * MREC;
     __syncthreads();
-
     for (;;) {
         int u = 0;
         if (lane == 0) u = atomicAdd(queue, 1);
@@ -213,34 +275,15 @@ __global__ void __launch_bounds__(UNIT_THREADS, CELESTE_UNIT_MINB)
         const PatchDev* prow = field.patches + (size_t)n * field.S_tot;       // patches of image n, by source row
         const PatchDev& pa = prow[plan.src_row[aslot]];
         const int band0 = field.images[n].band - 1;
-        __syncwarp();                                       // the previous unit's shared data is consumed
-#pragma unroll
-        for (int a = 0; a < NUA; ++a) acc[a * 32] = 0.0;
-        if (lane == 30) {
-            const ImageDev& img = field.images[n];
-            mi.pixels = img.pixels;
-            mi.sky = img.sky;
-            mi.pixconst = img.pixconst;
-            mi.iota = img.iota;
-            mi.bitmap = pa.bitmap;
-            mi.coefs = pa.coefs;
-            mi.scratch = my_scratch;
-            mi.H2 = pa.H2;
-            mi.W2 = pa.W2;
-            mi.off_h = pa.off_h;
-            mi.off_w = pa.off_w;
-            mi.imgH = img.H;
-            mi.n1 = pa.n1;
-            mi.n2 = pa.n2;
-            mi.band0 = band0;
-        }
-        double cnt_inactive = 0.0, cnt_active = 0.0, val = 0.0;
-
-        // ---- neighbours, one at a time in slot order: E_bg += E_s, V_bg += E2_s - E_s^2 over the shared pixels ----
-        if (uh.hasbg) {
+        if (!uh.hasbg) continue;
+        double* my_scratch = plan.bg + plan.bg_ptr[uh.pidx];
+        const float* img_pixels = field.images[n].pixels;
+        const int img_H = field.images[n].H;
+        double cnt_inactive = 0.0;
+        {
             {
                 const int tot = 2 * pa.H2 * pa.W2;
-                for (int i = lane; i < tot; i += 32) my_scratch[i] = 0.0;
+                for (int i = lane; i < tot; i += 32) my_scratch[i] = 0.0;       // (E_bg, V_bg) pairs, row-major
             }
             for (int s = uh.slot0; s < uh.slot1; ++s) {
                 if (s == aslot) continue;
@@ -273,7 +316,7 @@ __global__ void __launch_bounds__(UNIT_THREADS, CELESTE_UNIT_MINB)
                     const int nit = warp_max_int((len + 1) >> 1);
                     if (nit == 0) continue;
                     const int h = h_lo + row, w0 = w_lo + c0;       // 1-based image coordinates
-                    const int aH2 = pa.H2, aW2 = pa.W2, nH2 = p.H2, imgH = mi.imgH, n1 = p.n1, n2 = p.n2;
+                    const int aH2 = pa.H2, aW2 = pa.W2, nH2 = p.H2, imgH = img_H, n1 = p.n1, n2 = p.n2;
                     const double* coefs = p.coefs;
                     const double* si = s_si;
                     const double* recs = s_rec + kk * MREC;          // this lane's PSF component
@@ -294,9 +337,8 @@ __global__ void __launch_bounds__(UNIT_THREADS, CELESTE_UNIT_MINB)
                     const int acol = w0 - pa.off_w - 1 + kk, ncol = w0 - p.off_w - 1 + kk;      // own first column, 0-based
                     const uint8_t* abit = pa.bitmap + ah2 + (size_t)acol * aH2;
                     const uint8_t* nbit = p.bitmap + nh2 + (size_t)ncol * nH2;
-                    const float* px = mi.pixels + (size_t)(h - 1) + (size_t)(w0 - 1 + kk) * imgH;
-                    double* bgE = my_scratch + ah2 + (size_t)acol * aH2;
-                    const size_t bgplane = (size_t)aH2 * aW2;
+                    const float* px = img_pixels + (size_t)(h - 1) + (size_t)(w0 - 1 + kk) * imgH;
+                    double* bgE = my_scratch + 2 * ((size_t)ah2 * aW2 + acol);
                     const double theta = si[SI_THETA];
                     int t = 0;
                     while (t < nit) {
@@ -346,13 +388,13 @@ __global__ void __launch_bounds__(UNIT_THREADS, CELESTE_UNIT_MINB)
                                 const double Es = si[SI_CB] * f0 + si[SI_CB + 1] * f1;
                                 const double E2s = si[SI_CB + 2] * f0 * f0 + si[SI_CB + 3] * f1 * f1;
                                 bgE[0] += Es;
-                                bgE[bgplane] += E2s - Es * Es;
+                                bgE[1] += E2s - Es * Es;
                                 cnt_inactive += 1.0;                                          // elbo_objective.jl:353-357
                             }
                             abit += 2 * aH2;
                             nbit += 2 * nH2;
                             px += 2 * imgH;
-                            bgE += 2 * aH2;
+                            bgE += 4;
                             R0 = R2;
                             R1 = R3;
                         }
@@ -360,7 +402,71 @@ __global__ void __launch_bounds__(UNIT_THREADS, CELESTE_UNIT_MINB)
                 }
             }
         }
-        __syncwarp();          // every neighbour's sums are visible to the walk of the active source; s_rec is free
+        for (int o = 16; o > 0; o >>= 1) cnt_inactive += __shfl_xor_sync(0xffffffffu, cnt_inactive, o);
+        if (lane == 0) plan.partials[(size_t)uh.pidx * nacc + ACC_CNT_INACTIVE] = cnt_inactive;
+        __syncwarp();
+    }
+}
+
+// Phase A: the active source of a unit, row walks by lane pairs (see the file header).
+template <int MODE>
+__global__ void __launch_bounds__(UNIT_THREADS, CELESTE_UNIT_MINB)
+    unit_walk_kernel(PlanDev plan, const UnitHdr* __restrict__ units, int n_units, int* __restrict__ queue,
+                     const double* __restrict__ vp) {
+    constexpr int NUA = NUAcc<MODE>::value;
+    constexpr int NS = MODE == 0 ? 2 : 7;
+    constexpr int NACC = NAcc<MODE>::value;
+    CEL_DYNAMIC_SMEM(smem);
+    __shared__ double s_exptab[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, kk = tid & 1;
+    (void)kk;
+#ifdef CELESTE_HOST_EMULATION
+    if (tid < 8) s_exptab[tid] = h_exptab[tid];
+#else
+    if (tid < 8) s_exptab[tid] = c_exptab[tid];
+#endif
+    __shared__ double s_logtab[256];
+    double* wbase = smem + (size_t)warp * UnitWarpDoubles<MODE>::value;
+    double* acc = wbase + lane;                             // NUA x 32
+    double* s_rec = wbase + (size_t)NUA * 32;               // NC2 x MREC
+    double* s_si = s_rec + NC2 * MREC;                      // SU_STRIDE
+    UnitImg& mi = *reinterpret_cast<UnitImg*>(s_si + SU_STRIDE);
+#ifdef CELESTE_HOST_EMULATION
+    for (int i = tid; i < 256; i += UNIT_THREADS) s_logtab[i] = h_logtab[i];
+#else
+    for (int i = tid; i < 256; i += UNIT_THREADS) s_logtab[i] = g_logtab[i];
+#endif
+    __syncthreads();
+    for (;;) {
+        int u = 0;
+        if (lane == 0) u = atomicAdd(queue, 1);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= n_units) break;
+        const UnitHdr uh = units[u];
+        if (plan.task_mask && !plan.task_mask[uh.task]) continue;
+        const FieldDev field = plan.fields[uh.field];
+        const int n = uh.n, aslot = uh.aslot;
+        const PatchDev* prow = field.patches + (size_t)n * field.S_tot;       // patches of image n, by source row
+        const PatchDev& pa = prow[plan.src_row[aslot]];
+        const int band0 = field.images[n].band - 1;
+        __syncwarp();                                       // the previous unit's shared data is consumed
+#pragma unroll
+        for (int a = 0; a < NUA; ++a) acc[a * 32] = 0.0;
+        if (lane == 30) {
+            mi.pix = plan.pix + plan.l5_ptr[uh.pidx];
+            mi.iota = field.images[n].iota;
+            mi.coefs = pa.coefs;
+            mi.bg = uh.hasbg ? plan.bg + plan.bg_ptr[uh.pidx] : nullptr;
+            mi.H2 = pa.H2;
+            mi.W2 = pa.W2;
+            mi.off_h = pa.off_h;
+            mi.off_w = pa.off_w;
+            mi.n1 = pa.n1;
+            mi.n2 = pa.n2;
+            mi.band0 = band0;
+            mi.pad = 0;
+        }
+        double cnt_active = 0.0, val = 0.0;
         if (lane < NC2) {
             const double* vs = vp + (size_t)NPARAM * aslot;
             double xx[3];
@@ -375,7 +481,7 @@ __global__ void __launch_bounds__(UNIT_THREADS, CELESTE_UNIT_MINB)
         const int nseg = uh.nseg;
         const int total = (mi.H2 > 0 && W2 > 0) ? mi.H2 * nseg : 0;
         const int segw = (W2 + nseg - 1) / nseg;
-        double* l5plane = my_scratch + 2 * maxpix;
+        double* l5plane = MODE >= 2 ? plan.l5 + plan.l5_ptr[uh.pidx] : nullptr;
         for (int ub = 0; ub < total; ub += NPW) {                      // warp-uniform
             const int uu = ub + (lane >> 1);
             const bool has = uu < total;
@@ -421,8 +527,8 @@ __global__ void __launch_bounds__(UNIT_THREADS, CELESTE_UNIT_MINB)
                     }
                 }
             }
-            int pix = h2 + (c0 + kk) * H2c;                           // own pixel inside the patch
-            int ipix = (h - 1) + (w0 - 1 + kk) * mi.imgH;             // ... and inside the image
+            int pix = h2 * W2 + c0 + kk;                              // own pixel inside the patch (walk order)
+            const double iota_h = has ? (double)mi.iota[h - 1] : 0.0; // nelec_per_nmgy of this row
 
             int t = 0;
             while (t < nit) {
@@ -433,10 +539,7 @@ __global__ void __launch_bounds__(UNIT_THREADS, CELESTE_UNIT_MINB)
                     const int iown = 2 * t + kk;
                     const bool own = iown < len;
                     if (own) {
-                        CEL_PREFETCH_L1(mi.pixels + ipix);
-                        CEL_PREFETCH_L1(mi.sky + ipix);
-                        CEL_PREFETCH_L1(mi.pixconst + ipix);
-                        CEL_PREFETCH_L1(mi.bitmap + pix);
+                        CEL_PREFETCH_L1(mi.pix + pix + 2);                 // the pair's next two records share a sector
                         if (fast) {
                             CEL_PREFETCH_L1(mi.coefs + coff);
                             CEL_PREFETCH_L1(mi.coefs + coff + mi.n1 + 3);
@@ -484,18 +587,17 @@ __global__ void __launch_bounds__(UNIT_THREADS, CELESTE_UNIT_MINB)
                     for (int q = 0; q < NS; ++q)
                         T[q] = (kk == 0 ? S[0][q] : S[1][q]) + __shfl_xor_sync(0xffffffffu, kk == 0 ? S[1][q] : S[0][q], 1);
 
-                    unsigned char bit = 0;
-                    float xf = 0.f, skyf = 0.f;
+                    float xf = nanf(""), skyf = 0.f;
                     double pconst = 0.0, bE = 0.0, bV = 0.0;
                     double f0 = 0.0, g0[2] = {0.0, 0.0}, h0[3] = {0.0, 0.0, 0.0};
                     if (own) {
-                        bit = mi.bitmap[pix];
-                        xf = mi.pixels[ipix];
-                        skyf = mi.sky[ipix];
-                        pconst = mi.pixconst[ipix];
-                        if (uh.hasbg) {
-                            bE = mi.scratch[pix];
-                            bV = mi.scratch[pix + H2c * W2];
+                        const PixRec pr = mi.pix[pix];
+                        xf = pr.x;
+                        skyf = pr.sky;
+                        pconst = pr.pixconst;
+                        if (mi.bg) {
+                            bE = mi.bg[2 * pix];
+                            bV = mi.bg[2 * pix + 1];
                         }
                         if (fast) {
                             const double* ccol = mi.coefs + coff;
@@ -549,10 +651,10 @@ __global__ void __launch_bounds__(UNIT_THREADS, CELESTE_UNIT_MINB)
                         }
                     }
                     double l5 = 0.0;
-                    if (own && bit && !isnan(xf)) {                          // elbo_objective.jl:445, :459
+                    if (!isnan(xf)) {                                        // active and not masked (elbo_objective.jl:445, :459)
                         PixelConsts pc;
                         pc.x = (double)xf;
-                        pc.iota = (double)mi.iota[h - 1];
+                        pc.iota = iota_h;
                         pc.pixconst = pconst;
                         const bool covered = iown < ncov;      // the last column of the patch is not covered by its own source (:349)
                         const double f1 = theta * T[0] + (1.0 - theta) * T[1];
@@ -575,129 +677,12 @@ __global__ void __launch_bounds__(UNIT_THREADS, CELESTE_UNIT_MINB)
                         l5 = unit_pixel_term<MODE>(acc, pc, (double)skyf + bE, bV, covered, cb, f0, g0, h0, f1, r, val, s_logtab);
                     }
                     if (MODE >= 2 && own) l5plane[pix] = l5;
-                    pix += 2 * H2c;
-                    ipix += 2 * mi.imgH;
+                    pix += 2;
                     coff += 2 * mi.n1;
                 }
             }
         }
 
-        // ---- phase B: L5-weighted moments, one lane per component --------------------------------------------------
-        if (MODE >= 2) {
-            __syncwarp();                                            // the L5 plane is complete
-            double OUT[20];
-#pragma unroll
-            for (int q = 0; q < 20; ++q) OUT[q] = 0.0;
-            const int ncols = W2 - 1;                                // covered columns (:349)
-            if (lane < NC2 && mi.H2 > 0 && ncols > 0) {
-                const double* o = s_rec + lane * MREC;
-                const double l11 = o[0], l12 = o[1], l22 = o[2], cc = o[3], mu1 = o[4], mu2 = o[5], z = o[6];
-                double Dm[15];
-#pragma unroll
-                for (int q = 0; q < 15; ++q) Dm[q] = 0.0;
-                const int nsb = (ncols + MARCH_MAXSEG - 1) / MARCH_MAXSEG;
-                const int sw = (ncols + nsb - 1) / nsb;
-                for (int h2 = 0; h2 < mi.H2; ++h2) {
-                    const double d1 = (double)(mi.off_h + h2 + 1) - mu1;
-                    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0;
-                    for (int c0 = 0; c0 < ncols; c0 += sw) {
-                        const int c1 = min(c0 + sw, ncols);
-                        int c = c0;
-                        while (c < c1) {
-                            // exact (re)start of the recurrence at column c (the rule of march_start)
-                            double d2 = (double)(mi.off_w + c + 1) - mu2;
-                            const double p1 = l11 * d1 + l12 * d2;
-                            const double p2 = l12 * d1 + l22 * d2;
-                            const double q = d1 * p1 + d2 * p2;
-                            const double ra = -(p2 + 0.5 * l22);
-                            const bool sleep = q > MARCH_Q_SLEEP || ra > 700.0;
-                            double f = sleep ? 0.0 : z * exp_scaled_tab(q, -0.5, s_exptab);
-                            double r = sleep ? 0.0 : exp_scaled_tab(fmin(ra, 700.0), 1.0, s_exptab);
-                            const int cend = sleep ? min(c1, c + MARCH_CAREFUL_COLS) : c1;
-                            const double* lp = l5plane + h2 + (size_t)c * H2c;
-                            for (; c < cend; ++c) {
-                                const double v = f * *lp;
-                                const double v1 = v * d2;
-                                s0 += v;
-                                const double v2 = v1 * d2;
-                                s1 += v1;
-                                const double v3 = v2 * d2;
-                                s2 += v2;
-                                s3 += v3;
-                                s4 = fma(v3, d2, s4);
-                                f *= r;
-                                r *= cc;
-                                d2 += 1.0;
-                                lp += H2c;
-                            }
-                        }
-                    }
-                    // D[a][b] += d1^a s_b; index order 00 01 02 03 04 | 10 11 12 13 | 20 21 22 | 30 31 | 40
-                    const double e1 = d1, e2 = d1 * d1, e3 = e2 * d1, e4 = e2 * e2;
-                    Dm[0] += s0;
-                    Dm[1] += s1;
-                    Dm[2] += s2;
-                    Dm[3] += s3;
-                    Dm[4] += s4;
-                    Dm[5] = fma(e1, s0, Dm[5]);
-                    Dm[6] = fma(e1, s1, Dm[6]);
-                    Dm[7] = fma(e1, s2, Dm[7]);
-                    Dm[8] = fma(e1, s3, Dm[8]);
-                    Dm[9] = fma(e2, s0, Dm[9]);
-                    Dm[10] = fma(e2, s1, Dm[10]);
-                    Dm[11] = fma(e2, s2, Dm[11]);
-                    Dm[12] = fma(e3, s0, Dm[12]);
-                    Dm[13] = fma(e3, s1, Dm[13]);
-                    Dm[14] = fma(e4, s0, Dm[14]);
-                }
-                unit_moments_to_sums(l11, l12, l22, Dm, OUT);
-                // weights of the component: thc (u), thc nu (xs), thc nu^2 (ss), sg (tx), sg nu (ts)
-                const int j = lane >> 1;
-                const double theta = s_si[SI_THETA];
-                const double thc = j < NPROTO_DEV ? theta : 1.0 - theta;
-                const double sg = j < NPROTO_DEV ? 1.0 : -1.0;
-                const double nu = c_proto_nu[j];
-#pragma unroll
-                for (int q = 0; q < 3; ++q) OUT[q] *= thc;
-#pragma unroll
-                for (int q = 3; q < 9; ++q) OUT[q] *= thc * nu;
-#pragma unroll
-                for (int q = 9; q < 15; ++q) OUT[q] *= thc * nu * nu;
-#pragma unroll
-                for (int q = 15; q < 17; ++q) OUT[q] *= sg;
-#pragma unroll
-                for (int q = 17; q < 20; ++q) OUT[q] *= sg * nu;
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-                for (int q = 0; q < 20; ++q) OUT[q] += __shfl_xor_sync(0xffffffffu, OUT[q], o);
-            }
-            if (lane == 0) {
-                // R of GalRaw (elbo_math.cuh gal_eval): xx = (2 u1, u2, 2 u3); x-Sigma = xs; x-theta = -tx; Sigma-Sigma = ss;
-                // Sigma-theta = ts
-                acc[(UA_HH + tri6(0, 0)) * 32] += 2.0 * OUT[0];
-                acc[(UA_HH + tri6(0, 1)) * 32] += OUT[1];
-                acc[(UA_HH + tri6(1, 1)) * 32] += 2.0 * OUT[2];
-                acc[(UA_HH + tri6(0, 2)) * 32] += OUT[3];
-                acc[(UA_HH + tri6(0, 3)) * 32] += OUT[4];
-                acc[(UA_HH + tri6(0, 4)) * 32] += OUT[5];
-                acc[(UA_HH + tri6(1, 2)) * 32] += OUT[6];
-                acc[(UA_HH + tri6(1, 3)) * 32] += OUT[7];
-                acc[(UA_HH + tri6(1, 4)) * 32] += OUT[8];
-                acc[(UA_HH + tri6(2, 2)) * 32] += OUT[9];
-                acc[(UA_HH + tri6(2, 3)) * 32] += OUT[10];
-                acc[(UA_HH + tri6(2, 4)) * 32] += OUT[11];
-                acc[(UA_HH + tri6(3, 3)) * 32] += OUT[12];
-                acc[(UA_HH + tri6(3, 4)) * 32] += OUT[13];
-                acc[(UA_HH + tri6(4, 4)) * 32] += OUT[14];
-                acc[(UA_HH + tri6(0, 5)) * 32] -= OUT[15];
-                acc[(UA_HH + tri6(1, 5)) * 32] -= OUT[16];
-                acc[(UA_HH + tri6(2, 5)) * 32] += OUT[17];
-                acc[(UA_HH + tri6(3, 5)) * 32] += OUT[18];
-                acc[(UA_HH + tri6(4, 5)) * 32] += OUT[19];
-            }
-        }
         __syncwarp();
 
         // ---- fixed-order warp reduction -> the unit's partial vector -------------------------------------------------
@@ -706,12 +691,11 @@ __global__ void __launch_bounds__(UNIT_THREADS, CELESTE_UNIT_MINB)
         for (int o = 16; o > 0; o >>= 1) {
             val += __shfl_xor_sync(0xffffffffu, val, o);
             cnt_active += __shfl_xor_sync(0xffffffffu, cnt_active, o);
-            cnt_inactive += __shfl_xor_sync(0xffffffffu, cnt_inactive, o);
         }
         if (lane == 0) {
             out[ACC_VAL] = val;
             out[ACC_CNT_ACTIVE] = cnt_active;
-            out[ACC_CNT_INACTIVE] = cnt_inactive;
+            if (!uh.hasbg) out[ACC_CNT_INACTIVE] = 0.0;        // (units with neighbours: written by unit_bg_kernel)
         }
         if (MODE == 2 && lane < 3) out[ACC_CC + 7 + lane] = 0.0;
         for (int a = lane; a < NUA; a += 32) {
@@ -720,6 +704,150 @@ __global__ void __launch_bounds__(UNIT_THREADS, CELESTE_UNIT_MINB)
 #pragma unroll 8
             for (int i = 0; i < 32; ++i) s += row[(lane + i) & 31];
             out[unit_acc_index(a)] = s;
+        }
+    }
+}
+
+// Phase B + fold: L5-weighted moments of every component of the active source, one lane per component, then the
+// component's share of the 20 second-order mixture sums (hess_moments.inc), reduced over the warp and added to the
+// unit's HH sums in plan.partials (written by unit_walk_kernel<2> earlier on the stream).
+__global__ void __launch_bounds__(UNIT_THREADS, CELESTE_UNIT_MOM_MINB)
+    unit_moment_kernel(PlanDev plan, const UnitHdr* __restrict__ units, int n_units, int* __restrict__ queue,
+                       const double* __restrict__ vp) {
+    CEL_DYNAMIC_SMEM(smem);
+    __shared__ double s_exptab[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, kk = tid & 1;
+    (void)kk;
+#ifdef CELESTE_HOST_EMULATION
+    if (tid < 8) s_exptab[tid] = h_exptab[tid];
+#else
+    if (tid < 8) s_exptab[tid] = c_exptab[tid];
+#endif
+    double* s_rec = smem + (size_t)warp * (NC2 * MREC);
+    __syncthreads();
+    for (;;) {
+        int u = 0;
+        if (lane == 0) u = atomicAdd(queue, 1);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= n_units) break;
+        const UnitHdr uh = units[u];
+        if (plan.task_mask && !plan.task_mask[uh.task]) continue;
+        const FieldDev field = plan.fields[uh.field];
+        const int n = uh.n, aslot = uh.aslot;
+        const PatchDev* prow = field.patches + (size_t)n * field.S_tot;       // patches of image n, by source row
+        const PatchDev& pa = prow[plan.src_row[aslot]];
+        const int band0 = field.images[n].band - 1;
+        const int H2 = pa.H2, W2 = pa.W2, off_h = pa.off_h, off_w = pa.off_w;
+        if (H2 <= 0 || W2 <= 1) continue;                    // no covered pixel: nothing to add
+        __syncwarp();
+        const double* vs = vp + (size_t)NPARAM * aslot;
+        if (lane < NC2) {
+            double xx[3];
+            galaxy_xixi(vs[3], vs[4], vs[5], xx[0], xx[1], xx[2]);
+            march_make_record(pa, vs, xx, s_rec, lane);
+        }
+        __syncwarp();
+        const double* l5plane = plan.l5 + plan.l5_ptr[uh.pidx];
+        double OUT[20];
+#pragma unroll
+        for (int q = 0; q < 20; ++q) OUT[q] = 0.0;
+        const int ncols = W2 - 1;                                // covered columns (:349)
+        if (lane < NC2 && ncols > 0) {
+            const double* o = s_rec + lane * MREC;
+            const double l11 = o[0], l12 = o[1], l22 = o[2], cc = o[3], mu1 = o[4], mu2 = o[5], z = o[6];
+            double Dm[15];
+#pragma unroll
+            for (int q = 0; q < 15; ++q) Dm[q] = 0.0;
+            const int nsb = (ncols + MARCH_MAXSEG - 1) / MARCH_MAXSEG;
+            const int sw = (ncols + nsb - 1) / nsb;
+            for (int h2 = 0; h2 < H2; ++h2) {
+                const double d1 = (double)(off_h + h2 + 1) - mu1;
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0;
+                for (int c0 = 0; c0 < ncols; c0 += sw) {
+                    const int c1 = min(c0 + sw, ncols);
+                    int c = c0;
+                    while (c < c1) {
+                        // exact (re)start of the recurrence at column c (the rule of march_start)
+                        double d2 = (double)(off_w + c + 1) - mu2;
+                        const double p1 = l11 * d1 + l12 * d2;
+                        const double p2 = l12 * d1 + l22 * d2;
+                        const double q = d1 * p1 + d2 * p2;
+                        const double ra = -(p2 + 0.5 * l22);
+                        const bool sleep = q > MARCH_Q_SLEEP || ra > 700.0;
+                        double f = sleep ? 0.0 : z * exp_scaled_tab(q, -0.5, s_exptab);
+                        double r = sleep ? 0.0 : exp_scaled_tab(fmin(ra, 700.0), 1.0, s_exptab);
+                        const int cend = sleep ? min(c1, c + MARCH_CAREFUL_COLS) : c1;
+                        const double* lp = l5plane + (size_t)h2 * W2 + c;
+                        for (; c < cend; ++c) {
+                            const double v = f * *lp;
+                            const double v1 = v * d2;
+                            s0 += v;
+                            const double v2 = v1 * d2;
+                            s1 += v1;
+                            const double v3 = v2 * d2;
+                            s2 += v2;
+                            s3 += v3;
+                            s4 = fma(v3, d2, s4);
+                            f *= r;
+                            r *= cc;
+                            d2 += 1.0;
+                            lp += 1;
+                        }
+                    }
+                }
+                // D[a][b] += d1^a s_b; index order 00 01 02 03 04 | 10 11 12 13 | 20 21 22 | 30 31 | 40
+                const double e1 = d1, e2 = d1 * d1, e3 = e2 * d1, e4 = e2 * e2;
+                Dm[0] += s0;
+                Dm[1] += s1;
+                Dm[2] += s2;
+                Dm[3] += s3;
+                Dm[4] += s4;
+                Dm[5] = fma(e1, s0, Dm[5]);
+                Dm[6] = fma(e1, s1, Dm[6]);
+                Dm[7] = fma(e1, s2, Dm[7]);
+                Dm[8] = fma(e1, s3, Dm[8]);
+                Dm[9] = fma(e2, s0, Dm[9]);
+                Dm[10] = fma(e2, s1, Dm[10]);
+                Dm[11] = fma(e2, s2, Dm[11]);
+                Dm[12] = fma(e3, s0, Dm[12]);
+                Dm[13] = fma(e3, s1, Dm[13]);
+                Dm[14] = fma(e4, s0, Dm[14]);
+            }
+            unit_moments_to_sums(l11, l12, l22, Dm, OUT);
+            // weights of the component: thc (u), thc nu (xs), thc nu^2 (ss), sg (tx), sg nu (ts)
+            const int j = lane >> 1;
+            const double theta = vs[2];
+            const double thc = j < NPROTO_DEV ? theta : 1.0 - theta;
+            const double sg = j < NPROTO_DEV ? 1.0 : -1.0;
+            const double nu = c_proto_nu[j];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) OUT[q] *= thc;
+#pragma unroll
+            for (int q = 3; q < 9; ++q) OUT[q] *= thc * nu;
+#pragma unroll
+            for (int q = 9; q < 15; ++q) OUT[q] *= thc * nu * nu;
+#pragma unroll
+            for (int q = 15; q < 17; ++q) OUT[q] *= sg;
+#pragma unroll
+            for (int q = 17; q < 20; ++q) OUT[q] *= sg * nu;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int q = 0; q < 20; ++q) OUT[q] += __shfl_xor_sync(0xffffffffu, OUT[q], o);
+        }
+        if (lane < 20) {
+            // R of GalRaw (elbo_math.cuh gal_eval): xx = (2 u1, u2, 2 u3); x-Sigma = xs; x-theta = -tx; Sigma-Sigma = ss;
+            // Sigma-theta = ts.  Lane q owns sum q (every lane holds all 20 totals after the butterfly).
+            double mine = 0.0;
+#pragma unroll
+            for (int q = 0; q < 20; ++q)
+                if (lane == q) mine = OUT[q];
+            const int kq[20] = {0, 0, 1, 0, 0, 0, 1, 1, 1, 2, 2, 2, 3, 3, 4, 0, 1, 2, 3, 4};
+            const int lq[20] = {0, 1, 1, 2, 3, 4, 2, 3, 4, 2, 3, 4, 3, 4, 4, 5, 5, 5, 5, 5};
+            const double wq = (lane == 0 || lane == 2) ? 2.0 : ((lane == 15 || lane == 16) ? -1.0 : 1.0);
+            double* out = plan.partials + (size_t)uh.pidx * NACC_MODE2 + ACC_HH + tri6(kq[lane], lq[lane]);
+            *out += wq * mine;
         }
     }
 }
@@ -762,7 +890,7 @@ inline void build_unit_list(int n_subs, int N, const int* sub_task, const int* s
                         const int w_lo = std::max(ow, pw) + 1, w_hi = std::min(ow + W2, pw + pW2 - 1);
                         if (h_hi >= h_lo && w_hi >= w_lo) {
                             uh.hasbg = 1;
-                            c += (long)(h_hi - h_lo + 1) * (w_hi - w_lo + 1);
+                            uh.nbpix += (h_hi - h_lo + 1) * (w_hi - w_lo + 1);
                         }
                     }
                 }

@@ -59,15 +59,42 @@ void run_unit(PlanDev pd, const FieldDev& fd, const double* vp, double* v, doubl
                     units, maxpix);
     const int grid = 2;
     std::vector<double> part((size_t)pd.n_subs * pd.N * NAcc<MODE>::value + 1, 1e300);   // poisoned
-    std::vector<double> scratch((size_t)grid * UNIT_WARPS * 3 * maxpix + 1, 1e300);
+    std::vector<UnitHdr> ub;
+    for (const UnitHdr& x : units)
+        if (x.hasbg) ub.push_back(x);
+    std::vector<long long> bg_ptr((size_t)pd.n_subs * pd.N, -1), l5_ptr((size_t)pd.n_subs * pd.N, 0);
+    long long bg_total = 0, l5_total = 0;
+    for (int u = 0; u < pd.n_subs; ++u)
+        for (int n = 0; n < pd.N; ++n) {
+            const PatchDev& pa = fd.patches[(size_t)pd.src_row[pd.sub_slot[u]] + (size_t)n * fd.S_tot];
+            const long long px = (long long)std::max(pa.H2, 0) * std::max(pa.W2, 0);
+            bg_ptr[(size_t)u * pd.N + n] = bg_total;
+            bg_total += 2 * px;
+            l5_ptr[(size_t)u * pd.N + n] = l5_total;
+            l5_total += px;
+        }
+    std::vector<double> bg((size_t)bg_total + 1, 1e300), l5((size_t)l5_total + 1, 1e300);   // poisoned
     std::vector<int> cp((size_t)pd.n_subs * pd.N + 1);
     for (size_t i = 0; i < cp.size(); ++i) cp[i] = (int)i;
     pd.partials = part.data();
     pd.chunk_ptr = cp.data();
-    int queue = 0;
-    cuda_emul::launch(setup_kernel, 2, 64, 0, pd, vp);
-    cuda_emul::launch(unit_kernel<MODE>, grid, UNIT_THREADS, unit_smem_bytes<MODE>(), pd, (const UnitHdr*)units.data(),
-                      (int)units.size(), &queue, scratch.data(), (long long)(3 * maxpix), maxpix, vp);
+    pd.bg_ptr = bg_ptr.data();
+    pd.bg = bg.data();
+    std::vector<PixRec> pix((size_t)l5_total + 1);
+    pd.l5_ptr = l5_ptr.data();
+    pd.l5 = l5.data();
+    pd.pix = pix.data();
+    if (!units.empty()) cuda_emul::launch(unit_pack_kernel, (int)units.size(), 32, 0, pd, (const UnitHdr*)units.data(), (int)units.size(), pix.data());
+    int queue[4] = {0, 0, 0, 0};
+    if (MODE >= 1) cuda_emul::launch(slotbr_kernel, 1, std::max(pd.n_subs, 1), 0, pd, vp);
+    if (!ub.empty())
+        cuda_emul::launch(unit_bg_kernel, grid, UNIT_THREADS, unit_bg_smem_bytes(), pd, (const UnitHdr*)ub.data(), (int)ub.size(),
+                          &queue[0], vp, (int)NAcc<MODE>::value);
+    cuda_emul::launch(unit_walk_kernel<MODE>, grid, UNIT_THREADS, unit_smem_bytes<MODE>(), pd, (const UnitHdr*)units.data(),
+                      (int)units.size(), &queue[1], vp);
+    if (MODE == 2)
+        cuda_emul::launch(unit_moment_kernel, grid, UNIT_THREADS, unit_moment_smem_bytes(), pd, (const UnitHdr*)units.data(),
+                          (int)units.size(), &queue[2], vp);
     cuda_emul::launch(epilogue_kernel<MODE>, pd.n_tasks, EPI_THREADS, 0, pd, vp, v, d, h, counters, flags);
 }
 

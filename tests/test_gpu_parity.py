@@ -151,7 +151,7 @@ def test_plan_device_path_matches_host_path(cj):
     s.synchronize()
     assert np.array_equal(v.cpu().numpy(), host["v"]) and np.array_equal(d.cpu().numpy(), host["d"])
     assert np.array_equal(h.cpu().numpy(), host["h"]) and np.array_equal(cnt.cpu().numpy(), host["counters"])
-    assert plan.launches(2) == 3 and plan.kernel_name(2) == "unit_kernel"
+    assert plan.launches(2) == 5 and plan.kernel_name(2) == "unit_kernel"      # slotbr, bg, walk, moment, epilogue
 
 
 def test_multi_field_plan_equals_per_field_plans(cj):

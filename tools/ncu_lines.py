@@ -6,8 +6,10 @@ from collections import defaultdict
 
 f = sys.argv[1]
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-out = subprocess.run(["ncu", "-i", f, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True,
-                     text=True).stdout
+import os
+extra = os.environ.get("NCU_ARGS", "").split()        # e.g. NCU_ARGS="-k regex:unit_walk"
+out = subprocess.run(["ncu", "-i", f] + extra + ["--page", "source", "--csv", "--print-source", "cuda,sass"],
+                     capture_output=True, text=True).stdout
 cur_file, hdr, rows = None, None, []
 agg = defaultdict(lambda: [0, 0, 0, ""])   # samples, inst, thread inst, text
 for r in csv.reader(out.splitlines()):
