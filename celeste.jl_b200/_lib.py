@@ -67,7 +67,7 @@ EXPORTS = [
     "celeste_fp64_peak", "celeste_plan_enable_timing", "celeste_plan_kernel_times", "celeste_set_chunk_pixels",
     "celeste_plan_create_multi", "celeste_tr_subproblem", "celeste_plan_set_task_mask", "celeste_newton_step",
     "celeste_render_expectation", "celeste_patches_build", "celeste_patch_readback", "celeste_find_neighbors",
-    "celeste_plan_kernel_name",
+    "celeste_plan_kernel_name", "celeste_plan_unit_times", "celeste_plan_set_hessian_layout",
 ]
 
 
@@ -75,7 +75,7 @@ class celeste_newton_buffers(C.Structure):
     """include/celeste_cuda.h: device pointers of one batched Newton trust-region solve."""
     FIELDS = ["x", "f", "g", "H", "delta", "x_new", "m_pred", "interior", "active", "converged", "iters", "f_calls",
               "lo", "hi", "v", "d", "h", "flags", "vp_all", "aslot", "prior"]
-    _fields_ = [(name, C.c_void_p) for name in FIELDS]
+    _fields_ = [(name, C.c_void_p) for name in FIELDS] + [("h_layout", C.c_int64)]
 
 
 _lib = None
@@ -116,6 +116,8 @@ def load():
     lib.celeste_fp64_peak.argtypes = [C.POINTER(C.c_double), vp]
     lib.celeste_plan_enable_timing.argtypes = [vp, i32]
     lib.celeste_plan_kernel_times.argtypes = [vp, C.POINTER(C.c_float * 3)]
+    lib.celeste_plan_unit_times.argtypes = [vp, C.POINTER(C.c_float * 3)]
+    lib.celeste_plan_set_hessian_layout.argtypes = [vp, i32]
     lib.celeste_set_chunk_pixels.argtypes = [i32]
     lib.celeste_plan_set_task_mask.argtypes = [vp, vp]
     lib.celeste_tr_subproblem.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]

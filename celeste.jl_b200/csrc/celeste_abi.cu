@@ -191,6 +191,19 @@ struct celeste_field {
     DevBuf<double> double_pool;   // psf records + spline coefficient arrays
     unsigned long long patch_generation = 0;
     int uniform_K = 0;   // K shared by every patch (0: mixed) -> selects the K-specialised pixel kernel
+    // Plans of small celeste_elbo_batch / celeste_elbo_single calls, kept for the next call with the same task
+    // structure: ElboMaximize.evaluate! (ElboMaximize.jl:161-172) calls elbo once per Newton iterate with the same
+    // ElboArgs and a new vp, from every thread of the reference (one ElboArgs per thread, ParallelRun.jl:236-253).
+    struct CachedPlan {
+        std::vector<int32_t> key;
+        celeste_plan* plan = nullptr;
+        bool busy = false;
+        unsigned long long last_use = 0;
+    };
+    std::mutex cache_mu;
+    std::vector<CachedPlan> cache;
+    unsigned long long cache_clock = 0;
+    ~celeste_field();
 };
 
 struct celeste_plan {
@@ -219,7 +232,7 @@ struct celeste_plan {
     // unit_kernel (Hessian mode of the production shape; value / gradient with CELESTE_GRAD_KERNEL=unit): one warp per
     // (sub, image) unit pulled from a device-side queue
     DevBuf<UnitHdr> unitmap, unitmap_bg;   // every unit, heaviest first; the units with a neighbour, by shared pixels
-    DevBuf<int> unit_chunk_ptr;      // identity: one partial vector per (sub, image)
+    DevBuf<int> unit_chunk_ptr;      // the partial vectors (= units) of each (sub, image)
     DevBuf<int> unit_queue;          // one counter per kernel of the sequence
     DevBuf<long long> l5_ptr;
     DevBuf<double> l5;               // L5 = dL/df1 of every active pixel (phase A -> phase B)
@@ -240,12 +253,38 @@ struct celeste_plan {
     const unsigned char* task_mask = nullptr;   // device pointer owned by the caller
     bool timing = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_unit[2] = {nullptr, nullptr};   // after unit_bg_kernel, after unit_walk_kernel
+    bool unit_timed = false;
+    int hess_layout = CELESTE_HESS_DENSE;
+    // small plans (what celeste_elbo_single makes): all outputs in ONE device block mirrored by one pinned host block
+    // (a single D2H per call), and the kernel sequence of each mode captured once into a CUDA graph
+    DevBuf<unsigned char> out_block;
+    unsigned char* out_pin = nullptr;
+    double* vp_pin = nullptr;
+    cudaGraphExec_t graph[3] = {nullptr, nullptr, nullptr};
+    int graph_layout[3] = {-1, -1, -1};
+    void drop_graphs() {
+        for (auto& g : graph)
+            if (g) {
+                cudaGraphExecDestroy(g);
+                g = nullptr;
+            }
+    }
     ~celeste_plan() {
+        drop_graphs();
+        if (out_pin) cudaFreeHost(out_pin);
+        if (vp_pin) cudaFreeHost(vp_pin);
         if (stream) cudaStreamDestroy(stream);
         for (auto& e : ev)
             if (e) cudaEventDestroy(e);
+        for (auto& e : ev_unit)
+            if (e) cudaEventDestroy(e);
     }
 };
+
+celeste_field::~celeste_field() {
+    for (auto& c : cache) delete c.plan;
+}
 
 extern "C" {
 
@@ -762,20 +801,25 @@ int celeste_plan_create_multi(int32_t n_fields, celeste_field* const* fields, ce
         taskmap.swap(sorted);
     }
     pl->n_taskblocks = (int)taskmap.size();
-    // march_kernel serves the production shape (Sa = 1 everywhere, K = 2); CELESTE_GRAD_KERNEL=task keeps task_kernel
-    // (kernel-tuning / A-B knob)
+    // The production shape (Sa = 1 everywhere, K = 2: ParallelRun.jl:253,489, elbo_args.jl:197) is served by the unit
+    // kernels in every mode.  A/B knobs: CELESTE_GRAD_KERNEL=march (march_kernel) / =task (task_kernel) for the value
+    // and gradient modes, CELESTE_HESS_KERNEL=pixel (pixel_kernel<2>) for the Hessian mode.  Every other shape keeps
+    // task_kernel / pixel_kernel.
     {
-        const char* env = std::getenv("CELESTE_GRAD_KERNEL");
-        const bool want = !(env && std::strcmp(env, "task") == 0);
-        pl->use_march = want && pl->uniform_K == 2 && n_subs == n_tasks;
-        // march_kernel indexes pixels with 32-bit integers (registers are what limits it): larger images or patches
-        // keep task_kernel
-        for (int i = 0; i < n_fields && pl->use_march; ++i) {
+        bool shape_ok = pl->uniform_K == 2 && n_subs == n_tasks;
+        // the walk kernels index pixels with 32-bit integers (registers are what limits them)
+        for (int i = 0; i < n_fields && shape_ok; ++i) {
             for (const ImageDev& im : fields[i]->h_images)
-                if ((long long)im.H * im.W >= (1LL << 31)) pl->use_march = false;
+                if ((long long)im.H * im.W >= (1LL << 31)) shape_ok = false;
             for (const PatchDev& pa : fields[i]->h_patches)
-                if ((long long)pa.H2 * pa.W2 >= (1LL << 29)) pl->use_march = false;
+                if ((long long)pa.H2 * pa.W2 >= (1LL << 29)) shape_ok = false;
         }
+        const char* genv = std::getenv("CELESTE_GRAD_KERNEL");
+        const char* henv = std::getenv("CELESTE_HESS_KERNEL");
+        const bool g_march = genv && std::strcmp(genv, "march") == 0, g_task = genv && std::strcmp(genv, "task") == 0;
+        pl->use_march = shape_ok && g_march;
+        pl->use_unit_grad = shape_ok && !g_march && !g_task;
+        pl->use_unit_hess = shape_ok && !(henv && std::strcmp(henv, "pixel") == 0);
     }
     if (pl->use_march) {
         // A source normally gets ONE block (all its images: best packing of its rows into the block's walk slots).
@@ -813,6 +857,12 @@ int celeste_plan_create_multi(int32_t n_fields, celeste_field* const* fields, ce
                                W2 = pa.W2;
                            },
                            split, mm, part_ptr);
+        pl->n_marchblocks = (int)mm.size();
+        CUDA_TRY(pl->marchmap.upload(mm));
+        CUDA_TRY(pl->march_part_ptr.upload(part_ptr));
+    }
+    if (pl->use_march || pl->use_unit_grad || pl->use_unit_hess) {
+        // background planes (E_bg, V_bg) of every (sub, image) whose task has a neighbour
         std::vector<long long> bg_ptr((size_t)n_subs * pl->N, -1);
         long long bg_total = 0;
         for (int u = 0; u < n_subs; ++u) {
@@ -826,23 +876,17 @@ int celeste_plan_create_multi(int32_t n_fields, celeste_field* const* fields, ce
                 bg_total += 2LL * pa.H2 * pa.W2;
             }
         }
-        pl->n_marchblocks = (int)mm.size();
-        CUDA_TRY(pl->marchmap.upload(mm));
-        CUDA_TRY(pl->march_part_ptr.upload(part_ptr));
         CUDA_TRY(pl->bg_ptr.upload(bg_ptr));
         CUDA_TRY(pl->bg.alloc((size_t)bg_total));
     }
-    if (pl->use_march) {
-        // same shape condition as march_kernel; CELESTE_HESS_KERNEL=pixel keeps pixel_kernel<2> (A/B knob)
-        const char* henv = std::getenv("CELESTE_HESS_KERNEL");
-        pl->use_unit_hess = !(henv && std::strcmp(henv, "pixel") == 0);
-    }
-    {
-        const char* genv = std::getenv("CELESTE_GRAD_KERNEL");
-        pl->use_unit_grad = genv && std::strcmp(genv, "unit") == 0 && pl->uniform_K == 2 && n_subs == n_tasks;
-    }
     if (pl->use_unit_hess || pl->use_unit_grad) {
-        std::vector<UnitHdr> um;
+        std::vector<UnitHdr> um, ub;
+        std::vector<int> ucp;
+        cudaDeviceGetAttribute(&pl->sms, cudaDevAttrMultiProcessorCount, pl->device);
+        // small plans are cut finer: aim at ~2 units per resident warp (SMs x 3 blocks x 4 warps); CELESTE_UNIT_TARGET
+        // overrides (kernel-tuning knob)
+        long target = 2L * pl->sms * CELESTE_UNIT_MINB * UNIT_WARPS;
+        if (const char* env = std::getenv("CELESTE_UNIT_TARGET")) target = std::atol(env);
         build_unit_list(n_subs, pl->N, sub_task.data(), sub_slot.data(), task_ptr, tfield.data(),
                         [&](int slot, int n, int& oh, int& ow, int& H2, int& W2) {
                             const celeste_field* f = fields[sfield[slot]];
@@ -852,13 +896,8 @@ int celeste_plan_create_multi(int32_t n_fields, celeste_field* const* fields, ce
                             H2 = pa.H2;
                             W2 = pa.W2;
                         },
-                        um, pl->unit_maxpix);
+                        target, um, ub, ucp, pl->unit_maxpix);
         pl->n_units = (int)um.size();
-        cudaDeviceGetAttribute(&pl->sms, cudaDevAttrMultiProcessorCount, pl->device);
-        std::vector<UnitHdr> ub;
-        for (const UnitHdr& x : um)
-            if (x.hasbg) ub.push_back(x);
-        std::stable_sort(ub.begin(), ub.end(), [](const UnitHdr& a, const UnitHdr& b) { return a.nbpix > b.nbpix; });
         pl->n_units_bg = (int)ub.size();
         std::vector<long long> l5_ptr((size_t)n_subs * pl->N, 0);
         long long l5_total = 0;
@@ -870,11 +909,9 @@ int celeste_plan_create_multi(int32_t n_fields, celeste_field* const* fields, ce
                 l5_total += (long long)std::max(pa.H2, 0) * std::max(pa.W2, 0);
             }
         }
-        std::vector<int> ident((size_t)n_subs * pl->N + 1);
-        for (size_t i = 0; i < ident.size(); ++i) ident[i] = (int)i;
         CUDA_TRY(pl->unitmap.upload(um));
         CUDA_TRY(pl->unitmap_bg.upload(ub));
-        CUDA_TRY(pl->unit_chunk_ptr.upload(ident));
+        CUDA_TRY(pl->unit_chunk_ptr.upload(ucp));
         CUDA_TRY(pl->unit_queue.alloc(4));
         CUDA_TRY(pl->l5_ptr.upload(l5_ptr));
         CUDA_TRY(pl->l5.alloc(pl->use_unit_hess ? (size_t)l5_total : 0));
@@ -930,10 +967,40 @@ int celeste_set_chunk_pixels(int32_t chunk_pixels) {
 
 int celeste_plan_enable_timing(celeste_plan* p, int32_t on) {
     if (!p) return CELESTE_ERR_BAD_ARG;
-    if (on)
+    if (on) {
         for (auto& e : p->ev)
             if (!e) CUDA_TRY(cudaEventCreate(&e));
+        for (auto& e : p->ev_unit)
+            if (!e) CUDA_TRY(cudaEventCreate(&e));
+    }
     p->timing = on != 0;
+    return CELESTE_OK;
+}
+
+int celeste_plan_unit_times(celeste_plan* p, float ms[3]) {
+    if (!p || !ms || !p->timing) {
+        set_detail("plan_unit_times: timing not enabled");
+        return CELESTE_ERR_STATE;
+    }
+    ms[0] = ms[1] = ms[2] = 0.f;
+    if (!p->unit_timed) return CELESTE_OK;
+    CUDA_TRY(cudaEventSynchronize(p->ev[3]));
+    CUDA_TRY(cudaEventElapsedTime(&ms[0], p->ev[1], p->ev_unit[0]));
+    CUDA_TRY(cudaEventElapsedTime(&ms[1], p->ev_unit[0], p->ev_unit[1]));
+    CUDA_TRY(cudaEventElapsedTime(&ms[2], p->ev_unit[1], p->ev[2]));
+    return CELESTE_OK;
+}
+
+int celeste_plan_set_hessian_layout(celeste_plan* p, int32_t layout) {
+    if (!p || (layout != CELESTE_HESS_DENSE && layout != CELESTE_HESS_PACKED28)) {
+        set_detail("plan_set_hessian_layout: bad arguments (layout=%d)", layout);
+        return CELESTE_ERR_BAD_ARG;
+    }
+    if (layout == CELESTE_HESS_PACKED28 && p->n_subs != p->n_tasks) {
+        set_detail("plan_set_hessian_layout: the packed layout needs Sa = 1 in every task");
+        return CELESTE_ERR_UNSUPPORTED;
+    }
+    p->hess_layout = layout;      // (captured graphs carry their layout and are re-captured when it differs)
     return CELESTE_OK;
 }
 
@@ -1022,19 +1089,25 @@ static int launch_mode(celeste_plan* p, const double* vp_dev, double* v, double*
         if (p->n_units_bg > 0)
             unit_bg_kernel<<<grid_for(p->n_units_bg, CELESTE_UNIT_BG_MINB), UNIT_THREADS, unit_bg_smem_bytes(), st>>>(
                 pu, p->unitmap_bg.p, p->n_units_bg, p->unit_queue.p, vp_dev, NAcc<MODE>::value);
-        if (p->n_units > 0) {
+        if (p->timing) CUDA_TRY(cudaEventRecord(p->ev_unit[0], st));
+        if (p->n_units > 0)
             unit_walk_kernel<MODE><<<grid_for(p->n_units, CELESTE_UNIT_MINB), UNIT_THREADS, unit_smem_bytes<MODE>(), st>>>(
                 pu, p->unitmap.p, p->n_units, p->unit_queue.p + 1, vp_dev);
+        if (p->timing) CUDA_TRY(cudaEventRecord(p->ev_unit[1], st));
+        p->unit_timed = p->timing;
+        if (p->n_units > 0) {
             if (MODE == 2)
                 unit_moment_kernel<<<grid_for(p->n_units, CELESTE_UNIT_MOM_MINB), UNIT_THREADS, unit_moment_smem_bytes(), st>>>(
                     pu, p->unitmap.p, p->n_units, p->unit_queue.p + 2, vp_dev);
         }
         if (p->timing) CUDA_TRY(cudaEventRecord(p->ev[2], st));
-        epilogue_kernel<MODE><<<p->n_tasks, EPI_THREADS, 0, st>>>(pu, vp_dev, v, d, h, counters, flags);
+        epilogue_kernel<MODE><<<p->n_tasks, EPI_THREADS, 0, st>>>(pu, vp_dev, v, d, h, counters, flags,
+                                                                  p->hess_layout == CELESTE_HESS_PACKED28 ? 1 : 0);
         if (p->timing) CUDA_TRY(cudaEventRecord(p->ev[3], st));
         CUDA_TRY(cudaGetLastError());
         return CELESTE_OK;
     }
+    p->unit_timed = false;
     if constexpr (MODE <= 1) {
         if (p->use_march) {
             // value / gradient, production shape: row walks with the exp recurrence (march_kernels.cuh).  The blocks
@@ -1092,7 +1165,8 @@ static int launch_mode(celeste_plan* p, const double* vp_dev, double* v, double*
             pair_kernel<0><<<p->n_pairs * p->N, PAIR_THREADS, psm, st>>>(pd);
     }
     if (p->timing) CUDA_TRY(cudaEventRecord(p->ev[2], st));
-    epilogue_kernel<MODE><<<p->n_tasks, EPI_THREADS, 0, st>>>(pd, vp_dev, v, d, h, counters, flags);
+    epilogue_kernel<MODE><<<p->n_tasks, EPI_THREADS, 0, st>>>(pd, vp_dev, v, d, h, counters, flags,
+                                                              p->hess_layout == CELESTE_HESS_PACKED28 ? 1 : 0);
     if (p->timing) CUDA_TRY(cudaEventRecord(p->ev[3], st));
     CUDA_TRY(cudaGetLastError());
     return CELESTE_OK;
@@ -1122,6 +1196,73 @@ int celeste_elbo_plan_device(celeste_plan* p, const double* vp_dev, int32_t mode
     }
 }
 
+// Small plans: one H2D, one graph launch (the kernel sequence of `mode`, captured on first use), one D2H, one sync.
+static int plan_host_small(celeste_plan* p, const double* vp, int32_t mode, double* v, double* d, double* h,
+                           int64_t* counters, int32_t* flags, size_t nd, size_t nh) {
+    const size_t nt = p->n_tasks, nvp = (size_t)p->n_slots * NPARAM;
+    // block layout (8-byte aligned pieces): v | d | h | counters | flags
+    const size_t o_v = 0, o_d = o_v + nt * 8, o_h = o_d + nd * 8, o_c = o_h + nh * 8, o_f = o_c + 2 * nt * 8;
+    const size_t total = o_f + ((nt * 4 + 7) / 8) * 8;
+    if (p->out_block.n < total) {
+        p->drop_graphs();
+        CUDA_TRY(p->out_block.alloc(total));
+        if (p->out_pin) cudaFreeHost(p->out_pin);
+        p->out_pin = nullptr;
+        CUDA_TRY(cudaMallocHost((void**)&p->out_pin, total));
+    }
+    if (!p->vp_pin) CUDA_TRY(cudaMallocHost((void**)&p->vp_pin, nvp * sizeof(double)));
+    CUDA_TRY(p->vp_dev.ensure(nvp));
+    cudaStream_t st = p->stream;
+    unsigned char* ob = p->out_block.p;
+    std::memcpy(p->vp_pin, vp, nvp * sizeof(double));
+    CUDA_TRY(cudaMemcpyAsync(p->vp_dev.p, p->vp_pin, nvp * sizeof(double), cudaMemcpyHostToDevice, st));
+    const bool graphable = !p->timing && !p->task_mask && !p->need_pack;
+    if (graphable && p->graph[mode] && p->graph_layout[mode] == p->hess_layout) {
+        CUDA_TRY(cudaGraphLaunch(p->graph[mode], st));
+    } else {
+        const bool capture = graphable;
+        if (p->graph[mode]) {
+            cudaGraphExecDestroy(p->graph[mode]);
+            p->graph[mode] = nullptr;
+        }
+        if (capture) CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        int rc = celeste_elbo_plan_device(p, p->vp_dev.p, mode, (double*)(ob + o_v), (double*)(ob + o_d), (double*)(ob + o_h),
+                                          (int64_t*)(ob + o_c), (int32_t*)(ob + o_f), st);
+        if (capture) {
+            cudaGraph_t g = nullptr;
+            cudaError_t e = cudaStreamEndCapture(st, &g);
+            if (rc != CELESTE_OK || e != cudaSuccess || !g) {
+                if (g) cudaGraphDestroy(g);
+                if (rc != CELESTE_OK) return rc;
+                CUDA_TRY(e);
+            }
+            CUDA_TRY(cudaGraphInstantiate(&p->graph[mode], g, 0));
+            cudaGraphDestroy(g);
+            p->graph_layout[mode] = p->hess_layout;
+            CUDA_TRY(cudaGraphLaunch(p->graph[mode], st));
+        } else if (rc != CELESTE_OK) {
+            return rc;
+        }
+    }
+    CUDA_TRY(cudaMemcpyAsync(p->out_pin, ob, total, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    const unsigned char* op = p->out_pin;
+    std::memcpy(v, op + o_v, nt * 8);
+    if (mode >= 1) std::memcpy(d, op + o_d, nd * 8);
+    if (mode >= 2) std::memcpy(h, op + o_h, nh * 8);
+    if (counters) std::memcpy(counters, op + o_c, 2 * nt * 8);
+    const int* hf = reinterpret_cast<const int*>(op + o_f);
+    bool bad = false;
+    for (size_t t = 0; t < nt; ++t) {
+        if (flags) flags[t] = hf[t];
+        if (hf[t] & CELESTE_FLAG_NONFINITE) {
+            if (!bad) set_detail("task %zu: non-finite ELBO (assert_all_finite, elbo_args.jl:145)", t);
+            bad = true;
+        }
+    }
+    return bad ? CELESTE_ERR_NONFINITE : CELESTE_OK;
+}
+
 int celeste_elbo_plan_host(celeste_plan* p, const double* vp, int32_t mode, double* v, double* d, double* h,
                            int64_t* counters, int32_t* flags) {
     if (!p || !vp || !v || mode < 0 || mode > 2 || (mode >= 1 && !d) || (mode >= 2 && !h)) {
@@ -1132,11 +1273,14 @@ int celeste_elbo_plan_host(celeste_plan* p, const double* vp, int32_t mode, doub
     CUDA_TRY(cudaSetDevice(p->device));
     if (!p->stream) CUDA_TRY(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     const size_t nt = p->n_tasks;
+    const size_t nd = mode >= 1 ? (size_t)p->n_subs * NPARAM : 0;
+    const size_t nh = mode >= 2 ? (p->hess_layout == CELESTE_HESS_PACKED28 ? (size_t)p->n_tasks * HESS_PACKED_LEN : p->h_total) : 0;
+    if ((nt * 3 + nd + nh) * 8 + (size_t)p->n_slots * NPARAM * 8 <= (1u << 20))        // <= 1 MB moved per call
+        return plan_host_small(p, vp, mode, v, d, h, counters, flags, nd, nh);
     CUDA_TRY(p->vp_dev.ensure((size_t)p->n_slots * NPARAM));
     CUDA_TRY(p->v_dev.ensure(nt));
     CUDA_TRY(p->counters_dev.ensure(2 * nt));
     CUDA_TRY(p->flags_dev.ensure(nt));
-    const size_t nd = (size_t)p->n_subs * NPARAM, nh = p->h_total;
     if (mode >= 1) CUDA_TRY(p->d_dev.ensure(nd));
     if (mode >= 2) CUDA_TRY(p->h_dev.ensure(nh));
     cudaStream_t st = p->stream;
@@ -1167,11 +1311,93 @@ int celeste_elbo_batch(celeste_field* f, int32_t n_tasks, const int32_t* task_pt
                        const int32_t* active_ptr, const int32_t* active_idx, const double* vp, int32_t mode, double* v,
                        double* d, double* h, int64_t* counters, int32_t* flags) {
     if (n_tasks == 0) return CELESTE_OK;
+    if (!f || n_tasks < 0 || !task_ptr || !active_ptr) {
+        set_detail("elbo_batch: bad arguments");
+        return CELESTE_ERR_BAD_ARG;
+    }
+    // Small task lists keep their plan in the field (see celeste_field::CachedPlan): a repeated call with the same
+    // structure costs one H2D, one graph launch and one D2H.  CELESTE_PLAN_CACHE=0 disables it (A/B knob).
+    static const bool cache_on = !(std::getenv("CELESTE_PLAN_CACHE") && std::atoi(std::getenv("CELESTE_PLAN_CACHE")) == 0);
+    constexpr int CACHE_MAX_SLOTS = 512, CACHE_CAPACITY = 256;
+    const int n_slots = task_ptr[n_tasks], n_act = active_ptr[n_tasks];
+    if (!cache_on || n_slots < 0 || n_slots > CACHE_MAX_SLOTS || n_act < 0 || !source_ids || !active_idx) {
+        celeste_plan* pl = nullptr;
+        int rc = celeste_plan_create(f, &pl, n_tasks, task_ptr, source_ids, active_ptr, active_idx);
+        if (rc != CELESTE_OK) return rc;
+        rc = celeste_elbo_plan_host(pl, vp, mode, v, d, h, counters, flags);
+        celeste_plan_destroy(pl);
+        return rc;
+    }
+    std::vector<int32_t> key;
+    key.reserve(2 + 2 * (size_t)n_tasks + 2 + n_slots + n_act);
+    key.push_back(n_tasks);
+    {
+        // the kernel-selection knobs are read when a plan is built: a plan built under other knobs is another plan
+        unsigned hsh = 2166136261u;
+        for (const char* name : {"CELESTE_GRAD_KERNEL", "CELESTE_HESS_KERNEL", "CELESTE_MARCH_SPLIT", "CELESTE_MARCH_SPLIT_PCT",
+                                 "CELESTE_CHUNK_PIXELS", "CELESTE_UNIT_TARGET"}) {
+            const char* e = std::getenv(name);
+            for (const char* c = e ? e : ""; *c; ++c) hsh = (hsh ^ (unsigned char)*c) * 16777619u;
+            hsh = (hsh ^ 0xffu) * 16777619u;
+        }
+        key.push_back((int32_t)hsh);
+    }
+    key.insert(key.end(), task_ptr, task_ptr + n_tasks + 1);
+    key.insert(key.end(), active_ptr, active_ptr + n_tasks + 1);
+    key.insert(key.end(), source_ids, source_ids + n_slots);
+    key.insert(key.end(), active_idx, active_idx + n_act);
     celeste_plan* pl = nullptr;
-    int rc = celeste_plan_create(f, &pl, n_tasks, task_ptr, source_ids, active_ptr, active_idx);
-    if (rc != CELESTE_OK) return rc;
-    rc = celeste_elbo_plan_host(pl, vp, mode, v, d, h, counters, flags);
-    celeste_plan_destroy(pl);
+    {
+        std::lock_guard<std::mutex> lk(f->cache_mu);
+        for (auto& c : f->cache)
+            if (!c.busy && c.key == key) {
+                if (c.plan->patch_generation[0] != f->patch_generation) {      // celeste_patches_set since: rebuild
+                    delete c.plan;
+                    c.plan = nullptr;
+                    c.key.clear();
+                    continue;
+                }
+                c.busy = true;
+                c.last_use = ++f->cache_clock;
+                pl = c.plan;
+                break;
+            }
+    }
+    bool cached = pl != nullptr;
+    if (!pl) {
+        int rc = celeste_plan_create(f, &pl, n_tasks, task_ptr, source_ids, active_ptr, active_idx);
+        if (rc != CELESTE_OK) return rc;
+    }
+    int rc = celeste_elbo_plan_host(pl, vp, mode, v, d, h, counters, flags);
+    {
+        std::lock_guard<std::mutex> lk(f->cache_mu);
+        if (cached) {
+            for (auto& c : f->cache)
+                if (c.plan == pl) c.busy = false;
+        } else {
+            // insert: reuse an emptied entry, else grow, else evict the least recently used idle entry
+            celeste_field::CachedPlan* slot = nullptr;
+            for (auto& c : f->cache)
+                if (!c.plan) slot = &c;
+            if (!slot && (int)f->cache.size() < CACHE_CAPACITY) {
+                f->cache.emplace_back();
+                slot = &f->cache.back();
+            }
+            if (!slot) {
+                for (auto& c : f->cache)
+                    if (!c.busy && (!slot || c.last_use < slot->last_use)) slot = &c;
+                if (slot) delete slot->plan;
+            }
+            if (slot) {
+                slot->key = std::move(key);
+                slot->plan = pl;
+                slot->busy = false;
+                slot->last_use = ++f->cache_clock;
+            } else {
+                delete pl;       // every entry busy: do not keep this one
+            }
+        }
+    }
     return rc;
 }
 
@@ -1313,6 +1539,7 @@ int celeste_newton_step(int32_t phase, int32_t batch, const celeste_newton_buffe
     dev.vp_all = nb->vp_all;
     dev.aslot = reinterpret_cast<const long long*>(nb->aslot);
     dev.prior = nb->prior;
+    dev.h_layout = nb->h_layout;
     newton_step_kernel<<<batch, TR_THREADS, 0, (cudaStream_t)cuda_stream>>>(dev, phase);
     CUDA_TRY(cudaGetLastError());
     return CELESTE_OK;

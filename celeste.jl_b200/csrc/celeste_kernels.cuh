@@ -829,7 +829,7 @@ __global__ void __launch_bounds__(EPI_THREADS) epilogue_kernel(PlanDev plan,
                                                                const double* __restrict__ vp, double* __restrict__ out_v,
                                                                double* __restrict__ out_d, double* __restrict__ out_h,
                                                                long long* __restrict__ out_counters,
-                                                               int* __restrict__ out_flags) {
+                                                               int* __restrict__ out_flags, int hess_packed = 0) {
     constexpr int NACC = NAcc<MODE>::value;
     __shared__ double ysum[NACC_MODE2 > NPAIR_ACC ? NACC_MODE2 : NPAIR_ACC];
     __shared__ double Jy[NY][NLIVE];
@@ -850,14 +850,15 @@ __global__ void __launch_bounds__(EPI_THREADS) epilogue_kernel(PlanDev plan,
     const int Sa = sub1 - sub0;
     const int P = NPARAM * Sa;
     const FieldDev field = plan.fields[plan.task_field[t]];
-    double* Hout = MODE >= 2 ? out_h + plan.h_ptr[t] : nullptr;
+    // hess_packed (Sa = 1 plans): 406 doubles per task, the upper triangle of the 28 x 28 live block, row-major
+    double* Hout = MODE >= 2 ? out_h + (hess_packed ? (long long)HESS_PACKED_LEN * t : plan.h_ptr[t]) : nullptr;
 
     if (tid == 0) {
         s_val = 0.0;
         s_cnt[0] = s_cnt[1] = 0.0;
         s_bad = 0;
     }
-    if (MODE >= 2 && Sa > 1)
+    if (MODE >= 2 && Sa > 1 && !hess_packed)
         for (int i = tid; i < P * P; i += EPI_THREADS) Hout[i] = 0.0;   // cross blocks are filled below
     __syncthreads();
     int bad = 0;
@@ -972,7 +973,15 @@ __global__ void __launch_bounds__(EPI_THREADS) epilogue_kernel(PlanDev plan,
                 bad |= !isfinite(g);
             }
         }
-        if (MODE >= 2) {
+        if (MODE >= 2 && hess_packed) {
+            for (int i = tid; i < NLIVE * NLIVE; i += EPI_THREADS) {
+                const int r = i / NLIVE, c = i % NLIVE;
+                if (c < r) continue;
+                const double v = 0.5 * (Hacc[r][c] + Hacc[c][r]);
+                Hout[hess_packed_index(r, c)] = v;
+                bad |= !isfinite(v);
+            }
+        } else if (MODE >= 2) {
             for (int i = tid; i < NPARAM * NPARAM; i += EPI_THREADS) {
                 const int r = i % NPARAM, c = i / NPARAM;
                 double v = 0.0;

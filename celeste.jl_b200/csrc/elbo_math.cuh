@@ -55,6 +55,8 @@ constexpr int ACC_CC = 34;      // 10: d2L/dc dc, packed upper triangle
 constexpr int ACC_CR = 44;      // 24: d2L/dc dy, [c][k]
 constexpr int NACC_MODE0 = 3, NACC_MODE1 = 13, NACC_MODE2 = 68;
 template <int MODE> struct NAcc { static constexpr int value = MODE == 0 ? NACC_MODE0 : (MODE == 1 ? NACC_MODE1 : NACC_MODE2); };
+constexpr int HESS_PACKED_LEN = NLIVE * (NLIVE + 1) / 2;   // 406: upper triangle of the live 28 x 28 block (CELESTE_HESS_PACKED28)
+CEL_HD constexpr int hess_packed_index(int r, int c) { return r * NLIVE - (r * (r - 1)) / 2 + (c - r); }   // r <= c < 28
 CEL_HD constexpr int tri6(int k, int l) { return k * 6 - (k * (k - 1)) / 2 + (l - k); }   // k <= l < 6
 CEL_HD constexpr int tri4(int k, int l) { return k * 4 - (k * (k - 1)) / 2 + (l - k); }   // k <= l < 4
 

@@ -55,6 +55,7 @@ struct NewtonDev {
     double* vp_all;     // n_slots x 44: bound parameters the plan reads
     const long long* aslot;    // B: slot of each source's own parameters in vp_all
     const double* prior;       // PR_LEN doubles, or null: no KL term
+    long long h_layout;        // 0: h is B x 44 x 44; 1: B x 406 (CELESTE_HESS_PACKED28)
 };
 
 constexpr double NW_ETA = 0.1, NW_RHO_LOWER = 0.25, NW_RHO_UPPER = 0.75;
@@ -145,7 +146,15 @@ __global__ void __launch_bounds__(TR_THREADS) newton_step_kernel(NewtonDev nb, i
         bnd[tid] = vp_own[tid];
     }
     double* Hb = S.A;                                   // 44 x 44, leading dimension TR_LD
-    {
+    if (nb.h_layout == 1) {
+        // packed upper triangle of the live 28 x 28 block; every other entry of the 44 x 44 matrix is zero
+        const double* h = nb.h + (size_t)b * HESS_PACKED_LEN;
+        for (int e = tid; e < NW_BOUND * NW_BOUND; e += TR_THREADS) {
+            const int r = e / NW_BOUND, c = e % NW_BOUND;
+            const int lo_i = r < c ? r : c, hi_i = r < c ? c : r;
+            Hb[r * TR_LD + c] = hi_i < NLIVE ? h[hess_packed_index(lo_i, hi_i)] : 0.0;
+        }
+    } else {
         const double* h = nb.h + (size_t)b * NW_BOUND * NW_BOUND;
         for (int e = tid; e < NW_BOUND * NW_BOUND; e += TR_THREADS) Hb[(e / NW_BOUND) * TR_LD + (e % NW_BOUND)] = h[e];
     }

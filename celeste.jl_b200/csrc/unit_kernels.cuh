@@ -60,15 +60,19 @@ constexpr int UA_G = 0, UA_C1 = 6, UA_HH = 10, UA_CC = 31, UA_CR = 38;
 template <int MODE> struct NUAcc { static constexpr int value = MODE == 0 ? 0 : (MODE == 1 ? 10 : 62); };
 CEL_HD constexpr int unit_acc_index(int slot) { return slot < UA_CR ? slot + 3 : slot + 6; }
 
-struct UnitHdr {        // one (sub, image) unit; built on the host (build_unit_list), heaviest first
+struct UnitHdr {        // one unit = rows [h2_lo, h2_hi) of one (sub, image); built on the host (build_unit_list), heaviest first
     int aslot, slot0, slot1;
     int field, sub, task;
     int n;              // image
     int nseg;           // column segments per row of the active patch (phase A)
     int hasbg;          // some other source of the task reaches this image
-    int pidx;           // partial vector of this unit (sub * N + n)
-    int nbpix;          // pixels shared with neighbours (cost of the unit in unit_bg_kernel)
-    int pad1;
+    int pidx;           // partial vector of this unit in plan.partials
+    int nbpix;          // pixels shared with neighbours (cost of the (sub, image) in unit_bg_kernel)
+    int tn;             // sub * N + n: index of the (sub, image) planes (plan.pix / plan.l5 / plan.bg)
+    int h2_lo, h2_hi;   // rows of the active patch this unit walks (a large plan: all of them; a small plan is cut
+                        // finer so that one source's evaluation spreads over many SMs)
+    int first;          // 1: the unit that holds row 0 (it carries the (sub, image)'s neighbour counter)
+    int pad;
 };
 
 // One active pixel as the walk reads it: 16 bytes, stored per unit in WALK ORDER (row-major inside the patch: a row
@@ -228,11 +232,12 @@ __global__ void unit_pack_kernel(PlanDev plan, const UnitHdr* __restrict__ units
     const int u = blockIdx.x;
     if (u >= n_units) return;
     const UnitHdr uh = units[u];
+    if (!uh.first) return;
     const FieldDev field = plan.fields[uh.field];
     const ImageDev img = field.images[uh.n];
     const PatchDev& pa = field.patches[plan.src_row[uh.aslot] + (size_t)uh.n * field.S_tot];
     const int H2 = pa.H2, W2 = pa.W2;
-    PixRec* dst = out + plan.l5_ptr[uh.pidx];
+    PixRec* dst = out + plan.l5_ptr[uh.tn];
     for (int i = threadIdx.x; i < H2 * W2; i += blockDim.x) {
         const int h2 = i / W2, w2 = i - h2 * W2;
         const size_t ipix = (size_t)(pa.off_h + h2) + (size_t)(pa.off_w + w2) * img.H;
@@ -276,9 +281,8 @@ __global__ void __launch_bounds__(UNIT_THREADS, CELESTE_UNIT_BG_MINB)
         const PatchDev& pa = prow[plan.src_row[aslot]];
         const int band0 = field.images[n].band - 1;
         if (!uh.hasbg) continue;
-        double* my_scratch = plan.bg + plan.bg_ptr[uh.pidx];
-        const float* img_pixels = field.images[n].pixels;
-        const int img_H = field.images[n].H;
+        double* my_scratch = plan.bg + plan.bg_ptr[uh.tn];
+        const PixRec* arec = plan.pix + plan.l5_ptr[uh.tn];      // x = NaN: masked or not in the active bitmap
         double cnt_inactive = 0.0;
         {
             {
@@ -316,7 +320,7 @@ __global__ void __launch_bounds__(UNIT_THREADS, CELESTE_UNIT_BG_MINB)
                     const int nit = warp_max_int((len + 1) >> 1);
                     if (nit == 0) continue;
                     const int h = h_lo + row, w0 = w_lo + c0;       // 1-based image coordinates
-                    const int aH2 = pa.H2, aW2 = pa.W2, nH2 = p.H2, imgH = img_H, n1 = p.n1, n2 = p.n2;
+                    const int aW2 = pa.W2, nH2 = p.H2, n1 = p.n1, n2 = p.n2;
                     const double* coefs = p.coefs;
                     const double* si = s_si;
                     const double* recs = s_rec + kk * MREC;          // this lane's PSF component
@@ -335,9 +339,8 @@ __global__ void __launch_bounds__(UNIT_THREADS, CELESTE_UNIT_BG_MINB)
                     }
                     const int ah2 = h - pa.off_h - 1, nh2 = h - p.off_h - 1;
                     const int acol = w0 - pa.off_w - 1 + kk, ncol = w0 - p.off_w - 1 + kk;      // own first column, 0-based
-                    const uint8_t* abit = pa.bitmap + ah2 + (size_t)acol * aH2;
                     const uint8_t* nbit = p.bitmap + nh2 + (size_t)ncol * nH2;
-                    const float* px = img_pixels + (size_t)(h - 1) + (size_t)(w0 - 1 + kk) * imgH;
+                    const PixRec* px = arec + (size_t)ah2 * aW2 + acol;
                     double* bgE = my_scratch + 2 * ((size_t)ah2 * aW2 + acol);
                     const double theta = si[SI_THETA];
                     int t = 0;
@@ -347,12 +350,11 @@ __global__ void __launch_bounds__(UNIT_THREADS, CELESTE_UNIT_BG_MINB)
                         const int tend = careful ? min(nit, t + MARCH_CAREFUL_COLS / 2) : nit;
                         for (; t < tend; ++t) {
                             const bool own = 2 * t + kk < len;
-                            unsigned char ab = 0, nb = 0;
-                            float xv = 0.f;
+                            unsigned char nb = 0;
+                            float xv = nanf("");
                             if (own) {
-                                ab = *abit;
                                 nb = *nbit;
-                                xv = *px;
+                                xv = px->x;
                             }
                             double R2 = 0.0, R3 = 0.0;
                             if (fast && own) {
@@ -375,7 +377,7 @@ __global__ void __launch_bounds__(UNIT_THREADS, CELESTE_UNIT_BG_MINB)
                             double Fd = kk == 0 ? S[0][0] : S[1][0], Fe = kk == 0 ? S[0][1] : S[1][1];
                             Fd += __shfl_xor_sync(0xffffffffu, kk == 0 ? S[1][0] : S[0][0], 1);
                             Fe += __shfl_xor_sync(0xffffffffu, kk == 0 ? S[1][1] : S[0][1], 1);
-                            if (ab && nb && !isnan(xv)) {
+                            if (nb && !isnan(xv)) {
                                 double f0;
                                 if (fast) {
                                     const double v = si[SI_WY] * R0 + si[SI_WY + 1] * R1 + si[SI_WY + 2] * R2 + si[SI_WY + 3] * R3;
@@ -391,9 +393,8 @@ __global__ void __launch_bounds__(UNIT_THREADS, CELESTE_UNIT_BG_MINB)
                                 bgE[1] += E2s - Es * Es;
                                 cnt_inactive += 1.0;                                          // elbo_objective.jl:353-357
                             }
-                            abit += 2 * aH2;
                             nbit += 2 * nH2;
-                            px += 2 * imgH;
+                            px += 2;
                             bgE += 4;
                             R0 = R2;
                             R1 = R3;
@@ -453,10 +454,10 @@ __global__ void __launch_bounds__(UNIT_THREADS, CELESTE_UNIT_MINB)
 #pragma unroll
         for (int a = 0; a < NUA; ++a) acc[a * 32] = 0.0;
         if (lane == 30) {
-            mi.pix = plan.pix + plan.l5_ptr[uh.pidx];
+            mi.pix = plan.pix + plan.l5_ptr[uh.tn];
             mi.iota = field.images[n].iota;
             mi.coefs = pa.coefs;
-            mi.bg = uh.hasbg ? plan.bg + plan.bg_ptr[uh.pidx] : nullptr;
+            mi.bg = uh.hasbg ? plan.bg + plan.bg_ptr[uh.tn] : nullptr;
             mi.H2 = pa.H2;
             mi.W2 = pa.W2;
             mi.off_h = pa.off_h;
@@ -477,16 +478,16 @@ __global__ void __launch_bounds__(UNIT_THREADS, CELESTE_UNIT_MINB)
         __syncwarp();
 
         // ---- phase A: the active source, row walks by lane pairs ------------------------------------------------
-        const int H2c = max(mi.H2, 1), W2 = mi.W2;
+        const int H2c = max(uh.h2_hi - uh.h2_lo, 1), W2 = mi.W2;      // rows of this unit
         const int nseg = uh.nseg;
-        const int total = (mi.H2 > 0 && W2 > 0) ? mi.H2 * nseg : 0;
+        const int total = (uh.h2_hi > uh.h2_lo && W2 > 0) ? (uh.h2_hi - uh.h2_lo) * nseg : 0;
         const int segw = (W2 + nseg - 1) / nseg;
-        double* l5plane = MODE >= 2 ? plan.l5 + plan.l5_ptr[uh.pidx] : nullptr;
+        double* l5plane = MODE >= 2 ? plan.l5 + plan.l5_ptr[uh.tn] : nullptr;
         for (int ub = 0; ub < total; ub += NPW) {                      // warp-uniform
             const int uu = ub + (lane >> 1);
             const bool has = uu < total;
             const int ul = has ? uu : 0;
-            const int seg = ul / H2c, h2 = ul - seg * H2c;
+            const int seg = ul / H2c, h2 = uh.h2_lo + (ul - seg * H2c);
             const int c0 = seg * segw;
             const int len = has ? max(min(segw, W2 - c0), 0) : 0;
             const int nit = warp_max_int((len + 1) >> 1);
@@ -695,7 +696,7 @@ __global__ void __launch_bounds__(UNIT_THREADS, CELESTE_UNIT_MINB)
         if (lane == 0) {
             out[ACC_VAL] = val;
             out[ACC_CNT_ACTIVE] = cnt_active;
-            if (!uh.hasbg) out[ACC_CNT_INACTIVE] = 0.0;        // (units with neighbours: written by unit_bg_kernel)
+            if (!(uh.hasbg && uh.first)) out[ACC_CNT_INACTIVE] = 0.0;   // (else: written by unit_bg_kernel)
         }
         if (MODE == 2 && lane < 3) out[ACC_CC + 7 + lane] = 0.0;
         for (int a = lane; a < NUA; a += 32) {
@@ -747,7 +748,7 @@ __global__ void __launch_bounds__(UNIT_THREADS, CELESTE_UNIT_MOM_MINB)
             march_make_record(pa, vs, xx, s_rec, lane);
         }
         __syncwarp();
-        const double* l5plane = plan.l5 + plan.l5_ptr[uh.pidx];
+        const double* l5plane = plan.l5 + plan.l5_ptr[uh.tn];
         double OUT[20];
 #pragma unroll
         for (int q = 0; q < 20; ++q) OUT[q] = 0.0;
@@ -760,7 +761,7 @@ __global__ void __launch_bounds__(UNIT_THREADS, CELESTE_UNIT_MOM_MINB)
             for (int q = 0; q < 15; ++q) Dm[q] = 0.0;
             const int nsb = (ncols + MARCH_MAXSEG - 1) / MARCH_MAXSEG;
             const int sw = (ncols + nsb - 1) / nsb;
-            for (int h2 = 0; h2 < H2; ++h2) {
+            for (int h2 = uh.h2_lo; h2 < uh.h2_hi; ++h2) {
                 const double d1 = (double)(off_h + h2 + 1) - mu1;
                 double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0;
                 for (int c0 = 0; c0 < ncols; c0 += sw) {
@@ -778,21 +779,34 @@ __global__ void __launch_bounds__(UNIT_THREADS, CELESTE_UNIT_MOM_MINB)
                         double r = sleep ? 0.0 : exp_scaled_tab(fmin(ra, 700.0), 1.0, s_exptab);
                         const int cend = sleep ? min(c1, c + MARCH_CAREFUL_COLS) : c1;
                         const double* lp = l5plane + (size_t)h2 * W2 + c;
+#define CEL_MOMENT_STEP(L5V)                 \
+    {                                        \
+        const double v = f * (L5V);          \
+        const double v1 = v * d2;            \
+        s0 += v;                             \
+        const double v2 = v1 * d2;           \
+        s1 += v1;                            \
+        const double v3 = v2 * d2;           \
+        s2 += v2;                            \
+        s3 += v3;                            \
+        s4 = fma(v3, d2, s4);                \
+        f *= r;                              \
+        r *= cc;                             \
+        d2 += 1.0;                           \
+    }
+                        for (; c + 4 <= cend; c += 4) {           // four L5 loads in flight
+                            const double a0 = lp[0], a1 = lp[1], a2 = lp[2], a3 = lp[3];
+                            CEL_MOMENT_STEP(a0)
+                            CEL_MOMENT_STEP(a1)
+                            CEL_MOMENT_STEP(a2)
+                            CEL_MOMENT_STEP(a3)
+                            lp += 4;
+                        }
                         for (; c < cend; ++c) {
-                            const double v = f * *lp;
-                            const double v1 = v * d2;
-                            s0 += v;
-                            const double v2 = v1 * d2;
-                            s1 += v1;
-                            const double v3 = v2 * d2;
-                            s2 += v2;
-                            s3 += v3;
-                            s4 = fma(v3, d2, s4);
-                            f *= r;
-                            r *= cc;
-                            d2 += 1.0;
+                            CEL_MOMENT_STEP(*lp)
                             lp += 1;
                         }
+#undef CEL_MOMENT_STEP
                     }
                 }
                 // D[a][b] += d1^a s_b; index order 00 01 02 03 04 | 10 11 12 13 | 20 21 22 | 30 31 | 40
@@ -852,13 +866,22 @@ __global__ void __launch_bounds__(UNIT_THREADS, CELESTE_UNIT_MOM_MINB)
     }
 }
 
-// Host side: the unit list of a plan (every (sub, image), heaviest first) and each unit's column segmentation.
+// Host side: the unit list of a plan (heaviest first), each unit's column segmentation, and the partial vectors:
+// chunk_ptr[sub * N + n] .. chunk_ptr[sub * N + n + 1] are the partials of (sub, image) for epilogue_kernel.
+// A (sub, image) is ONE unit unless the plan is small against `target_units` (the warps the GPU keeps resident): then
+// its rows are cut into up to `cut` units so that a few sources still spread over the whole GPU (the latency of a
+// celeste_elbo_single call; the launch tail of a rank of an 8-GPU run).
 // geo(slot, n, off_h, off_w, H2, W2) -> the patch box of a slot in image n.
 template <typename Geo>
 inline void build_unit_list(int n_subs, int N, const int* sub_task, const int* sub_slot, const int* task_ptr,
-                            const int* task_field, Geo geo, std::vector<UnitHdr>& units, long long& maxpix) {
+                            const int* task_field, Geo geo, long target_units, std::vector<UnitHdr>& units,
+                            std::vector<UnitHdr>& bg_units, std::vector<int>& chunk_ptr, long long& maxpix) {
     units.clear();
+    bg_units.clear();
+    chunk_ptr.assign((size_t)n_subs * N + 1, 0);
     maxpix = 1;
+    const long whole = std::max(1L, (long)n_subs * N);
+    const int cut = (int)std::max(1L, std::min(8L, target_units / whole));     // units per (sub, image) at most
     std::vector<long> cost;
     for (int u = 0; u < n_subs; ++u) {
         const int t = sub_task[u];
@@ -874,13 +897,13 @@ inline void build_unit_list(int n_subs, int N, const int* sub_task, const int* s
             uh.sub = u;
             uh.task = t;
             uh.n = n;
-            uh.pidx = u * N + n;
+            uh.tn = u * N + n;
             uh.hasbg = 0;
-            long c = 0;
             uh.nseg = 1;
+            uh.first = 1;
+            int pieces = 1;
             if (H2 > 0 && W2 > 0) {
                 maxpix = std::max(maxpix, (long long)H2 * W2);
-                c = (long)H2 * W2 * 4;
                 for (int s = slot0; s < slot1; ++s) {
                     if (s == aslot) continue;
                     int ph, pw, pH2, pW2;
@@ -894,20 +917,34 @@ inline void build_unit_list(int n_subs, int N, const int* sub_task, const int* s
                         }
                     }
                 }
-                // column segments per row: minimise rounds of 16 walks x (iterations of two columns + an exact start)
-                const int nmin = std::max(1, (W2 + MARCH_MAXSEG - 1) / MARCH_MAXSEG);
-                long best = -1;
-                for (int cand = nmin; cand < nmin + 8; ++cand) {
-                    const int L = (W2 + cand - 1) / cand;
-                    const long cst = (long)((H2 * cand + NPW - 1) / NPW) * (10 * ((L + 1) / 2) + 5);
-                    if (best < 0 || cst < best) {
-                        best = cst;
-                        uh.nseg = cand;
+                pieces = std::max(1, std::min(cut, H2 / 4));
+            }
+            const int tn = u * N + n;
+            chunk_ptr[tn + 1] = chunk_ptr[tn] + pieces;
+            for (int pc = 0; pc < pieces; ++pc) {
+                UnitHdr x = uh;
+                x.h2_lo = (int)((long)std::max(H2, 0) * pc / pieces);
+                x.h2_hi = (int)((long)std::max(H2, 0) * (pc + 1) / pieces);
+                x.first = pc == 0;
+                x.pidx = chunk_ptr[tn] + pc;
+                const int rows = x.h2_hi - x.h2_lo;
+                if (rows > 0 && W2 > 0) {
+                    // column segments per row: minimise rounds of 16 walks x (iterations of two columns + an exact start)
+                    const int nmin = std::max(1, (W2 + MARCH_MAXSEG - 1) / MARCH_MAXSEG);
+                    long best = -1;
+                    for (int cand = nmin; cand < nmin + 8; ++cand) {
+                        const int L = (W2 + cand - 1) / cand;
+                        const long cst = (long)((rows * cand + NPW - 1) / NPW) * (10 * ((L + 1) / 2) + 5);
+                        if (best < 0 || cst < best) {
+                            best = cst;
+                            x.nseg = cand;
+                        }
                     }
                 }
+                units.push_back(x);
+                cost.push_back((long)std::max(rows, 0) * std::max(W2, 0));
+                if (pc == 0 && x.hasbg) bg_units.push_back(x);
             }
-            units.push_back(uh);
-            cost.push_back(c);
         }
     }
     std::vector<int> order(units.size());
@@ -916,6 +953,7 @@ inline void build_unit_list(int n_subs, int N, const int* sub_task, const int* s
     std::vector<UnitHdr> sorted(units.size());
     for (size_t i = 0; i < order.size(); ++i) sorted[i] = units[order[i]];
     units.swap(sorted);
+    std::stable_sort(bg_units.begin(), bg_units.end(), [](const UnitHdr& a, const UnitHdr& b) { return a.nbpix > b.nbpix; });
 }
 
 }  // namespace celeste

@@ -254,6 +254,7 @@ class Plan:
         self.n_tasks = len(dummy)
         self.n_src = int(self.task_ptr[-1])
         self.nd, self.nh = out_sizes(self.active_ptr)
+        self.hess_packed = False
         self._handle = C.c_void_p()
         tf = np.zeros(self.n_tasks, dtype=np.int32) if task_field is None else np.asarray(task_field, dtype=np.int32)
         assert tf.shape == (self.n_tasks,)
@@ -275,6 +276,20 @@ class Plan:
         ms = (C.c_float * 3)()
         _lib.check(_lib.load().celeste_plan_kernel_times(self._handle, C.byref(ms)))
         return tuple(float(x) for x in ms)
+
+    def unit_times_ms(self):
+        """(unit_bg_kernel, unit_walk_kernel, unit_moment_kernel) device milliseconds of the last evaluation when the
+        unit kernels ran (zeros otherwise)."""
+        ms = (C.c_float * 3)()
+        _lib.check(_lib.load().celeste_plan_unit_times(self._handle, C.byref(ms)))
+        return tuple(float(x) for x in ms)
+
+    def set_hessian_layout(self, packed: bool):
+        """celeste_plan_set_hessian_layout: packed = 406 doubles per task (upper triangle of the live 28 x 28 block,
+        row-major) instead of the dense 44 x 44 SensitiveFloat matrix.  Sa = 1 plans only."""
+        _lib.check(_lib.load().celeste_plan_set_hessian_layout(self._handle, 1 if packed else 0))
+        self.hess_packed = bool(packed)
+        self.nh = (406 * self.n_tasks) if packed else out_sizes(self.active_ptr)[1]
 
     def launches(self, mode: int) -> int:
         return int(_lib.load().celeste_plan_launches(self._handle, mode))

@@ -144,7 +144,12 @@ class BatchMaximizer:
         n = self.n
         self.v = torch.zeros(n, dtype=dt, device=self.dev)
         self.d = torch.zeros(n * 44, dtype=dt, device=self.dev)
-        self.h = torch.zeros(n * 44 * 44, dtype=dt, device=self.dev)
+        if fused is None:
+            fused = stepper is not None or (self.dev.type == "cuda" and runner is None)
+        self.fused = fused
+        # the device-resident loop takes the Hessian in the packed layout (406 doubles per source instead of 1936)
+        self.packed = bool(fused and runner is None and stepper is None and hasattr(plan, "set_hessian_layout"))
+        self.h = torch.zeros(n * (406 if self.packed else 44 * 44), dtype=dt, device=self.dev)
         self.cnt = torch.zeros(2 * n, dtype=torch.int64, device=self.dev)
         self.flags = torch.zeros(n, dtype=torch.int32, device=self.dev)
         vp0 = self.vp_all[self.aslot]
@@ -160,9 +165,6 @@ class BatchMaximizer:
         self.mask = torch.ones(n, dtype=torch.uint8, device=self.dev)
         self.use_mask = runner is None and hasattr(plan, "set_task_mask")
         self.profile = None        # set to {} to collect wall-clock per phase (synchronising; diagnostics only)
-        if fused is None:
-            fused = stepper is not None or (self.dev.type == "cuda" and runner is None)
-        self.fused = fused
 
     def _tick(self, name, t0):
         if self.profile is not None:
@@ -209,11 +211,15 @@ class BatchMaximizer:
         x = self.x
         if self.use_mask:
             self.plan.set_task_mask(self.mask.data_ptr())
+        if self.packed:
+            self.plan.set_hessian_layout(True)
         try:
             return self._run_fused() if self.fused else self._run(n, dev, x)
         finally:
             if self.use_mask:
                 self.plan.set_task_mask(0)
+            if self.packed:
+                self.plan.set_hessian_layout(False)
 
     def _step(self, phase):
         if self.stepper is not None:
@@ -245,7 +251,8 @@ class BatchMaximizer:
                   vp_all=self.vp_all, aslot=self.aslot.contiguous(),
                   prior=self.kl.packed() if self.include_kl else None)
         self._st = st                                          # keeps the tensors alive while the kernels run
-        self._buffers = _lib.celeste_newton_buffers(**{k: (t.data_ptr() if t is not None else None) for k, t in st.items()})
+        self._buffers = _lib.celeste_newton_buffers(**{k: (t.data_ptr() if t is not None else None) for k, t in st.items()},
+                                                    h_layout=1 if self.packed else 0)
         self.mask.fill_(1)
         self._step(2)                                          # vp_all[aslot] <- to_bound(x)
         self._evaluate_plan()

@@ -214,10 +214,11 @@ void celeste_plan_destroy(celeste_plan* p);
 /* number of kernel launches one celeste_elbo_plan_device call enqueues */
 int celeste_plan_launches(const celeste_plan* p, int32_t mode);
 /*
- * Name of the kernel that carries the pixel loop of `mode` for this plan, written to buf (<= 31 chars + NUL):
- * "march_kernel" (value / gradient, every task Sa = 1 and every patch K = 2 -- the production shape:
- * ParallelRun.jl:253,489, elbo_args.jl:197), "task_kernel" (value / gradient otherwise, or when the process
- * was started with CELESTE_GRAD_KERNEL=task), "pixel_kernel" (Hessian).  For profiling / bench reports.
+ * Name of the kernel family that carries the pixel loop of `mode` for this plan, written to buf (<= 31 chars + NUL):
+ * "unit_kernel" (every mode when every task has Sa = 1 and every patch K = 2 -- the production shape:
+ * ParallelRun.jl:253,489, elbo_args.jl:197 -- unit_bg_kernel + unit_walk_kernel<mode> [+ unit_moment_kernel]),
+ * "march_kernel" / "task_kernel" (value / gradient: CELESTE_GRAD_KERNEL=march / =task, or any other shape),
+ * "pixel_kernel" (Hessian: CELESTE_HESS_KERNEL=pixel, or any other shape).  For profiling / bench reports.
  */
 int celeste_plan_kernel_name(const celeste_plan* p, int32_t mode, char* buf);
 int celeste_elbo_plan_device(celeste_plan* p, const double* vp_dev, int32_t mode,
@@ -237,6 +238,21 @@ int celeste_elbo_plan_host(celeste_plan* p, const double* vp, int32_t mode,
  */
 int celeste_plan_enable_timing(celeste_plan* p, int32_t on);
 int celeste_plan_kernel_times(celeste_plan* p, float ms[3]);
+/* the "pixel" share of the last evaluation split by kernel when the unit kernels ran (else zeros):
+ * ms[0] unit_bg_kernel (neighbours), ms[1] unit_walk_kernel (the dominant kernel), ms[2] unit_moment_kernel */
+int celeste_plan_unit_times(celeste_plan* p, float ms[3]);
+/*
+ * Layout of the Hessian a plan writes (mode 2).  CELESTE_HESS_DENSE (default): per task the (44 Sa) x (44 Sa)
+ * column-major matrix of the reference's SensitiveFloat (SensitiveFloats.jl:29-31).  CELESTE_HESS_PACKED28 (plans
+ * whose tasks all have Sa = 1): per task the 406 doubles of the upper triangle (row-major: (0,0) (0,1) .. (0,27)
+ * (1,1) ..) of the 28 x 28 block of canonical ids 1..28 -- everything else of the 44 x 44 matrix is exactly zero
+ * (ids.k never receives a likelihood derivative) and the matrix is exactly symmetric, so nothing is lost; it is 4.8x
+ * less device->host traffic.  h / h_dev of the evaluation calls then hold 406 doubles per task.
+ */
+#define CELESTE_HESS_DENSE 0
+#define CELESTE_HESS_PACKED28 1
+#define CELESTE_HESS_PACKED28_LEN 406
+int celeste_plan_set_hessian_layout(celeste_plan* p, int32_t layout);
 /*
  * Optional per-task mask for the plan's evaluations: mask_dev is a DEVICE array of n_tasks bytes that the caller
  * may rewrite between calls; tasks whose byte is 0 are skipped and their outputs left untouched (the batched
@@ -338,11 +354,12 @@ typedef struct celeste_newton_buffers {
     const double* hi;     /* B x 26  box upper bounds                                                     */
     const double* v;      /* B       plan outputs at the candidate (celeste_elbo_plan_device, mode 2)     */
     const double* d;      /* B x 44                                                                       */
-    const double* h;      /* B x 44 x 44                                                                  */
+    const double* h;      /* B x 44 x 44, or B x 406 when h_layout = CELESTE_HESS_PACKED28                */
     const int32_t* flags; /* B                                                                            */
     double* vp_all;       /* n_slots x 44  the plan's bound parameters; row aslot[b] belongs to source b  */
     const int64_t* aslot; /* B                                                                            */
     const double* prior;  /* 360 doubles (kl.KLTerm.packed layout, see maximize_kernels.cuh) or NULL: no KL */
+    int64_t h_layout;     /* CELESTE_HESS_DENSE or CELESTE_HESS_PACKED28: layout of `h`                   */
 } celeste_newton_buffers;
 /*
  * phase 0: the plan was evaluated at to_bound(x): initialise f, g, H, delta = 1, active, and emit the first

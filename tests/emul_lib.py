@@ -23,6 +23,7 @@ def load():
         _lib.emul_elbo_batch.argtypes = [i32, vp, i32, vp, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, i32]
         _lib.emul_set_grad_kernel.argtypes = [i32]
         _lib.emul_set_hess_kernel.argtypes = [i32]
+        _lib.emul_set_unit_target.argtypes = [C.c_int64]
         _lib.emul_march_blocks.argtypes = [i32, i32, vp, i32, vp, vp, C.c_int64, i32, vp, vp]
         _lib.emul_tr_subproblem.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp]
         _lib.emul_newton_step.argtypes = [i32, i32, vp]

@@ -36,8 +36,9 @@ void galaxy_prototypes(double eta[NPROTO], double nu[NPROTO]) {
 }
 
 long g_march_split = 6000;   // pixels above which a source gets one march block per image (emul_set_grad_kernel(2) lowers it)
-int g_grad_kernel = 1;   // 1: march_kernel where the product would use it (Sa = 1, K = 2); 0: always task_kernel
+int g_grad_kernel = 3;   // 3: unit kernels where the product uses them (Sa = 1, K = 2); 1 / 2: march_kernel; 0: always task_kernel
 
+long g_unit_target = 0;  // build_unit_list: 0 = one unit per (sub, image); emul_set_unit_target cuts small plans finer
 int g_hess_kernel = 1;   // 1: unit_kernel<2> where the product would use it (Sa = 1, K = 2); 0: always pixel_kernel<2>
 
 // same launch sequence as celeste_abi.cu's unit path: setup (brightness moments for the epilogue), unit_kernel, epilogue
@@ -46,7 +47,8 @@ void run_unit(PlanDev pd, const FieldDev& fd, const double* vp, double* v, doubl
               int* flags) {
     std::vector<int> sub_task(pd.n_subs);
     for (int u = 0; u < pd.n_subs; ++u) sub_task[u] = u;
-    std::vector<UnitHdr> units;
+    std::vector<UnitHdr> units, ub;
+    std::vector<int> cp;
     long long maxpix = 1;
     build_unit_list(pd.n_subs, pd.N, sub_task.data(), pd.sub_slot, pd.task_ptr, (const int*)nullptr,
                     [&](int slot, int n, int& oh, int& ow, int& H2, int& W2) {
@@ -56,12 +58,9 @@ void run_unit(PlanDev pd, const FieldDev& fd, const double* vp, double* v, doubl
                         H2 = pa.H2;
                         W2 = pa.W2;
                     },
-                    units, maxpix);
+                    g_unit_target, units, ub, cp, maxpix);
     const int grid = 2;
-    std::vector<double> part((size_t)pd.n_subs * pd.N * NAcc<MODE>::value + 1, 1e300);   // poisoned
-    std::vector<UnitHdr> ub;
-    for (const UnitHdr& x : units)
-        if (x.hasbg) ub.push_back(x);
+    std::vector<double> part((size_t)cp.back() * NAcc<MODE>::value + 1, 1e300);   // poisoned
     std::vector<long long> bg_ptr((size_t)pd.n_subs * pd.N, -1), l5_ptr((size_t)pd.n_subs * pd.N, 0);
     long long bg_total = 0, l5_total = 0;
     for (int u = 0; u < pd.n_subs; ++u)
@@ -74,8 +73,6 @@ void run_unit(PlanDev pd, const FieldDev& fd, const double* vp, double* v, doubl
             l5_total += px;
         }
     std::vector<double> bg((size_t)bg_total + 1, 1e300), l5((size_t)l5_total + 1, 1e300);   // poisoned
-    std::vector<int> cp((size_t)pd.n_subs * pd.N + 1);
-    for (size_t i = 0; i < cp.size(); ++i) cp[i] = (int)i;
     pd.partials = part.data();
     pd.chunk_ptr = cp.data();
     pd.bg_ptr = bg_ptr.data();
@@ -95,7 +92,7 @@ void run_unit(PlanDev pd, const FieldDev& fd, const double* vp, double* v, doubl
     if (MODE == 2)
         cuda_emul::launch(unit_moment_kernel, grid, UNIT_THREADS, unit_moment_smem_bytes(), pd, (const UnitHdr*)units.data(),
                           (int)units.size(), &queue[2], vp);
-    cuda_emul::launch(epilogue_kernel<MODE>, pd.n_tasks, EPI_THREADS, 0, pd, vp, v, d, h, counters, flags);
+    cuda_emul::launch(epilogue_kernel<MODE>, pd.n_tasks, EPI_THREADS, 0, pd, vp, v, d, h, counters, flags, 0);
 }
 
 template <int MODE>
@@ -157,7 +154,7 @@ void run_task(PlanDev pd, const FieldDev& fd, const std::vector<TaskHdr>& taskma
             else
                 cuda_emul::launch(task_kernel<MODE, 0, true>, (int)taskmap.size(), PIX_THREADS, smem, pd, taskmap.data());
         }
-        cuda_emul::launch(epilogue_kernel<MODE>, pd.n_tasks, EPI_THREADS, 0, pd, vp, v, d, h, counters, flags);
+        cuda_emul::launch(epilogue_kernel<MODE>, pd.n_tasks, EPI_THREADS, 0, pd, vp, v, d, h, counters, flags, 0);
     }
 }
 
@@ -181,7 +178,7 @@ void run(const PlanDev& pd, const FieldDev& fd, int n_blocks, int chunk_pixels, 
         else
             cuda_emul::launch(pair_kernel<0>, pd.n_pairs * pd.N, PAIR_THREADS, psm, pd);
     }
-    cuda_emul::launch(epilogue_kernel<MODE>, pd.n_tasks, EPI_THREADS, 0, pd, vp, v, d, h, counters, flags);
+    cuda_emul::launch(epilogue_kernel<MODE>, pd.n_tasks, EPI_THREADS, 0, pd, vp, v, d, h, counters, flags, 0);
 }
 }  // namespace
 
@@ -323,8 +320,13 @@ extern "C" int emul_elbo_batch(int32_t N, const celeste_image* imgs, int32_t S_t
 
 // 0: task_kernel, 1: march_kernel, 2: march_kernel with every source split into one block per image, 3: unit_kernel
 extern "C" int emul_set_grad_kernel(int32_t which) {
-    g_grad_kernel = which == 0 ? 0 : (which == 3 ? 3 : 1);
+    g_grad_kernel = (which == 0 || which == 3) ? which : 1;
     g_march_split = which == 2 ? 1 : 6000;
+    return 0;
+}
+
+extern "C" int emul_set_unit_target(int64_t target) {
+    g_unit_target = (long)target;
     return 0;
 }
 
@@ -400,6 +402,7 @@ extern "C" int emul_newton_step(int32_t phase, int32_t batch, const celeste_newt
     dev.vp_all = nb->vp_all;
     dev.aslot = reinterpret_cast<const long long*>(nb->aslot);
     dev.prior = nb->prior;
+    dev.h_layout = nb->h_layout;
     cuda_emul::launch(newton_step_kernel, batch, TR_THREADS, 0, dev, phase);
     return 0;
 }

@@ -43,14 +43,12 @@ def test_march_kernel_matches_oracle_and_task_kernel(name):
         try:
             lib.emul_set_grad_kernel(0)
             direct = emul_lib.EmulField(images, patches).elbo_batch(tasks, mode=mode)
-        finally:
             lib.emul_set_grad_kernel(1)
-        march = emul_lib.EmulField(images, patches).elbo_batch(tasks, mode=mode)
-        try:
+            march = emul_lib.EmulField(images, patches).elbo_batch(tasks, mode=mode)
             lib.emul_set_grad_kernel(2)          # every source split into one block per image
             split = emul_lib.EmulField(images, patches).elbo_batch(tasks, mode=mode)
         finally:
-            lib.emul_set_grad_kernel(1)
+            lib.emul_set_grad_kernel(3)
         cases.assert_parity(ref, march, mode, name)
         cases.assert_parity(ref, split, mode, name + " (one block per image)")
         cases.assert_parity(ref, direct, mode, name)
@@ -72,11 +70,17 @@ def test_march_kernel_propagates_nonfinite_parameters(idx):
     images, patches, tasks = cases.get("two_body")
     bad = [(r, a, v.copy()) for r, a, v in tasks]
     bad[0][2][idx, 0] = np.nan
-    for mode in (0, 1):
-        ref = oracle_lib.OracleField(images, patches).elbo_batch(bad, mode=mode)
-        got = emul_lib.EmulField(images, patches).elbo_batch(bad, mode=mode)
-        assert ref["flags"].tolist() == [1, 0] and got["flags"].tolist() == [1, 0]
-        assert not np.isfinite(got["v"][0]) and np.isfinite(got["v"][1])
+    lib = emul_lib.load()
+    try:
+        for which in (1, 3):                      # march_kernel, unit kernels
+            lib.emul_set_grad_kernel(which)
+            for mode in (0, 1):
+                ref = oracle_lib.OracleField(images, patches).elbo_batch(bad, mode=mode)
+                got = emul_lib.EmulField(images, patches).elbo_batch(bad, mode=mode)
+                assert ref["flags"].tolist() == [1, 0] and got["flags"].tolist() == [1, 0]
+                assert not np.isfinite(got["v"][0]) and np.isfinite(got["v"][1])
+    finally:
+        lib.emul_set_grad_kernel(3)
 
 
 @pytest.mark.parametrize("seed", [0, 3, 7, 12, 19, 23, 31, 38])
@@ -84,10 +88,16 @@ def test_march_kernel_at_the_corners_of_the_parameter_box(seed):
     """Random small scenes with extreme source parameters (cases.random_extreme_scene): the recurrence of march_kernel
     against the oracle at the parity statement, value and gradient."""
     images, patches, tasks = cases.random_extreme_scene(seed)
-    for mode in (0, 1):
-        ref = oracle_lib.OracleField(images, patches).elbo_batch(tasks, mode=mode, n_threads=4)
-        got = emul_lib.EmulField(images, patches).elbo_batch(tasks, mode=mode)
-        cases.assert_parity(ref, got, mode, f"seed {seed}")
+    lib = emul_lib.load()
+    try:
+        for which in (1, 3):                      # march_kernel, unit kernels
+            lib.emul_set_grad_kernel(which)
+            for mode in (0, 1):
+                ref = oracle_lib.OracleField(images, patches).elbo_batch(tasks, mode=mode, n_threads=4)
+                got = emul_lib.EmulField(images, patches).elbo_batch(tasks, mode=mode)
+                cases.assert_parity(ref, got, mode, f"seed {seed} kernel {which}")
+    finally:
+        lib.emul_set_grad_kernel(3)
 
 
 def test_chunking_does_not_change_counters_or_parity():
@@ -137,15 +147,29 @@ def test_unit_kernel_matches_oracle_and_pixel_kernel(name):
     _tight(ref, unit, 2, name, 1e-10)
     assert np.array_equal(unit["counters"], direct["counters"])
     assert not np.array_equal(unit["h"], direct["h"]) or not unit["h"].any(), "the switch did not change kernels"
+    for mode in (0, 1):
+        r = oracle_lib.OracleField(images, patches).elbo_batch(tasks, mode=mode, n_threads=4)
+        g = emul_lib.EmulField(images, patches).elbo_batch(tasks, mode=mode)
+        cases.assert_parity(r, g, mode, name + f" unit_kernel mode {mode}")
+        _tight(r, g, mode, name, 1e-11)
+
+
+@pytest.mark.parametrize("name", ["two_body", "masked", "clipped_and_empty", "crowded", "wide_patch", "sharp_psf"])
+def test_unit_kernel_row_cuts_of_small_plans(name):
+    """A small plan cuts every (source, image) into up to 8 row ranges (one unit = one warp each) so that a single
+    celeste_elbo_single call spreads over the GPU; the partial vectors of the pieces meet in the epilogue.  Same
+    parity, same counters, in every mode."""
+    images, patches, tasks = cases.get(name)
+    lib = emul_lib.load()
     try:
-        lib.emul_set_grad_kernel(3)
-        for mode in (0, 1):
-            r = oracle_lib.OracleField(images, patches).elbo_batch(tasks, mode=mode, n_threads=4)
-            g = emul_lib.EmulField(images, patches).elbo_batch(tasks, mode=mode)
-            cases.assert_parity(r, g, mode, name + f" unit_kernel mode {mode}")
-            _tight(r, g, mode, name, 1e-11)
+        lib.emul_set_unit_target(10**6)
+        for mode in (0, 1, 2):
+            ref = oracle_lib.OracleField(images, patches).elbo_batch(tasks, mode=mode, n_threads=4)
+            got = emul_lib.EmulField(images, patches).elbo_batch(tasks, mode=mode)
+            cases.assert_parity(ref, got, mode, f"{name} mode {mode}, cut units")
+            _tight(ref, got, mode, name, 1e-10)
     finally:
-        lib.emul_set_grad_kernel(1)
+        lib.emul_set_unit_target(0)
 
 
 @pytest.mark.parametrize("idx", [0, 2, 3, 5, 10, 26])

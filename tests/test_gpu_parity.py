@@ -154,6 +154,32 @@ def test_plan_device_path_matches_host_path(cj):
     assert plan.launches(2) == 5 and plan.kernel_name(2) == "unit_kernel"      # slotbr, bg, walk, moment, epilogue
 
 
+def test_packed_hessian_layout_is_the_dense_upper_triangle(cj):
+    """celeste_plan_set_hessian_layout(CELESTE_HESS_PACKED28): 406 doubles per task = the upper triangle of the live
+    28 x 28 block, bit for bit the dense result; the rest of the dense 44 x 44 matrix is exactly zero / the mirror."""
+    images, patches, tasks = cases.get("small_field")
+    field = cj.DeviceField(images, patches)
+    plan = field.make_plan([t[0] for t in tasks], [t[1] for t in tasks])
+    vp = np.concatenate([t[2].ravel(order="F") for t in tasks])
+    dense = plan.run_host(vp, 2)
+    plan.set_hessian_layout(True)
+    packed = plan.run_host(vp, 2)
+    plan.set_hessian_layout(False)
+    n = plan.n_tasks
+    H = dense["h"].reshape(n, 44, 44)
+    P = packed["h"].reshape(n, 406)
+    iu = np.triu_indices(28)
+    assert np.array_equal(H[:, iu[0], iu[1]], P)
+    assert np.array_equal(H, H.transpose(0, 2, 1)) and not H[:, 28:, :].any()
+    assert np.array_equal(dense["d"], packed["d"]) and np.array_equal(dense["v"], packed["v"])
+    # Sa > 1 plans refuse the packed layout loudly
+    S = patches.shape[0]
+    multi = cj.Plan(field, [list(range(1, 4))], [[1, 2]])
+    with pytest.raises(cj._lib.CelesteError) as ei:
+        multi.set_hessian_layout(True)
+    assert ei.value.status == cj._lib.CELESTE_ERR_UNSUPPORTED
+
+
 def test_multi_field_plan_equals_per_field_plans(cj):
     """celeste_plan_create_multi: one plan over several inference boxes == the per-box plans, bit for bit."""
     a = cases.get("small_field")
@@ -200,20 +226,22 @@ def test_deterministic_and_mode_consistent(cj):
 @pytest.mark.parametrize("name", ["two_body", "masked", "clipped_and_empty", "crowded", "config2", "small_field", "wide_patch",
                                   "seven_images", "sharp_psf"])
 def test_march_kernel_matches_task_kernel(cj, name, monkeypatch):
-    """The two value / gradient kernels of the library -- march_kernel (row walks, exp recurrence; the default for
-    Sa = 1, K = 2) and task_kernel (direct evaluation; CELESTE_GRAD_KERNEL=task) -- agree to 1e-11, have identical
-    pixel-visit counters, and both meet the parity statement against the oracle."""
+    """Two of the value / gradient kernels of the library -- march_kernel (block per source, row walks with the exp
+    recurrence; CELESTE_GRAD_KERNEL=march) and task_kernel (direct evaluation; =task) -- agree to 1e-11, have identical
+    pixel-visit counters, and both meet the parity statement against the oracle.  (The default, the unit kernels, is
+    covered by test_unit_kernel_matches_pixel_kernel.)"""
     images, patches, tasks = cases.get(name)
     field = cj.DeviceField(images, patches)
     for mode in (0, 1):
         ref = oracle_lib.OracleField(images, patches).elbo_batch(tasks, mode=mode, n_threads=8)
         monkeypatch.setenv("CELESTE_GRAD_KERNEL", "task")
         direct = field.elbo_batch(tasks, mode=mode)
-        monkeypatch.delenv("CELESTE_GRAD_KERNEL")
+        monkeypatch.setenv("CELESTE_GRAD_KERNEL", "march")
         march = field.elbo_batch(tasks, mode=mode)
         monkeypatch.setenv("CELESTE_MARCH_SPLIT", "1")                 # every source: one block per image
         split = field.elbo_batch(tasks, mode=mode)
         monkeypatch.delenv("CELESTE_MARCH_SPLIT")
+        monkeypatch.delenv("CELESTE_GRAD_KERNEL")
         cases.assert_parity(ref, direct, mode, name + " task_kernel")
         cases.assert_parity(ref, march, mode, name + " march_kernel")
         cases.assert_parity(ref, split, mode, name + " march_kernel, one block per image")
@@ -247,13 +275,16 @@ def test_unit_kernel_matches_pixel_kernel(cj, name, monkeypatch):
     assert_tight(ref, unit, 2, name + " unit_kernel", rtol=1e-10)
     assert np.array_equal(unit["counters"], direct["counters"])
     assert not np.array_equal(unit["h"], direct["h"]) or not unit["h"].any(), "CELESTE_HESS_KERNEL did not switch kernels"
-    monkeypatch.setenv("CELESTE_GRAD_KERNEL", "unit")
     for mode in (0, 1):
         r = oracle_lib.OracleField(images, patches).elbo_batch(tasks, mode=mode, n_threads=8)
         g = field.elbo_batch(tasks, mode=mode)
         cases.assert_parity(r, g, mode, name + f" unit_kernel mode {mode}")
         assert_tight(r, g, mode, name + f" unit_kernel mode {mode}", rtol=2e-11)
-    monkeypatch.delenv("CELESTE_GRAD_KERNEL")
+        assert plan_kernel(cj, field, tasks, mode) == "unit_kernel"
+
+
+def plan_kernel(cj, field, tasks, mode):
+    return cj.Plan(field, [t[0] for t in tasks], [t[1] for t in tasks]).kernel_name(mode)
 
 
 @pytest.fixture(scope="module")
@@ -337,11 +368,12 @@ def test_two_field_plan_sampled_against_oracle(cj, field1000, mode):
 
 
 @pytest.mark.parametrize("name", sorted(cases.CASES))
-def test_march_kernel_tight_bound(cj, name):
-    """march_kernel against the oracle at 1e-11 on every named case it serves (Sa = 1, K = 2)."""
+def test_march_kernel_tight_bound(cj, name, monkeypatch):
+    """march_kernel (CELESTE_GRAD_KERNEL=march) against the oracle at 1e-11 on every named case it serves (Sa = 1, K = 2)."""
     images, patches, tasks = cases.get(name)
     if any(len(im.psf) != 2 for im in images):
         pytest.skip("K != 2: served by task_kernel")
+    monkeypatch.setenv("CELESTE_GRAD_KERNEL", "march")
     for mode in (0, 1):
         ref = oracle_lib.OracleField(images, patches).elbo_batch(tasks, mode=mode, n_threads=8)
         got = cj.DeviceField(images, patches).elbo_batch(tasks, mode=mode)

@@ -12,12 +12,20 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 out_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
 res = json.load(open(out_path)) if os.path.exists(out_path) else {}
+import re
+jobs = []
 for arg in sys.argv[1:]:
-    key, f = arg.split("=", 1)
+    key, f = arg.split("=", 1) if "=" in arg else ("auto", arg)
     raw = subprocess.run(["ncu", "-i", f, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
-    d = dict(zip(rows[0], rows[2]))
-    u = dict(zip(rows[0], rows[1]))
+    for vals in rows[2:]:
+        jobs.append((key, rows[0], rows[1], vals))
+for key, hdr, units, vals in jobs:
+    d = dict(zip(hdr, vals))
+    u = dict(zip(hdr, units))
+    if key == "auto":                  # "void unit_walk_kernel<2>(PlanDev, ...)" -> "unit_walk_kernel<2>"
+        m = re.search(r"(\w+(?:<[^>(]*>)?)\s*\(", d["Kernel Name"])
+        key = m.group(1)
 
     def val(k):
         return float(d[k])
@@ -32,10 +40,10 @@ for arg in sys.argv[1:]:
     dmul = val("smsp__sass_thread_inst_executed_op_dmul_pred_on.sum.per_cycle_elapsed")
     dadd = val("smsp__sass_thread_inst_executed_op_dadd_pred_on.sum.per_cycle_elapsed")
     flop = (2 * dfma + dmul + dadd) * cyc
-    mode = key[-2]
+    mode = key[-2] if key.endswith(">") else "2"
     res[key] = {
         "dram_bytes_per_launch": to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum"),
-        "sources": int(val("launch__grid_size")) if "march" in key or "task" in key else 10000,
+        "sources": int(val("launch__grid_size")) if ("march" in key or "task" in key) else 10000,
         "launch": f"the bench workload: one launch over the 10 000-source stripe (tools/profile_step.py 10 {mode} 3), "
                   "ncu --set full --clock-control none",
         "fp64_pipe_active_pct": val("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
