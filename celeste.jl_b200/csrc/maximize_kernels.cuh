@@ -113,7 +113,10 @@ __device__ inline double simplex_jac(const double* p, double alpha, int j, int j
 }
 
 // phase 0: first evaluation (at x);  phase 1: evaluation of the candidate x_new;  phase 2: to_bound!(x) -> vp_all
-__global__ void __launch_bounds__(TR_THREADS) newton_step_kernel(NewtonDev nb, int phase) {
+#ifndef CELESTE_NEWTON_MINB
+#define CELESTE_NEWTON_MINB 4
+#endif
+__global__ void __launch_bounds__(TR_THREADS, CELESTE_NEWTON_MINB) newton_step_kernel(NewtonDev nb, int phase) {
     __shared__ TrShared S;
     __shared__ double gb[NW_BOUND], bnd[NW_BOUND], xe[NW_FREE], sig[NW_BOX], d1[NW_BOX], d2[NW_BOX], pp[18], gnew[TR_MAXN];
     __shared__ double sbuf[TR_MAXN], xcand[NW_FREE];

@@ -3,7 +3,9 @@
 // Optim.NewtonTrustRegion (un-vendored dependency of ElboMaximize.jl:105-108,235) solves, per source and
 // per iterate,   min_s  g's + 1/2 s'Hs   s.t. |s| <= delta   for the 41 x 41 free-space Hessian.  cuSOLVER's
 // batched FP64 eigensolver and LAPACK-on-the-host both cost ~0.5 s per 1000 sources -- 100x the ELBO
-// evaluation itself -- so the subproblem gets its own kernel: ONE block per source,
+// evaluation itself -- so the subproblem gets its own code, ONE block per source.  Two implementations:
+// tr_solve_block (the product: Householder tridiagonalisation + O(n) work on the tridiagonal matrix, further down)
+// and tr_solve_block_jacobi (round 1: a full eigen-decomposition; kept as the A/B reference, -DCELESTE_TR_JACOBI):
 //   1. cyclic two-sided Jacobi eigen-decomposition in shared memory with the round-robin ("tournament")
 //      ordering: n/2 disjoint rotations per round are computed and applied in parallel;
 //   2. q = V'g; the secular equation |s(lam)| = delta by Newton on 1/|s| from just above the pole
@@ -35,7 +37,7 @@ struct TrShared {
 // Solve the subproblem held in S (S.A: symmetric n x n matrix zero-padded to the even size np, S.gsh: gradient
 // zero-padded) with all TR_THREADS threads of the block; S.A is destroyed.  s_out (n doubles, shared or global),
 // *m_out and *interior_out are written by the block; the caller synchronises before reading them.
-__device__ inline void tr_solve_block(TrShared& S, int n, double delta, double* s_out, double* m_out, int* interior_out) {
+__device__ inline void tr_solve_block_jacobi(TrShared& S, int n, double delta, double* s_out, double* m_out, int* interior_out) {
     double* A = S.A;
     double* V = S.V;
     double* rc = S.rc;
@@ -246,6 +248,317 @@ __device__ inline void tr_solve_block(TrShared& S, int n, double delta, double* 
         double t = 0.0;
         for (int j = 0; j < n; ++j) t += V[tid * TR_LD + j] * coef[j];
         s_out[tid] = t;
+    }
+}
+
+
+// 1 / x for the sequential tridiagonal recurrences (one reciprocal per step is the critical path there)
+__device__ __forceinline__ double tr_rcp(double x) {
+#if defined(__CUDA_ARCH__)
+    return __drcp_rn(x);
+#else
+    return 1.0 / x;
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------
+// The same subproblem WITHOUT an eigen-decomposition (the Jacobi version above costs ~8 sweeps x n^3 and was as
+// long as the ELBO evaluation it follows: 10 ms per 10 000 sources):
+//   1. Householder tridiagonalisation  H = Q T Q'  (4/3 n^3 flops, all threads of the block; reflectors kept in the
+//      lower triangle of S.A);
+//   2. everything that depended on eigenvalues is done on T in O(n) per evaluation by warp 0:
+//      lam_min by 32-way multisection on Sturm counts; |s(lam)| and d|s|^2/dlam by two solves with the LDL'
+//      factorisation of T + lam I (positive definite for lam > -lam_min); the secular equation by the SAME Newton
+//      iteration on 1/|s| from just above the pole, with the same stopping rule, as the eigenbasis version and the
+//      torch restatement (elbo_maximize.solve_tr_subproblem): in exact arithmetic the iterates coincide;
+//      the hard case (g orthogonal to the eigenvector z of lam_min, |s(-lam_min)| <= delta) with z from inverse
+//      iteration on T;
+//   3. s = Q s~ by the reflectors; predicted change m = g~'s~ + 1/2 s~'T s~.
+// Same interface as tr_solve_block_jacobi; S.A and S.V are destroyed.
+__device__ inline void tr_solve_block(TrShared& S, int n, double delta, double* s_out, double* m_out, int* interior_out) {
+#ifdef CELESTE_TR_JACOBI               // A/B knob: the eigen-decomposition version
+    tr_solve_block_jacobi(S, n, delta, s_out, m_out, interior_out);
+    return;
+#endif
+    double* A = S.A;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // work vectors carved out of S.V (free here)
+    double* hv = S.V;                 // current reflector v (length m)
+    double* hp = S.V + TR_MAXN;       // p = beta A22 v, then w
+    double* tau = S.V + 2 * TR_MAXN;  // beta_k of every reflector
+    double* v0s = S.V + 3 * TR_MAXN;  // v_0 of every reflector (its slot in A holds the sub-diagonal entry)
+    double* sc = S.V + 9 * TR_MAXN;   // scalars: [0] beta, [1] alpha, [2] K
+    double* dg = S.ev;                // diagonal of T
+    double* od = S.qg;                // off-diagonal: od[i] couples i and i + 1
+    double* gt = S.coef;              // g~ = Q'g, later s~
+    double* gsh = S.gsh;
+    auto wsum = [&](double v) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    };
+
+    // ---- 1. tridiagonalisation -------------------------------------------------------------------------------
+    for (int k = 0; k + 2 < n; ++k) {
+        const int m = n - k - 1;                  // x = A[k+1 .. n-1][k]
+        if (warp == 0) {
+            const int i0 = lane, i1 = lane + 32;
+            const double x0 = i0 < m ? A[(k + 1 + i0) * TR_LD + k] : 0.0;
+            const double x1 = i1 < m ? A[(k + 1 + i1) * TR_LD + k] : 0.0;
+            const double tail = wsum((i0 >= 1 ? x0 * x0 : 0.0) + x1 * x1);
+            const double xf = __shfl_sync(0xffffffffu, x0, 0);
+            double beta = 0.0, alpha = xf;
+            if (tail > 0.0) {
+                alpha = -copysign(sqrt(xf * xf + tail), xf);
+                const double v0 = xf - alpha;
+                beta = 2.0 / (v0 * v0 + tail);
+                if (i0 < m) hv[i0] = i0 == 0 ? v0 : x0;
+                if (i1 < m) hv[i1] = x1;
+            } else {
+                if (i0 < m) hv[i0] = 0.0;
+                if (i1 < m) hv[i1] = 0.0;
+            }
+            if (lane == 0) {
+                sc[0] = beta;
+                sc[1] = alpha;
+                tau[k] = beta;
+            }
+        }
+        __syncthreads();
+        const double beta = sc[0];
+        if (beta != 0.0) {                         // block-uniform
+            if (tid < m) {
+                const double* row = A + (k + 1 + tid) * TR_LD + (k + 1);
+                double t = 0.0;
+                for (int j = 0; j < m; ++j) t = fma(row[j], hv[j], t);
+                hp[tid] = beta * t;
+            }
+            __syncthreads();
+            if (warp == 0) {
+                const double t = wsum((lane < m ? hv[lane] * hp[lane] : 0.0) + (lane + 32 < m ? hv[lane + 32] * hp[lane + 32] : 0.0));
+                if (lane == 0) sc[2] = 0.5 * beta * t;
+            }
+            __syncthreads();
+            const double K = sc[2];
+            // A22 <- A22 - v w' - w v',  w = p - K v   (each thread forms the w it needs)
+            for (int e = tid; e < m * m; e += TR_THREADS) {
+                const int i = e / m, j = e - i * m;
+                const double wi = hp[i] - K * hv[i], wj = hp[j] - K * hv[j];
+                A[(k + 1 + i) * TR_LD + (k + 1 + j)] -= hv[i] * wj + wi * hv[j];
+            }
+        }
+        // keep the reflector in column k (below the sub-diagonal position) and the sub-diagonal entry
+        if (tid < m) A[(k + 1 + tid) * TR_LD + k] = tid == 0 ? sc[1] : hv[tid];
+        if (tid == 0) v0s[k] = hv[0];
+        __syncthreads();
+    }
+    if (tid < n) dg[tid] = A[tid * TR_LD + tid];
+    if (tid + 1 < n) od[tid] = A[(tid + 1) * TR_LD + tid];
+    if (tid < n) gt[tid] = gsh[tid];
+    __syncthreads();
+
+    if (warp == 0) {
+        // reflector k acts on entries k+1 .. n-1: v = (v0, A[k+2..][k])
+        auto apply = [&](int k, double* x) {
+            const double beta = tau[k];
+            if (beta == 0.0) return;
+            const int m = n - k - 1;
+            const int i0 = lane, i1 = lane + 32;
+            const double v0 = i0 < m ? (i0 == 0 ? v0s[k] : A[(k + 1 + i0) * TR_LD + k]) : 0.0;
+            const double v1 = i1 < m ? A[(k + 1 + i1) * TR_LD + k] : 0.0;
+            const double t = beta * wsum((i0 < m ? v0 * x[k + 1 + i0] : 0.0) + (i1 < m ? v1 * x[k + 1 + i1] : 0.0));
+            if (i0 < m) x[k + 1 + i0] -= t * v0;
+            if (i1 < m) x[k + 1 + i1] -= t * v1;
+            __syncwarp();
+        };
+        // ---- g~ = Q'g = H_{n-3} ... H_0 g
+        for (int k = 0; k + 2 < n; ++k) apply(k, gt);
+
+        // ---- 2. scalars on T -------------------------------------------------------------------------------
+        // Gershgorin bounds
+        double glo = 1.797e308, ghi = -1.797e308;
+        for (int i = lane; i < n; i += 32) {
+            const double r = (i > 0 ? fabs(od[i - 1]) : 0.0) + (i + 1 < n ? fabs(od[i]) : 0.0);
+            glo = fmin(glo, dg[i] - r);
+            ghi = fmax(ghi, dg[i] + r);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            glo = fmin(glo, __shfl_xor_sync(0xffffffffu, glo, o));
+            ghi = fmax(ghi, __shfl_xor_sync(0xffffffffu, ghi, o));
+        }
+        const double evabs_max = fmax(fabs(glo), fabs(ghi));
+        // number of eigenvalues of T below x (Sturm count by the pivots of T - x I)
+        double* od2 = S.V + 10 * TR_MAXN;            // squared off-diagonals
+        for (int i = lane; i + 1 < n; i += 32) od2[i] = od[i] * od[i];
+        __syncwarp();
+        auto below = [&](double x) {
+            int cnt = 0;
+            double q = dg[0] - x;
+            if (q < 0.0) ++cnt;
+            for (int i = 1; i < n; ++i) {
+                if (fabs(q) < 1e-300) q = q < 0.0 ? -1e-300 : 1e-300;
+                q = fma(-od2[i - 1], tr_rcp(q), dg[i] - x);
+                if (q < 0.0) ++cnt;
+            }
+            return cnt;
+        };
+        // lam_min: 32-way multisection of [glo, ghi]
+        double lo = glo - 1e-12 * (1.0 + evabs_max), hi = ghi + 1e-12 * (1.0 + evabs_max);
+        for (int round = 0; round < 14; ++round) {
+            const double x = lo + (hi - lo) * (double)(lane + 1) / 33.0;
+            const unsigned hit = __ballot_sync(0xffffffffu, below(x) >= 1);
+            const int first = hit ? __ffs(hit) - 1 : 32;                 // first lane whose x has an eigenvalue below it
+            const double nlo = first == 0 ? lo : lo + (hi - lo) * (double)first / 33.0;
+            const double nhi = first == 32 ? hi : lo + (hi - lo) * (double)(first + 1) / 33.0;
+            lo = nlo;
+            hi = nhi;
+            if (!(hi - lo > 4.0e-16 * (1.0 + evabs_max))) break;
+        }
+        const double lam_min = 0.5 * (lo + hi);
+
+        const double d2 = delta * delta;
+        // LDL' solves on lane 0 (results broadcast); x_out may alias rhs
+        double* sv = S.V + 4 * TR_MAXN;  // s(lam)
+        double* wv = S.V + 5 * TR_MAXN;  // (T + lam I)^-1 s
+        double* piv = S.V + 6 * TR_MAXN; // reciprocal pivots of T + lam I
+        double* lf = S.V + 11 * TR_MAXN; // its unit lower bidiagonal factor
+        auto solve_pair = [&](double lam, bool need_w, double& p2, double& sw) {
+            // lane 0: pivots, s = -(T + lam I)^-1 g~, optionally w = (T + lam I)^-1 s
+            if (lane == 0) {
+                // pivots q_i of T + lam I; piv[i] = 1 / q_i, lf[i] = od[i - 1] / q_{i-1} (the L factor)
+                double q = dg[0] + lam;
+                if (fabs(q) < 1e-300) q = 1e-300;
+                double rq = tr_rcp(q);
+                piv[0] = rq;
+                for (int i = 1; i < n; ++i) {
+                    lf[i] = od[i - 1] * rq;
+                    q = fma(-od[i - 1], lf[i], dg[i] + lam);
+                    if (fabs(q) < 1e-300) q = 1e-300;
+                    rq = tr_rcp(q);
+                    piv[i] = rq;
+                }
+                // forward: y_i = b_i - l_i y_{i-1};  back: x_i = (y_i - od_i x_{i+1}) / q_i
+                sv[0] = -gt[0];
+                for (int i = 1; i < n; ++i) sv[i] = fma(-lf[i], sv[i - 1], -gt[i]);
+                sv[n - 1] *= piv[n - 1];
+                for (int i = n - 2; i >= 0; --i) sv[i] = fma(-od[i], sv[i + 1], sv[i]) * piv[i];
+                if (need_w) {
+                    wv[0] = sv[0];
+                    for (int i = 1; i < n; ++i) wv[i] = fma(-lf[i], wv[i - 1], sv[i]);
+                    wv[n - 1] *= piv[n - 1];
+                    for (int i = n - 2; i >= 0; --i) wv[i] = fma(-od[i], wv[i + 1], wv[i]) * piv[i];
+                }
+            }
+            __syncwarp();
+            double a = 0.0, b = 0.0;
+            for (int i = lane; i < n; i += 32) {
+                a = fma(sv[i], sv[i], a);
+                if (need_w) b = fma(sv[i], wv[i], b);
+            }
+            p2 = wsum(a);
+            sw = wsum(b);
+            __syncwarp();
+        };
+        double p2 = 0.0, sw = 0.0;
+        const bool pos_def = lam_min >= 1e-8;
+        bool interior = false;
+        if (pos_def) {
+            solve_pair(0.0, false, p2, sw);
+            interior = p2 <= d2;
+        }
+        const double lam_lb = fmax(-lam_min, 0.0);
+        const double tiny = 1e-12 * (1.0 + evabs_max);
+        // Hard case (g orthogonal to the eigenvector z of lam_min and |s(-lam_min)| <= delta): detected by the first
+        // evaluation just above the pole -- any component of g~ along z would make |s| there astronomically large.
+        // Only then is z computed (inverse iteration on T) and the step completed along it to the boundary.
+        bool hard = false;
+        double* zv = S.V + 7 * TR_MAXN;
+        double* sh = S.V + 8 * TR_MAXN;
+        double ph2 = 0.0;
+        double lam = lam_lb + tiny;
+        if (!interior) {
+            solve_pair(lam, true, p2, sw);
+            if (lam_min <= 1e-8 && p2 <= d2) {
+                hard = true;
+                if (lane == 0) {
+                    const double shift = -lam_min + 4.0 * tiny * 1e-3;
+                    double q = dg[0] + shift;
+                    if (fabs(q) < 1e-300) q = 1e-300;
+                    double rq = tr_rcp(q);
+                    piv[0] = rq;
+                    for (int i = 1; i < n; ++i) {
+                        lf[i] = od[i - 1] * rq;
+                        q = fma(-od[i - 1], lf[i], dg[i] + shift);
+                        if (fabs(q) < 1e-300) q = 1e-300;
+                        rq = tr_rcp(q);
+                        piv[i] = rq;
+                    }
+                    for (int i = 0; i < n; ++i) zv[i] = ((i & 1) ? 1.0 : 0.73);
+                    for (int it = 0; it < 3; ++it) {
+                        for (int i = 1; i < n; ++i) zv[i] = fma(-lf[i], zv[i - 1], zv[i]);
+                        zv[n - 1] *= piv[n - 1];
+                        for (int i = n - 2; i >= 0; --i) zv[i] = fma(-od[i], zv[i + 1], zv[i]) * piv[i];
+                        double nr = 0.0;
+                        for (int i = 0; i < n; ++i) nr = fma(zv[i], zv[i], nr);
+                        nr = 1.0 / sqrt(nr);
+                        for (int i = 0; i < n; ++i) zv[i] *= nr;
+                    }
+                }
+                __syncwarp();
+                // s_h = s(lam_lb + tiny) with its z component removed
+                double c = 0.0;
+                for (int i = lane; i < n; i += 32) c = fma(zv[i], sv[i], c);
+                c = wsum(c);
+                double a = 0.0;
+                for (int i = lane; i < n; i += 32) {
+                    sh[i] = sv[i] - c * zv[i];
+                    a = fma(sh[i], sh[i], a);
+                }
+                ph2 = wsum(a);
+                __syncwarp();
+            } else {
+                for (int it = 0; it < 60; ++it) {
+                    if (it > 0) solve_pair(lam, true, p2, sw);
+                    const double pn = sqrt(p2);
+                    // d|s|^2 / dlam = -2 s'(T + lam I)^-1 s
+                    const double step = (pn - delta) / delta * p2 / (sw + 1e-300);
+                    double nw = lam + step;
+                    if (nw <= lam_lb) nw = 0.5 * (lam + lam_lb) + tiny;
+                    if (fabs(step) <= 1e-12 * (1.0 + fabs(lam))) break;
+                    lam = nw;
+                }
+            }
+        }
+        if (interior) {
+            lam = 0.0;
+            solve_pair(0.0, false, p2, sw);
+        } else if (!hard) {
+            solve_pair(lam, false, p2, sw);
+        }
+        // s~ -> gt's place is still needed for m: keep s~ in sv (or sh + tau z in the hard case)
+        if (hard) {
+            const double tz = sqrt(fmax(d2 - ph2, 0.0));
+            for (int i = lane; i < n; i += 32) sv[i] = sh[i] + tz * zv[i];
+            __syncwarp();
+        }
+        // m = g~'s~ + 1/2 s~'T s~
+        double mm = 0.0;
+        for (int i = lane; i < n; i += 32) {
+            double ts = dg[i] * sv[i];
+            if (i > 0) ts = fma(od[i - 1], sv[i - 1], ts);
+            if (i + 1 < n) ts = fma(od[i], sv[i + 1], ts);
+            mm += sv[i] * (gt[i] + 0.5 * ts);
+        }
+        mm = wsum(mm);
+        if (lane == 0) {
+            *m_out = mm;
+            *interior_out = interior ? 1 : 0;
+        }
+        // ---- 3. s = Q s~ = H_0 H_1 ... H_{n-3} s~
+        __syncwarp();
+        for (int k = n - 3; k >= 0; --k) apply(k, sv);
+        for (int i = lane; i < n; i += 32) s_out[i] = sv[i];
     }
 }
 

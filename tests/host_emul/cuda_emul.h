@@ -77,6 +77,15 @@ inline int __shfl_sync(unsigned, int v, int src) {
     c->warp_bar[w]->arrive_and_wait();
     return r;
 }
+inline double __shfl_sync(unsigned, double v, int src) {
+    auto* c = cuda_emul::ctx();
+    const int w = threadIdx.x / 32;
+    c->xchg_d[threadIdx.x] = v;
+    c->warp_bar[w]->arrive_and_wait();
+    const double r = c->xchg_d[w * 32 + src];
+    c->warp_bar[w]->arrive_and_wait();
+    return r;
+}
 inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
 inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }
