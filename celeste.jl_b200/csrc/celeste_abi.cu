@@ -883,10 +883,13 @@ int celeste_plan_create_multi(int32_t n_fields, celeste_field* const* fields, ce
         std::vector<UnitHdr> um, ub;
         std::vector<int> ucp;
         cudaDeviceGetAttribute(&pl->sms, cudaDevAttrMultiProcessorCount, pl->device);
-        // small plans are cut finer: aim at ~2 units per resident warp (SMs x 3 blocks x 4 warps); CELESTE_UNIT_TARGET
-        // overrides (kernel-tuning knob)
-        long target = 2L * pl->sms * CELESTE_UNIT_MINB * UNIT_WARPS;
-        if (const char* env = std::getenv("CELESTE_UNIT_TARGET")) target = std::atol(env);
+        // Rows per unit.  A plan that keeps every resident warp busy with >= 8 whole (sub, image) units is not cut (the
+        // per-unit prologue costs 5-20 % there: profiles/tuning_r02.md); a smaller plan -- a single celeste_elbo_single
+        // call, one rank's share of an 8-GPU run -- is cut at CELESTE_UNIT_ROWS rows so that its sources spread over the
+        // whole GPU and the launch has no tail.  Within either regime the cut depends on the patch only, so a task's
+        // result is bit-for-bit independent of what else is in the plan.  CELESTE_UNIT_ROWS=<n> forces n (0 = never).
+        long target = (long)n_subs * pl->N < 8L * pl->sms * CELESTE_UNIT_MINB * UNIT_WARPS ? CELESTE_UNIT_ROWS : 0;
+        if (const char* env = std::getenv("CELESTE_UNIT_ROWS")) target = std::atol(env);
         build_unit_list(n_subs, pl->N, sub_task.data(), sub_slot.data(), task_ptr, tfield.data(),
                         [&](int slot, int n, int& oh, int& ow, int& H2, int& W2) {
                             const celeste_field* f = fields[sfield[slot]];
@@ -1335,7 +1338,7 @@ int celeste_elbo_batch(celeste_field* f, int32_t n_tasks, const int32_t* task_pt
         // the kernel-selection knobs are read when a plan is built: a plan built under other knobs is another plan
         unsigned hsh = 2166136261u;
         for (const char* name : {"CELESTE_GRAD_KERNEL", "CELESTE_HESS_KERNEL", "CELESTE_MARCH_SPLIT", "CELESTE_MARCH_SPLIT_PCT",
-                                 "CELESTE_CHUNK_PIXELS", "CELESTE_UNIT_TARGET"}) {
+                                 "CELESTE_CHUNK_PIXELS", "CELESTE_UNIT_ROWS"}) {
             const char* e = std::getenv(name);
             for (const char* c = e ? e : ""; *c; ++c) hsh = (hsh ^ (unsigned char)*c) * 16777619u;
             hsh = (hsh ^ 0xffu) * 16777619u;

@@ -43,6 +43,9 @@ namespace celeste {
 #ifndef CELESTE_UNIT_MINB
 #define CELESTE_UNIT_MINB 3
 #endif
+#ifndef CELESTE_UNIT_ROWS
+#define CELESTE_UNIT_ROWS 16          // rows of a patch per unit (build_unit_list)
+#endif
 #ifndef CELESTE_UNIT_BG_MINB
 #define CELESTE_UNIT_BG_MINB 3
 #endif
@@ -868,20 +871,20 @@ __global__ void __launch_bounds__(UNIT_THREADS, CELESTE_UNIT_MOM_MINB)
 
 // Host side: the unit list of a plan (heaviest first), each unit's column segmentation, and the partial vectors:
 // chunk_ptr[sub * N + n] .. chunk_ptr[sub * N + n + 1] are the partials of (sub, image) for epilogue_kernel.
-// A (sub, image) is ONE unit unless the plan is small against `target_units` (the warps the GPU keeps resident): then
-// its rows are cut into up to `cut` units so that a few sources still spread over the whole GPU (the latency of a
-// celeste_elbo_single call; the launch tail of a rank of an 8-GPU run).
+// A (sub, image) is cut into units of at most `unit_rows` rows (equal pieces).  The cut depends on the patch ONLY, never
+// on what else is in the plan: a task's result is bit-for-bit the same alone, in a batch, or in another rank's shard.
+// Small pieces also let a single source spread over many SMs (the latency of a celeste_elbo_single call) and keep the
+// launch tail of a small plan (a rank of an 8-GPU run) short.
 // geo(slot, n, off_h, off_w, H2, W2) -> the patch box of a slot in image n.
 template <typename Geo>
 inline void build_unit_list(int n_subs, int N, const int* sub_task, const int* sub_slot, const int* task_ptr,
-                            const int* task_field, Geo geo, long target_units, std::vector<UnitHdr>& units,
+                            const int* task_field, Geo geo, long unit_rows, std::vector<UnitHdr>& units,
                             std::vector<UnitHdr>& bg_units, std::vector<int>& chunk_ptr, long long& maxpix) {
     units.clear();
     bg_units.clear();
     chunk_ptr.assign((size_t)n_subs * N + 1, 0);
     maxpix = 1;
-    const long whole = std::max(1L, (long)n_subs * N);
-    const int cut = (int)std::max(1L, std::min(8L, target_units / whole));     // units per (sub, image) at most
+    if (unit_rows <= 0) unit_rows = 1L << 30;                                  // 0: never cut
     std::vector<long> cost;
     for (int u = 0; u < n_subs; ++u) {
         const int t = sub_task[u];
@@ -917,7 +920,7 @@ inline void build_unit_list(int n_subs, int N, const int* sub_task, const int* s
                         }
                     }
                 }
-                pieces = std::max(1, std::min(cut, H2 / 4));
+                pieces = (int)std::max(1L, (H2 + unit_rows - 1) / unit_rows);
             }
             const int tn = u * N + n;
             chunk_ptr[tn + 1] = chunk_ptr[tn] + pieces;

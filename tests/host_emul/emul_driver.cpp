@@ -38,7 +38,7 @@ void galaxy_prototypes(double eta[NPROTO], double nu[NPROTO]) {
 long g_march_split = 6000;   // pixels above which a source gets one march block per image (emul_set_grad_kernel(2) lowers it)
 int g_grad_kernel = 3;   // 3: unit kernels where the product uses them (Sa = 1, K = 2); 1 / 2: march_kernel; 0: always task_kernel
 
-long g_unit_target = 0;  // build_unit_list: 0 = one unit per (sub, image); emul_set_unit_target cuts small plans finer
+long g_unit_target = CELESTE_UNIT_ROWS;  // build_unit_list: rows per unit (0 = never cut); emul_set_unit_target overrides
 int g_hess_kernel = 1;   // 1: unit_kernel<2> where the product would use it (Sa = 1, K = 2); 0: always pixel_kernel<2>
 
 // same launch sequence as celeste_abi.cu's unit path: setup (brightness moments for the epilogue), unit_kernel, epilogue

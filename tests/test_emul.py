@@ -155,21 +155,22 @@ def test_unit_kernel_matches_oracle_and_pixel_kernel(name):
 
 
 @pytest.mark.parametrize("name", ["two_body", "masked", "clipped_and_empty", "crowded", "wide_patch", "sharp_psf"])
-def test_unit_kernel_row_cuts_of_small_plans(name):
-    """A small plan cuts every (source, image) into up to 8 row ranges (one unit = one warp each) so that a single
-    celeste_elbo_single call spreads over the GPU; the partial vectors of the pieces meet in the epilogue.  Same
-    parity, same counters, in every mode."""
+@pytest.mark.parametrize("rows", [0, 3])
+def test_unit_kernel_row_cuts(name, rows):
+    """Every (source, image) is cut into units of at most CELESTE_UNIT_ROWS rows (one warp each; the partial vectors
+    of the pieces meet in the epilogue).  Other cuts -- none at all, 3 rows per unit -- give the same parity and the
+    same counters in every mode."""
     images, patches, tasks = cases.get(name)
     lib = emul_lib.load()
     try:
-        lib.emul_set_unit_target(10**6)
+        lib.emul_set_unit_target(rows)
         for mode in (0, 1, 2):
             ref = oracle_lib.OracleField(images, patches).elbo_batch(tasks, mode=mode, n_threads=4)
             got = emul_lib.EmulField(images, patches).elbo_batch(tasks, mode=mode)
-            cases.assert_parity(ref, got, mode, f"{name} mode {mode}, cut units")
+            cases.assert_parity(ref, got, mode, f"{name} mode {mode}, {rows} rows per unit")
             _tight(ref, got, mode, name, 1e-10)
     finally:
-        lib.emul_set_unit_target(0)
+        lib.emul_set_unit_target(16)
 
 
 @pytest.mark.parametrize("idx", [0, 2, 3, 5, 10, 26])
