@@ -1094,7 +1094,8 @@ static int launch_mode(celeste_plan* p, const double* vp_dev, double* v, double*
                 pu, p->unitmap_bg.p, p->n_units_bg, p->unit_queue.p, vp_dev, NAcc<MODE>::value);
         if (p->timing) CUDA_TRY(cudaEventRecord(p->ev_unit[0], st));
         if (p->n_units > 0)
-            unit_walk_kernel<MODE><<<grid_for(p->n_units, CELESTE_UNIT_MINB), UNIT_THREADS, unit_smem_bytes<MODE>(), st>>>(
+            unit_walk_kernel<MODE><<<grid_for(p->n_units, MODE == 2 ? CELESTE_UNIT_MINB : CELESTE_UNIT_MINB_GRAD), UNIT_THREADS,
+                                     unit_smem_bytes<MODE>(), st>>>(
                 pu, p->unitmap.p, p->n_units, p->unit_queue.p + 1, vp_dev);
         if (p->timing) CUDA_TRY(cudaEventRecord(p->ev_unit[1], st));
         p->unit_timed = p->timing;

@@ -872,6 +872,34 @@ __global__ void __launch_bounds__(EPI_THREADS) epilogue_kernel(PlanDev plan,
         if (tid < NLIVE) gacc[tid] = 0.0;
         if (tid == 0 && MODE >= 1) sigma_derivs(vs[3], vs[4], vs[5], J0, T0);
         __syncthreads();
+        // this thread's entries of the 28 x 28 block and what extra curvature term each takes: the same for every image
+        constexpr int EPI_ENT = (NLIVE * NLIVE + EPI_THREADS - 1) / EPI_THREADS;
+        int e_pp[EPI_ENT], e_q[EPI_ENT], e_kind[EPI_ENT], e_i[EPI_ENT], e_k1[EPI_ENT], e_k2[EPI_ENT];
+        if (MODE >= 2) {
+#pragma unroll
+            for (int j = 0; j < EPI_ENT; ++j) {
+                const int i = min(tid + j * EPI_THREADS, NLIVE * NLIVE - 1);
+                const int pp = i / NLIVE, q = i % NLIVE;
+                int ip = 0, kp = 0, iq = 0, kq = 0;
+                const bool bp = bright_of(pp, ip, kp), bq = bright_of(q, iq, kq);
+                e_pp[j] = pp;
+                e_q[j] = q;
+                e_kind[j] = 0;
+                e_i[j] = e_k1[j] = e_k2[j] = 0;
+                if (pp >= 3 && pp < 6 && q >= 3 && q < 6) {
+                    e_kind[j] = 1;
+                } else if (bp && bq && ip == iq) {
+                    e_kind[j] = 2;
+                    e_i[j] = ip;
+                    e_k1[j] = kp;
+                    e_k2[j] = kq;
+                } else if ((bp && q == 26 + ip) || (bq && pp == 26 + iq)) {
+                    e_kind[j] = 3;
+                    e_i[j] = bp ? ip : iq;
+                    e_k1[j] = bp ? kp : kq;
+                }
+            }
+        }
 
         for (int n = 0; n < plan.N; ++n) {
             const int tn = sub * plan.N + n;
@@ -933,29 +961,33 @@ __global__ void __launch_bounds__(EPI_THREADS) epilogue_kernel(PlanDev plan,
                     for (int i = tid; i < NY * NLIVE; i += EPI_THREADS) {
                         const int r = i / NLIVE, q = i % NLIVE;
                         double s = 0.0;
+#pragma unroll
                         for (int k = 0; k < NY; ++k) s += Hyy[r][k] * Jy[k][q];
                         Wm[r][q] = s;
                     }
                     __syncthreads();
                     // phase 4: Hacc += Jy' W + the curvature of Sigma(shape) + the curvature of c(a, beta), per entry
-                    for (int i = tid; i < NLIVE * NLIVE; i += EPI_THREADS) {
-                        const int pp = i / NLIVE, q = i % NLIVE;
+#pragma unroll
+                    for (int j = 0; j < EPI_ENT; ++j) {
+                        const int i = tid + j * EPI_THREADS;
+                        if (i >= NLIVE * NLIVE) break;
+                        const int pp = e_pp[j], q = e_q[j];
                         double s = 0.0;
+#pragma unroll
                         for (int r = 0; r < NY; ++r) s += Jy[r][pp] * Wm[r][q];
-                        if (pp >= 3 && pp < 6 && q >= 3 && q < 6) {
+                        const int kind = e_kind[j];
+                        if (kind == 1) {
                             // sum_k dL/dS_k * T0[k]   (transform_bvn_derivs_hessian!:481-488)
                             for (int k = 0; k < 3; ++k) s += ysum[ACC_G + 2 + k] * T0[k][pp - 3][q - 3];
-                        }
-                        int ip, kp, iq, kq;
-                        const bool bp = bright_of(pp, ip, kp), bq = bright_of(q, iq, kq);
-                        if (bp && bq && ip == iq) {
+                        } else if (kind == 2) {
                             // E * kappa kappa'
+                            const int ip = e_i[j], kp = e_k1[j], kq = e_k2[j];
                             const double ai = br[20 + ip], El = br[ip * 5 + b], Ell = br[10 + ip * 5 + b];
                             s += ai * (ysum[ACC_C1 + ip] * El * s_kap[kp] * s_kap[kq] +
                                        ysum[ACC_C1 + 2 + ip] * Ell * s_lam[kp] * s_lam[kq]);
-                        } else if ((bp && q == 26 + ip) || (bq && pp == 26 + iq)) {
+                        } else if (kind == 3) {
                             // the (a, beta) cross terms
-                            const int i2 = bp ? ip : iq, k2 = bp ? kp : kq;
+                            const int i2 = e_i[j], k2 = e_k1[j];
                             s += ysum[ACC_C1 + i2] * br[i2 * 5 + b] * s_kap[k2] + ysum[ACC_C1 + 2 + i2] * br[10 + i2 * 5 + b] * s_lam[k2];
                         }
                         Hacc[pp][q] += s;

@@ -43,6 +43,9 @@ namespace celeste {
 #ifndef CELESTE_UNIT_MINB
 #define CELESTE_UNIT_MINB 3
 #endif
+#ifndef CELESTE_UNIT_MINB_GRAD
+#define CELESTE_UNIT_MINB_GRAD CELESTE_UNIT_MINB      // value / gradient instantiations (few shared-memory accumulators)
+#endif
 #ifndef CELESTE_UNIT_ROWS
 #define CELESTE_UNIT_ROWS 16          // rows of a patch per unit (build_unit_list)
 #endif
@@ -53,6 +56,7 @@ namespace celeste {
 #define CELESTE_UNIT_MOM_MINB 5
 #endif
 constexpr int UNIT_WARPS = 4;
+constexpr int MOMENT_ROWBLOCK = 16;    // unit_moment_kernel: rows between exact starts of the row-direction recurrence
 constexpr int UNIT_THREADS = 32 * UNIT_WARPS;
 // per-(source, image) constants of the warp (shared memory): march's SI_* plus the second-derivative spline weights
 constexpr int SU_DDWX = 28, SU_DDWY = 32, SU_STRIDE = 36;
@@ -355,9 +359,12 @@ __global__ void __launch_bounds__(UNIT_THREADS, CELESTE_UNIT_BG_MINB)
                             const bool own = 2 * t + kk < len;
                             unsigned char nb = 0;
                             float xv = nanf("");
+                            double b0 = 0.0, b1 = 0.0;            // the sums so far: requested now, used after the mixture
                             if (own) {
                                 nb = *nbit;
                                 xv = px->x;
+                                b0 = bgE[0];
+                                b1 = bgE[1];
                             }
                             double R2 = 0.0, R3 = 0.0;
                             if (fast && own) {
@@ -392,8 +399,8 @@ __global__ void __launch_bounds__(UNIT_THREADS, CELESTE_UNIT_BG_MINB)
                                 const double f1 = theta * Fd + (1.0 - theta) * Fe;
                                 const double Es = si[SI_CB] * f0 + si[SI_CB + 1] * f1;
                                 const double E2s = si[SI_CB + 2] * f0 * f0 + si[SI_CB + 3] * f1 * f1;
-                                bgE[0] += Es;
-                                bgE[1] += E2s - Es * Es;
+                                bgE[0] = b0 + Es;
+                                bgE[1] = b1 + (E2s - Es * Es);
                                 cnt_inactive += 1.0;                                          // elbo_objective.jl:353-357
                             }
                             nbit += 2 * nH2;
@@ -414,7 +421,7 @@ __global__ void __launch_bounds__(UNIT_THREADS, CELESTE_UNIT_BG_MINB)
 
 // Phase A: the active source of a unit, row walks by lane pairs (see the file header).
 template <int MODE>
-__global__ void __launch_bounds__(UNIT_THREADS, CELESTE_UNIT_MINB)
+__global__ void __launch_bounds__(UNIT_THREADS, MODE == 2 ? CELESTE_UNIT_MINB : CELESTE_UNIT_MINB_GRAD)
     unit_walk_kernel(PlanDev plan, const UnitHdr* __restrict__ units, int n_units, int* __restrict__ queue,
                      const double* __restrict__ vp) {
     constexpr int NUA = NUAcc<MODE>::value;
@@ -764,6 +771,13 @@ __global__ void __launch_bounds__(UNIT_THREADS, CELESTE_UNIT_MOM_MINB)
             for (int q = 0; q < 15; ++q) Dm[q] = 0.0;
             const int nsb = (ncols + MARCH_MAXSEG - 1) / MARCH_MAXSEG;
             const int sw = (ncols + nsb - 1) / nsb;
+            // Start values of consecutive rows obey the same recurrence in the ROW direction (q(h + 1) - q(h) is linear
+            // in h): f(h + 1, c0) = f(h, c0) gh(h), gh(h + 1) = gh(h) exp(-L11), and the column ratio
+            // r(h + 1) = r(h) exp(-L12).  Used when a row is one segment, restarted exactly every MOMENT_ROWBLOCK rows and
+            // whenever the component was asleep at the last exact start.
+            const double ch = exp_scaled_tab(l11, -1.0, s_exptab), cl = exp_scaled_tab(fmin(fmax(l12, -700.0), 700.0), -1.0, s_exptab);
+            double f0 = 0.0, gh = 0.0, r0 = 0.0;
+            int since_exact = MOMENT_ROWBLOCK;                       // rows since the last exact start of column 0
             for (int h2 = uh.h2_lo; h2 < uh.h2_hi; ++h2) {
                 const double d1 = (double)(off_h + h2 + 1) - mu1;
                 double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0;
@@ -771,15 +785,33 @@ __global__ void __launch_bounds__(UNIT_THREADS, CELESTE_UNIT_MOM_MINB)
                     const int c1 = min(c0 + sw, ncols);
                     int c = c0;
                     while (c < c1) {
-                        // exact (re)start of the recurrence at column c (the rule of march_start)
                         double d2 = (double)(off_w + c + 1) - mu2;
-                        const double p1 = l11 * d1 + l12 * d2;
-                        const double p2 = l12 * d1 + l22 * d2;
-                        const double q = d1 * p1 + d2 * p2;
-                        const double ra = -(p2 + 0.5 * l22);
-                        const bool sleep = q > MARCH_Q_SLEEP || ra > 700.0;
-                        double f = sleep ? 0.0 : z * exp_scaled_tab(q, -0.5, s_exptab);
-                        double r = sleep ? 0.0 : exp_scaled_tab(fmin(ra, 700.0), 1.0, s_exptab);
+                        double f, r;
+                        bool sleep = false;
+                        if (nsb == 1 && c == 0 && since_exact < MOMENT_ROWBLOCK) {
+                            f0 *= gh;
+                            gh *= ch;
+                            r0 *= cl;
+                            f = f0;
+                            r = r0;
+                            ++since_exact;
+                        } else {
+                            // exact (re)start of the recurrence at column c (the rule of march_start)
+                            const double p1 = l11 * d1 + l12 * d2;
+                            const double p2 = l12 * d1 + l22 * d2;
+                            const double q = d1 * p1 + d2 * p2;
+                            const double ra = -(p2 + 0.5 * l22), rh = -(p1 + 0.5 * l11);
+                            sleep = q > MARCH_Q_SLEEP || ra > 700.0;
+                            f = sleep ? 0.0 : z * exp_scaled_tab(q, -0.5, s_exptab);
+                            r = sleep ? 0.0 : exp_scaled_tab(fmin(ra, 700.0), 1.0, s_exptab);
+                            if (nsb == 1 && c == 0) {
+                                const bool rowok = !sleep && rh < 700.0 && rh > -700.0;
+                                f0 = f;
+                                r0 = r;
+                                gh = rowok ? exp_scaled_tab(rh, 1.0, s_exptab) : 0.0;
+                                since_exact = rowok ? 1 : MOMENT_ROWBLOCK;
+                            }
+                        }
                         const int cend = sleep ? min(c1, c + MARCH_CAREFUL_COLS) : c1;
                         const double* lp = l5plane + (size_t)h2 * W2 + c;
 #define CEL_MOMENT_STEP(L5V)                 \

@@ -8,4 +8,4 @@ name=$1; shift
 root="$(cd "$(dirname "$0")/.." && pwd)"
 mkdir -p "$root/celeste.jl_b200/variants"
 nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -shared -Xcompiler -fPIC "$@" -Xptxas -v \
-  -o "$root/celeste.jl_b200/variants/libceleste_cuda_$name.so" "$root/celeste.jl_b200/csrc/celeste_abi.cu" 2>&1 | grep -A2 "march_kernelILi1" | tail -2
+  -o "$root/celeste.jl_b200/variants/libceleste_cuda_$name.so" "$root/celeste.jl_b200/csrc/celeste_abi.cu" 2>&1 | grep -A2 "unit_walk_kernelILi1" | tail -2
