@@ -234,6 +234,7 @@ struct celeste_plan {
     DevBuf<UnitHdr> unitmap, unitmap_bg;   // every unit, heaviest first; the units with a neighbour, by shared pixels
     DevBuf<int> unit_chunk_ptr;      // the partial vectors (= units) of each (sub, image)
     DevBuf<int> unit_queue;          // one counter per kernel of the sequence
+    DevBuf<double> bg_cnt;           // neighbour pixel-visits of each piece of unit_bg_kernel
     DevBuf<long long> l5_ptr;
     DevBuf<double> l5;               // L5 = dL/df1 of every active pixel (phase A -> phase B)
     DevBuf<PixRec> pix;              // pixel records of every unit in walk order (packed once, unit_pack_kernel)
@@ -899,7 +900,8 @@ int celeste_plan_create_multi(int32_t n_fields, celeste_field* const* fields, ce
                             H2 = pa.H2;
                             W2 = pa.W2;
                         },
-                        target, um, ub, ucp, pl->unit_maxpix);
+                        target, std::getenv("CELESTE_UNIT_PIXELS") ? std::atol(std::getenv("CELESTE_UNIT_PIXELS")) : 0L, um, ub, ucp,
+                        pl->unit_maxpix);
         pl->n_units = (int)um.size();
         pl->n_units_bg = (int)ub.size();
         std::vector<long long> l5_ptr((size_t)n_subs * pl->N, 0);
@@ -916,6 +918,7 @@ int celeste_plan_create_multi(int32_t n_fields, celeste_field* const* fields, ce
         CUDA_TRY(pl->unitmap_bg.upload(ub));
         CUDA_TRY(pl->unit_chunk_ptr.upload(ucp));
         CUDA_TRY(pl->unit_queue.alloc(4));
+        CUDA_TRY(pl->bg_cnt.alloc(std::max<size_t>(ub.size(), 1)));
         CUDA_TRY(pl->l5_ptr.upload(l5_ptr));
         CUDA_TRY(pl->l5.alloc(pl->use_unit_hess ? (size_t)l5_total : 0));
         CUDA_TRY(pl->pix.alloc((size_t)l5_total));
@@ -1020,7 +1023,7 @@ int celeste_plan_kernel_times(celeste_plan* p, float ms[3]) {
 int celeste_plan_launches(const celeste_plan* p, int32_t mode) {
     if (!p || p->n_tasks == 0) return 0;
     if ((mode <= 1 && p->use_unit_grad) || (mode == 2 && p->use_unit_hess))       // [slotbr,] [bg,] walk, [moment,] epilogue
-        return (mode >= 1 ? 1 : 0) + (p->n_units_bg > 0 ? 1 : 0) + 1 + (mode == 2 ? 1 : 0) + 1;
+        return 1 + (p->n_units_bg > 0 ? 1 : 0) + 1 + (mode == 2 ? 1 : 0) + 1;
     if (mode <= 1 && p->use_march) return 2;                                       // march, epilogue
     return (p->n_blocks > 0 ? 3 : 2) + ((mode == 2 && p->n_pairs > 0) ? 1 : 0);   // setup, pixel, [pair,] epilogue
 }
@@ -1062,6 +1065,7 @@ static PlanDev plan_dev(const celeste_plan* p) {
     d.partials = p->partials.p;
     d.bg_ptr = p->bg_ptr.p;
     d.bg = p->bg.p;
+    d.bg_cnt = p->bg_cnt.p;
     d.l5_ptr = p->l5_ptr.p;
     d.l5 = p->l5.p;
     d.pix = p->pix.p;
@@ -1084,14 +1088,14 @@ static int launch_mode(celeste_plan* p, const double* vp_dev, double* v, double*
             p->need_pack = false;
         }
         CUDA_TRY(cudaMemsetAsync(p->unit_queue.p, 0, 4 * sizeof(int), st));
-        if (MODE >= 1) slotbr_kernel<<<(p->n_subs + 127) / 128, 128, 0, st>>>(pu, vp_dev);
+        slotbr_kernel<<<(p->n_slots + 127) / 128, 128, 0, st>>>(pu, vp_dev);
         if (p->timing) CUDA_TRY(cudaEventRecord(p->ev[1], st));
         auto grid_for = [&](int n_units, int minb) {
             return std::max(1, std::min(p->sms * minb, (n_units + UNIT_WARPS - 1) / UNIT_WARPS));
         };
         if (p->n_units_bg > 0)
             unit_bg_kernel<<<grid_for(p->n_units_bg, CELESTE_UNIT_BG_MINB), UNIT_THREADS, unit_bg_smem_bytes(), st>>>(
-                pu, p->unitmap_bg.p, p->n_units_bg, p->unit_queue.p, vp_dev, NAcc<MODE>::value);
+                pu, p->unitmap_bg.p, p->n_units_bg, p->unit_queue.p, vp_dev);
         if (p->timing) CUDA_TRY(cudaEventRecord(p->ev_unit[0], st));
         if (p->n_units > 0)
             unit_walk_kernel<MODE><<<grid_for(p->n_units, MODE == 2 ? CELESTE_UNIT_MINB : CELESTE_UNIT_MINB_GRAD), UNIT_THREADS,
@@ -1339,7 +1343,7 @@ int celeste_elbo_batch(celeste_field* f, int32_t n_tasks, const int32_t* task_pt
         // the kernel-selection knobs are read when a plan is built: a plan built under other knobs is another plan
         unsigned hsh = 2166136261u;
         for (const char* name : {"CELESTE_GRAD_KERNEL", "CELESTE_HESS_KERNEL", "CELESTE_MARCH_SPLIT", "CELESTE_MARCH_SPLIT_PCT",
-                                 "CELESTE_CHUNK_PIXELS", "CELESTE_UNIT_ROWS"}) {
+                                 "CELESTE_CHUNK_PIXELS", "CELESTE_UNIT_ROWS", "CELESTE_UNIT_PIXELS"}) {
             const char* e = std::getenv(name);
             for (const char* c = e ? e : ""; *c; ++c) hsh = (hsh ^ (unsigned char)*c) * 16777619u;
             hsh = (hsh ^ 0xffu) * 16777619u;

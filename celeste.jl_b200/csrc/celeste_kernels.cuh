@@ -105,6 +105,7 @@ struct PlanDev {
     double* partials;        // n_blocks * NACC
     const long long* bg_ptr; // n_subs * N: offset of the (E_bg, V_bg) planes of (sub, image) in bg, -1 if the task has no neighbour
     double* bg;              // march_kernel's / unit kernels' per-(sub, image) background planes (E_bg, V_bg)
+    double* bg_cnt;          // neighbour pixel-visits counted by each piece of unit_bg_kernel
     const long long* l5_ptr; // n_subs * N: first pixel of (sub, image) in pix / l5 (unit kernels; walk order)
     double* l5;              // L5 = dL/df1 of every pixel of every unit (Hessian mode: phase A -> phase B)
     const struct PixRec* pix; // packed pixel records of every unit (unit_pack_kernel)
@@ -180,12 +181,12 @@ __global__ void setup_kernel(PlanDev plan, const double* __restrict__ vp) {
     }
 }
 
-// Brightness moments of the ACTIVE sources only (what epilogue_kernel reads from slotbr): the kernels that build their
-// own mixtures (unit_kernel) need nothing else from setup_kernel.  One thread per sub.
+// Brightness moments (source_brightness.jl:27-202) of EVERY slot of the plan, one thread per slot: what epilogue_kernel
+// reads for the active sources and what the unit kernels read for every source they walk (active or neighbour).  The
+// kernels that build their own mixtures (unit kernels) need nothing else from setup_kernel.
 __global__ void slotbr_kernel(PlanDev plan, const double* __restrict__ vp) {
-    const int u = blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= plan.n_subs) return;
-    const int slot = plan.sub_slot[u];
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= plan.n_slots) return;
     const double* vs = vp + (size_t)NPARAM * slot;
     double El[2][5], Ell[2][5];
     brightness_values(vs, El, Ell);

@@ -56,6 +56,7 @@ namespace celeste {
 #define CELESTE_UNIT_MOM_MINB 5
 #endif
 constexpr int UNIT_WARPS = 4;
+constexpr int UNIT_BG_PIXELS = 700;    // unit_bg_kernel: shared pixels (summed over neighbours) per piece, about
 constexpr int MOMENT_ROWBLOCK = 16;    // unit_moment_kernel: rows between exact starts of the row-direction recurrence
 constexpr int UNIT_THREADS = 32 * UNIT_WARPS;
 // per-(source, image) constants of the warp (shared memory): march's SI_* plus the second-derivative spline weights
@@ -79,6 +80,8 @@ struct UnitHdr {        // one unit = rows [h2_lo, h2_hi) of one (sub, image); b
     int h2_lo, h2_hi;   // rows of the active patch this unit walks (a large plan: all of them; a small plan is cut
                         // finer so that one source's evaluation spreads over many SMs)
     int first;          // 1: the unit that holds row 0 (it carries the (sub, image)'s neighbour counter)
+    int bgp0, bgp1;     // first unit: the (sub, image)'s pieces in unit_bg_kernel's list (their counters: plan.bg_cnt);
+                        // a piece of that list: bgp0 = its own slot
     int pad;
 };
 
@@ -107,15 +110,38 @@ constexpr size_t unit_smem_bytes() { return UnitWarpDoubles<MODE>::value * UNIT_
 constexpr size_t unit_bg_smem_bytes() { return (size_t)(NC2 * MREC + SU_STRIDE) * UNIT_WARPS * sizeof(double); }
 constexpr size_t unit_moment_smem_bytes() { return (size_t)(NC2 * MREC) * UNIT_WARPS * sizeof(double); }
 
-// per-(source, image) constants: march_stage_srcimg plus the second-derivative spline weights (MODE 2)
+// per-(source, image) constants of a walk (march's SI_* layout plus the second-derivative spline weights), staged by
+// FOUR lanes in parallel (which = 0..3): the brightness scalars of the image's band from the slot's precomputed
+// moments (slotbr_kernel; a_i E_l[i][b] in the summation order of brightness_values, as march_stage_srcimg computes
+// them), m_pos (linear_world_to_pix, wcs_utils.jl:14-18), the spline weights at the patch's fractional offsets.
 template <int MODE>
-__device__ inline void unit_stage_srcimg(const PatchDev& p, const double* vs, int band0, double* si) {
-    march_stage_srcimg<(MODE >= 1 ? 1 : 0)>(p, vs, band0, si);
-    if (MODE >= 2) {
-        const double ax = (double)(p.off_h + 1) - si[SI_M] + 26.0, ay = (double)(p.off_w + 1) - si[SI_M + 1] + 26.0;
-        double w[4], dw[4];
-        cubic_weights<2>(ax - floor(ax), w, dw, si + SU_DDWX);
-        cubic_weights<2>(ay - floor(ay), w, dw, si + SU_DDWY);
+__device__ inline void unit_stage_srcimg(const PatchDev& p, const double* vs, const double* br, int band0, double* si,
+                                         int which) {
+    if (which == 0) {
+        si[SI_CB + 0] = br[20] * br[band0];
+        si[SI_CB + 1] = br[21] * br[5 + band0];
+        si[SI_CB + 2] = br[20] * br[10 + band0];
+        si[SI_CB + 3] = br[21] * br[15 + band0];
+        si[SI_THETA] = vs[2];
+        si[SI_THETA + 1] = 0.0;
+    } else if (which == 1) {
+        double m1, m2;
+        march_m_pos(p, vs, m1, m2);
+        si[SI_M] = m1;
+        si[SI_M + 1] = m2;
+        for (int i = 0; i < 4; ++i) si[SI_J + i] = p.J[i];
+    } else {
+        double m1, m2;
+        march_m_pos(p, vs, m1, m2);
+        const double a = which == 2 ? (double)(p.off_h + 1) - m1 + 26.0 : (double)(p.off_w + 1) - m2 + 26.0;
+        double w[4], dw[4], ddw[4];
+        cubic_weights<MODE>(a - floor(a), w, dw, ddw);
+        const int o = which == 2 ? 0 : SI_WY - SI_WX;
+        for (int i = 0; i < 4; ++i) {
+            si[SI_WX + o + i] = w[i];
+            if (MODE >= 1) si[SI_DWX + o + i] = dw[i];
+            if (MODE >= 2) si[(which == 2 ? SU_DDWX : SU_DDWY) + i] = ddw[i];
+        }
     }
 }
 
@@ -261,7 +287,7 @@ __global__ void unit_pack_kernel(PlanDev plan, const UnitHdr* __restrict__ units
 // unit's (E_bg, V_bg) planes in plan.bg.  One warp per unit that has a neighbour; the walk is march_kernel's.
 __global__ void __launch_bounds__(UNIT_THREADS, CELESTE_UNIT_BG_MINB)
     unit_bg_kernel(PlanDev plan, const UnitHdr* __restrict__ units, int n_units, int* __restrict__ queue,
-                   const double* __restrict__ vp, int nacc /* doubles per partial vector: NAcc<mode> */) {
+                   const double* __restrict__ vp) {
     CEL_DYNAMIC_SMEM(smem);
     __shared__ double s_exptab[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, kk = tid & 1;
@@ -293,15 +319,16 @@ __global__ void __launch_bounds__(UNIT_THREADS, CELESTE_UNIT_BG_MINB)
         double cnt_inactive = 0.0;
         {
             {
-                const int tot = 2 * pa.H2 * pa.W2;
-                for (int i = lane; i < tot; i += 32) my_scratch[i] = 0.0;       // (E_bg, V_bg) pairs, row-major
+                const int i0 = 2 * uh.h2_lo * pa.W2, i1 = 2 * uh.h2_hi * pa.W2;  // this piece's rows of the planes
+                for (int i = i0 + lane; i < i1; i += 32) my_scratch[i] = 0.0;   // (E_bg, V_bg) pairs, row-major
             }
             for (int s = uh.slot0; s < uh.slot1; ++s) {
                 if (s == aslot) continue;
                 const PatchDev& p = prow[plan.src_row[s]];
                 // active pixels: rows off+1..off+H2, columns off+1..off+W2; the neighbour covers columns
                 // off+1..off+W2-1 only (strict `w2 < W2`, elbo_objective.jl:349)
-                const int h_lo = max(pa.off_h, p.off_h) + 1, h_hi = min(pa.off_h + pa.H2, p.off_h + p.H2);
+                // ... restricted to the rows h2_lo .. h2_hi - 1 of the active patch that this piece owns
+                const int h_lo = max(pa.off_h + uh.h2_lo, p.off_h) + 1, h_hi = min(pa.off_h + uh.h2_hi, p.off_h + p.H2);
                 const int w_lo = max(pa.off_w, p.off_w) + 1, w_hi = min(pa.off_w + pa.W2, p.off_w + p.W2 - 1);
                 if (h_hi < h_lo || w_hi < w_lo) continue;            // warp-uniform
                 const int bnh = h_hi - h_lo + 1, bnw = w_hi - w_lo + 1;
@@ -312,7 +339,7 @@ __global__ void __launch_bounds__(UNIT_THREADS, CELESTE_UNIT_BG_MINB)
                     galaxy_xixi(vs[3], vs[4], vs[5], xx[0], xx[1], xx[2]);
                     march_make_record(p, vs, xx, s_rec, lane);
                 }
-                if (lane == NC2) march_stage_srcimg<0>(p, vp + (size_t)NPARAM * s, band0, s_si);
+                if (lane >= NC2) unit_stage_srcimg<0>(p, vp + (size_t)NPARAM * s, plan.slotbr + (size_t)s * SLOTBR_STRIDE, band0, s_si, lane - NC2);
                 __syncwarp();
                 const int nsg = (bnw + MARCH_MAXSEG - 1) / MARCH_MAXSEG;
                 const int total = bnh * nsg;
@@ -414,7 +441,7 @@ __global__ void __launch_bounds__(UNIT_THREADS, CELESTE_UNIT_BG_MINB)
             }
         }
         for (int o = 16; o > 0; o >>= 1) cnt_inactive += __shfl_xor_sync(0xffffffffu, cnt_inactive, o);
-        if (lane == 0) plan.partials[(size_t)uh.pidx * nacc + ACC_CNT_INACTIVE] = cnt_inactive;
+        if (lane == 0) plan.bg_cnt[uh.bgp0] = cnt_inactive;
         __syncwarp();
     }
 }
@@ -484,7 +511,7 @@ __global__ void __launch_bounds__(UNIT_THREADS, MODE == 2 ? CELESTE_UNIT_MINB : 
             galaxy_xixi(vs[3], vs[4], vs[5], xx[0], xx[1], xx[2]);      // XiXi: one sin / cos per record lane, in parallel
             march_make_record(pa, vs, xx, s_rec, lane);
         }
-        if (lane == NC2) unit_stage_srcimg<MODE>(pa, vp + (size_t)NPARAM * aslot, band0, s_si);
+        if (lane >= NC2) unit_stage_srcimg<MODE>(pa, vp + (size_t)NPARAM * aslot, plan.slotbr + (size_t)aslot * SLOTBR_STRIDE, band0, s_si, lane - NC2);
         __syncwarp();
 
         // ---- phase A: the active source, row walks by lane pairs ------------------------------------------------
@@ -706,7 +733,10 @@ __global__ void __launch_bounds__(UNIT_THREADS, MODE == 2 ? CELESTE_UNIT_MINB : 
         if (lane == 0) {
             out[ACC_VAL] = val;
             out[ACC_CNT_ACTIVE] = cnt_active;
-            if (!(uh.hasbg && uh.first)) out[ACC_CNT_INACTIVE] = 0.0;   // (else: written by unit_bg_kernel)
+            double ci = 0.0;                                   // neighbour visits of the (sub, image): exact integer sums
+            if (uh.hasbg && uh.first)
+                for (int q = uh.bgp0; q < uh.bgp1; ++q) ci += plan.bg_cnt[q];
+            out[ACC_CNT_INACTIVE] = ci;
         }
         if (MODE == 2 && lane < 3) out[ACC_CC + 7 + lane] = 0.0;
         for (int a = lane; a < NUA; a += 32) {
@@ -910,7 +940,7 @@ __global__ void __launch_bounds__(UNIT_THREADS, CELESTE_UNIT_MOM_MINB)
 // geo(slot, n, off_h, off_w, H2, W2) -> the patch box of a slot in image n.
 template <typename Geo>
 inline void build_unit_list(int n_subs, int N, const int* sub_task, const int* sub_slot, const int* task_ptr,
-                            const int* task_field, Geo geo, long unit_rows, std::vector<UnitHdr>& units,
+                            const int* task_field, Geo geo, long unit_rows, long unit_pixels, std::vector<UnitHdr>& units,
                             std::vector<UnitHdr>& bg_units, std::vector<int>& chunk_ptr, long long& maxpix) {
     units.clear();
     bg_units.clear();
@@ -953,6 +983,8 @@ inline void build_unit_list(int n_subs, int N, const int* sub_task, const int* s
                     }
                 }
                 pieces = (int)std::max(1L, (H2 + unit_rows - 1) / unit_rows);
+                if (unit_pixels > 0)      // ... or by pixels: pieces of about unit_pixels pixels, at least 4 rows each
+                    pieces = (int)std::max(1L, std::min((long)std::max(1, H2 / 4), ((long)H2 * W2 + unit_pixels / 2) / unit_pixels));
             }
             const int tn = u * N + n;
             chunk_ptr[tn + 1] = chunk_ptr[tn] + pieces;
@@ -976,9 +1008,24 @@ inline void build_unit_list(int n_subs, int N, const int* sub_task, const int* s
                         }
                     }
                 }
+                if (pc == 0 && x.hasbg) {
+                    // neighbour work of the (sub, image): row pieces of at most ~UNIT_BG_PIXELS shared pixels, so that one
+                    // crowded source is not the tail of unit_bg_kernel
+                    const int bp = std::max(1, std::min(std::max(1, H2 / 2), (x.nbpix + UNIT_BG_PIXELS - 1) / UNIT_BG_PIXELS));
+                    x.bgp0 = (int)bg_units.size();
+                    x.bgp1 = x.bgp0 + bp;
+                    for (int b = 0; b < bp; ++b) {
+                        UnitHdr y = uh;
+                        y.h2_lo = (int)((long)H2 * b / bp);
+                        y.h2_hi = (int)((long)H2 * (b + 1) / bp);
+                        y.bgp0 = x.bgp0 + b;
+                        y.bgp1 = y.bgp0 + 1;
+                        y.nbpix = uh.nbpix / bp;
+                        bg_units.push_back(y);
+                    }
+                }
                 units.push_back(x);
                 cost.push_back((long)std::max(rows, 0) * std::max(W2, 0));
-                if (pc == 0 && x.hasbg) bg_units.push_back(x);
             }
         }
     }
