@@ -241,6 +241,7 @@ struct celeste_plan {
     int n_units = 0, n_units_bg = 0, sms = 148;
     long long unit_maxpix = 1;
     bool use_unit_hess = false, use_unit_grad = false;
+    bool block_epilogue = false;     // CELESTE_EPILOGUE=block: epilogue_kernel<2> instead of epilogue_hess_kernel (A/B knob)
     bool need_pack = false;          // pix is filled on the first evaluation (needs the uploaded plan arrays)
     DevBuf<PairHdr> pairmap;
     DevBuf<double> slotimg, slotbr, partials, pair_partials;
@@ -821,6 +822,8 @@ int celeste_plan_create_multi(int32_t n_fields, celeste_field* const* fields, ce
         pl->use_march = shape_ok && g_march;
         pl->use_unit_grad = shape_ok && !g_march && !g_task;
         pl->use_unit_hess = shape_ok && !(henv && std::strcmp(henv, "pixel") == 0);
+        const char* eenv = std::getenv("CELESTE_EPILOGUE");
+        pl->block_epilogue = eenv && std::strcmp(eenv, "block") == 0;
     }
     if (pl->use_march) {
         // A source normally gets ONE block (all its images: best packing of its rows into the block's walk slots).
@@ -1109,8 +1112,12 @@ static int launch_mode(celeste_plan* p, const double* vp_dev, double* v, double*
                     pu, p->unitmap.p, p->n_units, p->unit_queue.p + 2, vp_dev);
         }
         if (p->timing) CUDA_TRY(cudaEventRecord(p->ev[2], st));
-        epilogue_kernel<MODE><<<p->n_tasks, EPI_THREADS, 0, st>>>(pu, vp_dev, v, d, h, counters, flags,
-                                                                  p->hess_layout == CELESTE_HESS_PACKED28 ? 1 : 0);
+        if (MODE == 2 && !p->block_epilogue)
+            epilogue_hess_kernel<<<(p->n_tasks + EPH_WARPS - 1) / EPH_WARPS, 32 * EPH_WARPS, 0, st>>>(
+                pu, vp_dev, v, d, h, counters, flags, p->hess_layout == CELESTE_HESS_PACKED28 ? 1 : 0);
+        else
+            epilogue_kernel<MODE><<<p->n_tasks, EPI_THREADS, 0, st>>>(pu, vp_dev, v, d, h, counters, flags,
+                                                                      p->hess_layout == CELESTE_HESS_PACKED28 ? 1 : 0);
         if (p->timing) CUDA_TRY(cudaEventRecord(p->ev[3], st));
         CUDA_TRY(cudaGetLastError());
         return CELESTE_OK;
@@ -1343,7 +1350,7 @@ int celeste_elbo_batch(celeste_field* f, int32_t n_tasks, const int32_t* task_pt
         // the kernel-selection knobs are read when a plan is built: a plan built under other knobs is another plan
         unsigned hsh = 2166136261u;
         for (const char* name : {"CELESTE_GRAD_KERNEL", "CELESTE_HESS_KERNEL", "CELESTE_MARCH_SPLIT", "CELESTE_MARCH_SPLIT_PCT",
-                                 "CELESTE_CHUNK_PIXELS", "CELESTE_UNIT_ROWS", "CELESTE_UNIT_PIXELS"}) {
+                                 "CELESTE_CHUNK_PIXELS", "CELESTE_UNIT_ROWS", "CELESTE_UNIT_PIXELS", "CELESTE_EPILOGUE"}) {
             const char* e = std::getenv(name);
             for (const char* c = e ? e : ""; *c; ++c) hsh = (hsh ^ (unsigned char)*c) * 16777619u;
             hsh = (hsh ^ 0xffu) * 16777619u;

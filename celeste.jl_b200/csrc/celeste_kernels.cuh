@@ -1090,6 +1090,227 @@ __global__ void __launch_bounds__(EPI_THREADS) epilogue_kernel(PlanDev plan,
 }
 
 // ------------------------------------------------------------------------------------------------
+// epilogue_hess_kernel: the Hessian-mode epilogue of plans whose tasks all have Sa = 1 (the production shape), ONE WARP
+// per task.  Same chain rule as epilogue_kernel<2>, organised around the sparsity of Jy = d(c, y) / d(28 live parameters):
+// a parameter reaches at most three (c, y) rows -- position -> x (2 rows); gal_frac_dev -> theta (1); axis ratio, angle,
+// radius -> Sigma (3); the brightness parameters and is_star of type i -> (A_i, B_i) (2) -- so an entry of the 28 x 28
+// block costs <= 3 x 3 terms instead of two dense 10-term products, the 406 upper-triangle entries live in registers
+// (13 per lane) across the images, and nothing synchronises but the warp.  epilogue_kernel<2> (a block per task, dense
+// products through shared memory, 20 block barriers per task) took 0.6 ms per 10 000 tasks -- 12 % of the Hessian step.
+constexpr int EPH_WARPS = 4;
+constexpr int EPH_ENT = (HESS_PACKED_LEN + 31) / 32;   // upper-triangle entries per lane
+
+struct EphWarp {             // per-warp shared memory
+    double ysum[NACC_MODE2];
+    double Hyy[NY][NY];
+    double jv[NLIVE][3];     // the <= 3 non-zero entries of each column of Jy (zero-padded) ...
+    int jr[NLIVE][3];        // ... and their rows
+    double J0[3][3], T0[3][3][3];
+    double kap[10], lam[10];
+    double El[2][5], Ell[2][5];
+};
+
+__global__ void __launch_bounds__(32 * EPH_WARPS) epilogue_hess_kernel(PlanDev plan, const double* __restrict__ vp,
+                                                                       double* __restrict__ out_v, double* __restrict__ out_d,
+                                                                       double* __restrict__ out_h,
+                                                                       long long* __restrict__ out_counters,
+                                                                       int* __restrict__ out_flags, int hess_packed) {
+    __shared__ EphWarp sw[EPH_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int t = blockIdx.x * EPH_WARPS + warp;
+    if (t >= plan.n_tasks) return;
+    if (plan.task_mask && !plan.task_mask[t]) return;
+    EphWarp& W = sw[warp];
+    const int sub = plan.sub_ptr[t];                      // Sa == 1
+    const int aslot = plan.sub_slot[sub];
+    const double* vs = vp + (size_t)NPARAM * aslot;
+    const double* br = plan.slotbr + (size_t)aslot * SLOTBR_STRIDE;
+    const FieldDev field = plan.fields[plan.task_field[t]];
+    if (lane == 0) sigma_derivs(vs[3], vs[4], vs[5], W.J0, W.T0);
+    if (lane < 10) {
+        W.El[lane / 5][lane % 5] = br[lane];
+        W.Ell[lane / 5][lane % 5] = br[10 + lane];
+    }
+    // this lane's upper-triangle entries (pp <= q) and the extra curvature each takes -- the same for every image
+    int e_code[EPH_ENT];
+#pragma unroll
+    for (int j = 0; j < EPH_ENT; ++j) {
+        const int e = min(lane + 32 * j, HESS_PACKED_LEN - 1);
+        int pp = 0, rem = e;                              // row-major upper triangle: row pp holds NLIVE - pp entries
+        while (rem >= NLIVE - pp) {
+            rem -= NLIVE - pp;
+            ++pp;
+        }
+        const int q = pp + rem;
+        int ip = 0, kp = 0, iq = 0, kq = 0, kind = 0, a = 0, k1 = 0, k2 = 0;
+        const bool bp = bright_of(pp, ip, kp), bq = bright_of(q, iq, kq);
+        if (pp >= 3 && pp < 6 && q >= 3 && q < 6) {
+            kind = 1;
+        } else if (bp && bq && ip == iq) {
+            kind = 2;
+            a = ip;
+            k1 = kp;
+            k2 = kq;
+        } else if ((bp && q == 26 + ip) || (bq && pp == 26 + iq)) {
+            kind = 3;
+            a = bp ? ip : iq;
+            k1 = bp ? kp : kq;
+        }
+        e_code[j] = pp | (q << 5) | (kind << 10) | (a << 12) | (k1 << 13) | (k2 << 17);
+    }
+    double hacc[EPH_ENT];
+#pragma unroll
+    for (int j = 0; j < EPH_ENT; ++j) hacc[j] = 0.0;
+    double g = 0.0, val = 0.0, cnt0 = 0.0, cnt1 = 0.0;
+    const double a0 = br[20], a1 = br[21];
+    __syncwarp();
+
+    for (int n = 0; n < plan.N; ++n) {
+        const int tn = sub * plan.N + n;
+        const int c0 = plan.chunk_ptr[tn], c1 = plan.chunk_ptr[tn + 1];
+        const PatchDev& p = field.patches[plan.src_row[aslot] + (size_t)n * field.S_tot];
+        const int b = field.images[n].band - 1;
+        // 1. fixed-order sum of the unit partials; band coefficients
+        for (int a = lane; a < NACC_MODE2; a += 32) {
+            double s = 0.0;
+            for (int c = c0; c < c1; ++c) s += plan.partials[(size_t)c * NACC_MODE2 + a];
+            W.ysum[a] = s;
+        }
+        if (lane == 31) band_coefs(b, W.kap, W.lam);
+        __syncwarp();
+        // 2. Hyy from the packed sums; the non-zero entries of every column of Jy
+        for (int e = lane; e < NY * NY; e += 32) {
+            const int r = e / NY, c = e % NY;
+            const int lo = r < c ? r : c, hi = r < c ? c : r;
+            W.Hyy[r][c] = hi < 4 ? W.ysum[ACC_CC + tri4(lo, hi)]
+                                 : (lo < 4 ? W.ysum[ACC_CR + lo * 6 + (hi - 4)] : W.ysum[ACC_HH + tri6(lo - 4, hi - 4)]);
+        }
+        if (lane < NLIVE) {
+            const int q = lane;
+            double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+            int r0 = 0, r1 = 0, r2 = 0;
+            int i, k;
+            if (q < 2) {                                  // dx_a / dpos_q = -J[a][q]
+                r0 = 4;
+                r1 = 5;
+                v0 = -p.J[2 * q];
+                v1 = -p.J[2 * q + 1];
+            } else if (q == 2) {
+                r0 = 9;
+                v0 = 1.0;
+            } else if (q < 6) {
+                r0 = 6;
+                r1 = 7;
+                r2 = 8;
+                v0 = W.J0[0][q - 3];
+                v1 = W.J0[1][q - 3];
+                v2 = W.J0[2][q - 3];
+            } else if (bright_of(q, i, k)) {
+                const double ai = i == 0 ? a0 : a1;
+                r0 = i;
+                r1 = 2 + i;
+                v0 = ai * W.El[i][b] * W.kap[k];
+                v1 = ai * W.Ell[i][b] * W.lam[k];
+            } else {                                      // is_star
+                i = q - 26;
+                r0 = i;
+                r1 = 2 + i;
+                v0 = W.El[i][b];
+                v1 = W.Ell[i][b];
+            }
+            W.jr[q][0] = r0;
+            W.jr[q][1] = r1;
+            W.jr[q][2] = r2;
+            W.jv[q][0] = v0;
+            W.jv[q][1] = v1;
+            W.jv[q][2] = v2;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            val += W.ysum[ACC_VAL];
+            cnt0 += W.ysum[ACC_CNT_ACTIVE];
+            cnt1 += W.ysum[ACC_CNT_INACTIVE];
+        }
+        // 3. gradient: row r of the first-order sums is C1 (r < 4) or G (r >= 4)
+        if (lane < NLIVE) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const int r = W.jr[lane][a];
+                g = fma(W.jv[lane][a], r < 4 ? W.ysum[ACC_C1 + r] : W.ysum[ACC_G + r - 4], g);
+            }
+        }
+        // 4. H[pp][q] += Jy[:, pp]' Hyy Jy[:, q] + the curvature of Sigma(shape) and of c(a, beta)
+#pragma unroll
+        for (int j = 0; j < EPH_ENT; ++j) {
+            const int code = e_code[j];
+            const int pp = code & 31, q = (code >> 5) & 31, kind = (code >> 10) & 3;
+            double s = 0.0;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const int ra = W.jr[pp][a];
+                double tq = 0.0;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) tq = fma(W.Hyy[ra][W.jr[q][c]], W.jv[q][c], tq);
+                s = fma(W.jv[pp][a], tq, s);
+            }
+            if (kind == 1) {
+                // sum_k dL/dS_k * T0[k]   (transform_bvn_derivs_hessian!:481-488)
+                for (int k = 0; k < 3; ++k) s += W.ysum[ACC_G + 2 + k] * W.T0[k][pp - 3][q - 3];
+            } else if (kind == 2) {
+                const int ip = (code >> 12) & 1, kp = (code >> 13) & 15, kq = (code >> 17) & 15;
+                const double ai = ip == 0 ? a0 : a1;      // E * kappa kappa'
+                s += ai * (W.ysum[ACC_C1 + ip] * W.El[ip][b] * W.kap[kp] * W.kap[kq] +
+                           W.ysum[ACC_C1 + 2 + ip] * W.Ell[ip][b] * W.lam[kp] * W.lam[kq]);
+            } else if (kind == 3) {
+                const int i2 = (code >> 12) & 1, k2 = (code >> 13) & 15;      // the (a, beta) cross terms
+                s += W.ysum[ACC_C1 + i2] * W.El[i2][b] * W.kap[k2] + W.ysum[ACC_C1 + 2 + i2] * W.Ell[i2][b] * W.lam[k2];
+            }
+            hacc[j] += s;
+        }
+        __syncwarp();                                     // the image's tables are consumed
+    }
+
+    int bad = 0;
+    if (lane < NLIVE) bad |= !isfinite(g);
+    for (int i = lane; i < NPARAM; i += 32) out_d[(size_t)NPARAM * sub + i] = 0.0;
+    __syncwarp();
+    if (lane < NLIVE) out_d[(size_t)NPARAM * sub + lane] = g;
+    if (hess_packed) {
+        double* Hout = out_h + (size_t)HESS_PACKED_LEN * t;
+#pragma unroll
+        for (int j = 0; j < EPH_ENT; ++j) {
+            const int e = lane + 32 * j;
+            if (e < HESS_PACKED_LEN) {
+                Hout[e] = hacc[j];
+                bad |= !isfinite(hacc[j]);
+            }
+        }
+    } else {
+        double* Hout = out_h + plan.h_ptr[t];
+        for (int i = lane; i < NPARAM * NPARAM; i += 32) Hout[i] = 0.0;      // rows / cols 29..44 (ids.k) stay zero
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < EPH_ENT; ++j) {
+            const int e = lane + 32 * j;
+            if (e < HESS_PACKED_LEN) {
+                const int pp = e_code[j] & 31, q = (e_code[j] >> 5) & 31;
+                Hout[pp + (size_t)q * NPARAM] = hacc[j];                     // exactly symmetric by construction
+                Hout[q + (size_t)pp * NPARAM] = hacc[j];
+                bad |= !isfinite(hacc[j]);
+            }
+        }
+    }
+    if (lane == 0) {
+        out_v[t] = val;
+        out_counters[2 * t] = (long long)(cnt0 + 0.5);
+        out_counters[2 * t + 1] = (long long)(cnt1 + 0.5);
+        bad |= !isfinite(val);
+    }
+    const unsigned anybad = __ballot_sync(0xffffffffu, bad != 0);
+    if (lane == 0) out_flags[t] = anybad ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // render_kernel: the value-only full-image render -- what bin/write_celeste_expectation.jl:111-156
 // (fill_celeste_expectation!) computes by calling add_pixel_term! in value mode on EVERY pixel of every image:
 //     out[h, w] = E_G - sky = sum over the sources whose patch covers (h, w) of  a1 E_l1 f0 + a2 E_l2 f1

@@ -94,7 +94,11 @@ void run_unit(PlanDev pd, const FieldDev& fd, const double* vp, double* v, doubl
     if (MODE == 2)
         cuda_emul::launch(unit_moment_kernel, grid, UNIT_THREADS, unit_moment_smem_bytes(), pd, (const UnitHdr*)units.data(),
                           (int)units.size(), &queue[2], vp);
-    cuda_emul::launch(epilogue_kernel<MODE>, pd.n_tasks, EPI_THREADS, 0, pd, vp, v, d, h, counters, flags, 0);
+    if (MODE == 2)
+        cuda_emul::launch(epilogue_hess_kernel, (pd.n_tasks + EPH_WARPS - 1) / EPH_WARPS, 32 * EPH_WARPS, 0, pd, vp, v, d, h, counters,
+                          flags, 0);
+    else
+        cuda_emul::launch(epilogue_kernel<MODE>, pd.n_tasks, EPI_THREADS, 0, pd, vp, v, d, h, counters, flags, 0);
 }
 
 template <int MODE>
