@@ -190,31 +190,28 @@ __device__ __forceinline__ double unit_pixel_term(double* acc, const PixelConsts
     double b[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i) b[i] = (i == 2 || i == 3) ? LEV * Vz[i] : fma(ha, Ez[i], LEV * Vz[i]);
-    double ey[6], by[6];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-        ey[k] = A2 * r[k];
-        by[k] = b[5] * r[k];
-        if (k < 2) {
-            ey[k] = fma(A1, g0[k], ey[k]);
-            by[k] = fma(b[4], g0[k], by[k]);
-        }
-    }
+    // et_y = A2 r + A1 g0 and bt_y = b5 r + b4 g0 (g0 in the x rows only), so the y-y block is
+    //     HH = al r r' + be (g0 r' + r g0') + ga g0 g0' + L4 h0,
+    // and row c of the c-y block is  cr_c r' + cg_c g0'  -- scalars first, then one FMA per entry and vector.
     const double sig = gE - 2.0 * gV * m;           // Ezz entries (A1, f0), (A2, f1)
-    const double s24 = 2.0 * gV * f0, s35 = 2.0 * gV * f1, s44 = 2.0 * gV * B1, s55 = 2.0 * gV * B2;
-    double gr[6];
+    const double al = 2.0 * (A2 * b[5] + gV * B2);
+    const double be = fma(A1, b[5], A2 * b[4]);
+    const double ga = 2.0 * (A1 * b[4] + gV * B1);
+    double ar[6], bg0[2];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) gr[k] = s55 * r[k];
+    for (int k = 0; k < 6; ++k) ar[k] = al * r[k];
+    bg0[0] = be * g0[0];
+    bg0[1] = be * g0[1];
 #pragma unroll
     for (int k = 0; k < 6; ++k)
 #pragma unroll
         for (int l = k; l < 6; ++l) {
             double a = acc[(UA_HH + tri6(k, l)) * S];
-            a = fma(ey[k], by[l], a);
-            a = fma(by[k], ey[l], a);
-            a = fma(gr[k], r[l], a);
+            a = fma(ar[k], r[l], a);
+            if (k < 2) a = fma(bg0[k], r[l], a);
             if (l < 2) {
-                a = fma(s44 * g0[k], g0[l], a);
+                a = fma(r[k], bg0[l], a);
+                a = fma(ga * g0[k], g0[l], a);
                 a = fma(Lz[4], h0[k + l], a);              // h0 packed xx, xy, yy
             }
             acc[(UA_HH + tri6(k, l)) * S] = a;
@@ -226,27 +223,18 @@ __device__ __forceinline__ double unit_pixel_term(double* acc, const PixelConsts
     acc[(UA_CC + tri4(1, 1)) * S] += 2.0 * f1 * b[1];
     acc[(UA_CC + tri4(1, 2)) * S] += f1 * b[2];
     acc[(UA_CC + tri4(1, 3)) * S] += f1 * b[3];
+    // c-y block: e = (f0, f1, 0, 0) on the c rows
+    const double cr[4] = {fma(f0, b[5], b[0] * A2), fma(f1, b[5], fma(b[1], A2, sig)), b[2] * A2, fma(b[3], A2, 2.0 * gV * f1)};
+    const double cg[4] = {fma(f0, b[4], fma(b[0], A1, sig)), fma(f1, b[4], b[1] * A1), fma(b[2], A1, 2.0 * gV * f0), b[3] * A1};
 #pragma unroll
-    for (int k = 0; k < 6; ++k) {
-        double c0 = acc[(UA_CR + 0 * 6 + k) * S], c1 = acc[(UA_CR + 1 * 6 + k) * S];
-        double c2 = acc[(UA_CR + 2 * 6 + k) * S], c3 = acc[(UA_CR + 3 * 6 + k) * S];
-        c0 = fma(f0, by[k], c0);
-        c0 = fma(b[0], ey[k], c0);
-        c1 = fma(f1, by[k], c1);
-        c1 = fma(b[1], ey[k], c1);
-        c1 = fma(sig, r[k], c1);
-        c2 = fma(b[2], ey[k], c2);
-        c3 = fma(b[3], ey[k], c3);
-        c3 = fma(s35, r[k], c3);
-        if (k < 2) {
-            c0 = fma(sig, g0[k], c0);
-            c2 = fma(s24, g0[k], c2);
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            double a = acc[(UA_CR + c * 6 + k) * S];
+            a = fma(cr[c], r[k], a);
+            if (k < 2) a = fma(cg[c], g0[k], a);
+            acc[(UA_CR + c * 6 + k) * S] = a;
         }
-        acc[(UA_CR + 0 * 6 + k) * S] = c0;
-        acc[(UA_CR + 1 * 6 + k) * S] = c1;
-        acc[(UA_CR + 2 * 6 + k) * S] = c2;
-        acc[(UA_CR + 3 * 6 + k) * S] = c3;
-    }
     return Lz[5];
 }
 
