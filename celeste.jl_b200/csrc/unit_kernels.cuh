@@ -102,8 +102,17 @@ struct UnitImg {
     int H2, W2, off_h, off_w, n1, n2, band0, pad;
 };
 
+// Kernel-tuning knob, OFF by default: value / gradient instantiations have shared memory to spare, so the window of the
+// spline coefficient table that a unit can touch ((rows + 3) x (columns + 3) doubles) can be staged there
+// (-DCELESTE_UNIT_WIN=1600).  Measured: unit_walk_kernel<1> 1.97 -> 2.19 ms -- the 12.8 KB per warp come out of L1, and
+// the pixel records then miss more than the taps gain (profiles/tuning_r02.md).
+#ifndef CELESTE_UNIT_WIN
+#define CELESTE_UNIT_WIN 0
+#endif
+template <int MODE> struct UnitWin { static constexpr int value = MODE == 2 ? 0 : CELESTE_UNIT_WIN; };
 template <int MODE> struct UnitWarpDoubles {
-    static constexpr size_t value = (size_t)NUAcc<MODE>::value * 32 + (size_t)NC2 * MREC + SU_STRIDE + (sizeof(UnitImg) + 7) / 8;
+    static constexpr size_t value = (size_t)NUAcc<MODE>::value * 32 + (size_t)NC2 * MREC + SU_STRIDE + (sizeof(UnitImg) + 7) / 8 +
+                                    (size_t)UnitWin<MODE>::value;
 };
 template <int MODE>
 constexpr size_t unit_smem_bytes() { return UnitWarpDoubles<MODE>::value * UNIT_WARPS * sizeof(double); }
@@ -457,6 +466,9 @@ __global__ void __launch_bounds__(UNIT_THREADS, MODE == 2 ? CELESTE_UNIT_MINB : 
     double* s_rec = wbase + (size_t)NUA * 32;               // NC2 x MREC
     double* s_si = s_rec + NC2 * MREC;                      // SU_STRIDE
     UnitImg& mi = *reinterpret_cast<UnitImg*>(s_si + SU_STRIDE);
+    constexpr int WCAP = UnitWin<MODE>::value;
+    double* s_win = s_si + SU_STRIDE + (sizeof(UnitImg) + 7) / 8;     // WCAP doubles
+    (void)s_win;
 #ifdef CELESTE_HOST_EMULATION
     for (int i = tid; i < 256; i += UNIT_THREADS) s_logtab[i] = h_logtab[i];
 #else
@@ -504,6 +516,21 @@ __global__ void __launch_bounds__(UNIT_THREADS, MODE == 2 ? CELESTE_UNIT_MINB : 
 
         // ---- phase A: the active source, row walks by lane pairs ------------------------------------------------
         const int H2c = max(uh.h2_hi - uh.h2_lo, 1), W2 = mi.W2;      // rows of this unit
+        // window of the spline table this unit can touch: table rows wx0 .. wx0 + WR - 1, columns wy0 .. wy0 + WC - 1
+        const int wx0 = (int)floor((double)(mi.off_h + uh.h2_lo + 1) - s_si[SI_M] + 26.0) - 1;
+        const int wy0 = (int)floor((double)(mi.off_w + 1) - s_si[SI_M + 1] + 26.0) - 1;
+        const int WR = H2c + 3, WC = W2 + 3;
+        const bool winok = WCAP > 0 && WR * WC <= WCAP;
+        if (winok) {
+            for (int i = lane; i < WR * WC; i += 32) {
+                const int c = i / WR, r = i - c * WR;
+                const int tx = wx0 + r, ty = wy0 + c;
+                s_win[i] = (tx >= 0 && tx < mi.n1 && ty >= 0 && ty < mi.n2) ? __ldg(mi.coefs + (size_t)ty * mi.n1 + tx) : 0.0;
+            }
+            __syncwarp();
+        }
+        const double* cbase = winok ? s_win : mi.coefs;              // the star's taps: cbase[coff + ...], column stride cstr
+        const int cstr = winok ? WR : mi.n1;
         const int nseg = uh.nseg;
         const int total = (uh.h2_hi > uh.h2_lo && W2 > 0) ? (uh.h2_hi - uh.h2_lo) * nseg : 0;
         const int segw = (W2 + nseg - 1) / nseg;
@@ -529,19 +556,19 @@ __global__ void __launch_bounds__(UNIT_THREADS, MODE == 2 ? CELESTE_UNIT_MINB : 
             {
                 const int ixf = (int)floor((double)h - si[SI_M] + 26.0), iy0 = (int)floor((double)w0 - si[SI_M + 1] + 26.0);
                 fast = len > 0 && ixf >= 1 && ixf <= mi.n1 - 3 && iy0 >= 1 && iy0 + len - 1 <= mi.n2 - 3;
-                coff = fast ? (iy0 - 1 + kk) * mi.n1 + (ixf - 1) : 0;
+                coff = fast ? (winok ? (iy0 - 1 + kk - wy0) * WR + (ixf - 1 - wx0) : (iy0 - 1 + kk) * mi.n1 + (ixf - 1)) : 0;
             }
             double R0 = 0.0, R1 = 0.0, D0 = 0.0, D1 = 0.0, Q0 = 0.0, Q1 = 0.0;   // row-interpolated value / d / d2 columns
             if (fast && kk < len) {
 #pragma unroll
                 for (int b = 0; b < 2; ++b) {
-                    const double* ccol = mi.coefs + coff;
-                    const double q0 = __ldg(ccol), q1 = __ldg(ccol + 1), q2 = __ldg(ccol + 2), q3 = __ldg(ccol + 3);
+                    const double* ccol = cbase + coff;
+                    const double q0 = ccol[0], q1 = ccol[1], q2 = ccol[2], q3 = ccol[3];
                     const double r = si[SI_WX] * q0 + si[SI_WX + 1] * q1 + si[SI_WX + 2] * q2 + si[SI_WX + 3] * q3;
                     double d = 0.0, dd = 0.0;
                     if (MODE >= 1) d = si[SI_DWX] * q0 + si[SI_DWX + 1] * q1 + si[SI_DWX + 2] * q2 + si[SI_DWX + 3] * q3;
                     if (MODE >= 2) dd = si[SU_DDWX] * q0 + si[SU_DDWX + 1] * q1 + si[SU_DDWX + 2] * q2 + si[SU_DDWX + 3] * q3;
-                    coff += mi.n1;
+                    coff += cstr;
                     if (b == 0) {
                         R0 = r;
                         D0 = d;
@@ -566,7 +593,7 @@ __global__ void __launch_bounds__(UNIT_THREADS, MODE == 2 ? CELESTE_UNIT_MINB : 
                     const bool own = iown < len;
                     if (own) {
                         CEL_PREFETCH_L1(mi.pix + pix + 2);                 // the pair's next two records share a sector
-                        if (fast) {
+                        if (fast && !winok) {
                             CEL_PREFETCH_L1(mi.coefs + coff);
                             CEL_PREFETCH_L1(mi.coefs + coff + mi.n1 + 3);
                         }
@@ -626,10 +653,10 @@ __global__ void __launch_bounds__(UNIT_THREADS, MODE == 2 ? CELESTE_UNIT_MINB : 
                             bV = mi.bg[2 * pix + 1];
                         }
                         if (fast) {
-                            const double* ccol = mi.coefs + coff;
-                            const int n1 = mi.n1;
-                            const double q0 = __ldg(ccol), q1 = __ldg(ccol + 1), q2 = __ldg(ccol + 2), q3 = __ldg(ccol + 3);
-                            const double q4 = __ldg(ccol + n1), q5 = __ldg(ccol + n1 + 1), q6 = __ldg(ccol + n1 + 2), q7 = __ldg(ccol + n1 + 3);
+                            const double* ccol = cbase + coff;
+                            const int n1 = cstr;
+                            const double q0 = ccol[0], q1 = ccol[1], q2 = ccol[2], q3 = ccol[3];
+                            const double q4 = ccol[n1], q5 = ccol[n1 + 1], q6 = ccol[n1 + 2], q7 = ccol[n1 + 3];
                             const double R2 = si[SI_WX] * q0 + si[SI_WX + 1] * q1 + si[SI_WX + 2] * q2 + si[SI_WX + 3] * q3;
                             const double R3 = si[SI_WX] * q4 + si[SI_WX + 1] * q5 + si[SI_WX + 2] * q6 + si[SI_WX + 3] * q7;
                             const double wy0 = si[SI_WY], wy1 = si[SI_WY + 1], wy2 = si[SI_WY + 2], wy3 = si[SI_WY + 3];
@@ -704,7 +731,7 @@ __global__ void __launch_bounds__(UNIT_THREADS, MODE == 2 ? CELESTE_UNIT_MINB : 
                     }
                     if (MODE >= 2 && own) l5plane[pix] = l5;
                     pix += 2;
-                    coff += 2 * mi.n1;
+                    coff += 2 * cstr;
                 }
             }
         }
