@@ -50,10 +50,10 @@ namespace celeste {
 #define CELESTE_UNIT_ROWS 16          // rows of a patch per unit (build_unit_list)
 #endif
 #ifndef CELESTE_UNIT_BG_MINB
-#define CELESTE_UNIT_BG_MINB 3
+#define CELESTE_UNIT_BG_MINB 4
 #endif
 #ifndef CELESTE_UNIT_MOM_MINB
-#define CELESTE_UNIT_MOM_MINB 5
+#define CELESTE_UNIT_MOM_MINB 6
 #endif
 constexpr int UNIT_WARPS = 4;
 constexpr int UNIT_BG_PIXELS = 700;    // unit_bg_kernel: shared pixels (summed over neighbours) per piece, about

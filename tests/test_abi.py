@@ -52,6 +52,9 @@ def test_sass_is_sm100a_fp64():
     sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
     funcs = [f for f in sass.split("Function : ") if f.startswith("_ZN7celeste12pixel_kernelILi2ELi2ELb0E")]
     assert len(funcs) == 1 and funcs[0].count("DFMA") > 500
+    for name in ("_ZN7celeste16unit_walk_kernelILi1E", "_ZN7celeste16unit_walk_kernelILi2E", "_ZN7celeste18unit_moment_kernelE"):
+        funcs = [f for f in sass.split("Function : ") if f.startswith(name)]
+        assert len(funcs) == 1 and funcs[0].count("DFMA") > 200, name
 
 
 @pytest.mark.skipif(__import__("torch").cuda.is_available(), reason="only meaningful without a GPU")
