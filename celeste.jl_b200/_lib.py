@@ -67,7 +67,7 @@ EXPORTS = [
     "celeste_fp64_peak", "celeste_plan_enable_timing", "celeste_plan_kernel_times", "celeste_set_chunk_pixels",
     "celeste_plan_create_multi", "celeste_tr_subproblem", "celeste_plan_set_task_mask", "celeste_newton_step",
     "celeste_render_expectation", "celeste_patches_build", "celeste_patch_readback", "celeste_find_neighbors",
-    "celeste_plan_kernel_name", "celeste_plan_unit_times", "celeste_plan_set_hessian_layout",
+    "celeste_plan_kernel_name", "celeste_plan_unit_times", "celeste_plan_set_hessian_layout", "celeste_render_boxes",
 ]
 
 
@@ -122,6 +122,7 @@ def load():
     lib.celeste_plan_set_task_mask.argtypes = [vp, vp]
     lib.celeste_tr_subproblem.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.celeste_render_expectation.argtypes = [vp, i32, vp, vp, vp]
+    lib.celeste_render_boxes.argtypes = [vp, i32, vp, vp, vp]
     lib.celeste_patches_build.argtypes = [vp, i32, i32, C.POINTER(celeste_patch_spec)]
     lib.celeste_patch_readback.argtypes = [vp, i32, i32, vp, vp, vp]
     lib.celeste_find_neighbors.argtypes = [vp, vp, vp, C.c_int64, C.POINTER(C.c_int64)]

@@ -1424,8 +1424,20 @@ int celeste_elbo_single(celeste_field* f, int32_t S, const int32_t* source_ids, 
     return celeste_elbo_batch(f, 1, task_ptr, source_ids, active_ptr, active_idx, vp, mode, v, d, h, counters, flags);
 }
 
+static int render_impl(celeste_field* f, int32_t S, const int32_t* source_ids, const double* vp, double* const* out,
+                       int full_box);
+
 int celeste_render_expectation(celeste_field* f, int32_t S, const int32_t* source_ids, const double* vp,
                                double* const* out) {
+    return render_impl(f, S, source_ids, vp, out, 0);
+}
+
+int celeste_render_boxes(celeste_field* f, int32_t S, const int32_t* source_ids, const double* vp, double* const* out) {
+    return render_impl(f, S, source_ids, vp, out, 1);
+}
+
+static int render_impl(celeste_field* f, int32_t S, const int32_t* source_ids, const double* vp, double* const* out,
+                       int full_box) {
     if (!f || S < 0 || !out || (S > 0 && (!source_ids || !vp))) {
         set_detail("render_expectation: bad arguments (S=%d)", S);
         return CELESTE_ERR_BAD_ARG;
@@ -1473,7 +1485,7 @@ int celeste_render_expectation(celeste_field* f, int32_t S, const int32_t* sourc
                            H2 = p.H2;
                            W2 = p.W2;
                        },
-                       tiles, tile_slots);
+                       tiles, tile_slots, full_box);
     DevBuf<RenderTile> d_tiles;
     DevBuf<int> d_slots;
     CUDA_TRY(d_tiles.upload(tiles));
@@ -1490,9 +1502,9 @@ int celeste_render_expectation(celeste_field* f, int32_t S, const int32_t* sourc
     CUDA_TRY(d_ptrs.upload(h_ptrs));
     if (!tiles.empty()) {
         if (pl->uniform_K == 2)
-            render_kernel<2><<<(unsigned)tiles.size(), RENDER_THREADS, 0, st>>>(pd, d_tiles.p, d_slots.p, d_ptrs.p);
+            render_kernel<2><<<(unsigned)tiles.size(), RENDER_THREADS, 0, st>>>(pd, d_tiles.p, d_slots.p, d_ptrs.p, full_box);
         else
-            render_kernel<0><<<(unsigned)tiles.size(), RENDER_THREADS, 0, st>>>(pd, d_tiles.p, d_slots.p, d_ptrs.p);
+            render_kernel<0><<<(unsigned)tiles.size(), RENDER_THREADS, 0, st>>>(pd, d_tiles.p, d_slots.p, d_ptrs.p, full_box);
         CUDA_TRY(cudaGetLastError());
     }
     for (int n = 0; n < N; ++n)

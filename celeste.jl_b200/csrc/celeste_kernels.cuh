@@ -1329,7 +1329,7 @@ struct RenderTile {
 // host side: bin the S slots' patches of image n into tiles (CSR).  geo(s) -> off_h, off_w, H2, W2.
 template <typename Geo>
 inline void build_render_tiles(int N, const int* imgH, const int* imgW, int S, Geo geo, std::vector<RenderTile>& tiles,
-                               std::vector<int>& tile_slots) {
+                               std::vector<int>& tile_slots, int full_box = 0) {
     tiles.clear();
     tile_slots.clear();
     for (int n = 0; n < N; ++n) {
@@ -1340,7 +1340,7 @@ inline void build_render_tiles(int N, const int* imgH, const int* imgW, int S, G
             int oh, ow, H2, W2;
             geo(s, n, oh, ow, H2, W2);
             const int hlo = std::max(oh + 1, 1), hhi = std::min(oh + H2, H);
-            const int wlo = std::max(ow + 1, 1), whi = std::min(ow + W2 - 1, W);     // strict w2 < W2
+            const int wlo = std::max(ow + 1, 1), whi = std::min(ow + W2 - (full_box ? 0 : 1), W);     // strict w2 < W2
             if (hlo > hhi || wlo > whi) return false;
             t0 = (hlo - 1) / RT_H;
             t1 = (hhi - 1) / RT_H;
@@ -1372,7 +1372,7 @@ inline void build_render_tiles(int N, const int* imgH, const int* imgW, int S, G
 template <int KT>
 __global__ void __launch_bounds__(RENDER_THREADS) render_kernel(PlanDev plan, const RenderTile* __restrict__ tiles,
                                                                 const int* __restrict__ tile_slots,
-                                                                double* const* __restrict__ out) {
+                                                                double* const* __restrict__ out, int full_box = 0) {
     __shared__ double s_comps[MAX_COMPS * COMP_STRIDE];
     __shared__ double s_exptab[8];
     const int tid = threadIdx.x;
@@ -1399,7 +1399,8 @@ __global__ void __launch_bounds__(RENDER_THREADS) render_kernel(PlanDev plan, co
         for (int j = tid; j < nrec; j += RENDER_THREADS) s_comps[j] = rec[j];
         __syncthreads();
         const int h2 = h - p.off_h, w2 = w - p.off_w;
-        if (!inside || h2 < 1 || h2 > p.H2 || w2 < 1 || w2 >= p.W2) continue;
+        // full_box: every column of the box (Synthetic.gen_image! renders a body on its whole box); else the ELBO's rule
+        if (!inside || h2 < 1 || h2 > p.H2 || w2 < 1 || w2 > p.W2 - (full_box ? 0 : 1)) continue;
         if (!p.bitmap[(h2 - 1) + (size_t)(w2 - 1) * p.H2]) continue;
         const double* br = plan.slotbr + (size_t)s * SLOTBR_STRIDE;
         const double m1 = rec[MAX_COMPS * COMP_STRIDE], m2 = rec[MAX_COMPS * COMP_STRIDE + 1];

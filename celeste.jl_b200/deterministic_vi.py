@@ -212,9 +212,10 @@ class DeviceField:
     def make_plan(self, tasks_rows, tasks_active):
         return Plan(self, tasks_rows, tasks_active)
 
-    def render_expectation(self, rows, vp) -> List[np.ndarray]:
+    def render_expectation(self, rows, vp, full_box: bool = False) -> List[np.ndarray]:
         """celeste_render_expectation: for every image the H x W float64 array of E_G - sky (nanomaggies) summed
-        over the sources `rows` (1-based rows of the patch matrix) at variational parameters vp (44 x S)."""
+        over the sources `rows` (1-based rows of the patch matrix) at variational parameters vp (44 x S).
+        full_box = celeste_render_boxes: every column of each box (Synthetic.gen_image!), not the ELBO's w2 < W2."""
         lib = _lib.load()
         rows = np.ascontiguousarray(rows, dtype=np.int32)
         vpm = np.asfortranarray(vp, dtype=np.float64)
@@ -223,8 +224,8 @@ class DeviceField:
         fi = self._flat_images
         outs = [np.zeros((fi.arr[n].H, fi.arr[n].W), dtype=np.float64, order="F") for n in range(fi.N)]
         ptrs = (C.c_void_p * max(fi.N, 1))(*[o.ctypes.data for o in outs])
-        _lib.check(lib.celeste_render_expectation(self._handle, S, rows.ctypes.data if S else None,
-                                                  vpm.ctypes.data if S else None, ptrs))
+        fn = lib.celeste_render_boxes if full_box else lib.celeste_render_expectation
+        _lib.check(fn(self._handle, S, rows.ctypes.data if S else None, vpm.ctypes.data if S else None, ptrs))
         return outs
 
 

@@ -160,6 +160,53 @@ def gen_images(images: Sequence[Image], catalog: Sequence[CatalogEntry], seed: i
         img.pixels = np.asfortranarray(lam.numpy().astype(np.float32))
 
 
+def catalog_truth_vp(ce: CatalogEntry) -> np.ndarray:
+    """Variational parameters under which the model's expected flux IS the catalog entry's (Synthetic.jl:17-27
+    write_star / write_galaxy use ce.star_fluxes / ce.gal_fluxes directly): is_star 0 / 1, flux_scale = color_var = 0,
+    flux_loc = log r-band flux, colours = log flux ratios, so E_l[b] = exp(kappa_b . beta) = flux[b] exactly; the galaxy
+    shape as the catalog has it (no clamping)."""
+    vs = np.zeros(44)
+    vs[ids.pos] = ce.pos
+    vs[ids.is_star] = [1.0, 0.0] if ce.is_star else [0.0, 1.0]
+    for i, fl in enumerate((ce.star_fluxes, ce.gal_fluxes)):
+        fl = np.maximum(np.asarray(fl, dtype=np.float64), 1e-300)
+        vs[ids.flux_loc[i]] = math.log(fl[2])
+        vs[ids.color_mean[:, i]] = np.log(fl[1:] / fl[:-1])
+    vs[ids.gal_frac_dev] = ce.gal_frac_dev
+    vs[ids.gal_axis_ratio] = ce.gal_axis_ratio
+    vs[ids.gal_angle] = ce.gal_angle
+    vs[ids.gal_radius_px] = ce.gal_radius_px
+    return vs
+
+
+def gen_images_device(images: Sequence[Image], catalog: Sequence[CatalogEntry], seed: int = 1, expectation: bool = False,
+                      device: int = -1):
+    """Synthetic.gen_images! (Synthetic.jl:30-58) with the per-body render on the GPU: every body's expected flux on
+    its radius-25 box through celeste_render_boxes (the value-only render kernel over whole boxes) at the catalog's own
+    fluxes (catalog_truth_vp), then + sky, x iota and the Poisson draw on the host.  In place on img.pixels (Float32,
+    like the reference; the reference also ACCUMULATES in Float32 -- here the sum over bodies is Float64 and rounded
+    once, a difference of a few Float32 ulp of the pixel value)."""
+    from .deterministic_vi import DeviceField
+    from .model import ImagePatch
+    S, N = len(catalog), len(images)
+    for img in images:
+        img.pixels = np.zeros((img.H, img.W), dtype=np.float32, order="F")     # no masked pixels: full bitmaps
+    patches = np.empty((S, N), dtype=object)
+    for n, img in enumerate(images):
+        for s, ce in enumerate(catalog):
+            patches[s, n] = ImagePatch(img, box_around_point(img.wcs, ce.pos, 25))
+    field = DeviceField(images, patches, device=device)
+    vp = np.stack([catalog_truth_vp(ce) for ce in catalog], axis=1) if S else np.zeros((44, 0))
+    add = field.render_expectation(np.arange(1, S + 1), vp, full_box=True)
+    gen = torch.Generator(device="cpu").manual_seed(seed)
+    for img, a in zip(images, add):
+        lam = (a + np.asarray(img.sky, dtype=np.float64)) * np.asarray(img.nelec_per_nmgy, dtype=np.float64)[:, None]
+        if not expectation:
+            lam = torch.poisson(torch.from_numpy(np.ascontiguousarray(lam)).clamp_min(0), generator=gen).numpy()
+        img.pixels = np.asfortranarray(lam.astype(np.float32))
+    return images
+
+
 # ------------------------------------------------------------------ test/SampleData.jl analogues
 def sample_ce(pos, is_star: bool) -> CatalogEntry:
     """SampleData.jl:119-122."""

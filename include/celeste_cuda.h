@@ -312,6 +312,13 @@ int celeste_find_neighbors(celeste_field* f, int32_t* nbr_ptr, int32_t* nbr, int
  */
 int celeste_render_expectation(celeste_field* f, int32_t S, const int32_t* source_ids, const double* vp,
                                double* const* out);
+/*
+ * The same render over EVERY column of each source's box (no strict w2 < W2): what Synthetic.gen_image!
+ * (src/Synthetic.jl:30-47) adds for one body -- its expected flux on the whole radius-25 box -- when vp holds the
+ * catalog's fluxes exactly (is_star 0 / 1, flux_scale = color_var = 0: E_l = exp(flux_loc + colours) = catalog flux).
+ * The caller adds the sky, multiplies by iota and draws the Poisson sample (synthetic.gen_images_device).
+ */
+int celeste_render_boxes(celeste_field* f, int32_t S, const int32_t* source_ids, const double* vp, double* const* out);
 
 /*
  * Row f.2 (batched Newton trust region; the step ElboMaximize.maximize! delegates to Optim.NewtonTrustRegion,

@@ -31,6 +31,7 @@ def load():
         _lib.emul_bitmap_build.argtypes = [i32, i32, vp, i32, i32, i32, i32, vp]
         _lib.emul_find_neighbors.argtypes = [i32, i32, vp, vp, vp]
         _lib.emul_render_expectation.argtypes = [i32, vp, i32, vp, i32, vp, vp, vp]
+        _lib.emul_render_boxes.argtypes = [i32, vp, i32, vp, i32, vp, vp, vp]
     return _lib
 
 
@@ -80,11 +81,11 @@ def newton_stepper(phase, n, buffers):
     assert st == 0
 
 
-def render_expectation(images, patches, rows, vp):
+def render_expectation(images, patches, rows, vp, full_box=False):
     """render_kernel (+ setup_kernel, host tile binning) under emulation."""
     from oracle_lib import _render
     fi, fp = FlatImages(images), FlatPatches(patches)
-    return _render(load().emul_render_expectation, fi, fp, rows, vp)
+    return _render(load().emul_render_boxes if full_box else load().emul_render_expectation, fi, fp, rows, vp)
 
 
 def spline_build(grid_n, raw=None, psf=None):

@@ -414,8 +414,18 @@ extern "C" int emul_newton_step(int32_t phase, int32_t batch, const celeste_newt
 }
 
 // render_kernel under emulation (one field, slots = the S sources in order)
+static int emul_render_impl(int32_t N, const celeste_image* imgs, int32_t S_tot, const celeste_patch* patches, int32_t S,
+                            const int32_t* source_ids, const double* vp, double* const* out, int full_box);
 extern "C" int emul_render_expectation(int32_t N, const celeste_image* imgs, int32_t S_tot, const celeste_patch* patches,
                                        int32_t S, const int32_t* source_ids, const double* vp, double* const* out) {
+    return emul_render_impl(N, imgs, S_tot, patches, S, source_ids, vp, out, 0);
+}
+extern "C" int emul_render_boxes(int32_t N, const celeste_image* imgs, int32_t S_tot, const celeste_patch* patches,
+                                 int32_t S, const int32_t* source_ids, const double* vp, double* const* out) {
+    return emul_render_impl(N, imgs, S_tot, patches, S, source_ids, vp, out, 1);
+}
+static int emul_render_impl(int32_t N, const celeste_image* imgs, int32_t S_tot, const celeste_patch* patches, int32_t S,
+                            const int32_t* source_ids, const double* vp, double* const* out, int full_box) {
     galaxy_prototypes(c_proto_eta, c_proto_nu);
     std::vector<ImageDev> images(N);
     std::vector<int> imgH(N), imgW(N);
@@ -473,14 +483,14 @@ extern "C" int emul_render_expectation(int32_t N, const celeste_image* imgs, int
                            H2 = p.H2;
                            W2 = p.W2;
                        },
-                       tiles, tile_slots);
+                       tiles, tile_slots, full_box);
     bool k2 = true;
     for (size_t i = 0; i < pdv.size(); ++i) k2 = k2 && pdv[i].K == 2;
     if (!tiles.empty()) {
         if (k2)
-            cuda_emul::launch(render_kernel<2>, (int)tiles.size(), RENDER_THREADS, 0, pd, tiles.data(), tile_slots.data(), out);
+            cuda_emul::launch(render_kernel<2>, (int)tiles.size(), RENDER_THREADS, 0, pd, tiles.data(), tile_slots.data(), out, full_box);
         else
-            cuda_emul::launch(render_kernel<0>, (int)tiles.size(), RENDER_THREADS, 0, pd, tiles.data(), tile_slots.data(), out);
+            cuda_emul::launch(render_kernel<0>, (int)tiles.size(), RENDER_THREADS, 0, pd, tiles.data(), tile_slots.data(), out, full_box);
     }
     return 0;
 }

@@ -276,3 +276,29 @@ def test_emulated_patch_construction_kernels():
     for name in ("clipped_and_empty", "crowded", "small_field"):
         _, patches, _ = cases.get(name)
         assert emul_lib.find_all_neighbors(patches) == model.find_all_neighbors(patches)
+
+
+def test_emulated_box_render_reproduces_the_synthetic_image_generator():
+    """Synthetic.gen_image! (Synthetic.jl:30-47) through the render kernel: celeste_render_boxes at the catalog's own
+    fluxes (synthetic.catalog_truth_vp) + sky, x iota == the host renderer's expectation image (synthetic.gen_images,
+    Float32 pixels), including bodies whose radius-25 box is clipped by the image border and the last column of every
+    box (which the ELBO's strict w2 < W2 rule would leave out)."""
+    from celeste_jl_b200 import synthetic
+    from celeste_jl_b200.model import ImagePatch, box_around_point
+    images = synthetic.blank_images(70, 64, bands=(1, 3, 5))
+    catalog = [synthetic.sample_ce([30.3, 28.8], False), synthetic.sample_ce([8.1, 60.2], True),
+               synthetic.sample_ce([66.0, 5.5], False), synthetic.sample_ce([40.7, 41.9], True)]
+    catalog[2].gal_axis_ratio, catalog[2].gal_angle, catalog[2].gal_frac_dev = 0.4, 1.1, 0.8
+    ref = [im for im in synthetic.blank_images(70, 64, bands=(1, 3, 5))]
+    synthetic.gen_images(ref, catalog, expectation=True, device="cpu")
+    patches = np.empty((len(catalog), len(images)), dtype=object)
+    for n, img in enumerate(images):
+        for s, ce in enumerate(catalog):
+            patches[s, n] = ImagePatch(img, box_around_point(img.wcs, ce.pos, 25))
+    vp = np.stack([synthetic.catalog_truth_vp(ce) for ce in catalog], axis=1)
+    add = emul_lib.render_expectation(images, patches, np.arange(1, len(catalog) + 1), vp, full_box=True)
+    strict = emul_lib.render_expectation(images, patches, np.arange(1, len(catalog) + 1), vp)
+    for img, r, a, st in zip(images, ref, add, strict):
+        lam = (a + np.asarray(img.sky, dtype=np.float64)) * np.asarray(img.nelec_per_nmgy, dtype=np.float64)[:, None]
+        assert np.allclose(lam, r.pixels.astype(np.float64), rtol=2e-6, atol=1e-4), np.abs(lam - r.pixels).max()
+        assert (a != st).any() and (a >= st - 1e-12).all()       # the strict rule leaves each box's last column out

@@ -819,3 +819,22 @@ def test_config5_maximize_matches_the_oracle_driven_run_and_recovers_truth(cj):
         assert abs(bright / flux_r - 1.0) < 0.05, (t, bright, flux_r)
         checked += 1
     assert checked >= 5, checked
+
+
+def test_gen_images_device_matches_host_generator(cj):
+    """Synthetic.gen_images! with the per-body render on the GPU (celeste_render_boxes at the catalog's fluxes): the
+    expectation image equals the host renderer's to Float32 rounding on a 300-source field; the Poisson variant draws
+    from it."""
+    from celeste_jl_b200 import synthetic
+    cat = synthetic.draw_catalog(300, 700, 640, seed=4)
+    host = synthetic.blank_images(700, 640)
+    synthetic.gen_images(host, cat, expectation=True, device="cpu")
+    dev = synthetic.blank_images(700, 640)
+    synthetic.gen_images_device(dev, cat, expectation=True)
+    for h, d in zip(host, dev):
+        assert np.allclose(d.pixels.astype(np.float64), h.pixels.astype(np.float64), rtol=3e-6, atol=1e-3)
+    noisy = synthetic.blank_images(700, 640)
+    synthetic.gen_images_device(noisy, cat, seed=3)
+    for h, d in zip(host, noisy):
+        z = (d.pixels.astype(np.float64) - h.pixels) / np.sqrt(np.maximum(h.pixels, 1.0))
+        assert abs(z.mean()) < 0.01 and 0.97 < z.std() < 1.03 and (d.pixels == np.round(d.pixels)).all()
