@@ -54,9 +54,26 @@ void set_detail(const char* fmt, ...) {
     } while (0)
 
 template <typename T>
-struct DevBuf {
+struct DevBuf {                      // owns one cudaMalloc block: movable, not copyable
     T* p = nullptr;
     size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) {
+        o.p = nullptr;
+        o.n = 0;
+    }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) {
+            release();
+            p = o.p;
+            n = o.n;
+            o.p = nullptr;
+            o.n = 0;
+        }
+        return *this;
+    }
     ~DevBuf() { release(); }
     void release() {
         if (p) cudaFree(p);
@@ -109,6 +126,35 @@ int upload_constants() {
 }
 
 int g_chunk_pixels = 0;
+
+// cudaSetDevice for the duration of an ABI call; the caller's current device is restored on return
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = (prev == dev) || cudaSetDevice(dev) == cudaSuccess;
+        if (prev == dev) prev = -1;          // nothing to restore
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// multiprocessors of the current device (148 on a B200), queried once per device
+int sm_count() {
+    static std::mutex mu;
+    static std::map<int, int> cache;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(dev);
+    if (it != cache.end()) return it->second;
+    int n = 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[dev] = n;
+    return n;
+}
 
 template <int MODE>
 size_t pixel_smem_bytes() {
@@ -366,7 +412,7 @@ int celeste_field_create(celeste_field** out, int32_t N, const celeste_image* im
             CUDA_TRY(li.alloc(im.H));
             CUDA_TRY(cudaMemcpy(li.p, im.log_iota, im.H * sizeof(double), cudaMemcpyHostToDevice));
         }
-        prep_image_kernel<<<1184, 256>>>(im.H, im.W, f->pixels[n].p, f->iota[n].p, li.p, f->pixconst[n].p);
+        prep_image_kernel<<<8 * sm_count(), 256>>>(im.H, im.W, f->pixels[n].p, f->iota[n].p, li.p, f->pixconst[n].p);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaDeviceSynchronize());
         ImageDev d;
@@ -1080,7 +1126,7 @@ static int launch_mode(celeste_plan* p, const double* vp_dev, double* v, double*
                        int* flags, cudaStream_t st) {
     const PlanDev pd = plan_dev(p);
     const long total = (long)p->n_slots * p->N * MAX_K;
-    const int sblocks = (int)std::max<long>(1, std::min<long>((total + 127) / 128, 148L * 16));
+    const int sblocks = (int)std::max<long>(1, std::min<long>((total + 127) / 128, 16L * sm_count()));
     if (p->timing) CUDA_TRY(cudaEventRecord(p->ev[0], st));
     if ((MODE <= 1 && p->use_unit_grad) || (MODE == 2 && p->use_unit_hess)) {
         // one warp per (sub, image) unit from a device-side queue (unit_kernels.cuh); the epilogue is the general one
@@ -1202,6 +1248,16 @@ int celeste_elbo_plan_device(celeste_plan* p, const double* vp_dev, int32_t mode
             return CELESTE_ERR_STATE;
         }
     if (p->n_tasks == 0) return CELESTE_OK;
+    {
+        // the plan's buffers live on p->device: launching from another current device would hand the kernels
+        // foreign pointers (an opaque CUDA error later); refuse it here
+        int cur = -1;
+        CUDA_TRY(cudaGetDevice(&cur));
+        if (cur != p->device) {
+            set_detail("elbo_plan_device: current device %d, the plan lives on device %d (call cudaSetDevice first)", cur, p->device);
+            return CELESTE_ERR_STATE;
+        }
+    }
     cudaStream_t st = (cudaStream_t)cuda_stream;
     long long* c = reinterpret_cast<long long*>(counters_dev);
     switch (mode) {
@@ -1285,7 +1341,11 @@ int celeste_elbo_plan_host(celeste_plan* p, const double* vp, int32_t mode, doub
         return CELESTE_ERR_BAD_ARG;
     }
     if (p->n_tasks == 0) return CELESTE_OK;
-    CUDA_TRY(cudaSetDevice(p->device));
+    DeviceGuard guard(p->device);           // run on the plan's device, give the caller's current device back
+    if (!guard.ok) {
+        set_detail("elbo_plan_host: cannot select device %d", p->device);
+        return CELESTE_ERR_CUDA;
+    }
     if (!p->stream) CUDA_TRY(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     const size_t nt = p->n_tasks;
     const size_t nd = mode >= 1 ? (size_t)p->n_subs * NPARAM : 0;
@@ -1467,7 +1527,7 @@ static int render_impl(celeste_field* f, int32_t S, const int32_t* source_ids, c
     const PlanDev pd = plan_dev(pl.get());
     {
         const long total = (long)pl->n_slots * N * MAX_K;
-        const int sblocks = (int)std::max<long>(1, std::min<long>((total + 127) / 128, 148L * 16));
+        const int sblocks = (int)std::max<long>(1, std::min<long>((total + 127) / 128, 16L * sm_count()));
         setup_kernel<<<sblocks, 128, 0, st>>>(pd, pl->vp_dev.p);
     }
     std::vector<int> imgH(N), imgW(N);
@@ -1582,7 +1642,7 @@ int celeste_fp64_peak(double* tflops_out, void* cuda_stream) {
     cudaEvent_t e0, e1;
     CUDA_TRY(cudaEventCreate(&e0));
     CUDA_TRY(cudaEventCreate(&e1));
-    const int blocks = 148 * 8, threads = 256, iters = 4096;
+    const int blocks = sm_count() * 8, threads = 256, iters = 4096;
     dfma_peak_kernel<<<blocks, threads, 0, st>>>(out.p, 64, 1.0);   // warm-up
     double best = 0;
     for (int rep = 0; rep < 5; ++rep) {

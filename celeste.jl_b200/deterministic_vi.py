@@ -323,6 +323,18 @@ class Plan:
         _lib.check(st)
 
 
+_KL_CPU = None
+
+
+def _kl_term_cpu():
+    """One KLTerm for the process (it reads the prior file and inverts 16 covariance matrices when built)."""
+    global _KL_CPU
+    if _KL_CPU is None:
+        from .kl import KLTerm
+        _KL_CPU = KLTerm("cpu")
+    return _KL_CPU
+
+
 # ------------------------------------------------------------------ elbo_args.jl:165-211
 class ElboArgs:
     """elbo_args.jl:165-211.  `patches` is the S x N object matrix of ImagePatch;
@@ -392,7 +404,7 @@ def elbo(ea: ElboArgs, vp: VariationalParams,
         from .kl import KLTerm
         order = 2 if res.has_hessian else (1 if res.has_gradient else 0)
         act = torch.tensor(np.stack([np.asarray(vp[s - 1], dtype=np.float64) for s in ea.active_sources]))
-        kv, kg, kH = KLTerm("cpu")(act, order=order)
+        kv, kg, kH = _kl_term_cpu()(act, order=order)
         res.v += float(kv.sum())
         for sa in range(ea.Sa):                                   # add_sources_sf!, SensitiveFloats.jl:215-250
             if res.has_gradient:
