@@ -287,6 +287,7 @@ struct celeste_plan {
     int n_units = 0, n_units_bg = 0, sms = 148;
     long long unit_maxpix = 1;
     bool use_unit_hess = false, use_unit_grad = false;
+    bool small_plan = false;         // fewer than 8 whole (sub, image) units per resident warp: cut finer (see plan creation)
     bool block_epilogue = false;     // CELESTE_EPILOGUE=block: epilogue_kernel<2> instead of epilogue_hess_kernel (A/B knob)
     bool need_pack = false;          // pix is filled on the first evaluation (needs the uploaded plan arrays)
     DevBuf<PairHdr> pairmap;
@@ -938,7 +939,8 @@ int celeste_plan_create_multi(int32_t n_fields, celeste_field* const* fields, ce
         // call, one rank's share of an 8-GPU run -- is cut at CELESTE_UNIT_ROWS rows so that its sources spread over the
         // whole GPU and the launch has no tail.  Within either regime the cut depends on the patch only, so a task's
         // result is bit-for-bit independent of what else is in the plan.  CELESTE_UNIT_ROWS=<n> forces n (0 = never).
-        long target = (long)n_subs * pl->N < 8L * pl->sms * CELESTE_UNIT_MINB * UNIT_WARPS ? CELESTE_UNIT_ROWS : 0;
+        pl->small_plan = (long)n_subs * pl->N < 8L * pl->sms * CELESTE_UNIT_MINB * UNIT_WARPS;
+        long target = pl->small_plan ? CELESTE_UNIT_ROWS : 0;
         if (const char* env = std::getenv("CELESTE_UNIT_ROWS")) target = std::atol(env);
         build_unit_list(n_subs, pl->N, sub_task.data(), sub_slot.data(), task_ptr, tfield.data(),
                         [&](int slot, int n, int& oh, int& ow, int& H2, int& W2) {
@@ -949,8 +951,8 @@ int celeste_plan_create_multi(int32_t n_fields, celeste_field* const* fields, ce
                             H2 = pa.H2;
                             W2 = pa.W2;
                         },
-                        target, std::getenv("CELESTE_UNIT_PIXELS") ? std::atol(std::getenv("CELESTE_UNIT_PIXELS")) : 0L, um, ub, ucp,
-                        pl->unit_maxpix);
+                        target, std::getenv("CELESTE_UNIT_PIXELS") ? std::atol(std::getenv("CELESTE_UNIT_PIXELS")) : 0L,
+                        pl->small_plan ? UNIT_BG_PIXELS_SMALL : UNIT_BG_PIXELS_BIG, um, ub, ucp, pl->unit_maxpix);
         pl->n_units = (int)um.size();
         pl->n_units_bg = (int)ub.size();
         std::vector<long long> l5_ptr((size_t)n_subs * pl->N, 0);
@@ -1136,15 +1138,19 @@ static int launch_mode(celeste_plan* p, const double* vp_dev, double* v, double*
             if (p->n_units > 0) unit_pack_kernel<<<p->n_units, 128, 0, st>>>(pu, p->unitmap.p, p->n_units, p->pix.p);
             p->need_pack = false;
         }
-        CUDA_TRY(cudaMemsetAsync(p->unit_queue.p, 0, 4 * sizeof(int), st));
-        slotbr_kernel<<<(p->n_slots + 127) / 128, 128, 0, st>>>(pu, vp_dev);
+        slotbr_kernel<<<(std::max(p->n_slots, 4) + 127) / 128, 128, 0, st>>>(pu, vp_dev, p->unit_queue.p);
         if (p->timing) CUDA_TRY(cudaEventRecord(p->ev[1], st));
         auto grid_for = [&](int n_units, int minb) {
             return std::max(1, std::min(p->sms * minb, (n_units + UNIT_WARPS - 1) / UNIT_WARPS));
         };
-        if (p->n_units_bg > 0)
-            unit_bg_kernel<<<grid_for(p->n_units_bg, CELESTE_UNIT_BG_MINB), UNIT_THREADS, unit_bg_smem_bytes(), st>>>(
-                pu, p->unitmap_bg.p, p->n_units_bg, p->unit_queue.p, vp_dev);
+        if (p->n_units_bg > 0) {
+            if (p->small_plan)
+                unit_bg_kernel<3><<<grid_for(p->n_units_bg, 3), UNIT_THREADS, unit_bg_smem_bytes(), st>>>(
+                    pu, p->unitmap_bg.p, p->n_units_bg, p->unit_queue.p, vp_dev);
+            else
+                unit_bg_kernel<CELESTE_UNIT_BG_MINB><<<grid_for(p->n_units_bg, CELESTE_UNIT_BG_MINB), UNIT_THREADS, unit_bg_smem_bytes(), st>>>(
+                    pu, p->unitmap_bg.p, p->n_units_bg, p->unit_queue.p, vp_dev);
+        }
         if (p->timing) CUDA_TRY(cudaEventRecord(p->ev_unit[0], st));
         if (p->n_units > 0)
             unit_walk_kernel<MODE><<<grid_for(p->n_units, MODE == 2 ? CELESTE_UNIT_MINB : CELESTE_UNIT_MINB_GRAD), UNIT_THREADS,

@@ -184,8 +184,9 @@ __global__ void setup_kernel(PlanDev plan, const double* __restrict__ vp) {
 // Brightness moments (source_brightness.jl:27-202) of EVERY slot of the plan, one thread per slot: what epilogue_kernel
 // reads for the active sources and what the unit kernels read for every source they walk (active or neighbour).  The
 // kernels that build their own mixtures (unit kernels) need nothing else from setup_kernel.
-__global__ void slotbr_kernel(PlanDev plan, const double* __restrict__ vp) {
+__global__ void slotbr_kernel(PlanDev plan, const double* __restrict__ vp, int* __restrict__ queue) {
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot < 4 && queue) queue[slot] = 0;              // the unit kernels' work-queue counters of this evaluation
     if (slot >= plan.n_slots) return;
     const double* vs = vp + (size_t)NPARAM * slot;
     double El[2][5], Ell[2][5];

@@ -56,7 +56,9 @@ namespace celeste {
 #define CELESTE_UNIT_MOM_MINB 6
 #endif
 constexpr int UNIT_WARPS = 4;
-constexpr int UNIT_BG_PIXELS = 700;    // unit_bg_kernel: shared pixels (summed over neighbours) per piece, about
+// unit_bg_kernel: shared pixels (summed over neighbours) per piece, about -- large pieces on a plan that fills the GPU
+// (fewer per-neighbour prologues), small ones on a small plan (balance)
+constexpr int UNIT_BG_PIXELS_BIG = 1400, UNIT_BG_PIXELS_SMALL = 350;
 constexpr int MOMENT_ROWBLOCK = 16;    // unit_moment_kernel: rows between exact starts of the row-direction recurrence
 constexpr int UNIT_THREADS = 32 * UNIT_WARPS;
 // per-(source, image) constants of the warp (shared memory): march's SI_* plus the second-derivative spline weights
@@ -282,7 +284,10 @@ __global__ void unit_pack_kernel(PlanDev plan, const UnitHdr* __restrict__ units
 // Neighbouring sources (value only, elbo_objective.jl:38-40,69): E_bg += E_s, V_bg += E2_s - E_s^2 over the pixels a
 // neighbour shares with the active patch, one neighbour at a time in slot order (fixed summation order), into the
 // unit's (E_bg, V_bg) planes in plan.bg.  One warp per unit that has a neighbour; the walk is march_kernel's.
-__global__ void __launch_bounds__(UNIT_THREADS, CELESTE_UNIT_BG_MINB)
+// MINB: blocks per SM the registers are budgeted for -- 4 (128 registers) is faster on a plan that fills the GPU, 3 (168,
+// no spills) on a small, latency-bound plan (profiles/tuning_r02.md).
+template <int MINB>
+__global__ void __launch_bounds__(UNIT_THREADS, MINB)
     unit_bg_kernel(PlanDev plan, const UnitHdr* __restrict__ units, int n_units, int* __restrict__ queue,
                    const double* __restrict__ vp) {
     CEL_DYNAMIC_SMEM(smem);
@@ -955,7 +960,8 @@ __global__ void __launch_bounds__(UNIT_THREADS, CELESTE_UNIT_MOM_MINB)
 // geo(slot, n, off_h, off_w, H2, W2) -> the patch box of a slot in image n.
 template <typename Geo>
 inline void build_unit_list(int n_subs, int N, const int* sub_task, const int* sub_slot, const int* task_ptr,
-                            const int* task_field, Geo geo, long unit_rows, long unit_pixels, std::vector<UnitHdr>& units,
+                            const int* task_field, Geo geo, long unit_rows, long unit_pixels, int bg_pixels,
+                            std::vector<UnitHdr>& units,
                             std::vector<UnitHdr>& bg_units, std::vector<int>& chunk_ptr, long long& maxpix) {
     units.clear();
     bg_units.clear();
@@ -1005,8 +1011,16 @@ inline void build_unit_list(int n_subs, int N, const int* sub_task, const int* s
             chunk_ptr[tn + 1] = chunk_ptr[tn] + pieces;
             for (int pc = 0; pc < pieces; ++pc) {
                 UnitHdr x = uh;
-                x.h2_lo = (int)((long)std::max(H2, 0) * pc / pieces);
-                x.h2_hi = (int)((long)std::max(H2, 0) * (pc + 1) / pieces);
+                if (unit_pixels > 0 || pieces == 1) {
+                    x.h2_lo = (int)((long)std::max(H2, 0) * pc / pieces);
+                    x.h2_hi = (int)((long)std::max(H2, 0) * (pc + 1) / pieces);
+                } else {
+                    // pieces of exactly unit_rows rows and a remainder: with unit_rows = the 16 walk slots of a warp a
+                    // full piece is ONE round of whole-row walks (one exact start per row); equal halves of a 23-row
+                    // patch would need 3 rounds of 6-pixel segments each (measured: tuning_r02.md)
+                    x.h2_lo = (int)std::min((long)H2, pc * unit_rows);
+                    x.h2_hi = (int)std::min((long)H2, (pc + 1) * unit_rows);
+                }
                 x.first = pc == 0;
                 x.pidx = chunk_ptr[tn] + pc;
                 const int rows = x.h2_hi - x.h2_lo;
@@ -1026,7 +1040,7 @@ inline void build_unit_list(int n_subs, int N, const int* sub_task, const int* s
                 if (pc == 0 && x.hasbg) {
                     // neighbour work of the (sub, image): row pieces of at most ~UNIT_BG_PIXELS shared pixels, so that one
                     // crowded source is not the tail of unit_bg_kernel
-                    const int bp = std::max(1, std::min(std::max(1, H2 / 2), (x.nbpix + UNIT_BG_PIXELS - 1) / UNIT_BG_PIXELS));
+                    const int bp = std::max(1, std::min(std::max(1, H2 / 2), (x.nbpix + bg_pixels - 1) / bg_pixels));
                     x.bgp0 = (int)bg_units.size();
                     x.bgp1 = x.bgp0 + bp;
                     for (int b = 0; b < bp; ++b) {

@@ -58,7 +58,7 @@ void run_unit(PlanDev pd, const FieldDev& fd, const double* vp, double* v, doubl
                         H2 = pa.H2;
                         W2 = pa.W2;
                     },
-                    g_unit_target, 0L, units, ub, cp, maxpix);
+                    g_unit_target, 0L, g_unit_target > 0 ? UNIT_BG_PIXELS_SMALL : UNIT_BG_PIXELS_BIG, units, ub, cp, maxpix);
     const int grid = 2;
     std::vector<double> part((size_t)cp.back() * NAcc<MODE>::value + 1, 1e300);   // poisoned
     std::vector<long long> bg_ptr((size_t)pd.n_subs * pd.N, -1), l5_ptr((size_t)pd.n_subs * pd.N, 0);
@@ -85,9 +85,9 @@ void run_unit(PlanDev pd, const FieldDev& fd, const double* vp, double* v, doubl
     pd.bg_cnt = bg_cnt.data();
     if (!units.empty()) cuda_emul::launch(unit_pack_kernel, (int)units.size(), 32, 0, pd, (const UnitHdr*)units.data(), (int)units.size(), pix.data());
     int queue[4] = {0, 0, 0, 0};
-    cuda_emul::launch(slotbr_kernel, 1, std::max(pd.n_slots, 1), 0, pd, vp);
+    cuda_emul::launch(slotbr_kernel, 1, std::max(pd.n_slots, 4), 0, pd, vp, &queue[0]);
     if (!ub.empty())
-        cuda_emul::launch(unit_bg_kernel, grid, UNIT_THREADS, unit_bg_smem_bytes(), pd, (const UnitHdr*)ub.data(), (int)ub.size(),
+        cuda_emul::launch(unit_bg_kernel<3>, grid, UNIT_THREADS, unit_bg_smem_bytes(), pd, (const UnitHdr*)ub.data(), (int)ub.size(),
                           &queue[0], vp);
     cuda_emul::launch(unit_walk_kernel<MODE>, grid, UNIT_THREADS, unit_smem_bytes<MODE>(), pd, (const UnitHdr*)units.data(),
                       (int)units.size(), &queue[1], vp);
