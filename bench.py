@@ -534,7 +534,7 @@ def main():
                 prof = {}
         kernels = {}
         for name, ms_k in parts.items():
-            t = prof.get(name)
+            t = prof.get(name) or next((v for k, v in prof.items() if k.startswith(name + "<")), None)
             ent = {"ms_per_step": ms_k}
             if t and t.get("sources") == int(total_sources) and ms_k > 0:
                 ex = t["executed_flop_per_launch"] / (ms_k * 1e-3) / 1e12       # whole-job: the capture is the N = 1 launch
