@@ -461,7 +461,7 @@ def main():
         vp_all = vps[0].reshape(-1, 44)
         slot0 = np.concatenate([[0], np.cumsum([len(r) for r in all_rows])])
         oracles = {}
-        rel_v = rel_d = rel_h = 0.0
+        rel_v = rel_d = rel_h = rel_h3 = 0.0
         counters_equal = True
         for k, t in enumerate(pick):
             fi = task_field[t]
@@ -477,6 +477,7 @@ def main():
             if mode >= 2:
                 sc = np.abs(ref["h"]).max()
                 rel_h = max(rel_h, float((np.abs(ref["h"] - h[k]) / np.maximum(np.abs(ref["h"]), sc * 1e-6)).max()))
+                rel_h3 = max(rel_h3, float((np.abs(ref["h"] - h[k]) / np.maximum(np.abs(ref["h"]), sc * 1e-3)).max()))
         out = {"n": int(len(pick) * world), "max_rel_v": max_over_ranks(rel_v), "counters_equal": bool(min_over_ranks(counters_equal)),
                "tolerance": 1e-8, "what": "seeded sample of each rank's tasks vs the CPU oracle; gradient / Hessian "
                "component-wise |delta| / max(|ref_ij|, 1e-6 * max|ref|)"}
@@ -484,6 +485,9 @@ def main():
             out["max_rel_d"] = max_over_ranks(rel_d)
         if mode >= 2:
             out["max_rel_h"] = max_over_ranks(rel_h)
+            # the same with a floor of 1e-3 of the largest entry: the 1e-6 floor is reached by entries a million times
+            # smaller than the matrix scale, whose absolute error (< 1 ulp of the largest entry) is rounding noise
+            out["max_rel_h_floor_1e-3"] = max_over_ranks(rel_h3)
         out["ok"] = bool(out["counters_equal"] and max(out["max_rel_v"], out.get("max_rel_d", 0), out.get("max_rel_h", 0)) <= 1e-8)
         return out
 
