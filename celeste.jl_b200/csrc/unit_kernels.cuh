@@ -112,9 +112,21 @@ struct UnitImg {
 #define CELESTE_UNIT_WIN 0
 #endif
 template <int MODE> struct UnitWin { static constexpr int value = MODE == 2 ? 0 : CELESTE_UNIT_WIN; };
+// Two more knobs of the walk's loads, both measured and OFF (profiles/tuning_r02.md):
+//   -DCELESTE_UNIT_CPASYNC=1   each lane streams its own pixel records global -> shared with cp.async (LDGSTS), three
+//                              iterations deep, instead of prefetch.global.L1 + a plain load
+//   -DCELESTE_UNIT_PF_AHEAD=k  the spline taps are prefetched k iterations further ahead (0: the current iteration's)
+#ifndef CELESTE_UNIT_CPASYNC
+#define CELESTE_UNIT_CPASYNC 0
+#endif
+#ifndef CELESTE_UNIT_PF_AHEAD
+#define CELESTE_UNIT_PF_AHEAD 0
+#endif
+constexpr int UNIT_RING = 3;                                     // cp.async ring slots per lane
+constexpr int UNIT_RING_DOUBLES = CELESTE_UNIT_CPASYNC ? UNIT_RING * 32 * 2 : 0;
 template <int MODE> struct UnitWarpDoubles {
     static constexpr size_t value = (size_t)NUAcc<MODE>::value * 32 + (size_t)NC2 * MREC + SU_STRIDE + (sizeof(UnitImg) + 7) / 8 +
-                                    (size_t)UnitWin<MODE>::value;
+                                    (size_t)UnitWin<MODE>::value + UNIT_RING_DOUBLES;
 };
 template <int MODE>
 constexpr size_t unit_smem_bytes() { return UnitWarpDoubles<MODE>::value * UNIT_WARPS * sizeof(double); }
@@ -448,6 +460,25 @@ __global__ void __launch_bounds__(UNIT_THREADS, MINB)
     }
 }
 
+// cp.async (LDGSTS) of one 16-byte record, for the CELESTE_UNIT_CPASYNC variant
+__device__ __forceinline__ void unit_cp_async16(void* smem_dst, const void* gsrc) {
+#ifndef CELESTE_HOST_EMULATION
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+#else
+    memcpy(smem_dst, gsrc, 16);
+#endif
+}
+__device__ __forceinline__ void unit_cp_async_commit() {
+#ifndef CELESTE_HOST_EMULATION
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int N> __device__ __forceinline__ void unit_cp_async_wait() {
+#ifndef CELESTE_HOST_EMULATION
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
+}
+
 // Phase A: the active source of a unit, row walks by lane pairs (see the file header).
 template <int MODE>
 __global__ void __launch_bounds__(UNIT_THREADS, MODE == 2 ? CELESTE_UNIT_MINB : CELESTE_UNIT_MINB_GRAD)
@@ -474,6 +505,10 @@ __global__ void __launch_bounds__(UNIT_THREADS, MODE == 2 ? CELESTE_UNIT_MINB : 
     constexpr int WCAP = UnitWin<MODE>::value;
     double* s_win = s_si + SU_STRIDE + (sizeof(UnitImg) + 7) / 8;     // WCAP doubles
     (void)s_win;
+#if CELESTE_UNIT_CPASYNC
+    // ring[slot][lane], 16 bytes each; every term of the per-warp layout before it is an even number of doubles
+    PixRec* ring = reinterpret_cast<PixRec*>(s_win + WCAP) + lane;
+#endif
 #ifdef CELESTE_HOST_EMULATION
     for (int i = tid; i < 256; i += UNIT_THREADS) s_logtab[i] = h_logtab[i];
 #else
@@ -589,6 +624,13 @@ __global__ void __launch_bounds__(UNIT_THREADS, MODE == 2 ? CELESTE_UNIT_MINB : 
             const double iota_h = has ? (double)mi.iota[h - 1] : 0.0; // nelec_per_nmgy of this row
 
             int t = 0;
+#if CELESTE_UNIT_CPASYNC
+#pragma unroll
+            for (int a = 0; a < UNIT_RING - 1; ++a) {                  // records of iterations 0 and 1 of this row piece
+                if (2 * a + kk < len) unit_cp_async16(ring + a * 32, mi.pix + pix + 2 * a);
+                unit_cp_async_commit();
+            }
+#endif
             while (t < nit) {
                 const bool asleep = march_start(recs, s_exptab, (double)h, (double)(w0 + 2 * t), fp, rr);
                 const bool careful = __ballot_sync(0xffffffffu, asleep && len > 0) != 0u;
@@ -596,12 +638,22 @@ __global__ void __launch_bounds__(UNIT_THREADS, MODE == 2 ? CELESTE_UNIT_MINB : 
                 for (; t < tend; ++t) {
                     const int iown = 2 * t + kk;
                     const bool own = iown < len;
+#if CELESTE_UNIT_CPASYNC
+                    if (iown + 2 * (UNIT_RING - 1) < len)
+                        unit_cp_async16(ring + ((t + UNIT_RING - 1) % UNIT_RING) * 32, mi.pix + pix + 2 * (UNIT_RING - 1));
+                    unit_cp_async_commit();
+#endif
                     if (own) {
+#if !CELESTE_UNIT_CPASYNC
                         CEL_PREFETCH_L1(mi.pix + pix + 2);                 // the pair's next two records share a sector
+#endif
                         if (fast && !winok) {
-                            CEL_PREFETCH_L1(mi.coefs + coff);
-                            CEL_PREFETCH_L1(mi.coefs + coff + mi.n1 + 3);
+                            CEL_PREFETCH_L1(mi.coefs + coff + CELESTE_UNIT_PF_AHEAD * 2 * mi.n1);
+                            CEL_PREFETCH_L1(mi.coefs + coff + CELESTE_UNIT_PF_AHEAD * 2 * mi.n1 + mi.n1 + 3);
                         }
+#if CELESTE_UNIT_PF_AHEAD
+                        if (mi.bg) CEL_PREFETCH_L1(mi.bg + 2 * (pix + 2));
+#endif
                     }
                     // this lane's half (PSF component kk) of the mixture sums of both pixels (columns 2t and 2t + 1)
                     double S[2][NS];
@@ -648,8 +700,15 @@ __global__ void __launch_bounds__(UNIT_THREADS, MODE == 2 ? CELESTE_UNIT_MINB : 
                     float xf = nanf(""), skyf = 0.f;
                     double pconst = 0.0, bE = 0.0, bV = 0.0;
                     double f0 = 0.0, g0[2] = {0.0, 0.0}, h0[3] = {0.0, 0.0, 0.0};
+#if CELESTE_UNIT_CPASYNC
+                    unit_cp_async_wait<UNIT_RING - 1>();                   // this iteration's group has landed
+#endif
                     if (own) {
+#if CELESTE_UNIT_CPASYNC
+                        const PixRec pr = ring[(t % UNIT_RING) * 32];
+#else
                         const PixRec pr = mi.pix[pix];
+#endif
                         xf = pr.x;
                         skyf = pr.sky;
                         pconst = pr.pixconst;
