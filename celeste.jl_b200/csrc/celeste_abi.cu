@@ -295,9 +295,7 @@ struct celeste_plan {
     int n_subs = 0, n_pairs = 0;
     size_t h_total = 0;      // doubles in the Hessian output: sum over tasks of (44 Sa)^2
     // staging for the host-buffer entry point
-    DevBuf<double> vp_dev, v_dev, d_dev, h_dev;
-    DevBuf<long long> counters_dev;
-    DevBuf<int> flags_dev;
+    DevBuf<double> vp_dev, d_dev, h_dev;
     cudaStream_t stream = nullptr;
     const unsigned char* task_mask = nullptr;   // device pointer owned by the caller
     bool timing = false;
@@ -308,6 +306,8 @@ struct celeste_plan {
     // small plans (what celeste_elbo_single makes): all outputs in ONE device block mirrored by one pinned host block
     // (a single D2H per call), and the kernel sequence of each mode captured once into a CUDA graph
     DevBuf<unsigned char> out_block;
+    DevBuf<unsigned char> small_block;      // v | counters | flags of the large-plan host path
+    unsigned char* small_pin = nullptr;
     unsigned char* out_pin = nullptr;
     double* vp_pin = nullptr;
     cudaGraphExec_t graph[3] = {nullptr, nullptr, nullptr};
@@ -322,6 +322,7 @@ struct celeste_plan {
     ~celeste_plan() {
         drop_graphs();
         if (out_pin) cudaFreeHost(out_pin);
+        if (small_pin) cudaFreeHost(small_pin);
         if (vp_pin) cudaFreeHost(vp_pin);
         if (stream) cudaStreamDestroy(stream);
         for (auto& e : ev)
@@ -1358,25 +1359,32 @@ int celeste_elbo_plan_host(celeste_plan* p, const double* vp, int32_t mode, doub
     const size_t nh = mode >= 2 ? (p->hess_layout == CELESTE_HESS_PACKED28 ? (size_t)p->n_tasks * HESS_PACKED_LEN : p->h_total) : 0;
     if ((nt * 3 + nd + nh) * 8 + (size_t)p->n_slots * NPARAM * 8 <= (1u << 20))        // <= 1 MB moved per call
         return plan_host_small(p, vp, mode, v, d, h, counters, flags, nd, nh);
+    // v | counters | flags live in ONE device block mirrored by a pinned host block: one D2H for the three small
+    // outputs (every copy costs ~8 us of latency on the stream, which is what a 1250-source step has to spare), and no
+    // pageable destination; the gradient and the Hessian go straight into the caller's buffers
+    const size_t o_v = 0, o_c = o_v + nt * 8, o_f = o_c + 2 * nt * 8, small_total = o_f + ((nt * 4 + 7) / 8) * 8;
+    if (p->small_block.n < small_total) {
+        CUDA_TRY(p->small_block.alloc(small_total));
+        if (p->small_pin) cudaFreeHost(p->small_pin);
+        p->small_pin = nullptr;
+        CUDA_TRY(cudaMallocHost((void**)&p->small_pin, small_total));
+    }
     CUDA_TRY(p->vp_dev.ensure((size_t)p->n_slots * NPARAM));
-    CUDA_TRY(p->v_dev.ensure(nt));
-    CUDA_TRY(p->counters_dev.ensure(2 * nt));
-    CUDA_TRY(p->flags_dev.ensure(nt));
     if (mode >= 1) CUDA_TRY(p->d_dev.ensure(nd));
     if (mode >= 2) CUDA_TRY(p->h_dev.ensure(nh));
     cudaStream_t st = p->stream;
+    unsigned char* sb = p->small_block.p;
     CUDA_TRY(cudaMemcpyAsync(p->vp_dev.p, vp, (size_t)p->n_slots * NPARAM * sizeof(double), cudaMemcpyHostToDevice, st));
-    int rc = celeste_elbo_plan_device(p, p->vp_dev.p, mode, p->v_dev.p, p->d_dev.p, p->h_dev.p,
-                                      reinterpret_cast<int64_t*>(p->counters_dev.p), p->flags_dev.p, st);
+    int rc = celeste_elbo_plan_device(p, p->vp_dev.p, mode, (double*)(sb + o_v), p->d_dev.p, p->h_dev.p,
+                                      (int64_t*)(sb + o_c), (int32_t*)(sb + o_f), st);
     if (rc != CELESTE_OK) return rc;
-    std::vector<int> hflags(nt);
-    CUDA_TRY(cudaMemcpyAsync(v, p->v_dev.p, nt * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (mode >= 1) CUDA_TRY(cudaMemcpyAsync(d, p->d_dev.p, nd * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (mode >= 2) CUDA_TRY(cudaMemcpyAsync(h, p->h_dev.p, nh * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (counters)
-        CUDA_TRY(cudaMemcpyAsync(counters, p->counters_dev.p, 2 * nt * sizeof(long long), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(hflags.data(), p->flags_dev.p, nt * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(p->small_pin, sb, small_total, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    std::memcpy(v, p->small_pin + o_v, nt * 8);
+    if (counters) std::memcpy(counters, p->small_pin + o_c, 2 * nt * 8);
+    const int* hflags = reinterpret_cast<const int*>(p->small_pin + o_f);
     bool bad = false;
     for (size_t t = 0; t < nt; ++t) {
         if (flags) flags[t] = hflags[t];

@@ -18,7 +18,7 @@
 
 #ifndef CELESTE_HOST_EMULATION   // tests/host_emul compiles this file with a host emulation layer instead
 #include <cuda_runtime.h>
-#define CEL_DYNAMIC_SMEM(name) extern __shared__ double name[]
+#define CEL_DYNAMIC_SMEM(name) extern __shared__ __align__(16) double name[]
 #else
 #define CEL_DYNAMIC_SMEM(name) double* name = ::cuda_emul::dynamic_smem()
 #endif

@@ -112,21 +112,32 @@ struct UnitImg {
 #define CELESTE_UNIT_WIN 0
 #endif
 template <int MODE> struct UnitWin { static constexpr int value = MODE == 2 ? 0 : CELESTE_UNIT_WIN; };
-// Two more knobs of the walk's loads, both measured and OFF (profiles/tuning_r02.md):
-//   -DCELESTE_UNIT_CPASYNC=1   each lane streams its own pixel records global -> shared with cp.async (LDGSTS), three
-//                              iterations deep, instead of prefetch.global.L1 + a plain load
-//   -DCELESTE_UNIT_PF_AHEAD=k  the spline taps are prefetched k iterations further ahead (0: the current iteration's)
+// How the walk gets its pixel records (profiles/tuning_r02.md):
+//   CELESTE_UNIT_CPASYNC = 2 (default)  value / gradient instantiations: each lane streams its own 16-byte records
+//                              global -> shared with cp.async (LDGSTS), three iterations deep (1.5 KB ring per warp);
+//                              the Hessian instantiation, whose shared memory is full of accumulators, keeps
+//                              prefetch.global.L1 + a plain load.  Measured: unit_walk_kernel<1> 1.963 -> 1.936 ms
+//                        = 1  every mode (unit_walk_kernel<2>: 2.93 -> 3.26 ms: the ring costs it L1)
+//                        = 0  never
+//   CELESTE_UNIT_PF_AHEAD = k  the spline taps are prefetched k iterations further ahead (measured: slower, off)
+//   CELESTE_UNIT_BG_PF = 1 (default)  unit_bg_kernel prefetches the next iteration's bitmap byte / record / sums / taps
+//                              (0.289 -> 0.284 ms)
 #ifndef CELESTE_UNIT_CPASYNC
-#define CELESTE_UNIT_CPASYNC 0
+#define CELESTE_UNIT_CPASYNC 2
+#endif
+#ifndef CELESTE_UNIT_BG_PF
+#define CELESTE_UNIT_BG_PF 1
 #endif
 #ifndef CELESTE_UNIT_PF_AHEAD
 #define CELESTE_UNIT_PF_AHEAD 0
 #endif
 constexpr int UNIT_RING = 3;                                     // cp.async ring slots per lane
-constexpr int UNIT_RING_DOUBLES = CELESTE_UNIT_CPASYNC ? UNIT_RING * 32 * 2 : 0;
+template <int MODE> struct UnitCpAsync {
+    static constexpr bool value = CELESTE_UNIT_CPASYNC == 1 || (CELESTE_UNIT_CPASYNC == 2 && MODE <= 1);
+};
 template <int MODE> struct UnitWarpDoubles {
     static constexpr size_t value = (size_t)NUAcc<MODE>::value * 32 + (size_t)NC2 * MREC + SU_STRIDE + (sizeof(UnitImg) + 7) / 8 +
-                                    (size_t)UnitWin<MODE>::value + UNIT_RING_DOUBLES;
+                                    (size_t)UnitWin<MODE>::value + (UnitCpAsync<MODE>::value ? UNIT_RING * 32 * 2 : 0);
 };
 template <int MODE>
 constexpr size_t unit_smem_bytes() { return UnitWarpDoubles<MODE>::value * UNIT_WARPS * sizeof(double); }
@@ -406,6 +417,15 @@ __global__ void __launch_bounds__(UNIT_THREADS, MINB)
                                 xv = px->x;
                                 b0 = bgE[0];
                                 b1 = bgE[1];
+#if CELESTE_UNIT_BG_PF
+                                CEL_PREFETCH_L1(nbit + 2 * nH2);       // the next iteration's loads
+                                CEL_PREFETCH_L1(px + 2);
+                                CEL_PREFETCH_L1(bgE + 4);
+                                if (fast) {
+                                    CEL_PREFETCH_L1(ccol + 2 * n1);
+                                    CEL_PREFETCH_L1(ccol + 3 * n1 + 3);
+                                }
+#endif
                             }
                             double R2 = 0.0, R3 = 0.0;
                             if (fast && own) {
@@ -505,10 +525,10 @@ __global__ void __launch_bounds__(UNIT_THREADS, MODE == 2 ? CELESTE_UNIT_MINB : 
     constexpr int WCAP = UnitWin<MODE>::value;
     double* s_win = s_si + SU_STRIDE + (sizeof(UnitImg) + 7) / 8;     // WCAP doubles
     (void)s_win;
-#if CELESTE_UNIT_CPASYNC
     // ring[slot][lane], 16 bytes each; every term of the per-warp layout before it is an even number of doubles
+    constexpr bool CPA = UnitCpAsync<MODE>::value;
     PixRec* ring = reinterpret_cast<PixRec*>(s_win + WCAP) + lane;
-#endif
+    (void)ring;
 #ifdef CELESTE_HOST_EMULATION
     for (int i = tid; i < 256; i += UNIT_THREADS) s_logtab[i] = h_logtab[i];
 #else
@@ -624,13 +644,13 @@ __global__ void __launch_bounds__(UNIT_THREADS, MODE == 2 ? CELESTE_UNIT_MINB : 
             const double iota_h = has ? (double)mi.iota[h - 1] : 0.0; // nelec_per_nmgy of this row
 
             int t = 0;
-#if CELESTE_UNIT_CPASYNC
+            if (CPA) {
 #pragma unroll
-            for (int a = 0; a < UNIT_RING - 1; ++a) {                  // records of iterations 0 and 1 of this row piece
-                if (2 * a + kk < len) unit_cp_async16(ring + a * 32, mi.pix + pix + 2 * a);
-                unit_cp_async_commit();
+                for (int a = 0; a < UNIT_RING - 1; ++a) {              // records of iterations 0 and 1 of this row piece
+                    if (2 * a + kk < len) unit_cp_async16(ring + a * 32, mi.pix + pix + 2 * a);
+                    unit_cp_async_commit();
+                }
             }
-#endif
             while (t < nit) {
                 const bool asleep = march_start(recs, s_exptab, (double)h, (double)(w0 + 2 * t), fp, rr);
                 const bool careful = __ballot_sync(0xffffffffu, asleep && len > 0) != 0u;
@@ -638,15 +658,13 @@ __global__ void __launch_bounds__(UNIT_THREADS, MODE == 2 ? CELESTE_UNIT_MINB : 
                 for (; t < tend; ++t) {
                     const int iown = 2 * t + kk;
                     const bool own = iown < len;
-#if CELESTE_UNIT_CPASYNC
-                    if (iown + 2 * (UNIT_RING - 1) < len)
-                        unit_cp_async16(ring + ((t + UNIT_RING - 1) % UNIT_RING) * 32, mi.pix + pix + 2 * (UNIT_RING - 1));
-                    unit_cp_async_commit();
-#endif
+                    if (CPA) {
+                        if (iown + 2 * (UNIT_RING - 1) < len)
+                            unit_cp_async16(ring + ((t + UNIT_RING - 1) % UNIT_RING) * 32, mi.pix + pix + 2 * (UNIT_RING - 1));
+                        unit_cp_async_commit();
+                    }
                     if (own) {
-#if !CELESTE_UNIT_CPASYNC
-                        CEL_PREFETCH_L1(mi.pix + pix + 2);                 // the pair's next two records share a sector
-#endif
+                        if (!CPA) CEL_PREFETCH_L1(mi.pix + pix + 2);       // the pair's next two records share a sector
                         if (fast && !winok) {
                             CEL_PREFETCH_L1(mi.coefs + coff + CELESTE_UNIT_PF_AHEAD * 2 * mi.n1);
                             CEL_PREFETCH_L1(mi.coefs + coff + CELESTE_UNIT_PF_AHEAD * 2 * mi.n1 + mi.n1 + 3);
@@ -700,15 +718,9 @@ __global__ void __launch_bounds__(UNIT_THREADS, MODE == 2 ? CELESTE_UNIT_MINB : 
                     float xf = nanf(""), skyf = 0.f;
                     double pconst = 0.0, bE = 0.0, bV = 0.0;
                     double f0 = 0.0, g0[2] = {0.0, 0.0}, h0[3] = {0.0, 0.0, 0.0};
-#if CELESTE_UNIT_CPASYNC
-                    unit_cp_async_wait<UNIT_RING - 1>();                   // this iteration's group has landed
-#endif
+                    if (CPA) unit_cp_async_wait<UNIT_RING - 1>();          // this iteration's group has landed
                     if (own) {
-#if CELESTE_UNIT_CPASYNC
-                        const PixRec pr = ring[(t % UNIT_RING) * 32];
-#else
-                        const PixRec pr = mi.pix[pix];
-#endif
+                        const PixRec pr = CPA ? ring[(t % UNIT_RING) * 32] : mi.pix[pix];
                         xf = pr.x;
                         skyf = pr.sky;
                         pconst = pr.pixconst;

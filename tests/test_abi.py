@@ -55,6 +55,10 @@ def test_sass_is_sm100a_fp64():
     for name in ("_ZN7celeste16unit_walk_kernelILi1E", "_ZN7celeste16unit_walk_kernelILi2E", "_ZN7celeste18unit_moment_kernelE"):
         funcs = [f for f in sass.split("Function : ") if f.startswith(name)]
         assert len(funcs) == 1 and funcs[0].count("DFMA") > 200, name
+    # the value / gradient walks stream their pixel records with cp.async (LDGSTS); the Hessian walk does not
+    for name, want in (("_ZN7celeste16unit_walk_kernelILi1E", True), ("_ZN7celeste16unit_walk_kernelILi2E", False)):
+        f = [f for f in sass.split("Function : ") if f.startswith(name)][0]
+        assert ("LDGSTS" in f) == want, name
 
 
 @pytest.mark.skipif(__import__("torch").cuda.is_available(), reason="only meaningful without a GPU")

@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 export CELESTE_STRIPE_CACHE=/tmp/celeste_stripe
 B="--steps 30 --warmup 3 --no-cpu-baseline --no-maximize --no-render --no-single"
 V=$PWD/celeste.jl_b200/variants
-run() { name=$1; shift; env "$@" timeout 600 python bench.py $B > gpurun_out/ab_$name.json 2> gpurun_out/ab_$name.err; echo "$name rc=$?"; }
+run() { name=$1; shift; env "$@" timeout 600 python bench.py $B $EXTRA > gpurun_out/ab_$name.json 2> gpurun_out/ab_$name.err; echo "$name rc=$?"; }
 for v in "$@"; do run $v CELESTE_CUDA_LIB=$V/libceleste_cuda_$v.so; done
 python - "$@" <<'PY'
 import json, sys
