@@ -50,6 +50,9 @@ def parse():
     ap.add_argument("--no-hessian", action="store_true")
     ap.add_argument("--no-render", action="store_true", help="skip the full-image expectation render leg (row f.4)")
     ap.add_argument("--no-maximize", action="store_true", help="skip the config-5 leg (full Newton loop on field 0)")
+    ap.add_argument("--maximize-timeline", action="store_true",
+                    help="diagnosis: rerun the maximize leg with a sync per iteration and report [active sources, "
+                         "evaluation ms, newton step ms] per lock-step iteration")
     ap.add_argument("--no-single", action="store_true", help="skip the single-call latency leg (celeste_elbo_single)")
     return ap.parse_args()
 
@@ -624,6 +627,32 @@ def main():
                         "catalog_check": catalog_check,
                         "what": "one_node_single_infer semantics on the whole stripe: generic init, KL included, Newton "
                                 "trust region x_tol 1e-7 / f_tol 1e-6 / g_tol 1e-8 / 50 iterations, converged sources masked"}
+
+        if args.maximize_timeline and rank == 0:
+            bm = BatchMaximizer(plans[0], vps0, include_kl=True)
+            tl, ev0, ev1 = [], torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            orig_eval, orig_step = bm._evaluate_plan, bm._step
+
+            def eval_wrap():
+                torch.cuda.synchronize()
+                a = int(bm.mask.sum().item())
+                ev0.record()
+                orig_eval()
+                ev1.record()
+                torch.cuda.synchronize()
+                tl.append([a, round(ev0.elapsed_time(ev1), 4), None])
+
+            def step_wrap(phase):
+                ev0.record()
+                orig_step(phase)
+                ev1.record()
+                torch.cuda.synchronize()
+                if tl and phase in (0, 1):
+                    tl[-1][2] = round(ev0.elapsed_time(ev1), 4)
+
+            bm._evaluate_plan, bm._step = eval_wrap, step_wrap
+            bm.run()
+            maximize_leg["timeline"] = tl
 
     # row f.4: the value-only full-image render (fill_celeste_expectation!) of field 0, through the C ABI with host
     # buffers (122 MB of float64 expectation images come back per call); rank 0 only, informational

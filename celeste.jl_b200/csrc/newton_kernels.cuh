@@ -327,11 +327,16 @@ __device__ inline void tr_solve_block(TrShared& S, int n, double delta, double* 
         __syncthreads();
         const double beta = sc[0];
         if (beta != 0.0) {                         // block-uniform
-            if (tid < m) {
-                const double* row = A + (k + 1 + tid) * TR_LD + (k + 1);
+            {
+                // p = beta A22 v: two threads per row (TR_THREADS / 2 >= TR_MAXN rows), halves of the dot product
+                const int r = tid >> 1, part = tid & 1;
                 double t = 0.0;
-                for (int j = 0; j < m; ++j) t = fma(row[j], hv[j], t);
-                hp[tid] = beta * t;
+                if (r < m) {
+                    const double* row = A + (k + 1 + r) * TR_LD + (k + 1);
+                    for (int j = part; j < m; j += 2) t = fma(row[j], hv[j], t);
+                }
+                t += __shfl_xor_sync(0xffffffffu, t, 1);
+                if (r < m && part == 0) hp[r] = beta * t;
             }
             __syncthreads();
             if (warp == 0) {
@@ -340,11 +345,17 @@ __device__ inline void tr_solve_block(TrShared& S, int n, double delta, double* 
             }
             __syncthreads();
             const double K = sc[2];
-            // A22 <- A22 - v w' - w v',  w = p - K v   (each thread forms the w it needs)
-            for (int e = tid; e < m * m; e += TR_THREADS) {
-                const int i = e / m, j = e - i * m;
-                const double wi = hp[i] - K * hv[i], wj = hp[j] - K * hv[j];
-                A[(k + 1 + i) * TR_LD + (k + 1 + j)] -= hv[i] * wj + wi * hv[j];
+            // A22 <- A22 - v w' - w v',  w = p - K v: thread (j, i0) owns column j of the rows i0, i0 + 2, ...
+            // (no integer division by m in the inner loop)
+            {
+                const int j = tid & 63, i0 = tid >> 6;
+                if (j < m) {
+                    const double vj = hv[j], wj = hp[j] - K * vj;
+                    for (int i = i0; i < m; i += TR_THREADS / 64) {
+                        const double vi = hv[i], wi = hp[i] - K * vi;
+                        A[(k + 1 + i) * TR_LD + (k + 1 + j)] -= vi * wj + wi * vj;
+                    }
+                }
             }
         }
         // keep the reflector in column k (below the sub-diagonal position) and the sub-diagonal entry
@@ -403,65 +414,80 @@ __device__ inline void tr_solve_block(TrShared& S, int n, double delta, double* 
             }
             return cnt;
         };
-        // lam_min: 32-way multisection of [glo, ghi]
-        double lo = glo - 1e-12 * (1.0 + evabs_max), hi = ghi + 1e-12 * (1.0 + evabs_max);
-        for (int round = 0; round < 14; ++round) {
-            const double x = lo + (hi - lo) * (double)(lane + 1) / 33.0;
-            const unsigned hit = __ballot_sync(0xffffffffu, below(x) >= 1);
-            const int first = hit ? __ffs(hit) - 1 : 32;                 // first lane whose x has an eigenvalue below it
-            const double nlo = first == 0 ? lo : lo + (hi - lo) * (double)first / 33.0;
-            const double nhi = first == 32 ? hi : lo + (hi - lo) * (double)(first + 1) / 33.0;
-            lo = nlo;
-            hi = nhi;
-            if (!(hi - lo > 4.0e-16 * (1.0 + evabs_max))) break;
+        // Positive definite (no eigenvalue below 1e-8)?  One Sturm count.  lam_min itself is needed only when T is not:
+        // then 32-way multisection of [glo, min(ghi, 1e-8)]
+        const bool pos_def = below(1e-8) == 0;
+        double lam_min = 1e-8;
+        if (!pos_def) {
+            double lo = glo - 1e-12 * (1.0 + evabs_max), hi = fmin(ghi, 1e-8) + 1e-12 * (1.0 + evabs_max);
+            for (int round = 0; round < 14; ++round) {
+                const double x = lo + (hi - lo) * (double)(lane + 1) / 33.0;
+                const unsigned hit = __ballot_sync(0xffffffffu, below(x) >= 1);
+                const int first = hit ? __ffs(hit) - 1 : 32;             // first lane whose x has an eigenvalue below it
+                const double nlo = first == 0 ? lo : lo + (hi - lo) * (double)first / 33.0;
+                const double nhi = first == 32 ? hi : lo + (hi - lo) * (double)(first + 1) / 33.0;
+                lo = nlo;
+                hi = nhi;
+                if (!(hi - lo > 4.0e-16 * (1.0 + evabs_max))) break;
+            }
+            lam_min = 0.5 * (lo + hi);
         }
-        const double lam_min = 0.5 * (lo + hi);
 
         const double d2 = delta * delta;
         // LDL' solves on lane 0 (results broadcast); x_out may alias rhs
         double* sv = S.V + 4 * TR_MAXN;  // s(lam)
-        double* wv = S.V + 5 * TR_MAXN;  // (T + lam I)^-1 s
+        double* wv = S.V + 5 * TR_MAXN;  // u = L^-1 s  (s'(T + lam I)^-1 s = sum u_i^2 / q_i)
         double* piv = S.V + 6 * TR_MAXN; // reciprocal pivots of T + lam I
         double* lf = S.V + 11 * TR_MAXN; // its unit lower bidiagonal factor
         auto solve_pair = [&](double lam, bool need_w, double& p2, double& sw) {
-            // lane 0: pivots, s = -(T + lam I)^-1 g~, optionally w = (T + lam I)^-1 s
+            // lane 0: T + lam I = L D L', s = -(T + lam I)^-1 g~, and optionally u = L^-1 s for
+            // s'(T + lam I)^-1 s = sum u_i^2 / q_i.  Every recurrence carries its running value in a register (the
+            // chain per step is then one rcp + fma for the pivots, one fma for a forward solve, fma + mul for the back
+            // solve -- not a shared-memory store / load round trip), and the forward solve of g~ rides along with the
+            // factorisation (two independent chains).
             if (lane == 0) {
-                // pivots q_i of T + lam I; piv[i] = 1 / q_i, lf[i] = od[i - 1] / q_{i-1} (the L factor)
                 double q = dg[0] + lam;
                 if (fabs(q) < 1e-300) q = 1e-300;
-                double rq = tr_rcp(q);
+                double rq = tr_rcp(q);             // piv[i] = 1 / q_i, lf[i] = od[i - 1] / q_{i-1} (the L factor)
                 piv[0] = rq;
+                double y = -gt[0];
+                sv[0] = y;
                 for (int i = 1; i < n; ++i) {
-                    lf[i] = od[i - 1] * rq;
-                    q = fma(-od[i - 1], lf[i], dg[i] + lam);
+                    const double l = od[i - 1] * rq;
+                    lf[i] = l;
+                    q = fma(-od2[i - 1], rq, dg[i] + lam);
                     if (fabs(q) < 1e-300) q = 1e-300;
                     rq = tr_rcp(q);
                     piv[i] = rq;
+                    y = fma(-l, y, -gt[i]);        // forward: y_i = b_i - l_i y_{i-1}
+                    sv[i] = y;
                 }
-                // forward: y_i = b_i - l_i y_{i-1};  back: x_i = (y_i - od_i x_{i+1}) / q_i
-                sv[0] = -gt[0];
-                for (int i = 1; i < n; ++i) sv[i] = fma(-lf[i], sv[i - 1], -gt[i]);
-                sv[n - 1] *= piv[n - 1];
-                for (int i = n - 2; i >= 0; --i) sv[i] = fma(-od[i], sv[i + 1], sv[i]) * piv[i];
+                double x = y * rq;                 // back: x_i = (y_i - od_i x_{i+1}) / q_i
+                sv[n - 1] = x;
+                for (int i = n - 2; i >= 0; --i) {
+                    x = fma(-od[i], x, sv[i]) * piv[i];
+                    sv[i] = x;
+                }
                 if (need_w) {
-                    wv[0] = sv[0];
-                    for (int i = 1; i < n; ++i) wv[i] = fma(-lf[i], wv[i - 1], sv[i]);
-                    wv[n - 1] *= piv[n - 1];
-                    for (int i = n - 2; i >= 0; --i) wv[i] = fma(-od[i], wv[i + 1], wv[i]) * piv[i];
+                    double u = sv[0];
+                    wv[0] = u;
+                    for (int i = 1; i < n; ++i) {
+                        u = fma(-lf[i], u, sv[i]);
+                        wv[i] = u;
+                    }
                 }
             }
             __syncwarp();
             double a = 0.0, b = 0.0;
             for (int i = lane; i < n; i += 32) {
                 a = fma(sv[i], sv[i], a);
-                if (need_w) b = fma(sv[i], wv[i], b);
+                if (need_w) b = fma(wv[i] * wv[i], piv[i], b);
             }
             p2 = wsum(a);
             sw = wsum(b);
             __syncwarp();
         };
         double p2 = 0.0, sw = 0.0;
-        const bool pos_def = lam_min >= 1e-8;
         bool interior = false;
         if (pos_def) {
             solve_pair(0.0, false, p2, sw);
@@ -479,7 +505,7 @@ __device__ inline void tr_solve_block(TrShared& S, int n, double delta, double* 
         double lam = lam_lb + tiny;
         if (!interior) {
             solve_pair(lam, true, p2, sw);
-            if (lam_min <= 1e-8 && p2 <= d2) {
+            if (!pos_def && p2 <= d2) {
                 hard = true;
                 if (lane == 0) {
                     const double shift = -lam_min + 4.0 * tiny * 1e-3;
