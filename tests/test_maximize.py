@@ -215,6 +215,37 @@ def _verify_sample_galaxy(vs, pos):
         assert abs(vs[ids.color_mean[b, 1]] - true_colors[b]) < 0.2
 
 
+@pytest.mark.parametrize("n", [2, 3, 7, 20, 41])
+def test_tr_subproblem_kernel_sizes_and_special_matrices(n):
+    """The tridiagonal solver at other sizes and on the matrices that take its shortcuts: positive definite with the
+    Newton step inside the region (no multisection, one solve) and outside it (secular iteration from lam = 0),
+    diagonal H (every Householder reflector is the identity), indefinite, and a singular H."""
+    import emul_lib
+    rng = np.random.default_rng(60 + n)
+    B = 8
+    A = rng.normal(size=(B, n, n))
+    H = A + A.transpose(0, 2, 1)
+    H[0] = A[0] @ A[0].T + np.eye(n)                       # positive definite, interior (delta large)
+    H[1] = A[1] @ A[1].T + np.eye(n)                       # positive definite, boundary (delta small)
+    H[2] = np.diag(rng.uniform(0.5, 3.0, n))               # diagonal, positive definite
+    H[3] = np.diag(np.linspace(-2.0, 3.0, n))              # diagonal, indefinite
+    v = rng.normal(size=n)
+    H[4] = np.outer(v, v)                                  # singular (rank 1), positive semi-definite
+    g = rng.normal(size=(B, n))
+    delta = rng.uniform(0.5, 3.0, B)
+    delta[0], delta[1] = 1e3, 1e-2
+    s, m, interior = emul_lib.tr_subproblem(g, H, delta)
+    rs, rm, rint = em.solve_tr_subproblem(torch.tensor(g), torch.tensor(H), torch.tensor(delta))
+    assert np.array_equal(interior, rint.numpy())
+    assert interior[0] == 1 and interior[1] == 0
+    assert np.allclose(m, rm.numpy(), rtol=1e-8, atol=1e-12)
+    for b in range(B):
+        assert np.linalg.norm(s[b]) <= delta[b] * (1 + 1e-9)
+        assert np.allclose(s[b], rs[b].numpy(), rtol=1e-6, atol=1e-8 * max(np.abs(rs[b].numpy()).max(), 1e-30)), b
+        model = g[b] @ s[b] + 0.5 * s[b] @ H[b] @ s[b]
+        assert model == pytest.approx(m[b], rel=1e-9, abs=1e-11)
+
+
 def test_galaxy_optimization_recovers_truth():
     """test/test_optimization.jl:53-58 (test_galaxy_optimization: include_kl = false, loc_width = 3)."""
     images, patches, vp, _ = synthetic.gen_sample_galaxy_dataset()
