@@ -275,8 +275,8 @@ struct celeste_plan {
     DevBuf<double> bg;
     int n_marchblocks = 0;
     bool use_march = false;
-    // unit_kernel (Hessian mode of the production shape; value / gradient with CELESTE_GRAD_KERNEL=unit): one warp per
-    // (sub, image) unit pulled from a device-side queue
+    // unit kernels (every mode of the production shape; CELESTE_GRAD_KERNEL=march|task and CELESTE_HESS_KERNEL=pixel
+    // select the round-1 kernels for A/B runs): one warp per unit -- rows of a (sub, image) -- pulled from a device-side queue
     DevBuf<UnitHdr> unitmap, unitmap_bg;   // every unit, heaviest first; the units with a neighbour, by shared pixels
     DevBuf<int> unit_chunk_ptr;      // the partial vectors (= units) of each (sub, image)
     DevBuf<int> unit_queue;          // one counter per kernel of the sequence

@@ -1,6 +1,7 @@
-// unit_kernels.cuh -- the ELBO hot loop (add_pixel_term!, elbo_objective.jl:330-392) with ONE WARP per
-// (active source, image) "unit", pulled from a device-side queue (heaviest first): the Hessian mode of the
-// production shape (Sa = 1, K = 2; ElboMaximize.jl:150-152 always asks for the Hessian).
+// unit_kernels.cuh -- the ELBO hot loop (add_pixel_term!, elbo_objective.jl:330-392) with ONE WARP per "unit" (rows
+// [h2_lo, h2_hi) of one (active source, image)), pulled from a device-side queue (heaviest first): every mode of the
+// production shape (Sa = 1, K = 2).  The Hessian mode (ElboMaximize.jl:150-152 always asks for the Hessian) is the
+// one the formulation below is about; modes 0 / 1 are its phase A alone.
 //
 // The reference -- and pixel_kernel<2> -- push every one of the 28 Gaussian components of every pixel through the
 // second-order chain rule (27 sums, ~96 FP64 per component-pixel).  Here the second-order work is split by what is
@@ -11,7 +12,7 @@
 //
 //  phase A  walks the rows of the patch exactly like march_kernel (a lane PAIR per walk, exp recurrence along the
 //           row, 17 FP64 per component-pixel for f1 and its 6 first derivatives), finishes the pixel term with its
-//           full second-order part EXCEPT L5 d2f1, and stores L5 = dL/df1 of every pixel in a per-warp scratch plane.
+//           full second-order part EXCEPT L5 d2f1, and stores L5 = dL/df1 of every pixel in the unit's plane of plan.l5.
 //  phase B  re-walks the patch with one LANE PER COMPONENT: f_c(pix) by the same recurrence (2 multiplications),
 //           v = L5(pix) f_c(pix), and the five row moments sum v d2^b; at the end of a row they are folded into the
 //           15 moments D[a][b] = sum L5 f_c d1^a d2^b (a + b <= 4, d = x - mu_c).  ~12 FP64 per component-pixel.
